@@ -1,0 +1,144 @@
+/* movenet_b200 -- C ABI of the B200-native WaveNet hot path.
+ *
+ * This is the drop-in boundary.  The reference (cosmicBboy/movenet) is pure
+ * Python and has no FFI of its own: its "plugin interface" for this path is the
+ * nn.Module surface of movenet/wavenet.py:50-239 and movenet/modules.py:15-142.
+ * Each entry point below names the reference lines whose arithmetic it
+ * replaces.  Plain pointers and sizes only: no torch types, no exceptions, no
+ * allocation (every buffer is caller-owned device memory; sizes come from
+ * mvn_*_bytes).  Every launcher takes the CUDA stream explicitly, returns 0 on
+ * success and a non-zero code on failure, with a message in mvn_last_error().
+ * There is no CPU fallback anywhere behind this interface.
+ *
+ * Layouts
+ *   audio / probabilities / logits : (B, A, T) fp32, channels-first, exactly the
+ *       reference's AudioTensor (movenet/types.py:4) -- API tensors.
+ *   video                          : (B, 160, 64, 64, Cin) fp32 (movenet/types.py:5)
+ *   internal activations           : time-major (B, T, C), fp32 or bf16 (act_dtype)
+ *   parameters                     : the reference's own state_dict tensors, fp32,
+ *       passed as a DEVICE array of device pointers in state_dict order
+ *       (MVN_PARAM_* indices below); gradients likewise.
+ */
+#ifndef MOVENET_B200_H
+#define MOVENET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVN_DTYPE_F32 0
+#define MVN_DTYPE_BF16 1
+
+#define MVN_MAX_AUDIO_FRAMES 160000 /* movenet/wavenet.py:27 */
+#define MVN_MAX_VIDEO_FRAMES 160    /* movenet/wavenet.py:28 */
+#define MVN_VIDEO_HW 64             /* movenet/wavenet.py:29 */
+#define MVN_UPSAMPLE_STRIDE 10      /* movenet/wavenet.py:31 */
+
+/* WaveNet.__init__ arguments (movenet/wavenet.py:75-83) + the batch geometry
+ * and the forward() flags (movenet/wavenet.py:158-165). */
+typedef struct mvn_shape {
+    int layer_size, stack_size;
+    int input_channels;     /* A */
+    int residual_channels;  /* C */
+    int skip_channels;      /* S */
+    int context_in_channels;
+    int batch;              /* B */
+    int frames;             /* T */
+    int has_video;          /* 1: video-conditioned (frames must be 160000) */
+    int act_dtype;          /* MVN_DTYPE_F32 (exact mode) | MVN_DTYPE_BF16 (tensor-core mode) */
+    int remove_last;        /* forward(remove_last=...) */
+    int output_logits;      /* 1: raw logits (output_unnormalized=False, sic), 0: softmax probabilities */
+} mvn_shape_t;
+
+/* index of each reference parameter in the pointer tables (state_dict order) */
+#define MVN_PARAM_VIDEO_CONV_W 0
+#define MVN_PARAM_VIDEO_CONV_B 1
+#define MVN_PARAM_VT_W(i) (2 + 2 * (i))
+#define MVN_PARAM_VT_B(i) (3 + 2 * (i))
+#define MVN_PARAM_CAUSAL_W 8
+#define MVN_PARAM_LAYER(l, j) (9 + 10 * (l) + (j))
+/* j: 0 conv_filter.conv.weight 1 conv_gate.conv.weight 2 context_conv_filter.weight 3 .bias
+ *    4 context_conv_gate.weight 5 .bias 6 conv_residual.weight 7 .bias 8 conv_skip.weight 9 .bias */
+#define MVN_PARAM_DENSE(n_layers, j) (9 + 10 * (n_layers) + (j)) /* conv1.w conv1.b conv2.w conv2.b */
+#define MVN_PARAM_COUNT(n_layers) (13 + 10 * (n_layers))
+
+const char* mvn_last_error(void);
+int mvn_version(void);
+
+/* geometry helpers: WaveNet.receptive_fields (movenet/wavenet.py:125-134) and
+ * compute_output_size (movenet/wavenet.py:136-147; returns <1 when the
+ * reference raises ValueError). */
+int mvn_receptive_fields(int layer_size, int stack_size);
+int mvn_output_size(int layer_size, int stack_size, int frames);
+
+/* buffer sizes (bytes) for one (shape) */
+size_t mvn_packed_bytes(const mvn_shape_t* s);   /* packed weights; packed grads use the same size */
+size_t mvn_acts_bytes(const mvn_shape_t* s);     /* activations kept from forward to backward */
+size_t mvn_scratch_bytes(const mvn_shape_t* s);  /* reusable workspace for forward / backward */
+
+/* mu-law companding: torchaudio.functional.mu_law_encoding / mu_law_decoding
+ * (call sites movenet/dataset.py:284, movenet/callbacks.py:66-76).  Encoding is
+ * a search over A-1 decision thresholds held in the input dtype (built on the
+ * host, see movenet_b200/mulaw.py), which is what makes the integer codes
+ * bit-identical to the CPU function; inputs outside [-1, 1] and NaN take the
+ * direct formula.  dtype: 0 fp32, 2 fp64 input. */
+int mvn_mulaw_encode(const void* x, int x_is_f64, const void* thresholds, int n_channels, int64_t* codes,
+                     int64_t n, void* stream);
+int mvn_mulaw_decode(const int64_t* codes, const float* lut, int n_channels, float* x, int64_t n, void* stream);
+/* codes (B,T) int64 -> one-hot (B,A,T) fp32 (movenet/dataset.py:285-288) */
+int mvn_one_hot(const int64_t* codes, float* audio, int B, int A, int T, void* stream);
+
+/* re-layout the reference parameters for the kernels (once per optimizer step) */
+int mvn_pack_weights(const mvn_shape_t* s, const void* const* param_ptrs_dev, void* packed, void* stream);
+/* packed gradients -> reference-layout gradient tensors, all living in ONE flat fp32 buffer (so the
+ * data-parallel all-reduce is a single message): offsets_dev[i] is the element offset of parameter i
+ * (state_dict order) inside flat_grads, or -1 for a parameter that gets no gradient. */
+int mvn_unpack_grads(const mvn_shape_t* s, const void* packed_grads, float* flat_grads,
+                     const int64_t* offsets_dev, void* stream);
+
+/* WaveNet.forward (movenet/wavenet.py:158-191): causal conv (modules.py:15-30),
+ * video encoder + upsampler (wavenet.py:149-156), the gated residual stack
+ * (modules.py:67-130), the skip sum (wavenet.py:181), the dense head
+ * (modules.py:133-142) and the softmax (wavenet.py:191).
+ * out: (B, A, T-RF+1-remove_last) fp32. */
+int mvn_wavenet_forward(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,
+                        void* acts, float* out, void* scratch, void* stream);
+
+/* autograd of the above for d(loss)/d(out) = dout; fills packed_grads (same
+ * layout as the packed weights), to be followed by mvn_unpack_grads. */
+int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,
+                         const void* acts, const float* out, const float* dout, void* packed_grads,
+                         void* scratch, void* stream);
+
+/* stage-level entry points (the same kernels the two calls above launch) */
+int mvn_onehot_to_codes(const float* audio, int B, int A, int T, int* codes, unsigned char* dense, void* stream);
+int mvn_input_fwd(const mvn_shape_t* s, const void* packed, const float* audio, void* acts, void* stream);
+int mvn_video_fwd(const mvn_shape_t* s, const void* packed, const float* video, void* acts, void* stream);
+int mvn_layer_fwd(const mvn_shape_t* s, const void* packed, int layer, void* acts, void* scratch, void* stream);
+int mvn_head_fwd(const mvn_shape_t* s, const void* packed, void* acts, float* out, void* scratch, void* stream);
+/* read back an internal activation as fp32 (tests): which = 0 layer input x_l (B,T,C), 1 skip sum (B,Tout,S),
+ * 2 upsampled context (B,T,C) */
+int mvn_debug_read(const mvn_shape_t* s, const void* acts, int which, int layer, float* dst, void* stream);
+
+/* cached autoregressive decoding: WaveNet.generate (movenet/wavenet.py:193-239)
+ * with per-layer dilation queues instead of a window recompute per sample.
+ * state: mvn_decode_state_bytes; prefill fills the queues from the activations
+ * of a mvn_wavenet_forward over the prompt (shape.frames = prompt length);
+ * steps generates n_new samples starting at absolute position t_start
+ * and writes int32 codes (B, n_new) and optionally the logits (B, n_new, A).
+ * temperature == 0: argmax, ties to the lowest index like torch.argmax;
+ * temperature > 0: a draw from softmax(softmax(z)/temperature) (movenet/wavenet.py:227-231)
+ * from a counter-based generator keyed by (seed, clip, position). */
+size_t mvn_decode_state_bytes(const mvn_shape_t* s);
+int mvn_decode_prefill(const mvn_shape_t* s, const void* acts, void* state, void* stream);
+int mvn_decode_steps(const mvn_shape_t* s, const void* packed, void* state, const void* ctx, int t_start,
+                     int n_new, int* out_codes, float* out_logits, float temperature, unsigned seed,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

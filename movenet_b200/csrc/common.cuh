@@ -1,0 +1,46 @@
+// Shared helpers for the movenet_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define MVN_F32 0
+#define MVN_BF16 1
+
+#define MVN_LRELU_SLOPE 0.01f   // F.leaky_relu default (movenet/modules.py:140-141)
+
+// error plumbing: every extern "C" entry returns 0 or a non-zero code and
+// leaves a message for mvn_last_error(); nothing throws across the C boundary.
+void mvn_set_error(const char* fmt, ...);
+int mvn_check_launch(const char* what);
+
+#define MVN_REQUIRE(cond, ...)                      \
+    do {                                            \
+        if (!(cond)) {                              \
+            mvn_set_error(__VA_ARGS__);             \
+            return -1;                              \
+        }                                           \
+    } while (0)
+
+#define MVN_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) {                                              \
+            mvn_set_error("%s failed: %s", #call, cudaGetErrorString(e__));    \
+            return (int)e__;                                                   \
+        }                                                                      \
+    } while (0)
+
+__device__ __forceinline__ float mvn_ld(const void* p, int dtype, long long i) {
+    return dtype == MVN_BF16 ? __bfloat162float(((const __nv_bfloat16*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void mvn_st(void* p, int dtype, long long i, float v) {
+    if (dtype == MVN_BF16) ((__nv_bfloat16*)p)[i] = __float2bfloat16(v);
+    else ((float*)p)[i] = v;
+}
+__device__ __forceinline__ float mvn_lrelu(float v) { return v > 0.f ? v : MVN_LRELU_SLOPE * v; }
+__device__ __forceinline__ float mvn_lrelu_grad(float pre) { return pre > 0.f ? 1.f : MVN_LRELU_SLOPE; }
+__device__ __forceinline__ float mvn_sigmoid(float v) { return 1.f / (1.f + expf(-v)); }
+
+static inline int mvn_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

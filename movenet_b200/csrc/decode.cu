@@ -1,0 +1,302 @@
+// Cached autoregressive decoding: WaveNet.generate (movenet/wavenet.py:193-239) without the
+// per-sample window recompute.  Every layer keeps a ring of its last d inputs ("dilation queue"),
+// so one new sample costs one pass over the N layers instead of RF of them.
+//
+// fp32 (exact) path: one CTA owns CB clips for the whole run and loops over the samples; the
+// layer weights are staged in shared memory when they fit (they do for the receptive-field
+// config, experiments/04), the queues live in HBM laid out (layer, slot, clip, channel) so a CTA's
+// pops and pushes are contiguous across its clips.
+#include "common.cuh"
+#include "layout.h"
+
+struct DecodeArgs {
+    const float* packed; PackedLayout P;
+    int N, A, C, S, Kz, video, B, Tctx, ctx_dtype;
+    int t_start, n_new, smem_weights;
+    float temperature; unsigned seed;
+    float* queues; int* last2;           // [B][2] : code[t-2], code[t-1]
+    const void* ctx;
+    int* out_codes; float* out_logits;
+    long long qoff[MVN_MAX_LAYERS];      // element offset of layer l's ring (per clip), before the *B factor
+    int dil[MVN_MAX_LAYERS];
+};
+
+// out[cb][n] = bias[n] + sum_k W[k][n] * in[cb][k]   for every (cb, n) pair, spread over the CTA
+template <int CB>
+__device__ __forceinline__ void matvec(const float* __restrict__ W, int ldw, int K, int Nout, const float* in, int ldin,
+                                       const float* bias, float* out, int ldout, bool lrelu_in, bool accumulate) {
+    for (int idx = threadIdx.x; idx < CB * Nout; idx += blockDim.x) {
+        const int cb = idx / Nout, n = idx - cb * Nout;
+        float acc = bias ? bias[n] : 0.f;
+        const float* x = in + cb * ldin;
+        const float* w = W + n;
+#pragma unroll 8
+        for (int k = 0; k < K; ++k) {
+            float xv = x[k];
+            if (lrelu_in) xv = mvn_lrelu(xv);
+            acc = fmaf(w[(size_t)k * ldw], xv, acc);
+        }
+        if (accumulate) out[cb * ldout + n] += acc; else out[cb * ldout + n] = acc;
+    }
+}
+
+template <int CB>
+__global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int C = a.C, S = a.S, A = a.A, N = a.N, Kz = a.Kz;
+    const int clip0 = blockIdx.x * CB;
+    // carve shared memory
+    float* h = sm;                       // [CB][C]   current layer input x_l[t]
+    float* olds = h + CB * C;            // [N][CB][C] queue pops for this step
+    float* zin = olds + (size_t)N * CB * C;   // [CB][Kz] : old | h | ctx
+    float* zb = zin + CB * Kz;           // [CB][2C]
+    float* gated = zb + CB * 2 * C;      // [CB][C]
+    float* rs = gated + CB * C;          // [CB][C+S]
+    float* skip = rs + CB * (C + S);     // [CB][S]
+    float* a1 = skip + CB * S;           // [CB][A]
+    float* zl = a1 + CB * A;             // [CB][A]
+    float* wsm = zl + CB * A;            // staged weights (optional)
+    __shared__ int code_prev[CB], code_cur[CB];
+
+    const size_t lsz = (size_t)Kz * 2 * C + 2 * C + (size_t)C * (C + S) + (C + S);   // staged floats per layer
+    if (a.smem_weights) {
+        for (int l = 0; l < N; ++l) {
+            const float* lw = a.packed + a.P.layer0 + (size_t)l * a.P.layer_stride;
+            float* dst = wsm + l * lsz;
+            for (int i = threadIdx.x; i < Kz * 2 * C; i += blockDim.x) dst[i] = lw[a.P.oWz + i];
+            dst += Kz * 2 * C;
+            for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) dst[i] = lw[a.P.obz + i];
+            dst += 2 * C;
+            for (int i = threadIdx.x; i < C * (C + S); i += blockDim.x) dst[i] = lw[a.P.oWrs + i];
+            dst += C * (C + S);
+            for (int i = threadIdx.x; i < C + S; i += blockDim.x) dst[i] = lw[a.P.obrs + i];
+        }
+        float* hd = wsm + N * lsz;
+        for (int i = threadIdx.x; i < S * A; i += blockDim.x) hd[i] = a.packed[a.P.w1p + i];
+        hd += S * A;
+        for (int i = threadIdx.x; i < A; i += blockDim.x) hd[i] = a.packed[a.P.b1 + i];
+        hd += A;
+        for (int i = threadIdx.x; i < A * A; i += blockDim.x) hd[i] = a.packed[a.P.w2p + i];
+        hd += A * A;
+        for (int i = threadIdx.x; i < A; i += blockDim.x) hd[i] = a.packed[a.P.b2 + i];
+    }
+    if (threadIdx.x < CB) {
+        const int b = clip0 + threadIdx.x;
+        code_prev[threadIdx.x] = b < a.B ? a.last2[2 * b] : -1;
+        code_cur[threadIdx.x] = b < a.B ? a.last2[2 * b + 1] : -1;
+    }
+    __syncthreads();
+
+    const float* win = a.packed + a.P.win;
+    for (int i = a.t_start; i < a.t_start + a.n_new; ++i) {
+        const int tau = i - 1;           // the model consumes x[..tau] and predicts sample i
+        // causal conv (movenet/modules.py:15-30) for one-hot inputs: two weight rows
+        for (int idx = threadIdx.x; idx < CB * C; idx += blockDim.x) {
+            const int cb = idx / C, c = idx - cb * C;
+            const int c0 = code_prev[cb], c1 = code_cur[cb];
+            float v = 0.f;
+            if (c0 >= 0) v += win[(size_t)c0 * C + c];
+            if (c1 >= 0) v += win[((size_t)A + c1) * C + c];
+            h[idx] = v;
+        }
+        for (int idx = threadIdx.x; idx < CB * S; idx += blockDim.x) skip[idx] = 0.f;
+        // all queue pops of this step: their addresses depend on tau only
+        for (int idx = threadIdx.x; idx < N * CB * C; idx += blockDim.x) {
+            const int l = idx / (CB * C), r = idx - l * CB * C, cb = r / C, c = r - cb * C;
+            const int d = a.dil[l], b = clip0 + cb;
+            float v = 0.f;
+            if (b < a.B && tau - d >= 0) v = a.queues[a.qoff[l] * a.B + ((size_t)(tau % d) * a.B + b) * C + c];
+            olds[idx] = v;
+        }
+        __syncthreads();
+        for (int l = 0; l < N; ++l) {
+            const float* lw = a.packed + a.P.layer0 + (size_t)l * a.P.layer_stride;
+            const float *Wz, *bz, *Wrs, *brs;
+            if (a.smem_weights) {
+                Wz = wsm + l * lsz; bz = Wz + Kz * 2 * C; Wrs = bz + 2 * C; brs = Wrs + C * (C + S);
+            } else { Wz = lw + a.P.oWz; bz = lw + a.P.obz; Wrs = lw + a.P.oWrs; brs = lw + a.P.obrs; }
+            const int d = a.dil[l];
+            // gather [x_l[tau-d] | x_l[tau] | ctx[tau]] and push x_l[tau] into the ring
+            for (int idx = threadIdx.x; idx < CB * C; idx += blockDim.x) {
+                const int cb = idx / C, c = idx - cb * C, b = clip0 + cb;
+                const float hv = h[idx];
+                zin[cb * Kz + c] = olds[(l * CB + cb) * C + c];
+                zin[cb * Kz + C + c] = hv;
+                if (a.video) zin[cb * Kz + 2 * C + c] = (b < a.B && tau >= 0 && tau < a.Tctx)
+                    ? mvn_ld(a.ctx, a.ctx_dtype, ((size_t)b * a.Tctx + tau) * C + c) : 0.f;
+                if (b < a.B && tau >= 0) a.queues[a.qoff[l] * a.B + ((size_t)(tau % d) * a.B + b) * C + c] = hv;
+            }
+            __syncthreads();
+            matvec<CB>(Wz, 2 * C, Kz, 2 * C, zin, Kz, bz, zb, 2 * C, false, false);
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < CB * C; idx += blockDim.x) {
+                const int cb = idx / C, c = idx - cb * C;
+                gated[idx] = tanhf(zb[cb * 2 * C + 2 * c]) * mvn_sigmoid(zb[cb * 2 * C + 2 * c + 1]);
+            }
+            __syncthreads();
+            matvec<CB>(Wrs, C + S, C, C + S, gated, C, brs, rs, C + S, false, false);
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < CB * (C + S); idx += blockDim.x) {
+                const int cb = idx / (C + S), n = idx - cb * (C + S);
+                if (n < C) h[cb * C + n] += rs[idx]; else skip[cb * S + n - C] += rs[idx];
+            }
+            __syncthreads();
+        }
+        // dense head (movenet/modules.py:133-142)
+        const float *W1, *b1, *W2, *b2;
+        if (a.smem_weights) { W1 = wsm + N * lsz; b1 = W1 + S * A; W2 = b1 + A; b2 = W2 + A * A; }
+        else { W1 = a.packed + a.P.w1p; b1 = a.packed + a.P.b1; W2 = a.packed + a.P.w2p; b2 = a.packed + a.P.b2; }
+        matvec<CB>(W1, A, S, A, skip, S, b1, a1, A, true, false);
+        __syncthreads();
+        matvec<CB>(W2, A, A, A, a1, A, b2, zl, A, true, false);
+        __syncthreads();
+        // next sample: argmax over channels, ties to the lowest index (torch.argmax); or, for
+        // temperature > 0, a draw from softmax(softmax(z) / temperature) (movenet/wavenet.py:227-233)
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int cb = warp; cb < CB; cb += (blockDim.x >> 5)) {
+            const int b = clip0 + cb;
+            float* zr = zl + cb * A;
+            float best = -INFINITY; int arg = 0x7fffffff;
+            for (int n = lane; n < A; n += 32) {
+                const float v = zr[n];
+                if (v > best) { best = v; arg = n; }
+                if (a.out_logits && b < a.B) a.out_logits[((size_t)b * a.n_new + (i - a.t_start)) * A + n] = v;
+            }
+            for (int o = 16; o; o >>= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+                if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+            }
+            if (a.temperature > 0.f) {
+                float sum = 0.f;                                   // p = softmax(z)
+                for (int n = lane; n < A; n += 32) sum += expf(zr[n] - best);
+                for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const float pmax = 1.f / sum / a.temperature;      // largest p / temperature
+                float qsum = 0.f;                                  // q ~ exp(p / temperature - max)
+                __syncwarp();
+                for (int n = lane; n < A; n += 32) {
+                    const float q = expf(expf(zr[n] - best) / sum / a.temperature - pmax);
+                    a1[cb * A + n] = q; qsum += q;
+                }
+                for (int o = 16; o; o >>= 1) qsum += __shfl_xor_sync(0xffffffffu, qsum, o);
+                __syncwarp();
+                // counter-based uniform in [0,1): one draw per (seed, clip, position)
+                unsigned long long x = ((unsigned long long)a.seed << 32) ^ ((unsigned long long)(unsigned)b * 0x9E3779B97F4A7C15ULL) ^ (unsigned long long)(unsigned)i;
+                x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 27; x *= 0x94D049BB133111EBULL; x ^= x >> 31;
+                const float target = (float)(x >> 40) * (1.f / 16777216.f) * qsum;
+                const int chunk = (A + 31) / 32, lo = lane * chunk, hi = min(lo + chunk, A);
+                float local = 0.f;
+                for (int n = lo; n < hi; ++n) local += a1[cb * A + n];
+                float incl = local;
+                for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                const float excl = incl - local;
+                int pick = -1;
+                if (target >= excl && target < incl) {
+                    float run = excl; pick = hi - 1;
+                    for (int n = lo; n < hi; ++n) { run += a1[cb * A + n]; if (target < run) { pick = n; break; } }
+                }
+                int chosen = A - 1;                                // rounding fell off the end: last channel
+                for (int src = 31; src >= 0; --src) { const int pk = __shfl_sync(0xffffffffu, pick, src); if (pk >= 0) chosen = pk; }
+                arg = chosen;
+            }
+            if (lane == 0) {
+                code_prev[cb] = code_cur[cb]; code_cur[cb] = arg;
+                if (b < a.B) a.out_codes[(size_t)b * a.n_new + (i - a.t_start)] = arg;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < CB) {
+        const int b = clip0 + threadIdx.x;
+        if (b < a.B) { a.last2[2 * b] = code_prev[threadIdx.x]; a.last2[2 * b + 1] = code_cur[threadIdx.x]; }
+    }
+}
+
+// fill the rings from the layer inputs of a forward pass over the prompt: ring_l[tau % d] = x_l[tau]
+__global__ void decode_prefill_kernel(const void* __restrict__ x, int adt, int B, int T, int C, int d,
+                                      float* __restrict__ ring) {
+    const long long n = (long long)B * d * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C); const long long r = i / C; const int b = (int)(r % B); const int slot = (int)(r / B);
+        // the time in [T-d, T) whose slot this is
+        int tau = (T / d) * d + slot; if (tau >= T) tau -= d;
+        ring[i] = (tau >= 0 && tau >= T - d) ? mvn_ld(x, adt, ((size_t)b * T + tau) * C + c) : 0.f;
+    }
+}
+
+__global__ void decode_last2_kernel(const int* __restrict__ codes, int B, int T, int* __restrict__ last2) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    last2[2 * b] = T >= 2 ? codes[(size_t)b * T + T - 2] : -1;
+    last2[2 * b + 1] = T >= 1 ? codes[(size_t)b * T + T - 1] : -1;
+}
+
+static size_t queue_floats(const Geo& g, long long* qoff) {
+    long long o = 0;
+    for (int l = 0; l < g.N; ++l) { if (qoff) qoff[l] = o; o += (long long)g.dil[l] * g.C; }
+    return (size_t)o;
+}
+
+extern "C" size_t mvn_decode_state_bytes(const mvn_shape_t* s) {
+    Geo g; if (geo_init(g, s)) return 0;
+    return al256(queue_floats(g, nullptr) * (size_t)g.B * 4) + al256((size_t)g.B * 2 * 4);
+}
+
+extern "C" int mvn_decode_prefill(const mvn_shape_t* s, const void* acts, void* state, void* stream) {
+    Geo g; MVN_REQUIRE(s && geo_init(g, s) == 0, "mvn_decode_prefill: bad shape");
+    MVN_REQUIRE(acts && state, "mvn_decode_prefill: null buffer");
+    ActsLayout AL; acts_layout(g, AL);
+    long long qoff[MVN_MAX_LAYERS];
+    const size_t qf = queue_floats(g, qoff);
+    float* queues = (float*)state;
+    int* last2 = (int*)((char*)state + al256(qf * (size_t)g.B * 4));
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int l = 0; l < g.N; ++l) {
+        const void* x = (const char*)acts + AL.x0 + (size_t)l * AL.x_stride;
+        const long long n = (long long)g.B * g.dil[l] * g.C;
+        decode_prefill_kernel<<<mvn_cdiv(n, 256) < 1184 ? mvn_cdiv(n, 256) : 1184, 256, 0, st>>>(
+            x, g.adt, g.B, g.T, g.C, g.dil[l], queues + qoff[l] * g.B);
+    }
+    decode_last2_kernel<<<mvn_cdiv(g.B, 128), 128, 0, st>>>((const int*)((const char*)acts + AL.codes), g.B, g.T, last2);
+    return mvn_check_launch("decode_prefill");
+}
+
+template <int CB>
+static int launch_decode(DecodeArgs& a, const Geo& g, cudaStream_t st) {
+    const size_t act_floats = (size_t)CB * g.C + (size_t)g.N * CB * g.C + (size_t)CB * g.Kz + (size_t)CB * 2 * g.C +
+                              (size_t)CB * g.C + (size_t)CB * (g.C + g.S) + (size_t)CB * g.S + 2 * (size_t)CB * g.A;
+    const size_t lsz = (size_t)g.Kz * 2 * g.C + 2 * g.C + (size_t)g.C * (g.C + g.S) + (g.C + g.S);
+    const size_t w_floats = g.N * lsz + (size_t)g.S * g.A + g.A + (size_t)g.A * g.A + g.A;
+    const size_t cap = 220 * 1024;
+    MVN_REQUIRE(act_floats * 4 <= cap, "decode: model too large for the per-CTA activation staging");
+    a.smem_weights = (act_floats + w_floats) * 4 <= cap;
+    const size_t smem = (act_floats + (a.smem_weights ? w_floats : 0)) * 4;
+    MVN_CUDA(cudaFuncSetAttribute(decode_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap));
+    decode_kernel<CB><<<mvn_cdiv(g.B, CB), 256, smem, st>>>(a);
+    return mvn_check_launch("decode_steps");
+}
+
+extern "C" int mvn_decode_steps(const mvn_shape_t* s, const void* packed, void* state, const void* ctx, int t_start,
+                                int n_new, int* out_codes, float* out_logits, float temperature, unsigned seed,
+                                void* stream) {
+    Geo g; MVN_REQUIRE(s && geo_init(g, s) == 0, "mvn_decode_steps: bad shape");
+    MVN_REQUIRE(packed && state && out_codes && n_new >= 0 && t_start >= 1, "mvn_decode_steps: bad arguments");
+    MVN_REQUIRE(!g.video || ctx, "mvn_decode_steps: shape says video but ctx is null");
+    if (n_new == 0) return 0;
+    DecodeArgs args;
+    memset(&args, 0, sizeof(args));
+    args.packed = (const float*)packed; packed_layout(g, args.P);
+    args.N = g.N; args.A = g.A; args.C = g.C; args.S = g.S; args.Kz = g.Kz; args.video = g.video; args.B = g.B;
+    args.Tctx = g.T; args.ctx_dtype = g.adt; args.t_start = t_start; args.n_new = n_new;
+    args.temperature = temperature; args.seed = seed;
+    const size_t qf = queue_floats(g, args.qoff);
+    args.queues = (float*)state; args.last2 = (int*)((char*)state + al256(qf * (size_t)g.B * 4));
+    args.ctx = ctx; args.out_codes = out_codes; args.out_logits = out_logits;
+    for (int l = 0; l < g.N; ++l) args.dil[l] = g.dil[l];
+    cudaStream_t st = (cudaStream_t)stream;
+    // clips per CTA: keep every SM busy first, then amortise weight reads over more clips
+    if (g.B >= 148 * 8 && (size_t)g.N * 8 * g.C * 4 <= 64 * 1024) return launch_decode<8>(args, g, st);
+    if (g.B >= 148 * 4 && (size_t)g.N * 4 * g.C * 4 <= 64 * 1024) return launch_decode<4>(args, g, st);
+    if (g.B >= 148 * 2) return launch_decode<2>(args, g, st);
+    return launch_decode<1>(args, g, st);
+}

@@ -1,0 +1,11 @@
+// tcgen05 / TMEM / TMA (bf16, fp32 accumulate) fused layer kernels -- see layer_tc.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include "layout.h"
+
+// 1 when the tensor-core layer kernel covers this (C, S, video) combination
+int mvn_tc_layer_supported(int C, int S, int video);
+// GatedResidualConv1d.forward (movenet/modules.py:67-93) as one fused kernel.
+// x_out may be null for the last layer (its residual output is discarded).
+int mvn_tc_layer_fwd(const void* x_in, const void* ctx, void* x_out, float* skip_sum, const float* layer_weights,
+                     const PackedLayout& P, const Geo& g, int layer, cudaStream_t st);

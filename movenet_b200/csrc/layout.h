@@ -1,0 +1,151 @@
+// Host-side geometry: where everything lives inside the caller-owned buffers.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include "../../include/movenet_b200.h"
+
+#define MVN_MAX_LAYERS 256
+
+struct Geo {
+    int L, St, A, C, S, Cin, B, T, video, adt, remove_last, logits;
+    int N;        // layers
+    int RF;       // receptive_fields (movenet/wavenet.py:125-134)
+    int Tout;     // T - RF + 1      (movenet/wavenet.py:136-147)
+    int Tn;       // Tout - remove_last : columns the caller receives
+    int Kz;       // 2C (+C with video): contraction length of the gate GEMM
+    int es;       // bytes per activation element
+    int dil[MVN_MAX_LAYERS];
+};
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static inline int geo_init(Geo& g, const mvn_shape_t* s) {
+    g.L = s->layer_size; g.St = s->stack_size; g.A = s->input_channels; g.C = s->residual_channels;
+    g.S = s->skip_channels; g.Cin = s->context_in_channels; g.B = s->batch; g.T = s->frames;
+    g.video = s->has_video; g.adt = s->act_dtype; g.remove_last = s->remove_last; g.logits = s->output_logits;
+    g.N = g.L * g.St;
+    if (g.L < 1 || g.St < 1 || g.N > MVN_MAX_LAYERS || g.L > 24) return -1;
+    long long rf = g.St;
+    for (int st = 0; st < g.St; ++st)
+        for (int x = 0; x < g.L; ++x) { g.dil[st * g.L + x] = 1 << x; rf += (1LL << x); }
+    if (rf > 0x7fffffffLL) return -1;
+    g.RF = (int)rf;
+    g.Tout = g.T - g.RF + 1;
+    g.Tn = g.Tout - (g.remove_last ? 1 : 0);
+    g.Kz = g.video ? 3 * g.C : 2 * g.C;
+    g.es = g.adt == MVN_DTYPE_BF16 ? 2 : 4;
+    return 0;
+}
+
+// ---- packed weights (fp32 elements) -------------------------------------------------------------
+struct PackedLayout {
+    size_t win;                 // [2][A][C]      Win[tap][a][c] = causal_conv.conv.weight[c][a][tap]
+    size_t layer0, layer_stride;
+    // inside one layer
+    size_t oWz;                 // [Kz][2C]   rows: tap0 C | tap1 C | ctx C ; cols interleaved (filter c, gate c)
+    size_t obz;                 // [2C]       context conv biases (0 without video)
+    size_t oWrs;                // [C][C+S]   cols: residual C | skip S
+    size_t obrs;                // [C+S]
+    size_t oWzT;                // [2C][Kz]   transpose of Wz (backward data)
+    size_t oWrsT;               // [C+S][C]   transpose of Wrs
+    size_t w1p, b1, w2p, b2;    // head: [S][A], [A], [A][A], [A]
+    size_t w1pT, w2pT;          // [A][S], [A][A]
+    size_t wv, bv;              // video conv: [4096*Cin][C], [C]
+    size_t wt[3], bt[3], wtT[3];// transposed convs: [C][10C], [10C] (bias tiled), [10C][C]
+    size_t total;               // elements
+};
+
+static inline void packed_layout(const Geo& g, PackedLayout& p) {
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 63) & ~(size_t)63; return r; };
+    const size_t A = g.A, C = g.C, S = g.S, Kz = g.Kz;
+    p.win = take(2 * A * C);
+    size_t l0 = o;
+    p.oWz = take(Kz * 2 * C) - l0;
+    p.obz = take(2 * C) - l0;
+    p.oWrs = take(C * (C + S)) - l0;
+    p.obrs = take(C + S) - l0;
+    p.oWzT = take(2 * C * Kz) - l0;
+    p.oWrsT = take((C + S) * C) - l0;
+    p.layer0 = l0;
+    p.layer_stride = o - l0;
+    o = l0 + p.layer_stride * g.N;
+    p.w1p = take(S * A); p.b1 = take(A); p.w2p = take(A * A); p.b2 = take(A);
+    p.w1pT = take(A * S); p.w2pT = take(A * A);
+    if (g.video) {
+        p.wv = take((size_t)4096 * g.Cin * C); p.bv = take(C);
+        for (int i = 0; i < 3; ++i) { p.wt[i] = take(C * 10 * C); p.bt[i] = take(10 * C); p.wtT[i] = take(10 * C * C); }
+    } else {
+        p.wv = p.bv = 0;
+        for (int i = 0; i < 3; ++i) p.wt[i] = p.bt[i] = p.wtT[i] = 0;
+    }
+    p.total = o;
+}
+
+// ---- activations kept from forward to backward (byte offsets) -----------------------------------
+struct ActsLayout {
+    size_t codes;     // int32 [B*T]   argmax over channels of every audio column
+    size_t dense;     // uint8 [B*T]   1 where the column is not an exact one-hot
+    size_t x0;        // layer inputs x_0..x_{N-1}, each (B,T,C) act dtype ; x_0 = causal conv output
+    size_t x_stride;
+    size_t ctx;       // (B,T,C) act dtype (video only)
+    size_t skip;      // (B,Tout,S) fp32
+    size_t a1;        // (B,Tn,A) fp32 : dense_conv.conv1 output (pre-activation)
+    size_t enc, u1, u2; // video: (B,160,C) (B,1600,C) (B,16000,C) fp32
+    size_t total;
+};
+
+static inline void acts_layout(const Geo& g, ActsLayout& a) {
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += al256(n); return r; };
+    const size_t BT = (size_t)g.B * g.T;
+    a.codes = take(BT * 4);
+    a.dense = take(BT);
+    a.x_stride = al256(BT * g.C * g.es);
+    a.x0 = take(a.x_stride * g.N);
+    a.ctx = g.video ? take(BT * g.C * g.es) : 0;
+    a.skip = take((size_t)g.B * (g.Tout > 0 ? g.Tout : 0) * g.S * 4);
+    a.a1 = take((size_t)g.B * (g.Tout > 0 ? g.Tout : 0) * g.A * 4);
+    if (g.video) {
+        a.enc = take((size_t)g.B * 160 * g.C * 4);
+        a.u1 = take((size_t)g.B * 1600 * g.C * 4);
+        a.u2 = take((size_t)g.B * 16000 * g.C * 4);
+    } else a.enc = a.u1 = a.u2 = 0;
+    a.total = o;
+}
+
+// ---- reusable workspace (byte offsets) ----------------------------------------------------------
+struct ScratchLayout {
+    size_t gated;     // (B,T,C) act dtype
+    size_t z;         // (B,Tn,A) fp32 : head logits, time-major ; backward: d(logits)
+    size_t da1;       // (B,Tn,A) fp32
+    size_t dskip;     // (B,Tout,S) fp32
+    size_t dgated;    // (B,T,C) act dtype
+    size_t dz;        // (B,T,2C) act dtype
+    size_t dxa, dxb;  // (B,T,C) act dtype, ping-pong
+    size_t dctx;      // (B,T,C) fp32
+    size_t du2, du1, denc;
+    size_t total;
+};
+
+static inline void scratch_layout(const Geo& g, ScratchLayout& w) {
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += al256(n); return r; };
+    const size_t BT = (size_t)g.B * g.T;
+    const size_t BTo = (size_t)g.B * (g.Tout > 0 ? g.Tout : 0);
+    w.gated = take(BT * g.C * g.es);
+    w.z = take(BTo * g.A * 4);
+    w.da1 = take(BTo * g.A * 4);
+    w.dskip = take(BTo * g.S * 4);
+    w.dgated = take(BT * g.C * g.es);
+    w.dz = take(BT * 2 * g.C * g.es);
+    w.dxa = take(BT * g.C * g.es);
+    w.dxb = take(BT * g.C * g.es);
+    if (g.video) {
+        w.dctx = take(BT * g.C * 4);
+        w.du2 = take((size_t)g.B * 16000 * g.C * 4);
+        w.du1 = take((size_t)g.B * 1600 * g.C * 4);
+        w.denc = take((size_t)g.B * 160 * g.C * 4);
+    } else w.dctx = w.du2 = w.du1 = w.denc = 0;
+    w.total = o;
+}

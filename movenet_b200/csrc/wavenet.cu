@@ -1,0 +1,538 @@
+// WaveNet forward / backward orchestration and the non-GEMM kernels
+// (one-hot detection, input gather, softmax <-> channels-first transposes).
+#include "common.cuh"
+#include "gemm_f32.cuh"
+#include "layout.h"
+#include "layer_tc.h"
+
+// ------------------------------------------------------------------------------------------------
+// audio (B,A,T) fp32 -> codes[b][t] = argmax_a (first max, like torch.argmax), dense[b][t] = 1 when
+// the column is not an exact one-hot (then the input conv takes the dense path).
+// The same codes are the training targets: target[t] = codes[t + RF]
+// (movenet/pytorch_lightning_trainer.py:64).
+__global__ void codes_kernel(const float* __restrict__ audio, int A, int T, int* __restrict__ codes,
+                             unsigned char* __restrict__ dense) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (t >= T) return;
+    const float* p = audio + (size_t)b * A * T + t;
+    float best = p[0]; int arg = 0, ones = (best == 1.f), other = (best != 0.f && best != 1.f);
+    for (int a = 1; a < A; ++a) {
+        const float v = p[(size_t)a * T];
+        if (v > best || (v != v && best == best)) { best = v; arg = a; }   // NaN wins like torch
+        ones += (v == 1.f); other += (v != 0.f && v != 1.f);
+    }
+    codes[(size_t)b * T + t] = arg;
+    dense[(size_t)b * T + t] = (ones == 1 && other == 0) ? 0 : 1;
+}
+
+// CausalConv1d (movenet/modules.py:15-30): h0[t] = W[:,:,0] x[t-1] + W[:,:,1] x[t], x[-1] = 0.
+// One-hot columns are a gather of two rows of Win[tap][a][:]; anything else takes the dense sum.
+__global__ void input_fwd_kernel(const float* __restrict__ audio, const int* __restrict__ codes,
+                                 const unsigned char* __restrict__ dense, const float* __restrict__ win,
+                                 void* __restrict__ h0, int adt, int A, int C, int T, long long rows) {
+    const int cg = (C + 3) / 4;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cg) return;
+    const long long row = idx / cg;
+    const int c0 = (int)(idx % cg) * 4;
+    const long long b = row / T; const int t = (int)(row % T);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int tap = 0; tap < 2; ++tap) {
+        const int ts = t - 1 + tap;
+        if (ts < 0) continue;
+        const long long r = b * T + ts;
+        const float* wt = win + (size_t)tap * A * C;
+        if (!dense[r]) {
+            const float* wr = wt + (size_t)codes[r] * C + c0;
+            for (int j = 0; j < 4 && c0 + j < C; ++j) acc[j] += wr[j];
+        } else {
+            for (int a = 0; a < A; ++a) {
+                const float x = audio[((size_t)b * A + a) * T + ts];
+                if (x != 0.f) for (int j = 0; j < 4 && c0 + j < C; ++j) acc[j] = fmaf(x, wt[(size_t)a * C + c0 + j], acc[j]);
+            }
+        }
+    }
+    for (int j = 0; j < 4 && c0 + j < C; ++j) mvn_st(h0, adt, row * C + c0 + j, acc[j]);
+}
+
+// dWin[tap][a][c] += sum_t dh0[t][c] * x[a][t-1+tap]
+__global__ void input_bwd_kernel(const float* __restrict__ audio, const int* __restrict__ codes,
+                                 const unsigned char* __restrict__ dense, const void* __restrict__ dh0, int adt,
+                                 float* __restrict__ dwin, int A, int C, int T, long long rows, int rows_per_cta,
+                                 int use_smem) {
+    extern __shared__ float sacc[];
+    const int n = 2 * A * C;
+    if (use_smem) { for (int i = threadIdx.x; i < n; i += blockDim.x) sacc[i] = 0.f; __syncthreads(); }
+    float* acc = use_smem ? sacc : dwin;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const long long rbeg = (long long)blockIdx.x * rows_per_cta;
+    long long rend = rbeg + rows_per_cta; if (rend > rows) rend = rows;
+    for (long long row = rbeg + warp; row < rend; row += nw) {
+        const long long b = row / T; const int t = (int)(row % T);
+        for (int tap = 0; tap < 2; ++tap) {
+            const int ts = t - 1 + tap;
+            if (ts < 0) continue;
+            const long long r = b * T + ts;
+            if (!dense[r]) {
+                float* dst = acc + ((size_t)tap * A + codes[r]) * C;
+                for (int c = lane; c < C; c += 32) {
+                    const float g = mvn_ld(dh0, adt, row * C + c);
+                    if (g != 0.f) atomicAdd(dst + c, g);
+                }
+            } else {
+                for (int a = 0; a < A; ++a) {
+                    const float x = audio[((size_t)b * A + a) * T + ts];
+                    if (x == 0.f) continue;
+                    float* dst = acc + ((size_t)tap * A + a) * C;
+                    for (int c = lane; c < C; c += 32) atomicAdd(dst + c, x * mvn_ld(dh0, adt, row * C + c));
+                }
+            }
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) if (sacc[i] != 0.f) atomicAdd(dwin + i, sacc[i]);
+    }
+}
+
+// z (B,Tn,A) time-major fp32 -> out (B,A,Tn) channels-first: softmax over A (movenet/wavenet.py:191)
+// or a plain transpose when the caller asked for logits.
+__global__ void softmax_nct_fwd_kernel(const float* __restrict__ z, float* __restrict__ out, int A, int Tn,
+                                       int logits) {
+    extern __shared__ float tile[];      // [32][A+1]
+    const int b = blockIdx.y, j0 = blockIdx.x * 32, ld = A + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int r = warp; r < 32; r += nw) {
+        const int j = j0 + r;
+        if (j >= Tn) continue;
+        const float* zr = z + ((size_t)b * Tn + j) * A;
+        float m = -INFINITY;
+        for (int a = lane; a < A; a += 32) { const float v = zr[a]; tile[r * ld + a] = v; m = fmaxf(m, v); }
+        if (!logits) {
+            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float sum = 0.f;
+            for (int a = lane; a < A; a += 32) { const float e = expf(tile[r * ld + a] - m); tile[r * ld + a] = e; sum += e; }
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float inv = 1.f / sum;
+            for (int a = lane; a < A; a += 32) tile[r * ld + a] *= inv;
+        }
+    }
+    __syncthreads();
+    const int j = j0 + lane;
+    if (j < Tn)
+        for (int a = warp; a < A; a += nw) out[((size_t)b * A + a) * Tn + j] = tile[lane * ld + a];
+}
+
+// d(logits) time-major from d(out) channels-first: dz = p * (dp - sum_a dp*p)  (or transpose for logits)
+__global__ void softmax_nct_bwd_kernel(const float* __restrict__ probs, const float* __restrict__ dout,
+                                       float* __restrict__ dz, int A, int Tn, int logits) {
+    extern __shared__ float tile[];      // p[32][A+1], dp[32][A+1]
+    const int b = blockIdx.y, j0 = blockIdx.x * 32, ld = A + 1;
+    float* tp = tile; float* td = tile + 32 * ld;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int j = j0 + lane;
+    if (j < Tn)
+        for (int a = warp; a < A; a += nw) {
+            const size_t o = ((size_t)b * A + a) * Tn + j;
+            td[lane * ld + a] = dout[o];
+            if (!logits) tp[lane * ld + a] = probs[o];
+        }
+    __syncthreads();
+    for (int r = warp; r < 32; r += nw) {
+        const int jj = j0 + r;
+        if (jj >= Tn) continue;
+        float* dr = dz + ((size_t)b * Tn + jj) * A;
+        if (logits) { for (int a = lane; a < A; a += 32) dr[a] = td[r * ld + a]; continue; }
+        float dot = 0.f;
+        for (int a = lane; a < A; a += 32) dot = fmaf(td[r * ld + a], tp[r * ld + a], dot);
+        for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        for (int a = lane; a < A; a += 32) dr[a] = tp[r * ld + a] * (td[r * ld + a] - dot);
+    }
+}
+
+__global__ void to_f32_kernel(const void* __restrict__ src, int dtype, float* __restrict__ dst, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = mvn_ld(src, dtype, i);
+}
+
+// ------------------------------------------------------------------------------------------------
+static GemmSrc make_src(const void* ptr, int dtype, int ld, int K, int T, int shift, int pre, const float* W, int ldw) {
+    GemmSrc s; s.ptr = ptr; s.W = W; s.dtype = dtype; s.ld = ld; s.K = K; s.T = T; s.shift = shift; s.pre = pre; s.ldw = ldw;
+    return s;
+}
+static void set_out(RowGemmArgs& a, void* out, int dtype, int ld, int T, int shift) {
+    a.out = out; a.out_dtype = dtype; a.ldo = ld; a.out_T = T; a.out_shift = shift;
+}
+static void set_out2(RowGemmArgs& a, void* out, int dtype, int ld, int T, int shift) {
+    a.out2 = out; a.out2_dtype = dtype; a.ldo2 = ld; a.out2_T = T; a.out2_shift = shift;
+}
+static void set_aux(RowGemmArgs& a, const void* aux, int dtype, int ld, int T, int shift) {
+    a.aux = aux; a.aux_dtype = dtype; a.lda = ld; a.aux_T = T; a.aux_shift = shift;
+}
+static RowGemmArgs new_args(long long rows, int Trow, int N, int epi, const float* bias) {
+    RowGemmArgs a; memset(&a, 0, sizeof(a));
+    a.rows = rows; a.Trow = Trow; a.N = N; a.epi = epi; a.bias = bias;
+    return a;
+}
+static TnSrc make_tn(const void* ptr, int dtype, int ld, int K, int T, int shift, int pre, float* out, int ldo) {
+    TnSrc s; s.ptr = ptr; s.out = out; s.dtype = dtype; s.ld = ld; s.K = K; s.T = T; s.shift = shift; s.pre = pre; s.ldo = ldo;
+    return s;
+}
+
+struct Ctx {
+    Geo g; PackedLayout P; ActsLayout AL; ScratchLayout SL;
+    const float* packed; char* acts; char* scratch; cudaStream_t st;
+    const float* lw(int l) const { return packed + P.layer0 + (size_t)l * P.layer_stride; }
+    void* x(int l) const { return acts + AL.x0 + (size_t)l * AL.x_stride; }
+};
+
+static int ctx_init(Ctx& c, const mvn_shape_t* s, const void* packed, const void* acts, const void* scratch, void* stream,
+                    const char* who) {
+    MVN_REQUIRE(s != nullptr, "%s: null shape", who);
+    MVN_REQUIRE(geo_init(c.g, s) == 0, "%s: bad layer_size/stack_size", who);
+    MVN_REQUIRE(c.g.A >= 1 && c.g.C >= 1 && c.g.S >= 1 && c.g.B >= 1, "%s: bad channel/batch sizes", who);
+    MVN_REQUIRE(c.g.Tout >= 1, "%s: input time steps (%d) must be larger than the receptive fields (%d)", who, c.g.T, c.g.RF);
+    MVN_REQUIRE(!c.g.video || c.g.T == MVN_MAX_AUDIO_FRAMES, "%s: video conditioning needs %d frames", who, MVN_MAX_AUDIO_FRAMES);
+    MVN_REQUIRE(c.g.adt == MVN_DTYPE_F32 || c.g.adt == MVN_DTYPE_BF16, "%s: bad act_dtype", who);
+    MVN_REQUIRE((long long)c.g.B * c.g.T < 0x7fffffffLL, "%s: batch*frames overflows", who);
+    packed_layout(c.g, c.P); acts_layout(c.g, c.AL); scratch_layout(c.g, c.SL);
+    c.packed = (const float*)packed; c.acts = (char*)acts; c.scratch = (char*)scratch; c.st = (cudaStream_t)stream;
+    return 0;
+}
+
+extern "C" size_t mvn_packed_bytes(const mvn_shape_t* s) {
+    Geo g; if (geo_init(g, s)) return 0; PackedLayout P; packed_layout(g, P); return P.total * 4;
+}
+extern "C" size_t mvn_acts_bytes(const mvn_shape_t* s) {
+    Geo g; if (geo_init(g, s)) return 0; ActsLayout a; acts_layout(g, a); return a.total;
+}
+extern "C" size_t mvn_scratch_bytes(const mvn_shape_t* s) {
+    Geo g; if (geo_init(g, s)) return 0; ScratchLayout w; scratch_layout(g, w); return w.total;
+}
+extern "C" int mvn_receptive_fields(int layer_size, int stack_size) {
+    mvn_shape_t s; memset(&s, 0, sizeof(s)); s.layer_size = layer_size; s.stack_size = stack_size;
+    Geo g; if (geo_init(g, &s)) return -1; return g.RF;
+}
+extern "C" int mvn_output_size(int layer_size, int stack_size, int frames) {
+    const int rf = mvn_receptive_fields(layer_size, stack_size);
+    return rf < 0 ? -1 : frames - rf + 1;
+}
+
+extern "C" int mvn_onehot_to_codes(const float* audio, int B, int A, int T, int* codes, unsigned char* dense, void* stream) {
+    MVN_REQUIRE(audio && codes && dense && B > 0 && A > 0 && T > 0, "mvn_onehot_to_codes: bad arguments");
+    dim3 grid(mvn_cdiv(T, 256), B);
+    codes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(audio, A, T, codes, dense);
+    return mvn_check_launch("onehot_to_codes");
+}
+
+static int input_fwd(const Ctx& c, const float* audio) {
+    const Geo& g = c.g;
+    int* codes = (int*)(c.acts + c.AL.codes); unsigned char* dense = (unsigned char*)(c.acts + c.AL.dense);
+    int rc = mvn_onehot_to_codes(audio, g.B, g.A, g.T, codes, dense, c.st);
+    if (rc) return rc;
+    const long long rows = (long long)g.B * g.T, n = rows * ((g.C + 3) / 4);
+    input_fwd_kernel<<<mvn_cdiv(n, 256), 256, 0, c.st>>>(audio, codes, dense, c.packed + c.P.win, c.x(0), g.adt, g.A, g.C, g.T, rows);
+    return mvn_check_launch("input_fwd");
+}
+
+static int video_fwd(const Ctx& c, const float* video) {
+    const Geo& g = c.g; const int C = g.C;
+    float* enc = (float*)(c.acts + c.AL.enc); float* u1 = (float*)(c.acts + c.AL.u1); float* u2 = (float*)(c.acts + c.AL.u2);
+    void* ctx = c.acts + c.AL.ctx;
+    int rc;
+    {   // Conv3d with a (1,64,64) kernel = one 4096*Cin -> C linear map per frame (movenet/wavenet.py:94-98,152)
+        const int rows = g.B * 160, K = 4096 * g.Cin;
+        RowGemmArgs a = new_args(rows, rows, C, EPI_STORE, c.packed + c.P.bv);
+        a.nsrc = 1; a.src[0] = make_src(video, MVN_F32, K, K, rows, 0, 0, c.packed + c.P.wv, C);
+        set_out(a, enc, MVN_F32, C, rows, 0);
+        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+    }
+    // ConvTranspose1d(k=10, stride=10): out[10 i + j] = W[:, :, j]^T in[i] + b -- a [rows x C] x [C x 10C] GEMM whose
+    // row-major output IS the time-major upsampled signal (movenet/wavenet.py:102-118,154)
+    const void* in[3] = {enc, u1, u2}; void* out[3] = {u1, u2, ctx};
+    const int len[3] = {160, 1600, 16000};
+    for (int i = 0; i < 3; ++i) {
+        const int rows = g.B * len[i];
+        RowGemmArgs a = new_args(rows, rows, 10 * C, EPI_STORE, c.packed + c.P.bt[i]);
+        a.nsrc = 1; a.src[0] = make_src(in[i], MVN_F32, C, C, rows, 0, 0, c.packed + c.P.wt[i], 10 * C);
+        set_out(a, out[i], i == 2 ? g.adt : MVN_F32, 10 * C, rows, 0);
+        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+    }
+    return 0;
+}
+
+// GatedResidualConv1d.forward (movenet/modules.py:67-93)
+static int layer_fwd(const Ctx& c, int l) {
+    const Geo& g = c.g; const int C = g.C, S = g.S, d = g.dil[l];
+    const long long rows = (long long)g.B * g.T;
+    const float* lw = c.lw(l);
+    const bool last = (l == g.N - 1);
+    float* skip = (float*)(c.acts + c.AL.skip);
+    void* ctx = g.video ? c.acts + c.AL.ctx : nullptr;
+    if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
+        return mvn_tc_layer_fwd(c.x(l), ctx, last ? nullptr : c.x(l + 1), skip, lw, c.P, g, l, c.st);
+    }
+    void* gated = c.scratch + c.SL.gated;
+    int rc;
+    RowGemmArgs a = new_args(rows, g.T, 2 * C, EPI_GATE, lw + c.P.obz);
+    a.nsrc = 2;
+    a.src[0] = make_src(c.x(l), g.adt, C, C, g.T, -d, 0, lw + c.P.oWz, 2 * C);
+    a.src[1] = make_src(c.x(l), g.adt, C, C, g.T, 0, 0, lw + c.P.oWz + (size_t)C * 2 * C, 2 * C);
+    if (g.video) { a.nsrc = 3; a.src[2] = make_src(ctx, g.adt, C, C, g.T, 0, 0, lw + c.P.oWz + (size_t)2 * C * 2 * C, 2 * C); }
+    set_out(a, gated, g.adt, C, g.T, 0);
+    if ((rc = mvn_row_gemm(a, c.st))) return rc;
+
+    // residual + skip 1x1 convs; the last layer's residual is discarded (movenet/modules.py:125-130)
+    RowGemmArgs r = new_args(rows, g.T, last ? S : C + S, EPI_RESID_SKIP, lw + c.P.obrs + (last ? C : 0));
+    r.nsrc = 1; r.src[0] = make_src(gated, g.adt, C, C, g.T, 0, 0, lw + c.P.oWrs + (last ? C : 0), C + S);
+    r.split = last ? 0 : C;
+    if (!last) { set_out(r, c.x(l + 1), g.adt, C, g.T, 0); set_aux(r, c.x(l), g.adt, C, g.T, 0); }
+    set_out2(r, skip, MVN_F32, S, g.Tout, -(g.RF - 1));
+    return mvn_row_gemm(r, c.st);
+}
+
+// DenseConv (movenet/modules.py:133-142) + drop-last + softmax (movenet/wavenet.py:183-191)
+static int head_fwd(const Ctx& c, float* out) {
+    const Geo& g = c.g;
+    if (g.Tn <= 0) return 0;
+    const long long rows = (long long)g.B * g.Tn;
+    float* skip = (float*)(c.acts + c.AL.skip); float* a1 = (float*)(c.acts + c.AL.a1); float* z = (float*)(c.scratch + c.SL.z);
+    int rc;
+    RowGemmArgs a = new_args(rows, g.Tn, g.A, EPI_STORE, c.packed + c.P.b1);
+    a.nsrc = 1; a.src[0] = make_src(skip, MVN_F32, g.S, g.S, g.Tout, 0, 1, c.packed + c.P.w1p, g.A);
+    set_out(a, a1, MVN_F32, g.A, g.Tn, 0);
+    if ((rc = mvn_row_gemm(a, c.st))) return rc;
+    RowGemmArgs b = new_args(rows, g.Tn, g.A, EPI_STORE, c.packed + c.P.b2);
+    b.nsrc = 1; b.src[0] = make_src(a1, MVN_F32, g.A, g.A, g.Tn, 0, 1, c.packed + c.P.w2p, g.A);
+    set_out(b, z, MVN_F32, g.A, g.Tn, 0);
+    if ((rc = mvn_row_gemm(b, c.st))) return rc;
+    dim3 grid(mvn_cdiv(g.Tn, 32), g.B);
+    const size_t smem = (size_t)32 * (g.A + 1) * 4;
+    MVN_REQUIRE(smem <= 200 * 1024, "head: input_channels too large (%d)", g.A);
+    MVN_CUDA(cudaFuncSetAttribute(softmax_nct_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    softmax_nct_fwd_kernel<<<grid, 256, smem, c.st>>>(z, out, g.A, g.Tn, g.logits);
+    return mvn_check_launch("softmax_nct_fwd");
+}
+
+extern "C" int mvn_input_fwd(const mvn_shape_t* s, const void* packed, const float* audio, void* acts, void* stream) {
+    Ctx c; int rc = ctx_init(c, s, packed, acts, nullptr, stream, "mvn_input_fwd"); if (rc) return rc;
+    return input_fwd(c, audio);
+}
+extern "C" int mvn_video_fwd(const mvn_shape_t* s, const void* packed, const float* video, void* acts, void* stream) {
+    Ctx c; int rc = ctx_init(c, s, packed, acts, nullptr, stream, "mvn_video_fwd"); if (rc) return rc;
+    MVN_REQUIRE(c.g.video && video, "mvn_video_fwd: shape has no video");
+    return video_fwd(c, video);
+}
+extern "C" int mvn_layer_fwd(const mvn_shape_t* s, const void* packed, int layer, void* acts, void* scratch, void* stream) {
+    Ctx c; int rc = ctx_init(c, s, packed, acts, scratch, stream, "mvn_layer_fwd"); if (rc) return rc;
+    MVN_REQUIRE(layer >= 0 && layer < c.g.N, "mvn_layer_fwd: layer %d out of range", layer);
+    if (layer == 0) MVN_CUDA(cudaMemsetAsync(c.acts + c.AL.skip, 0, (size_t)c.g.B * c.g.Tout * c.g.S * 4, c.st));
+    return layer_fwd(c, layer);
+}
+extern "C" int mvn_head_fwd(const mvn_shape_t* s, const void* packed, void* acts, float* out, void* scratch, void* stream) {
+    Ctx c; int rc = ctx_init(c, s, packed, acts, scratch, stream, "mvn_head_fwd"); if (rc) return rc;
+    return head_fwd(c, out);
+}
+
+extern "C" int mvn_wavenet_forward(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,
+                                   void* acts, float* out, void* scratch, void* stream) {
+    Ctx c; int rc = ctx_init(c, s, packed, acts, scratch, stream, "mvn_wavenet_forward"); if (rc) return rc;
+    MVN_REQUIRE(audio && out && packed && acts && scratch, "mvn_wavenet_forward: null buffer");
+    MVN_REQUIRE(!c.g.video || video, "mvn_wavenet_forward: shape says video but video is null");
+    if (c.g.video && (rc = video_fwd(c, video))) return rc;
+    if ((rc = input_fwd(c, audio))) return rc;
+    MVN_CUDA(cudaMemsetAsync(c.acts + c.AL.skip, 0, (size_t)c.g.B * c.g.Tout * c.g.S * 4, c.st));
+    for (int l = 0; l < c.g.N; ++l) if ((rc = layer_fwd(c, l))) return rc;
+    return head_fwd(c, out);
+}
+
+extern "C" int mvn_debug_read(const mvn_shape_t* s, const void* acts, int which, int layer, float* dst, void* stream) {
+    Ctx c; int rc = ctx_init(c, s, nullptr, acts, nullptr, stream, "mvn_debug_read"); if (rc) return rc;
+    const Geo& g = c.g; const void* src; int dt; long long n;
+    if (which == 0) { MVN_REQUIRE(layer >= 0 && layer < g.N, "mvn_debug_read: bad layer"); src = c.x(layer); dt = g.adt; n = (long long)g.B * g.T * g.C; }
+    else if (which == 1) { src = c.acts + c.AL.skip; dt = MVN_F32; n = (long long)g.B * g.Tout * g.S; }
+    else if (which == 2) { MVN_REQUIRE(g.video, "mvn_debug_read: no context"); src = c.acts + c.AL.ctx; dt = g.adt; n = (long long)g.B * g.T * g.C; }
+    else { mvn_set_error("mvn_debug_read: bad selector"); return -1; }
+    to_f32_kernel<<<1184, 256, 0, c.st>>>(src, dt, dst, n);
+    return mvn_check_launch("debug_read");
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+static int head_bwd(const Ctx& c, const float* out, const float* dout, float* pg) {
+    const Geo& g = c.g;
+    float* skip = (float*)(c.acts + c.AL.skip); float* a1 = (float*)(c.acts + c.AL.a1);
+    float* dzh = (float*)(c.scratch + c.SL.z); float* da1 = (float*)(c.scratch + c.SL.da1); float* dskip = (float*)(c.scratch + c.SL.dskip);
+    MVN_CUDA(cudaMemsetAsync(dskip, 0, (size_t)g.B * g.Tout * g.S * 4, c.st));
+    if (g.Tn <= 0) return 0;
+    const long long rows = (long long)g.B * g.Tn;
+    int rc;
+    dim3 grid(mvn_cdiv(g.Tn, 32), g.B);
+    const size_t smem = (size_t)2 * 32 * (g.A + 1) * 4;
+    MVN_REQUIRE(smem <= 200 * 1024, "head: input_channels too large (%d)", g.A);
+    MVN_CUDA(cudaFuncSetAttribute(softmax_nct_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    softmax_nct_bwd_kernel<<<grid, 256, smem, c.st>>>(out, dout, dzh, g.A, g.Tn, g.logits);
+    if ((rc = mvn_check_launch("softmax_nct_bwd"))) return rc;
+    {   // conv2 weight/bias grads: dW2p[k][n] = sum lrelu(a1)[k] dz[n]
+        TnGemmArgs t; memset(&t, 0, sizeof(t));
+        t.rows = rows; t.Trow = g.Tn; t.N = g.A; t.nsrc = 1;
+        t.src[0] = make_tn(a1, MVN_F32, g.A, g.A, g.Tn, 0, 1, pg + c.P.w2p, g.A);
+        t.q = dzh; t.q_dtype = MVN_F32; t.ldq = g.A; t.q_T = g.Tn; t.q_shift = 0; t.dbias = pg + c.P.b2;
+        if ((rc = mvn_tn_gemm(t, c.st))) return rc;
+    }
+    {   // da1 = (dz W2) * lrelu'(a1)
+        RowGemmArgs a = new_args(rows, g.Tn, g.A, EPI_MUL_LRELU_GRAD, nullptr);
+        a.nsrc = 1; a.src[0] = make_src(dzh, MVN_F32, g.A, g.A, g.Tn, 0, 0, c.packed + c.P.w2pT, g.A);
+        set_out(a, da1, MVN_F32, g.A, g.Tn, 0); set_aux(a, a1, MVN_F32, g.A, g.Tn, 0);
+        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+    }
+    {   // conv1 grads: dW1p[s][a] = sum lrelu(skip)[s] da1[a]
+        TnGemmArgs t; memset(&t, 0, sizeof(t));
+        t.rows = rows; t.Trow = g.Tn; t.N = g.A; t.nsrc = 1;
+        t.src[0] = make_tn(skip, MVN_F32, g.S, g.S, g.Tout, 0, 1, pg + c.P.w1p, g.A);
+        t.q = da1; t.q_dtype = MVN_F32; t.ldq = g.A; t.q_T = g.Tn; t.q_shift = 0; t.dbias = pg + c.P.b1;
+        if ((rc = mvn_tn_gemm(t, c.st))) return rc;
+    }
+    {   // dskip = (da1 W1) * lrelu'(skip_sum); the dropped last column keeps a zero gradient
+        RowGemmArgs a = new_args(rows, g.Tn, g.S, EPI_MUL_LRELU_GRAD, nullptr);
+        a.nsrc = 1; a.src[0] = make_src(da1, MVN_F32, g.A, g.A, g.Tn, 0, 0, c.packed + c.P.w1pT, g.S);
+        set_out(a, dskip, MVN_F32, g.S, g.Tout, 0); set_aux(a, skip, MVN_F32, g.S, g.Tout, 0);
+        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+    }
+    return 0;
+}
+
+static int layer_bwd(const Ctx& c, int l, const void* dx_next, void* dx_cur, float* pg) {
+    const Geo& g = c.g; const int C = g.C, S = g.S, d = g.dil[l], Kz = g.Kz;
+    const long long rows = (long long)g.B * g.T;
+    const float* lw = c.lw(l);
+    float* lg = pg + c.P.layer0 + (size_t)l * c.P.layer_stride;
+    float* dskip = (float*)(c.scratch + c.SL.dskip);
+    void* dgated = c.scratch + c.SL.dgated; void* dz = c.scratch + c.SL.dz; void* gated = c.scratch + c.SL.gated;
+    void* ctx = g.video ? c.acts + c.AL.ctx : nullptr;
+    const int sshift = -(g.RF - 1);
+    int rc;
+    {   // d(gated) = Wr^T d(residual) + Ws^T d(skip)
+        RowGemmArgs a = new_args(rows, g.T, C, EPI_STORE, nullptr);
+        int n = 0;
+        if (dx_next) a.src[n++] = make_src(dx_next, g.adt, C, C, g.T, 0, 0, lw + c.P.oWrsT, C);
+        a.src[n++] = make_src(dskip, MVN_F32, S, S, g.Tout, sshift, 0, lw + c.P.oWrsT + (size_t)C * C, C);
+        a.nsrc = n;
+        set_out(a, dgated, g.adt, C, g.T, 0);
+        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+    }
+    {   // recompute the pre-activations, then d(pre) = d(gated) * d(tanh*sigmoid)
+        RowGemmArgs a = new_args(rows, g.T, 2 * C, EPI_GATE_BWD, lw + c.P.obz);
+        a.nsrc = 2;
+        a.src[0] = make_src(c.x(l), g.adt, C, C, g.T, -d, 0, lw + c.P.oWz, 2 * C);
+        a.src[1] = make_src(c.x(l), g.adt, C, C, g.T, 0, 0, lw + c.P.oWz + (size_t)C * 2 * C, 2 * C);
+        if (g.video) { a.nsrc = 3; a.src[2] = make_src(ctx, g.adt, C, C, g.T, 0, 0, lw + c.P.oWz + (size_t)2 * C * 2 * C, 2 * C); }
+        set_out(a, dz, g.adt, 2 * C, g.T, 0); set_out2(a, gated, g.adt, C, g.T, 0); set_aux(a, dgated, g.adt, C, g.T, 0);
+        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+    }
+    {   // weight grads of the dilated convs (+ context convs and their biases)
+        TnGemmArgs t; memset(&t, 0, sizeof(t));
+        t.rows = rows; t.Trow = g.T; t.N = 2 * C; t.nsrc = 2;
+        t.src[0] = make_tn(c.x(l), g.adt, C, C, g.T, -d, 0, lg + c.P.oWz, 2 * C);
+        t.src[1] = make_tn(c.x(l), g.adt, C, C, g.T, 0, 0, lg + c.P.oWz + (size_t)C * 2 * C, 2 * C);
+        if (g.video) { t.nsrc = 3; t.src[2] = make_tn(ctx, g.adt, C, C, g.T, 0, 0, lg + c.P.oWz + (size_t)2 * C * 2 * C, 2 * C); }
+        t.q = dz; t.q_dtype = g.adt; t.ldq = 2 * C; t.q_T = g.T; t.q_shift = 0;
+        t.dbias = g.video ? lg + c.P.obz : nullptr;
+        if ((rc = mvn_tn_gemm(t, c.st))) return rc;
+    }
+    if (dx_next) {   // residual 1x1 conv grads
+        TnGemmArgs t; memset(&t, 0, sizeof(t));
+        t.rows = rows; t.Trow = g.T; t.N = C; t.nsrc = 1;
+        t.src[0] = make_tn(gated, g.adt, C, C, g.T, 0, 0, lg + c.P.oWrs, C + S);
+        t.q = dx_next; t.q_dtype = g.adt; t.ldq = C; t.q_T = g.T; t.q_shift = 0; t.dbias = lg + c.P.obrs;
+        if ((rc = mvn_tn_gemm(t, c.st))) return rc;
+    }
+    {   // skip 1x1 conv grads
+        TnGemmArgs t; memset(&t, 0, sizeof(t));
+        t.rows = rows; t.Trow = g.T; t.N = S; t.nsrc = 1;
+        t.src[0] = make_tn(gated, g.adt, C, C, g.T, 0, 0, lg + c.P.oWrs + C, C + S);
+        t.q = dskip; t.q_dtype = MVN_F32; t.ldq = S; t.q_T = g.Tout; t.q_shift = sshift; t.dbias = lg + c.P.obrs + C;
+        if ((rc = mvn_tn_gemm(t, c.st))) return rc;
+    }
+    {   // d(x_l)[t] = d(x_{l+1})[t] + W1^T dz[t] + W0^T dz[t+d]
+        RowGemmArgs a = new_args(rows, g.T, C, EPI_ADD_AUX, nullptr);
+        a.nsrc = 2;
+        a.src[0] = make_src(dz, g.adt, 2 * C, 2 * C, g.T, 0, 0, lw + c.P.oWzT + C, Kz);
+        a.src[1] = make_src(dz, g.adt, 2 * C, 2 * C, g.T, d, 0, lw + c.P.oWzT, Kz);
+        set_out(a, dx_cur, g.adt, C, g.T, 0);
+        if (dx_next) set_aux(a, dx_next, g.adt, C, g.T, 0);
+        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+    }
+    if (g.video) {   // d(ctx) += V^T dz
+        RowGemmArgs a = new_args(rows, g.T, C, EPI_ACCUM, nullptr);
+        a.nsrc = 1; a.src[0] = make_src(dz, g.adt, 2 * C, 2 * C, g.T, 0, 0, lw + c.P.oWzT + 2 * C, Kz);
+        set_out(a, c.scratch + c.SL.dctx, MVN_F32, C, g.T, 0);
+        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+    }
+    return 0;
+}
+
+static int input_bwd(const Ctx& c, const float* audio, const void* dh0, float* pg) {
+    const Geo& g = c.g;
+    const long long rows = (long long)g.B * g.T;
+    const size_t smem = (size_t)2 * g.A * g.C * 4;
+    const int use_smem = smem <= 160 * 1024;
+    const int ctas = 148 * 2;
+    const int rpc = (int)((rows + ctas - 1) / ctas);
+    MVN_CUDA(cudaFuncSetAttribute(input_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    input_bwd_kernel<<<mvn_cdiv(rows, rpc), 256, use_smem ? smem : 0, c.st>>>(
+        audio, (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), dh0, g.adt,
+        pg + c.P.win, g.A, g.C, g.T, rows, rpc, use_smem);
+    return mvn_check_launch("input_bwd");
+}
+
+static int video_bwd(const Ctx& c, const float* video, float* pg) {
+    const Geo& g = c.g; const int C = g.C;
+    const float* enc = (const float*)(c.acts + c.AL.enc); const float* u1 = (const float*)(c.acts + c.AL.u1);
+    const float* u2 = (const float*)(c.acts + c.AL.u2);
+    float* dctx = (float*)(c.scratch + c.SL.dctx); float* du2 = (float*)(c.scratch + c.SL.du2);
+    float* du1 = (float*)(c.scratch + c.SL.du1); float* denc = (float*)(c.scratch + c.SL.denc);
+    const float* in[3] = {enc, u1, u2}; const float* dout[3] = {du1, du2, dctx}; float* din[3] = {denc, du1, du2};
+    const int len[3] = {160, 1600, 16000};
+    int rc;
+    for (int i = 2; i >= 0; --i) {
+        const int rows = g.B * len[i];
+        TnGemmArgs t; memset(&t, 0, sizeof(t));
+        t.rows = rows; t.Trow = rows; t.N = 10 * C; t.nsrc = 1;
+        t.src[0] = make_tn(in[i], MVN_F32, C, C, rows, 0, 0, pg + c.P.wt[i], 10 * C);
+        t.q = dout[i]; t.q_dtype = MVN_F32; t.ldq = 10 * C; t.q_T = rows; t.q_shift = 0; t.dbias = pg + c.P.bt[i];
+        if ((rc = mvn_tn_gemm(t, c.st))) return rc;
+        RowGemmArgs a = new_args(rows, rows, C, EPI_STORE, nullptr);
+        a.nsrc = 1; a.src[0] = make_src(dout[i], MVN_F32, 10 * C, 10 * C, rows, 0, 0, c.packed + c.P.wtT[i], C);
+        set_out(a, din[i], MVN_F32, C, rows, 0);
+        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+    }
+    const int rows = g.B * 160, K = 4096 * g.Cin;
+    TnGemmArgs t; memset(&t, 0, sizeof(t));
+    t.rows = rows; t.Trow = rows; t.N = C; t.nsrc = 1;
+    t.src[0] = make_tn(video, MVN_F32, K, K, rows, 0, 0, pg + c.P.wv, C);
+    t.q = denc; t.q_dtype = MVN_F32; t.ldq = C; t.q_T = rows; t.q_shift = 0; t.dbias = pg + c.P.bv;
+    return mvn_tn_gemm(t, c.st);
+}
+
+extern "C" int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,
+                                    const void* acts, const float* out, const float* dout, void* packed_grads,
+                                    void* scratch, void* stream) {
+    Ctx c; int rc = ctx_init(c, s, packed, acts, scratch, stream, "mvn_wavenet_backward"); if (rc) return rc;
+    MVN_REQUIRE(audio && dout && packed && acts && scratch && packed_grads, "mvn_wavenet_backward: null buffer");
+    MVN_REQUIRE(c.g.logits || out, "mvn_wavenet_backward: the probabilities returned by forward are required");
+    const Geo& g = c.g;
+    float* pg = (float*)packed_grads;
+    MVN_CUDA(cudaMemsetAsync(pg, 0, c.P.total * 4, c.st));
+    if ((rc = head_bwd(c, out, dout, pg))) return rc;
+    if (g.video) MVN_CUDA(cudaMemsetAsync(c.scratch + c.SL.dctx, 0, (size_t)g.B * g.T * g.C * 4, c.st));
+    void* bufs[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};
+    const void* dx_next = nullptr; int cur = 0;
+    for (int l = g.N - 1; l >= 0; --l) {
+        if ((rc = layer_bwd(c, l, dx_next, bufs[cur], pg))) return rc;
+        dx_next = bufs[cur]; cur ^= 1;
+    }
+    if ((rc = input_bwd(c, audio, dx_next, pg))) return rc;
+    if (g.video && (rc = video_bwd(c, video, pg))) return rc;
+    return 0;
+}

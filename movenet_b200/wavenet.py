@@ -1,0 +1,319 @@
+"""B200-native WaveNet with the reference's nn.Module surface.
+
+Drop-in for ``movenet.wavenet.WaveNet`` (cosmicBboy/movenet, movenet/wavenet.py:50-239):
+same constructor arguments, attributes, sub-module / parameter names and shapes
+(``state_dict`` interchanges with reference checkpoints), same ``forward`` and
+``generate`` signatures and semantics -- including the inverted
+``output_unnormalized`` flag (movenet/wavenet.py:189-191: the default returns
+softmax probabilities).  The arithmetic runs in the hand-written sm_100a CUDA
+library behind include/movenet_b200.h; there is no PyTorch or CPU fallback.
+
+Deviations from the reference as shipped (all documented in DESIGN.md):
+* video conditioning: the reference raises at movenet/modules.py:76 (a length-T
+  context is added to a length-(T-d) tensor); here the context is right-aligned
+  the way the same function aligns the residual (movenet/modules.py:84).
+* ``generate`` runs a cached (dilation-queue) decoder instead of recomputing a
+  window per sample; see ``generate`` for what that means when stack_size == 1.
+"""
+import ctypes as C
+import functools
+import math
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .modules import CausalConv1d, DenseConv, ResidualConvStack
+from .types import AudioTensor, VideoTensor
+
+# fixed clip geometry (movenet/wavenet.py:27-31): 10 s at 16 kHz, 16 video frames / s
+MAX_AUDIO_FRAMES = 160000
+MAX_VIDEO_FRAMES = 160
+VIDEO_KERNEL_SIZE = (1, 64, 64)
+UPSAMPLE_STRIDE = 10
+
+_DTYPES = {"fp32": _lib.F32, "float32": _lib.F32, "bf16": _lib.BF16, "bfloat16": _lib.BF16}
+
+
+def upsample_kernel_size_solver(in_size, out_size, stride=1, padding=0, output_padding=0, dilation=1):
+    """Kernel size that makes ConvTranspose1d map in_size -> out_size (movenet/wavenet.py:34-47)."""
+    k = out_size - 1 - output_padding - (in_size - 1) * stride + 2 * padding
+    return (int(k / dilation + 1),)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Buffers:
+    """Caller-owned device buffers for one (device, shape): the C ABI never allocates."""
+
+    def __init__(self, shape: _lib.Shape, device):
+        self.shape = shape
+        self.device = device
+        self.packed = torch.empty(_lib.size("mvn_packed_bytes", shape), dtype=torch.uint8, device=device)
+        self.packed_grads = None
+        self.scratch = None
+        self.acts_bytes = _lib.size("mvn_acts_bytes", shape)
+
+    def get_scratch(self):
+        if self.scratch is None:
+            self.scratch = torch.empty(_lib.size("mvn_scratch_bytes", self.shape), dtype=torch.uint8, device=self.device)
+        return self.scratch
+
+    def get_packed_grads(self):
+        if self.packed_grads is None:
+            self.packed_grads = torch.empty_like(self.packed)
+        return self.packed_grads
+
+
+class _WaveNetFunction(torch.autograd.Function):
+    """forward()/backward() of the whole network as ONE autograd node."""
+
+    @staticmethod
+    def forward(ctx, module, audio, video, remove_last, output_logits, *params):
+        bufs = module._buffers(audio, video is not None, remove_last, output_logits)
+        shape = bufs.shape
+        module._pack(bufs, params)
+        Tn = shape.frames - module.receptive_fields + 1 - (1 if remove_last else 0)
+        out = torch.empty(shape.batch, shape.input_channels, max(Tn, 0), dtype=torch.float32, device=audio.device)
+        acts = torch.empty(bufs.acts_bytes, dtype=torch.uint8, device=audio.device)
+        _lib.call("mvn_wavenet_forward", C.byref(shape), bufs.packed.data_ptr(), audio.data_ptr(),
+                  0 if video is None else video.data_ptr(), acts.data_ptr(), out.data_ptr(),
+                  bufs.get_scratch().data_ptr(), _stream())
+        ctx.module, ctx.bufs, ctx.acts = module, bufs, acts
+        ctx.has_video = video is not None
+        ctx.save_for_backward(audio, video, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        module, bufs = ctx.module, ctx.bufs
+        audio, video, out = ctx.saved_tensors
+        dout = dout.contiguous().float()
+        pg = bufs.get_packed_grads()
+        _lib.call("mvn_wavenet_backward", C.byref(bufs.shape), bufs.packed.data_ptr(), audio.data_ptr(),
+                  0 if video is None else video.data_ptr(), ctx.acts.data_ptr(), out.data_ptr(), dout.data_ptr(),
+                  pg.data_ptr(), bufs.get_scratch().data_ptr(), _stream())
+        ctx.acts = None
+        flat, views = module._flat_grads(ctx.has_video, audio.device)
+        offs = module._grad_offsets(ctx.has_video, audio.device)
+        _lib.call("mvn_unpack_grads", C.byref(bufs.shape), pg.data_ptr(), flat.data_ptr(), offs.data_ptr(), _stream())
+        module._reduce_grads(flat)
+        return (None, None, None, None, None, *views)
+
+
+class WaveNet(nn.Module):
+    """WaveNet with local (video) conditioning -- see the module docstring.
+
+    Extra, defaulted, keyword-only knob (not in the reference): ``compute_dtype``
+    = "fp32" (exact mode: CUDA-core fp32 arithmetic everywhere, the mode the
+    token-exact decode guarantee is stated for) or "bf16" (tensor-core mode:
+    bf16 activations, fp32 accumulation).  Default: $MOVENET_B200_DTYPE or fp32.
+    """
+
+    def __init__(self, layer_size: int, stack_size: int, input_channels: int, residual_channels: int = 16,
+                 skip_channels: int = 16, context_in_channels: int = 1, *, compute_dtype: Optional[str] = None):
+        super().__init__()
+        self.layer_size = layer_size
+        self.stack_size = stack_size
+        self.input_channels = input_channels
+        self.residual_channels = residual_channels
+        self.skip_channels = skip_channels
+        self.context_in_channels = context_in_channels
+        compute_dtype = compute_dtype or os.environ.get("MOVENET_B200_DTYPE", "fp32")
+        if compute_dtype not in _DTYPES:
+            raise ValueError(f"compute_dtype must be one of {sorted(_DTYPES)}")
+        self.compute_dtype = compute_dtype
+
+        # video encoder: one 64x64 "pixel" linear map per frame (movenet/wavenet.py:94-98)
+        self.video_conv = nn.Conv3d(context_in_channels, residual_channels, kernel_size=VIDEO_KERNEL_SIZE)
+        # learned upsampling 160 -> 1600 -> 16000 -> 160000 frames (movenet/wavenet.py:100-118)
+        sizes = np.geomspace(MAX_VIDEO_FRAMES, MAX_AUDIO_FRAMES,
+                             num=math.ceil(np.log10(MAX_AUDIO_FRAMES / MAX_VIDEO_FRAMES) + 1)).astype(int)
+        self.video_transpose = nn.Sequential(*[
+            nn.ConvTranspose1d(residual_channels, residual_channels,
+                               kernel_size=upsample_kernel_size_solver(a, b, stride=UPSAMPLE_STRIDE),
+                               stride=UPSAMPLE_STRIDE)
+            for a, b in zip(sizes[:-1], sizes[1:])])
+        assert len(self.video_transpose) == 3 and all(m.kernel_size == (10,) for m in self.video_transpose)
+        self.causal_conv = CausalConv1d(input_channels, residual_channels)
+        self.residual_conv_stack = ResidualConvStack(layer_size, stack_size, residual_channels, skip_channels)
+        self.dense_conv = DenseConv(skip_channels, input_channels)
+
+        self._bufs = {}
+        self._ptr_tables = {}
+        self._dp_group = None
+        self._dp_world = 1
+
+    # ------------------------------------------------------------------ reference surface
+    @property
+    def receptive_fields(self) -> int:
+        """sum of dilations + one per stack (movenet/wavenet.py:125-134)."""
+        return sum(self.residual_conv_stack.dilations) + self.residual_conv_stack.stack_size
+
+    def compute_output_size(self, x) -> int:
+        """T - RF + 1, ValueError when the input is too short (movenet/wavenet.py:136-147)."""
+        output_size = int(x.size(2)) - self.receptive_fields + 1
+        if output_size < 1:
+            raise ValueError(
+                "input time steps must be larger than the number of receptive fields. "
+                f"Number of input timesteps = {x.size(2)}, receptive fields = {self.receptive_fields}")
+        return output_size
+
+    def upsample_video(self, video: VideoTensor) -> torch.Tensor:
+        """(B,160,64,64,Cin) -> (B,C,160000) fp32, channels-first (movenet/wavenet.py:149-156).
+
+        Inspection helper: ``forward`` runs the same kernels internally and keeps the
+        result time-major; this copy is detached from autograd.
+        """
+        video = self._check_video(video)
+        B = video.shape[0]
+        shape = self._shape(B, MAX_AUDIO_FRAMES, True, True, False, _lib.F32)
+        bufs = self._buffers_for(shape, video.device)
+        with torch.cuda.device(video.device):
+            self._pack(bufs, self._param_list())
+            acts = torch.empty(bufs.acts_bytes, dtype=torch.uint8, device=video.device)
+            _lib.call("mvn_video_fwd", C.byref(shape), bufs.packed.data_ptr(), video.data_ptr(), acts.data_ptr(), _stream())
+            ctx = torch.empty(B, MAX_AUDIO_FRAMES, self.residual_channels, dtype=torch.float32, device=video.device)
+            _lib.call("mvn_debug_read", C.byref(shape), acts.data_ptr(), 2, 0, ctx.data_ptr(), _stream())
+        out = ctx.permute(0, 2, 1).contiguous()
+        assert out.shape[-1] == MAX_AUDIO_FRAMES
+        return out
+
+    def forward(self, audio: AudioTensor, video: Optional[VideoTensor] = None, global_features=None,
+                output_unnormalized: bool = True, remove_last: bool = True):
+        """movenet/wavenet.py:158-191.  NOTE the reference's flag polarity: the default
+        (``output_unnormalized=True``) returns softmax PROBABILITIES over dim 1, raw logits come
+        back only for ``output_unnormalized=False``.  ``global_features`` is unused there too."""
+        audio = self._check_audio(audio)
+        if video is not None:
+            video = self._check_video(video)
+            assert audio.shape[2] == MAX_AUDIO_FRAMES and video.shape[0] == audio.shape[0], (
+                "expected video and audio tensors to have equal sizes, found "
+                f"{(video.shape[0], self.residual_channels, MAX_AUDIO_FRAMES)}, "
+                f"{(audio.shape[0], self.residual_channels, audio.shape[2])}")
+        self.compute_output_size(audio)
+        with torch.cuda.device(audio.device):
+            return _WaveNetFunction.apply(self, audio, video, bool(remove_last), not output_unnormalized,
+                                          *self._param_list())
+
+    @torch.no_grad()
+    def generate(self, audio: AudioTensor, video: Optional[VideoTensor] = None, global_features=None,
+                 n_samples: Optional[int] = None, temperature: float = 1.0):
+        """movenet/wavenet.py:193-239: keep the first RF columns of ``audio`` as the prompt and
+        generate up to ``n_samples`` TOTAL columns; returns the (B, A, n) one-hot tensor.
+
+        The reference recomputes an RF-long window per sample; this runs the cached decoder
+        (per-layer dilation queues, O(layers) per sample).  With stack_size >= 2 the two are the
+        same function of the prompt.  With stack_size == 1 the reference's zero-padded window edge
+        leaks into its output while the cache evaluates the true causal model, so
+        logits differ by O(1e-5..1e-3) there.  Only ``temperature == 0`` (argmax) is deterministic
+        in the reference; ``temperature > 0`` draws from softmax(probs / temperature).
+        """
+        from .decode import cached_generate
+        self.eval()
+        return cached_generate(self, audio, video, n_samples, temperature)
+
+    # ------------------------------------------------------------------ data parallel
+    def enable_data_parallel(self, process_group=None):
+        """Average gradients over ``process_group`` with one all-reduce of the flat gradient
+        buffer per backward (the role DistributedDataParallel plays at movenet/trainer.py:230-234)."""
+        import torch.distributed as dist
+        self._dp_group = process_group if process_group is not None else dist.group.WORLD
+        self._dp_world = dist.get_world_size(self._dp_group)
+        return self
+
+    def _reduce_grads(self, flat):
+        if self._dp_world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self._dp_group)
+            flat.mul_(1.0 / self._dp_world)
+
+    # ------------------------------------------------------------------ plumbing
+    def _param_list(self):
+        """parameters in state_dict order == the C ABI's MVN_PARAM_* order"""
+        return [p for _, p in self.named_parameters()]
+
+    def _check_audio(self, audio):
+        if not isinstance(audio, torch.Tensor) or audio.dim() != 3:
+            raise ValueError("audio must be a (batch, channels, frames) tensor")
+        if not audio.is_cuda:
+            raise RuntimeError("movenet_b200.WaveNet runs on CUDA tensors only (there is no CPU path)")
+        if audio.shape[1] != self.input_channels:
+            raise RuntimeError(f"expected {self.input_channels} audio channels, found {audio.shape[1]}")
+        if audio.requires_grad:
+            raise RuntimeError("gradients with respect to the audio input are not implemented")
+        return audio.detach().float().contiguous()
+
+    def _check_video(self, video):
+        if not video.is_cuda:
+            raise RuntimeError("movenet_b200.WaveNet runs on CUDA tensors only (there is no CPU path)")
+        assert video.dim() == 5 and tuple(video.shape[1:]) == (MAX_VIDEO_FRAMES, 64, 64, self.context_in_channels), (
+            f"expected video of shape (B, {MAX_VIDEO_FRAMES}, 64, 64, {self.context_in_channels}), found {tuple(video.shape)}")
+        return video.detach().float().contiguous()
+
+    def _shape(self, B, T, has_video, remove_last, output_logits, act_dtype=None):
+        return _lib.Shape(self.layer_size, self.stack_size, self.input_channels, self.residual_channels,
+                          self.skip_channels, self.context_in_channels, B, T, int(has_video),
+                          _DTYPES[self.compute_dtype] if act_dtype is None else act_dtype,
+                          int(remove_last), int(output_logits))
+
+    def _buffers_for(self, shape, device):
+        key = (shape.key(), str(device))
+        bufs = self._bufs.get(key)
+        if bufs is None:
+            if len(self._bufs) >= 8:          # bound the cache: drop the oldest geometry
+                self._bufs.pop(next(iter(self._bufs)))
+            bufs = self._bufs[key] = _Buffers(shape, device)
+        return bufs
+
+    def _buffers(self, audio, has_video, remove_last, output_logits):
+        shape = self._shape(audio.shape[0], audio.shape[2], has_video, remove_last, output_logits)
+        return self._buffers_for(shape, audio.device)
+
+    def _pack(self, bufs, params):
+        """re-layout the reference parameters for the kernels (weights change every optimizer step)"""
+        ptrs = tuple(p.data_ptr() for p in params)
+        key = ("w", str(bufs.device))
+        cached = self._ptr_tables.get(key)
+        if cached is None or cached[0] != ptrs:
+            for p in params:
+                if p.dtype != torch.float32 or not p.is_contiguous() or p.device != bufs.device:
+                    raise RuntimeError("movenet_b200.WaveNet parameters must be contiguous fp32 tensors on the input's device")
+            table = torch.tensor(ptrs, dtype=torch.int64).to(bufs.device)
+            cached = self._ptr_tables[key] = (ptrs, table)
+        _lib.call("mvn_pack_weights", C.byref(bufs.shape), cached[1].data_ptr(), bufs.packed.data_ptr(), _stream())
+
+    def _grad_layout(self, has_video):
+        """element offset of every parameter's gradient in the flat buffer (-1: no gradient, as in the
+        reference: video/context parameters without video, and the last layer's conv_residual whose
+        output is discarded, movenet/modules.py:125-130)."""
+        last = f"residual_conv_stack.conv_layers.{self.layer_size * self.stack_size - 1}.conv_residual."
+        offsets, off = [], 0
+        for name, p in self.named_parameters():
+            no_grad = (not p.requires_grad or name.startswith(last)
+                       or (not has_video and (name.startswith("video_") or ".context_conv_" in name)))
+            if no_grad:
+                offsets.append(-1)
+            else:
+                offsets.append(off)
+                off += (p.numel() + 3) // 4 * 4
+        return offsets, off
+
+    def _grad_offsets(self, has_video, device):
+        key = ("g", has_video, str(device))
+        if key not in self._ptr_tables:
+            offsets, _ = self._grad_layout(has_video)
+            self._ptr_tables[key] = torch.tensor(offsets, dtype=torch.int64).to(device)
+        return self._ptr_tables[key]
+
+    def _flat_grads(self, has_video, device):
+        offsets, total = self._grad_layout(has_video)
+        flat = torch.empty(total, dtype=torch.float32, device=device)
+        views = [None if o < 0 else flat[o:o + p.numel()].view_as(p)
+                 for o, (_, p) in zip(offsets, self.named_parameters())]
+        return flat, views

