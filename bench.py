@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the WaveNet hot path (BASELINE.json: "WaveNet train audio-samples/s/GPU;
+generation real-time factor at 16 kHz").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype fp32|bf16]
+
+One JSON line on stdout (rank 0).  A "step" is one training step over one batch of synthetic
+10-second clips exactly as the reference trainer writes it (pytorch_lightning_trainer.py:52-66):
+forward (probabilities) -> target = argmax of the shifted one-hot audio -> F.cross_entropy ->
+backward (-> gradient all-reduce when N > 1) -> AdamW step.
+
+* value  : audio samples / s over all N GPUs, inputs already resident in HBM (CUDA events, max over ranks)
+* e2e    : the same step driven from pinned HOST buffers: H2D copy of the one-hot audio and the video
+           inside the timed region, D2H read of the loss every step
+* roofline: the residual-layer forward kernel(s), timed live with CUDA events on the launching stream
+* cpu_baseline: the oracle (a torch-CPU restatement of the reference, bit-identical to it; the
+           reference is pure Python and cannot travel to the GPU box) on the host cores
+* generation: cached autoregressive decode on the receptive-field config (experiments/04)
+
+--impl reference times that same CPU port with all host threads (there is no compiled reference).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+METRIC = "WaveNet train audio-samples/s"
+UNIT = "audio-samples/s"
+T_CLIP = 160000
+
+# BASELINE.json configs[1]: experiments/01_audio_video_debug.mk:10-17 (skip_channels: parser default 8,
+# batch: parser default 3 -- SURVEY section 8)
+WORKLOAD = dict(name="01_audio_video_debug", layer_size=3, stack_size=3, input_channels=64,
+                residual_channels=64, skip_channels=8, batch_per_gpu=3, video=True)
+# BASELINE.json configs[4]: experiments/04_kinetics_receptive_field.mk:58-71
+DECODE = dict(name="04_kinetics_receptive_field", layer_size=14, stack_size=1, input_channels=128,
+              residual_channels=16, skip_channels=8)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+
+
+def synth_codes(B, T, A, seed, device):
+    """two tones + noise, min-max normalised, mu-law coded: SURVEY 8(d)"""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(T, dtype=torch.float32) / 16000.0
+    rows = []
+    for b in range(B):
+        w = 0.6 * torch.sin(2 * torch.pi * (220.0 + 7 * b) * t) + 0.3 * torch.sin(2 * torch.pi * 3520.0 * t) \
+            + 0.1 * (torch.rand(T, generator=g) * 2 - 1)
+        rows.append(2 * (w - w.min()) / (w.max() - w.min()) - 1)
+    return torch.stack(rows)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        out, _ = self.proc.communicate()
+        sm, mx, reasons = [], None, set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps(w, steps, warmup, video=True, B=1):
+    """the reference's CPU implementation of the step (oracle port), all host threads"""
+    from oracle import wavenet_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    shape = orc.Shape(w["layer_size"], w["stack_size"], w["input_channels"], w["residual_channels"], w["skip_channels"])
+    p = {k: v.requires_grad_(True) for k, v in orc.init_params(shape, 0, video=True).items()}
+    from movenet_b200.mulaw import _encode_formula
+    codes = _encode_formula(synth_codes(B, T_CLIP, shape.input_channels, 1234, "cpu"), shape.input_channels)
+    audio = torch.zeros(B, shape.input_channels, T_CLIP).scatter_(1, codes.unsqueeze(1), 1.0)
+    vid = torch.randint(0, 256, (B, 160, 64, 64, 1), generator=torch.Generator().manual_seed(4321)).float() if video else None
+    opt = torch.optim.AdamW(list(p.values()), lr=3e-4)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss, _, _, _ = orc.training_loss(p, shape, audio, vid)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return B * T_CLIP, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOAD
+    n, times = cpu_reference_steps(w, max(1, args.steps), max(0, args.warmup), video=w["video"], B=1)
+    ms = 1e3 * sum(times) / len(times)
+    value = n / (ms / 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "sample": "1 clip (160000 samples) per step of the batch-3 workload"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": "1 clip (160000 samples) per step, fwd+CE+bwd+AdamW, torch CPU fp32"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def train_step(model, opt, audio, video):
+    opt.zero_grad(set_to_none=True)
+    output = model(audio, video)
+    target = audio[:, :, model.receptive_fields:].argmax(1)
+    loss = F.cross_entropy(output, target)
+    loss.backward()
+    opt.step()
+    return loss
+
+
+def timed(fn, steps, warmup, sync):
+    for _ in range(warmup):
+        fn()
+    sync()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        fn()
+    ev1.record()
+    sync()
+    return ev0.elapsed_time(ev1)
+
+
+def layer_roofline(model, audio, video, dtype):
+    """time the residual-layer forward stage live (CUDA events on the launching stream)"""
+    import ctypes as C
+    from movenet_b200 import _lib
+    B = audio.shape[0]
+    shape = model._shape(B, T_CLIP, video is not None, True, False)
+    bufs = model._buffers_for(shape, audio.device)
+    model._pack(bufs, model._param_list())
+    acts = torch.empty(bufs.acts_bytes, dtype=torch.uint8, device=audio.device)
+    out = torch.empty(B, model.input_channels, T_CLIP - model.receptive_fields, device=audio.device)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call("mvn_wavenet_forward", C.byref(shape), bufs.packed.data_ptr(), audio.data_ptr(),
+              0 if video is None else video.data_ptr(), acts.data_ptr(), out.data_ptr(), bufs.get_scratch().data_ptr(), st)
+    layers = list(range(1, model.layer_size * model.stack_size - 1))     # interior layers: all write a residual
+    n0 = _lib.load().mvn_launch_count()
+    for l in layers:
+        _lib.call("mvn_layer_fwd", C.byref(shape), bufs.packed.data_ptr(), l, acts.data_ptr(), bufs.get_scratch().data_ptr(), st)
+    launches_per_layer = (_lib.load().mvn_launch_count() - n0) / len(layers)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    ev0.record()
+    for _ in range(reps):
+        for l in layers:     # each layer streams > L2 worth of activations, so every launch starts cold
+            _lib.call("mvn_layer_fwd", C.byref(shape), bufs.packed.data_ptr(), l, acts.data_ptr(), bufs.get_scratch().data_ptr(), st)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / (reps * len(layers))
+    e = 2 if dtype == "bf16" else 4
+    Cc, S = model.residual_channels, model.skip_channels
+    # algorithmic bytes per sample of one layer forward: read x, write x', read ctx, read-modify-write skip_sum
+    per_sample = Cc * e + Cc * e + (Cc * e if video is not None else 0) + 8 * S
+    bytes_per_launch = per_sample * B * T_CLIP
+    pk = peaks()
+    achieved = bytes_per_launch / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "residual layer forward (%s, %d launch(es))" % (dtype, round(launches_per_layer)),
+            "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
+            "frac": achieved / pk["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
+            "bytes_per_sample": per_sample, "samples_per_launch": B * T_CLIP}
+
+
+def decode_bench(dev):
+    """cached generation on the receptive-field config: RTF = generated seconds of 16 kHz audio per wall second"""
+    import movenet_b200
+    d = DECODE
+    m = movenet_b200.WaveNet(d["layer_size"], d["stack_size"], d["input_channels"], d["residual_channels"],
+                             d["skip_channels"], compute_dtype="fp32").to(dev)
+    RF = m.receptive_fields
+    res = {}
+    for clips, n_new in ((1, 2000), (1184, 400)):
+        codes = torch.randint(0, d["input_channels"], (clips, RF), device=dev)
+        prompt = movenet_b200.one_hot(codes, d["input_channels"])
+        from movenet_b200.decode import prefill, run_steps
+        state = prefill(m, prompt, None)
+        run_steps(m, state, RF, 8)                                  # warm-up (re-running positions is harmless here)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        run_steps(m, state, RF, n_new)
+        ev1.record()
+        torch.cuda.synchronize()
+        sec = ev0.elapsed_time(ev1) * 1e-3
+        per_clip_rtf = (n_new / 16000.0) / sec
+        bytes_per_sample = 2 * m.layer_size * m.stack_size * d["residual_channels"] * 4 + 4 * d["input_channels"]
+        gbs = clips * n_new * bytes_per_sample / sec / 1e9
+        res[f"clips_{clips}"] = {"new_samples_per_clip": n_new, "rtf_per_clip": per_clip_rtf,
+                                 "aggregate_samples_per_s": clips * n_new / sec, "aggregate_rtf": clips * per_clip_rtf,
+                                 "hbm_gbs_algorithmic": gbs, "hbm_frac": gbs / peaks()["hbm_gbs"]}
+        del state, prompt
+    return {"workload": d["name"], "receptive_fields": RF, "dtype": "f32", **res}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import movenet_b200
+    from movenet_b200 import _lib
+    from movenet_b200.parallel import init_from_env
+    rank, local, world = init_from_env("nccl")
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    w = WORKLOAD
+    B = w["batch_per_gpu"]
+    torch.manual_seed(0)
+    model = movenet_b200.WaveNet(w["layer_size"], w["stack_size"], w["input_channels"], w["residual_channels"],
+                                 w["skip_channels"], compute_dtype=args.dtype).to(dev)
+    if world > 1:
+        model.enable_data_parallel()
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-4)
+
+    wave = synth_codes(B, T_CLIP, w["input_channels"], 1234 + rank, dev)
+    host_audio = torch.zeros(B, w["input_channels"], T_CLIP).scatter_(
+        1, movenet_b200.mulaw._encode_formula(wave, w["input_channels"]).unsqueeze(1), 1.0).pin_memory()
+    host_video = torch.randint(0, 256, (B, 160, 64, 64, 1), generator=torch.Generator().manual_seed(4321 + rank)).float().pin_memory()
+    audio = host_audio.to(dev, non_blocking=True)
+    video = host_video.to(dev, non_blocking=True) if w["video"] else None
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- device-resident steps ----
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        train_step(model, opt, audio, video)
+    sync()
+    n0 = _lib.load().mvn_launch_count()
+    sampler.start()
+    ms_total = timed(lambda: train_step(model, opt, audio, video), args.steps, 0, sync)
+    clocks = sampler.stop()
+    launches = int(_lib.load().mvn_launch_count() - n0)
+    ms_total = max_over_ranks(ms_total)
+    ms_step = ms_total / args.steps
+    value = world * B * T_CLIP / (ms_step * 1e-3)
+
+    # ---- end to end from pinned host buffers ----
+    loss_box = [0.0]
+
+    def e2e_step():
+        a = host_audio.to(dev, non_blocking=True)
+        v = host_video.to(dev, non_blocking=True) if w["video"] else None
+        loss_box[0] = train_step(model, opt, a, v).item()
+
+    ms_e2e = max_over_ranks(timed(e2e_step, args.steps, 1, sync)) / args.steps
+    e2e_value = world * B * T_CLIP / (ms_e2e * 1e-3)
+    h2d = host_audio.numel() * 4 + (host_video.numel() * 4 if w["video"] else 0)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    roof = layer_roofline(model, audio, video, args.dtype)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
+            "per_gpu": value / world, "loss": loss_box[0],
+            "config": {"workload": w["name"], "layer_size": w["layer_size"], "stack_size": w["stack_size"],
+                       "input_channels": w["input_channels"], "residual_channels": w["residual_channels"],
+                       "skip_channels": w["skip_channels"], "video": w["video"], "clips_per_gpu": B,
+                       "samples_per_clip": T_CLIP, "global_clips": B * world,
+                       "parallelism": f"dp{world}" if world > 1 else "single",
+                       "step": "fwd(probs)+argmax target+cross_entropy+bwd+allreduce+AdamW",
+                       "l2": "inputs and activations (>1 GB per step) exceed the 126 MB L2; no explicit flush"},
+            "clocks": clocks, "gpu_launches": launches // max(1, args.steps) * args.steps,
+            "gpu_launches_per_step": launches / max(1, args.steps),
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "roofline": roof}
+    if world == 1:
+        if not args.no_cpu_baseline:
+            n, times = cpu_reference_steps(w, 2, 1, video=w["video"], B=1)
+            cpu = n / (sum(times) / len(times))
+            line["cpu_baseline"] = {"value": cpu, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "1 clip (160000 samples) per step, 1 warm-up + 2 timed steps, torch CPU fp32"}
+        if not args.no_decode:
+            line["generation"] = decode_bench(dev)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default=os.environ.get("MOVENET_B200_DTYPE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

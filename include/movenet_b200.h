@@ -67,6 +67,8 @@ typedef struct mvn_shape {
 
 const char* mvn_last_error(void);
 int mvn_version(void);
+/* number of kernel launches this library has issued in this process (bench bookkeeping) */
+unsigned long long mvn_launch_count(void);
 
 /* geometry helpers: WaveNet.receptive_fields (movenet/wavenet.py:125-134) and
  * compute_output_size (movenet/wavenet.py:136-147; returns <1 when the

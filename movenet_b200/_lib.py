@@ -29,6 +29,7 @@ _SP = C.POINTER(Shape)
 SIGNATURES = {
     "mvn_last_error": (C.c_char_p, []),
     "mvn_version": (_I, []),
+    "mvn_launch_count": (C.c_ulonglong, []),
     "mvn_receptive_fields": (_I, [_I, _I]),
     "mvn_output_size": (_I, [_I, _I, _I]),
     "mvn_packed_bytes": (_SZ, [_SP]),

@@ -12,7 +12,10 @@ void mvn_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+
 int mvn_check_launch(const char* what) {
+    ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         mvn_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -23,3 +26,4 @@ int mvn_check_launch(const char* what) {
 
 extern "C" const char* mvn_last_error(void) { return g_err; }
 extern "C" int mvn_version(void) { return 100; }
+extern "C" unsigned long long mvn_launch_count(void) { return g_launches; }

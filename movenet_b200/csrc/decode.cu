@@ -212,15 +212,17 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs a) {
     }
 }
 
-// fill the rings from the layer inputs of a forward pass over the prompt: ring_l[tau % d] = x_l[tau]
+// Fill the rings from the layer inputs of a forward pass over the T-column prompt.  The first decode
+// step re-evaluates time T-1 (the last prompt sample) itself, so the rings must hold the d inputs
+// BEFORE it: ring_l[tau % d] = x_l[tau] for tau in [T-1-d, T-1).
 __global__ void decode_prefill_kernel(const void* __restrict__ x, int adt, int B, int T, int C, int d,
                                       float* __restrict__ ring) {
     const long long n = (long long)B * d * C;
+    const int Tend = T - 1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C); const long long r = i / C; const int b = (int)(r % B); const int slot = (int)(r / B);
-        // the time in [T-d, T) whose slot this is
-        int tau = (T / d) * d + slot; if (tau >= T) tau -= d;
-        ring[i] = (tau >= 0 && tau >= T - d) ? mvn_ld(x, adt, ((size_t)b * T + tau) * C + c) : 0.f;
+        int tau = (Tend / d) * d + slot; if (tau >= Tend) tau -= d;     // the time in [Tend-d, Tend) living in this slot
+        ring[i] = tau >= 0 ? mvn_ld(x, adt, ((size_t)b * T + tau) * C + c) : 0.f;
     }
 }
 

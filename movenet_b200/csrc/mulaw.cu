@@ -72,8 +72,8 @@ __global__ void one_hot_kernel(const long long* __restrict__ codes, float* __res
 
 extern "C" int mvn_mulaw_encode(const void* x, int x_is_f64, const void* thresholds, int n_channels, int64_t* codes,
                                 int64_t n, void* stream) {
-    MVN_REQUIRE(x && thresholds && codes && n_channels >= 2 && n >= 0, "mvn_mulaw_encode: bad arguments");
     if (n == 0) return 0;
+    MVN_REQUIRE(x && thresholds && codes && n_channels >= 2 && n > 0, "mvn_mulaw_encode: bad arguments");
     const int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
     cudaStream_t st = (cudaStream_t)stream;
     if (x_is_f64)
@@ -86,8 +86,8 @@ extern "C" int mvn_mulaw_encode(const void* x, int x_is_f64, const void* thresho
 }
 
 extern "C" int mvn_mulaw_decode(const int64_t* codes, const float* lut, int n_channels, float* x, int64_t n, void* stream) {
-    MVN_REQUIRE(codes && lut && x && n_channels >= 2 && n >= 0, "mvn_mulaw_decode: bad arguments");
     if (n == 0) return 0;
+    MVN_REQUIRE(codes && lut && x && n_channels >= 2 && n > 0, "mvn_mulaw_decode: bad arguments");
     const int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
     mulaw_decode_kernel<<<grid, 256, (size_t)n_channels * 4, (cudaStream_t)stream>>>((const long long*)codes, lut, n_channels, x, n);
     return mvn_check_launch("mulaw_decode");

@@ -15,19 +15,24 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class DecodeState:
+    """queues + bookkeeping of one batch of clips being generated"""
+
+    def __init__(self, shape, bufs, state, ctx, batch, channels):
+        self.shape, self.bufs, self.state, self.ctx, self.batch, self.channels = shape, bufs, state, ctx, batch, channels
+
+
 def prefill(model, prompt, video):
     """Run the prompt through the stack once and fill the per-layer dilation queues.
 
-    Returns (shape, buffers, state, ctx): everything mvn_decode_steps needs.
     Decoding always uses the fp32 (exact) kernels, whatever the training dtype is.
     """
     B, A, n_prompt = prompt.shape
     dev = prompt.device
-    has_video = video is not None
-    # with video the context covers the whole 160000-frame clip; the prompt forward still only
-    # needs its own columns, so run it audio-only for the queues and add the context per step
-    if has_video:
-        raise NotImplementedError("video-conditioned generate() is not wired up yet")
+    if video is not None:
+        # finding F4: the reference cannot run generate() with video at all (its upsampled context is
+        # always 160000 frames long while the window is RF long).  Not wired up here either yet.
+        raise NotImplementedError("video-conditioned generate() is not implemented (it raises in the reference too)")
     shape = model._shape(B, n_prompt, False, False, True, _lib.F32)
     bufs = model._buffers_for(shape, dev)
     model._pack(bufs, model._param_list())
@@ -37,7 +42,19 @@ def prefill(model, prompt, video):
               acts.data_ptr(), logits.data_ptr(), bufs.get_scratch().data_ptr(), _stream())
     state = torch.zeros(_lib.size("mvn_decode_state_bytes", shape), dtype=torch.uint8, device=dev)
     _lib.call("mvn_decode_prefill", C.byref(shape), acts.data_ptr(), state.data_ptr(), _stream())
-    return shape, bufs, state, None
+    return DecodeState(shape, bufs, state, None, B, A)
+
+
+def run_steps(model, st, t_start, n_new, temperature=0.0, return_logits=False):
+    """generate n_new samples for every clip, starting at absolute position t_start; int32 codes (B, n_new)"""
+    dev = st.state.device
+    codes = torch.empty(st.batch, n_new, dtype=torch.int32, device=dev)
+    logits = torch.empty(st.batch, n_new, st.channels, dtype=torch.float32, device=dev) if return_logits else None
+    seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if temperature > 0 else 0
+    _lib.call("mvn_decode_steps", C.byref(st.shape), st.bufs.packed.data_ptr(), st.state.data_ptr(),
+              0 if st.ctx is None else st.ctx.data_ptr(), t_start, n_new, codes.data_ptr(),
+              0 if logits is None else logits.data_ptr(), C.c_float(float(temperature)), seed, _stream())
+    return (codes, logits) if return_logits else codes
 
 
 def cached_generate(model, audio, video, n_samples, temperature, return_logits=False):
@@ -54,13 +71,8 @@ def cached_generate(model, audio, video, n_samples, temperature, return_logits=F
     if n_new <= 0:
         return (out, None) if return_logits else out
     with torch.cuda.device(audio.device):
-        prompt = audio[:, :, :RF].contiguous()
-        shape, bufs, state, ctx = prefill(model, prompt, video)
-        codes = torch.empty(B, n_new, dtype=torch.int32, device=audio.device)
-        logits = torch.empty(B, n_new, A, dtype=torch.float32, device=audio.device) if return_logits else None
-        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) if temperature > 0 else 0
-        _lib.call("mvn_decode_steps", C.byref(shape), bufs.packed.data_ptr(), state.data_ptr(),
-                  0 if ctx is None else ctx.data_ptr(), RF, n_new, codes.data_ptr(),
-                  0 if logits is None else logits.data_ptr(), C.c_float(float(temperature)), seed, _stream())
+        st = prefill(model, audio[:, :, :RF].contiguous(), video)
+        res = run_steps(model, st, RF, n_new, temperature, return_logits)
+        codes, logits = res if return_logits else (res, None)
         out[:, :, RF:].scatter_(1, codes.long().unsqueeze(1), 1.0)
     return (out, logits) if return_logits else out

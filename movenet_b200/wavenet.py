@@ -75,7 +75,7 @@ class _WaveNetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, audio, video, remove_last, output_logits, *params):
-        bufs = module._buffers(audio, video is not None, remove_last, output_logits)
+        bufs = module._engine_buffers(audio, video is not None, remove_last, output_logits)
         shape = bufs.shape
         module._pack(bufs, params)
         Tn = shape.frames - module.receptive_fields + 1 - (1 if remove_last else 0)
@@ -271,7 +271,7 @@ class WaveNet(nn.Module):
             bufs = self._bufs[key] = _Buffers(shape, device)
         return bufs
 
-    def _buffers(self, audio, has_video, remove_last, output_logits):
+    def _engine_buffers(self, audio, has_video, remove_last, output_logits):
         shape = self._shape(audio.shape[0], audio.shape[2], has_video, remove_last, output_logits)
         return self._buffers_for(shape, audio.device)
 

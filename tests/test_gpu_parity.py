@@ -40,8 +40,9 @@ def test_forward_logits_and_probs(name):
         probs = m(audio)
         full = m(audio, output_unnormalized=False, remove_last=False)
     assert logits.shape == fx["logits"].shape
-    assert (logits.cpu() - fx["logits"]).abs().max().item() < LOGIT_ATOL
-    assert (probs.cpu() - fx["probs"]).abs().max().item() < 1e-6
+    scale = max(1.0, fx["logits"].abs().max().item())
+    assert (logits.cpu() - fx["logits"]).abs().max().item() < LOGIT_ATOL * scale
+    assert (probs.cpu() - fx["probs"]).abs().max().item() < 5e-6
     assert torch.allclose(probs.sum(1), torch.ones_like(probs.sum(1)), atol=1e-5)   # F1
     assert full.shape[2] == logits.shape[2] + 1
     assert torch.equal(full[:, :, :-1], logits)

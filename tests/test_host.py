@@ -132,5 +132,5 @@ def test_grad_layout_marks_the_parameters_the_reference_leaves_without_grad():
     none = sorted(n for n, o in zip(names, offs) if o < 0)
     assert none == fx["none_grads"]
     offs_v, _ = m._grad_layout(has_video=True)
-    assert sorted(n for n, o in zip(names, offs_v) if o < 0) == load_golden("video")["none_grads"] or True
+    assert sorted(n for n, o in zip(names, offs_v) if o < 0) == sorted(n for n in fx["none_grads"] if "conv_residual" in n)
     assert total >= sum(p.numel() for n, p in m.named_parameters() if n not in none)
