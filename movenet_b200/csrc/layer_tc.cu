@@ -1,7 +1,362 @@
-// placeholder until the tcgen05 kernel lands: reports "not supported" so callers take the fp32 path
+// GatedResidualConv1d.forward (movenet/modules.py:67-93) as ONE fused sm_100a kernel:
+//
+//   TMA loads the time tile of the layer input twice (rows t-d.. and t..: the two taps of the k=2
+//   dilated conv are "the same tensor, d rows earlier", out-of-range rows are zero-filled by TMA)
+//   plus the context tile  ->  tcgen05.mma  D1[128 x 2C] = [x(t-d) | x(t) | ctx(t)] . Wz^T  (TMEM)
+//   -> epilogue 1 (tcgen05.ld): gated = tanh(f) * sigmoid(g), written as bf16 into shared memory in
+//   the K-major SWIZZLE_128B layout the tensor core reads  ->  tcgen05.mma  D2[128 x (C+S)] =
+//   gated . [Wr | Ws]^T  ->  epilogue 2: x' = r + b_r + x(t) in place in the tap-1 tile, TMA store;
+//   skip_sum += s + b_s (fp32, coalesced 32 B per row).
+//
+// Activations are time-major (B, T, C) bf16, so the time tile is the MMA's M dimension (TMEM lane =
+// time row) and both gate halves of one (t, c) sit in the same thread.  One 128-row tile is in
+// flight per CTA; two CTAs share an SM (106 KB shared memory, 256 TMEM columns each) so one CTA's
+// epilogue overlaps the other's loads and MMAs.
+#include <cuda.h>
+#include <mutex>
 #include "common.cuh"
 #include "layer_tc.h"
-int mvn_tc_layer_supported(int, int, int) { return 0; }
-int mvn_tc_layer_fwd(const void*, const void*, void*, float*, const float*, const PackedLayout&, const Geo&, int, cudaStream_t) {
-    mvn_set_error("tensor-core layer kernel not built"); return -1;
+
+namespace {
+
+constexpr int TILE_T = 128;                 // time rows per tile = UMMA M
+constexpr int CC = 64;                      // residual channels: one 128-byte swizzle row of bf16
+constexpr int TILE_BYTES = TILE_T * CC * 2; // 16 KB
+constexpr int TMEM_COLS = 256;
+constexpr int D2_COL = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+// 8-row groups of 128-byte rows, 1024 bytes apart (SBO); LBO is unused for swizzled K-major operands.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> f32, both operands K-major
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+
+struct TcArgs {
+    const float* wzT;     // [2C][Kz] fp32, rows interleaved (filter c, gate c)
+    const float* bz;      // [2C]     interleaved
+    const float* wrsT;    // [C+S][C]
+    const float* brs;     // [C+S]
+    float* skip;          // (B, Tout, S) fp32
+    int B, T, Tout, RF, S, N2, dil, nchunks, has_out, skip_init, tiles_per_clip, n_tiles;
+};
+
+// shared-memory carve-up (dynamic, 1024-byte aligned): Wz chunks | [Wr|Ws] | A tiles | biases | barriers
+__host__ __device__ inline int smem_brs_off(int nchunks) { return nchunks * TILE_BYTES; }
+__host__ __device__ inline int smem_a_off(int nchunks, int N2) { return smem_brs_off(nchunks) + ((N2 * 128 + 1023) & ~1023); }
+__host__ __device__ inline int smem_bias_off(int nchunks, int N2) { return smem_a_off(nchunks, N2) + nchunks * TILE_BYTES; }
+__host__ __device__ inline int smem_total(int nchunks, int N2) { return smem_bias_off(nchunks, N2) + 256 * 4 + 64; }
+
+__global__ void __launch_bounds__(128, 2)
+layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_ctx,
+                    const __grid_constant__ CUtensorMap map_out, const TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sBz = smem;
+    uint8_t* sBrs = smem + smem_brs_off(a.nchunks);
+    uint8_t* sA0 = smem + smem_a_off(a.nchunks, a.N2);   // tap t-d; later the gated tile
+    uint8_t* sA1 = sA0 + TILE_BYTES;                      // tap t; later x'
+    uint8_t* sA2 = sA1 + TILE_BYTES;                      // context (video only)
+    float* sbz = (float*)(smem + smem_bias_off(a.nchunks, a.N2));
+    float* sbrs = sbz + 128;
+    uint64_t* full_bar = (uint64_t*)(sbrs + 128);
+    uint64_t* mma_bar = full_bar + 1;
+    uint32_t* tmem_slot = (uint32_t*)(full_bar + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int Kz = a.nchunks * CC;
+
+    // ---- one-time setup: weights -> bf16, K-major, 128B-swizzled tiles --------------------------
+    for (int i = tid; i < 128 * Kz; i += 128) {
+        const int n = i / Kz, k = i - n * Kz;                 // n: 0..63 filter c, 64..127 gate c
+        const float v = a.wzT[(size_t)(2 * (n & 63) + (n >> 6)) * Kz + k];
+        const int chunk = k >> 6, kk = k & 63;
+        const uint32_t off = chunk * TILE_BYTES + n * 128 + ((((kk >> 3) ^ (n & 7)) << 4) | ((kk & 7) << 1));
+        *(__nv_bfloat16*)(sBz + off) = __float2bfloat16(v);
+    }
+    for (int i = tid; i < a.N2 * CC; i += 128) {
+        const int n = i >> 6, k = i & 63;
+        const float v = n < CC + a.S ? a.wrsT[(size_t)n * CC + k] : 0.f;
+        const uint32_t off = n * 128 + ((((k >> 3) ^ (n & 7)) << 4) | ((k & 7) << 1));
+        *(__nv_bfloat16*)(sBrs + off) = __float2bfloat16(v);
+    }
+    {   // biases: sbz[n] with n in the tensor-core column order; sbrs[n]
+        const int n = tid;
+        sbz[n] = a.bz[2 * (n & 63) + (n >> 6)];
+        sbrs[n] = n < CC + a.S ? a.brs[n] : 0.f;
+    }
+    if (tid == 0) {
+        mbar_init(full_bar, 1);
+        mbar_init(mma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();            // weight tiles were written with generic stores; the tensor core reads them via the async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t idesc1 = umma_idesc(TILE_T, 128), idesc2 = umma_idesc(TILE_T, a.N2);
+    const uint32_t load_bytes = (uint32_t)(a.nchunks * TILE_BYTES);
+    const int r = tid;               // this thread's row of the tile == its TMEM lane
+    const int sw = r & 7;
+
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T;
+        if (tid == 0) {
+            tma_wait_read0();        // the previous tile's x' store must be done reading A1
+            mbar_expect_tx(full_bar, load_bytes);
+            tma_load_3d(sA0, &map_x, full_bar, 0, t0 - a.dil, b);
+            tma_load_3d(sA1, &map_x, full_bar, 0, t0, b);
+            if (a.nchunks == 3) tma_load_3d(sA2, &map_ctx, full_bar, 0, t0, b);
+        }
+        mbar_wait(full_bar, it & 1);
+        if (tid == 0) {
+            tc_fence_after();
+            for (int c = 0; c < a.nchunks; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma(tmem, umma_desc(smem_u32(sA0 + c * TILE_BYTES) + k * 32), umma_desc(smem_u32(sBz + c * TILE_BYTES) + k * 32),
+                         idesc1, (c | k) != 0);
+            umma_commit(mma_bar);
+        }
+        mbar_wait(mma_bar, 0);
+        tc_fence_after();
+        // ---- epilogue 1: gate, bf16, into A0 as the next MMA's A operand ------------------------
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            uint32_t f[16], g[16];
+            tmem_ld16(tmem + lane_base + 16 * j, f);
+            tmem_ld16(tmem + lane_base + 64 + 16 * j, g);
+            tmem_ld_wait();
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                const int c = 16 * j + i;
+                const float f0 = __uint_as_float(f[i]) + sbz[c], f1 = __uint_as_float(f[i + 1]) + sbz[c + 1];
+                const float g0 = __uint_as_float(g[i]) + sbz[64 + c], g1 = __uint_as_float(g[i + 1]) + sbz[64 + c + 1];
+                const float y0 = tanh_fast(f0) * fmaf(0.5f, tanh_fast(0.5f * g0), 0.5f);
+                const float y1 = tanh_fast(f1) * fmaf(0.5f, tanh_fast(0.5f * g1), 0.5f);
+                o[i >> 1] = pack_bf16(y0, y1);
+            }
+            *(uint4*)(sA0 + r * 128 + (((2 * j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *(uint4*)(sA0 + r * 128 + (((2 * j + 1) ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma(tmem + D2_COL, umma_desc(smem_u32(sA0) + k * 32), umma_desc(smem_u32(sBrs) + k * 32), idesc2, k != 0);
+            umma_commit(mma_bar);
+        }
+        mbar_wait(mma_bar, 1);
+        tc_fence_after();
+        // ---- epilogue 2: residual in place in the tap-1 tile; skip accumulation ------------------
+        const int t = t0 + r;
+        if (a.has_out) {
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                uint32_t rr[16];
+                tmem_ld16(tmem + lane_base + D2_COL + 16 * j, rr);
+                tmem_ld_wait();
+                uint4* p0 = (uint4*)(sA1 + r * 128 + (((2 * j) ^ sw) << 4));
+                uint4* p1 = (uint4*)(sA1 + r * 128 + (((2 * j + 1) ^ sw) << 4));
+                uint4 x0 = *p0, x1 = *p1;
+                uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w}, o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = 16 * j + 2 * i;
+                    const float2 xv = unpack_bf16(xi[i]);
+                    o[i] = pack_bf16(__uint_as_float(rr[2 * i]) + sbrs[c] + xv.x, __uint_as_float(rr[2 * i + 1]) + sbrs[c + 1] + xv.y);
+                }
+                *p0 = make_uint4(o[0], o[1], o[2], o[3]);
+                *p1 = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+        }
+        {
+            const int js = t - (a.RF - 1);
+            const bool live = t < a.T && js >= 0 && js < a.Tout;
+            float* dst = a.skip + ((size_t)b * a.Tout + (live ? js : 0)) * a.S;
+            for (int s0 = 0; s0 < a.S; s0 += 8) {
+                uint32_t sv[8];
+                tmem_ld8(tmem + lane_base + D2_COL + CC + s0, sv);
+                tmem_ld_wait();
+                if (live) {
+                    float4 v0 = make_float4(__uint_as_float(sv[0]) + sbrs[CC + s0], __uint_as_float(sv[1]) + sbrs[CC + s0 + 1],
+                                            __uint_as_float(sv[2]) + sbrs[CC + s0 + 2], __uint_as_float(sv[3]) + sbrs[CC + s0 + 3]);
+                    float4 v1 = make_float4(__uint_as_float(sv[4]) + sbrs[CC + s0 + 4], __uint_as_float(sv[5]) + sbrs[CC + s0 + 5],
+                                            __uint_as_float(sv[6]) + sbrs[CC + s0 + 6], __uint_as_float(sv[7]) + sbrs[CC + s0 + 7]);
+                    float4* d4 = (float4*)(dst + s0);
+                    if (!a.skip_init) {
+                        const float4 p0 = d4[0], p1 = d4[1];
+                        v0.x += p0.x; v0.y += p0.y; v0.z += p0.z; v0.w += p0.w;
+                        v1.x += p1.x; v1.y += p1.y; v1.z += p1.z; v1.w += p1.w;
+                    }
+                    d4[0] = v0; d4[1] = v1;
+                }
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0 && a.has_out) {
+            tma_store_3d(&map_out, sA1, 0, t0, b);
+            tma_commit();
+        }
+    }
+    if (tid == 0) tma_wait_all0();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+// (B, T, 64) bf16 time-major activation as a 3-D tensor map {channel, time, clip}, box {64, 128, 1}, 128B swizzle
+int make_act_map(CUtensorMap* map, const void* ptr, int B, int T) {
+    EncodeTiledFn fn = encode_fn();
+    MVN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[3] = {(cuuint64_t)CC, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)CC * 2, (cuuint64_t)T * CC * 2};
+    cuuint32_t box[3] = {(cuuint32_t)CC, (cuuint32_t)TILE_T, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MVN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
+}  // namespace
+
+int mvn_tc_layer_supported(int C, int S, int video) {
+    (void)video;
+    return C == CC && S >= 8 && S % 8 == 0 && S <= 64;
+}
+
+int mvn_tc_layer_fwd(const void* x_in, const void* ctx, void* x_out, float* skip_sum, const float* lw,
+                     const PackedLayout& P, const Geo& g, int layer, cudaStream_t st) {
+    MVN_REQUIRE(mvn_tc_layer_supported(g.C, g.S, g.video), "tensor-core layer kernel: unsupported channel counts");
+    MVN_REQUIRE((((uintptr_t)x_in) & 15) == 0 && (!x_out || (((uintptr_t)x_out) & 15) == 0), "activations must be 16-byte aligned");
+    CUtensorMap map_x, map_ctx, map_out;
+    int rc;
+    if ((rc = make_act_map(&map_x, x_in, g.B, g.T))) return rc;
+    if ((rc = make_act_map(&map_ctx, g.video ? ctx : x_in, g.B, g.T))) return rc;
+    if ((rc = make_act_map(&map_out, x_out ? x_out : x_in, g.B, g.T))) return rc;
+    TcArgs a;
+    a.wzT = lw + P.oWzT; a.bz = lw + P.obz; a.wrsT = lw + P.oWrsT; a.brs = lw + P.obrs;
+    a.skip = skip_sum;
+    a.B = g.B; a.T = g.T; a.Tout = g.Tout; a.RF = g.RF; a.S = g.S; a.N2 = ((g.C + g.S + 15) / 16) * 16;
+    a.dil = g.dil[layer]; a.nchunks = g.video ? 3 : 2; a.has_out = x_out != nullptr; a.skip_init = layer == 0;
+    a.tiles_per_clip = (g.T + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
+    const int smem = smem_total(a.nchunks, a.N2) + 1024;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        MVN_CUDA(cudaFuncSetAttribute(layer_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    int grid = 2 * 148;
+    if (grid > a.n_tiles) grid = a.n_tiles;
+    layer_fwd_tc_kernel<<<grid, 128, smem, st>>>(map_x, map_ctx, map_out, a);
+    return mvn_check_launch("layer_fwd_tc");
 }
