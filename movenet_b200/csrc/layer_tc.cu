@@ -107,19 +107,48 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 }
 
 struct TcArgs {
-    const float* wzT;     // [2C][Kz] fp32, rows interleaved (filter c, gate c)
-    const float* bz;      // [2C]     interleaved
-    const float* wrsT;    // [C+S][C]
-    const float* brs;     // [C+S]
+    const void* img;      // shared-memory weight image of this layer (mvn_tc_pack)
     float* skip;          // (B, Tout, S) fp32
     int B, T, Tout, RF, S, N2, dil, nchunks, has_out, skip_init, tiles_per_clip, n_tiles;
 };
 
-// shared-memory carve-up (dynamic, 1024-byte aligned): Wz chunks | [Wr|Ws] | A tiles | biases | barriers
+// shared-memory carve-up (dynamic, 1024-byte aligned): Wz chunks | [Wr|Ws] | biases (1 KB) | A tiles | barriers.
+// The first three are one contiguous image prepared by mvn_tc_pack and fetched with a single bulk copy.
 __host__ __device__ inline int smem_brs_off(int nchunks) { return nchunks * TILE_BYTES; }
-__host__ __device__ inline int smem_a_off(int nchunks, int N2) { return smem_brs_off(nchunks) + ((N2 * 128 + 1023) & ~1023); }
-__host__ __device__ inline int smem_bias_off(int nchunks, int N2) { return smem_a_off(nchunks, N2) + nchunks * TILE_BYTES; }
-__host__ __device__ inline int smem_total(int nchunks, int N2) { return smem_bias_off(nchunks, N2) + 256 * 4 + 64; }
+__host__ __device__ inline int smem_bias_off(int nchunks, int N2) { return smem_brs_off(nchunks) + ((N2 * 128 + 1023) & ~1023); }
+__host__ __device__ inline int smem_a_off(int nchunks, int N2) { return smem_bias_off(nchunks, N2) + 1024; }
+__host__ __device__ inline int smem_total(int nchunks, int N2) { return smem_a_off(nchunks, N2) + nchunks * TILE_BYTES + 64; }
+
+// image writer: one block row per layer
+__global__ void tc_pack_kernel(const float* const* __restrict__ ptrs, float* __restrict__ packed, PackedLayout P, int S,
+                               int nchunks, int N2, int video) {
+    const int l = blockIdx.y;
+    const float* const* lp = ptrs + MVN_PARAM_LAYER(l, 0);
+    const float *wf = lp[0], *wg = lp[1], *vf = lp[2], *bvf = lp[3], *vg = lp[4], *bvg = lp[5], *wr = lp[6], *br = lp[7],
+                *ws = lp[8], *bs = lp[9];
+    uint8_t* img = (uint8_t*)(packed + P.layer0 + (size_t)l * P.layer_stride + P.oTc);
+    const int Kz = nchunks * CC, nz = 128 * Kz, nrs = N2 * CC;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nz + nrs + 256; i += gridDim.x * blockDim.x) {
+        if (i < nz) {
+            const int n = i / Kz, k = i - n * Kz, c = n & 63, gate = n >> 6;
+            float v;
+            if (k < CC) v = (gate ? wg : wf)[((size_t)c * CC + k) * 2 + 0];
+            else if (k < 2 * CC) v = (gate ? wg : wf)[((size_t)c * CC + (k - CC)) * 2 + 1];
+            else v = (gate ? vg : vf)[(size_t)c * CC + (k - 2 * CC)];
+            const int chunk = k >> 6, kk = k & 63;
+            *(__nv_bfloat16*)(img + chunk * TILE_BYTES + n * 128 + ((((kk >> 3) ^ (n & 7)) << 4) | ((kk & 7) << 1))) = __float2bfloat16(v);
+        } else if (i < nz + nrs) {
+            const int j = i - nz, n = j >> 6, k = j & 63;
+            const float v = n < CC ? wr[(size_t)n * CC + k] : (n < CC + S ? ws[(size_t)(n - CC) * CC + k] : 0.f);
+            *(__nv_bfloat16*)(img + smem_brs_off(nchunks) + n * 128 + ((((k >> 3) ^ (n & 7)) << 4) | ((k & 7) << 1))) = __float2bfloat16(v);
+        } else {
+            const int n = i - nz - nrs;
+            float* bias = (float*)(img + smem_bias_off(nchunks, N2));
+            if (n < 128) bias[n] = video ? ((n >> 6) ? bvg : bvf)[n & 63] : 0.f;
+            else { const int m = n - 128; bias[n] = m < CC ? br[m] : (m < CC + S ? bs[m - CC] : 0.f); }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(128, 2)
 layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_ctx,
@@ -128,50 +157,35 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sBz = smem;
     uint8_t* sBrs = smem + smem_brs_off(a.nchunks);
+    float* sbz = (float*)(smem + smem_bias_off(a.nchunks, a.N2));
+    float* sbrs = sbz + 128;
     uint8_t* sA0 = smem + smem_a_off(a.nchunks, a.N2);   // tap t-d; later the gated tile
     uint8_t* sA1 = sA0 + TILE_BYTES;                      // tap t; later x'
     uint8_t* sA2 = sA1 + TILE_BYTES;                      // context (video only)
-    float* sbz = (float*)(smem + smem_bias_off(a.nchunks, a.N2));
-    float* sbrs = sbz + 128;
-    uint64_t* full_bar = (uint64_t*)(sbrs + 128);
+    uint64_t* full_bar = (uint64_t*)(sA0 + a.nchunks * TILE_BYTES);
     uint64_t* mma_bar = full_bar + 1;
     uint32_t* tmem_slot = (uint32_t*)(full_bar + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int Kz = a.nchunks * CC;
 
-    // ---- one-time setup: weights -> bf16, K-major, 128B-swizzled tiles --------------------------
-    for (int i = tid; i < 128 * Kz; i += 128) {
-        const int n = i / Kz, k = i - n * Kz;                 // n: 0..63 filter c, 64..127 gate c
-        const float v = a.wzT[(size_t)(2 * (n & 63) + (n >> 6)) * Kz + k];
-        const int chunk = k >> 6, kk = k & 63;
-        const uint32_t off = chunk * TILE_BYTES + n * 128 + ((((kk >> 3) ^ (n & 7)) << 4) | ((kk & 7) << 1));
-        *(__nv_bfloat16*)(sBz + off) = __float2bfloat16(v);
-    }
-    for (int i = tid; i < a.N2 * CC; i += 128) {
-        const int n = i >> 6, k = i & 63;
-        const float v = n < CC + a.S ? a.wrsT[(size_t)n * CC + k] : 0.f;
-        const uint32_t off = n * 128 + ((((k >> 3) ^ (n & 7)) << 4) | ((k & 7) << 1));
-        *(__nv_bfloat16*)(sBrs + off) = __float2bfloat16(v);
-    }
-    {   // biases: sbz[n] with n in the tensor-core column order; sbrs[n]
-        const int n = tid;
-        sbz[n] = a.bz[2 * (n & 63) + (n >> 6)];
-        sbrs[n] = n < CC + a.S ? a.brs[n] : 0.f;
-    }
+    // ---- one-time setup: barriers, TMEM, and the weight image (one bulk copy) --------------------
     if (tid == 0) {
         mbar_init(full_bar, 1);
         mbar_init(mma_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t wbytes = (uint32_t)smem_a_off(a.nchunks, a.N2);
+        mbar_expect_tx(full_bar, wbytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(smem)), "l"(a.img), "r"(wbytes), "r"(smem_u32(full_bar)) : "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    fence_proxy_async();            // weight tiles were written with generic stores; the tensor core reads them via the async proxy
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    mbar_wait(full_bar, 0);
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const uint32_t idesc1 = umma_idesc(TILE_T, 128), idesc2 = umma_idesc(TILE_T, a.N2);
@@ -179,7 +193,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int r = tid;               // this thread's row of the tile == its TMEM lane
     const int sw = r & 7;
 
-    uint32_t it = 0;
+    uint32_t it = 1;            // phase 0 of full_bar was the weight image
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
         const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T;
         if (tid == 0) {
@@ -189,6 +203,12 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             tma_load_3d(sA1, &map_x, full_bar, 0, t0, b);
             if (a.nchunks == 3) tma_load_3d(sA2, &map_ctx, full_bar, 0, t0, b);
         }
+        // the running skip sum of this row: fetch it now, it is only needed at the very end of the tile
+        const int t = t0 + r, js = t - (a.RF - 1);
+        const bool live = t < a.T && js >= 0 && js < a.Tout;
+        float* skip_dst = a.skip + ((size_t)b * a.Tout + (live ? js : 0)) * a.S;
+        float4 old0 = make_float4(0.f, 0.f, 0.f, 0.f), old1 = old0;
+        if (live && !a.skip_init) { old0 = ((const float4*)skip_dst)[0]; old1 = ((const float4*)skip_dst)[1]; }
         mbar_wait(full_bar, it & 1);
         if (tid == 0) {
             tc_fence_after();
@@ -234,7 +254,6 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         mbar_wait(mma_bar, 1);
         tc_fence_after();
         // ---- epilogue 2: residual in place in the tap-1 tile; skip accumulation ------------------
-        const int t = t0 + r;
         if (a.has_out) {
 #pragma unroll 1
             for (int j = 0; j < 4; ++j) {
@@ -255,27 +274,23 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 *p1 = make_uint4(o[4], o[5], o[6], o[7]);
             }
         }
-        {
-            const int js = t - (a.RF - 1);
-            const bool live = t < a.T && js >= 0 && js < a.Tout;
-            float* dst = a.skip + ((size_t)b * a.Tout + (live ? js : 0)) * a.S;
-            for (int s0 = 0; s0 < a.S; s0 += 8) {
-                uint32_t sv[8];
-                tmem_ld8(tmem + lane_base + D2_COL + CC + s0, sv);
-                tmem_ld_wait();
-                if (live) {
-                    float4 v0 = make_float4(__uint_as_float(sv[0]) + sbrs[CC + s0], __uint_as_float(sv[1]) + sbrs[CC + s0 + 1],
-                                            __uint_as_float(sv[2]) + sbrs[CC + s0 + 2], __uint_as_float(sv[3]) + sbrs[CC + s0 + 3]);
-                    float4 v1 = make_float4(__uint_as_float(sv[4]) + sbrs[CC + s0 + 4], __uint_as_float(sv[5]) + sbrs[CC + s0 + 5],
-                                            __uint_as_float(sv[6]) + sbrs[CC + s0 + 6], __uint_as_float(sv[7]) + sbrs[CC + s0 + 7]);
-                    float4* d4 = (float4*)(dst + s0);
-                    if (!a.skip_init) {
-                        const float4 p0 = d4[0], p1 = d4[1];
-                        v0.x += p0.x; v0.y += p0.y; v0.z += p0.z; v0.w += p0.w;
-                        v1.x += p1.x; v1.y += p1.y; v1.z += p1.z; v1.w += p1.w;
-                    }
-                    d4[0] = v0; d4[1] = v1;
+        for (int s0 = 0; s0 < a.S; s0 += 8) {
+            uint32_t sv[8];
+            tmem_ld8(tmem + lane_base + D2_COL + CC + s0, sv);
+            tmem_ld_wait();
+            if (live) {
+                float4 v0 = make_float4(__uint_as_float(sv[0]) + sbrs[CC + s0], __uint_as_float(sv[1]) + sbrs[CC + s0 + 1],
+                                        __uint_as_float(sv[2]) + sbrs[CC + s0 + 2], __uint_as_float(sv[3]) + sbrs[CC + s0 + 3]);
+                float4 v1 = make_float4(__uint_as_float(sv[4]) + sbrs[CC + s0 + 4], __uint_as_float(sv[5]) + sbrs[CC + s0 + 5],
+                                        __uint_as_float(sv[6]) + sbrs[CC + s0 + 6], __uint_as_float(sv[7]) + sbrs[CC + s0 + 7]);
+                float4* d4 = (float4*)(skip_dst + s0);
+                if (!a.skip_init) {
+                    float4 p0, p1;
+                    if (s0 == 0) { p0 = old0; p1 = old1; } else { p0 = d4[0]; p1 = d4[1]; }
+                    v0.x += p0.x; v0.y += p0.y; v0.z += p0.z; v0.w += p0.w;
+                    v1.x += p1.x; v1.y += p1.y; v1.z += p1.z; v1.w += p1.w;
                 }
+                d4[0] = v0; d4[1] = v1;
             }
         }
         fence_proxy_async();
@@ -334,6 +349,14 @@ int mvn_tc_layer_supported(int C, int S, int video) {
     return C == CC && S >= 8 && S % 8 == 0 && S <= 64;
 }
 
+int mvn_tc_pack(const float* const* param_ptrs_dev, float* packed, const PackedLayout& P, const Geo& g, cudaStream_t st) {
+    const int nchunks = g.video ? 3 : 2, N2 = ((g.C + g.S + 15) / 16) * 16;
+    MVN_REQUIRE(smem_a_off(nchunks, N2) <= MVN_TC_IMG_BYTES, "tensor-core weight image does not fit its slot");
+    dim3 grid(16, g.N);
+    tc_pack_kernel<<<grid, 256, 0, st>>>(param_ptrs_dev, packed, P, g.S, nchunks, N2, g.video);
+    return mvn_check_launch("tc_pack");
+}
+
 int mvn_tc_layer_fwd(const void* x_in, const void* ctx, void* x_out, float* skip_sum, const float* lw,
                      const PackedLayout& P, const Geo& g, int layer, cudaStream_t st) {
     MVN_REQUIRE(mvn_tc_layer_supported(g.C, g.S, g.video), "tensor-core layer kernel: unsupported channel counts");
@@ -344,7 +367,7 @@ int mvn_tc_layer_fwd(const void* x_in, const void* ctx, void* x_out, float* skip
     if ((rc = make_act_map(&map_ctx, g.video ? ctx : x_in, g.B, g.T))) return rc;
     if ((rc = make_act_map(&map_out, x_out ? x_out : x_in, g.B, g.T))) return rc;
     TcArgs a;
-    a.wzT = lw + P.oWzT; a.bz = lw + P.obz; a.wrsT = lw + P.oWrsT; a.brs = lw + P.obrs;
+    a.img = lw + P.oTc;
     a.skip = skip_sum;
     a.B = g.B; a.T = g.T; a.Tout = g.Tout; a.RF = g.RF; a.S = g.S; a.N2 = ((g.C + g.S + 15) / 16) * 16;
     a.dil = g.dil[layer]; a.nchunks = g.video ? 3 : 2; a.has_out = x_out != nullptr; a.skip_init = layer == 0;

@@ -9,3 +9,5 @@ int mvn_tc_layer_supported(int C, int S, int video);
 // x_out may be null for the last layer (its residual output is discarded).
 int mvn_tc_layer_fwd(const void* x_in, const void* ctx, void* x_out, float* skip_sum, const float* layer_weights,
                      const PackedLayout& P, const Geo& g, int layer, cudaStream_t st);
+// build the per-layer shared-memory weight images inside the packed buffer (called by mvn_pack_weights)
+int mvn_tc_pack(const float* const* param_ptrs_dev, float* packed, const PackedLayout& P, const Geo& g, cudaStream_t st);

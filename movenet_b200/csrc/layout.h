@@ -5,6 +5,8 @@
 #include "../../include/movenet_b200.h"
 
 #define MVN_MAX_LAYERS 256
+// tensor-core weight image of one layer: 3 Wz chunks + [Wr|Ws] (<=128 rows) of 16 KB each, + 1 KB of biases
+#define MVN_TC_IMG_BYTES (4 * 16384 + 1024)
 
 struct Geo {
     int L, St, A, C, S, Cin, B, T, video, adt, remove_last, logits;
@@ -48,6 +50,7 @@ struct PackedLayout {
     size_t obrs;                // [C+S]
     size_t oWzT;                // [2C][Kz]   transpose of Wz (backward data)
     size_t oWrsT;               // [C+S][C]   transpose of Wrs
+    size_t oTc;                 // tensor-core shared-memory image (bf16, swizzled; see layer_tc.cu), C == 64 only
     size_t w1p, b1, w2p, b2;    // head: [S][A], [A], [A][A], [A]
     size_t w1pT, w2pT;          // [A][S], [A][A]
     size_t wv, bv;              // video conv: [4096*Cin][C], [C]
@@ -67,6 +70,7 @@ static inline void packed_layout(const Geo& g, PackedLayout& p) {
     p.obrs = take(C + S) - l0;
     p.oWzT = take(2 * C * Kz) - l0;
     p.oWrsT = take((C + S) * C) - l0;
+    p.oTc = take(g.C == 64 ? MVN_TC_IMG_BYTES / 4 : 0) - l0;
     p.layer0 = l0;
     p.layer_stride = o - l0;
     o = l0 + p.layer_stride * g.N;

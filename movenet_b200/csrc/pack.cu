@@ -2,6 +2,7 @@
 // form the kernels consume, and the reverse map for gradients.
 #include "common.cuh"
 #include "layout.h"
+#include "layer_tc.h"
 
 // one block row per layer: blockIdx.y = layer.  ptrs = device table in state_dict order.
 __global__ void pack_layer_kernel(const float* const* __restrict__ ptrs, float* __restrict__ packed,
@@ -180,7 +181,11 @@ extern "C" int mvn_pack_weights(const mvn_shape_t* s, const void* const* param_p
     pack_layer_kernel<<<gl, 256, 0, st>>>(ptrs, (float*)packed, P, g.C, g.S, g.Kz, g.video);
     dim3 gm(32, 6);
     pack_misc_kernel<<<gm, 256, 0, st>>>(ptrs, (float*)packed, P, g.A, g.C, g.S, g.Cin, g.N, g.video);
-    return mvn_check_launch("pack_weights");
+    int rc = mvn_check_launch("pack_weights");
+    if (rc) return rc;
+    if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video))
+        return mvn_tc_pack(ptrs, (float*)packed, P, g, st);
+    return 0;
 }
 
 extern "C" int mvn_unpack_grads(const mvn_shape_t* s, const void* packed_grads, float* flat_grads,
