@@ -1,0 +1,378 @@
+// Backward of GatedResidualConv1d (autograd of movenet/modules.py:67-93) as ONE fused sm_100a kernel
+// per layer: data gradients, weight gradients and bias gradients, all on tcgen05 tensor cores.
+//
+// The gradient of the residual stream is never materialised as one tensor.  Layer l+1 hands down
+//   P[t] = d(x_{l+1})[t] without its tap-0 term        and   U[t] = W0^T dz_{l+1}[t]   (the tap-0 term,
+//   which belongs to time t - d_{l+1}),  so  d(x_{l+1})[t] = P[t] + U[t + d_{l+1}]
+// and the dilation shift becomes a TMA row coordinate instead of a scatter.  Per 128-row time tile:
+//
+//   TMA : x(t-d) x(t) ctx(t) P(t) U(t+d_up)          | threads: d(skip) rows -> bf16 tile
+//   dxs = P + U  (in place, bf16)
+//   G1  : D1 = [x(t-d)|x(t)|ctx] . Wz^T               (recompute the gate pre-activations)
+//   G2  : D3 = [dxs | dskip] . [Wr ; Ws]              (d gated)          B read MN-major from the SAME image
+//   epilogue 1: th, sg, gated, dz_f, dz_g  -> bf16 tiles DZ0 DZ1 G  (128B-swizzled)
+//   G3  : D4 = dz . Wz  -> [U' | W1^T dz | V^T dz]    (B = the forward weight image read MN-major)
+//   W1  : dWz^T  += dz^T . [x(t-d)|x(t)|ctx]          (K = time: every tile is read MN-major)
+//   W2  : dWrs^T += [dxs|dskip]^T . gated ;  bias grads = the same A operands times an all-ones B
+//   epilogue 2: P' = dxs + D4[tap1] ; U' = D4[tap0]  -> TMA stores ; d(ctx) += D4[ctx]
+//
+// The weight-gradient accumulators stay in TMEM for the CTA's whole tile loop and are written once
+// per CTA as partial sums; a small second kernel reduces the partials in a fixed order
+// (deterministic, no atomics) into the packed gradient buffer.
+#include "tc_common.cuh"
+#include "layer_tc.h"
+
+using namespace tc;
+
+namespace {
+
+constexpr int W1_COL = 192, W2_COL = 384, B1_COL = 448, B2_COL = 464;
+constexpr int PART_LD = 256;                       // partial row: 192 (dWz^T) + 64 (dWrs^T)
+constexpr int PART_FLOATS = 128 * PART_LD + 256;   // + bias sums of the two A operands
+
+struct BwdArgs {
+    const void* img;
+    const float* dskip;   // (B, Tout, S) fp32
+    float* dctx;          // (B, T, C) fp32, accumulated; null without video
+    float* partial;       // [grid][PART_FLOATS]
+    int B, T, Tout, RF, S, N2, dil, dil_up, nchunks, tiles_per_clip, n_tiles;
+};
+
+__host__ __device__ inline int bwd_tiles_off(int nc, int N2) { return smem_a_off(nc, N2); }
+// tiles after the image: A0..A(nc-1) | DXS | DSK | U | DZ0 | DZ1 | G | ONES(1 KB) | barriers
+__host__ __device__ inline int bwd_smem_total(int nc, int N2) { return bwd_tiles_off(nc, N2) + (nc + 6) * TILE_BYTES + 1024 + 64; }
+
+__global__ void __launch_bounds__(128, 1)
+layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_ctx,
+                    const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_u,
+                    const __grid_constant__ CUtensorMap map_pout, const __grid_constant__ CUtensorMap map_uout,
+                    const BwdArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int nc = a.nchunks;
+    uint8_t* sBz = smem;
+    uint8_t* sBrs = smem + smem_brs_off(nc);
+    float* sbz = (float*)(smem + smem_bias_off(nc, a.N2));
+    uint8_t* sA = smem + bwd_tiles_off(nc, a.N2);
+    uint8_t* sDXS = sA + nc * TILE_BYTES;
+    uint8_t* sDSK = sDXS + TILE_BYTES;
+    uint8_t* sU = sDSK + TILE_BYTES;
+    uint8_t* sDZ = sU + TILE_BYTES;               // DZ0 (filter half) | DZ1 (gate half)
+    uint8_t* sG = sDZ + 2 * TILE_BYTES;
+    uint8_t* sONES = sG + TILE_BYTES;
+    uint64_t* full_bar = (uint64_t*)(sONES + 1024);
+    uint64_t* mma_bar = full_bar + 1;
+    uint64_t* w_bar = full_bar + 2;
+    uint32_t* tmem_slot = (uint32_t*)(full_bar + 3);
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int r = tid, sw = r & 7;
+    const int NZ = nc * CC;                        // columns of D4 / dWz^T
+
+    if (tid == 0) {
+        mbar_init(full_bar, 1); mbar_init(mma_bar, 1); mbar_init(w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t wbytes = (uint32_t)smem_a_off(nc, a.N2);
+        mbar_expect_tx(full_bar, wbytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(smem)), "l"(a.img), "r"(wbytes), "r"(smem_u32(full_bar)) : "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // constant tiles: DSK is zero outside the S live channels, ONES is all bf16 1.0
+    for (int i = tid; i < TILE_BYTES / 16; i += 128) ((uint4*)sDSK)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 1024 / 4; i += 128) ((uint32_t*)sONES)[i] = 0x3F803F80u;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    mbar_wait(full_bar, 0);
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+
+    const uint32_t iG1 = umma_idesc_major(TILE_T, 128, 0, 0);
+    const uint32_t iG2 = umma_idesc_major(TILE_T, 64, 0, 1);
+    const uint32_t iG3 = umma_idesc_major(TILE_T, NZ, 0, 1);
+    const uint32_t iW1 = umma_idesc_major(TILE_T, NZ, 1, 1);
+    const uint32_t iW2 = umma_idesc_major(TILE_T, 64, 1, 1);
+    const uint32_t iB = umma_idesc_major(TILE_T, 16, 1, 1);
+    const uint32_t load_bytes = (uint32_t)((nc + 2) * TILE_BYTES);
+
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T;
+        const int t = t0 + r;
+        if (tid == 0) {
+            tma_wait_read0();                  // the previous tile's P'/U' stores have finished reading U / DXS
+            mbar_expect_tx(full_bar, load_bytes);
+            tma_load_3d(sA, &map_x, full_bar, 0, t0 - a.dil, b);
+            tma_load_3d(sA + TILE_BYTES, &map_x, full_bar, 0, t0, b);
+            if (nc == 3) tma_load_3d(sA + 2 * TILE_BYTES, &map_ctx, full_bar, 0, t0, b);
+            tma_load_3d(sDXS, &map_p, full_bar, 0, t0, b);
+            tma_load_3d(sU, &map_u, full_bar, 0, t0 + a.dil_up, b);
+        }
+        {   // d(skip) row of this thread -> bf16, logical channels [0, S) of the DSK tile
+            const int js = t - (a.RF - 1);
+            const bool live = t < a.T && js >= 0 && js < a.Tout;
+            const float* src = a.dskip + ((size_t)b * a.Tout + (live ? js : 0)) * a.S;
+            for (int s0 = 0; s0 < a.S; s0 += 8) {
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (live) { v0 = ((const float4*)(src + s0))[0]; v1 = ((const float4*)(src + s0))[1]; }
+                *(uint4*)(sDSK + r * 128 + ((((s0 >> 3)) ^ sw) << 4)) =
+                    make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+            }
+        }
+        mbar_wait(full_bar, (it + 1) & 1);
+        // ---- dxs = P + U(t + d_up), in place -----------------------------------------------------
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            uint4* pp = (uint4*)(sDXS + r * 128 + ((q ^ sw) << 4));
+            const uint4 pv = *pp, uv = *(const uint4*)(sU + r * 128 + ((q ^ sw) << 4));
+            const uint32_t pa[4] = {pv.x, pv.y, pv.z, pv.w}, ua[4] = {uv.x, uv.y, uv.z, uv.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 x = unpack_bf16(pa[i]), y = unpack_bf16(ua[i]);
+                o[i] = pack_bf16(x.x + y.x, x.y + y.y);
+            }
+            *pp = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int c = 0; c < nc; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma(tmem, umma_desc(smem_u32(sA + c * TILE_BYTES) + k * 32), umma_desc(smem_u32(sBz + c * TILE_BYTES) + k * 32),
+                         iG1, (c | k) != 0);
+            // d(gated) = dxs . Wr + dskip . Ws : contraction over the image's ROWS (c_out | s) -> B is MN-major
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma(tmem + 128, umma_desc(smem_u32(sDXS) + k * 32), umma_desc_mn(smem_u32(sBrs) + k * 2048, TILE_BYTES), iG2, k != 0);
+            umma(tmem + 128, umma_desc(smem_u32(sDSK)), umma_desc_mn(smem_u32(sBrs) + 4 * 2048, TILE_BYTES), iG2, 1);
+            umma_commit(mma_bar);
+        }
+        mbar_wait(mma_bar, 0);
+        tc_fence_after();
+        // ---- epilogue 1: gate derivative -------------------------------------------------------
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            uint32_t f[16], g[16], dg[16];
+            tmem_ld16(tmem + lane_base + 16 * j, f);
+            tmem_ld16(tmem + lane_base + 64 + 16 * j, g);
+            tmem_ld16(tmem + lane_base + 128 + 16 * j, dg);
+            tmem_ld_wait();
+            uint32_t of[8], og[8], oy[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                float zf[2], zg[2], y[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int c = 16 * j + i + e;
+                    const float th = tanh_fast(__uint_as_float(f[i + e]) + sbz[c]);
+                    const float sg = fmaf(0.5f, tanh_fast(0.5f * (__uint_as_float(g[i + e]) + sbz[64 + c])), 0.5f);
+                    const float d = __uint_as_float(dg[i + e]);
+                    y[e] = th * sg;
+                    zf[e] = d * sg * (1.f - th * th);
+                    zg[e] = d * y[e] * (1.f - sg);
+                }
+                of[i >> 1] = pack_bf16(zf[0], zf[1]); og[i >> 1] = pack_bf16(zg[0], zg[1]); oy[i >> 1] = pack_bf16(y[0], y[1]);
+            }
+            const int o0 = r * 128 + (((2 * j) ^ sw) << 4), o1 = r * 128 + (((2 * j + 1) ^ sw) << 4);
+            *(uint4*)(sDZ + o0) = make_uint4(of[0], of[1], of[2], of[3]);
+            *(uint4*)(sDZ + o1) = make_uint4(of[4], of[5], of[6], of[7]);
+            *(uint4*)(sDZ + TILE_BYTES + o0) = make_uint4(og[0], og[1], og[2], og[3]);
+            *(uint4*)(sDZ + TILE_BYTES + o1) = make_uint4(og[4], og[5], og[6], og[7]);
+            *(uint4*)(sG + o0) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
+            *(uint4*)(sG + o1) = make_uint4(oy[4], oy[5], oy[6], oy[7]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            // G3: D4[t][kin] = sum_m dz[t][m] Wz[m][kin]  (A = dz tiles K-major, B = the image read MN-major)
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma(tmem, umma_desc(smem_u32(sDZ + c * TILE_BYTES) + k * 32),
+                         umma_desc_mn(smem_u32(sBz) + (c * 64 + k * 16) * 128, TILE_BYTES), iG3, (c | k) != 0);
+            umma_commit(mma_bar);
+            // weight / bias gradients: K = time.  Every tile is [time x 64 ch], i.e. an MN-major operand.
+            const uint32_t acc0 = it != 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t acc = acc0 | (k != 0);
+                const uint64_t dz_mn = umma_desc_mn(smem_u32(sDZ) + k * 2048, TILE_BYTES);
+                const uint64_t dx_mn = umma_desc_mn(smem_u32(sDXS) + k * 2048, TILE_BYTES);
+                const uint64_t ones = umma_desc_mn_plain(smem_u32(sONES), 256, 128);
+                umma(tmem + W1_COL, dz_mn, umma_desc_mn(smem_u32(sA) + k * 2048, TILE_BYTES), iW1, acc);
+                umma(tmem + W2_COL, dx_mn, umma_desc_mn(smem_u32(sG) + k * 2048, TILE_BYTES), iW2, acc);
+                umma(tmem + B1_COL, dz_mn, ones, iB, acc);
+                umma(tmem + B2_COL, dx_mn, ones, iB, acc);
+            }
+            umma_commit(w_bar);
+        }
+        mbar_wait(mma_bar, 1);
+        tc_fence_after();
+        // ---- epilogue 2a: P' = dxs + W1^T dz -> the U tile (free since the pre-sum); d(ctx) += V^T dz
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            uint32_t v[16];
+            tmem_ld16(tmem + lane_base + 64 + 16 * j, v);
+            tmem_ld_wait();
+            const uint4 x0 = *(const uint4*)(sDXS + r * 128 + (((2 * j) ^ sw) << 4));
+            const uint4 x1 = *(const uint4*)(sDXS + r * 128 + (((2 * j + 1) ^ sw) << 4));
+            const uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 xv = unpack_bf16(xi[i]);
+                o[i] = pack_bf16(__uint_as_float(v[2 * i]) + xv.x, __uint_as_float(v[2 * i + 1]) + xv.y);
+            }
+            *(uint4*)(sU + r * 128 + (((2 * j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *(uint4*)(sU + r * 128 + (((2 * j + 1) ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        if (nc == 3) {
+            float4* dst = (float4*)(a.dctx + ((size_t)b * a.T + (t < a.T ? t : 0)) * CC);
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_base + 128 + 16 * j, v);
+                tmem_ld_wait();
+                if (t < a.T) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 o = dst[4 * j + q];
+                        o.x += __uint_as_float(v[4 * q]); o.y += __uint_as_float(v[4 * q + 1]);
+                        o.z += __uint_as_float(v[4 * q + 2]); o.w += __uint_as_float(v[4 * q + 3]);
+                        dst[4 * j + q] = o;
+                    }
+                }
+            }
+        }
+        // ---- epilogue 2b: once the weight-gradient MMAs no longer read DXS: U' = W0^T dz -> DXS tile
+        mbar_wait(w_bar, it & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+            uint32_t v[16];
+            tmem_ld16(tmem + lane_base + 16 * j, v);
+            tmem_ld_wait();
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            *(uint4*)(sDXS + r * 128 + (((2 * j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *(uint4*)(sDXS + r * 128 + (((2 * j + 1) ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_3d(&map_pout, sU, 0, t0, b);
+            tma_store_3d(&map_uout, sDXS, 0, t0, b);
+            tma_commit();
+        }
+    }
+    // ---- flush this CTA's partial weight / bias gradients ----------------------------------------
+    tc_fence_after();
+    float* part = a.partial + (size_t)blockIdx.x * PART_FLOATS;
+    float* prow = part + (size_t)r * PART_LD;
+#pragma unroll 1
+    for (int j = 0; j < NZ / 16; ++j) {
+        uint32_t v[16];
+        tmem_ld16(tmem + lane_base + W1_COL + 16 * j, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            ((float4*)(prow + 16 * j))[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                        __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+    }
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        uint32_t v[16];
+        tmem_ld16(tmem + lane_base + W2_COL + 16 * j, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            ((float4*)(prow + 192 + 16 * j))[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                              __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+    }
+    {
+        uint32_t v1[8], v2[8];
+        tmem_ld8(tmem + lane_base + B1_COL, v1);
+        tmem_ld8(tmem + lane_base + B2_COL, v2);
+        tmem_ld_wait();
+        part[128 * PART_LD + r] = __uint_as_float(v1[0]);
+        part[128 * PART_LD + 128 + r] = __uint_as_float(v2[0]);
+    }
+    if (tid == 0) tma_wait_all0();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+    }
+}
+
+// Fixed-order reduction of the per-CTA partials into the packed gradient layout (layout.h):
+//   dWz[k][2c+gate] = sum_cta part[gate*64+c][k] ; dbz likewise ; dWrs[k][n] = sum_cta part[n'][192+k] ; dbrs.
+__global__ void tc_bwd_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ lg, PackedLayout P,
+                                     int S, int Kz, int video, int has_resid) {
+    const int nWz = Kz * 128, nbz = 128, nWrs = CC * (CC + S), nbrs = CC + S;
+    const int total = nWz + nbz + nWrs + nbrs;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int j = i, src; float* dst;
+        if (j < nWz) { const int k = j / 128, n = j % 128; src = ((n & 1) * 64 + (n >> 1)) * PART_LD + k; dst = lg + P.oWz + j; }
+        else if ((j -= nWz) < nbz) { if (!video) continue; src = 128 * PART_LD + (j & 1) * 64 + (j >> 1); dst = lg + P.obz + j; }
+        else if ((j -= nbz) < nWrs) {
+            const int k = j / (CC + S), n = j % (CC + S);
+            if (n < CC && !has_resid) continue;
+            src = n * PART_LD + 192 + k; dst = lg + P.oWrs + j;
+        } else { j -= nWrs; if (j < CC && !has_resid) continue; src = 128 * PART_LD + 128 + j; dst = lg + P.obrs + j; }
+        float acc = 0.f;
+        for (int c = 0; c < n_cta; ++c) acc += partial[(size_t)c * PART_FLOATS + src];
+        *dst = acc;
+    }
+}
+
+}  // namespace
+
+size_t mvn_tc_bwd_partial_bytes() { return (size_t)148 * PART_FLOATS * 4; }
+
+int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const void* u_in, void* p_out, void* u_out,
+                     const float* dskip, float* dctx, const float* lw, float* lg, float* partial, const PackedLayout& P,
+                     const Geo& g, int layer, cudaStream_t st) {
+    MVN_REQUIRE(mvn_tc_layer_supported(g.C, g.S, g.video), "tensor-core layer kernel: unsupported channel counts");
+    CUtensorMap mx, mc, mp, mu, mpo, muo;
+    int rc;
+    if ((rc = make_act_map(&mx, x_in, g.B, g.T))) return rc;
+    if ((rc = make_act_map(&mc, g.video ? ctx : x_in, g.B, g.T))) return rc;
+    if ((rc = make_act_map(&mp, p_in, g.B, g.T))) return rc;
+    if ((rc = make_act_map(&mu, u_in, g.B, g.T))) return rc;
+    if ((rc = make_act_map(&mpo, p_out, g.B, g.T))) return rc;
+    if ((rc = make_act_map(&muo, u_out, g.B, g.T))) return rc;
+    BwdArgs a;
+    a.img = lw + P.oTc; a.dskip = dskip; a.dctx = g.video ? dctx : nullptr; a.partial = partial;
+    a.B = g.B; a.T = g.T; a.Tout = g.Tout; a.RF = g.RF; a.S = g.S; a.N2 = ((g.C + g.S + 15) / 16) * 16;
+    a.dil = g.dil[layer]; a.dil_up = layer + 1 < g.N ? g.dil[layer + 1] : 0;
+    a.nchunks = g.video ? 3 : 2;
+    a.tiles_per_clip = (g.T + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
+    const int smem = bwd_smem_total(a.nchunks, a.N2) + 1024;
+    MVN_REQUIRE(smem <= 227 * 1024, "tensor-core backward kernel: shared memory budget exceeded (%d)", smem);
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    int grid = 148;
+    if (grid > a.n_tiles) grid = a.n_tiles;
+    layer_bwd_tc_kernel<<<grid, 128, smem, st>>>(mx, mc, mp, mu, mpo, muo, a);
+    if ((rc = mvn_check_launch("layer_bwd_tc"))) return rc;
+    tc_bwd_reduce_kernel<<<64, 256, 0, st>>>(partial, grid, lg, P, g.S, g.Kz, g.video, layer + 1 < g.N);
+    return mvn_check_launch("tc_bwd_reduce");
+}

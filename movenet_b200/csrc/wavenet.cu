@@ -56,8 +56,10 @@ __global__ void input_fwd_kernel(const float* __restrict__ audio, const int* __r
 }
 
 // dWin[tap][a][c] += sum_t dh0[t][c] * x[a][t-1+tap]
+// d(h0)[t] = dh0[t] (+ dh0b[t + shift_b] when the gradient arrives as the (P, U) pair of the tensor-core path)
 __global__ void input_bwd_kernel(const float* __restrict__ audio, const int* __restrict__ codes,
-                                 const unsigned char* __restrict__ dense, const void* __restrict__ dh0, int adt,
+                                 const unsigned char* __restrict__ dense, const void* __restrict__ dh0,
+                                 const void* __restrict__ dh0b, int shift_b, int adt,
                                  float* __restrict__ dwin, int A, int C, int T, long long rows, int rows_per_cta,
                                  int use_smem) {
     extern __shared__ float sacc[];
@@ -76,7 +78,8 @@ __global__ void input_bwd_kernel(const float* __restrict__ audio, const int* __r
             if (!dense[r]) {
                 float* dst = acc + ((size_t)tap * A + codes[r]) * C;
                 for (int c = lane; c < C; c += 32) {
-                    const float g = mvn_ld(dh0, adt, row * C + c);
+                    float g = mvn_ld(dh0, adt, row * C + c);
+                    if (dh0b && t + shift_b < T) g += mvn_ld(dh0b, adt, (row + shift_b) * C + c);
                     if (g != 0.f) atomicAdd(dst + c, g);
                 }
             } else {
@@ -84,7 +87,11 @@ __global__ void input_bwd_kernel(const float* __restrict__ audio, const int* __r
                     const float x = audio[((size_t)b * A + a) * T + ts];
                     if (x == 0.f) continue;
                     float* dst = acc + ((size_t)tap * A + a) * C;
-                    for (int c = lane; c < C; c += 32) atomicAdd(dst + c, x * mvn_ld(dh0, adt, row * C + c));
+                    for (int c = lane; c < C; c += 32) {
+                        float g = mvn_ld(dh0, adt, row * C + c);
+                        if (dh0b && t + shift_b < T) g += mvn_ld(dh0b, adt, (row + shift_b) * C + c);
+                        atomicAdd(dst + c, x * g);
+                    }
                 }
             }
         }
@@ -472,7 +479,7 @@ static int layer_bwd(const Ctx& c, int l, const void* dx_next, void* dx_cur, flo
     return 0;
 }
 
-static int input_bwd(const Ctx& c, const float* audio, const void* dh0, float* pg) {
+static int input_bwd(const Ctx& c, const float* audio, const void* dh0, const void* dh0b, int shift_b, float* pg) {
     const Geo& g = c.g;
     const long long rows = (long long)g.B * g.T;
     const size_t smem = (size_t)2 * g.A * g.C * 4;
@@ -481,7 +488,7 @@ static int input_bwd(const Ctx& c, const float* audio, const void* dh0, float* p
     const int rpc = (int)((rows + ctas - 1) / ctas);
     MVN_CUDA(cudaFuncSetAttribute(input_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     input_bwd_kernel<<<mvn_cdiv(rows, rpc), 256, use_smem ? smem : 0, c.st>>>(
-        audio, (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), dh0, g.adt,
+        audio, (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), dh0, dh0b, shift_b, g.adt,
         pg + c.P.win, g.A, g.C, g.T, rows, rpc, use_smem);
     return mvn_check_launch("input_bwd");
 }
@@ -526,13 +533,31 @@ extern "C" int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, co
     MVN_CUDA(cudaMemsetAsync(pg, 0, c.P.total * 4, c.st));
     if ((rc = head_bwd(c, out, dout, pg))) return rc;
     if (g.video) MVN_CUDA(cudaMemsetAsync(c.scratch + c.SL.dctx, 0, (size_t)g.B * g.T * g.C * 4, c.st));
-    void* bufs[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};
-    const void* dx_next = nullptr; int cur = 0;
-    for (int l = g.N - 1; l >= 0; --l) {
-        if ((rc = layer_bwd(c, l, dx_next, bufs[cur], pg))) return rc;
-        dx_next = bufs[cur]; cur ^= 1;
+    if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
+        // tensor-core path: the stream gradient travels as (P, U), see layer_tc_bwd.cu
+        void* Pb[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};
+        void* Ub[2] = {c.scratch + c.SL.dgated, c.scratch + c.SL.dz};
+        const size_t nb = (size_t)g.B * g.T * g.C * g.es;
+        MVN_CUDA(cudaMemsetAsync(Pb[0], 0, nb, c.st));     // the last layer's residual output is discarded: zero gradient
+        MVN_CUDA(cudaMemsetAsync(Ub[0], 0, nb, c.st));
+        int cur = 0;
+        for (int l = g.N - 1; l >= 0; --l) {
+            float* lg = pg + c.P.layer0 + (size_t)l * c.P.layer_stride;
+            if ((rc = mvn_tc_layer_bwd(c.x(l), g.video ? c.acts + c.AL.ctx : nullptr, Pb[cur], Ub[cur], Pb[cur ^ 1], Ub[cur ^ 1],
+                                       (const float*)(c.scratch + c.SL.dskip), (float*)(c.scratch + c.SL.dctx), c.lw(l), lg,
+                                       (float*)(c.scratch + c.SL.tc_partial), c.P, g, l, c.st))) return rc;
+            cur ^= 1;
+        }
+        if ((rc = input_bwd(c, audio, Pb[cur], Ub[cur], g.dil[0], pg))) return rc;
+    } else {
+        void* bufs[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};
+        const void* dx_next = nullptr; int cur = 0;
+        for (int l = g.N - 1; l >= 0; --l) {
+            if ((rc = layer_bwd(c, l, dx_next, bufs[cur], pg))) return rc;
+            dx_next = bufs[cur]; cur ^= 1;
+        }
+        if ((rc = input_bwd(c, audio, dx_next, nullptr, 0, pg))) return rc;
     }
-    if ((rc = input_bwd(c, audio, dx_next, pg))) return rc;
     if (g.video && (rc = video_bwd(c, video, pg))) return rc;
     return 0;
 }
