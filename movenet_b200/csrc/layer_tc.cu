@@ -60,7 +60,7 @@ __global__ void tc_pack_kernel(const float* const* __restrict__ ptrs, float* __r
     }
 }
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_ctx,
                     const __grid_constant__ CUtensorMap map_out, const TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -97,10 +97,11 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     tc_fence_after();
     mbar_wait(full_bar, 0);
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t idesc1 = umma_idesc(TILE_T, 128), idesc2 = umma_idesc(TILE_T, a.N2);
     const uint32_t load_bytes = (uint32_t)(a.nchunks * TILE_BYTES);
-    const int r = tid;               // this thread's row of the tile == its TMEM lane
+    const int r = tid & 127;         // this thread's row of the tile == its TMEM lane (warps w and w+4 share a lane quarter
+    const int half = tid >> 7;       // and split the channel range between them)
     const int sw = r & 7;
 
     uint32_t it = 1;            // phase 0 of full_bar was the weight image
@@ -118,7 +119,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const bool live = t < a.T && js >= 0 && js < a.Tout;
         float* skip_dst = a.skip + ((size_t)b * a.Tout + (live ? js : 0)) * a.S;
         float4 old0 = make_float4(0.f, 0.f, 0.f, 0.f), old1 = old0;
-        if (live && !a.skip_init) { old0 = ((const float4*)skip_dst)[0]; old1 = ((const float4*)skip_dst)[1]; }
+        if (half == 0 && live && !a.skip_init) { old0 = ((const float4*)skip_dst)[0]; old1 = ((const float4*)skip_dst)[1]; }
         mbar_wait(full_bar, it & 1);
         if (tid == 0) {
             tc_fence_after();
@@ -133,7 +134,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tc_fence_after();
         // ---- epilogue 1: gate, bf16, into A0 as the next MMA's A operand ------------------------
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 2 * half; j < 2 * half + 2; ++j) {
             uint32_t f[16], g[16];
             tmem_ld16(tmem + lane_base + 16 * j, f);
             tmem_ld16(tmem + lane_base + 64 + 16 * j, g);
@@ -166,7 +167,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         // ---- epilogue 2: residual in place in the tap-1 tile; skip accumulation ------------------
         if (a.has_out) {
 #pragma unroll 1
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 2 * half; j < 2 * half + 2; ++j) {
                 uint32_t rr[16];
                 tmem_ld16(tmem + lane_base + D2_COL + 16 * j, rr);
                 tmem_ld_wait();
@@ -184,7 +185,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 *p1 = make_uint4(o[4], o[5], o[6], o[7]);
             }
         }
-        for (int s0 = 0; s0 < a.S; s0 += 8) {
+        for (int s0 = 8 * half; s0 < a.S; s0 += 16) {
             uint32_t sv[8];
             tmem_ld8(tmem + lane_base + D2_COL + CC + s0, sv);
             tmem_ld_wait();
@@ -250,8 +251,7 @@ int tc::make_act_map(CUtensorMap* map, const void* ptr, int B, int T) {
 }
 
 int mvn_tc_layer_supported(int C, int S, int video) {
-    (void)video;
-    return C == CC && S >= 8 && S % 8 == 0 && S <= 64;
+    return C == CC && S >= 8 && S % 8 == 0 && S <= (video ? 32 : 64);   // the backward kernel's shared-memory budget
 }
 
 int mvn_tc_pack(const float* const* param_ptrs_dev, float* packed, const PackedLayout& P, const Geo& g, cudaStream_t st) {
@@ -285,6 +285,6 @@ int mvn_tc_layer_fwd(const void* x_in, const void* ctx, void* x_out, float* skip
     }
     int grid = 2 * 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    layer_fwd_tc_kernel<<<grid, 128, smem, st>>>(map_x, map_ctx, map_out, a);
+    layer_fwd_tc_kernel<<<grid, 256, smem, st>>>(map_x, map_ctx, map_out, a);
     return mvn_check_launch("layer_fwd_tc");
 }

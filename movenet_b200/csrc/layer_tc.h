@@ -13,7 +13,8 @@ int mvn_tc_layer_fwd(const void* x_in, const void* ctx, void* x_out, float* skip
 int mvn_tc_pack(const float* const* param_ptrs_dev, float* packed, const PackedLayout& P, const Geo& g, cudaStream_t st);
 // Backward of one layer on tensor cores (layer_tc_bwd.cu).  The residual-stream gradient travels as the pair
 // (P, U): d(x_{l+1})[t] = P[t] + U[t + dilation_{l+1}].  lg = this layer's slot of the packed gradients.
+// q_in / q_out: running sum over layers of the context gradient, bf16 (B,T,C) (video only).
 size_t mvn_tc_bwd_partial_bytes();
 int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const void* u_in, void* p_out, void* u_out,
-                     const float* dskip, float* dctx, const float* lw, float* lg, float* partial, const PackedLayout& P,
+                     const float* dskip, const void* q_in, void* q_out, const float* lw, float* lg, float* partial, const PackedLayout& P,
                      const Geo& g, int layer, cudaStream_t st);

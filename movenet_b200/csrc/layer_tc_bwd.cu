@@ -33,19 +33,19 @@ constexpr int PART_FLOATS = 128 * PART_LD + 256;   // + bias sums of the two A o
 struct BwdArgs {
     const void* img;
     const float* dskip;   // (B, Tout, S) fp32
-    float* dctx;          // (B, T, C) fp32, accumulated; null without video
     float* partial;       // [grid][PART_FLOATS]
     int B, T, Tout, RF, S, N2, dil, dil_up, nchunks, tiles_per_clip, n_tiles;
 };
 
 __host__ __device__ inline int bwd_tiles_off(int nc, int N2) { return smem_a_off(nc, N2); }
-// tiles after the image: A0..A(nc-1) | DXS | DSK | U | DZ0 | DZ1 | G | ONES(1 KB) | barriers
-__host__ __device__ inline int bwd_smem_total(int nc, int N2) { return bwd_tiles_off(nc, N2) + (nc + 6) * TILE_BYTES + 1024 + 64; }
+// tiles after the image: A0..A(nc-1) | DXS | DSK | U | DZ0 | DZ1 | G | [Q, video only] | ONES(1 KB) | barriers
+__host__ __device__ inline int bwd_smem_total(int nc, int N2) { return bwd_tiles_off(nc, N2) + (nc + 6 + (nc == 3)) * TILE_BYTES + 1024 + 64; }
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_ctx,
                     const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_u,
                     const __grid_constant__ CUtensorMap map_pout, const __grid_constant__ CUtensorMap map_uout,
+                    const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_qout,
                     const BwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -59,14 +59,16 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint8_t* sU = sDSK + TILE_BYTES;
     uint8_t* sDZ = sU + TILE_BYTES;               // DZ0 (filter half) | DZ1 (gate half)
     uint8_t* sG = sDZ + 2 * TILE_BYTES;
-    uint8_t* sONES = sG + TILE_BYTES;
+    uint8_t* sQ = sG + TILE_BYTES;                // running sum of the context gradient (video only)
+    uint8_t* sONES = sQ + (nc == 3 ? TILE_BYTES : 0);
     uint64_t* full_bar = (uint64_t*)(sONES + 1024);
     uint64_t* mma_bar = full_bar + 1;
     uint64_t* w_bar = full_bar + 2;
     uint32_t* tmem_slot = (uint32_t*)(full_bar + 3);
 
     const int tid = threadIdx.x, warp = tid >> 5;
-    const int r = tid, sw = r & 7;
+    const int r = tid & 127, sw = r & 7;          // row of the tile == TMEM lane; warps w and w+4 share a lane quarter
+    const int half = tid >> 7;                    // ... and split the channel range between them
     const int NZ = nc * CC;                        // columns of D4 / dWz^T
 
     if (tid == 0) {
@@ -82,15 +84,15 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // constant tiles: DSK is zero outside the S live channels, ONES is all bf16 1.0
-    for (int i = tid; i < TILE_BYTES / 16; i += 128) ((uint4*)sDSK)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 1024 / 4; i += 128) ((uint32_t*)sONES)[i] = 0x3F803F80u;
+    for (int i = tid; i < TILE_BYTES / 16; i += 256) ((uint4*)sDSK)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 1024 / 4; i += 256) ((uint32_t*)sONES)[i] = 0x3F803F80u;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     mbar_wait(full_bar, 0);
     const uint32_t tmem = *tmem_slot;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
 
     const uint32_t iG1 = umma_idesc_major(TILE_T, 128, 0, 0);
     const uint32_t iG2 = umma_idesc_major(TILE_T, 64, 0, 1);
@@ -98,7 +100,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const uint32_t iW1 = umma_idesc_major(TILE_T, NZ, 1, 1);
     const uint32_t iW2 = umma_idesc_major(TILE_T, 64, 1, 1);
     const uint32_t iB = umma_idesc_major(TILE_T, 16, 1, 1);
-    const uint32_t load_bytes = (uint32_t)((nc + 2) * TILE_BYTES);
+    const uint32_t load_bytes = (uint32_t)((nc + 2 + (nc == 3)) * TILE_BYTES);
 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -112,8 +114,9 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             if (nc == 3) tma_load_3d(sA + 2 * TILE_BYTES, &map_ctx, full_bar, 0, t0, b);
             tma_load_3d(sDXS, &map_p, full_bar, 0, t0, b);
             tma_load_3d(sU, &map_u, full_bar, 0, t0 + a.dil_up, b);
+            if (nc == 3) tma_load_3d(sQ, &map_q, full_bar, 0, t0, b);
         }
-        {   // d(skip) row of this thread -> bf16, logical channels [0, S) of the DSK tile
+        if (half == 0) {   // d(skip) row of this thread -> bf16, logical channels [0, S) of the DSK tile
             const int js = t - (a.RF - 1);
             const bool live = t < a.T && js >= 0 && js < a.Tout;
             const float* src = a.dskip + ((size_t)b * a.Tout + (live ? js : 0)) * a.S;
@@ -127,7 +130,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         mbar_wait(full_bar, (it + 1) & 1);
         // ---- dxs = P + U(t + d_up), in place -----------------------------------------------------
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int q = 4 * half; q < 4 * half + 4; ++q) {
             uint4* pp = (uint4*)(sDXS + r * 128 + ((q ^ sw) << 4));
             const uint4 pv = *pp, uv = *(const uint4*)(sU + r * 128 + ((q ^ sw) << 4));
             const uint32_t pa[4] = {pv.x, pv.y, pv.z, pv.w}, ua[4] = {uv.x, uv.y, uv.z, uv.w};
@@ -160,7 +163,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tc_fence_after();
         // ---- epilogue 1: gate derivative -------------------------------------------------------
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 2 * half; j < 2 * half + 2; ++j) {
             uint32_t f[16], g[16], dg[16];
             tmem_ld16(tmem + lane_base + 16 * j, f);
             tmem_ld16(tmem + lane_base + 64 + 16 * j, g);
@@ -219,9 +222,9 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
         mbar_wait(mma_bar, 1);
         tc_fence_after();
-        // ---- epilogue 2a: P' = dxs + W1^T dz -> the U tile (free since the pre-sum); d(ctx) += V^T dz
+        // ---- epilogue 2a: P' = dxs + W1^T dz -> the U tile (free since the pre-sum); Q' = Q + V^T dz in place
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 2 * half; j < 2 * half + 2; ++j) {
             uint32_t v[16];
             tmem_ld16(tmem + lane_base + 64 + 16 * j, v);
             tmem_ld_wait();
@@ -238,28 +241,30 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             *(uint4*)(sU + r * 128 + (((2 * j + 1) ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
         }
         if (nc == 3) {
-            float4* dst = (float4*)(a.dctx + ((size_t)b * a.T + (t < a.T ? t : 0)) * CC);
 #pragma unroll 1
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 2 * half; j < 2 * half + 2; ++j) {
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + 128 + 16 * j, v);
                 tmem_ld_wait();
-                if (t < a.T) {
+                uint4* p0 = (uint4*)(sQ + r * 128 + (((2 * j) ^ sw) << 4));
+                uint4* p1 = (uint4*)(sQ + r * 128 + (((2 * j + 1) ^ sw) << 4));
+                const uint4 x0 = *p0, x1 = *p1;
+                const uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                uint32_t o[8];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float4 o = dst[4 * j + q];
-                        o.x += __uint_as_float(v[4 * q]); o.y += __uint_as_float(v[4 * q + 1]);
-                        o.z += __uint_as_float(v[4 * q + 2]); o.w += __uint_as_float(v[4 * q + 3]);
-                        dst[4 * j + q] = o;
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    const float2 xv = unpack_bf16(xi[i]);
+                    o[i] = pack_bf16(__uint_as_float(v[2 * i]) + xv.x, __uint_as_float(v[2 * i + 1]) + xv.y);
                 }
+                *p0 = make_uint4(o[0], o[1], o[2], o[3]);
+                *p1 = make_uint4(o[4], o[5], o[6], o[7]);
             }
         }
         // ---- epilogue 2b: once the weight-gradient MMAs no longer read DXS: U' = W0^T dz -> DXS tile
         mbar_wait(w_bar, it & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 2 * half; j < 2 * half + 2; ++j) {
             uint32_t v[16];
             tmem_ld16(tmem + lane_base + 16 * j, v);
             tmem_ld_wait();
@@ -275,6 +280,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         if (tid == 0) {
             tma_store_3d(&map_pout, sU, 0, t0, b);
             tma_store_3d(&map_uout, sDXS, 0, t0, b);
+            if (nc == 3) tma_store_3d(&map_qout, sQ, 0, t0, b);
             tma_commit();
         }
     }
@@ -283,7 +289,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     float* part = a.partial + (size_t)blockIdx.x * PART_FLOATS;
     float* prow = part + (size_t)r * PART_LD;
 #pragma unroll 1
-    for (int j = 0; j < NZ / 16; ++j) {
+    for (int j = half; j < NZ / 16; j += 2) {
         uint32_t v[16];
         tmem_ld16(tmem + lane_base + W1_COL + 16 * j, v);
         tmem_ld_wait();
@@ -293,7 +299,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                                                         __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
     }
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
+    for (int j = half; j < 4; j += 2) {
         uint32_t v[16];
         tmem_ld16(tmem + lane_base + W2_COL + 16 * j, v);
         tmem_ld_wait();
@@ -307,8 +313,10 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tmem_ld8(tmem + lane_base + B1_COL, v1);
         tmem_ld8(tmem + lane_base + B2_COL, v2);
         tmem_ld_wait();
-        part[128 * PART_LD + r] = __uint_as_float(v1[0]);
-        part[128 * PART_LD + 128 + r] = __uint_as_float(v2[0]);
+        if (half == 0) {
+            part[128 * PART_LD + r] = __uint_as_float(v1[0]);
+            part[128 * PART_LD + 128 + r] = __uint_as_float(v2[0]);
+        }
     }
     if (tid == 0) tma_wait_all0();
     tc_fence_before();
@@ -323,19 +331,25 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 //   dWz[k][2c+gate] = sum_cta part[gate*64+c][k] ; dbz likewise ; dWrs[k][n] = sum_cta part[n'][192+k] ; dbrs.
 __global__ void tc_bwd_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ lg, PackedLayout P,
                                      int S, int Kz, int video, int has_resid) {
-    const int nWz = Kz * 128, nbz = 128, nWrs = CC * (CC + S), nbrs = CC + S;
-    const int total = nWz + nbz + nWrs + nbrs;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int j = i, src; float* dst;
-        if (j < nWz) { const int k = j / 128, n = j % 128; src = ((n & 1) * 64 + (n >> 1)) * PART_LD + k; dst = lg + P.oWz + j; }
-        else if ((j -= nWz) < nbz) { if (!video) continue; src = 128 * PART_LD + (j & 1) * 64 + (j >> 1); dst = lg + P.obz + j; }
-        else if ((j -= nbz) < nWrs) {
-            const int k = j / (CC + S), n = j % (CC + S);
-            if (n < CC && !has_resid) continue;
-            src = n * PART_LD + 192 + k; dst = lg + P.oWrs + j;
-        } else { j -= nWrs; if (j < CC && !has_resid) continue; src = 128 * PART_LD + 128 + j; dst = lg + P.obrs + j; }
+    // one thread per SOURCE element so the n_cta reads of a warp are coalesced; the destination is scattered
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < PART_FLOATS; i += gridDim.x * blockDim.x) {
+        float* dst = nullptr;
+        if (i < 128 * PART_LD) {
+            const int m = i / PART_LD, col = i % PART_LD;
+            if (col < 192) {                       // dWz^T[m = gate*64 + c][k = col]
+                if (col < Kz) dst = lg + P.oWz + (size_t)col * 128 + 2 * (m & 63) + (m >> 6);
+            } else {                               // dWrs^T[m = c_out | 64 + s][k = col - 192]
+                const int n = m;                   // C == 64: column n of Wrs is row m
+                if (n < CC + S && (n >= CC || has_resid)) dst = lg + P.oWrs + (size_t)(col - 192) * (CC + S) + n;
+            }
+        } else {
+            const int j = i - 128 * PART_LD;
+            if (j < 128) { if (video) dst = lg + P.obz + 2 * (j & 63) + (j >> 6); }
+            else { const int n = j - 128; if (n < CC + S && (n >= CC || has_resid)) dst = lg + P.obrs + n; }
+        }
+        if (!dst) continue;
         float acc = 0.f;
-        for (int c = 0; c < n_cta; ++c) acc += partial[(size_t)c * PART_FLOATS + src];
+        for (int c = 0; c < n_cta; ++c) acc += partial[(size_t)c * PART_FLOATS + i];
         *dst = acc;
     }
 }
@@ -345,10 +359,10 @@ __global__ void tc_bwd_reduce_kernel(const float* __restrict__ partial, int n_ct
 size_t mvn_tc_bwd_partial_bytes() { return (size_t)148 * PART_FLOATS * 4; }
 
 int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const void* u_in, void* p_out, void* u_out,
-                     const float* dskip, float* dctx, const float* lw, float* lg, float* partial, const PackedLayout& P,
+                     const float* dskip, const void* q_in, void* q_out, const float* lw, float* lg, float* partial, const PackedLayout& P,
                      const Geo& g, int layer, cudaStream_t st) {
     MVN_REQUIRE(mvn_tc_layer_supported(g.C, g.S, g.video), "tensor-core layer kernel: unsupported channel counts");
-    CUtensorMap mx, mc, mp, mu, mpo, muo;
+    CUtensorMap mx, mc, mp, mu, mpo, muo, mq, mqo;
     int rc;
     if ((rc = make_act_map(&mx, x_in, g.B, g.T))) return rc;
     if ((rc = make_act_map(&mc, g.video ? ctx : x_in, g.B, g.T))) return rc;
@@ -356,8 +370,10 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     if ((rc = make_act_map(&mu, u_in, g.B, g.T))) return rc;
     if ((rc = make_act_map(&mpo, p_out, g.B, g.T))) return rc;
     if ((rc = make_act_map(&muo, u_out, g.B, g.T))) return rc;
+    if ((rc = make_act_map(&mq, g.video ? q_in : x_in, g.B, g.T))) return rc;
+    if ((rc = make_act_map(&mqo, g.video ? q_out : p_out, g.B, g.T))) return rc;
     BwdArgs a;
-    a.img = lw + P.oTc; a.dskip = dskip; a.dctx = g.video ? dctx : nullptr; a.partial = partial;
+    a.img = lw + P.oTc; a.dskip = dskip; a.partial = partial;
     a.B = g.B; a.T = g.T; a.Tout = g.Tout; a.RF = g.RF; a.S = g.S; a.N2 = ((g.C + g.S + 15) / 16) * 16;
     a.dil = g.dil[layer]; a.dil_up = layer + 1 < g.N ? g.dil[layer + 1] : 0;
     a.nchunks = g.video ? 3 : 2;
@@ -371,8 +387,8 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     }
     int grid = 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    layer_bwd_tc_kernel<<<grid, 128, smem, st>>>(mx, mc, mp, mu, mpo, muo, a);
+    layer_bwd_tc_kernel<<<grid, 256, smem, st>>>(mx, mc, mp, mu, mpo, muo, mq, mqo, a);
     if ((rc = mvn_check_launch("layer_bwd_tc"))) return rc;
-    tc_bwd_reduce_kernel<<<64, 256, 0, st>>>(partial, grid, lg, P, g.S, g.Kz, g.video, layer + 1 < g.N);
+    tc_bwd_reduce_kernel<<<(PART_FLOATS + 255) / 256, 256, 0, st>>>(partial, grid, lg, P, g.S, g.Kz, g.video, layer + 1 < g.N);
     return mvn_check_launch("tc_bwd_reduce");
 }

@@ -493,13 +493,14 @@ static int input_bwd(const Ctx& c, const float* audio, const void* dh0, const vo
     return mvn_check_launch("input_bwd");
 }
 
-static int video_bwd(const Ctx& c, const float* video, float* pg) {
+static int video_bwd(const Ctx& c, const float* video, const void* dctx, int dctx_dtype, float* pg) {
     const Geo& g = c.g; const int C = g.C;
     const float* enc = (const float*)(c.acts + c.AL.enc); const float* u1 = (const float*)(c.acts + c.AL.u1);
     const float* u2 = (const float*)(c.acts + c.AL.u2);
-    float* dctx = (float*)(c.scratch + c.SL.dctx); float* du2 = (float*)(c.scratch + c.SL.du2);
+    float* du2 = (float*)(c.scratch + c.SL.du2);
     float* du1 = (float*)(c.scratch + c.SL.du1); float* denc = (float*)(c.scratch + c.SL.denc);
-    const float* in[3] = {enc, u1, u2}; const float* dout[3] = {du1, du2, dctx}; float* din[3] = {denc, du1, du2};
+    const float* in[3] = {enc, u1, u2}; const void* dout[3] = {du1, du2, dctx}; float* din[3] = {denc, du1, du2};
+    const int ddt[3] = {MVN_F32, MVN_F32, dctx_dtype};
     const int len[3] = {160, 1600, 16000};
     int rc;
     for (int i = 2; i >= 0; --i) {
@@ -507,10 +508,10 @@ static int video_bwd(const Ctx& c, const float* video, float* pg) {
         TnGemmArgs t; memset(&t, 0, sizeof(t));
         t.rows = rows; t.Trow = rows; t.N = 10 * C; t.nsrc = 1;
         t.src[0] = make_tn(in[i], MVN_F32, C, C, rows, 0, 0, pg + c.P.wt[i], 10 * C);
-        t.q = dout[i]; t.q_dtype = MVN_F32; t.ldq = 10 * C; t.q_T = rows; t.q_shift = 0; t.dbias = pg + c.P.bt[i];
+        t.q = dout[i]; t.q_dtype = ddt[i]; t.ldq = 10 * C; t.q_T = rows; t.q_shift = 0; t.dbias = pg + c.P.bt[i];
         if ((rc = mvn_tn_gemm(t, c.st))) return rc;
         RowGemmArgs a = new_args(rows, rows, C, EPI_STORE, nullptr);
-        a.nsrc = 1; a.src[0] = make_src(dout[i], MVN_F32, 10 * C, 10 * C, rows, 0, 0, c.packed + c.P.wtT[i], C);
+        a.nsrc = 1; a.src[0] = make_src(dout[i], ddt[i], 10 * C, 10 * C, rows, 0, 0, c.packed + c.P.wtT[i], C);
         set_out(a, din[i], MVN_F32, C, rows, 0);
         if ((rc = mvn_row_gemm(a, c.st))) return rc;
     }
@@ -533,6 +534,7 @@ extern "C" int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, co
     MVN_CUDA(cudaMemsetAsync(pg, 0, c.P.total * 4, c.st));
     if ((rc = head_bwd(c, out, dout, pg))) return rc;
     if (g.video) MVN_CUDA(cudaMemsetAsync(c.scratch + c.SL.dctx, 0, (size_t)g.B * g.T * g.C * 4, c.st));
+    const void* dctx_final = c.scratch + c.SL.dctx; int dctx_dtype = MVN_F32;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
         // tensor-core path: the stream gradient travels as (P, U), see layer_tc_bwd.cu
         void* Pb[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};
@@ -540,15 +542,18 @@ extern "C" int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, co
         const size_t nb = (size_t)g.B * g.T * g.C * g.es;
         MVN_CUDA(cudaMemsetAsync(Pb[0], 0, nb, c.st));     // the last layer's residual output is discarded: zero gradient
         MVN_CUDA(cudaMemsetAsync(Ub[0], 0, nb, c.st));
+        // running sum of the context gradient, bf16, ping-pong inside the (zeroed) fp32 dctx slot
+        void* Qb[2] = {c.scratch + c.SL.dctx, c.scratch + c.SL.dctx + nb};
         int cur = 0;
         for (int l = g.N - 1; l >= 0; --l) {
             float* lg = pg + c.P.layer0 + (size_t)l * c.P.layer_stride;
             if ((rc = mvn_tc_layer_bwd(c.x(l), g.video ? c.acts + c.AL.ctx : nullptr, Pb[cur], Ub[cur], Pb[cur ^ 1], Ub[cur ^ 1],
-                                       (const float*)(c.scratch + c.SL.dskip), (float*)(c.scratch + c.SL.dctx), c.lw(l), lg,
+                                       (const float*)(c.scratch + c.SL.dskip), Qb[cur], Qb[cur ^ 1], c.lw(l), lg,
                                        (float*)(c.scratch + c.SL.tc_partial), c.P, g, l, c.st))) return rc;
             cur ^= 1;
         }
         if ((rc = input_bwd(c, audio, Pb[cur], Ub[cur], g.dil[0], pg))) return rc;
+        dctx_final = Qb[cur]; dctx_dtype = MVN_BF16;
     } else {
         void* bufs[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};
         const void* dx_next = nullptr; int cur = 0;
@@ -558,6 +563,6 @@ extern "C" int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, co
         }
         if ((rc = input_bwd(c, audio, dx_next, nullptr, 0, pg))) return rc;
     }
-    if (g.video && (rc = video_bwd(c, video, pg))) return rc;
+    if (g.video && (rc = video_bwd(c, video, dctx_final, dctx_dtype, pg))) return rc;
     return 0;
 }

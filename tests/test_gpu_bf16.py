@@ -16,9 +16,9 @@ LOSS_RTOL = 1e-3
 # bf16 activations AND bf16 activation-gradients: every weight gradient is a sum over ~1e2..1e5 time
 # steps of products of rounded terms with heavy cancellation, so the per-tensor error is a few
 # percent (up to ~12 % for the deepest tensor of the gain-2.5 fixture).  Stated tolerance: 25 %
-# relative L2 per tensor and cosine similarity >= 0.995 over the whole gradient.
+# relative L2 per tensor and cosine similarity >= 0.99 over the whole gradient.
 GRAD_RTOL = 0.25
-GRAD_COS = 0.995
+GRAD_COS = 0.99
 
 
 def build(fx, dtype):
