@@ -184,7 +184,9 @@ extern "C" int mvn_pack_weights(const mvn_shape_t* s, const void* const* param_p
     int rc = mvn_check_launch("pack_weights");
     if (rc) return rc;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video))
-        return mvn_tc_pack(ptrs, (float*)packed, P, g, st);
+        if ((rc = mvn_tc_pack(ptrs, (float*)packed, P, g, st))) return rc;
+    if (g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S))   // conv2.weight is (A, A, 1): already [n][k]
+        if ((rc = mvn_tc_head_pack((const float*)packed + P.w2pT, (float*)packed, P, st))) return rc;
     return 0;
 }
 

@@ -30,13 +30,14 @@ __global__ void codes_kernel(const float* __restrict__ audio, int A, int T, int*
 __global__ void input_fwd_kernel(const float* __restrict__ audio, const int* __restrict__ codes,
                                  const unsigned char* __restrict__ dense, const float* __restrict__ win,
                                  void* __restrict__ h0, int adt, int A, int C, int T, long long rows) {
-    const int cg = (C + 3) / 4;
+    const int cg = (C + 7) / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * cg) return;
     const long long row = idx / cg;
-    const int c0 = (int)(idx % cg) * 4;
+    const int c0 = (int)(idx % cg) * 8;
     const long long b = row / T; const int t = (int)(row % T);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool vec = (C % 8 == 0);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int tap = 0; tap < 2; ++tap) {
         const int ts = t - 1 + tap;
         if (ts < 0) continue;
@@ -44,15 +45,66 @@ __global__ void input_fwd_kernel(const float* __restrict__ audio, const int* __r
         const float* wt = win + (size_t)tap * A * C;
         if (!dense[r]) {
             const float* wr = wt + (size_t)codes[r] * C + c0;
-            for (int j = 0; j < 4 && c0 + j < C; ++j) acc[j] += wr[j];
+            if (vec) {
+                const float4 w0 = ((const float4*)wr)[0], w1 = ((const float4*)wr)[1];
+                acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
+                acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
+            } else {
+                for (int j = 0; j < 8 && c0 + j < C; ++j) acc[j] += wr[j];
+            }
         } else {
             for (int a = 0; a < A; ++a) {
                 const float x = audio[((size_t)b * A + a) * T + ts];
-                if (x != 0.f) for (int j = 0; j < 4 && c0 + j < C; ++j) acc[j] = fmaf(x, wt[(size_t)a * C + c0 + j], acc[j]);
+                if (x != 0.f) for (int j = 0; j < 8 && c0 + j < C; ++j) acc[j] = fmaf(x, wt[(size_t)a * C + c0 + j], acc[j]);
             }
         }
     }
-    for (int j = 0; j < 4 && c0 + j < C; ++j) mvn_st(h0, adt, row * C + c0 + j, acc[j]);
+    if (vec && adt == MVN_BF16) {
+        __nv_bfloat162 o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+        *(uint4*)((__nv_bfloat16*)h0 + row * C + c0) = *(const uint4*)o;
+    } else if (vec) {
+        float4* d = (float4*)((float*)h0 + row * C + c0);
+        d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]); d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+        for (int j = 0; j < 8 && c0 + j < C; ++j) mvn_st(h0, adt, row * C + c0 + j, acc[j]);
+    }
+}
+
+// Conv3d with a (1,64,64) kernel over 160-frame clips: [B*160 rows] x [4096*Cin] . [4096*Cin x C].  Few rows, long K:
+// split K over CTAs (8 rows x all channels x one K slice each) and add the slices with fp32 atomics into the
+// bias-initialised output.
+__global__ void video_conv_init_kernel(float* __restrict__ enc, const float* __restrict__ bias, int rows, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * C) enc[i] = bias[i % C];
+}
+#define VC_ROWS 8
+#define VC_K 512
+__global__ void __launch_bounds__(256) video_conv_kernel(const float* __restrict__ video, const float* __restrict__ wv,
+                                                         float* __restrict__ enc, int rows, int K, int C) {
+    __shared__ float xs[VC_ROWS][VC_K];
+    const int r0 = blockIdx.x * VC_ROWS, k0 = blockIdx.y * VC_K;
+    for (int i = threadIdx.x; i < VC_ROWS * VC_K; i += blockDim.x) {
+        const int rr = i / VC_K, kk = i % VC_K;
+        xs[rr][kk] = (r0 + rr < rows && k0 + kk < K) ? video[(size_t)(r0 + rr) * K + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+    const int cpg = blockDim.x / 4;              // threads per row group
+    const int grp = threadIdx.x / cpg, cl = threadIdx.x % cpg;
+    for (int c = cl; c < C; c += cpg) {
+        float a0 = 0.f, a1 = 0.f;
+        const float* w = wv + (size_t)k0 * C + c;
+        const int kmax = min(VC_K, K - k0);
+#pragma unroll 8
+        for (int kk = 0; kk < kmax; ++kk) {
+            const float wvv = w[(size_t)kk * C];
+            a0 = fmaf(xs[2 * grp][kk], wvv, a0);
+            a1 = fmaf(xs[2 * grp + 1][kk], wvv, a1);
+        }
+        if (r0 + 2 * grp < rows) atomicAdd(enc + (size_t)(r0 + 2 * grp) * C + c, a0);
+        if (r0 + 2 * grp + 1 < rows) atomicAdd(enc + (size_t)(r0 + 2 * grp + 1) * C + c, a1);
+    }
 }
 
 // dWin[tap][a][c] += sum_t dh0[t][c] * x[a][t-1+tap]
@@ -237,7 +289,7 @@ static int input_fwd(const Ctx& c, const float* audio) {
     int* codes = (int*)(c.acts + c.AL.codes); unsigned char* dense = (unsigned char*)(c.acts + c.AL.dense);
     int rc = mvn_onehot_to_codes(audio, g.B, g.A, g.T, codes, dense, c.st);
     if (rc) return rc;
-    const long long rows = (long long)g.B * g.T, n = rows * ((g.C + 3) / 4);
+    const long long rows = (long long)g.B * g.T, n = rows * ((g.C + 7) / 8);
     input_fwd_kernel<<<mvn_cdiv(n, 256), 256, 0, c.st>>>(audio, codes, dense, c.packed + c.P.win, c.x(0), g.adt, g.A, g.C, g.T, rows);
     return mvn_check_launch("input_fwd");
 }
@@ -249,10 +301,11 @@ static int video_fwd(const Ctx& c, const float* video) {
     int rc;
     {   // Conv3d with a (1,64,64) kernel = one 4096*Cin -> C linear map per frame (movenet/wavenet.py:94-98,152)
         const int rows = g.B * 160, K = 4096 * g.Cin;
-        RowGemmArgs a = new_args(rows, rows, C, EPI_STORE, c.packed + c.P.bv);
-        a.nsrc = 1; a.src[0] = make_src(video, MVN_F32, K, K, rows, 0, 0, c.packed + c.P.wv, C);
-        set_out(a, enc, MVN_F32, C, rows, 0);
-        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+        video_conv_init_kernel<<<mvn_cdiv((long long)rows * C, 256), 256, 0, c.st>>>(enc, c.packed + c.P.bv, rows, C);
+        if ((rc = mvn_check_launch("video_conv_init"))) return rc;
+        dim3 grid(mvn_cdiv(rows, VC_ROWS), mvn_cdiv(K, VC_K));
+        video_conv_kernel<<<grid, 256, 0, c.st>>>(video, c.packed + c.P.wv, enc, rows, K, C);
+        if ((rc = mvn_check_launch("video_conv"))) return rc;
     }
     // ConvTranspose1d(k=10, stride=10): out[10 i + j] = W[:, :, j]^T in[i] + b -- a [rows x C] x [C x 10C] GEMM whose
     // row-major output IS the time-major upsampled signal (movenet/wavenet.py:102-118,154)
@@ -304,6 +357,8 @@ static int head_fwd(const Ctx& c, float* out) {
     if (g.Tn <= 0) return 0;
     const long long rows = (long long)g.B * g.Tn;
     float* skip = (float*)(c.acts + c.AL.skip); float* a1 = (float*)(c.acts + c.AL.a1); float* z = (float*)(c.scratch + c.SL.z);
+    if (g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S))
+        return mvn_tc_head_fwd(c.packed, c.P, g, skip, out, c.st);
     int rc;
     RowGemmArgs a = new_args(rows, g.Tn, g.A, EPI_STORE, c.packed + c.P.b1);
     a.nsrc = 1; a.src[0] = make_src(skip, MVN_F32, g.S, g.S, g.Tout, 0, 1, c.packed + c.P.w1p, g.A);
@@ -372,6 +427,8 @@ static int head_bwd(const Ctx& c, const float* out, const float* dout, float* pg
     float* dzh = (float*)(c.scratch + c.SL.z); float* da1 = (float*)(c.scratch + c.SL.da1); float* dskip = (float*)(c.scratch + c.SL.dskip);
     MVN_CUDA(cudaMemsetAsync(dskip, 0, (size_t)g.B * g.Tout * g.S * 4, c.st));
     if (g.Tn <= 0) return 0;
+    if (g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S))
+        return mvn_tc_head_bwd(c.packed, c.P, g, skip, out, dout, dskip, pg, (float*)(c.scratch + c.SL.tc_partial), c.st);
     const long long rows = (long long)g.B * g.Tn;
     int rc;
     dim3 grid(mvn_cdiv(g.Tn, 32), g.B);
