@@ -1,0 +1,156 @@
+// Weight gradient of the causal input conv (movenet/modules.py:15-30) on tensor cores, A = C = 64:
+//   dW[c][a][tap] = sum_t d(h0)[t][c] * x[a][t-1+tap]
+// With one-hot audio x is a one-hot matrix, so this is  OneHot^T . d(h0)  with K = time: the one-hot tiles
+// [time x 64 codes] are built in shared memory from the integer codes (exact in bf16) and used as the
+// MN-major M operand (tap 0 | tap 1 = the two 64-row halves of M = 128), d(h0) arrives as the (P, U) tile
+// pair of the tensor-core backward (two accumulating MMA chains).  Columns that are not one-hot put
+// their real values into the tile (bf16-rounded).
+#include "tc_common.cuh"
+#include "layer_tc.h"
+
+using namespace tc;
+
+namespace {
+
+constexpr int IPART = 128 * 64;
+
+struct InArgs {
+    const float* audio; const int* codes; const unsigned char* dense;
+    float* partial;
+    int B, T, A, dil0, tiles_per_clip, n_tiles;
+};
+
+__global__ void __launch_bounds__(128, 3)
+input_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_u, const InArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sOH = smem;                        // OH0 | OH1
+    uint8_t* sP = smem + 2 * TILE_BYTES;
+    uint8_t* sU = sP + TILE_BYTES;
+    uint64_t* full_bar = (uint64_t*)(sU + TILE_BYTES);
+    uint64_t* w_bar = full_bar + 1;
+    uint32_t* tmem_slot = (uint32_t*)(full_bar + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, r = tid, sw = r & 7;
+
+    if (tid == 0) { mbar_init(full_bar, 1); mbar_init(w_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t idesc = umma_idesc_major(TILE_T, 64, 1, 1);
+
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T, t = t0 + r;
+        if (it) { mbar_wait(w_bar, (it - 1) & 1); tc_fence_after(); }     // the previous tile's MMAs are done with the tiles
+        if (tid == 0) {
+            mbar_expect_tx(full_bar, 2 * TILE_BYTES);
+            tma_load_3d(sP, &map_p, full_bar, 0, t0, b);
+            tma_load_3d(sU, &map_u, full_bar, 0, t0 + a.dil0, b);
+        }
+        // one-hot rows of this time step: tap 1 looks at x[t], tap 0 at x[t-1]
+#pragma unroll
+        for (int tap = 0; tap < 2; ++tap) {
+            uint8_t* row = sOH + tap * TILE_BYTES + r * 128;
+            const int ts = t - 1 + tap;
+            const bool in = t < a.T && ts >= 0;
+            const long long gr = (long long)b * a.T + (in ? ts : 0);
+            if (in && a.dense[gr]) {
+                for (int q = 0; q < 8; ++q) {
+                    float v[8];
+                    for (int e = 0; e < 8; ++e) {
+                        const int ch = 8 * q + e;
+                        v[e] = ch < a.A ? a.audio[((size_t)b * a.A + ch) * a.T + ts] : 0.f;
+                    }
+                    *(uint4*)(row + ((q ^ sw) << 4)) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                }
+            } else {
+                const int code = in ? a.codes[gr] : -1;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    uint4 z = make_uint4(0, 0, 0, 0);
+                    if ((code >> 3) == q) {
+                        const uint32_t one = (code & 1) ? 0x3F800000u : 0x00003F80u;
+                        const int w = (code & 7) >> 1;
+                        if (w == 0) z.x = one; else if (w == 1) z.y = one; else if (w == 2) z.z = one; else z.w = one;
+                    }
+                    *(uint4*)(row + ((q ^ sw) << 4)) = z;
+                }
+            }
+        }
+        fence_proxy_async();
+        mbar_wait(full_bar, it & 1);
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t acc0 = it != 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint64_t oh = umma_desc_mn(smem_u32(sOH) + k * 2048, TILE_BYTES);
+                umma(tmem, oh, umma_desc_mn(smem_u32(sP) + k * 2048, TILE_BYTES), idesc, acc0 | (k != 0));
+                umma(tmem, oh, umma_desc_mn(smem_u32(sU) + k * 2048, TILE_BYTES), idesc, 1);
+            }
+            umma_commit(w_bar);
+        }
+    }
+    if (it) mbar_wait(w_bar, (it - 1) & 1);
+    tc_fence_after();
+    float* part = a.partial + (size_t)blockIdx.x * IPART + (size_t)r * 64;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        uint32_t v[16];
+        tmem_ld16(tmem + lane_base + 16 * j, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            ((float4*)(part + 16 * j))[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                        __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(64) : "memory");
+    }
+}
+
+// dwin[tap][a][c] = sum_cta part[tap*64 + a][c]
+__global__ void input_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ dwin, int A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= IPART) return;
+    const int m = i >> 6, c = i & 63, tap = m >> 6, ch = m & 63;
+    if (ch >= A) return;
+    float acc = 0.f;
+    for (int k = 0; k < n_cta; ++k) acc += partial[(size_t)k * IPART + i];
+    dwin[((size_t)tap * A + ch) * 64 + c] = acc;
+}
+
+}  // namespace
+
+int mvn_tc_input_supported(int A, int C) { return C == 64 && A <= 64; }
+
+int mvn_tc_input_bwd(const float* audio, const int* codes, const unsigned char* dense, const void* p, const void* u,
+                     float* dwin, float* partial, const Geo& g, cudaStream_t st) {
+    CUtensorMap mp, mu;
+    int rc;
+    if ((rc = make_act_map(&mp, p, g.B, g.T))) return rc;
+    if ((rc = make_act_map(&mu, u, g.B, g.T))) return rc;
+    InArgs a;
+    a.audio = audio; a.codes = codes; a.dense = dense; a.partial = partial;
+    a.B = g.B; a.T = g.T; a.A = g.A; a.dil0 = g.dil[0];
+    a.tiles_per_clip = (g.T + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
+    const int smem = 4 * TILE_BYTES + 64 + 1024;
+    static bool attr = false;
+    if (!attr) { MVN_CUDA(cudaFuncSetAttribute(input_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    const int grid = a.n_tiles < 3 * 148 ? a.n_tiles : 3 * 148;
+    input_bwd_tc_kernel<<<grid, 128, smem, st>>>(mp, mu, a);
+    if ((rc = mvn_check_launch("input_bwd_tc"))) return rc;
+    input_reduce_kernel<<<(IPART + 255) / 256, 256, 0, st>>>(partial, grid, dwin, g.A);
+    return mvn_check_launch("input_reduce");
+}

@@ -609,7 +609,10 @@ extern "C" int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, co
                                        (float*)(c.scratch + c.SL.tc_partial), c.P, g, l, c.st))) return rc;
             cur ^= 1;
         }
-        if ((rc = input_bwd(c, audio, Pb[cur], Ub[cur], g.dil[0], pg))) return rc;
+        if (mvn_tc_input_supported(g.A, g.C)) {
+            if ((rc = mvn_tc_input_bwd(audio, (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), Pb[cur],
+                                       Ub[cur], pg + c.P.win, (float*)(c.scratch + c.SL.tc_partial), g, c.st))) return rc;
+        } else if ((rc = input_bwd(c, audio, Pb[cur], Ub[cur], g.dil[0], pg))) return rc;
         dctx_final = Qb[cur]; dctx_dtype = MVN_BF16;
     } else {
         void* bufs[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};
