@@ -113,6 +113,13 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             tma_load_3d(sA0, &map_x, full_bar, 0, t0 - a.dil, b);
             tma_load_3d(sA1, &map_x, full_bar, 0, t0, b);
             if (a.nchunks == 3) tma_load_3d(sA2, &map_ctx, full_bar, 0, t0, b);
+            const int nt = tile + gridDim.x;       // this CTA's next tile: start pulling it into L2 now
+            if (nt < a.n_tiles) {
+                const int nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
+                tma_prefetch_3d(&map_x, 0, n0 - a.dil, nb);
+                tma_prefetch_3d(&map_x, 0, n0, nb);
+                if (a.nchunks == 3) tma_prefetch_3d(&map_ctx, 0, n0, nb);
+            }
         }
         // the running skip sum of this row: fetch it now, it is only needed at the very end of the tile
         const int t = t0 + r, js = t - (a.RF - 1);

@@ -115,6 +115,15 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             tma_load_3d(sDXS, &map_p, full_bar, 0, t0, b);
             tma_load_3d(sU, &map_u, full_bar, 0, t0 + a.dil_up, b);
             if (nc == 3) tma_load_3d(sQ, &map_q, full_bar, 0, t0, b);
+            const int nt = tile + gridDim.x;       // this CTA's next tile: start pulling it into L2 now
+            if (nt < a.n_tiles) {
+                const int nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
+                tma_prefetch_3d(&map_x, 0, n0 - a.dil, nb);
+                tma_prefetch_3d(&map_x, 0, n0, nb);
+                if (nc == 3) { tma_prefetch_3d(&map_ctx, 0, n0, nb); tma_prefetch_3d(&map_q, 0, n0, nb); }
+                tma_prefetch_3d(&map_p, 0, n0, nb);
+                tma_prefetch_3d(&map_u, 0, n0 + a.dil_up, nb);
+            }
         }
         if (half == 0) {   // d(skip) row of this thread -> bf16, logical channels [0, S) of the DSK tile
             const int js = t - (a.RF - 1);
