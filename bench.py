@@ -172,8 +172,18 @@ def timed(fn, steps, warmup, sync):
     return ev0.elapsed_time(ev1)
 
 
+def _ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None"""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel)
+    except (OSError, ValueError):
+        return None
+
+
 def layer_roofline(model, audio, video, dtype):
-    """time the residual-layer forward stage live (CUDA events on the launching stream)"""
+    """time the residual-layer kernels live (CUDA events on the launching stream): backward (the dominant kernel
+    of the step) and forward"""
     import ctypes as C
     from movenet_b200 import _lib
     B = audio.shape[0]
@@ -183,34 +193,57 @@ def layer_roofline(model, audio, video, dtype):
     acts = torch.empty(bufs.acts_bytes, dtype=torch.uint8, device=audio.device)
     out = torch.empty(B, model.input_channels, T_CLIP - model.receptive_fields, device=audio.device)
     st = torch.cuda.current_stream().cuda_stream
-    _lib.call("mvn_wavenet_forward", C.byref(shape), bufs.packed.data_ptr(), audio.data_ptr(),
-              0 if video is None else video.data_ptr(), acts.data_ptr(), out.data_ptr(), bufs.get_scratch().data_ptr(), st)
-    layers = list(range(1, model.layer_size * model.stack_size - 1))     # interior layers: all write a residual
-    n0 = _lib.load().mvn_launch_count()
-    for l in layers:
-        _lib.call("mvn_layer_fwd", C.byref(shape), bufs.packed.data_ptr(), l, acts.data_ptr(), bufs.get_scratch().data_ptr(), st)
-    launches_per_layer = (_lib.load().mvn_launch_count() - n0) / len(layers)
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 3
-    ev0.record()
-    for _ in range(reps):
-        for l in layers:     # each layer streams > L2 worth of activations, so every launch starts cold
-            _lib.call("mvn_layer_fwd", C.byref(shape), bufs.packed.data_ptr(), l, acts.data_ptr(), bufs.get_scratch().data_ptr(), st)
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / (reps * len(layers))
+    vp = 0 if video is None else video.data_ptr()
+    scratch = bufs.get_scratch()
+    pg = bufs.get_packed_grads()
+    _lib.call("mvn_wavenet_forward", C.byref(shape), bufs.packed.data_ptr(), audio.data_ptr(), vp, acts.data_ptr(),
+              out.data_ptr(), scratch.data_ptr(), st)
+    dout = torch.randn_like(out) * 1e-6
+    _lib.call("mvn_wavenet_backward", C.byref(shape), bufs.packed.data_ptr(), audio.data_ptr(), vp, acts.data_ptr(),
+              out.data_ptr(), dout.data_ptr(), pg.data_ptr(), scratch.data_ptr(), st)
+    layers = list(range(1, model.layer_size * model.stack_size - 1))     # interior layers
+    lib = _lib.load()
+
+    def time_stage(fn):
+        n0 = lib.mvn_launch_count()
+        for l in layers:
+            fn(l)
+        per_layer = (lib.mvn_launch_count() - n0) / len(layers)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        ev0.record()
+        for _ in range(reps):
+            for l in layers:     # each layer streams > L2 worth of activations, so every launch starts cold
+                fn(l)
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / (reps * len(layers)), per_layer
+
+    ms_f, n_f = time_stage(lambda l: _lib.call("mvn_layer_fwd", C.byref(shape), bufs.packed.data_ptr(), l, acts.data_ptr(),
+                                               scratch.data_ptr(), st))
+    ms_b, n_b = time_stage(lambda l: _lib.call("mvn_layer_bwd", C.byref(shape), bufs.packed.data_ptr(), l, acts.data_ptr(),
+                                               pg.data_ptr(), scratch.data_ptr(), st))
     e = 2 if dtype == "bf16" else 4
     Cc, S = model.residual_channels, model.skip_channels
-    # algorithmic bytes per sample of one layer forward: read x, write x', read ctx, read-modify-write skip_sum
-    per_sample = Cc * e + Cc * e + (Cc * e if video is not None else 0) + 8 * S
-    bytes_per_launch = per_sample * B * T_CLIP
+    vid = video is not None
+    # algorithmic bytes per audio sample of one layer
+    fwd_b = Cc * e + Cc * e + (Cc * e if vid else 0) + 8 * S                 # read x, write x', read ctx, RMW skip_sum
+    # backward: read x, P, U (stream gradient pair), d(skip) (+ ctx and the ctx-gradient stream Q);
+    #           write P', U' (+ Q')
+    bwd_b = 3 * Cc * e + 4 * S + 2 * Cc * e + (3 * Cc * e if vid else 0)
     pk = peaks()
-    achieved = bytes_per_launch / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "residual layer forward (%s, %d launch(es))" % (dtype, round(launches_per_layer)),
-            "achieved": achieved, "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
-            "frac": achieved / pk["hbm_gbs"], "traffic": None, "ms_per_launch": ms,
-            "bytes_per_sample": per_sample, "samples_per_launch": B * T_CLIP}
+    n = B * T_CLIP
+
+    def obj(name, ms, per_sample, launches, kernel):
+        ach = per_sample * n / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": "%s (%s, %d launch(es) per layer)" % (name, dtype, round(launches)),
+                "achieved": ach, "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
+                "frac": ach / pk["hbm_gbs"], "traffic": _ncu_traffic(kernel), "ms_per_launch": ms,
+                "bytes_per_sample": per_sample, "samples_per_launch": n}
+
+    return (obj("residual layer backward", ms_b, bwd_b, n_b, "layer_bwd_tc_kernel"),
+            obj("residual layer forward", ms_f, fwd_b, n_f, "layer_fwd_tc_kernel"))
 
 
 def decode_bench(dev):
@@ -314,7 +347,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    roof = layer_roofline(model, audio, video, args.dtype)
+    roof, roof_fwd = layer_roofline(model, audio, video, args.dtype)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.dtype == "fp32" else "bf16", "data": "synthetic",
@@ -330,7 +363,7 @@ def run_ours(args):
             "gpu_launches_per_step": launches / max(1, args.steps),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
-            "roofline": roof}
+            "roofline": roof, "roofline_layer_forward": roof_fwd}
     if world == 1:
         if not args.no_cpu_baseline:
             n, times = cpu_reference_steps(w, 2, 1, video=w["video"], B=1)
@@ -351,7 +384,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--dtype", default=os.environ.get("MOVENET_B200_DTYPE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--dtype", default=os.environ.get("MOVENET_B200_DTYPE", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     args = ap.parse_args()

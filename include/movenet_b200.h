@@ -121,6 +121,9 @@ int mvn_input_fwd(const mvn_shape_t* s, const void* packed, const float* audio, 
 int mvn_video_fwd(const mvn_shape_t* s, const void* packed, const float* video, void* acts, void* stream);
 int mvn_layer_fwd(const mvn_shape_t* s, const void* packed, int layer, void* acts, void* scratch, void* stream);
 int mvn_head_fwd(const mvn_shape_t* s, const void* packed, void* acts, float* out, void* scratch, void* stream);
+/* one layer of the backward pass on the gradient state currently in `scratch` (profiling / roofline timing) */
+int mvn_layer_bwd(const mvn_shape_t* s, const void* packed, int layer, const void* acts, void* packed_grads,
+                  void* scratch, void* stream);
 /* read back an internal activation as fp32 (tests): which = 0 layer input x_l (B,T,C), 1 skip sum (B,Tout,S),
  * 2 upsampled context (B,T,C) */
 int mvn_debug_read(const mvn_shape_t* s, const void* acts, int which, int layer, float* dst, void* stream);

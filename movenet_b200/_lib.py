@@ -47,6 +47,7 @@ SIGNATURES = {
     "mvn_video_fwd": (_I, [_SP, _P, _P, _P, _P]),
     "mvn_layer_fwd": (_I, [_SP, _P, _I, _P, _P, _P]),
     "mvn_head_fwd": (_I, [_SP, _P, _P, _P, _P, _P]),
+    "mvn_layer_bwd": (_I, [_SP, _P, _I, _P, _P, _P, _P]),
     "mvn_debug_read": (_I, [_SP, _P, _I, _I, _P, _P]),
     "mvn_decode_state_bytes": (_SZ, [_SP]),
     "mvn_decode_prefill": (_I, [_SP, _P, _P, _P]),

@@ -41,7 +41,7 @@ __host__ __device__ inline int bwd_tiles_off(int nc, int N2) { return smem_a_off
 // tiles after the image: A0..A(nc-1) | DXS | DSK | U | DZ0 | DZ1 | G | [Q, video only] | ONES(1 KB) | barriers
 __host__ __device__ inline int bwd_smem_total(int nc, int N2) { return bwd_tiles_off(nc, N2) + (nc + 6 + (nc == 3)) * TILE_BYTES + 1024 + 64; }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(512, 1)
 layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_ctx,
                     const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_u,
                     const __grid_constant__ CUtensorMap map_pout, const __grid_constant__ CUtensorMap map_uout,
@@ -68,7 +68,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int r = tid & 127, sw = r & 7;          // row of the tile == TMEM lane; warps w and w+4 share a lane quarter
-    const int half = tid >> 7;                    // ... and split the channel range between them
+    const int half = tid >> 7;                    // ... and split the channel range between them (4 quarters)
     const int NZ = nc * CC;                        // columns of D4 / dWz^T
 
     if (tid == 0) {
@@ -84,8 +84,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // constant tiles: DSK is zero outside the S live channels, ONES is all bf16 1.0
-    for (int i = tid; i < TILE_BYTES / 16; i += 256) ((uint4*)sDSK)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 1024 / 4; i += 256) ((uint32_t*)sONES)[i] = 0x3F803F80u;
+    for (int i = tid; i < TILE_BYTES / 16; i += 512) ((uint4*)sDSK)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 1024 / 4; i += 512) ((uint32_t*)sONES)[i] = 0x3F803F80u;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -139,7 +139,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         mbar_wait(full_bar, (it + 1) & 1);
         // ---- dxs = P + U(t + d_up), in place -----------------------------------------------------
 #pragma unroll
-        for (int q = 4 * half; q < 4 * half + 4; ++q) {
+        for (int q = 2 * half; q < 2 * half + 2; ++q) {
             uint4* pp = (uint4*)(sDXS + r * 128 + ((q ^ sw) << 4));
             const uint4 pv = *pp, uv = *(const uint4*)(sU + r * 128 + ((q ^ sw) << 4));
             const uint32_t pa[4] = {pv.x, pv.y, pv.z, pv.w}, ua[4] = {uv.x, uv.y, uv.z, uv.w};
@@ -172,7 +172,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tc_fence_after();
         // ---- epilogue 1: gate derivative -------------------------------------------------------
 #pragma unroll 1
-        for (int j = 2 * half; j < 2 * half + 2; ++j) {
+        for (int j = half; j < half + 1; ++j) {
             uint32_t f[16], g[16], dg[16];
             tmem_ld16(tmem + lane_base + 16 * j, f);
             tmem_ld16(tmem + lane_base + 64 + 16 * j, g);
@@ -233,7 +233,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tc_fence_after();
         // ---- epilogue 2a: P' = dxs + W1^T dz -> the U tile (free since the pre-sum); Q' = Q + V^T dz in place
 #pragma unroll 1
-        for (int j = 2 * half; j < 2 * half + 2; ++j) {
+        for (int j = half; j < half + 1; ++j) {
             uint32_t v[16];
             tmem_ld16(tmem + lane_base + 64 + 16 * j, v);
             tmem_ld_wait();
@@ -251,7 +251,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
         if (nc == 3) {
 #pragma unroll 1
-            for (int j = 2 * half; j < 2 * half + 2; ++j) {
+            for (int j = half; j < half + 1; ++j) {
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + 128 + 16 * j, v);
                 tmem_ld_wait();
@@ -273,7 +273,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         mbar_wait(w_bar, it & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int j = 2 * half; j < 2 * half + 2; ++j) {
+        for (int j = half; j < half + 1; ++j) {
             uint32_t v[16];
             tmem_ld16(tmem + lane_base + 16 * j, v);
             tmem_ld_wait();
@@ -298,7 +298,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     float* part = a.partial + (size_t)blockIdx.x * PART_FLOATS;
     float* prow = part + (size_t)r * PART_LD;
 #pragma unroll 1
-    for (int j = half; j < NZ / 16; j += 2) {
+    for (int j = half; j < NZ / 16; j += 4) {
         uint32_t v[16];
         tmem_ld16(tmem + lane_base + W1_COL + 16 * j, v);
         tmem_ld_wait();
@@ -308,7 +308,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                                                         __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
     }
 #pragma unroll 1
-    for (int j = half; j < 4; j += 2) {
+    for (int j = half; j < 4; j += 4) {
         uint32_t v[16];
         tmem_ld16(tmem + lane_base + W2_COL + 16 * j, v);
         tmem_ld_wait();
@@ -396,7 +396,7 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     }
     int grid = 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    layer_bwd_tc_kernel<<<grid, 256, smem, st>>>(mx, mc, mp, mu, mpo, muo, mq, mqo, a);
+    layer_bwd_tc_kernel<<<grid, 512, smem, st>>>(mx, mc, mp, mu, mpo, muo, mq, mqo, a);
     if ((rc = mvn_check_launch("layer_bwd_tc"))) return rc;
     tc_bwd_reduce_kernel<<<(PART_FLOATS + 255) / 256, 256, 0, st>>>(partial, grid, lg, P, g.S, g.Kz, g.video, layer + 1 < g.N);
     return mvn_check_launch("tc_bwd_reduce");

@@ -580,6 +580,24 @@ static int video_bwd(const Ctx& c, const float* video, const void* dctx, int dct
     return mvn_tn_gemm(t, c.st);
 }
 
+// one layer of the backward pass on whatever gradient state the scratch buffer holds (profiling / roofline timing)
+extern "C" int mvn_layer_bwd(const mvn_shape_t* s, const void* packed, int layer, const void* acts, void* packed_grads,
+                             void* scratch, void* stream) {
+    Ctx c; int rc = ctx_init(c, s, packed, acts, scratch, stream, "mvn_layer_bwd"); if (rc) return rc;
+    const Geo& g = c.g;
+    MVN_REQUIRE(layer >= 0 && layer < g.N && packed_grads, "mvn_layer_bwd: bad arguments");
+    float* pg = (float*)packed_grads;
+    if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
+        const size_t nb = (size_t)g.B * g.T * g.C * g.es;
+        float* lg = pg + c.P.layer0 + (size_t)layer * c.P.layer_stride;
+        return mvn_tc_layer_bwd(c.x(layer), g.video ? c.acts + c.AL.ctx : nullptr, c.scratch + c.SL.dxa, c.scratch + c.SL.dgated,
+                                c.scratch + c.SL.dxb, c.scratch + c.SL.dz, (const float*)(c.scratch + c.SL.dskip),
+                                c.scratch + c.SL.dctx, c.scratch + c.SL.dctx + nb, c.lw(layer), lg,
+                                (float*)(c.scratch + c.SL.tc_partial), c.P, g, layer, c.st);
+    }
+    return layer_bwd(c, layer, layer + 1 < g.N ? c.scratch + c.SL.dxa : nullptr, c.scratch + c.SL.dxb, pg);
+}
+
 extern "C" int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,
                                     const void* acts, const float* out, const float* dout, void* packed_grads,
                                     void* scratch, void* stream) {
