@@ -115,6 +115,16 @@ int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, const float* 
                          const void* acts, const float* out, const float* dout, void* packed_grads,
                          void* scratch, void* stream);
 
+/* The trainer's loss, F.cross_entropy(forward(...), target) (movenet/pytorch_lightning_trainer.py:62-65), i.e. a
+ * cross-entropy over the PROBABILITIES (a second softmax), mean over B*T columns, fused:
+ *   fwd: loss (1 float) from probs (B,A,T) fp32 and int64 targets (B,T); partials: mvn_softmax_ce_partials floats
+ *   bwd: dprobs = grad_loss[0]/(B*T) * (softmax_c(probs) - onehot(target)) */
+size_t mvn_softmax_ce_partials(int B, int T);
+int mvn_softmax_ce_fwd(const float* probs, const int64_t* target, int B, int A, int T, float* partials, float* loss,
+                       void* stream);
+int mvn_softmax_ce_bwd(const float* probs, const int64_t* target, const float* grad_loss, int B, int A, int T,
+                       float* dprobs, void* stream);
+
 /* stage-level entry points (the same kernels the two calls above launch) */
 int mvn_onehot_to_codes(const float* audio, int B, int A, int T, int* codes, unsigned char* dense, void* stream);
 int mvn_input_fwd(const mvn_shape_t* s, const void* packed, const float* audio, void* acts, void* stream);

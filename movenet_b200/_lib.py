@@ -42,6 +42,9 @@ SIGNATURES = {
     "mvn_unpack_grads": (_I, [_SP, _P, _P, _P, _P]),
     "mvn_wavenet_forward": (_I, [_SP, _P, _P, _P, _P, _P, _P, _P]),
     "mvn_wavenet_backward": (_I, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mvn_softmax_ce_partials": (_SZ, [_I, _I]),
+    "mvn_softmax_ce_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "mvn_softmax_ce_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
     "mvn_onehot_to_codes": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "mvn_input_fwd": (_I, [_SP, _P, _P, _P, _P]),
     "mvn_video_fwd": (_I, [_SP, _P, _P, _P, _P]),

@@ -26,6 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .loss import ProbabilityTensor
 from .modules import CausalConv1d, DenseConv, ResidualConvStack
 from .types import AudioTensor, VideoTensor
 
@@ -198,8 +199,10 @@ class WaveNet(nn.Module):
                 f"{(audio.shape[0], self.residual_channels, audio.shape[2])}")
         self.compute_output_size(audio)
         with torch.cuda.device(audio.device):
-            return _WaveNetFunction.apply(self, audio, video, bool(remove_last), not output_unnormalized,
-                                          *self._param_list())
+            out = _WaveNetFunction.apply(self, audio, video, bool(remove_last), not output_unnormalized,
+                                         *self._param_list())
+        # probabilities know the fused route for the trainer's F.cross_entropy(output, target) (loss.py)
+        return out.as_subclass(ProbabilityTensor) if output_unnormalized else out
 
     @torch.no_grad()
     def generate(self, audio: AudioTensor, video: Optional[VideoTensor] = None, global_features=None,

@@ -256,3 +256,32 @@ def test_full_size_clip_properties():
         assert not torch.equal(p[:, :, 100000:], p2[:, :, 100000:])
         p_single = m(audio[1:2])
         assert torch.equal(p_single[0], p[1])
+
+
+def test_fused_cross_entropy_route_equals_torch():
+    """F.cross_entropy(model(...), target) is routed to the fused kernel (movenet_b200/loss.py); it must be the
+    same function as torch's chain, and every other use of the output must behave like a plain tensor."""
+    fx = load_golden("cfg03")
+    m = build(fx)
+    audio = golden_audio(fx).cuda()
+    target = audio[:, :, m.receptive_fields:].argmax(1)
+    out = m(audio)
+    assert isinstance(out, movenet_b200.loss.ProbabilityTensor)
+    plain = out.detach().as_subclass(torch.Tensor).clone().requires_grad_(True)
+    ref = F.cross_entropy(plain, target)
+    ref.backward()
+    probe = out.detach().clone().requires_grad_(True)          # still a ProbabilityTensor -> fused route
+    fused = F.cross_entropy(probe, target)
+    fused.backward()
+    assert abs(fused.item() - ref.item()) < 1e-6 * abs(ref.item()) + 1e-7
+    assert rel_l2(probe.grad.as_subclass(torch.Tensor), plain.grad) < 1e-5
+    # scaled upstream gradient (gradient accumulation divides the loss, movenet/trainer.py:130)
+    probe.grad = None
+    (F.cross_entropy(probe, target) / 10).backward()
+    assert rel_l2(probe.grad.as_subclass(torch.Tensor), plain.grad / 10) < 1e-5
+    # non-default arguments fall back to torch and still agree
+    assert abs(F.cross_entropy(out, target, reduction="sum").item() - ref.item() * target.numel()) < 1e-3 * target.numel()
+    assert torch.equal(out.argmax(1), plain.argmax(1))
+    assert out.detach().cpu().sum().item() == pytest.approx(plain.detach().cpu().sum().item())
+    logits = m(audio, output_unnormalized=False)
+    assert type(logits) is torch.Tensor
