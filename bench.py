@@ -246,6 +246,33 @@ def layer_roofline(model, audio, video, dtype):
             obj("residual layer forward", ms_f, fwd_b, n_f, "layer_fwd_tc_kernel"))
 
 
+def model_state_repeat(m, st, reps):
+    """replicate a prefilled decode state `reps` times along the clip axis (queues are (layer, slot, clip, channel))"""
+    from movenet_b200.decode import DecodeState
+    from movenet_b200 import _lib
+    import ctypes as C
+    B = st.batch
+    shape = m._shape(B * reps, st.shape.frames, False, False, True, _lib.F32)
+    bufs = m._buffers_for(shape, st.state.device)
+    m._pack(bufs, m._param_list())
+    name = "mvn_decode_tc_state_bytes" if st.fast else "mvn_decode_state_bytes"
+    big = torch.zeros(_lib.size(name, shape), dtype=torch.uint8, device=st.state.device)
+    es = 2 if st.fast else 4
+    Cc = m.residual_channels
+    dil = m.residual_conv_stack.dilations
+    src_off = dst_off = 0
+    for d in dil:                                   # per layer: (slot, clip, channel)
+        n_src = d * B * Cc * es
+        src = st.state[src_off:src_off + n_src].view(d, B * Cc * es)
+        big[dst_off:dst_off + n_src * reps].view(d, reps, B * Cc * es).copy_(src.unsqueeze(1).expand(d, reps, B * Cc * es))
+        src_off += n_src; dst_off += n_src * reps
+    a256 = lambda x: (x + 255) // 256 * 256
+    src_l2 = a256(src_off); dst_l2 = a256(dst_off)
+    l2 = st.state[src_l2:src_l2 + B * 8].view(B, 8)
+    big[dst_l2:dst_l2 + B * reps * 8].view(reps, B, 8).copy_(l2.unsqueeze(0).expand(reps, B, 8))
+    return DecodeState(shape, bufs, big, None, B * reps, st.channels, fast=st.fast)
+
+
 def decode_bench(dev):
     """cached generation on the receptive-field config: RTF = generated seconds of 16 kHz audio per wall second"""
     import movenet_b200
@@ -254,11 +281,22 @@ def decode_bench(dev):
                              d["skip_channels"], compute_dtype="fp32").to(dev)
     RF = m.receptive_fields
     res = {}
-    for clips, n_new in ((1, 2000), (1184, 400)):
-        codes = torch.randint(0, d["input_channels"], (clips, RF), device=dev)
+    from movenet_b200.decode import fast_mode_available, prefill, run_steps
+    for mode, clips, n_new in (("exact_f32", 1, 2000), ("exact_f32", 1184, 400), ("fast_bf16", 148 * 256, 400)):
+        fast = mode == "fast_bf16"
+        if fast and not fast_mode_available(m, clips, RF):
+            continue
+        state = None
+        per = min(clips, 2368)                      # build the prompt batch in slices: the one-hot prompt is large
+        codes = torch.randint(0, d["input_channels"], (per, RF), device=dev)
         prompt = movenet_b200.one_hot(codes, d["input_channels"])
-        from movenet_b200.decode import prefill, run_steps
-        state = prefill(m, prompt, None)
+        if clips > per:                             # big batch: prefill one slice and replicate its queues (timing only)
+            state = prefill(m, prompt, None, fast=fast)
+            reps = clips // per
+            big = model_state_repeat(m, state, reps)
+            state = big
+        else:
+            state = prefill(m, prompt, None, fast=fast)
         run_steps(m, state, RF, 8)                                  # warm-up (re-running positions is harmless here)
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -267,12 +305,15 @@ def decode_bench(dev):
         ev1.record()
         torch.cuda.synchronize()
         sec = ev0.elapsed_time(ev1) * 1e-3
+        nclips = state.batch
         per_clip_rtf = (n_new / 16000.0) / sec
-        bytes_per_sample = 2 * m.layer_size * m.stack_size * d["residual_channels"] * 4 + 4 * d["input_channels"]
-        gbs = clips * n_new * bytes_per_sample / sec / 1e9
-        res[f"clips_{clips}"] = {"new_samples_per_clip": n_new, "rtf_per_clip": per_clip_rtf,
-                                 "aggregate_samples_per_s": clips * n_new / sec, "aggregate_rtf": clips * per_clip_rtf,
-                                 "hbm_gbs_algorithmic": gbs, "hbm_frac": gbs / peaks()["hbm_gbs"]}
+        e = 2 if fast else 4
+        bytes_per_sample = 2 * m.layer_size * m.stack_size * d["residual_channels"] * e + 4 * d["input_channels"]
+        gbs = nclips * n_new * bytes_per_sample / sec / 1e9
+        res[f"{mode}_clips_{nclips}"] = {"new_samples_per_clip": n_new, "rtf_per_clip": per_clip_rtf,
+                                         "aggregate_samples_per_s": nclips * n_new / sec, "aggregate_rtf": nclips * per_clip_rtf,
+                                         "bytes_per_sample": bytes_per_sample, "hbm_gbs_algorithmic": gbs,
+                                         "hbm_frac": gbs / peaks()["hbm_gbs"]}
         del state, prompt
     return {"workload": d["name"], "receptive_fields": RF, "dtype": "f32", **res}
 
@@ -323,23 +364,45 @@ def run_ours(args):
     n0 = _lib.load().mvn_launch_count()
     sampler.start()
     ms_total = timed(lambda: train_step(model, opt, audio, video), args.steps, 0, sync)
-    clocks = sampler.stop()
     launches = int(_lib.load().mvn_launch_count() - n0)
     ms_total = max_over_ranks(ms_total)
     ms_step = ms_total / args.steps
     value = world * B * T_CLIP / (ms_step * 1e-3)
 
     # ---- end to end from pinned host buffers ----
+    # every step's inputs cross PCIe inside the timed region; the copy of step i+1 is issued on a side stream
+    # while step i computes (an ordinary prefetching input pipeline), the loss is read back every step.
     loss_box = [0.0]
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [[None, None, None], [None, None, None]]
+
+    def issue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            slot[0] = host_audio.to(dev, non_blocking=True)
+            slot[1] = host_video.to(dev, non_blocking=True) if w["video"] else None
+            slot[2] = torch.cuda.Event()
+            slot[2].record(copy_stream)
+
+    state = {"i": 0}
 
     def e2e_step():
-        a = host_audio.to(dev, non_blocking=True)
-        v = host_video.to(dev, non_blocking=True) if w["video"] else None
+        cur = slots[state["i"] & 1]
+        if cur[2] is None:
+            issue_copy(cur)
+        issue_copy(slots[(state["i"] + 1) & 1])          # next step's inputs
+        torch.cuda.current_stream().wait_event(cur[2])
+        a, v = cur[0], cur[1]
+        a.record_stream(torch.cuda.current_stream())
+        if v is not None:
+            v.record_stream(torch.cuda.current_stream())
         loss_box[0] = train_step(model, opt, a, v).item()
+        cur[2] = None
+        state["i"] += 1
 
     ms_e2e = max_over_ranks(timed(e2e_step, args.steps, 1, sync)) / args.steps
     e2e_value = world * B * T_CLIP / (ms_e2e * 1e-3)
     h2d = host_audio.numel() * 4 + (host_video.numel() * 4 if w["video"] else 0)
+    clocks = sampler.stop()
 
     if rank != 0:
         if world > 1:

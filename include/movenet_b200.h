@@ -153,6 +153,19 @@ int mvn_decode_steps(const mvn_shape_t* s, const void* packed, void* state, cons
                      int n_new, int* out_codes, float* out_logits, float temperature, unsigned seed,
                      void* stream);
 
+/* Throughput mode of the cached decoder on tensor cores (bf16 operands and queues, fp32 accumulation): 128 clips
+ * advance in lock-step as the rows of tcgen05 MMAs, weights resident in shared memory.  Available when
+ * mvn_decode_tc_supported(shape) (no video, skip_channels == 8, residual_channels 16 or 32, input_channels <= 128:
+ * the receptive-field configuration, experiments/04).  Same prefill contract as mvn_decode_prefill.
+ * out_codes_t is STEP-major (n_new, B) so a step's tokens are one coalesced store; forced (B, n_new) optionally
+ * overrides the chosen token (teacher forcing, used by the parity tests to compare logits step by step). */
+int mvn_decode_tc_supported(const mvn_shape_t* s);
+size_t mvn_decode_tc_state_bytes(const mvn_shape_t* s);
+int mvn_decode_tc_prefill(const mvn_shape_t* s, const void* acts, void* state, void* stream);
+int mvn_decode_tc_steps(const mvn_shape_t* s, const void* packed, void* state, int t_start, int n_new,
+                        int* out_codes_t, float* out_logits, const int* forced, float temperature, unsigned seed,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

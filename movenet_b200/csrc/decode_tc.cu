@@ -1,0 +1,443 @@
+// Cached autoregressive decoding on tensor cores: the throughput mode of WaveNet.generate
+// (movenet/wavenet.py:193-239) for models whose weights fit in shared memory (the receptive-field
+// configuration, experiments/04: C = 16, S = 8, A = 128, 14 layers).
+//
+// A group of 4 warps advances 128 clips in lock-step: clip = MMA row = TMEM lane = thread.  Per layer
+//   A = [x_l[t-d] | x_l[t]]  (queue pop from HBM, current activation from registers)  -> bf16 tile
+//   tcgen05.mma  D1[128 x 2C] = A . Wz^T   -> gate in-thread -> bf16 tile
+//   tcgen05.mma  D2[128 x (C+S)] = gated . [Wr|Ws]^T -> residual / skip update in registers
+// then the dense head (two more MMAs) and the next token is chosen by the thread that owns the clip:
+// argmax (lowest index on ties) or a draw from softmax(softmax(z)/temperature) need no cross-thread
+// traffic at all.  Two such groups share one CTA (and one copy of the weights in shared memory) and
+// interleave, so one group's MMA / barrier latency hides behind the other's epilogue.
+//
+// Queues are bf16, laid out (layer, slot, clip, channel): a group's pop and push of one layer are two
+// contiguous 128 x C x 2-byte blocks.  Operand tiles use the un-swizzled K-major core-matrix layout
+// (8 rows x 16 bytes contiguous), which is compact for any K and conflict-free for one-row-per-thread
+// epilogue writes.
+#include "tc_common.cuh"
+#include "layer_tc.h"
+
+using namespace tc;
+
+namespace {
+
+constexpr int DS = 8;            // skip_channels handled
+constexpr int GROUPS = 2;        // 128-clip groups per CTA
+
+struct DecTcArgs {
+    const uint8_t* img; int img_bytes;
+    __nv_bfloat16* queues; int* last2; int* out_codes_t; float* out_logits; const int* forced;
+    int B, N, A, t_start, n_new;
+    float temperature; unsigned seed;
+    int layer_stride, oWrs, oBrs, oW1, oB1, oW2, oB2, oWin;
+    long long qoff[MVN_MAX_LAYERS];
+    int dil[MVN_MAX_LAYERS];
+};
+
+// byte offset of element (r, k) in a K-major, un-swizzled tile whose rows hold K elements (bf16)
+__host__ __device__ inline int core_off(int r, int k, int K) { return (r >> 3) * (K * 16) + (k >> 3) * 128 + (r & 7) * 16 + (k & 7) * 2; }
+__device__ __forceinline__ uint64_t desc_k_plain(uint32_t saddr, int K) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(128 >> 4) << 16;                  // LBO: next 8-element core along K
+    d |= (uint64_t)(((K * 16) >> 4) & 0x3FFF) << 32;  // SBO: next 8-row group
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+
+template <int C>
+struct Img {   // image layout shared by the pack kernel and the decode kernel
+    static constexpr int N2 = ((C + DS + 15) / 16) * 16;
+    static constexpr int wz = 0, wz_bytes = 2 * C * 2 * C * 2;
+    static constexpr int wrs = wz + wz_bytes, wrs_bytes = N2 * C * 2;
+    static constexpr int brs = wrs + wrs_bytes, layer_bytes = brs + N2 * 4;
+};
+
+template <int C>
+__global__ void decode_tc_pack_kernel(const float* __restrict__ packed, PackedLayout P, int N, int A, uint8_t* __restrict__ img,
+                                      int oW1, int oB1, int oW2, int oB2, int oWin) {
+    using I = Img<C>;
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int l = 0; l < N; ++l) {
+        const float* lw = packed + P.layer0 + (size_t)l * P.layer_stride;
+        uint8_t* li = img + (size_t)l * I::layer_bytes;
+        for (int i = i0; i < 2 * C * 2 * C; i += stride) {          // Wz^T[n][k], n: filter c | gate c ; k: tap0 | tap1
+            const int n = i / (2 * C), k = i % (2 * C);
+            const float v = lw[P.oWz + (size_t)k * 2 * C + 2 * (n % C) + n / C];
+            *(__nv_bfloat16*)(li + I::wz + core_off(n, k, 2 * C)) = __float2bfloat16(v);
+        }
+        for (int i = i0; i < I::N2 * C; i += stride) {               // [Wr|Ws]^T[n][k]
+            const int n = i / C, k = i % C;
+            const float v = n < C + DS ? lw[P.oWrs + (size_t)k * (C + DS) + n] : 0.f;
+            *(__nv_bfloat16*)(li + I::wrs + core_off(n, k, C)) = __float2bfloat16(v);
+        }
+        for (int i = i0; i < I::N2; i += stride) ((float*)(li + I::brs))[i] = i < C + DS ? lw[P.obrs + i] : 0.f;
+    }
+    for (int i = i0; i < A * 16; i += stride) {                      // W1^T[n][k], k padded 8 -> 16
+        const int n = i / 16, k = i % 16;
+        *(__nv_bfloat16*)(img + oW1 + core_off(n, k, 16)) = __float2bfloat16(k < DS ? packed[P.w1p + (size_t)k * A + n] : 0.f);
+    }
+    for (int i = i0; i < A * A; i += stride) {                       // W2^T[n][k]
+        const int n = i / A, k = i % A;
+        *(__nv_bfloat16*)(img + oW2 + core_off(n, k, A)) = __float2bfloat16(packed[P.w2p + (size_t)k * A + n]);
+    }
+    for (int i = i0; i < A; i += stride) { ((float*)(img + oB1))[i] = packed[P.b1 + i]; ((float*)(img + oB2))[i] = packed[P.b2 + i]; }
+    for (int i = i0; i < 2 * A * C; i += stride) ((float*)(img + oWin))[i] = packed[P.win + i];
+}
+
+template <int C>
+__global__ void __launch_bounds__(128 * GROUPS, 1) decode_tc_kernel(const DecTcArgs a) {
+    using I = Img<C>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* simg = smem;
+    const int A = a.A;
+    const int tid = threadIdx.x, grp = tid >> 7, r = tid & 127, warp = tid >> 5;
+    // per-group tiles after the image: layer A [128 x 2C] | gated [128 x C] | head A [128 x max(16, A)]
+    const int tiles_per_group = 128 * 2 * C * 2 + 128 * C * 2 + 128 * A * 2;
+    uint8_t* gbase = smem + ((a.img_bytes + 1023) & ~1023) + grp * ((tiles_per_group + 1023) & ~1023);
+    uint8_t* sA = gbase;
+    uint8_t* sG = sA + 128 * 2 * C * 2;
+    uint8_t* sH = sG + 128 * C * 2;
+    uint64_t* bars = (uint64_t*)(smem + ((a.img_bytes + 1023) & ~1023) + GROUPS * ((tiles_per_group + 1023) & ~1023));
+    uint64_t* mma_bar = bars + grp;
+    uint32_t* tmem_slot = (uint32_t*)(bars + GROUPS);
+
+    for (int i = tid; i < a.img_bytes / 16; i += blockDim.x) ((uint4*)simg)[i] = ((const uint4*)a.img)[i];
+    if (r == 0) mbar_init(mma_bar, 1);
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot + grp * 256;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    constexpr int D1 = 0, D2 = 2 * C;             // TMEM columns: D1 [0, 2C) ; D2 [2C, 2C + N2) ; head [128, 128 + A)
+    constexpr int DH = 128;
+    const uint32_t i1 = umma_idesc_major(128, 2 * C, 0, 0), i2 = umma_idesc_major(128, I::N2, 0, 0), ih = umma_idesc_major(128, A, 0, 0);
+
+    const int b = (blockIdx.x * GROUPS + grp) * 128 + r;
+    const bool live = b < a.B;
+    const float* win = (const float*)(simg + a.oWin);
+    int code_prev = live ? a.last2[2 * b] : -1, code_cur = live ? a.last2[2 * b + 1] : -1;
+    uint32_t phase = 0;
+
+    for (int i = a.t_start; i < a.t_start + a.n_new; ++i) {
+        const int tau = i - 1;
+        float h[C], skip[DS];
+#pragma unroll
+        for (int c = 0; c < C; ++c) h[c] = 0.f;
+        if (code_prev >= 0) {
+#pragma unroll
+            for (int c = 0; c < C; c += 4) { const float4 w = *(const float4*)(win + (size_t)code_prev * C + c); h[c] += w.x; h[c + 1] += w.y; h[c + 2] += w.z; h[c + 3] += w.w; }
+        }
+        if (code_cur >= 0) {
+#pragma unroll
+            for (int c = 0; c < C; c += 4) { const float4 w = *(const float4*)(win + ((size_t)A + code_cur) * C + c); h[c] += w.x; h[c + 1] += w.y; h[c + 2] += w.z; h[c + 3] += w.w; }
+        }
+#pragma unroll
+        for (int s = 0; s < DS; ++s) skip[s] = 0.f;
+
+        for (int l = 0; l < a.N; ++l) {
+            const uint8_t* li = simg + (size_t)l * I::layer_bytes;
+            const int d = a.dil[l];
+            __nv_bfloat16* ring = a.queues + a.qoff[l] * a.B + ((size_t)(tau % d) * a.B + (live ? b : 0)) * C;
+            // A row = [x_l[tau - d] | x_l[tau]] ; then push x_l[tau]
+#pragma unroll
+            for (int q = 0; q < C / 8; ++q) {
+                uint4 old = make_uint4(0, 0, 0, 0);
+                if (live && tau - d >= 0) old = ((const uint4*)ring)[q];
+                *(uint4*)(sA + core_off(r, 8 * q, 2 * C)) = old;
+                const uint4 cur = make_uint4(pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
+                                             pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
+                *(uint4*)(sA + core_off(r, C + 8 * q, 2 * C)) = cur;
+                if (live) ((uint4*)ring)[q] = cur;
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            group_sync(grp);
+            if (r == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 2 * C / 16; ++k)
+                    umma(tmem + D1, desc_k_plain(smem_u32(sA) + k * 256, 2 * C), desc_k_plain(smem_u32(li + I::wz) + k * 256, 2 * C), i1, k != 0);
+                umma_commit(mma_bar);
+            }
+            mbar_wait(mma_bar, phase); phase ^= 1;
+            tc_fence_after();
+            {
+                uint32_t f[C], g[C];
+#pragma unroll
+                for (int q = 0; q < C / 16; ++q) { tmem_ld16(tmem + lane_base + D1 + 16 * q, f + 16 * q); tmem_ld16(tmem + lane_base + D1 + C + 16 * q, g + 16 * q); }
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < C / 8; ++q) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = 8 * q + 2 * e;
+                        const float y0 = tanh_fast(__uint_as_float(f[c])) * fmaf(0.5f, tanh_fast(0.5f * __uint_as_float(g[c])), 0.5f);
+                        const float y1 = tanh_fast(__uint_as_float(f[c + 1])) * fmaf(0.5f, tanh_fast(0.5f * __uint_as_float(g[c + 1])), 0.5f);
+                        o[e] = pack_bf16(y0, y1);
+                    }
+                    *(uint4*)(sG + core_off(r, 8 * q, C)) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            group_sync(grp);
+            if (r == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < C / 16; ++k)
+                    umma(tmem + D2, desc_k_plain(smem_u32(sG) + k * 256, C), desc_k_plain(smem_u32(li + I::wrs) + k * 256, C), i2, k != 0);
+                umma_commit(mma_bar);
+            }
+            mbar_wait(mma_bar, phase); phase ^= 1;
+            tc_fence_after();
+            {
+                const float* brs = (const float*)(li + I::brs);
+                uint32_t v[I::N2];
+#pragma unroll
+                for (int q = 0; q < I::N2 / 16; ++q) tmem_ld16(tmem + lane_base + D2 + 16 * q, v + 16 * q);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < C; ++c) h[c] += __uint_as_float(v[c]) + brs[c];
+#pragma unroll
+                for (int s = 0; s < DS; ++s) skip[s] += __uint_as_float(v[C + s]) + brs[C + s];
+            }
+            tc_fence_before();
+        }
+        // ---- dense head: a1 = W1 lrelu(skip) + b1 ; z = W2 lrelu(a1) + b2 -----------------------------
+        {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float x0 = skip[2 * e], x1 = skip[2 * e + 1];
+                o[e] = pack_bf16(x0 > 0.f ? x0 : MVN_LRELU_SLOPE * x0, x1 > 0.f ? x1 : MVN_LRELU_SLOPE * x1);
+            }
+            *(uint4*)(sH + core_off(r, 0, 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *(uint4*)(sH + core_off(r, 8, 16)) = make_uint4(0, 0, 0, 0);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        group_sync(grp);
+        if (r == 0) {
+            tc_fence_after();
+            umma(tmem + DH, desc_k_plain(smem_u32(sH), 16), desc_k_plain(smem_u32(simg + a.oW1), 16), ih, 0);
+            umma_commit(mma_bar);
+        }
+        mbar_wait(mma_bar, phase); phase ^= 1;
+        tc_fence_after();
+        {
+            const float* b1 = (const float*)(simg + a.oB1);
+            for (int q = 0; q < A / 16; ++q) {
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_base + DH + 16 * q, v);
+                tmem_ld_wait();
+                uint32_t o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float x0 = __uint_as_float(v[2 * e]) + b1[16 * q + 2 * e], x1 = __uint_as_float(v[2 * e + 1]) + b1[16 * q + 2 * e + 1];
+                    o[e] = pack_bf16(x0 > 0.f ? x0 : MVN_LRELU_SLOPE * x0, x1 > 0.f ? x1 : MVN_LRELU_SLOPE * x1);
+                }
+                *(uint4*)(sH + core_off(r, 16 * q, A)) = make_uint4(o[0], o[1], o[2], o[3]);
+                *(uint4*)(sH + core_off(r, 16 * q + 8, A)) = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        group_sync(grp);          // also: every thread has finished reading a1 from TMEM before it is overwritten
+        if (r == 0) {
+            tc_fence_after();
+            for (int k = 0; k < A / 16; ++k)
+                umma(tmem + DH, desc_k_plain(smem_u32(sH) + k * 256, A), desc_k_plain(smem_u32(simg + a.oW2) + k * 256, A), ih, k != 0);
+            umma_commit(mma_bar);
+        }
+        mbar_wait(mma_bar, phase); phase ^= 1;
+        tc_fence_after();
+        // ---- next token, chosen by the thread that owns the clip --------------------------------------
+        int arg = 0;
+        {
+            const float* b2 = (const float*)(simg + a.oB2);
+            float best = -INFINITY;
+            for (int q = 0; q < A / 16; ++q) {
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_base + DH + 16 * q, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const float z = __uint_as_float(v[e]) + b2[16 * q + e];
+                    if (z > best) { best = z; arg = 16 * q + e; }
+                    if (a.out_logits && live) a.out_logits[((size_t)b * a.n_new + (i - a.t_start)) * A + 16 * q + e] = z;
+                }
+            }
+            if (a.temperature > 0.f) {      // draw from softmax(softmax(z) / temperature) (movenet/wavenet.py:227-231)
+                float s = 0.f;
+                for (int q = 0; q < A / 16; ++q) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + lane_base + DH + 16 * q, v); tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) s += __expf(__uint_as_float(v[e]) + b2[16 * q + e] - best);
+                }
+                const float inv_s = 1.f / s, inv_t = 1.f / a.temperature, pmax = inv_s * inv_t;
+                float qs = 0.f;
+                for (int q = 0; q < A / 16; ++q) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + lane_base + DH + 16 * q, v); tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) qs += __expf(__expf(__uint_as_float(v[e]) + b2[16 * q + e] - best) * inv_s * inv_t - pmax);
+                }
+                unsigned long long x = ((unsigned long long)a.seed << 32) ^ ((unsigned long long)(unsigned)b * 0x9E3779B97F4A7C15ULL) ^ (unsigned long long)(unsigned)i;
+                x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 27; x *= 0x94D049BB133111EBULL; x ^= x >> 31;
+                const float target = (float)(x >> 40) * (1.f / 16777216.f) * qs;
+                float run = 0.f; int pick = -1;
+                for (int q = 0; q < A / 16; ++q) {
+                    uint32_t v[16];
+                    tmem_ld16(tmem + lane_base + DH + 16 * q, v); tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        run += __expf(__expf(__uint_as_float(v[e]) + b2[16 * q + e] - best) * inv_s * inv_t - pmax);
+                        if (pick < 0 && target < run) pick = 16 * q + e;
+                    }
+                }
+                arg = pick < 0 ? A - 1 : pick;
+            }
+        }
+        if (a.forced && live) arg = a.forced[(size_t)b * a.n_new + (i - a.t_start)];
+        if (live) a.out_codes_t[(size_t)(i - a.t_start) * a.B + b] = arg;
+        code_prev = code_cur; code_cur = arg;
+        tc_fence_before();
+        group_sync(grp);          // the head's TMEM columns and tiles are free for the next step
+    }
+    if (live) { a.last2[2 * b] = code_prev; a.last2[2 * b + 1] = code_cur; }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "n"(512) : "memory");
+    }
+}
+
+// rings (layer, slot, clip, channel) bf16 from the layer inputs of a forward over the T-column prompt:
+// ring_l[tau % d] = x_l[tau] for tau in [T-1-d, T-1)  (the first decode step re-evaluates time T-1 itself)
+__global__ void decode_tc_prefill_kernel(const void* __restrict__ x, int adt, int B, int T, int C, int d, __nv_bfloat16* __restrict__ ring) {
+    const long long n = (long long)B * d * C;
+    const int Tend = T - 1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C); const long long rr = i / C; const int b = (int)(rr % B); const int slot = (int)(rr / B);
+        int tau = (Tend / d) * d + slot; if (tau >= Tend) tau -= d;
+        ring[i] = __float2bfloat16(tau >= 0 ? mvn_ld(x, adt, ((size_t)b * T + tau) * C + c) : 0.f);
+    }
+}
+__global__ void decode_tc_last2_kernel(const int* __restrict__ codes, int B, int T, int* __restrict__ last2) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    last2[2 * b] = T >= 2 ? codes[(size_t)b * T + T - 2] : -1;
+    last2[2 * b + 1] = T >= 1 ? codes[(size_t)b * T + T - 1] : -1;
+}
+
+static size_t queue_elems(const Geo& g, long long* qoff) {
+    long long o = 0;
+    for (int l = 0; l < g.N; ++l) { if (qoff) qoff[l] = o; o += (long long)g.dil[l] * g.C; }
+    return (size_t)o;
+}
+
+template <int C>
+int image_offsets(const Geo& g, DecTcArgs& a) {
+    using I = Img<C>;
+    int o = g.N * I::layer_bytes;
+    a.layer_stride = I::layer_bytes; a.oWrs = I::wrs; a.oBrs = I::brs;
+    a.oW1 = o; o += g.A * 16 * 2;
+    a.oB1 = o; o += g.A * 4;
+    a.oW2 = o; o += g.A * g.A * 2;
+    a.oB2 = o; o += g.A * 4;
+    a.oWin = o; o += 2 * g.A * g.C * 4;
+    a.img_bytes = (o + 15) & ~15;
+    return a.img_bytes;
+}
+
+template <int C>
+int smem_bytes(const Geo& g, int img_bytes) {
+    const int tiles = 128 * 2 * C * 2 + 128 * C * 2 + 128 * g.A * 2;
+    return ((img_bytes + 1023) & ~1023) + GROUPS * ((tiles + 1023) & ~1023) + 64 + 1024;
+}
+
+template <int C>
+int run_steps(const Geo& g, DecTcArgs& a, const float* packed, const PackedLayout& P, uint8_t* img, cudaStream_t st) {
+    decode_tc_pack_kernel<C><<<64, 256, 0, st>>>(packed, P, g.N, g.A, img, a.oW1, a.oB1, a.oW2, a.oB2, a.oWin);
+    int rc = mvn_check_launch("decode_tc_pack");
+    if (rc) return rc;
+    const int smem = smem_bytes<C>(g, a.img_bytes);
+    MVN_CUDA(cudaFuncSetAttribute(decode_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    decode_tc_kernel<C><<<mvn_cdiv(g.B, 128 * GROUPS), 128 * GROUPS, smem, st>>>(a);
+    return mvn_check_launch("decode_tc_steps");
+}
+
+}  // namespace
+
+int mvn_tc_decode_supported(const Geo& g) {
+    if (g.video || g.S != DS || (g.C != 16 && g.C != 32) || g.A % 16 || g.A < 16 || g.A > 128) return 0;
+    DecTcArgs a;
+    const int img = g.C == 16 ? image_offsets<16>(g, a) : image_offsets<32>(g, a);
+    const int smem = g.C == 16 ? smem_bytes<16>(g, img) : smem_bytes<32>(g, img);
+    return smem <= 227 * 1024;
+}
+
+extern "C" size_t mvn_decode_tc_state_bytes(const mvn_shape_t* s) {
+    Geo g; if (geo_init(g, s)) return 0;
+    DecTcArgs a;
+    const int img = g.C == 16 ? image_offsets<16>(g, a) : image_offsets<32>(g, a);
+    return al256(queue_elems(g, nullptr) * (size_t)g.B * 2) + al256((size_t)g.B * 2 * 4) + al256(img);
+}
+
+extern "C" int mvn_decode_tc_supported(const mvn_shape_t* s) {
+    Geo g; if (geo_init(g, s)) return 0;
+    return mvn_tc_decode_supported(g);
+}
+
+extern "C" int mvn_decode_tc_prefill(const mvn_shape_t* s, const void* acts, void* state, void* stream) {
+    Geo g; MVN_REQUIRE(s && geo_init(g, s) == 0, "mvn_decode_tc_prefill: bad shape");
+    MVN_REQUIRE(acts && state && mvn_tc_decode_supported(g), "mvn_decode_tc_prefill: unsupported shape");
+    ActsLayout AL; acts_layout(g, AL);
+    long long qoff[MVN_MAX_LAYERS];
+    const size_t qe = queue_elems(g, qoff);
+    __nv_bfloat16* queues = (__nv_bfloat16*)state;
+    int* last2 = (int*)((char*)state + al256(qe * (size_t)g.B * 2));
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int l = 0; l < g.N; ++l) {
+        const void* x = (const char*)acts + AL.x0 + (size_t)l * AL.x_stride;
+        const long long n = (long long)g.B * g.dil[l] * g.C;
+        decode_tc_prefill_kernel<<<mvn_cdiv(n, 256) < 1184 ? mvn_cdiv(n, 256) : 1184, 256, 0, st>>>(x, g.adt, g.B, g.T, g.C, g.dil[l],
+                                                                                                 queues + qoff[l] * g.B);
+    }
+    decode_tc_last2_kernel<<<mvn_cdiv(g.B, 128), 128, 0, st>>>((const int*)((const char*)acts + AL.codes), g.B, g.T, last2);
+    return mvn_check_launch("decode_tc_prefill");
+}
+
+extern "C" int mvn_decode_tc_steps(const mvn_shape_t* s, const void* packed, void* state, int t_start, int n_new,
+                                   int* out_codes_t, float* out_logits, const int* forced, float temperature, unsigned seed,
+                                   void* stream) {
+    Geo g; MVN_REQUIRE(s && geo_init(g, s) == 0, "mvn_decode_tc_steps: bad shape");
+    MVN_REQUIRE(packed && state && out_codes_t && n_new >= 0 && t_start >= 1 && mvn_tc_decode_supported(g), "mvn_decode_tc_steps: bad arguments");
+    if (n_new == 0) return 0;
+    DecTcArgs a; memset(&a, 0, sizeof(a));
+    PackedLayout P; packed_layout(g, P);
+    const size_t qe = queue_elems(g, a.qoff);
+    for (int l = 0; l < g.N; ++l) a.dil[l] = g.dil[l];
+    a.queues = (__nv_bfloat16*)state;
+    a.last2 = (int*)((char*)state + al256(qe * (size_t)g.B * 2));
+    uint8_t* img = (uint8_t*)state + al256(qe * (size_t)g.B * 2) + al256((size_t)g.B * 2 * 4);
+    a.img = img;
+    a.out_codes_t = out_codes_t; a.out_logits = out_logits; a.forced = forced;
+    a.B = g.B; a.N = g.N; a.A = g.A; a.t_start = t_start; a.n_new = n_new; a.temperature = temperature; a.seed = seed;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g.C == 16) { image_offsets<16>(g, a); return run_steps<16>(g, a, (const float*)packed, P, img, st); }
+    image_offsets<32>(g, a); return run_steps<32>(g, a, (const float*)packed, P, img, st);
+}

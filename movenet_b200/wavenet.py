@@ -145,6 +145,9 @@ class WaveNet(nn.Module):
         self.residual_conv_stack = ResidualConvStack(layer_size, stack_size, residual_channels, skip_channels)
         self.dense_conv = DenseConv(skip_channels, input_channels)
 
+        #: "exact": fp32 CUDA-core decoder, token-exact against the reference (default);
+        #: "fast" : tensor-core decoder (bf16 queues / operands) where mvn_decode_tc_supported -- throughput mode
+        self.decode_mode = os.environ.get("MOVENET_B200_DECODE", "exact")
         self._bufs = {}
         self._ptr_tables = {}
         self._dp_group = None
@@ -219,7 +222,7 @@ class WaveNet(nn.Module):
         """
         from .decode import cached_generate
         self.eval()
-        return cached_generate(self, audio, video, n_samples, temperature)
+        return cached_generate(self, audio, video, n_samples, temperature, fast=(self.decode_mode == "fast"))
 
     # ------------------------------------------------------------------ data parallel
     def enable_data_parallel(self, process_group=None):

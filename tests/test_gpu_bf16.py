@@ -98,3 +98,38 @@ def test_bf16_ragged_tile_edges():
             b = m16(audio, output_unnormalized=False, remove_last=False)
         assert a.shape == b.shape == (3, 64, T - 23)
         assert (a - b).abs().max().item() <= LOGIT_RTOL * a.abs().max().item(), T
+
+
+def test_tensor_core_decoder_teacher_forced_logits():
+    """Throughput decoder (tcgen05, bf16 queues) on the receptive-field architecture (stack_size 1, C 16, A 128):
+    teacher-forced with the reference's own generated tokens, its logits must match the oracle's true-causal logits
+    within the bf16 tolerance at every step; free-running it must emit valid tokens = argmax of its own logits."""
+    from movenet_b200.decode import fast_mode_available, prefill, run_steps
+    fx = load_golden("cfg04_short")
+    m = build(fx, "fp32")
+    RF = m.receptive_fields
+    audio = golden_audio(fx).cuda()
+    n = fx["gen_codes"].shape[1]
+    B = audio.shape[0]
+    assert fast_mode_available(m, B, RF)
+    forced = fx["gen_codes"][:, RF:].cuda()
+    st = prefill(m, audio[:, :, :RF].contiguous(), None, fast=True)
+    codes, logits = run_steps(m, st, RF, n - RF, 0.0, return_logits=True, forced=forced)
+    assert torch.equal(codes.cpu().long(), fx["gen_codes"][:, RF:].long())
+    ref = fx["gen_causal_logits"]                                   # (B, A, n_new)
+    got = logits.permute(0, 2, 1).cpu()
+    assert (got - ref).abs().max().item() <= LOGIT_RTOL * ref.abs().max().item()
+    # free-running through the public entry point
+    m.decode_mode = "fast"
+    gen = m.generate(audio[:, :, :RF], n_samples=n, temperature=0.0)
+    assert gen.shape == (B, m.input_channels, n)
+    assert torch.equal(gen.sum(1).cpu(), torch.ones(B, n))
+    assert torch.equal(gen[:, :, :RF].cpu(), golden_audio(fx)[:, :, :RF])
+    st = prefill(m, audio[:, :, :RF].contiguous(), None, fast=True)
+    codes, logits = run_steps(m, st, RF, n - RF, 0.0, return_logits=True)
+    assert torch.equal(codes.long(), logits.argmax(2))
+    assert torch.equal(codes.long().cpu(), gen[:, :, RF:].argmax(1).cpu())
+    # many clips (several CTAs, both groups, a ragged last group)
+    big = audio[:1, :, :RF].repeat(300, 1, 1).contiguous()
+    g2 = m.generate(big, n_samples=RF + 8, temperature=0.0)
+    assert torch.equal(g2[0], g2[299]) and torch.equal(g2[0], g2[128]) and torch.equal(g2[0, :, :RF + 8].cpu(), gen[0, :, :RF + 8].cpu())
