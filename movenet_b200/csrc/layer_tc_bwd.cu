@@ -64,7 +64,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint64_t* full_bar = (uint64_t*)(sONES + 1024);
     uint64_t* mma_bar = full_bar + 1;
     uint64_t* w_bar = full_bar + 2;
-    uint32_t* tmem_slot = (uint32_t*)(full_bar + 3);
+    uint64_t* a_bar = full_bar + 3;              // the x / ctx tiles of a tile arrive on their own barrier, one tile ahead
+    uint32_t* tmem_slot = (uint32_t*)(full_bar + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int r = tid & 127, sw = r & 7;          // row of the tile == TMEM lane; warps w and w+4 share a lane quarter
@@ -72,7 +73,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int NZ = nc * CC;                        // columns of D4 / dWz^T
 
     if (tid == 0) {
-        mbar_init(full_bar, 1); mbar_init(mma_bar, 1); mbar_init(w_bar, 1);
+        mbar_init(full_bar, 1); mbar_init(mma_bar, 1); mbar_init(w_bar, 1); mbar_init(a_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t wbytes = (uint32_t)smem_a_off(nc, a.N2);
         mbar_expect_tx(full_bar, wbytes);
@@ -100,18 +101,37 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const uint32_t iW1 = umma_idesc_major(TILE_T, NZ, 1, 1);
     const uint32_t iW2 = umma_idesc_major(TILE_T, 64, 1, 1);
     const uint32_t iB = umma_idesc_major(TILE_T, 16, 1, 1);
-    const uint32_t load_bytes = (uint32_t)((nc + 2 + (nc == 3)) * TILE_BYTES);
+    const uint32_t load_bytes = (uint32_t)((2 + (nc == 3)) * TILE_BYTES);       // P, U (+ Q)
+    const uint32_t a_bytes = (uint32_t)(nc * TILE_BYTES);                        // x(t-d), x(t) (+ ctx)
+
+    // x / ctx tiles of tile `tl` -> a_bar
+    auto load_a_tiles = [&](int tl) {
+        const int lb = tl / a.tiles_per_clip, l0 = (tl - lb * a.tiles_per_clip) * TILE_T;
+        mbar_expect_tx(a_bar, a_bytes);
+        tma_load_3d(sA, &map_x, a_bar, 0, l0 - a.dil, lb);
+        tma_load_3d(sA + TILE_BYTES, &map_x, a_bar, 0, l0, lb);
+        if (nc == 3) tma_load_3d(sA + 2 * TILE_BYTES, &map_ctx, a_bar, 0, l0, lb);
+    };
+    // this thread's d(skip) row of tile `tl` (first 8 channels), fetched one tile ahead
+    auto load_dskip = [&](int tl, float4& v0, float4& v1) {
+        const int lb = tl / a.tiles_per_clip, lt = (tl - lb * a.tiles_per_clip) * TILE_T + r, js = lt - (a.RF - 1);
+        v0 = make_float4(0.f, 0.f, 0.f, 0.f); v1 = v0;
+        if (tl < a.n_tiles && lt < a.T && js >= 0 && js < a.Tout) {
+            const float4* src = (const float4*)(a.dskip + ((size_t)lb * a.Tout + js) * a.S);
+            v0 = src[0]; v1 = src[1];
+        }
+    };
+    if (tid == 0 && (int)blockIdx.x < a.n_tiles) load_a_tiles(blockIdx.x);
+    float4 ds0, ds1;
+    load_dskip(blockIdx.x, ds0, ds1);
 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
         const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T;
         const int t = t0 + r;
         if (tid == 0) {
-            tma_wait_read0();                  // the previous tile's P'/U' stores have finished reading U / DXS
+            tma_wait_read0();                  // the previous tile's P'/U'/Q' stores have finished reading their tiles
             mbar_expect_tx(full_bar, load_bytes);
-            tma_load_3d(sA, &map_x, full_bar, 0, t0 - a.dil, b);
-            tma_load_3d(sA + TILE_BYTES, &map_x, full_bar, 0, t0, b);
-            if (nc == 3) tma_load_3d(sA + 2 * TILE_BYTES, &map_ctx, full_bar, 0, t0, b);
             tma_load_3d(sDXS, &map_p, full_bar, 0, t0, b);
             tma_load_3d(sU, &map_u, full_bar, 0, t0 + a.dil_up, b);
             if (nc == 3) tma_load_3d(sQ, &map_q, full_bar, 0, t0, b);
@@ -126,15 +146,27 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             }
         }
         if (half == 0) {   // d(skip) row of this thread -> bf16, logical channels [0, S) of the DSK tile
+            *(uint4*)(sDSK + r * 128 + ((0 ^ sw) << 4)) =
+                make_uint4(pack_bf16(ds0.x, ds0.y), pack_bf16(ds0.z, ds0.w), pack_bf16(ds1.x, ds1.y), pack_bf16(ds1.z, ds1.w));
             const int js = t - (a.RF - 1);
             const bool live = t < a.T && js >= 0 && js < a.Tout;
             const float* src = a.dskip + ((size_t)b * a.Tout + (live ? js : 0)) * a.S;
-            for (int s0 = 0; s0 < a.S; s0 += 8) {
+            for (int s0 = 8; s0 < a.S; s0 += 8) {
                 float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
                 if (live) { v0 = ((const float4*)(src + s0))[0]; v1 = ((const float4*)(src + s0))[1]; }
                 *(uint4*)(sDSK + r * 128 + ((((s0 >> 3)) ^ sw) << 4)) =
                     make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
             }
+        }
+        // recompute GEMM as soon as the x / ctx tiles are in: it overlaps the arrival of P / U and the pre-sum
+        mbar_wait(a_bar, it & 1);
+        if (tid == 0) {
+            tc_fence_after();
+            for (int c = 0; c < nc; ++c)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma(tmem, umma_desc(smem_u32(sA + c * TILE_BYTES) + k * 32), umma_desc(smem_u32(sBz + c * TILE_BYTES) + k * 32),
+                         iG1, (c | k) != 0);
         }
         mbar_wait(full_bar, (it + 1) & 1);
         // ---- dxs = P + U(t + d_up), in place -----------------------------------------------------
@@ -156,11 +188,6 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            for (int c = 0; c < nc; ++c)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma(tmem, umma_desc(smem_u32(sA + c * TILE_BYTES) + k * 32), umma_desc(smem_u32(sBz + c * TILE_BYTES) + k * 32),
-                         iG1, (c | k) != 0);
             // d(gated) = dxs . Wr + dskip . Ws : contraction over the image's ROWS (c_out | s) -> B is MN-major
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -272,6 +299,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         // ---- epilogue 2b: once the weight-gradient MMAs no longer read DXS: U' = W0^T dz -> DXS tile
         mbar_wait(w_bar, it & 1);
         tc_fence_after();
+        if (tid == 0 && tile + (int)gridDim.x < a.n_tiles) load_a_tiles(tile + gridDim.x);   // x / ctx tiles are free: next tile
+        load_dskip(tile + gridDim.x, ds0, ds1);
 #pragma unroll 1
         for (int j = half; j < half + 1; ++j) {
             uint32_t v[16];
