@@ -42,6 +42,8 @@ struct RowGemmArgs {
     void* out2; int out2_dtype, ldo2, out2_T, out2_shift;
     const void* aux; int aux_dtype, lda, aux_T, aux_shift;
     int split;
+    int allow_ksplit; // caller opt-in (the result then depends on the order of fp32 atomics: not bit-reproducible)
+    int ksplit;      // > 1: the K chunks are dealt round-robin to gridDim.z CTAs which atomically add into a ZEROED fp32 output (EPI_STORE only)
 };
 
 struct TnSrc {
@@ -133,11 +135,13 @@ __global__ void __launch_bounds__(256) row_gemm_kernel(const RowGemmArgs a) {
     const long long lb = lr / a.Trow;
     const int lt = (int)(lr - lb * a.Trow);
     const int wk = tid >> 4, wn = (tid & 15) * 4;
+    int chunk = 0;
 
     for (int s = 0; s < a.nsrc; ++s) {
         const GemmSrc& S = a.src[s];
         const long long srow = (lr < a.rows) ? mvn_map_row(lb, lt, S.T, S.shift) : -1;
         for (int k0 = 0; k0 < S.K; k0 += RG_BK) {
+            if (a.ksplit > 1 && (chunk++ % a.ksplit) != (int)blockIdx.z) continue;
             float v[8], w[4];
             mvn_load8(S.ptr, S.dtype, srow, S.ld, k0 + kh, S.K, S.pre, v);
             mvn_load4w(S.W, S.ldw, k0 + wk, S.K, n0 + wn, a.N, w);
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(256) row_gemm_kernel(const RowGemmArgs a) {
 
     const int nb = n0 + tx * 4;
     float bias[4] = {0.f, 0.f, 0.f, 0.f};
-    if (a.bias) {
+    if (a.bias && (a.ksplit <= 1 || blockIdx.z == 0)) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) if (nb + j < a.N) bias[j] = a.bias[nb + j];
     }
@@ -178,8 +182,10 @@ __global__ void __launch_bounds__(256) row_gemm_kernel(const RowGemmArgs a) {
         for (int j = 0; j < 4; ++j) v[j] = acc[i][j] + bias[j];
         switch (a.epi) {
         case EPI_STORE:
-            if (orow >= 0)
-                for (int j = 0; j < 4; ++j) if (nb + j < a.N) mvn_st(a.out, a.out_dtype, orow * a.ldo + nb + j, v[j]);
+            if (orow >= 0) {
+                if (a.ksplit > 1) { for (int j = 0; j < 4; ++j) if (nb + j < a.N) atomicAdd((float*)a.out + orow * a.ldo + nb + j, v[j]); }
+                else for (int j = 0; j < 4; ++j) if (nb + j < a.N) mvn_st(a.out, a.out_dtype, orow * a.ldo + nb + j, v[j]);
+            }
             break;
         case EPI_ACCUM:
             if (orow >= 0)
@@ -244,9 +250,24 @@ __global__ void __launch_bounds__(256) row_gemm_kernel(const RowGemmArgs a) {
     }
 }
 
-static inline int mvn_row_gemm(const RowGemmArgs& a, cudaStream_t st) {
+static inline int mvn_row_gemm(RowGemmArgs a, cudaStream_t st) {
     if (a.rows <= 0 || a.N <= 0) return 0;
     dim3 grid(mvn_cdiv(a.rows, RG_BM), mvn_cdiv(a.N, RG_BN));
+    // few rows but a long contraction (the small video-upsampler GEMMs): split K so the grid fills the chip
+    int ktot = 0;
+    for (int s = 0; s < a.nsrc; ++s) ktot += a.src[s].K;
+    a.ksplit = 1;
+    if (a.allow_ksplit && a.epi == EPI_STORE && a.out_dtype == MVN_F32 && a.out_shift == 0 && a.out_T == a.Trow && grid.x * grid.y < 148 && ktot >= 256) {
+        int ks = (2 * 148) / (grid.x * grid.y);
+        if (ks > ktot / (2 * RG_BK)) ks = ktot / (2 * RG_BK);
+        if (ks > 1) {
+            a.ksplit = ks;
+            if (cudaMemset2DAsync(a.out, (size_t)a.ldo * 4, 0, (size_t)a.N * 4, (size_t)a.rows, st) != cudaSuccess) {
+                mvn_set_error("row_gemm: clearing the split-K output failed"); return -1;
+            }
+            grid.z = ks;
+        }
+    }
     row_gemm_kernel<<<grid, 256, 0, st>>>(a);
     return mvn_check_launch("row_gemm");
 }
@@ -340,7 +361,7 @@ static inline int mvn_tn_gemm(TnGemmArgs a, cudaStream_t st) {
     long long want = (148LL * 8) / ((long long)ktiles * ntiles);
     if (want < 1) want = 1;
     long long rpc = (a.rows + want - 1) / want;
-    if (rpc < 256) rpc = 256;
+    if (rpc < 64) rpc = 64;
     rpc = ((rpc + TN_BR - 1) / TN_BR) * TN_BR;
     a.rows_per_cta = rpc;
     dim3 grid(ktiles, ntiles, mvn_cdiv(a.rows, rpc));

@@ -316,6 +316,7 @@ static int video_fwd(const Ctx& c, const float* video) {
         RowGemmArgs a = new_args(rows, rows, 10 * C, EPI_STORE, c.packed + c.P.bt[i]);
         a.nsrc = 1; a.src[0] = make_src(in[i], MVN_F32, C, C, rows, 0, 0, c.packed + c.P.wt[i], 10 * C);
         set_out(a, out[i], i == 2 ? g.adt : MVN_F32, 10 * C, rows, 0);
+        a.allow_ksplit = 1;
         if ((rc = mvn_row_gemm(a, c.st))) return rc;
     }
     return 0;
@@ -570,6 +571,7 @@ static int video_bwd(const Ctx& c, const float* video, const void* dctx, int dct
         RowGemmArgs a = new_args(rows, rows, C, EPI_STORE, nullptr);
         a.nsrc = 1; a.src[0] = make_src(dout[i], ddt[i], 10 * C, 10 * C, rows, 0, 0, c.packed + c.P.wtT[i], C);
         set_out(a, din[i], MVN_F32, C, rows, 0);
+        a.allow_ksplit = 1;
         if ((rc = mvn_row_gemm(a, c.st))) return rc;
     }
     const int rows = g.B * 160, K = 4096 * g.Cin;
