@@ -29,3 +29,10 @@ int mvn_tc_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, co
 int mvn_tc_input_supported(int A, int C);
 int mvn_tc_input_bwd(const float* audio, const int* codes, const unsigned char* dense, const void* p, const void* u,
                      float* dwin, float* partial, const Geo& g, cudaStream_t st);
+// last level of the video upsampler on tensor cores (upsample_tc.cu), C == 64
+int mvn_tc_upsample_supported(int C);
+size_t mvn_tc_upsample_img_floats();
+int mvn_tc_upsample_pack(const float* wt, const float* bt, float* img, cudaStream_t st);
+int mvn_tc_upsample_fwd(const float* img, const void* u2_bf16, void* ctx_bf16, long long rows, cudaStream_t st);
+int mvn_tc_upsample_bwd(const float* img, const void* u2_bf16, const void* dctx_bf16, float* du2, float* dwt, float* dbt,
+                        float* partial, long long rows, cudaStream_t st);

@@ -56,6 +56,7 @@ struct PackedLayout {
     size_t tc_head;             // tensor-core image of conv2.weight (bf16 [64][64], 128B swizzle), A == 64 only
     size_t wv, bv;              // video conv: [4096*Cin][C], [C]
     size_t wt[3], bt[3], wtT[3];// transposed convs: [C][10C], [10C] (bias tiled), [10C][C]
+    size_t tc_up;               // tensor-core image of the last upsampler level (bf16 [640][64] + bias), video && C == 64
     size_t total;               // elements
 };
 
@@ -81,7 +82,9 @@ static inline void packed_layout(const Geo& g, PackedLayout& p) {
     if (g.video) {
         p.wv = take((size_t)4096 * g.Cin * C); p.bv = take(C);
         for (int i = 0; i < 3; ++i) { p.wt[i] = take(C * 10 * C); p.bt[i] = take(10 * C); p.wtT[i] = take(10 * C * C); }
+        p.tc_up = take(C == 64 ? (5 * 16384 + 3072) / 4 : 0);
     } else {
+        p.tc_up = 0;
         p.wv = p.bv = 0;
         for (int i = 0; i < 3; ++i) p.wt[i] = p.bt[i] = p.wtT[i] = 0;
     }

@@ -311,11 +311,13 @@ static int video_fwd(const Ctx& c, const float* video) {
     // row-major output IS the time-major upsampled signal (movenet/wavenet.py:102-118,154)
     const void* in[3] = {enc, u1, u2}; void* out[3] = {u1, u2, ctx};
     const int len[3] = {160, 1600, 16000};
+    const bool tc3 = g.adt == MVN_DTYPE_BF16 && mvn_tc_upsample_supported(C);   // last level on tensor cores: u2 kept in bf16
     for (int i = 0; i < 3; ++i) {
         const int rows = g.B * len[i];
+        if (i == 2 && tc3) return mvn_tc_upsample_fwd(c.packed + c.P.tc_up, u2, ctx, rows, c.st);
         RowGemmArgs a = new_args(rows, rows, 10 * C, EPI_STORE, c.packed + c.P.bt[i]);
         a.nsrc = 1; a.src[0] = make_src(in[i], MVN_F32, C, C, rows, 0, 0, c.packed + c.P.wt[i], 10 * C);
-        set_out(a, out[i], i == 2 ? g.adt : MVN_F32, 10 * C, rows, 0);
+        set_out(a, out[i], (i == 2 || (i == 1 && tc3)) ? g.adt : MVN_F32, 10 * C, rows, 0);
         a.allow_ksplit = 1;
         if ((rc = mvn_row_gemm(a, c.st))) return rc;
     }
@@ -563,6 +565,11 @@ static int video_bwd(const Ctx& c, const float* video, const void* dctx, int dct
     int rc;
     for (int i = 2; i >= 0; --i) {
         const int rows = g.B * len[i];
+        if (i == 2 && dctx_dtype == MVN_BF16 && g.adt == MVN_DTYPE_BF16 && mvn_tc_upsample_supported(C)) {
+            if ((rc = mvn_tc_upsample_bwd(c.packed + c.P.tc_up, u2, dctx, du2, pg + c.P.wt[2], pg + c.P.bt[2],
+                                          (float*)(c.scratch + c.SL.tc_partial), rows, c.st))) return rc;
+            continue;
+        }
         TnGemmArgs t; memset(&t, 0, sizeof(t));
         t.rows = rows; t.Trow = rows; t.N = 10 * C; t.nsrc = 1;
         t.src[0] = make_tn(in[i], MVN_F32, C, C, rows, 0, 0, pg + c.P.wt[i], 10 * C);
