@@ -124,11 +124,17 @@ input_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_cons
 __global__ void input_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ dwin, int A) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= IPART) return;
-    const int m = i >> 6, c = i & 63, tap = m >> 6, ch = m & 63;
+    const int m = i >> 6, col = i & 63, tap = m >> 6, ch = m & 63;
     if (ch >= A) return;
-    float acc = 0.f;
-    for (int k = 0; k < n_cta; ++k) acc += partial[(size_t)k * IPART + i];
-    dwin[((size_t)tap * A + ch) * 64 + c] = acc;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int c = 0;
+    for (; c + 4 <= n_cta; c += 4) {
+        a0 += partial[(size_t)c * IPART + i]; a1 += partial[(size_t)(c + 1) * IPART + i];
+        a2 += partial[(size_t)(c + 2) * IPART + i]; a3 += partial[(size_t)(c + 3) * IPART + i];
+    }
+    for (; c < n_cta; ++c) a0 += partial[(size_t)c * IPART + i];
+    const float acc = (a0 + a1) + (a2 + a3);
+    dwin[((size_t)tap * A + ch) * 64 + col] = acc;
 }
 
 }  // namespace

@@ -79,8 +79,8 @@ __global__ void video_conv_init_kernel(float* __restrict__ enc, const float* __r
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows * C) enc[i] = bias[i % C];
 }
-#define VC_ROWS 8
-#define VC_K 512
+#define VC_ROWS 32
+#define VC_K 256
 __global__ void __launch_bounds__(256) video_conv_kernel(const float* __restrict__ video, const float* __restrict__ wv,
                                                          float* __restrict__ enc, int rows, int K, int C) {
     __shared__ float xs[VC_ROWS][VC_K];
@@ -90,20 +90,21 @@ __global__ void __launch_bounds__(256) video_conv_kernel(const float* __restrict
         xs[rr][kk] = (r0 + rr < rows && k0 + kk < K) ? video[(size_t)(r0 + rr) * K + k0 + kk] : 0.f;
     }
     __syncthreads();
-    const int cpg = blockDim.x / 4;              // threads per row group
+    const int cpg = blockDim.x / 4;              // 4 thread groups, 8 rows each
     const int grp = threadIdx.x / cpg, cl = threadIdx.x % cpg;
     for (int c = cl; c < C; c += cpg) {
-        float a0 = 0.f, a1 = 0.f;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const float* w = wv + (size_t)k0 * C + c;
         const int kmax = min(VC_K, K - k0);
-#pragma unroll 8
+#pragma unroll 4
         for (int kk = 0; kk < kmax; ++kk) {
             const float wvv = w[(size_t)kk * C];
-            a0 = fmaf(xs[2 * grp][kk], wvv, a0);
-            a1 = fmaf(xs[2 * grp + 1][kk], wvv, a1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(xs[8 * grp + i][kk], wvv, acc[i]);
         }
-        if (r0 + 2 * grp < rows) atomicAdd(enc + (size_t)(r0 + 2 * grp) * C + c, a0);
-        if (r0 + 2 * grp + 1 < rows) atomicAdd(enc + (size_t)(r0 + 2 * grp + 1) * C + c, a1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (r0 + 8 * grp + i < rows) atomicAdd(enc + (size_t)(r0 + 8 * grp + i) * C + c, acc[i]);
     }
 }
 

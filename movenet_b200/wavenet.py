@@ -241,8 +241,18 @@ class WaveNet(nn.Module):
 
     # ------------------------------------------------------------------ plumbing
     def _param_list(self):
-        """parameters in state_dict order == the C ABI's MVN_PARAM_* order"""
-        return [p for _, p in self.named_parameters()]
+        """parameters in state_dict order == the C ABI's MVN_PARAM_* order (cached: walking the module tree every
+        step costs more host time than some of the kernels take)"""
+        cache = self.__dict__.get("_param_cache")
+        if cache is None:
+            cache = self.__dict__["_param_cache"] = [p for _, p in self.named_parameters()]
+        return cache
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_param_cache", None)
+        self.__dict__.pop("_grad_cache", None)
+        self._ptr_tables = {}
+        return super()._apply(fn, *args, **kwargs)
 
     def _check_audio(self, audio):
         if not isinstance(audio, torch.Tensor) or audio.dim() != 3:
@@ -298,6 +308,9 @@ class WaveNet(nn.Module):
         """element offset of every parameter's gradient in the flat buffer (-1: no gradient, as in the
         reference: video/context parameters without video, and the last layer's conv_residual whose
         output is discarded, movenet/modules.py:125-130)."""
+        cache = self.__dict__.setdefault("_grad_cache", {})
+        if has_video in cache:
+            return cache[has_video][0], cache[has_video][1]
         last = f"residual_conv_stack.conv_layers.{self.layer_size * self.stack_size - 1}.conv_residual."
         offsets, off = [], 0
         for name, p in self.named_parameters():
@@ -308,6 +321,14 @@ class WaveNet(nn.Module):
             else:
                 offsets.append(off)
                 off += (p.numel() + 3) // 4 * 4
+        # split plan: consecutive chunks of the flat buffer = [grad, pad, grad, pad, ...]
+        sizes, shapes = [], []
+        for o, p in zip(offsets, self._param_list()):
+            if o >= 0:
+                n = p.numel()
+                sizes += [n, (n + 3) // 4 * 4 - n]
+                shapes.append(p.shape)
+        cache[has_video] = (offsets, off, sizes, shapes)
         return offsets, off
 
     def _grad_offsets(self, has_video, device):
@@ -318,8 +339,17 @@ class WaveNet(nn.Module):
         return self._ptr_tables[key]
 
     def _flat_grads(self, has_video, device):
+        """a fresh flat fp32 buffer and, per parameter, the view of it that becomes param.grad (None: no gradient)"""
         offsets, total = self._grad_layout(has_video)
+        _, _, sizes, shapes = self._grad_cache[has_video]
         flat = torch.empty(total, dtype=torch.float32, device=device)
-        views = [None if o < 0 else flat[o:o + p.numel()].view_as(p)
-                 for o, (_, p) in zip(offsets, self.named_parameters())]
+        chunks = flat.split_with_sizes(sizes)[0::2]
+        it = iter(zip(chunks, shapes))
+        views = []
+        for o in offsets:
+            if o < 0:
+                views.append(None)
+            else:
+                c, shp = next(it)
+                views.append(c.view(shp))
         return flat, views
