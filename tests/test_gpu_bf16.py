@@ -133,3 +133,24 @@ def test_tensor_core_decoder_teacher_forced_logits():
     big = audio[:1, :, :RF].repeat(300, 1, 1).contiguous()
     g2 = m.generate(big, n_samples=RF + 8, temperature=0.0)
     assert torch.equal(g2[0], g2[299]) and torch.equal(g2[0], g2[128]) and torch.equal(g2[0, :, :RF + 8].cpu(), gen[0, :, :RF + 8].cpu())
+
+
+def test_bf16_non_one_hot_audio():
+    """arbitrary float audio (not one-hot) through the tensor-core mode: the input conv takes its dense path in the
+    forward kernel and the one-hot^T x d(h0) weight-gradient kernel puts the real values into its operand tile."""
+    fx = load_golden("cfg00")
+    m32, m16 = build(fx, "fp32"), build(fx, "bf16")
+    g = torch.Generator().manual_seed(5)
+    audio = torch.rand(2, 64, 200, generator=g).cuda()
+    audio[0, :, 17] = 0
+    audio[1, :, 18] = 0; audio[1, 5, 18] = 1
+    target = audio[:, :, m32.receptive_fields:].argmax(1)
+    grads = []
+    for m in (m32, m16):
+        out = m(audio)
+        F.cross_entropy(out, target).backward()
+        grads.append(m.causal_conv.conv.weight.grad.clone())
+    assert rel_l2(grads[1], grads[0]) < GRAD_RTOL
+    with torch.no_grad():
+        a, b = m32(audio, output_unnormalized=False), m16(audio, output_unnormalized=False)
+    assert (a - b).abs().max().item() <= LOGIT_RTOL * a.abs().max().item()
