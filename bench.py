@@ -282,7 +282,7 @@ def decode_bench(dev):
     RF = m.receptive_fields
     res = {}
     from movenet_b200.decode import fast_mode_available, prefill, run_steps
-    for mode, clips, n_new in (("exact_f32", 1, 2000), ("exact_f32", 1184, 400), ("fast_bf16", 148 * 256, 400)):
+    for mode, clips, n_new in (("exact_f32", 1, 2000), ("exact_f32", 1184, 400), ("fast_bf16", 148 * 512, 400)):
         fast = mode == "fast_bf16"
         if fast and not fast_mode_available(m, clips, RF):
             continue

@@ -23,10 +23,11 @@ using namespace tc;
 namespace {
 
 constexpr int DS = 8;            // skip_channels handled
-constexpr int GROUPS = 2;        // 128-clip groups per CTA
+template <int C> struct Cfg { static constexpr int GROUPS = C <= 16 ? 4 : 2; };   // 128-clip groups per CTA (register budget)
 
 struct DecTcArgs {
     const uint8_t* img; int img_bytes;
+    const float* win;      // [2][A][C] fp32 input-conv rows, gathered from global memory (L1/L2 resident)
     __nv_bfloat16* queues; int* last2; int* out_codes_t; float* out_logits; const int* forced;
     int B, N, A, t_start, n_new;
     float temperature; unsigned seed;
@@ -84,23 +85,25 @@ __global__ void decode_tc_pack_kernel(const float* __restrict__ packed, PackedLa
         *(__nv_bfloat16*)(img + oW2 + core_off(n, k, A)) = __float2bfloat16(packed[P.w2p + (size_t)k * A + n]);
     }
     for (int i = i0; i < A; i += stride) { ((float*)(img + oB1))[i] = packed[P.b1 + i]; ((float*)(img + oB2))[i] = packed[P.b2 + i]; }
-    for (int i = i0; i < 2 * A * C; i += stride) ((float*)(img + oWin))[i] = packed[P.win + i];
 }
 
 template <int C>
-__global__ void __launch_bounds__(128 * GROUPS, 1) decode_tc_kernel(const DecTcArgs a) {
+__global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(const DecTcArgs a) {
     using I = Img<C>;
+    constexpr int GROUPS = Cfg<C>::GROUPS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* simg = smem;
     const int A = a.A;
     const int tid = threadIdx.x, grp = tid >> 7, r = tid & 127, warp = tid >> 5;
-    // per-group tiles after the image: layer A [128 x 2C] | gated [128 x C] | head A [128 x max(16, A)]
-    const int tiles_per_group = 128 * 2 * C * 2 + 128 * C * 2 + 128 * A * 2;
+    // per-group tiles after the image: layer A [128 x 2C] | gated [128 x C], and -- aliased onto them, the layers are
+    // finished when the head runs -- the head's A tile [128 x max(16, A)]
+    const int layer_tiles = 128 * 2 * C * 2 + 128 * C * 2, head_tile = 128 * A * 2;
+    const int tiles_per_group = layer_tiles > head_tile ? layer_tiles : head_tile;
     uint8_t* gbase = smem + ((a.img_bytes + 1023) & ~1023) + grp * ((tiles_per_group + 1023) & ~1023);
     uint8_t* sA = gbase;
     uint8_t* sG = sA + 128 * 2 * C * 2;
-    uint8_t* sH = sG + 128 * C * 2;
+    uint8_t* sH = gbase;
     uint64_t* bars = (uint64_t*)(smem + ((a.img_bytes + 1023) & ~1023) + GROUPS * ((tiles_per_group + 1023) & ~1023));
     uint64_t* mma_bar = bars + grp;
     uint32_t* tmem_slot = (uint32_t*)(bars + GROUPS);
@@ -116,15 +119,16 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) decode_tc_kernel(const DecTcA
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot + grp * 256;
+    const uint32_t tmem = *tmem_slot + grp * (512 / GROUPS);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    constexpr int D1 = 0, D2 = 2 * C;             // TMEM columns: D1 [0, 2C) ; D2 [2C, 2C + N2) ; head [128, 128 + A)
-    constexpr int DH = 128;
+    // TMEM columns of the group's window: D1 [0, 2C) ; D2 [2C, 2C + N2) ; the head reuses [0, A) once the layers are done
+    constexpr int D1 = 0, D2 = 2 * C, DH = 0;
+    static_assert(2 * C + I::N2 <= 512 / GROUPS, "TMEM window");
     const uint32_t i1 = umma_idesc_major(128, 2 * C, 0, 0), i2 = umma_idesc_major(128, I::N2, 0, 0), ih = umma_idesc_major(128, A, 0, 0);
 
     const int b = (blockIdx.x * GROUPS + grp) * 128 + r;
     const bool live = b < a.B;
-    const float* win = (const float*)(simg + a.oWin);
+    const float* win = a.win;
     int code_prev = live ? a.last2[2 * b] : -1, code_cur = live ? a.last2[2 * b + 1] : -1;
     uint32_t phase = 0;
 
@@ -358,15 +362,16 @@ int image_offsets(const Geo& g, DecTcArgs& a) {
     a.oB1 = o; o += g.A * 4;
     a.oW2 = o; o += g.A * g.A * 2;
     a.oB2 = o; o += g.A * 4;
-    a.oWin = o; o += 2 * g.A * g.C * 4;
+    a.oWin = o;
     a.img_bytes = (o + 15) & ~15;
     return a.img_bytes;
 }
 
 template <int C>
 int smem_bytes(const Geo& g, int img_bytes) {
-    const int tiles = 128 * 2 * C * 2 + 128 * C * 2 + 128 * g.A * 2;
-    return ((img_bytes + 1023) & ~1023) + GROUPS * ((tiles + 1023) & ~1023) + 64 + 1024;
+    const int layer_tiles = 128 * 2 * C * 2 + 128 * C * 2, head_tile = 128 * g.A * 2;
+    const int tiles = layer_tiles > head_tile ? layer_tiles : head_tile;
+    return ((img_bytes + 1023) & ~1023) + Cfg<C>::GROUPS * ((tiles + 1023) & ~1023) + 64 + 1024;
 }
 
 template <int C>
@@ -376,7 +381,7 @@ int run_steps(const Geo& g, DecTcArgs& a, const float* packed, const PackedLayou
     if (rc) return rc;
     const int smem = smem_bytes<C>(g, a.img_bytes);
     MVN_CUDA(cudaFuncSetAttribute(decode_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    decode_tc_kernel<C><<<mvn_cdiv(g.B, 128 * GROUPS), 128 * GROUPS, smem, st>>>(a);
+    decode_tc_kernel<C><<<mvn_cdiv(g.B, 128 * Cfg<C>::GROUPS), 128 * Cfg<C>::GROUPS, smem, st>>>(a);
     return mvn_check_launch("decode_tc_steps");
 }
 
@@ -435,7 +440,7 @@ extern "C" int mvn_decode_tc_steps(const mvn_shape_t* s, const void* packed, voi
     a.last2 = (int*)((char*)state + al256(qe * (size_t)g.B * 2));
     uint8_t* img = (uint8_t*)state + al256(qe * (size_t)g.B * 2) + al256((size_t)g.B * 2 * 4);
     a.img = img;
-    a.out_codes_t = out_codes_t; a.out_logits = out_logits; a.forced = forced;
+    a.out_codes_t = out_codes_t; a.out_logits = out_logits; a.forced = forced; a.win = (const float*)packed + P.win;
     a.B = g.B; a.N = g.N; a.A = g.A; a.t_start = t_start; a.n_new = n_new; a.temperature = temperature; a.seed = seed;
     cudaStream_t st = (cudaStream_t)stream;
     if (g.C == 16) { image_offsets<16>(g, a); return run_steps<16>(g, a, (const float*)packed, P, img, st); }

@@ -364,14 +364,9 @@ __global__ void head_reduce_kernel(const float* __restrict__ partial, int n_cta,
             dst = m < 64 ? pg + P.b2 + m : pg + P.b1 + (m - 64);
         }
         if (!dst) continue;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int c = 0;
-        for (; c + 4 <= n_cta; c += 4) {
-            a0 += partial[(size_t)c * HPART + i]; a1 += partial[(size_t)(c + 1) * HPART + i];
-            a2 += partial[(size_t)(c + 2) * HPART + i]; a3 += partial[(size_t)(c + 3) * HPART + i];
-        }
-        for (; c < n_cta; ++c) a0 += partial[(size_t)c * HPART + i];
-        const float acc = (a0 + a1) + (a2 + a3);
+        float acc = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < n_cta; ++c) acc += partial[(size_t)c * HPART + i];
         *dst = acc;
     }
 }

@@ -126,14 +126,9 @@ __global__ void input_reduce_kernel(const float* __restrict__ partial, int n_cta
     if (i >= IPART) return;
     const int m = i >> 6, col = i & 63, tap = m >> 6, ch = m & 63;
     if (ch >= A) return;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int c = 0;
-    for (; c + 4 <= n_cta; c += 4) {
-        a0 += partial[(size_t)c * IPART + i]; a1 += partial[(size_t)(c + 1) * IPART + i];
-        a2 += partial[(size_t)(c + 2) * IPART + i]; a3 += partial[(size_t)(c + 3) * IPART + i];
-    }
-    for (; c < n_cta; ++c) a0 += partial[(size_t)c * IPART + i];
-    const float acc = (a0 + a1) + (a2 + a3);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < n_cta; ++c) acc += partial[(size_t)c * IPART + i];
     dwin[((size_t)tap * A + ch) * 64 + col] = acc;
 }
 

@@ -386,14 +386,9 @@ __global__ void tc_bwd_reduce_kernel(const float* __restrict__ partial, int n_ct
             else { const int n = j - 128; if (n < CC + S && (n >= CC || has_resid)) dst = lg + P.obrs + n; }
         }
         if (!dst) continue;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int c = 0;
-        for (; c + 4 <= n_cta; c += 4) {
-            a0 += partial[(size_t)c * PART_FLOATS + i]; a1 += partial[(size_t)(c + 1) * PART_FLOATS + i];
-            a2 += partial[(size_t)(c + 2) * PART_FLOATS + i]; a3 += partial[(size_t)(c + 3) * PART_FLOATS + i];
-        }
-        for (; c < n_cta; ++c) a0 += partial[(size_t)c * PART_FLOATS + i];
-        const float acc = (a0 + a1) + (a2 + a3);
+        float acc = 0.f;
+#pragma unroll 8
+        for (int c = 0; c < n_cta; ++c) acc += partial[(size_t)c * PART_FLOATS + i];
         *dst = acc;
     }
 }

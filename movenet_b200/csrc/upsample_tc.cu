@@ -278,14 +278,9 @@ up_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_u2, const __grid_consta
 __global__ void up_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ dwt, float* __restrict__ dbt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= UPART) return;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int c = 0;
-    for (; c + 4 <= n_cta; c += 4) {
-        a0 += partial[(size_t)c * UPART + i]; a1 += partial[(size_t)(c + 1) * UPART + i];
-        a2 += partial[(size_t)(c + 2) * UPART + i]; a3 += partial[(size_t)(c + 3) * UPART + i];
-    }
-    for (; c < n_cta; ++c) a0 += partial[(size_t)c * UPART + i];
-    const float acc = (a0 + a1) + (a2 + a3);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < n_cta; ++c) acc += partial[(size_t)c * UPART + i];
     if (i < UN * 64) dwt[(size_t)(i & 63) * UN + (i >> 6)] = acc; else dbt[i - UN * 64] = acc;
 }
 
