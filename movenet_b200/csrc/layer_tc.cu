@@ -31,7 +31,7 @@ __host__ __device__ inline int smem_total(int nchunks, int N2) { return smem_a_o
 
 // image writer: one block row per layer
 __global__ void tc_pack_kernel(const float* const* __restrict__ ptrs, float* __restrict__ packed, PackedLayout P, int S,
-                               int nchunks, int N2, int video) {
+                               int nchunks, int N2, int video, int Cl) {
     const int l = blockIdx.y;
     const float* const* lp = ptrs + MVN_PARAM_LAYER(l, 0);
     const float *wf = lp[0], *wg = lp[1], *vf = lp[2], *bvf = lp[3], *vg = lp[4], *bvg = lp[5], *wr = lp[6], *br = lp[7],
@@ -41,21 +41,24 @@ __global__ void tc_pack_kernel(const float* const* __restrict__ ptrs, float* __r
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nz + nrs + 256; i += gridDim.x * blockDim.x) {
         if (i < nz) {
             const int n = i / Kz, k = i - n * Kz, c = n & 63, gate = n >> 6;
-            float v;
-            if (k < CC) v = (gate ? wg : wf)[((size_t)c * CC + k) * 2 + 0];
-            else if (k < 2 * CC) v = (gate ? wg : wf)[((size_t)c * CC + (k - CC)) * 2 + 1];
-            else v = (gate ? vg : vf)[(size_t)c * CC + (k - 2 * CC)];
+            float v = 0.f;
             const int chunk = k >> 6, kk = k & 63;
+            if (c < Cl && kk < Cl) {          // reference tensors have Cl <= 64 channels; the rest of the image is zero
+                if (k < CC) v = (gate ? wg : wf)[((size_t)c * Cl + kk) * 2 + 0];
+                else if (k < 2 * CC) v = (gate ? wg : wf)[((size_t)c * Cl + kk) * 2 + 1];
+                else v = (gate ? vg : vf)[(size_t)c * Cl + kk];
+            }
             *(__nv_bfloat16*)(img + chunk * TILE_BYTES + n * 128 + ((((kk >> 3) ^ (n & 7)) << 4) | ((kk & 7) << 1))) = __float2bfloat16(v);
         } else if (i < nz + nrs) {
             const int j = i - nz, n = j >> 6, k = j & 63;
-            const float v = n < CC ? wr[(size_t)n * CC + k] : (n < CC + S ? ws[(size_t)(n - CC) * CC + k] : 0.f);
+            float v = 0.f;
+            if (k < Cl) { if (n < CC) { if (n < Cl) v = wr[(size_t)n * Cl + k]; } else if (n < CC + S) v = ws[(size_t)(n - CC) * Cl + k]; }
             *(__nv_bfloat16*)(img + smem_brs_off(nchunks) + n * 128 + ((((k >> 3) ^ (n & 7)) << 4) | ((k & 7) << 1))) = __float2bfloat16(v);
         } else {
             const int n = i - nz - nrs;
             float* bias = (float*)(img + smem_bias_off(nchunks, N2));
-            if (n < 128) bias[n] = video ? ((n >> 6) ? bvg : bvf)[n & 63] : 0.f;
-            else { const int m = n - 128; bias[n] = m < CC ? br[m] : (m < CC + S ? bs[m - CC] : 0.f); }
+            if (n < 128) bias[n] = (video && (n & 63) < Cl) ? ((n >> 6) ? bvg : bvf)[n & 63] : 0.f;
+            else { const int m = n - 128; bias[n] = m < CC ? (m < Cl ? br[m] : 0.f) : (m < CC + S ? bs[m - CC] : 0.f); }
         }
     }
 }
@@ -265,7 +268,7 @@ int mvn_tc_pack(const float* const* param_ptrs_dev, float* packed, const PackedL
     const int nchunks = g.video ? 3 : 2, N2 = ((g.C + g.S + 15) / 16) * 16;
     MVN_REQUIRE(smem_a_off(nchunks, N2) <= MVN_TC_IMG_BYTES, "tensor-core weight image does not fit its slot");
     dim3 grid(16, g.N);
-    tc_pack_kernel<<<grid, 256, 0, st>>>(param_ptrs_dev, packed, P, g.S, nchunks, N2, g.video);
+    tc_pack_kernel<<<grid, 256, 0, st>>>(param_ptrs_dev, packed, P, g.S, nchunks, N2, g.video, g.Cl);
     return mvn_check_launch("tc_pack");
 }
 

@@ -192,7 +192,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 umma(tmem + 128, umma_desc(smem_u32(sDXS) + k * 32), umma_desc_mn(smem_u32(sBrs) + k * 2048, TILE_BYTES), iG2, k != 0);
-            umma(tmem + 128, umma_desc(smem_u32(sDSK)), umma_desc_mn(smem_u32(sBrs) + 4 * 2048, TILE_BYTES), iG2, 1);
+            for (int k = 0; k < (a.S + 15) / 16; ++k)      // the skip channels: rows 64.. of the image, 16 per step
+                umma(tmem + 128, umma_desc(smem_u32(sDSK) + k * 32), umma_desc_mn(smem_u32(sBrs) + (4 + k) * 2048, TILE_BYTES), iG2, 1);
             umma_commit(mma_bar);
         }
         mbar_wait(mma_bar, 0);

@@ -10,6 +10,9 @@
 
 struct Geo {
     int L, St, A, C, S, Cin, B, T, video, adt, remove_last, logits;
+    int Cl;       // the model's residual_channels; C is the PHYSICAL channel count of every internal buffer: in the
+                  // tensor-core (bf16) mode narrower models are zero-padded to 64 channels (the pad stays exactly zero
+                  // through every layer: tanh(0)*sigmoid(0) = 0), so one set of C = 64 kernels serves them all
     int N;        // layers
     int RF;       // receptive_fields (movenet/wavenet.py:125-134)
     int Tout;     // T - RF + 1      (movenet/wavenet.py:136-147)
@@ -22,7 +25,9 @@ struct Geo {
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static inline int geo_init(Geo& g, const mvn_shape_t* s) {
-    g.L = s->layer_size; g.St = s->stack_size; g.A = s->input_channels; g.C = s->residual_channels;
+    g.L = s->layer_size; g.St = s->stack_size; g.A = s->input_channels; g.Cl = s->residual_channels;
+    g.C = (s->act_dtype == MVN_DTYPE_BF16 && g.Cl < 64 && s->skip_channels % 8 == 0 && s->skip_channels >= 8 &&
+           s->skip_channels <= (s->has_video ? 32 : 64)) ? 64 : g.Cl;
     g.S = s->skip_channels; g.Cin = s->context_in_channels; g.B = s->batch; g.T = s->frames;
     g.video = s->has_video; g.adt = s->act_dtype; g.remove_last = s->remove_last; g.logits = s->output_logits;
     g.N = g.L * g.St;

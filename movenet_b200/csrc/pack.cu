@@ -5,8 +5,9 @@
 #include "layer_tc.h"
 
 // one block row per layer: blockIdx.y = layer.  ptrs = device table in state_dict order.
+// C: physical channels of the packed layout, Cl <= C: channels of the reference tensors (the rest is zero padding)
 __global__ void pack_layer_kernel(const float* const* __restrict__ ptrs, float* __restrict__ packed,
-                                  PackedLayout P, int C, int S, int Kz, int video) {
+                                  PackedLayout P, int C, int Cl, int S, int Kz, int video) {
     const int l = blockIdx.y;
     const float* const* lp = ptrs + MVN_PARAM_LAYER(l, 0);
     const float *wf = lp[0], *wg = lp[1], *vf = lp[2], *bvf = lp[3], *vg = lp[4], *bvg = lp[5], *wr = lp[6],
@@ -18,83 +19,87 @@ __global__ void pack_layer_kernel(const float* const* __restrict__ ptrs, float* 
         int j = i;
         if (j < nWz) {
             const int k = j / (2 * C), n = j % (2 * C), c = n >> 1, gate = n & 1;
-            float v;
-            if (k < C) v = (gate ? wg : wf)[((size_t)c * C + k) * 2 + 0];
-            else if (k < 2 * C) v = (gate ? wg : wf)[((size_t)c * C + (k - C)) * 2 + 1];
-            else v = (gate ? vg : vf)[(size_t)c * C + (k - 2 * C)];
+            float v = 0.f;
+            const int kk = k % C;            // input channel inside its tap / context block
+            if (c < Cl && kk < Cl) {
+                if (k < C) v = (gate ? wg : wf)[((size_t)c * Cl + kk) * 2 + 0];
+                else if (k < 2 * C) v = (gate ? wg : wf)[((size_t)c * Cl + kk) * 2 + 1];
+                else v = (gate ? vg : vf)[(size_t)c * Cl + kk];
+            }
             base[P.oWz + j] = v;
             base[P.oWzT + (size_t)n * Kz + k] = v;
             continue;
         }
         j -= nWz;
-        if (j < nbz) { base[P.obz + j] = video ? ((j & 1) ? bvg : bvf)[j >> 1] : 0.f; continue; }
+        if (j < nbz) { base[P.obz + j] = (video && (j >> 1) < Cl) ? ((j & 1) ? bvg : bvf)[j >> 1] : 0.f; continue; }
         j -= nbz;
         if (j < nWrs) {
             const int k = j / (C + S), n = j % (C + S);
-            const float v = n < C ? wr[(size_t)n * C + k] : ws[(size_t)(n - C) * C + k];
+            float v = 0.f;
+            if (k < Cl) { if (n < C) { if (n < Cl) v = wr[(size_t)n * Cl + k]; } else v = ws[(size_t)(n - C) * Cl + k]; }
             base[P.oWrs + j] = v;
             base[P.oWrsT + (size_t)n * C + k] = v;
             continue;
         }
         j -= nWrs;
-        base[P.obrs + j] = j < C ? br[j] : bs[j - C];
+        base[P.obrs + j] = j < C ? (j < Cl ? br[j] : 0.f) : bs[j - C];
     }
 }
 
 __global__ void unpack_layer_kernel(float* __restrict__ flat, const long long* __restrict__ offs,
-                                    const float* __restrict__ packed, PackedLayout P, int C, int S, int Kz, int video) {
+                                    const float* __restrict__ packed, PackedLayout P, int C, int Cl, int S, int Kz, int video) {
     const int l = blockIdx.y;
     float* lp[10];
 #pragma unroll
     for (int j = 0; j < 10; ++j) { const long long o = offs[MVN_PARAM_LAYER(l, j)]; lp[j] = o < 0 ? nullptr : flat + o; }
     const float* base = packed + P.layer0 + (size_t)l * P.layer_stride;
-    const int nW = C * C * 2, nV = C * C;
-    // segments: wf, wg (C*C*2 each) | vf, vg (C*C each) | bvf, bvg (C each) | wr (C*C) | br (C) | ws (S*C) | bs (S)
-    const int total = 2 * nW + 2 * nV + 2 * C + nV + C + S * C + S;
+    const int nW = Cl * Cl * 2, nV = Cl * Cl;
+    // segments (reference shapes, Cl channels): wf, wg | vf, vg | bvf, bvg | wr | br | ws | bs
+    const int total = 2 * nW + 2 * nV + 2 * Cl + nV + Cl + S * Cl + S;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int j = i;
         if (j < 2 * nW) {
             const int gate = j >= nW; if (gate) j -= nW;
-            const int tap = j & 1, k = (j >> 1) % C, c = (j >> 1) / C;
+            const int tap = j & 1, k = (j >> 1) % Cl, c = (j >> 1) / Cl;
             if (lp[gate]) lp[gate][j] = base[P.oWz + (size_t)(tap * C + k) * 2 * C + 2 * c + gate];
             continue;
         }
         j -= 2 * nW;
         if (j < 2 * nV) {
             const int gate = j >= nV; if (gate) j -= nV;
-            const int k = j % C, c = j / C;
+            const int k = j % Cl, c = j / Cl;
             float* dst = lp[gate ? 4 : 2];
             if (dst) dst[j] = video ? base[P.oWz + (size_t)(2 * C + k) * 2 * C + 2 * c + gate] : 0.f;
             continue;
         }
         j -= 2 * nV;
-        if (j < 2 * C) {
-            const int gate = j >= C; if (gate) j -= C;
+        if (j < 2 * Cl) {
+            const int gate = j >= Cl; if (gate) j -= Cl;
             float* dst = lp[gate ? 5 : 3];
             if (dst) dst[j] = video ? base[P.obz + 2 * j + gate] : 0.f;
             continue;
         }
-        j -= 2 * C;
-        if (j < nV) { const int k = j % C, n = j / C; if (lp[6]) lp[6][j] = base[P.oWrs + (size_t)k * (C + S) + n]; continue; }
+        j -= 2 * Cl;
+        if (j < nV) { const int k = j % Cl, n = j / Cl; if (lp[6]) lp[6][j] = base[P.oWrs + (size_t)k * (C + S) + n]; continue; }
         j -= nV;
-        if (j < C) { if (lp[7]) lp[7][j] = base[P.obrs + j]; continue; }
-        j -= C;
-        if (j < S * C) { const int k = j % C, s = j / C; if (lp[8]) lp[8][j] = base[P.oWrs + (size_t)k * (C + S) + C + s]; continue; }
-        j -= S * C;
+        if (j < Cl) { if (lp[7]) lp[7][j] = base[P.obrs + j]; continue; }
+        j -= Cl;
+        if (j < S * Cl) { const int k = j % Cl, s = j / Cl; if (lp[8]) lp[8][j] = base[P.oWrs + (size_t)k * (C + S) + C + s]; continue; }
+        j -= S * Cl;
         if (lp[9]) lp[9][j] = base[P.obrs + C + j];
     }
 }
 
 // input conv, head, video: blockIdx.y selects the group
 __global__ void pack_misc_kernel(const float* const* __restrict__ ptrs, float* __restrict__ packed, PackedLayout P,
-                                 int A, int C, int S, int Cin, int N, int video) {
+                                 int A, int C, int Cl, int S, int Cin, int N, int video) {
     const int grp = blockIdx.y;
     const int stride = gridDim.x * blockDim.x, i0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp == 0) {            // Win[tap][a][c] = w[c][a][tap]
         const float* w = ptrs[MVN_PARAM_CAUSAL_W];
         for (int i = i0; i < 2 * A * C; i += stride) {
             const int c = i % C, a = (i / C) % A, tap = i / (A * C);
-            packed[P.win + i] = w[((size_t)c * A + a) * 2 + tap];
+            packed[P.win + i] = c < Cl ? w[((size_t)c * A + a) * 2 + tap] : 0.f;
         }
     } else if (grp == 1) {     // head
         const float *w1 = ptrs[MVN_PARAM_DENSE(N, 0)], *b1 = ptrs[MVN_PARAM_DENSE(N, 1)],
@@ -115,25 +120,25 @@ __global__ void pack_misc_kernel(const float* const* __restrict__ ptrs, float* _
         const int K = 4096 * Cin;
         for (int i = i0; i < K * C; i += stride) {
             const int c = i % C, kk = i / C, ci = kk % Cin, hw = kk / Cin;
-            packed[P.wv + i] = w[((size_t)c * Cin + ci) * 4096 + hw];
+            packed[P.wv + i] = c < Cl ? w[((size_t)c * Cin + ci) * 4096 + hw] : 0.f;
         }
-        for (int i = i0; i < C; i += stride) packed[P.bv + i] = b[i];
+        for (int i = i0; i < C; i += stride) packed[P.bv + i] = i < Cl ? b[i] : 0.f;
     } else if (video && grp >= 3 && grp < 6) {   // ConvTranspose1d: wt[ci][j*C + co] = w[ci][co][j]
         const int lv = grp - 3;
         const float *w = ptrs[MVN_PARAM_VT_W(lv)], *b = ptrs[MVN_PARAM_VT_B(lv)];
         for (int i = i0; i < C * 10 * C; i += stride) {
             const int n = i % (10 * C), ci = i / (10 * C), j = n / C, co = n % C;
-            const float v = w[((size_t)ci * C + co) * 10 + j];
+            const float v = (ci < Cl && co < Cl) ? w[((size_t)ci * Cl + co) * 10 + j] : 0.f;
             packed[P.wt[lv] + i] = v;
             packed[P.wtT[lv] + (size_t)n * C + ci] = v;
         }
-        for (int i = i0; i < 10 * C; i += stride) packed[P.bt[lv] + i] = b[i % C];
+        for (int i = i0; i < 10 * C; i += stride) packed[P.bt[lv] + i] = (i % C) < Cl ? b[i % C] : 0.f;
     }
 }
 
 __global__ void unpack_misc_kernel(float* __restrict__ flat, const long long* __restrict__ offs,
                                    const float* __restrict__ packed, PackedLayout P,
-                                   int A, int C, int S, int Cin, int N, int video) {
+                                   int A, int C, int Cl, int S, int Cin, int N, int video) {
     const int grp = blockIdx.y;
     auto gp = [&](int i) -> float* { const long long o = offs[i]; return o < 0 ? nullptr : flat + o; };
     const int stride = gridDim.x * blockDim.x, i0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -141,7 +146,7 @@ __global__ void unpack_misc_kernel(float* __restrict__ flat, const long long* __
         float* w = gp(MVN_PARAM_CAUSAL_W);
         if (w) for (int i = i0; i < 2 * A * C; i += stride) {
             const int c = i % C, a = (i / C) % A, tap = i / (A * C);
-            w[((size_t)c * A + a) * 2 + tap] = packed[P.win + i];
+            if (c < Cl) w[((size_t)c * A + a) * 2 + tap] = packed[P.win + i];
         }
     } else if (grp == 1) {
         float *w1 = gp(MVN_PARAM_DENSE(N, 0)), *b1 = gp(MVN_PARAM_DENSE(N, 1)),
@@ -154,17 +159,17 @@ __global__ void unpack_misc_kernel(float* __restrict__ flat, const long long* __
         const int K = 4096 * Cin;
         if (w) for (int i = i0; i < K * C; i += stride) {
             const int c = i % C, kk = i / C, ci = kk % Cin, hw = kk / Cin;
-            w[((size_t)c * Cin + ci) * 4096 + hw] = video ? packed[P.wv + i] : 0.f;
+            if (c < Cl) w[((size_t)c * Cin + ci) * 4096 + hw] = video ? packed[P.wv + i] : 0.f;
         }
-        if (b) for (int i = i0; i < C; i += stride) b[i] = video ? packed[P.bv + i] : 0.f;
+        if (b) for (int i = i0; i < Cl; i += stride) b[i] = video ? packed[P.bv + i] : 0.f;
     } else if (grp >= 3 && grp < 6) {
         const int lv = grp - 3;
         float *w = gp(MVN_PARAM_VT_W(lv)), *b = gp(MVN_PARAM_VT_B(lv));
         if (w) for (int i = i0; i < C * 10 * C; i += stride) {
             const int n = i % (10 * C), ci = i / (10 * C), j = n / C, co = n % C;
-            w[((size_t)ci * C + co) * 10 + j] = video ? packed[P.wt[lv] + i] : 0.f;
+            if (ci < Cl && co < Cl) w[((size_t)ci * Cl + co) * 10 + j] = video ? packed[P.wt[lv] + i] : 0.f;
         }
-        if (b) for (int i = i0; i < C; i += stride) {
+        if (b) for (int i = i0; i < Cl; i += stride) {
             float acc = 0.f;
             if (video) for (int j = 0; j < 10; ++j) acc += packed[P.bt[lv] + j * C + i];
             b[i] = acc;
@@ -178,9 +183,9 @@ extern "C" int mvn_pack_weights(const mvn_shape_t* s, const void* const* param_p
     cudaStream_t st = (cudaStream_t)stream;
     const float* const* ptrs = (const float* const*)param_ptrs_dev;
     dim3 gl(8, g.N);
-    pack_layer_kernel<<<gl, 256, 0, st>>>(ptrs, (float*)packed, P, g.C, g.S, g.Kz, g.video);
+    pack_layer_kernel<<<gl, 256, 0, st>>>(ptrs, (float*)packed, P, g.C, g.Cl, g.S, g.Kz, g.video);
     dim3 gm(32, 6);
-    pack_misc_kernel<<<gm, 256, 0, st>>>(ptrs, (float*)packed, P, g.A, g.C, g.S, g.Cin, g.N, g.video);
+    pack_misc_kernel<<<gm, 256, 0, st>>>(ptrs, (float*)packed, P, g.A, g.C, g.Cl, g.S, g.Cin, g.N, g.video);
     int rc = mvn_check_launch("pack_weights");
     if (rc) return rc;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video))
@@ -200,8 +205,8 @@ extern "C" int mvn_unpack_grads(const mvn_shape_t* s, const void* packed_grads, 
     MVN_REQUIRE(packed_grads && flat_grads && offsets_dev, "mvn_unpack_grads: null buffer");
     const long long* offs = (const long long*)offsets_dev;
     dim3 gl(8, g.N);
-    unpack_layer_kernel<<<gl, 256, 0, st>>>(flat_grads, offs, (const float*)packed_grads, P, g.C, g.S, g.Kz, g.video);
+    unpack_layer_kernel<<<gl, 256, 0, st>>>(flat_grads, offs, (const float*)packed_grads, P, g.C, g.Cl, g.S, g.Kz, g.video);
     dim3 gm(32, 6);
-    unpack_misc_kernel<<<gm, 256, 0, st>>>(flat_grads, offs, (const float*)packed_grads, P, g.A, g.C, g.S, g.Cin, g.N, g.video);
+    unpack_misc_kernel<<<gm, 256, 0, st>>>(flat_grads, offs, (const float*)packed_grads, P, g.A, g.C, g.Cl, g.S, g.Cin, g.N, g.video);
     return mvn_check_launch("unpack_grads");
 }

@@ -31,7 +31,7 @@ def rel_l2(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize("name", ["cfg00", "cfg00_gain", "cfg03", "testarch_small"])
+@pytest.mark.parametrize("name", ["cfg00", "cfg00_gain", "cfg03", "cfg04_short", "testarch_small", "odd"])
 def test_bf16_forward_loss_and_grads_against_golden(name):
     fx = load_golden(name)
     m = build(fx, "bf16")
