@@ -1,5 +1,6 @@
 // WaveNet forward / backward orchestration and the non-GEMM kernels
 // (one-hot detection, input gather, softmax <-> channels-first transposes).
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_f32.cuh"
 #include "layout.h"
@@ -334,6 +335,8 @@ static int layer_fwd(const Ctx& c, int l) {
     float* skip = (float*)(c.acts + c.AL.skip);
     void* ctx = g.video ? c.acts + c.AL.ctx : nullptr;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
+        static const bool v1 = getenv("MOVENET_B200_FWD_V1") != nullptr;   // A/B switch: the first-generation kernel
+        if (!v1 && g.S <= 32) return mvn_tc_layer_fwd2(c.x(l), ctx, last ? nullptr : c.x(l + 1), skip, lw, c.P, g, l, c.st);
         return mvn_tc_layer_fwd(c.x(l), ctx, last ? nullptr : c.x(l + 1), skip, lw, c.P, g, l, c.st);
     }
     void* gated = c.scratch + c.SL.gated;
