@@ -1,8 +1,9 @@
 // Forward residual layer, second generation: one persistent CTA per SM, warp-specialised.
 //
-//   warp 8  (one lane) : TMA producer   -- a 3-stage ring of {x(t-d), x(t), ctx(t)} tiles, up to 3 tiles ahead
-//   warp 9  (one lane) : MMA issuer     -- gate GEMM of tile k, then the residual/skip GEMM of tile k-1
-//   warps 0-3, 4-7     : two epilogue groups, each owning every other tile and its own TMEM window
+//   warp 16 (one lane) : TMA producer   -- a 3-stage ring of {x(t-d), x(t), ctx(t)} tiles, up to 3 tiles ahead
+//   warp 17 (one lane) : MMA issuer     -- gate GEMM of tile k, then the residual/skip GEMM of tile k-1
+//   warps 0-7, 8-15    : two epilogue groups of 8 warps, each owning every other tile and its own TMEM window
+//                        (two warps share a TMEM lane quarter and split the channel range)
 //
 // so the loads, the tensor-core work and the two epilogues of consecutive tiles all overlap (the first generation
 // kept one tile in flight per CTA and relied on two co-resident CTAs to overlap).  Same math, same operand images
@@ -23,9 +24,9 @@ struct Fwd2Args {
     int B, T, Tout, RF, S, N2, dil, nchunks, has_out, skip_init, tiles_per_clip, n_tiles;
 };
 
-__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory"); }
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 layer_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_ctx,
                      const __grid_constant__ CUtensorMap map_out, const Fwd2Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -67,7 +68,7 @@ layer_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const uint32_t tmem = *tmem_slot;
     const int n_mine = a.n_tiles > (int)blockIdx.x ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    if (warp == 8) {
+    if (warp == 16) {
         // ================================ TMA producer ============================================
         if ((tid & 31) == 0) {
             for (int k = 0; k < n_mine; ++k) {
@@ -81,7 +82,7 @@ layer_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 if (nc == 3) tma_load_3d(dst + 2 * TILE_BYTES, &map_ctx, full + st, 0, t0, b);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 17) {
         // ================================ MMA issuer ==============================================
         if ((tid & 31) == 0) {
             const uint32_t idesc1 = umma_idesc(TILE_T, 128), idesc2 = umma_idesc(TILE_T, a.N2);
@@ -114,7 +115,7 @@ layer_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         }
     } else {
         // ================================ epilogue groups =========================================
-        const int g = warp >> 2, r = tid & 127, sw = r & 7;
+        const int g = warp >> 3, r = tid & 127, sw = r & 7, half = (tid >> 7) & 1;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t tm = tmem + g * GROUP_COLS;
         mbar_wait(img_bar, 0);                 // biases live in the image
@@ -127,12 +128,12 @@ layer_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             const bool live = t < a.T && js >= 0 && js < a.Tout;
             float* skip_dst = a.skip + ((size_t)b * a.Tout + (live ? js : 0)) * a.S;
             float4 old0 = make_float4(0.f, 0.f, 0.f, 0.f), old1 = old0;
-            if (live && !a.skip_init) { old0 = ((const float4*)skip_dst)[0]; old1 = ((const float4*)skip_dst)[1]; }
+            if (half == 0 && live && !a.skip_init) { old0 = ((const float4*)skip_dst)[0]; old1 = ((const float4*)skip_dst)[1]; }
 
             mbar_wait(mma1_done + g, j & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 2 * half; q < 2 * half + 2; ++q) {
                 uint32_t f[16], gg[16];
                 tmem_ld16(tm + lane_base + 16 * q, f);
                 tmem_ld16(tm + lane_base + 64 + 16 * q, gg);
@@ -152,13 +153,13 @@ layer_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             fence_proxy_async();
             tc_fence_before();
             group_bar(g);
-            if (r == 0) mbar_arrive(g_ready + g);
+            if (r == 0 && half == 0) mbar_arrive(g_ready + g);
 
             mbar_wait(mma2_done + g, j & 1);
             tc_fence_after();
             if (a.has_out) {
 #pragma unroll 1
-                for (int q = 0; q < 4; ++q) {
+                for (int q = 2 * half; q < 2 * half + 2; ++q) {
                     uint32_t rr[16];
                     tmem_ld16(tm + lane_base + 128 + 16 * q, rr);
                     tmem_ld_wait();
@@ -177,7 +178,7 @@ layer_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     *p1 = make_uint4(o[4], o[5], o[6], o[7]);
                 }
             }
-            for (int s0 = 0; s0 < a.S; s0 += 8) {
+            for (int s0 = 8 * half; s0 < a.S; s0 += 16) {
                 uint32_t sv[8];
                 tmem_ld8(tm + lane_base + 128 + CC + s0, sv);
                 tmem_ld_wait();
@@ -199,7 +200,7 @@ layer_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             fence_proxy_async();
             tc_fence_before();
             group_bar(g);
-            if (r == 0) {
+            if (r == 0 && half == 0) {
                 mbar_arrive(tmem_free + g);            // every thread of the group has drained its TMEM rows
                 if (a.has_out) {
                     tma_store_3d(&map_out, sA1, 0, t0, b);
@@ -209,7 +210,7 @@ layer_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 mbar_arrive(empty + st);
             }
         }
-        if (r == 0) tma_wait_all0();
+        if (r == 0 && half == 0) tma_wait_all0();
     }
     tc_fence_before();
     __syncthreads();
@@ -242,6 +243,6 @@ int mvn_tc_layer_fwd2(const void* x_in, const void* ctx, void* x_out, float* ski
     }
     int grid = 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    layer_fwd_tc2_kernel<<<grid, 320, smem, st>>>(map_x, map_ctx, map_out, a);
+    layer_fwd_tc2_kernel<<<grid, 576, smem, st>>>(map_x, map_ctx, map_out, a);
     return mvn_check_launch("layer_fwd_tc2");
 }

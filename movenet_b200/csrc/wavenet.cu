@@ -335,8 +335,11 @@ static int layer_fwd(const Ctx& c, int l) {
     float* skip = (float*)(c.acts + c.AL.skip);
     void* ctx = g.video ? c.acts + c.AL.ctx : nullptr;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
-        static const bool v1 = getenv("MOVENET_B200_FWD_V1") != nullptr;   // A/B switch: the first-generation kernel
-        if (!v1 && g.S <= 32) return mvn_tc_layer_fwd2(c.x(l), ctx, last ? nullptr : c.x(l + 1), skip, lw, c.P, g, l, c.st);
+        // A/B switch: the warp-specialised persistent variant (layer_tc_fwd2.cu) measures the same 60 us per layer as
+        // the two-CTAs-per-SM kernel below on B200 (both are bound by the epilogue's XU/issue work and the MMA
+        // round-trip latency, profiles/), so the simpler kernel stays the default
+        static const bool v2 = getenv("MOVENET_B200_FWD_V2") != nullptr;
+        if (v2 && g.S <= 32) return mvn_tc_layer_fwd2(c.x(l), ctx, last ? nullptr : c.x(l + 1), skip, lw, c.P, g, l, c.st);
         return mvn_tc_layer_fwd(c.x(l), ctx, last ? nullptr : c.x(l + 1), skip, lw, c.P, g, l, c.st);
     }
     void* gated = c.scratch + c.SL.gated;
