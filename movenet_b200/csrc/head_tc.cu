@@ -1,16 +1,19 @@
 // DenseConv head (movenet/modules.py:133-142) + drop-last + softmax (movenet/wavenet.py:183-191) and its
-// backward on tcgen05 tensor cores, for input_channels == 64.
+// backward on tcgen05 tensor cores, for input_channels A == 64 or 128 (template parameter).
 //
-// One thread owns one time row (TMEM lane = time), so the softmax over the 64 channels needs no
-// shuffles and the channels-first (B, A, T) API tensors are read/written with the warp's 32 lanes on
-// 32 consecutive time steps: coalesced without a transpose.
+// One thread owns one time row (TMEM lane = time) and 32 of the A channels (A/32 groups of 128 threads share
+// the rows), so the softmax needs no shuffles -- only a tiny shared-memory exchange between the groups -- and
+// the channels-first (B, A, T) API tensors are read/written with a warp's 32 lanes on 32 consecutive time
+// steps: coalesced without a transpose.
 //
-// forward : a1 = W1 lrelu(skip) + b1 on CUDA cores (K = S is tiny) -> lrelu -> bf16 tile (K-major,
+// forward : a1 = W1 lrelu(skip) + b1 on CUDA cores (K = S is tiny) -> lrelu -> bf16 tiles (K-major,
 //           128B swizzle) -> tcgen05.mma z = . W2^T -> softmax -> probabilities (or logits).
-// backward: recompute a1; dz = p (dp - <dp, p>) in-thread -> bf16 tile -> tcgen05.mma da1 = dz . W2
+// backward: recompute a1; dz = p (dp - <dp, p>) in-thread -> bf16 tiles -> tcgen05.mma da1 = dz . W2
 //           (B = the SAME W2 image read MN-major) -> lrelu' -> dskip on CUDA cores;
-//           weight / bias gradients: [dz | da1]^T . [lrelu(a1) | lrelu(skip)] with K = time, accumulated
-//           in TMEM over the CTA's tiles, written as per-CTA partials and reduced in a fixed order.
+//           weight / bias gradients with K = time, accumulated in TMEM over the CTA's tiles, written as
+//           per-CTA partials and reduced in a fixed order:
+//             A == 64 : one chain  [dz | da1]^T . [lrelu(a1) | lrelu(skip)]   (M = 128 = 64 + 64)
+//             A == 128: two chains  dz^T . lrelu(a1)   and   da1^T . lrelu(skip)
 #include "tc_common.cuh"
 #include "layer_tc.h"
 
@@ -18,14 +21,17 @@ using namespace tc;
 
 namespace {
 
-constexpr int HA = 64;                       // input_channels handled
-constexpr int HPART = 128 * 128 + 128;       // per-CTA partial: D_w[128][128] + bias sums[128]
+template <int A> struct HP {      // per-CTA partial gradients
+    // A == 64 : D_w[128][128] (rows dz|da1, cols lrelu(a1)|lrelu(skip)) + 128 bias sums
+    // A == 128: D_w2[128][128] (dz x lrelu(a1)) | D_w1[128][64] (da1 x lrelu(skip)) | 256 bias sums (dz | da1)
+    static constexpr int floats = A == 64 ? 128 * 128 + 128 : 128 * 128 + 128 * 64 + 256;
+};
 
 struct HeadArgs {
     const float* w1p;    // [S][A] fp32
     const float* b1;     // [A]
     const float* b2;     // [A]
-    const void* img;     // W2 image: [A n][A k] bf16, K-major, 128B swizzle
+    const void* img;     // W2 image: A/64 chunks of [A n][64 k] bf16, K-major, 128B swizzle
     const float* skip;   // (B, Tout, S)
     float* out;          // forward: (B, A, Tn)
     const float* probs;  // backward
@@ -38,14 +44,14 @@ struct HeadArgs {
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : MVN_LRELU_SLOPE * v; }
 
 // a1[n] for n in [n0, n0+32) of one row, from the row's S skip values (already leaky-ReLU'd)
-template <int S>
+template <int A, int S>
 __device__ __forceinline__ void head_a1(const float* sw1, const float* sb1, const float* ls, int n0, float* a1) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) a1[i] = sb1[n0 + i];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
         const float x = ls[s];
-        const float4* w = (const float4*)(sw1 + s * HA + n0);
+        const float4* w = (const float4*)(sw1 + s * A + n0);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const float4 wv = w[q];
@@ -55,9 +61,10 @@ __device__ __forceinline__ void head_a1(const float* sw1, const float* sb1, cons
     }
 }
 
-// 32 fp32 values of row r, channels [32*half, +32) -> bf16 chunks of a 128B-swizzled [128 x 64] tile
-__device__ __forceinline__ void store_half_row(uint8_t* tile, int r, int half, const float* v) {
-    const int sw = r & 7;
+// 32 fp32 values of row r, channels [32*part, +32) -> bf16 chunks of the 128B-swizzled [128 x 64] tile(s) at `tiles`
+__device__ __forceinline__ void store_part_row(uint8_t* tiles, int r, int part, const float* v) {
+    uint8_t* tile = tiles + (part >> 1) * TILE_BYTES;
+    const int sw = r & 7, half = part & 1;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
         *(uint4*)(tile + r * 128 + (((4 * half + q) ^ sw) << 4)) =
@@ -65,26 +72,27 @@ __device__ __forceinline__ void store_half_row(uint8_t* tile, int r, int half, c
                        pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
 }
 
-template <int S>
-__global__ void __launch_bounds__(256, 2) head_fwd_tc_kernel(const HeadArgs a) {
+template <int A, int S>
+__global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_fwd_tc_kernel(const HeadArgs a) {
+    constexpr int PARTS = A / 32, KC = A / 64, NT = A * 4, W2_BYTES = A * A * 2;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sW2 = smem;                          // 8 KB image
-    uint8_t* sA = smem + 8192;                    // 16 KB: lrelu(a1) tile
-    float* sw1 = (float*)(sA + TILE_BYTES);       // [S][64]
-    float* sb1 = sw1 + S * HA;
-    float* sb2 = sb1 + HA;
-    float* sx = sb2 + HA;                         // [2][128] softmax exchange
-    uint64_t* mma_bar = (uint64_t*)(sx + 256);
+    uint8_t* sW2 = smem;
+    uint8_t* sA = smem + W2_BYTES;                // KC tiles: lrelu(a1)
+    float* sw1 = (float*)(sA + KC * TILE_BYTES);  // [S][A]
+    float* sb1 = sw1 + S * A;
+    float* sb2 = sb1 + A;
+    float* sx = sb2 + A;                          // [PARTS][128] softmax exchange
+    uint64_t* mma_bar = (uint64_t*)(sx + PARTS * 128);
     uint32_t* tmem_slot = (uint32_t*)(mma_bar + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, half = tid >> 7, n0 = 32 * half;
+    const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, part = tid >> 7, n0 = 32 * part;
 
-    for (int i = tid; i < 8192 / 16; i += 256) ((uint4*)sW2)[i] = ((const uint4*)a.img)[i];
-    for (int i = tid; i < S * HA; i += 256) sw1[i] = a.w1p[i];
-    if (tid < HA) { sb1[tid] = a.b1[tid]; sb2[tid] = a.b2[tid]; }
+    for (int i = tid; i < W2_BYTES / 16; i += NT) ((uint4*)sW2)[i] = ((const uint4*)a.img)[i];
+    for (int i = tid; i < S * A; i += NT) sw1[i] = a.w1p[i];
+    if (tid < A) { sb1[tid] = a.b1[tid]; sb2[tid] = a.b2[tid]; }
     if (tid == 0) { mbar_init(mma_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(64) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(A) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     fence_proxy_async();
@@ -93,7 +101,7 @@ __global__ void __launch_bounds__(256, 2) head_fwd_tc_kernel(const HeadArgs a) {
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t idesc = umma_idesc_major(TILE_T, HA, 0, 0);
+    const uint32_t idesc = umma_idesc_major(TILE_T, A, 0, 0);
 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -102,24 +110,28 @@ __global__ void __launch_bounds__(256, 2) head_fwd_tc_kernel(const HeadArgs a) {
         float ls[S];
         {
             const float* src = a.skip + ((size_t)b * a.Tout + (live ? j : 0)) * S;
-            #pragma unroll
+#pragma unroll
             for (int s = 0; s < S; s += 4) {
                 const float4 v = live ? *(const float4*)(src + s) : make_float4(0.f, 0.f, 0.f, 0.f);
                 ls[s] = lrelu(v.x); ls[s + 1] = lrelu(v.y); ls[s + 2] = lrelu(v.z); ls[s + 3] = lrelu(v.w);
             }
         }
         float v[32];
-        head_a1<S>(sw1, sb1, ls, n0, v);
+        head_a1<A, S>(sw1, sb1, ls, n0, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
-        store_half_row(sA, r, half, v);
+        store_part_row(sA, r, part, v);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma(tmem, umma_desc(smem_u32(sA) + k * 32), umma_desc(smem_u32(sW2) + k * 32), idesc, k != 0);
+            for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma(tmem, umma_desc(smem_u32(sA + kc * TILE_BYTES) + k * 32), umma_desc(smem_u32(sW2 + kc * A * 128) + k * 32), idesc,
+                         (kc | k) != 0);
             umma_commit(mma_bar);
         }
         mbar_wait(mma_bar, it & 1);
@@ -134,63 +146,71 @@ __global__ void __launch_bounds__(256, 2) head_fwd_tc_kernel(const HeadArgs a) {
             v[i] = __uint_as_float(z0[i]) + sb2[n0 + i]; v[16 + i] = __uint_as_float(z1[i]) + sb2[n0 + 16 + i];
             m = fmaxf(m, fmaxf(v[i], v[16 + i]));
         }
-        if (!a.logits) {      // softmax over all 64 channels: the two halves of a row live in threads r and r + 128
-            sx[half * 128 + r] = m;
+        if (!a.logits) {      // softmax over all A channels: a row's channel groups live in threads r, r + 128, ...
+            sx[part * 128 + r] = m;
             __syncthreads();
-            m = fmaxf(sx[r], sx[128 + r]);
+#pragma unroll
+            for (int p = 0; p < PARTS; ++p) m = fmaxf(m, sx[p * 128 + r]);
             float sum = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) { v[i] = __expf(v[i] - m); sum += v[i]; }
             __syncthreads();
-            sx[half * 128 + r] = sum;
+            sx[part * 128 + r] = sum;
             __syncthreads();
-            const float inv = 1.f / (sx[r] + sx[128 + r]);
+            float tot = 0.f;
+#pragma unroll
+            for (int p = 0; p < PARTS; ++p) tot += sx[p * 128 + r];
+            const float inv = 1.f / tot;
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= inv;
         }
         if (live) {
-            float* dst = a.out + ((size_t)b * HA + n0) * a.Tn + j;
+            float* dst = a.out + ((size_t)b * A + n0) * a.Tn + j;
 #pragma unroll
             for (int i = 0; i < 32; ++i) dst[(size_t)i * a.Tn] = v[i];
         }
         tc_fence_before();
-        __syncthreads();       // every thread has read its TMEM row and the A tile is free again
+        __syncthreads();       // every thread has read its TMEM row and the A tiles are free again
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(64) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(A) : "memory");
     }
 }
 
-template <int S>
-__global__ void __launch_bounds__(256, 2) head_bwd_tc_kernel(const HeadArgs a) {
+template <int A, int S>
+__global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(const HeadArgs a) {
+    constexpr int PARTS = A / 32, KC = A / 64, NT = A * 4, W2_BYTES = A * A * 2;
+    constexpr int TMEM_COLS = A == 64 ? 256 : 512;
+    // TMEM columns: da_pre [0, A) | weight-gradient accumulators | bias sums
+    constexpr int DA_COL = 0, W_COL = A, W1_COL = 2 * A /* A == 128 only */, B_COL = A == 64 ? 192 : 320;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sW2 = smem;                          // 8 KB
-    uint8_t* sDZ = smem + 8192;                   // [DZ | DA1] adjacent: the M = 128 operand of the weight-gradient MMA
-    uint8_t* sDA = sDZ + TILE_BYTES;
-    uint8_t* sLA = sDA + TILE_BYTES;              // [LA | LS] adjacent: its N = 128 operand
-    uint8_t* sLS = sLA + TILE_BYTES;
+    uint8_t* sW2 = smem;
+    uint8_t* sDZ = smem + W2_BYTES;               // A == 64: [DZ | DA] adjacent form the M = 128 operand
+    uint8_t* sDA = sDZ + KC * TILE_BYTES;
+    uint8_t* sLA = sDA + KC * TILE_BYTES;         // A == 64: [LA | LS] adjacent form the N = 128 operand
+    uint8_t* sLS = sLA + KC * TILE_BYTES;
     uint8_t* sONES = sLS + TILE_BYTES;            // 1 KB
-    float* sw1 = (float*)(sONES + 1024);          // [S][64]
-    float* sb1 = sw1 + S * HA;
-    float* sx = sb1 + HA;                         // [2][128] exchange: <dp,p> halves
-    float* sds = sx + 256;                        // [128][S+1] exchange: dskip partial of half 1
-    uint64_t* mma_bar = (uint64_t*)(sds + 128 * (S + 1));
+    float* sw1 = (float*)(sONES + 1024);          // [S][A]
+    float* sb1 = sw1 + S * A;
+    float* sx = sb1 + A;                          // [PARTS][128] exchange: <dp,p> partial sums
+    float* sds = sx + PARTS * 128;                // [PARTS-1][128][S+1] exchange: dskip partial sums
+    uint64_t* mma_bar = (uint64_t*)(sds + (PARTS - 1) * 128 * (S + 1) + ((PARTS - 1) * 128 * (S + 1) & 1));
     uint64_t* w_bar = mma_bar + 1;
     uint32_t* tmem_slot = (uint32_t*)(mma_bar + 2);
-    const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, half = tid >> 7, n0 = 32 * half, sw = r & 7;
+    const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, part = tid >> 7, n0 = 32 * part, sw = r & 7;
 
-    for (int i = tid; i < 8192 / 16; i += 256) ((uint4*)sW2)[i] = ((const uint4*)a.img)[i];
-    for (int i = tid; i < S * HA; i += 256) sw1[i] = a.w1p[i];
-    if (tid < HA) sb1[tid] = a.b1[tid];
-    for (int i = tid; i < TILE_BYTES / 16; i += 256) ((uint4*)sLS)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 256; i += 256) ((uint32_t*)sONES)[i] = 0x3F803F80u;
+    for (int i = tid; i < W2_BYTES / 16; i += NT) ((uint4*)sW2)[i] = ((const uint4*)a.img)[i];
+    for (int i = tid; i < S * A; i += NT) sw1[i] = a.w1p[i];
+    if (tid < A) sb1[tid] = a.b1[tid];
+    for (int i = tid; i < TILE_BYTES / 16; i += NT) ((uint4*)sLS)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 256; i += NT) ((uint32_t*)sONES)[i] = 0x3F803F80u;
     if (tid == 0) { mbar_init(mma_bar, 1); mbar_init(w_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     fence_proxy_async();
@@ -199,10 +219,10 @@ __global__ void __launch_bounds__(256, 2) head_bwd_tc_kernel(const HeadArgs a) {
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t iG = umma_idesc_major(TILE_T, HA, 0, 1);        // da1 = dz . W2 : B MN-major
-    const uint32_t iW = umma_idesc_major(TILE_T, 128, 1, 1);       // [dz|da1]^T . [la|ls]
+    const uint32_t iG = umma_idesc_major(TILE_T, A, 0, 1);         // da_pre = dz . W2 : B MN-major
+    const uint32_t iW = umma_idesc_major(TILE_T, 128, 1, 1);
+    const uint32_t iW1 = umma_idesc_major(TILE_T, 64, 1, 1);
     const uint32_t iB = umma_idesc_major(TILE_T, 16, 1, 1);
-    constexpr int DA_COL = 0, W_COL = 64, B_COL = 192;
 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -213,7 +233,7 @@ __global__ void __launch_bounds__(256, 2) head_bwd_tc_kernel(const HeadArgs a) {
         unsigned long long skip_pos = 0;
         {
             const float* src = a.skip + ((size_t)b * a.Tout + (live ? j : 0)) * S;
-            #pragma unroll
+#pragma unroll
             for (int s = 0; s < S; s += 4) {
                 const float4 v = live ? *(const float4*)(src + s) : make_float4(0.f, 0.f, 0.f, 0.f);
                 const float x[4] = {v.x, v.y, v.z, v.w};
@@ -223,7 +243,7 @@ __global__ void __launch_bounds__(256, 2) head_bwd_tc_kernel(const HeadArgs a) {
         }
         float dz[32];
         {
-            const size_t o = ((size_t)b * HA + n0) * a.Tn + (live ? j : 0);
+            const size_t o = ((size_t)b * A + n0) * a.Tn + (live ? j : 0);
             float dot = 0.f;
             float p[32];
 #pragma unroll
@@ -233,22 +253,24 @@ __global__ void __launch_bounds__(256, 2) head_bwd_tc_kernel(const HeadArgs a) {
                 dot = fmaf(dz[i], p[i], dot);
             }
             if (!a.logits) {
-                sx[half * 128 + r] = dot;
+                sx[part * 128 + r] = dot;
                 __syncthreads();
-                dot = sx[r] + sx[128 + r];
+                dot = 0.f;
+#pragma unroll
+                for (int q = 0; q < PARTS; ++q) dot += sx[q * 128 + r];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) dz[i] = p[i] * (dz[i] - dot);
             }
         }
         float a1[32];
-        head_a1<S>(sw1, sb1, ls, n0, a1);
+        head_a1<A, S>(sw1, sb1, ls, n0, a1);
         uint32_t a1_pos = 0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) { a1_pos |= (uint32_t)(a1[i] > 0.f) << i; a1[i] = lrelu(a1[i]); }
         if (it) { mbar_wait(w_bar, (it - 1) & 1); tc_fence_after(); }      // previous tile's MMAs are done with the tiles
-        store_half_row(sDZ, r, half, dz);
-        store_half_row(sLA, r, half, a1);
-        if (half == 0) {
+        store_part_row(sDZ, r, part, dz);
+        store_part_row(sLA, r, part, a1);
+        if (part == 0) {
 #pragma unroll
             for (int s = 0; s < S; s += 8)
                 *(uint4*)(sLS + r * 128 + (((s >> 3) ^ sw) << 4)) =
@@ -260,9 +282,11 @@ __global__ void __launch_bounds__(256, 2) head_bwd_tc_kernel(const HeadArgs a) {
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
+            // da_pre[t][k] = sum_n dz[t][n] W2[n][k] : contraction over the image's ROWS, 16 per step
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                umma(tmem + DA_COL, umma_desc(smem_u32(sDZ) + k * 32), umma_desc_mn(smem_u32(sW2) + k * 2048, TILE_BYTES), iG, k != 0);
+            for (int s = 0; s < A / 16; ++s)
+                umma(tmem + DA_COL, umma_desc(smem_u32(sDZ + (s >> 2) * TILE_BYTES) + (s & 3) * 32),
+                     umma_desc_mn(smem_u32(sW2) + s * 2048, A * 128), iG, s != 0);
             umma_commit(mma_bar);
         }
         mbar_wait(mma_bar, it & 1);
@@ -280,10 +304,10 @@ __global__ void __launch_bounds__(256, 2) head_bwd_tc_kernel(const HeadArgs a) {
                 da[16 + i] = __uint_as_float(v1[i]) * ((a1_pos >> (16 + i)) & 1 ? 1.f : MVN_LRELU_SLOPE);
             }
         }
-        store_half_row(sDA, r, half, da);
+        store_part_row(sDA, r, part, da);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            const float4* w = (const float4*)(sw1 + s * HA + n0);
+            const float4* w = (const float4*)(sw1 + s * A + n0);
             float acc = 0.f;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -291,11 +315,11 @@ __global__ void __launch_bounds__(256, 2) head_bwd_tc_kernel(const HeadArgs a) {
                 acc = fmaf(wv.x, da[4 * q], acc); acc = fmaf(wv.y, da[4 * q + 1], acc);
                 acc = fmaf(wv.z, da[4 * q + 2], acc); acc = fmaf(wv.w, da[4 * q + 3], acc);
             }
-            ls[s] = acc;                         // reuse: partial dskip over this half's 32 channels
+            ls[s] = acc;                         // reuse: partial dskip over this thread's 32 channels
         }
-        if (half == 1) {
+        if (part > 0) {
 #pragma unroll
-            for (int s = 0; s < S; ++s) sds[r * (S + 1) + s] = ls[s];
+            for (int s = 0; s < S; ++s) sds[((part - 1) * 128 + r) * (S + 1) + s] = ls[s];
         }
         fence_proxy_async();
         tc_fence_before();
@@ -303,22 +327,36 @@ __global__ void __launch_bounds__(256, 2) head_bwd_tc_kernel(const HeadArgs a) {
         if (tid == 0) {
             tc_fence_after();
             const uint32_t acc0 = it != 0;
+            const uint64_t ones = umma_desc_mn_plain(smem_u32(sONES), 256, 128);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const uint64_t am = umma_desc_mn(smem_u32(sDZ) + k * 2048, TILE_BYTES);
-                umma(tmem + W_COL, am, umma_desc_mn(smem_u32(sLA) + k * 2048, TILE_BYTES), iW, acc0 | (k != 0));
-                umma(tmem + B_COL, am, umma_desc_mn_plain(smem_u32(sONES), 256, 128), iB, acc0 | (k != 0));
+                const uint32_t acc = acc0 | (k != 0);
+                const uint64_t dz_mn = umma_desc_mn(smem_u32(sDZ) + k * 2048, TILE_BYTES);
+                if constexpr (A == 64) {          // [dz|da1]^T . [la|ls]
+                    umma(tmem + W_COL, dz_mn, umma_desc_mn(smem_u32(sLA) + k * 2048, TILE_BYTES), iW, acc);
+                    umma(tmem + B_COL, dz_mn, ones, iB, acc);
+                } else {                          // dz^T . la ; da1^T . ls ; bias sums of both
+                    const uint64_t da_mn = umma_desc_mn(smem_u32(sDA) + k * 2048, TILE_BYTES);
+                    umma(tmem + W_COL, dz_mn, umma_desc_mn(smem_u32(sLA) + k * 2048, TILE_BYTES), iW, acc);
+                    umma(tmem + W1_COL, da_mn, umma_desc_mn(smem_u32(sLS) + k * 2048, TILE_BYTES), iW1, acc);
+                    umma(tmem + B_COL, dz_mn, ones, iB, acc);
+                    umma(tmem + B_COL + 16, da_mn, ones, iB, acc);
+                }
             }
             umma_commit(w_bar);
         }
-        if (half == 0 && live) {
-            float* dst = a.dskip + ((size_t)b * a.Tout + j) * a.S;
-            #pragma unroll
+        if (part == 0 && live) {
+            float* dst = a.dskip + ((size_t)b * a.Tout + j) * S;
+#pragma unroll
             for (int s = 0; s < S; s += 4) {
                 float o[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    o[e] = (ls[s + e] + sds[r * (S + 1) + s + e]) * ((skip_pos >> (s + e)) & 1 ? 1.f : MVN_LRELU_SLOPE);
+                for (int e = 0; e < 4; ++e) {
+                    float acc = ls[s + e];
+#pragma unroll
+                    for (int q = 0; q < PARTS - 1; ++q) acc += sds[(q * 128 + r) * (S + 1) + s + e];
+                    o[e] = acc * ((skip_pos >> (s + e)) & 1 ? 1.f : MVN_LRELU_SLOPE);
+                }
                 *(float4*)(dst + s) = make_float4(o[0], o[1], o[2], o[3]);
             }
         }
@@ -326,42 +364,66 @@ __global__ void __launch_bounds__(256, 2) head_bwd_tc_kernel(const HeadArgs a) {
     }
     if (it) { mbar_wait(w_bar, (it - 1) & 1); }
     tc_fence_after();
-    float* part = a.partial + (size_t)blockIdx.x * HPART;
+    float* part_out = a.partial + (size_t)blockIdx.x * HP<A>::floats;
+    // D_w (A == 64) / D_w2 (A == 128): 128 columns
 #pragma unroll 1
-    for (int jj = half; jj < 8; jj += 2) {
+    for (int jj = part; jj < 8; jj += PARTS) {
         uint32_t v[16];
         tmem_ld16(tmem + lane_base + W_COL + 16 * jj, v);
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            ((float4*)(part + (size_t)r * 128 + 16 * jj))[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                                                          __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            ((float4*)(part_out + (size_t)r * 128 + 16 * jj))[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                              __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+    }
+    if constexpr (A == 128) {
+#pragma unroll 1
+        for (int jj = part; jj < 4; jj += PARTS) {
+            uint32_t v[16];
+            tmem_ld16(tmem + lane_base + W1_COL + 16 * jj, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                ((float4*)(part_out + 128 * 128 + (size_t)r * 64 + 16 * jj))[q] =
+                    make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        }
     }
     {
-        uint32_t v[8];
+        uint32_t v[8], v2[8];
         tmem_ld8(tmem + lane_base + B_COL, v);
+        tmem_ld8(tmem + lane_base + B_COL + 16, v2);      // A == 128 only: da1 sums (harmless extra read otherwise)
         tmem_ld_wait();
-        if (half == 0) part[128 * 128 + r] = __uint_as_float(v[0]);
+        if (part == 0) {
+            if constexpr (A == 64) part_out[128 * 128 + r] = __uint_as_float(v[0]);
+            else { part_out[128 * 128 + 128 * 64 + r] = __uint_as_float(v[0]); part_out[128 * 128 + 128 * 64 + 128 + r] = __uint_as_float(v2[0]); }
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
     }
 }
 
-// D_w[m][n]: m < 64: dz channel, m >= 64: da1 channel ; n < 64: lrelu(a1) channel, n >= 64: lrelu(skip) channel
+template <int A>
 __global__ void head_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ pg, PackedLayout P, int S) {
+    constexpr int HPART = HP<A>::floats;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HPART; i += gridDim.x * blockDim.x) {
         float* dst = nullptr;
-        if (i < 128 * 128) {
-            const int m = i >> 7, n = i & 127;
-            if (m < 64 && n < 64) dst = pg + P.w2p + (size_t)n * HA + m;                 // dw2p[k = n][n_out = m]
-            else if (m >= 64 && n >= 64 && n - 64 < S) dst = pg + P.w1p + (size_t)(n - 64) * HA + (m - 64);   // dw1p[s][a]
+        if constexpr (A == 64) {      // D_w[m][n]: m < 64 dz, m >= 64 da1 ; n < 64 lrelu(a1), n >= 64 lrelu(skip)
+            if (i < 128 * 128) {
+                const int m = i >> 7, n = i & 127;
+                if (m < 64 && n < 64) dst = pg + P.w2p + (size_t)n * A + m;                       // dw2p[k = n][n_out = m]
+                else if (m >= 64 && n >= 64 && n - 64 < S) dst = pg + P.w1p + (size_t)(n - 64) * A + (m - 64);   // dw1p[s][a]
+            } else {
+                const int m = i - 128 * 128;
+                dst = m < 64 ? pg + P.b2 + m : pg + P.b1 + (m - 64);
+            }
         } else {
-            const int m = i - 128 * 128;
-            dst = m < 64 ? pg + P.b2 + m : pg + P.b1 + (m - 64);
+            if (i < 128 * 128) { const int m = i >> 7, n = i & 127; dst = pg + P.w2p + (size_t)n * A + m; }
+            else if (i < 128 * 128 + 128 * 64) { const int q = i - 128 * 128, m = q >> 6, n = q & 63; if (n < S) dst = pg + P.w1p + (size_t)n * A + m; }
+            else { const int m = i - 128 * 128 - 128 * 64; dst = m < 128 ? pg + P.b2 + m : pg + P.b1 + (m - 128); }
         }
         if (!dst) continue;
         float acc = 0.f;
@@ -371,24 +433,45 @@ __global__ void head_reduce_kernel(const float* __restrict__ partial, int n_cta,
     }
 }
 
-// W2 image: [n][k] = dense_conv.conv2.weight[n][k], bf16, 128B swizzle
-__global__ void head_pack_kernel(const float* __restrict__ w2, uint8_t* __restrict__ img) {
+// W2 image: chunk kc = k / 64 holds [n][k % 64] = dense_conv.conv2.weight[n][k], bf16, 128B swizzle, A rows per chunk
+__global__ void head_pack_kernel(const float* __restrict__ w2, uint8_t* __restrict__ img, int A) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= HA * HA) return;
-    const int n = i >> 6, k = i & 63;
-    *(__nv_bfloat16*)(img + n * 128 + ((((k >> 3) ^ (n & 7)) << 4) | ((k & 7) << 1))) = __float2bfloat16(w2[i]);
+    if (i >= A * A) return;
+    const int n = i / A, k = i % A, kc = k >> 6, kk = k & 63;
+    *(__nv_bfloat16*)(img + (size_t)kc * A * 128 + n * 128 + ((((kk >> 3) ^ (n & 7)) << 4) | ((kk & 7) << 1))) = __float2bfloat16(w2[i]);
 }
 
-int fwd_smem(int S) { return 8192 + TILE_BYTES + (S * HA + 2 * HA + 256) * 4 + 64 + 1024; }
-int bwd_smem(int S) { return 8192 + 4 * TILE_BYTES + 1024 + (S * HA + HA + 256 + 128 * (S + 1)) * 4 + 64 + 1024; }
+template <int A> int fwd_smem(int S) { return A * A * 2 + (A / 64) * TILE_BYTES + (S * A + 2 * A + (A / 32) * 128) * 4 + 64 + 1024; }
+template <int A> int bwd_smem(int S) {
+    return A * A * 2 + (3 * (A / 64) + 1) * TILE_BYTES + 1024 + (S * A + A + (A / 32) * 128 + (A / 32 - 1) * 128 * (S + 1) + 2) * 4 + 64 + 1024;
+}
+
+template <int A, int S>
+int launch_fwd(const HeadArgs& a, int grid, cudaStream_t st) {
+    const int smem = fwd_smem<A>(S);
+    MVN_CUDA(cudaFuncSetAttribute(head_fwd_tc_kernel<A, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    head_fwd_tc_kernel<A, S><<<grid, A * 4, smem, st>>>(a);
+    return 0;
+}
+template <int A, int S>
+int launch_bwd(const HeadArgs& a, int grid, cudaStream_t st) {
+    const int smem = bwd_smem<A>(S);
+    MVN_CUDA(cudaFuncSetAttribute(head_bwd_tc_kernel<A, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    head_bwd_tc_kernel<A, S><<<grid, A * 4, smem, st>>>(a);
+    return 0;
+}
 
 }  // namespace
 
-int mvn_tc_head_supported(int A, int S) { return A == HA && (S == 8 || S == 16 || S == 32 || S == 64); }
-size_t mvn_tc_head_partial_bytes() { return (size_t)2 * 148 * HPART * 4; }
+int mvn_tc_head_supported(int A, int S) {
+    if (A == 64) return S == 8 || S == 16 || S == 32 || S == 64;
+    if (A == 128) return S == 8 || S == 16 || S == 32;
+    return 0;
+}
+size_t mvn_tc_head_partial_bytes() { return (size_t)2 * 148 * HP<128>::floats * 4; }
 
-int mvn_tc_head_pack(const float* w2_ref, float* packed, const PackedLayout& P, cudaStream_t st) {
-    head_pack_kernel<<<(HA * HA + 255) / 256, 256, 0, st>>>(w2_ref, (uint8_t*)(packed + P.tc_head));
+int mvn_tc_head_pack(const float* w2_ref, float* packed, const PackedLayout& P, int A, cudaStream_t st) {
+    head_pack_kernel<<<(A * A + 255) / 256, 256, 0, st>>>(w2_ref, (uint8_t*)(packed + P.tc_head), A);
     return mvn_check_launch("head_pack");
 }
 
@@ -398,18 +481,27 @@ static void fill_args(HeadArgs& a, const float* packed, const PackedLayout& P, c
     a.tiles_per_clip = (g.Tn + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
 }
 
+#define HEAD_DISPATCH(FN, ...)                                                                          \
+    do {                                                                                                \
+        int rc_ = -1;                                                                                   \
+        if (g.A == 64) {                                                                                \
+            if (g.S == 8) rc_ = FN<64, 8>(__VA_ARGS__); else if (g.S == 16) rc_ = FN<64, 16>(__VA_ARGS__); \
+            else if (g.S == 32) rc_ = FN<64, 32>(__VA_ARGS__); else if (g.S == 64) rc_ = FN<64, 64>(__VA_ARGS__); \
+        } else if (g.A == 128) {                                                                        \
+            if (g.S == 8) rc_ = FN<128, 8>(__VA_ARGS__); else if (g.S == 16) rc_ = FN<128, 16>(__VA_ARGS__); \
+            else if (g.S == 32) rc_ = FN<128, 32>(__VA_ARGS__);                                         \
+        }                                                                                               \
+        if (rc_ < 0) { mvn_set_error("head: unsupported channel counts"); return -1; }                  \
+        if (rc_) return rc_;                                                                            \
+    } while (0)
+
 int mvn_tc_head_fwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, float* out, cudaStream_t st) {
     HeadArgs a; memset(&a, 0, sizeof(a)); fill_args(a, packed, P, g);
     a.skip = skip; a.out = out;
     if (a.n_tiles <= 0) return 0;
-    const int smem = fwd_smem(g.S);
-    const int grid = a.n_tiles < 4 * 148 ? a.n_tiles : 4 * 148;
-#define HEAD_FWD_CASE(SS)                                                                                                   \
-    case SS:                                                                                                                \
-        MVN_CUDA(cudaFuncSetAttribute(head_fwd_tc_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));         \
-        head_fwd_tc_kernel<SS><<<grid, 256, smem, st>>>(a);                                                                 \
-        break;
-    switch (g.S) { HEAD_FWD_CASE(8) HEAD_FWD_CASE(16) HEAD_FWD_CASE(32) HEAD_FWD_CASE(64) default: mvn_set_error("head: unsupported skip_channels"); return -1; }
+    const int per_sm = g.A == 64 ? 4 : 1;
+    const int grid = a.n_tiles < per_sm * 148 ? a.n_tiles : per_sm * 148;
+    HEAD_DISPATCH(launch_fwd, a, grid, st);
     return mvn_check_launch("head_fwd_tc");
 }
 
@@ -418,16 +510,12 @@ int mvn_tc_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, co
     HeadArgs a; memset(&a, 0, sizeof(a)); fill_args(a, packed, P, g);
     a.skip = skip; a.probs = probs; a.dout = dout; a.dskip = dskip; a.partial = partial;
     if (a.n_tiles <= 0) return 0;
-    const int smem = bwd_smem(g.S);
-    const int grid = a.n_tiles < 2 * 148 ? a.n_tiles : 2 * 148;
-#define HEAD_BWD_CASE(SS)                                                                                                   \
-    case SS:                                                                                                                \
-        MVN_CUDA(cudaFuncSetAttribute(head_bwd_tc_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));         \
-        head_bwd_tc_kernel<SS><<<grid, 256, smem, st>>>(a);                                                                 \
-        break;
-    switch (g.S) { HEAD_BWD_CASE(8) HEAD_BWD_CASE(16) HEAD_BWD_CASE(32) HEAD_BWD_CASE(64) default: mvn_set_error("head: unsupported skip_channels"); return -1; }
+    const int per_sm = g.A == 64 ? 2 : 1;
+    const int grid = a.n_tiles < per_sm * 148 ? a.n_tiles : per_sm * 148;
+    HEAD_DISPATCH(launch_bwd, a, grid, st);
     int rc = mvn_check_launch("head_bwd_tc");
     if (rc) return rc;
-    head_reduce_kernel<<<(HPART + 255) / 256, 256, 0, st>>>(partial, grid, pg, P, g.S);
+    if (g.A == 64) head_reduce_kernel<64><<<(HP<64>::floats + 255) / 256, 256, 0, st>>>(partial, grid, pg, P, g.S);
+    else head_reduce_kernel<128><<<(HP<128>::floats + 255) / 256, 256, 0, st>>>(partial, grid, pg, P, g.S);
     return mvn_check_launch("head_reduce");
 }

@@ -18,10 +18,10 @@ size_t mvn_tc_bwd_partial_bytes();
 int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const void* u_in, void* p_out, void* u_out,
                      const float* dskip, const void* q_in, void* q_out, const float* lw, float* lg, float* partial, const PackedLayout& P,
                      const Geo& g, int layer, cudaStream_t st);
-// DenseConv head + softmax on tensor cores (head_tc.cu), input_channels == 64
+// DenseConv head + softmax on tensor cores (head_tc.cu), input_channels == 64 or 128
 int mvn_tc_head_supported(int A, int S);
 size_t mvn_tc_head_partial_bytes();
-int mvn_tc_head_pack(const float* w2_ref, float* packed, const PackedLayout& P, cudaStream_t st);
+int mvn_tc_head_pack(const float* w2_ref, float* packed, const PackedLayout& P, int A, cudaStream_t st);
 int mvn_tc_head_fwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, float* out, cudaStream_t st);
 int mvn_tc_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, const float* probs,
                     const float* dout, float* dskip, float* pg, float* partial, cudaStream_t st);

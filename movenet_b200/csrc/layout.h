@@ -58,7 +58,7 @@ struct PackedLayout {
     size_t oTc;                 // tensor-core shared-memory image (bf16, swizzled; see layer_tc.cu), C == 64 only
     size_t w1p, b1, w2p, b2;    // head: [S][A], [A], [A][A], [A]
     size_t w1pT, w2pT;          // [A][S], [A][A]
-    size_t tc_head;             // tensor-core image of conv2.weight (bf16 [64][64], 128B swizzle), A == 64 only
+    size_t tc_head;             // tensor-core image of conv2.weight (bf16, A/64 chunks of [A][64], 128B swizzle), A == 64 or 128
     size_t wv, bv;              // video conv: [4096*Cin][C], [C]
     size_t wt[3], bt[3], wtT[3];// transposed convs: [C][10C], [10C] (bias tiled), [10C][C]
     size_t tc_up;               // tensor-core image of the last upsampler level (bf16 [640][64] + bias), video && C == 64
@@ -83,7 +83,7 @@ static inline void packed_layout(const Geo& g, PackedLayout& p) {
     o = l0 + p.layer_stride * g.N;
     p.w1p = take(S * A); p.b1 = take(A); p.w2p = take(A * A); p.b2 = take(A);
     p.w1pT = take(A * S); p.w2pT = take(A * A);
-    p.tc_head = take(A == 64 ? 2048 : 0);
+    p.tc_head = take((A == 64 || A == 128) ? A * A / 2 : 0);
     if (g.video) {
         p.wv = take((size_t)4096 * g.Cin * C); p.bv = take(C);
         for (int i = 0; i < 3; ++i) { p.wt[i] = take(C * 10 * C); p.bt[i] = take(10 * C); p.wtT[i] = take(10 * C * C); }
@@ -162,6 +162,6 @@ static inline void scratch_layout(const Geo& g, ScratchLayout& w) {
         w.du1 = take((size_t)g.B * 1600 * g.C * 4);
         w.denc = take((size_t)g.B * 160 * g.C * 4);
     } else w.dctx = w.du2 = w.du1 = w.denc = 0;
-    w.tc_partial = take(g.adt == MVN_DTYPE_BF16 && (g.C == 64 || g.A == 64) ? (size_t)2 * 148 * (128 * 256 + 256) * 4 : 0);
+    w.tc_partial = take(g.adt == MVN_DTYPE_BF16 && (g.C == 64 || g.A == 64 || g.A == 128) ? (size_t)2 * 148 * (128 * 256 + 256) * 4 : 0);
     w.total = o;
 }
