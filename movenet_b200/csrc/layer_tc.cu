@@ -143,24 +143,25 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         mbar_wait(mma_bar, 0);
         tc_fence_after();
         // ---- epilogue 1: gate, bf16, into A0 as the next MMA's A operand ------------------------
-#pragma unroll 1
-        for (int j = 2 * half; j < 2 * half + 2; ++j) {
-            uint32_t f[16], g[16];
-            tmem_ld16(tmem + lane_base + 16 * j, f);
-            tmem_ld16(tmem + lane_base + 64 + 16 * j, g);
+        // (this thread's 32 channels in ONE TMEM round trip: all loads in flight, then 32 independent chains)
+        {
+            uint32_t f[32], g[32];
+            tmem_ld32(tmem + lane_base + 32 * half, f);
+            tmem_ld32(tmem + lane_base + 64 + 32 * half, g);
             tmem_ld_wait();
-            uint32_t o[8];
 #pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-                const int c = 16 * j + i;
-                const float f0 = __uint_as_float(f[i]) + sbz[c], f1 = __uint_as_float(f[i + 1]) + sbz[c + 1];
-                const float g0 = __uint_as_float(g[i]) + sbz[64 + c], g1 = __uint_as_float(g[i + 1]) + sbz[64 + c + 1];
-                const float y0 = tanh_fast(f0) * fmaf(0.5f, tanh_fast(0.5f * g0), 0.5f);
-                const float y1 = tanh_fast(f1) * fmaf(0.5f, tanh_fast(0.5f * g1), 0.5f);
-                o[i >> 1] = pack_bf16(y0, y1);
+            for (int q = 0; q < 4; ++q) {
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = 8 * q + 2 * e, c = 32 * half + i;
+                    const float f0 = __uint_as_float(f[i]) + sbz[c], f1 = __uint_as_float(f[i + 1]) + sbz[c + 1];
+                    const float g0 = __uint_as_float(g[i]) + sbz[64 + c], g1 = __uint_as_float(g[i + 1]) + sbz[64 + c + 1];
+                    o[e] = pack_bf16(tanh_fast(f0) * fmaf(0.5f, tanh_fast(0.5f * g0), 0.5f),
+                                     tanh_fast(f1) * fmaf(0.5f, tanh_fast(0.5f * g1), 0.5f));
+                }
+                *(uint4*)(sA0 + r * 128 + (((4 * half + q) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
-            *(uint4*)(sA0 + r * 128 + (((2 * j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-            *(uint4*)(sA0 + r * 128 + (((2 * j + 1) ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -176,23 +177,23 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tc_fence_after();
         // ---- epilogue 2: residual in place in the tap-1 tile; skip accumulation ------------------
         if (a.has_out) {
-#pragma unroll 1
-            for (int j = 2 * half; j < 2 * half + 2; ++j) {
-                uint32_t rr[16];
-                tmem_ld16(tmem + lane_base + D2_COL + 16 * j, rr);
-                tmem_ld_wait();
-                uint4* p0 = (uint4*)(sA1 + r * 128 + (((2 * j) ^ sw) << 4));
-                uint4* p1 = (uint4*)(sA1 + r * 128 + (((2 * j + 1) ^ sw) << 4));
-                uint4 x0 = *p0, x1 = *p1;
-                uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w}, o[8];
+            uint32_t rr[32];
+            tmem_ld32(tmem + lane_base + D2_COL + 32 * half, rr);
+            uint4 xin[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = 16 * j + 2 * i;
-                    const float2 xv = unpack_bf16(xi[i]);
-                    o[i] = pack_bf16(__uint_as_float(rr[2 * i]) + sbrs[c] + xv.x, __uint_as_float(rr[2 * i + 1]) + sbrs[c + 1] + xv.y);
+            for (int q = 0; q < 4; ++q) xin[q] = *(const uint4*)(sA1 + r * 128 + (((4 * half + q) ^ sw) << 4));
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t xi[4] = {xin[q].x, xin[q].y, xin[q].z, xin[q].w};
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = 8 * q + 2 * e, c = 32 * half + i;
+                    const float2 xv = unpack_bf16(xi[e]);
+                    o[e] = pack_bf16(__uint_as_float(rr[i]) + sbrs[c] + xv.x, __uint_as_float(rr[i + 1]) + sbrs[c + 1] + xv.y);
                 }
-                *p0 = make_uint4(o[0], o[1], o[2], o[3]);
-                *p1 = make_uint4(o[4], o[5], o[6], o[7]);
+                *(uint4*)(sA1 + r * 128 + (((4 * half + q) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
         }
         for (int s0 = 8 * half; s0 < a.S; s0 += 16) {
