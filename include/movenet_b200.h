@@ -109,6 +109,11 @@ int mvn_unpack_grads(const mvn_shape_t* s, const void* packed_grads, float* flat
 int mvn_wavenet_forward(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,
                         void* acts, float* out, void* scratch, void* stream);
 
+/* Integer-code input: instead of the one-hot float tensor the caller may hand over the class indices
+ * themselves -- (B, T) int64, 1/(4A) of the bytes.  Call this with the buffer that will be passed as `acts`, then
+ * mvn_wavenet_forward / mvn_wavenet_backward with audio == NULL. */
+int mvn_codes_input(const mvn_shape_t* s, const int64_t* codes, void* acts, void* stream);
+
 /* autograd of the above for d(loss)/d(out) = dout; fills packed_grads (same
  * layout as the packed weights), to be followed by mvn_unpack_grads. */
 int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,

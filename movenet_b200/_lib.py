@@ -40,6 +40,7 @@ SIGNATURES = {
     "mvn_one_hot": (_I, [_P, _P, _I, _I, _I, _P]),
     "mvn_pack_weights": (_I, [_SP, _P, _P, _P]),
     "mvn_unpack_grads": (_I, [_SP, _P, _P, _P, _P]),
+    "mvn_codes_input": (_I, [_SP, _P, _P, _P]),
     "mvn_wavenet_forward": (_I, [_SP, _P, _P, _P, _P, _P, _P, _P]),
     "mvn_wavenet_backward": (_I, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mvn_softmax_ce_partials": (_SZ, [_I, _I]),

@@ -286,10 +286,30 @@ extern "C" int mvn_onehot_to_codes(const float* audio, int B, int A, int T, int*
     return mvn_check_launch("onehot_to_codes");
 }
 
+// int64 class indices (B,T) -> the int32 codes / "not one-hot" flags the kernels consume
+__global__ void codes_from_int64_kernel(const long long* __restrict__ src, int A, long long n, int* __restrict__ codes,
+                                        unsigned char* __restrict__ dense) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long v = src[i];
+        codes[i] = (v >= 0 && v < A) ? (int)v : 0;
+        dense[i] = 0;
+    }
+}
+
+extern "C" int mvn_codes_input(const mvn_shape_t* s, const int64_t* codes, void* acts, void* stream) {
+    Ctx c; int rc = ctx_init(c, s, nullptr, acts, nullptr, stream, "mvn_codes_input"); if (rc) return rc;
+    MVN_REQUIRE(codes && acts, "mvn_codes_input: null buffer");
+    const long long n = (long long)c.g.B * c.g.T;
+    codes_from_int64_kernel<<<mvn_cdiv(n, 256) < 2368 ? mvn_cdiv(n, 256) : 2368, 256, 0, c.st>>>(
+        (const long long*)codes, c.g.A, n, (int*)(c.acts + c.AL.codes), (unsigned char*)(c.acts + c.AL.dense));
+    return mvn_check_launch("codes_input");
+}
+
 static int input_fwd(const Ctx& c, const float* audio) {
     const Geo& g = c.g;
     int* codes = (int*)(c.acts + c.AL.codes); unsigned char* dense = (unsigned char*)(c.acts + c.AL.dense);
-    int rc = mvn_onehot_to_codes(audio, g.B, g.A, g.T, codes, dense, c.st);
+    int rc = 0;
+    if (audio) rc = mvn_onehot_to_codes(audio, g.B, g.A, g.T, codes, dense, c.st);   // null: mvn_codes_input filled them
     if (rc) return rc;
     const long long rows = (long long)g.B * g.T, n = rows * ((g.C + 7) / 8);
     input_fwd_kernel<<<mvn_cdiv(n, 256), 256, 0, c.st>>>(audio, codes, dense, c.packed + c.P.win, c.x(0), g.adt, g.A, g.C, g.T, rows);
@@ -409,7 +429,7 @@ extern "C" int mvn_head_fwd(const mvn_shape_t* s, const void* packed, void* acts
 extern "C" int mvn_wavenet_forward(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,
                                    void* acts, float* out, void* scratch, void* stream) {
     Ctx c; int rc = ctx_init(c, s, packed, acts, scratch, stream, "mvn_wavenet_forward"); if (rc) return rc;
-    MVN_REQUIRE(audio && out && packed && acts && scratch, "mvn_wavenet_forward: null buffer");
+    MVN_REQUIRE(out && packed && acts && scratch, "mvn_wavenet_forward: null buffer");
     MVN_REQUIRE(!c.g.video || video, "mvn_wavenet_forward: shape says video but video is null");
     if (c.g.video && (rc = video_fwd(c, video))) return rc;
     if ((rc = input_fwd(c, audio))) return rc;
@@ -618,7 +638,7 @@ extern "C" int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, co
                                     const void* acts, const float* out, const float* dout, void* packed_grads,
                                     void* scratch, void* stream) {
     Ctx c; int rc = ctx_init(c, s, packed, acts, scratch, stream, "mvn_wavenet_backward"); if (rc) return rc;
-    MVN_REQUIRE(audio && dout && packed && acts && scratch && packed_grads, "mvn_wavenet_backward: null buffer");
+    MVN_REQUIRE(dout && packed && acts && scratch && packed_grads, "mvn_wavenet_backward: null buffer");
     MVN_REQUIRE(c.g.logits || out, "mvn_wavenet_backward: the probabilities returned by forward are required");
     const Geo& g = c.g;
     float* pg = (float*)packed_grads;

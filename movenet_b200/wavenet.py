@@ -82,7 +82,10 @@ class _WaveNetFunction(torch.autograd.Function):
         Tn = shape.frames - module.receptive_fields + 1 - (1 if remove_last else 0)
         out = torch.empty(shape.batch, shape.input_channels, max(Tn, 0), dtype=torch.float32, device=audio.device)
         acts = torch.empty(bufs.acts_bytes, dtype=torch.uint8, device=audio.device)
-        _lib.call("mvn_wavenet_forward", C.byref(shape), bufs.packed.data_ptr(), audio.data_ptr(),
+        is_codes = audio.dim() == 2
+        if is_codes:
+            _lib.call("mvn_codes_input", C.byref(shape), audio.data_ptr(), acts.data_ptr(), _stream())
+        _lib.call("mvn_wavenet_forward", C.byref(shape), bufs.packed.data_ptr(), 0 if is_codes else audio.data_ptr(),
                   0 if video is None else video.data_ptr(), acts.data_ptr(), out.data_ptr(),
                   bufs.get_scratch().data_ptr(), _stream())
         ctx.module, ctx.bufs, ctx.acts = module, bufs, acts
@@ -96,7 +99,7 @@ class _WaveNetFunction(torch.autograd.Function):
         audio, video, out = ctx.saved_tensors
         dout = dout.contiguous().float()
         pg = bufs.get_packed_grads()
-        _lib.call("mvn_wavenet_backward", C.byref(bufs.shape), bufs.packed.data_ptr(), audio.data_ptr(),
+        _lib.call("mvn_wavenet_backward", C.byref(bufs.shape), bufs.packed.data_ptr(), 0 if audio.dim() == 2 else audio.data_ptr(),
                   0 if video is None else video.data_ptr(), ctx.acts.data_ptr(), out.data_ptr(), dout.data_ptr(),
                   pg.data_ptr(), bufs.get_scratch().data_ptr(), _stream())
         ctx.acts = None
@@ -192,15 +195,23 @@ class WaveNet(nn.Module):
                 output_unnormalized: bool = True, remove_last: bool = True):
         """movenet/wavenet.py:158-191.  NOTE the reference's flag polarity: the default
         (``output_unnormalized=True``) returns softmax PROBABILITIES over dim 1, raw logits come
-        back only for ``output_unnormalized=False``.  ``global_features`` is unused there too."""
+        back only for ``output_unnormalized=False``.  ``global_features`` is unused there too.
+
+        Non-breaking overload: ``audio`` may also be the (batch, frames) INTEGER tensor of mu-law
+        codes themselves instead of their one-hot expansion -- 1/(4A) of the bytes to move to the device; the
+        training target is then simply ``audio[:, receptive_fields:]``."""
         audio = self._check_audio(audio)
+        frames = audio.shape[-1]
         if video is not None:
             video = self._check_video(video)
-            assert audio.shape[2] == MAX_AUDIO_FRAMES and video.shape[0] == audio.shape[0], (
+            assert frames == MAX_AUDIO_FRAMES and video.shape[0] == audio.shape[0], (
                 "expected video and audio tensors to have equal sizes, found "
                 f"{(video.shape[0], self.residual_channels, MAX_AUDIO_FRAMES)}, "
-                f"{(audio.shape[0], self.residual_channels, audio.shape[2])}")
-        self.compute_output_size(audio)
+                f"{(audio.shape[0], self.residual_channels, frames)}")
+        if frames - self.receptive_fields + 1 < 1:
+            raise ValueError(
+                "input time steps must be larger than the number of receptive fields. "
+                f"Number of input timesteps = {frames}, receptive fields = {self.receptive_fields}")
         with torch.cuda.device(audio.device):
             out = _WaveNetFunction.apply(self, audio, video, bool(remove_last), not output_unnormalized,
                                          *self._param_list())
@@ -255,6 +266,10 @@ class WaveNet(nn.Module):
         return super()._apply(fn, *args, **kwargs)
 
     def _check_audio(self, audio):
+        if isinstance(audio, torch.Tensor) and audio.dim() == 2 and not audio.is_floating_point():
+            if not audio.is_cuda:
+                raise RuntimeError("movenet_b200.WaveNet runs on CUDA tensors only (there is no CPU path)")
+            return audio.detach().to(torch.int64).contiguous()          # integer codes (batch, frames)
         if not isinstance(audio, torch.Tensor) or audio.dim() != 3:
             raise ValueError("audio must be a (batch, channels, frames) tensor")
         if not audio.is_cuda:
@@ -288,7 +303,7 @@ class WaveNet(nn.Module):
         return bufs
 
     def _engine_buffers(self, audio, has_video, remove_last, output_logits):
-        shape = self._shape(audio.shape[0], audio.shape[2], has_video, remove_last, output_logits)
+        shape = self._shape(audio.shape[0], audio.shape[-1], has_video, remove_last, output_logits)
         return self._buffers_for(shape, audio.device)
 
     def _pack(self, bufs, params):

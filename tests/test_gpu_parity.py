@@ -285,3 +285,24 @@ def test_fused_cross_entropy_route_equals_torch():
     assert out.detach().cpu().sum().item() == pytest.approx(plain.detach().cpu().sum().item())
     logits = m(audio, output_unnormalized=False)
     assert type(logits) is torch.Tensor
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_integer_code_input_equals_one_hot_input(dtype):
+    """forward(codes) (non-breaking overload) is the same function as forward(one_hot(codes))"""
+    fx = load_golden("cfg00")
+    m = build(fx, dtype)
+    audio = golden_audio(fx).cuda()
+    codes = fx["codes"].long().cuda()
+    target = codes[:, m.receptive_fields:]
+    out_a = m(audio)
+    F.cross_entropy(out_a, target).backward()
+    grads_a = {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}
+    m.zero_grad(set_to_none=True)
+    out_b = m(codes)
+    F.cross_entropy(out_b, target).backward()
+    assert torch.equal(out_a.detach(), out_b.detach())
+    for k, g in grads_a.items():
+        assert rel_l2(dict(m.named_parameters())[k].grad, g) < 1e-5, k
+    with pytest.raises(ValueError):
+        m(codes[:, :m.receptive_fields - 1])
