@@ -14,7 +14,9 @@ int mvn_tc_pack(const float* const* param_ptrs_dev, float* packed, const PackedL
 // Backward of one layer on tensor cores (layer_tc_bwd.cu).  The residual-stream gradient travels as the pair
 // (P, U): d(x_{l+1})[t] = P[t] + U[t + dilation_{l+1}].  lg = this layer's slot of the packed gradients.
 // q_in / q_out: running sum over layers of the context gradient, bf16 (B,T,C) (video only).
-size_t mvn_tc_bwd_partial_bytes();
+size_t mvn_tc_bwd_partial_bytes();          // per layer; the layers' partial slots are consecutive
+// reduce every layer's per-CTA partials into the packed gradients (one launch, after the backward sweep)
+int mvn_tc_bwd_reduce_all(const float* partial_all, float* pg, const PackedLayout& P, const Geo& g, cudaStream_t st);
 int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const void* u_in, void* p_out, void* u_out,
                      const float* dskip, const void* q_in, void* q_out, const float* lw, float* lg, float* partial, const PackedLayout& P,
                      const Geo& g, int layer, cudaStream_t st);

@@ -368,8 +368,13 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
 // Fixed-order reduction of the per-CTA partials into the packed gradient layout (layout.h):
 //   dWz[k][2c+gate] = sum_cta part[gate*64+c][k] ; dbz likewise ; dWrs[k][n] = sum_cta part[n'][192+k] ; dbrs.
-__global__ void tc_bwd_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ lg, PackedLayout P,
-                                     int S, int Kz, int video, int has_resid) {
+// blockIdx.y = layer: every layer's partials are reduced by ONE launch after the whole backward sweep
+__global__ void tc_bwd_reduce_kernel(const float* __restrict__ partial_all, int n_cta, float* __restrict__ pg, PackedLayout P,
+                                     int S, int Kz, int video, int n_layers) {
+    const int layer = blockIdx.y;
+    const float* partial = partial_all + (size_t)layer * 148 * PART_FLOATS;
+    float* lg = pg + P.layer0 + (size_t)layer * P.layer_stride;
+    const int has_resid = layer + 1 < n_layers;
     // one thread per SOURCE element so the n_cta reads of a warp are coalesced; the destination is scattered
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < PART_FLOATS; i += gridDim.x * blockDim.x) {
         float* dst = nullptr;
@@ -396,7 +401,16 @@ __global__ void tc_bwd_reduce_kernel(const float* __restrict__ partial, int n_ct
 
 }  // namespace
 
-size_t mvn_tc_bwd_partial_bytes() { return (size_t)148 * PART_FLOATS * 4; }
+size_t mvn_tc_bwd_partial_bytes() { return (size_t)148 * PART_FLOATS * 4; }   // per layer
+
+int mvn_tc_bwd_reduce_all(const float* partial_all, float* pg, const PackedLayout& P, const Geo& g, cudaStream_t st) {
+    int grid_ctas = 148;
+    const int n_tiles = ((g.T + TILE_T - 1) / TILE_T) * g.B;
+    if (grid_ctas > n_tiles) grid_ctas = n_tiles;
+    dim3 grid((PART_FLOATS + 255) / 256, g.N);
+    tc_bwd_reduce_kernel<<<grid, 256, 0, st>>>(partial_all, grid_ctas, pg, P, g.S, g.Kz, g.video, g.N);
+    return mvn_check_launch("tc_bwd_reduce");
+}
 
 int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const void* u_in, void* p_out, void* u_out,
                      const float* dskip, const void* q_in, void* q_out, const float* lw, float* lg, float* partial, const PackedLayout& P,
@@ -428,7 +442,6 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     int grid = 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
     layer_bwd_tc_kernel<<<grid, 512, smem, st>>>(mx, mc, mp, mu, mpo, muo, mq, mqo, a);
-    if ((rc = mvn_check_launch("layer_bwd_tc"))) return rc;
-    tc_bwd_reduce_kernel<<<(PART_FLOATS + 255) / 256, 256, 0, st>>>(partial, grid, lg, P, g.S, g.Kz, g.video, layer + 1 < g.N);
-    return mvn_check_launch("tc_bwd_reduce");
+    (void)lg;
+    return mvn_check_launch("layer_bwd_tc");
 }

@@ -139,7 +139,8 @@ struct ScratchLayout {
     size_t dxa, dxb;  // (B,T,C) act dtype, ping-pong
     size_t dctx;      // (B,T,C) fp32
     size_t du2, du1, denc;
-    size_t tc_partial; // per-CTA partial weight gradients of the tensor-core backward kernel
+    size_t tc_partial; // per-CTA partial weight gradients of the head / input / upsampler tensor-core kernels
+    size_t tc_layer_partial; // ... and of the layer backward kernel, one slot per layer (reduced together at the end)
     size_t total;
 };
 
@@ -162,6 +163,8 @@ static inline void scratch_layout(const Geo& g, ScratchLayout& w) {
         w.du1 = take((size_t)g.B * 1600 * g.C * 4);
         w.denc = take((size_t)g.B * 160 * g.C * 4);
     } else w.dctx = w.du2 = w.du1 = w.denc = 0;
+    // slot 0: head / input / upsampler partials (used one after the other); slots 1..N: one per layer
     w.tc_partial = take(g.adt == MVN_DTYPE_BF16 && (g.C == 64 || g.A == 64 || g.A == 128) ? (size_t)2 * 148 * (128 * 256 + 256) * 4 : 0);
+    w.tc_layer_partial = take(g.adt == MVN_DTYPE_BF16 && g.C == 64 ? (size_t)g.N * 148 * (128 * 256 + 256) * 4 : 0);
     w.total = o;
 }

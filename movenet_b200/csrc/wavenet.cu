@@ -629,7 +629,8 @@ extern "C" int mvn_layer_bwd(const mvn_shape_t* s, const void* packed, int layer
         return mvn_tc_layer_bwd(c.x(layer), g.video ? c.acts + c.AL.ctx : nullptr, c.scratch + c.SL.dxa, c.scratch + c.SL.dgated,
                                 c.scratch + c.SL.dxb, c.scratch + c.SL.dz, (const float*)(c.scratch + c.SL.dskip),
                                 c.scratch + c.SL.dctx, c.scratch + c.SL.dctx + nb, c.lw(layer), lg,
-                                (float*)(c.scratch + c.SL.tc_partial), c.P, g, layer, c.st);
+                                (float*)(c.scratch + c.SL.tc_layer_partial + (size_t)layer * mvn_tc_bwd_partial_bytes()), c.P, g, layer,
+                                c.st);
     }
     return layer_bwd(c, layer, layer + 1 < g.N ? c.scratch + c.SL.dxa : nullptr, c.scratch + c.SL.dxb, pg);
 }
@@ -660,9 +661,11 @@ extern "C" int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, co
             float* lg = pg + c.P.layer0 + (size_t)l * c.P.layer_stride;
             if ((rc = mvn_tc_layer_bwd(c.x(l), g.video ? c.acts + c.AL.ctx : nullptr, Pb[cur], Ub[cur], Pb[cur ^ 1], Ub[cur ^ 1],
                                        (const float*)(c.scratch + c.SL.dskip), Qb[cur], Qb[cur ^ 1], c.lw(l), lg,
-                                       (float*)(c.scratch + c.SL.tc_partial), c.P, g, l, c.st))) return rc;
+                                       (float*)(c.scratch + c.SL.tc_layer_partial + (size_t)l * mvn_tc_bwd_partial_bytes()), c.P, g, l,
+                                       c.st))) return rc;
             cur ^= 1;
         }
+        if ((rc = mvn_tc_bwd_reduce_all((const float*)(c.scratch + c.SL.tc_layer_partial), pg, c.P, g, c.st))) return rc;
         if (mvn_tc_input_supported(g.A, g.C)) {
             if ((rc = mvn_tc_input_bwd(audio, (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), Pb[cur],
                                        Ub[cur], pg + c.P.win, (float*)(c.scratch + c.SL.tc_partial), g, c.st))) return rc;
