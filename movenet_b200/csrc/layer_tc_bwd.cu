@@ -39,9 +39,11 @@ struct BwdArgs {
 
 __host__ __device__ inline int bwd_tiles_off(int nc, int N2) { return smem_a_off(nc, N2); }
 // tiles after the image: A0..A(nc-1) | DXS | DSK | U | DZ0 | DZ1 | G | [Q, video only] | ONES(1 KB) | barriers
-__host__ __device__ inline int bwd_smem_total(int nc, int N2) { return bwd_tiles_off(nc, N2) + (nc + 6 + (nc == 3)) * TILE_BYTES + 1024 + 64; }
+__host__ __device__ inline int bwd_smem_total(int nc, int N2) { return bwd_tiles_off(nc, N2) + (nc + 6 + (nc == 3)) * TILE_BYTES + 1024 + 128; }
 
-__global__ void __launch_bounds__(512, 1)
+constexpr int N_WORKERS = 512, N_THREADS = N_WORKERS + 32;   // 16 worker warps + the control warp
+
+__global__ void __launch_bounds__(N_THREADS, 1)
 layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_ctx,
                     const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_u,
                     const __grid_constant__ CUtensorMap map_pout, const __grid_constant__ CUtensorMap map_uout,
@@ -61,232 +63,278 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint8_t* sG = sDZ + 2 * TILE_BYTES;
     uint8_t* sQ = sG + TILE_BYTES;                // running sum of the context gradient (video only)
     uint8_t* sONES = sQ + (nc == 3 ? TILE_BYTES : 0);
-    uint64_t* full_bar = (uint64_t*)(sONES + 1024);
-    uint64_t* mma_bar = full_bar + 1;
-    uint64_t* w_bar = full_bar + 2;
-    uint64_t* a_bar = full_bar + 3;              // the x / ctx tiles of a tile arrive on their own barrier, one tile ahead
-    uint32_t* tmem_slot = (uint32_t*)(full_bar + 4);
+    // barriers, one completion per tile each (parity = tile iteration & 1), except IMG (once).
+    // E_* are the worker -> control-warp signals (512 arrivals), the rest are TMA / tcgen05.commit completions.
+    enum { IMG = 0, A_IN, P_IN, U_IN, Q_IN, G1, G2, G3, W1, WALL, E_DXS, E_DZ, E_OUT, N_BARS };
+    uint64_t* bar = (uint64_t*)(sONES + 1024);
+    uint32_t* tmem_slot = (uint32_t*)(bar + N_BARS);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int r = tid & 127, sw = r & 7;          // row of the tile == TMEM lane; warps w and w+4 share a lane quarter
-    const int half = tid >> 7;                    // ... and split the channel range between them (4 quarters)
+    const int half = (tid >> 7) & 3;              // ... and split the channel range between them (4 quarters of 16)
     const int NZ = nc * CC;                        // columns of D4 / dWz^T
 
     if (tid == 0) {
-        mbar_init(full_bar, 1); mbar_init(mma_bar, 1); mbar_init(w_bar, 1); mbar_init(a_bar, 1);
+        for (int i = 0; i < N_BARS; ++i) mbar_init(bar + i, i >= E_DXS ? N_WORKERS : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t wbytes = (uint32_t)smem_a_off(nc, a.N2);
-        mbar_expect_tx(full_bar, wbytes);
+        mbar_expect_tx(bar + IMG, wbytes);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(smem)), "l"(a.img), "r"(wbytes), "r"(smem_u32(full_bar)) : "memory");
+                     ::"r"(smem_u32(smem)), "l"(a.img), "r"(wbytes), "r"(smem_u32(bar + IMG)) : "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // constant tiles: DSK is zero outside the S live channels, ONES is all bf16 1.0
-    for (int i = tid; i < TILE_BYTES / 16; i += 512) ((uint4*)sDSK)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 1024 / 4; i += 512) ((uint32_t*)sONES)[i] = 0x3F803F80u;
+    for (int i = tid; i < TILE_BYTES / 16; i += N_THREADS) ((uint4*)sDSK)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 1024 / 4; i += N_THREADS) ((uint32_t*)sONES)[i] = 0x3F803F80u;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    mbar_wait(full_bar, 0);
+    mbar_wait(bar + IMG, 0);
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
 
-    const uint32_t iG1 = umma_idesc_major(TILE_T, 128, 0, 0);
-    const uint32_t iG2 = umma_idesc_major(TILE_T, 64, 0, 1);
-    const uint32_t iG3 = umma_idesc_major(TILE_T, NZ, 0, 1);
-    const uint32_t iW1 = umma_idesc_major(TILE_T, NZ, 1, 1);
-    const uint32_t iW2 = umma_idesc_major(TILE_T, 64, 1, 1);
-    const uint32_t iB = umma_idesc_major(TILE_T, 16, 1, 1);
-    const uint32_t load_bytes = (uint32_t)((2 + (nc == 3)) * TILE_BYTES);       // P, U (+ Q)
-    const uint32_t a_bytes = (uint32_t)(nc * TILE_BYTES);                        // x(t-d), x(t) (+ ctx)
-
-    // x / ctx tiles of tile `tl` -> a_bar
-    auto load_a_tiles = [&](int tl) {
-        const int lb = tl / a.tiles_per_clip, l0 = (tl - lb * a.tiles_per_clip) * TILE_T;
-        mbar_expect_tx(a_bar, a_bytes);
-        tma_load_3d(sA, &map_x, a_bar, 0, l0 - a.dil, lb);
-        tma_load_3d(sA + TILE_BYTES, &map_x, a_bar, 0, l0, lb);
-        if (nc == 3) tma_load_3d(sA + 2 * TILE_BYTES, &map_ctx, a_bar, 0, l0, lb);
-    };
-    // this thread's d(skip) row of tile `tl` (first 8 channels), fetched one tile ahead
-    auto load_dskip = [&](int tl, float4& v0, float4& v1) {
-        const int lb = tl / a.tiles_per_clip, lt = (tl - lb * a.tiles_per_clip) * TILE_T + r, js = lt - (a.RF - 1);
-        v0 = make_float4(0.f, 0.f, 0.f, 0.f); v1 = v0;
-        if (tl < a.n_tiles && lt < a.T && js >= 0 && js < a.Tout) {
-            const float4* src = (const float4*)(a.dskip + ((size_t)lb * a.Tout + js) * a.S);
-            v0 = src[0]; v1 = src[1];
+    // One tile at a time per CTA (TMEM and shared memory are full), but its phases overlap:
+    //  * a control thread issues every TMA and MMA, so the 16 worker warps never wait for instruction issue
+    //    and never meet at a CTA-wide barrier: the hand-offs are mbarriers in both directions;
+    //  * G1 runs as soon as x/ctx are in, and the tanh/sigmoid half of epilogue 1 only needs G1, so it runs while P
+    //    is still in flight and while G2 executes;
+    //  * the outputs are staged in the DZ tiles (free once W1 is done), so the stores of tile i drain during
+    //    tile i+1, and U(i+1), x/ctx(i+1), P(i+1) are loaded as soon as their buffers are free
+    //    (after the pre-sum / after W1 / after W2).
+    if (tid == N_WORKERS) {
+        // ================================ control thread ==========================================
+        const uint32_t iG1 = umma_idesc_major(TILE_T, 128, 0, 0);
+        const uint32_t iG2 = umma_idesc_major(TILE_T, 64, 0, 1);
+        const uint32_t iG3 = umma_idesc_major(TILE_T, NZ, 0, 1);
+        const uint32_t iW1 = umma_idesc_major(TILE_T, NZ, 1, 1);
+        const uint32_t iW2 = umma_idesc_major(TILE_T, 64, 1, 1);
+        const uint32_t iB = umma_idesc_major(TILE_T, 16, 1, 1);
+        auto load_a_tiles = [&](int lb, int l0) {       // x / ctx tiles -> A_IN
+            mbar_expect_tx(bar + A_IN, (uint32_t)(nc * TILE_BYTES));
+            tma_load_3d(sA, &map_x, bar + A_IN, 0, l0 - a.dil, lb);
+            tma_load_3d(sA + TILE_BYTES, &map_x, bar + A_IN, 0, l0, lb);
+            if (nc == 3) tma_load_3d(sA + 2 * TILE_BYTES, &map_ctx, bar + A_IN, 0, l0, lb);
+        };
+        auto load_tile = [&](uint8_t* dst, const CUtensorMap* map, int which, int lb, int l0) {
+            mbar_expect_tx(bar + which, (uint32_t)TILE_BYTES);
+            tma_load_3d(dst, map, bar + which, 0, l0, lb);
+        };
+        {
+            const int lb = (int)blockIdx.x / a.tiles_per_clip, l0 = ((int)blockIdx.x - lb * a.tiles_per_clip) * TILE_T;
+            load_a_tiles(lb, l0);
+            load_tile(sDXS, &map_p, P_IN, lb, l0);
+            load_tile(sU, &map_u, U_IN, lb, l0 + a.dil_up);
         }
-    };
-    if (tid == 0 && (int)blockIdx.x < a.n_tiles) load_a_tiles(blockIdx.x);
-    float4 ds0, ds1;
-    load_dskip(blockIdx.x, ds0, ds1);
-
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-        const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T;
-        const int t = t0 + r;
-        if (tid == 0) {
-            tma_wait_read0();                  // the previous tile's P'/U'/Q' stores have finished reading their tiles
-            mbar_expect_tx(full_bar, load_bytes);
-            tma_load_3d(sDXS, &map_p, full_bar, 0, t0, b);
-            tma_load_3d(sU, &map_u, full_bar, 0, t0 + a.dil_up, b);
-            if (nc == 3) tma_load_3d(sQ, &map_q, full_bar, 0, t0, b);
-            const int nt = tile + gridDim.x;       // this CTA's next tile: start pulling it into L2 now
-            if (nt < a.n_tiles) {
-                const int nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
-                tma_prefetch_3d(&map_x, 0, n0 - a.dil, nb);
-                tma_prefetch_3d(&map_x, 0, n0, nb);
-                if (nc == 3) { tma_prefetch_3d(&map_ctx, 0, n0, nb); tma_prefetch_3d(&map_q, 0, n0, nb); }
-                tma_prefetch_3d(&map_p, 0, n0, nb);
-                tma_prefetch_3d(&map_u, 0, n0 + a.dil_up, nb);
-            }
-        }
-        if (half == 0) {   // d(skip) row of this thread -> bf16, logical channels [0, S) of the DSK tile
-            *(uint4*)(sDSK + r * 128 + ((0 ^ sw) << 4)) =
-                make_uint4(pack_bf16(ds0.x, ds0.y), pack_bf16(ds0.z, ds0.w), pack_bf16(ds1.x, ds1.y), pack_bf16(ds1.z, ds1.w));
-            const int js = t - (a.RF - 1);
-            const bool live = t < a.T && js >= 0 && js < a.Tout;
-            const float* src = a.dskip + ((size_t)b * a.Tout + (live ? js : 0)) * a.S;
-            for (int s0 = 8; s0 < a.S; s0 += 8) {
-                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-                if (live) { v0 = ((const float4*)(src + s0))[0]; v1 = ((const float4*)(src + s0))[1]; }
-                *(uint4*)(sDSK + r * 128 + ((((s0 >> 3)) ^ sw) << 4)) =
-                    make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
-            }
-        }
-        // recompute GEMM as soon as the x / ctx tiles are in: it overlaps the arrival of P / U and the pre-sum
-        mbar_wait(a_bar, it & 1);
-        if (tid == 0) {
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t ph = it & 1;
+            const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T;
+            const int nt = tile + gridDim.x;           // this CTA's next tile
+            const bool has_next = nt < a.n_tiles;
+            const int nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
+            // G1: recompute the gate pre-activations (the tile's TMEM columns are free: E_OUT of the previous tile)
+            mbar_wait(bar + A_IN, ph);
             tc_fence_after();
             for (int c = 0; c < nc; ++c)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma(tmem, umma_desc(smem_u32(sA + c * TILE_BYTES) + k * 32), umma_desc(smem_u32(sBz + c * TILE_BYTES) + k * 32),
                          iG1, (c | k) != 0);
-        }
-        mbar_wait(full_bar, (it + 1) & 1);
-        // ---- dxs = P + U(t + d_up), in place -----------------------------------------------------
-#pragma unroll
-        for (int q = 2 * half; q < 2 * half + 2; ++q) {
-            uint4* pp = (uint4*)(sDXS + r * 128 + ((q ^ sw) << 4));
-            const uint4 pv = *pp, uv = *(const uint4*)(sU + r * 128 + ((q ^ sw) << 4));
-            const uint32_t pa[4] = {pv.x, pv.y, pv.z, pv.w}, ua[4] = {uv.x, uv.y, uv.z, uv.w};
-            uint32_t o[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 x = unpack_bf16(pa[i]), y = unpack_bf16(ua[i]);
-                o[i] = pack_bf16(x.x + y.x, x.y + y.y);
+            umma_commit(bar + G1);
+            if (has_next) {                        // start pulling the next tile into L2 now
+                tma_prefetch_3d(&map_x, 0, n0 - a.dil, nb);
+                tma_prefetch_3d(&map_x, 0, n0, nb);
+                if (nc == 3) { tma_prefetch_3d(&map_ctx, 0, n0, nb); tma_prefetch_3d(&map_q, 0, n0, nb); }
+                tma_prefetch_3d(&map_p, 0, n0, nb);
+                tma_prefetch_3d(&map_u, 0, n0 + a.dil_up, nb);
             }
-            *pp = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+            tma_wait_read0();     // the previous tile's P'/U'/Q' stores have left DZ0 / DZ1 / Q  (ordered before G2's commit:
+                                  // the workers write DZ again only after they have seen G2)
+            if (nc == 3) load_tile(sQ, &map_q, Q_IN, b, t0);                         // needed by epilogue 2 only
+            // G2: d(gated) = dxs . Wr + dskip . Ws : contraction over the image's ROWS (c_out | s) -> B is MN-major
+            mbar_wait(bar + E_DXS, ph);
             tc_fence_after();
-            // d(gated) = dxs . Wr + dskip . Ws : contraction over the image's ROWS (c_out | s) -> B is MN-major
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 umma(tmem + 128, umma_desc(smem_u32(sDXS) + k * 32), umma_desc_mn(smem_u32(sBrs) + k * 2048, TILE_BYTES), iG2, k != 0);
             for (int k = 0; k < (a.S + 15) / 16; ++k)      // the skip channels: rows 64.. of the image, 16 per step
                 umma(tmem + 128, umma_desc(smem_u32(sDSK) + k * 32), umma_desc_mn(smem_u32(sBrs) + (4 + k) * 2048, TILE_BYTES), iG2, 1);
-            umma_commit(mma_bar);
-        }
-        mbar_wait(mma_bar, 0);
-        tc_fence_after();
-        // ---- epilogue 1: gate derivative -------------------------------------------------------
-#pragma unroll 1
-        for (int j = half; j < half + 1; ++j) {
-            uint32_t f[16], g[16], dg[16];
-            tmem_ld16(tmem + lane_base + 16 * j, f);
-            tmem_ld16(tmem + lane_base + 64 + 16 * j, g);
-            tmem_ld16(tmem + lane_base + 128 + 16 * j, dg);
-            tmem_ld_wait();
-            uint32_t of[8], og[8], oy[8];
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-                float zf[2], zg[2], y[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int c = 16 * j + i + e;
-                    const float th = tanh_fast(__uint_as_float(f[i + e]) + sbz[c]);
-                    const float sg = fmaf(0.5f, tanh_fast(0.5f * (__uint_as_float(g[i + e]) + sbz[64 + c])), 0.5f);
-                    const float d = __uint_as_float(dg[i + e]);
-                    y[e] = th * sg;
-                    zf[e] = d * sg * (1.f - th * th);
-                    zg[e] = d * y[e] * (1.f - sg);
-                }
-                of[i >> 1] = pack_bf16(zf[0], zf[1]); og[i >> 1] = pack_bf16(zg[0], zg[1]); oy[i >> 1] = pack_bf16(y[0], y[1]);
-            }
-            const int o0 = r * 128 + (((2 * j) ^ sw) << 4), o1 = r * 128 + (((2 * j + 1) ^ sw) << 4);
-            *(uint4*)(sDZ + o0) = make_uint4(of[0], of[1], of[2], of[3]);
-            *(uint4*)(sDZ + o1) = make_uint4(of[4], of[5], of[6], of[7]);
-            *(uint4*)(sDZ + TILE_BYTES + o0) = make_uint4(og[0], og[1], og[2], og[3]);
-            *(uint4*)(sDZ + TILE_BYTES + o1) = make_uint4(og[4], og[5], og[6], og[7]);
-            *(uint4*)(sG + o0) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
-            *(uint4*)(sG + o1) = make_uint4(oy[4], oy[5], oy[6], oy[7]);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
+            umma_commit(bar + G2);
+            if (has_next) load_tile(sU, &map_u, U_IN, nb, n0 + a.dil_up);            // the U tile is free from here on
             // G3: D4[t][kin] = sum_m dz[t][m] Wz[m][kin]  (A = dz tiles K-major, B = the image read MN-major)
+            mbar_wait(bar + E_DZ, ph);
+            tc_fence_after();
             for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma(tmem, umma_desc(smem_u32(sDZ + c * TILE_BYTES) + k * 32),
                          umma_desc_mn(smem_u32(sBz) + (c * 64 + k * 16) * 128, TILE_BYTES), iG3, (c | k) != 0);
-            umma_commit(mma_bar);
+            umma_commit(bar + G3);
             // weight / bias gradients: K = time.  Every tile is [time x 64 ch], i.e. an MN-major operand.
+            // First the ones that read the x/ctx and DZ tiles (W1): those buffers are needed first.
             const uint32_t acc0 = it != 0;
+            const uint64_t ones = umma_desc_mn_plain(smem_u32(sONES), 256, 128);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const uint32_t acc = acc0 | (k != 0);
                 const uint64_t dz_mn = umma_desc_mn(smem_u32(sDZ) + k * 2048, TILE_BYTES);
-                const uint64_t dx_mn = umma_desc_mn(smem_u32(sDXS) + k * 2048, TILE_BYTES);
-                const uint64_t ones = umma_desc_mn_plain(smem_u32(sONES), 256, 128);
-                umma(tmem + W1_COL, dz_mn, umma_desc_mn(smem_u32(sA) + k * 2048, TILE_BYTES), iW1, acc);
-                umma(tmem + W2_COL, dx_mn, umma_desc_mn(smem_u32(sG) + k * 2048, TILE_BYTES), iW2, acc);
-                umma(tmem + B1_COL, dz_mn, ones, iB, acc);
-                umma(tmem + B2_COL, dx_mn, ones, iB, acc);
+                umma(tmem + W1_COL, dz_mn, umma_desc_mn(smem_u32(sA) + k * 2048, TILE_BYTES), iW1, acc0 | (k != 0));
+                umma(tmem + B1_COL, dz_mn, ones, iB, acc0 | (k != 0));
             }
-            umma_commit(w_bar);
-        }
-        mbar_wait(mma_bar, 1);
-        tc_fence_after();
-        // ---- epilogue 2a: P' = dxs + W1^T dz -> the U tile (free since the pre-sum); Q' = Q + V^T dz in place
-#pragma unroll 1
-        for (int j = half; j < half + 1; ++j) {
-            uint32_t v[16];
-            tmem_ld16(tmem + lane_base + 64 + 16 * j, v);
-            tmem_ld_wait();
-            const uint4 x0 = *(const uint4*)(sDXS + r * 128 + (((2 * j) ^ sw) << 4));
-            const uint4 x1 = *(const uint4*)(sDXS + r * 128 + (((2 * j + 1) ^ sw) << 4));
-            const uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-            uint32_t o[8];
+            umma_commit(bar + W1);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float2 xv = unpack_bf16(xi[i]);
-                o[i] = pack_bf16(__uint_as_float(v[2 * i]) + xv.x, __uint_as_float(v[2 * i + 1]) + xv.y);
+            for (int k = 0; k < 8; ++k) {
+                const uint64_t dx_mn = umma_desc_mn(smem_u32(sDXS) + k * 2048, TILE_BYTES);
+                umma(tmem + W2_COL, dx_mn, umma_desc_mn(smem_u32(sG) + k * 2048, TILE_BYTES), iW2, acc0 | (k != 0));
+                umma(tmem + B2_COL, dx_mn, ones, iB, acc0 | (k != 0));
             }
-            *(uint4*)(sU + r * 128 + (((2 * j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-            *(uint4*)(sU + r * 128 + (((2 * j + 1) ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+            umma_commit(bar + WALL);
+            if (has_next) {
+                mbar_wait(bar + W1, ph);           // W1 no longer reads the x/ctx tiles
+                load_a_tiles(nb, n0);
+            }
+            mbar_wait(bar + E_OUT, ph);            // P', U', Q' are staged; nobody reads DXS or the tile's TMEM columns any more
+            tma_store_3d(&map_pout, sDZ, 0, t0, b);
+            tma_store_3d(&map_uout, sDZ + TILE_BYTES, 0, t0, b);
+            if (nc == 3) tma_store_3d(&map_qout, sQ, 0, t0, b);
+            tma_commit();
+            if (has_next) {
+                mbar_wait(bar + WALL, ph);         // W2 no longer reads DXS
+                load_tile(sDXS, &map_p, P_IN, nb, n0);
+            }
         }
-        if (nc == 3) {
-#pragma unroll 1
-            for (int j = half; j < half + 1; ++j) {
-                uint32_t v[16];
-                tmem_ld16(tmem + lane_base + 128 + 16 * j, v);
+        tma_wait_all0();
+    } else if (tid < N_WORKERS) {
+        // ================================ worker warps ============================================
+        // this thread's d(skip) row of tile `tl` (first 8 channels), fetched one tile ahead
+        auto load_dskip = [&](int tl, float4& v0, float4& v1) {
+            const int lb = tl / a.tiles_per_clip, lt = (tl - lb * a.tiles_per_clip) * TILE_T + r, js = lt - (a.RF - 1);
+            v0 = make_float4(0.f, 0.f, 0.f, 0.f); v1 = v0;
+            if (tl < a.n_tiles && lt < a.T && js >= 0 && js < a.Tout) {
+                const float4* src = (const float4*)(a.dskip + ((size_t)lb * a.Tout + js) * a.S);
+                v0 = src[0]; v1 = src[1];
+            }
+        };
+        float4 ds0, ds1;
+        load_dskip(blockIdx.x, ds0, ds1);
+        const int o0 = r * 128 + (((2 * half) ^ sw) << 4), o1 = r * 128 + (((2 * half + 1) ^ sw) << 4);   // this thread's 16 channels
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+            const uint32_t ph = it & 1;
+            const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T;
+            const int t = t0 + r;
+            if (it) mbar_wait(bar + WALL, ph ^ 1);      // the previous tile's weight-gradient MMAs are done with DSK and G
+            if (half == 0) {   // d(skip) row of this thread -> bf16, logical channels [0, S) of the DSK tile
+                *(uint4*)(sDSK + r * 128 + ((0 ^ sw) << 4)) =
+                    make_uint4(pack_bf16(ds0.x, ds0.y), pack_bf16(ds0.z, ds0.w), pack_bf16(ds1.x, ds1.y), pack_bf16(ds1.z, ds1.w));
+                const int js = t - (a.RF - 1);
+                const bool live = t < a.T && js >= 0 && js < a.Tout;
+                const float* src = a.dskip + ((size_t)b * a.Tout + (live ? js : 0)) * a.S;
+                for (int s0 = 8; s0 < a.S; s0 += 8) {
+                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                    if (live) { v0 = ((const float4*)(src + s0))[0]; v1 = ((const float4*)(src + s0))[1]; }
+                    *(uint4*)(sDSK + r * 128 + ((((s0 >> 3)) ^ sw) << 4)) =
+                        make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+                }
+            }
+            // ---- epilogue 1a (needs G1 only): th, sg, gated -> G tile ---------------------------------
+            float th[16], sg[16];
+            mbar_wait(bar + G1, ph);
+            tc_fence_after();
+            {
+                uint32_t f[16], g[16];
+                tmem_ld16(tmem + lane_base + 16 * half, f);
+                tmem_ld16(tmem + lane_base + 64 + 16 * half, g);
                 tmem_ld_wait();
-                uint4* p0 = (uint4*)(sQ + r * 128 + (((2 * j) ^ sw) << 4));
-                uint4* p1 = (uint4*)(sQ + r * 128 + (((2 * j + 1) ^ sw) << 4));
+                uint32_t oy[8];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int c = 16 * half + i + e;
+                        th[i + e] = tanh_fast(__uint_as_float(f[i + e]) + sbz[c]);
+                        sg[i + e] = fmaf(0.5f, tanh_fast(0.5f * (__uint_as_float(g[i + e]) + sbz[64 + c])), 0.5f);
+                    }
+                    oy[i >> 1] = pack_bf16(th[i] * sg[i], th[i + 1] * sg[i + 1]);
+                }
+                *(uint4*)(sG + o0) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
+                *(uint4*)(sG + o1) = make_uint4(oy[4], oy[5], oy[6], oy[7]);
+            }
+            // ---- dxs = P + U(t + d_up), in place -----------------------------------------------------
+            mbar_wait(bar + P_IN, ph);
+            mbar_wait(bar + U_IN, ph);
+#pragma unroll
+            for (int q = 2 * half; q < 2 * half + 2; ++q) {
+                uint4* pp = (uint4*)(sDXS + r * 128 + ((q ^ sw) << 4));
+                const uint4 pv = *pp, uv = *(const uint4*)(sU + r * 128 + ((q ^ sw) << 4));
+                const uint32_t pa[4] = {pv.x, pv.y, pv.z, pv.w}, ua[4] = {uv.x, uv.y, uv.z, uv.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 x = unpack_bf16(pa[i]), y = unpack_bf16(ua[i]);
+                    o[i] = pack_bf16(x.x + y.x, x.y + y.y);
+                }
+                *pp = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+            fence_proxy_async();
+            mbar_arrive(bar + E_DXS);
+            // ---- epilogue 1b: gate derivative -> DZ0 | DZ1 ------------------------------------------
+            mbar_wait(bar + G2, ph);
+            tc_fence_after();
+            {
+                uint32_t dg[16];
+                tmem_ld16(tmem + lane_base + 128 + 16 * half, dg);
+                tmem_ld_wait();
+                uint32_t of[8], og[8];
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    float zf[2], zg[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float d = __uint_as_float(dg[i + e]), h = th[i + e], s = sg[i + e];
+                        zf[e] = d * s * (1.f - h * h);
+                        zg[e] = d * (h * s) * (1.f - s);
+                    }
+                    of[i >> 1] = pack_bf16(zf[0], zf[1]); og[i >> 1] = pack_bf16(zg[0], zg[1]);
+                }
+                *(uint4*)(sDZ + o0) = make_uint4(of[0], of[1], of[2], of[3]);
+                *(uint4*)(sDZ + o1) = make_uint4(of[4], of[5], of[6], of[7]);
+                *(uint4*)(sDZ + TILE_BYTES + o0) = make_uint4(og[0], og[1], og[2], og[3]);
+                *(uint4*)(sDZ + TILE_BYTES + o1) = make_uint4(og[4], og[5], og[6], og[7]);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar + E_DZ);
+            // ---- epilogue 2: P' = dxs + W1^T dz, U' = W0^T dz (registers until the DZ tiles are free); Q' = Q + V^T dz in place
+            mbar_wait(bar + G3, ph);
+            tc_fence_after();
+            uint32_t po[8], uo[8];
+            {
+                uint32_t v[16], w[16];
+                tmem_ld16(tmem + lane_base + 64 + 16 * half, v);
+                tmem_ld16(tmem + lane_base + 16 * half, w);
+                const uint4 x0 = *(const uint4*)(sDXS + o0), x1 = *(const uint4*)(sDXS + o1);
+                const uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 xv = unpack_bf16(xi[i]);
+                    po[i] = pack_bf16(__uint_as_float(v[2 * i]) + xv.x, __uint_as_float(v[2 * i + 1]) + xv.y);
+                    uo[i] = pack_bf16(__uint_as_float(w[2 * i]), __uint_as_float(w[2 * i + 1]));
+                }
+            }
+            if (nc == 3) {
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_base + 128 + 16 * half, v);
+                mbar_wait(bar + Q_IN, ph);
+                uint4* p0 = (uint4*)(sQ + o0);
+                uint4* p1 = (uint4*)(sQ + o1);
                 const uint4 x0 = *p0, x1 = *p1;
                 const uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                tmem_ld_wait();
                 uint32_t o[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -296,34 +344,20 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 *p0 = make_uint4(o[0], o[1], o[2], o[3]);
                 *p1 = make_uint4(o[4], o[5], o[6], o[7]);
             }
+            mbar_wait(bar + W1, ph);            // W1 no longer reads the DZ tiles
+            *(uint4*)(sDZ + o0) = make_uint4(po[0], po[1], po[2], po[3]);
+            *(uint4*)(sDZ + o1) = make_uint4(po[4], po[5], po[6], po[7]);
+            *(uint4*)(sDZ + TILE_BYTES + o0) = make_uint4(uo[0], uo[1], uo[2], uo[3]);
+            *(uint4*)(sDZ + TILE_BYTES + o1) = make_uint4(uo[4], uo[5], uo[6], uo[7]);
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar + E_OUT);
+            load_dskip(tile + gridDim.x, ds0, ds1);
         }
-        // ---- epilogue 2b: once the weight-gradient MMAs no longer read DXS: U' = W0^T dz -> DXS tile
-        mbar_wait(w_bar, it & 1);
-        tc_fence_after();
-        if (tid == 0 && tile + (int)gridDim.x < a.n_tiles) load_a_tiles(tile + gridDim.x);   // x / ctx tiles are free: next tile
-        load_dskip(tile + gridDim.x, ds0, ds1);
-#pragma unroll 1
-        for (int j = half; j < half + 1; ++j) {
-            uint32_t v[16];
-            tmem_ld16(tmem + lane_base + 16 * j, v);
-            tmem_ld_wait();
-            uint32_t o[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = pack_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-            *(uint4*)(sDXS + r * 128 + (((2 * j) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-            *(uint4*)(sDXS + r * 128 + (((2 * j + 1) ^ sw) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tma_store_3d(&map_pout, sU, 0, t0, b);
-            tma_store_3d(&map_uout, sDXS, 0, t0, b);
-            if (nc == 3) tma_store_3d(&map_qout, sQ, 0, t0, b);
-            tma_commit();
-        }
+        if (it) mbar_wait(bar + WALL, (it - 1) & 1);
     }
     // ---- flush this CTA's partial weight / bias gradients ----------------------------------------
+    if (tid < N_WORKERS) {
     tc_fence_after();
     float* part = a.partial + (size_t)blockIdx.x * PART_FLOATS;
     float* prow = part + (size_t)r * PART_LD;
@@ -357,7 +391,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             part[128 * PART_LD + 128 + r] = __uint_as_float(v2[0]);
         }
     }
-    if (tid == 0) tma_wait_all0();
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -441,7 +475,7 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     }
     int grid = 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    layer_bwd_tc_kernel<<<grid, 512, smem, st>>>(mx, mc, mp, mu, mpo, muo, mq, mqo, a);
+    layer_bwd_tc_kernel<<<grid, N_THREADS, smem, st>>>(mx, mc, mp, mu, mpo, muo, mq, mqo, a);
     (void)lg;
     return mvn_check_launch("layer_bwd_tc");
 }
