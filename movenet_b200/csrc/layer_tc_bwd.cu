@@ -105,8 +105,19 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     //  * the outputs are staged in the DZ tiles (free once W1 is done), so the stores of tile i drain during
     //    tile i+1, and U(i+1), x/ctx(i+1), P(i+1) are loaded as soon as their buffers are free
     //    (after the pre-sum / after W1 / after W2).
-    if (tid == N_WORKERS) {
-        // ================================ control thread ==========================================
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // warp-uniform copy: keeps the role branch convergent
+    if (warp_u == N_WORKERS / 32) {
+        // ================================ control warp ============================================
+        // The whole warp runs the loop (so the code stays on the uniform datapath); one elected lane issues.
+        const bool leader = elect_one();
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+        // base descriptors of every operand; one MMA's descriptors are these plus a compile-time offset
+        const uint64_t kA = umma_desc(smem_u32(sA)), kBz = umma_desc(smem_u32(sBz)), kDXS = umma_desc(smem_u32(sDXS)),
+                       kDSK = umma_desc(smem_u32(sDSK)), kDZ = umma_desc(smem_u32(sDZ));
+        const uint64_t mBrs = umma_desc_mn(smem_u32(sBrs), TILE_BYTES), mBz = umma_desc_mn(smem_u32(sBz), TILE_BYTES),
+                       mDZ = umma_desc_mn(smem_u32(sDZ), TILE_BYTES), mA = umma_desc_mn(smem_u32(sA), TILE_BYTES),
+                       mDXS = umma_desc_mn(smem_u32(sDXS), TILE_BYTES), mG = umma_desc_mn(smem_u32(sG), TILE_BYTES);
+        const uint64_t ones = umma_desc_mn_plain(smem_u32(sONES), 256, 128);
         const uint32_t iG1 = umma_idesc_major(TILE_T, 128, 0, 0);
         const uint32_t iG2 = umma_idesc_major(TILE_T, 64, 0, 1);
         const uint32_t iG3 = umma_idesc_major(TILE_T, NZ, 0, 1);
@@ -123,7 +134,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             mbar_expect_tx(bar + which, (uint32_t)TILE_BYTES);
             tma_load_3d(dst, map, bar + which, 0, l0, lb);
         };
-        {
+        if (leader) {
             const int lb = (int)blockIdx.x / a.tiles_per_clip, l0 = ((int)blockIdx.x - lb * a.tiles_per_clip) * TILE_T;
             load_a_tiles(lb, l0);
             load_tile(sDXS, &map_p, P_IN, lb, l0);
@@ -139,74 +150,84 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             // G1: recompute the gate pre-activations (the tile's TMEM columns are free: E_OUT of the previous tile)
             mbar_wait(bar + A_IN, ph);
             tc_fence_after();
-            for (int c = 0; c < nc; ++c)
+            if (leader) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma(tmem, umma_desc(smem_u32(sA + c * TILE_BYTES) + k * 32), umma_desc(smem_u32(sBz + c * TILE_BYTES) + k * 32),
-                         iG1, (c | k) != 0);
-            umma_commit(bar + G1);
-            if (has_next) {                        // start pulling the next tile into L2 now
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (c < nc)
+                            umma(tmem_u, desc_adv(kA, c * TILE_BYTES + k * 32), desc_adv(kBz, c * TILE_BYTES + k * 32), iG1, (c | k) != 0);
+                umma_commit(bar + G1);
+            }
+            if (leader && has_next) {              // start pulling the next tile into L2 now
                 tma_prefetch_3d(&map_x, 0, n0 - a.dil, nb);
                 tma_prefetch_3d(&map_x, 0, n0, nb);
                 if (nc == 3) { tma_prefetch_3d(&map_ctx, 0, n0, nb); tma_prefetch_3d(&map_q, 0, n0, nb); }
                 tma_prefetch_3d(&map_p, 0, n0, nb);
                 tma_prefetch_3d(&map_u, 0, n0 + a.dil_up, nb);
             }
-            tma_wait_read0();     // the previous tile's P'/U'/Q' stores have left DZ0 / DZ1 / Q  (ordered before G2's commit:
-                                  // the workers write DZ again only after they have seen G2)
-            if (nc == 3) load_tile(sQ, &map_q, Q_IN, b, t0);                         // needed by epilogue 2 only
+            if (leader) {
+                tma_wait_read0();     // the previous tile's P'/U'/Q' stores have left DZ0 / DZ1 / Q  (ordered before G2's
+                                      // commit: the workers write DZ again only after they have seen G2)
+                if (nc == 3) load_tile(sQ, &map_q, Q_IN, b, t0);                     // needed by epilogue 2 only
+            }
             // G2: d(gated) = dxs . Wr + dskip . Ws : contraction over the image's ROWS (c_out | s) -> B is MN-major
             mbar_wait(bar + E_DXS, ph);
             tc_fence_after();
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                umma(tmem + 128, umma_desc(smem_u32(sDXS) + k * 32), umma_desc_mn(smem_u32(sBrs) + k * 2048, TILE_BYTES), iG2, k != 0);
-            for (int k = 0; k < (a.S + 15) / 16; ++k)      // the skip channels: rows 64.. of the image, 16 per step
-                umma(tmem + 128, umma_desc(smem_u32(sDSK) + k * 32), umma_desc_mn(smem_u32(sBrs) + (4 + k) * 2048, TILE_BYTES), iG2, 1);
-            umma_commit(bar + G2);
-            if (has_next) load_tile(sU, &map_u, U_IN, nb, n0 + a.dil_up);            // the U tile is free from here on
+                for (int k = 0; k < 4; ++k)
+                    umma(tmem_u + 128, desc_adv(kDXS, k * 32), desc_adv(mBrs, k * 2048), iG2, k != 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)                // the skip channels: rows 64.. of the image, 16 per step
+                    if (k < (a.S + 15) / 16) umma(tmem_u + 128, desc_adv(kDSK, k * 32), desc_adv(mBrs, (4 + k) * 2048), iG2, 1);
+                umma_commit(bar + G2);
+                if (has_next) load_tile(sU, &map_u, U_IN, nb, n0 + a.dil_up);        // the U tile is free from here on
+            }
             // G3: D4[t][kin] = sum_m dz[t][m] Wz[m][kin]  (A = dz tiles K-major, B = the image read MN-major)
             mbar_wait(bar + E_DZ, ph);
             tc_fence_after();
+            if (leader) {
+#pragma unroll
             for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    umma(tmem, umma_desc(smem_u32(sDZ + c * TILE_BYTES) + k * 32),
-                         umma_desc_mn(smem_u32(sBz) + (c * 64 + k * 16) * 128, TILE_BYTES), iG3, (c | k) != 0);
+                    umma(tmem_u, desc_adv(kDZ, c * TILE_BYTES + k * 32), desc_adv(mBz, (c * 64 + k * 16) * 128), iG3, (c | k) != 0);
             umma_commit(bar + G3);
             // weight / bias gradients: K = time.  Every tile is [time x 64 ch], i.e. an MN-major operand.
             // First the ones that read the x/ctx and DZ tiles (W1): those buffers are needed first.
             const uint32_t acc0 = it != 0;
-            const uint64_t ones = umma_desc_mn_plain(smem_u32(sONES), 256, 128);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const uint64_t dz_mn = umma_desc_mn(smem_u32(sDZ) + k * 2048, TILE_BYTES);
-                umma(tmem + W1_COL, dz_mn, umma_desc_mn(smem_u32(sA) + k * 2048, TILE_BYTES), iW1, acc0 | (k != 0));
-                umma(tmem + B1_COL, dz_mn, ones, iB, acc0 | (k != 0));
+                umma(tmem_u + W1_COL, desc_adv(mDZ, k * 2048), desc_adv(mA, k * 2048), iW1, acc0 | (k != 0));
+                umma(tmem_u + B1_COL, desc_adv(mDZ, k * 2048), ones, iB, acc0 | (k != 0));
             }
             umma_commit(bar + W1);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const uint64_t dx_mn = umma_desc_mn(smem_u32(sDXS) + k * 2048, TILE_BYTES);
-                umma(tmem + W2_COL, dx_mn, umma_desc_mn(smem_u32(sG) + k * 2048, TILE_BYTES), iW2, acc0 | (k != 0));
-                umma(tmem + B2_COL, dx_mn, ones, iB, acc0 | (k != 0));
+                umma(tmem_u + W2_COL, desc_adv(mDXS, k * 2048), desc_adv(mG, k * 2048), iW2, acc0 | (k != 0));
+                umma(tmem_u + B2_COL, desc_adv(mDXS, k * 2048), ones, iB, acc0 | (k != 0));
             }
             umma_commit(bar + WALL);
+            }
             if (has_next) {
                 mbar_wait(bar + W1, ph);           // W1 no longer reads the x/ctx tiles
-                load_a_tiles(nb, n0);
+                if (leader) load_a_tiles(nb, n0);
             }
             mbar_wait(bar + E_OUT, ph);            // P', U', Q' are staged; nobody reads DXS or the tile's TMEM columns any more
-            tma_store_3d(&map_pout, sDZ, 0, t0, b);
-            tma_store_3d(&map_uout, sDZ + TILE_BYTES, 0, t0, b);
-            if (nc == 3) tma_store_3d(&map_qout, sQ, 0, t0, b);
-            tma_commit();
+            if (leader) {
+                tma_store_3d(&map_pout, sDZ, 0, t0, b);
+                tma_store_3d(&map_uout, sDZ + TILE_BYTES, 0, t0, b);
+                if (nc == 3) tma_store_3d(&map_qout, sQ, 0, t0, b);
+                tma_commit();
+            }
             if (has_next) {
                 mbar_wait(bar + WALL, ph);         // W2 no longer reads DXS
-                load_tile(sDXS, &map_p, P_IN, nb, n0);
+                if (leader) load_tile(sDXS, &map_p, P_IN, nb, n0);
             }
+            __syncwarp();
         }
-        tma_wait_all0();
+        if (leader) tma_wait_all0();
     } else if (tid < N_WORKERS) {
         // ================================ worker warps ============================================
         // this thread's d(skip) row of tile `tl` (first 8 channels), fetched one tile ahead
