@@ -80,6 +80,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint32_t* tmem_slot = (uint32_t*)(full_bar + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);     // warp-uniform copy: the issue branches stay convergent
 
     // ---- one-time setup: barriers, TMEM, and the weight image (one bulk copy) --------------------
     if (tid == 0) {
@@ -107,10 +108,16 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int half = tid >> 7;       // and split the channel range between them)
     const int sw = r & 7;
 
+    // all TMA / MMA instructions are issued by one elected lane of warp 0 from warp-uniform code (descriptors = base + constant)
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    bool issuer = false;
+    if (warp_u == 0) issuer = elect_one();
+
     uint32_t it = 1;            // phase 0 of full_bar was the weight image
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
         const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T;
-        if (tid == 0) {
+        if (warp_u == 0) {
+          if (issuer) {
             tma_wait_read0();        // the previous tile's x' store must be done reading A1
             mbar_expect_tx(full_bar, load_bytes);
             tma_load_3d(sA0, &map_x, full_bar, 0, t0 - a.dil, b);
@@ -123,6 +130,8 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 tma_prefetch_3d(&map_x, 0, n0, nb);
                 if (a.nchunks == 3) tma_prefetch_3d(&map_ctx, 0, n0, nb);
             }
+          }
+          __syncwarp();
         }
         // the running skip sum of this row: fetch it now, it is only needed at the very end of the tile
         const int t = t0 + r, js = t - (a.RF - 1);
@@ -131,14 +140,19 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         float4 old0 = make_float4(0.f, 0.f, 0.f, 0.f), old1 = old0;
         if (half == 0 && live && !a.skip_init) { old0 = ((const float4*)skip_dst)[0]; old1 = ((const float4*)skip_dst)[1]; }
         mbar_wait(full_bar, it & 1);
-        if (tid == 0) {
+        if (warp_u == 0) {
             tc_fence_after();
-            for (int c = 0; c < a.nchunks; ++c)
+            const uint64_t kA0 = umma_desc(smem_u32(sA0)), kBz = umma_desc(smem_u32(sBz));
+            if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma(tmem, umma_desc(smem_u32(sA0 + c * TILE_BYTES) + k * 32), umma_desc(smem_u32(sBz + c * TILE_BYTES) + k * 32),
-                         idesc1, (c | k) != 0);
-            umma_commit(mma_bar);
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (c < a.nchunks)
+                            umma(tmem_u, desc_adv(kA0, c * TILE_BYTES + k * 32), desc_adv(kBz, c * TILE_BYTES + k * 32), idesc1, (c | k) != 0);
+                umma_commit(mma_bar);
+            }
+            __syncwarp();
         }
         mbar_wait(mma_bar, 0);
         tc_fence_after();
@@ -166,12 +180,16 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0) {
             tc_fence_after();
+            const uint64_t kA0 = umma_desc(smem_u32(sA0)), kBrs = umma_desc(smem_u32(sBrs));
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                umma(tmem + D2_COL, umma_desc(smem_u32(sA0) + k * 32), umma_desc(smem_u32(sBrs) + k * 32), idesc2, k != 0);
-            umma_commit(mma_bar);
+                for (int k = 0; k < 4; ++k)
+                    umma(tmem_u + D2_COL, desc_adv(kA0, k * 32), desc_adv(kBrs, k * 32), idesc2, k != 0);
+                umma_commit(mma_bar);
+            }
+            __syncwarp();
         }
         mbar_wait(mma_bar, 1);
         tc_fence_after();
@@ -218,12 +236,12 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0 && a.has_out) {
+        if (issuer && a.has_out) {
             tma_store_3d(&map_out, sA1, 0, t0, b);
             tma_commit();
         }
     }
-    if (tid == 0) tma_wait_all0();
+    if (issuer) tma_wait_all0();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
