@@ -68,7 +68,8 @@ layer_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     const uint32_t tmem = *tmem_slot;
     const int n_mine = a.n_tiles > (int)blockIdx.x ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    if (warp == 16) {
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);     // warp-uniform copy: role branches stay convergent
+    if (warp_u == 16) {
         // ================================ TMA producer ============================================
         if ((tid & 31) == 0) {
             for (int k = 0; k < n_mine; ++k) {
@@ -82,33 +83,44 @@ layer_fwd_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 if (nc == 3) tma_load_3d(dst + 2 * TILE_BYTES, &map_ctx, full + st, 0, t0, b);
             }
         }
-    } else if (warp == 17) {
+    } else if (warp_u == 17) {
         // ================================ MMA issuer ==============================================
-        if ((tid & 31) == 0) {
+        // the whole warp runs the loop (uniform datapath), one elected lane issues; descriptors = base + constant
+        {
             const uint32_t idesc1 = umma_idesc(TILE_T, 128), idesc2 = umma_idesc(TILE_T, a.N2);
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+            const uint64_t kBz = umma_desc(smem_u32(sBz)), kBrs = umma_desc(smem_u32(sBrs));
             mbar_wait(img_bar, 0);
             auto mma2 = [&](int k) {
                 const int st = k % STAGES, g = k & 1, j = k >> 1;
-                uint8_t* sA0 = sStage + st * stage_bytes;
+                const uint64_t kA0 = umma_desc(smem_u32(sStage + st * stage_bytes));
                 mbar_wait(g_ready + g, j & 1);
                 tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma(tmem + g * GROUP_COLS + 128, umma_desc(smem_u32(sA0) + kk * 32), umma_desc(smem_u32(sBrs) + kk * 32), idesc2, kk != 0);
-                umma_commit(mma2_done + g);
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma(tmem_u + g * GROUP_COLS + 128, desc_adv(kA0, kk * 32), desc_adv(kBrs, kk * 32), idesc2, kk != 0);
+                    umma_commit(mma2_done + g);
+                }
+                __syncwarp();
             };
             for (int k = 0; k < n_mine; ++k) {
                 const int st = k % STAGES, g = k & 1, j = k >> 1;
-                uint8_t* sA0 = sStage + st * stage_bytes;
+                const uint64_t kA0 = umma_desc(smem_u32(sStage + st * stage_bytes));
                 mbar_wait(full + st, (k / STAGES) & 1);
                 if (j > 0) mbar_wait(tmem_free + g, (j - 1) & 1);
                 tc_fence_after();
-                for (int c = 0; c < nc; ++c)
+                if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma(tmem + g * GROUP_COLS, umma_desc(smem_u32(sA0 + c * TILE_BYTES) + kk * 32),
-                             umma_desc(smem_u32(sBz + c * TILE_BYTES) + kk * 32), idesc1, (c | kk) != 0);
-                umma_commit(mma1_done + g);
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            if (c < nc)
+                                umma(tmem_u + g * GROUP_COLS, desc_adv(kA0, c * TILE_BYTES + kk * 32), desc_adv(kBz, c * TILE_BYTES + kk * 32),
+                                     idesc1, (c | kk) != 0);
+                    umma_commit(mma1_done + g);
+                }
+                __syncwarp();
                 if (k > 0) mma2(k - 1);
             }
             if (n_mine > 0) mma2(n_mine - 1);
