@@ -7,13 +7,14 @@
 // and the dilation shift becomes a TMA row coordinate instead of a scatter.  Per 128-row time tile:
 //
 //   TMA : x(t-d) x(t) ctx(t) P(t) U(t+d_up)          | threads: d(skip) rows -> bf16 tile
-//   dxs = P + U  (in place, bf16)
+//   dxs = P + U is never formed in memory: every product with it is two accumulating MMAs
 //   G1  : D1 = [x(t-d)|x(t)|ctx] . Wz^T               (recompute the gate pre-activations)
-//   G2  : D3 = [dxs | dskip] . [Wr ; Ws]              (d gated)          B read MN-major from the SAME image
+//   G2  : D3 = [P | dskip] . [Wr ; Ws] + U . Wr       (d gated)          B read MN-major from the SAME image
 //   epilogue 1: th, sg, gated, dz_f, dz_g  -> bf16 tiles DZ0 DZ1 G  (128B-swizzled)
 //   G3  : D4 = dz . Wz  -> [U' | W1^T dz | V^T dz]    (B = the forward weight image read MN-major)
 //   W1  : dWz^T  += dz^T . [x(t-d)|x(t)|ctx]          (K = time: every tile is read MN-major)
-//   W2  : dWrs^T += [dxs|dskip]^T . gated ;  bias grads = the same A operands times an all-ones B
+//   W2  : dWrs^T += [P|dskip]^T . gated + [U|dskip]^T . gated (skip rows halved at the flush) ;
+//         bias grads = the same A operands times an all-ones B
 //   epilogue 2: P' = dxs + D4[tap1] ; U' = D4[tap0]  -> TMA stores ; d(ctx) += D4[ctx]
 //
 // The weight-gradient accumulators stay in TMEM for the CTA's whole tile loop and are written once
@@ -56,16 +57,16 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint8_t* sBrs = smem + smem_brs_off(nc);
     float* sbz = (float*)(smem + smem_bias_off(nc, a.N2));
     uint8_t* sA = smem + bwd_tiles_off(nc, a.N2);
-    uint8_t* sDXS = sA + nc * TILE_BYTES;
+    uint8_t* sU = sA + nc * TILE_BYTES;           // U | P | DSK in this order: [P|DSK] and [U|DSK] are both M=128 block pairs
+    uint8_t* sDXS = sU + TILE_BYTES;              // the P tile (the stream gradient is P + U, never summed in memory)
     uint8_t* sDSK = sDXS + TILE_BYTES;
-    uint8_t* sU = sDSK + TILE_BYTES;
-    uint8_t* sDZ = sU + TILE_BYTES;               // DZ0 (filter half) | DZ1 (gate half)
+    uint8_t* sDZ = sDSK + TILE_BYTES;             // DZ0 (filter half) | DZ1 (gate half)
     uint8_t* sG = sDZ + 2 * TILE_BYTES;
     uint8_t* sQ = sG + TILE_BYTES;                // running sum of the context gradient (video only)
     uint8_t* sONES = sQ + (nc == 3 ? TILE_BYTES : 0);
     // barriers, one completion per tile each (parity = tile iteration & 1), except IMG (once).
     // E_* are the worker -> control-warp signals (512 arrivals), the rest are TMA / tcgen05.commit completions.
-    enum { IMG = 0, A_IN, P_IN, U_IN, Q_IN, G1, G2, G3, W1, WALL, E_DXS, E_DZ, E_OUT, N_BARS };
+    enum { IMG = 0, A_IN, P_IN, U_IN, Q_IN, G1, G2, G3, W1, WALL, E_DSK, E_DZ, E_OUT, N_BARS };
     uint64_t* bar = (uint64_t*)(sONES + 1024);
     uint32_t* tmem_slot = (uint32_t*)(bar + N_BARS);
 
@@ -75,7 +76,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int NZ = nc * CC;                        // columns of D4 / dWz^T
 
     if (tid == 0) {
-        for (int i = 0; i < N_BARS; ++i) mbar_init(bar + i, i >= E_DXS ? N_WORKERS : 1);
+        for (int i = 0; i < N_BARS; ++i) mbar_init(bar + i, i >= E_DSK ? N_WORKERS : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t wbytes = (uint32_t)smem_a_off(nc, a.N2);
         mbar_expect_tx(bar + IMG, wbytes);
@@ -113,10 +114,11 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
         // base descriptors of every operand; one MMA's descriptors are these plus a compile-time offset
         const uint64_t kA = umma_desc(smem_u32(sA)), kBz = umma_desc(smem_u32(sBz)), kDXS = umma_desc(smem_u32(sDXS)),
-                       kDSK = umma_desc(smem_u32(sDSK)), kDZ = umma_desc(smem_u32(sDZ));
+                       kU = umma_desc(smem_u32(sU)), kDSK = umma_desc(smem_u32(sDSK)), kDZ = umma_desc(smem_u32(sDZ));
         const uint64_t mBrs = umma_desc_mn(smem_u32(sBrs), TILE_BYTES), mBz = umma_desc_mn(smem_u32(sBz), TILE_BYTES),
                        mDZ = umma_desc_mn(smem_u32(sDZ), TILE_BYTES), mA = umma_desc_mn(smem_u32(sA), TILE_BYTES),
-                       mDXS = umma_desc_mn(smem_u32(sDXS), TILE_BYTES), mG = umma_desc_mn(smem_u32(sG), TILE_BYTES);
+                       mDXS = umma_desc_mn(smem_u32(sDXS), TILE_BYTES), mU = umma_desc_mn(smem_u32(sU), 2 * TILE_BYTES),
+                       mG = umma_desc_mn(smem_u32(sG), TILE_BYTES);
         const uint64_t ones = umma_desc_mn_plain(smem_u32(sONES), 256, 128);
         const uint32_t iG1 = umma_idesc_major(TILE_T, 128, 0, 0);
         const uint32_t iG2 = umma_idesc_major(TILE_T, 64, 0, 1);
@@ -171,18 +173,23 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                                       // commit: the workers write DZ again only after they have seen G2)
                 if (nc == 3) load_tile(sQ, &map_q, Q_IN, b, t0);                     // needed by epilogue 2 only
             }
-            // G2: d(gated) = dxs . Wr + dskip . Ws : contraction over the image's ROWS (c_out | s) -> B is MN-major
-            mbar_wait(bar + E_DXS, ph);
+            // G2: d(gated) = (P + U) . Wr + dskip . Ws as three accumulating products (no pre-sum pass): contraction over
+            // the image's ROWS (c_out | s) -> B is MN-major.  Needs only the loads and the DSK tile, so it runs next to G1.
+            mbar_wait(bar + P_IN, ph);
+            mbar_wait(bar + U_IN, ph);
+            mbar_wait(bar + E_DSK, ph);
             tc_fence_after();
             if (leader) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma(tmem_u + 128, desc_adv(kDXS, k * 32), desc_adv(mBrs, k * 2048), iG2, k != 0);
 #pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma(tmem_u + 128, desc_adv(kU, k * 32), desc_adv(mBrs, k * 2048), iG2, 1);
+#pragma unroll
                 for (int k = 0; k < 4; ++k)                // the skip channels: rows 64.. of the image, 16 per step
                     if (k < (a.S + 15) / 16) umma(tmem_u + 128, desc_adv(kDSK, k * 32), desc_adv(mBrs, (4 + k) * 2048), iG2, 1);
                 umma_commit(bar + G2);
-                if (has_next) load_tile(sU, &map_u, U_IN, nb, n0 + a.dil_up);        // the U tile is free from here on
             }
             // G3: D4[t][kin] = sum_m dz[t][m] Wz[m][kin]  (A = dz tiles K-major, B = the image read MN-major)
             mbar_wait(bar + E_DZ, ph);
@@ -203,10 +210,16 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 umma(tmem_u + B1_COL, desc_adv(mDZ, k * 2048), ones, iB, acc0 | (k != 0));
             }
             umma_commit(bar + W1);
+            // [P|DSK]^T and [U|DSK]^T: the skip rows (64..) are accumulated twice and halved at the flush (exact)
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 umma(tmem_u + W2_COL, desc_adv(mDXS, k * 2048), desc_adv(mG, k * 2048), iW2, acc0 | (k != 0));
                 umma(tmem_u + B2_COL, desc_adv(mDXS, k * 2048), ones, iB, acc0 | (k != 0));
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                umma(tmem_u + W2_COL, desc_adv(mU, k * 2048), desc_adv(mG, k * 2048), iW2, 1);
+                umma(tmem_u + B2_COL, desc_adv(mU, k * 2048), ones, iB, 1);
             }
             umma_commit(bar + WALL);
             }
@@ -222,8 +235,11 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 tma_commit();
             }
             if (has_next) {
-                mbar_wait(bar + WALL, ph);         // W2 no longer reads DXS
-                if (leader) load_tile(sDXS, &map_p, P_IN, nb, n0);
+                mbar_wait(bar + WALL, ph);         // W2 no longer reads the P and U tiles
+                if (leader) {
+                    load_tile(sDXS, &map_p, P_IN, nb, n0);
+                    load_tile(sU, &map_u, U_IN, nb, n0 + a.dil_up);
+                }
             }
             __syncwarp();
         }
@@ -261,6 +277,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
                 }
             }
+            fence_proxy_async();
+            mbar_arrive(bar + E_DSK);
             // ---- epilogue 1a (needs G1 only): th, sg, gated -> G tile ---------------------------------
             float th[16], sg[16];
             mbar_wait(bar + G1, ph);
@@ -284,24 +302,6 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 *(uint4*)(sG + o0) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
                 *(uint4*)(sG + o1) = make_uint4(oy[4], oy[5], oy[6], oy[7]);
             }
-            // ---- dxs = P + U(t + d_up), in place -----------------------------------------------------
-            mbar_wait(bar + P_IN, ph);
-            mbar_wait(bar + U_IN, ph);
-#pragma unroll
-            for (int q = 2 * half; q < 2 * half + 2; ++q) {
-                uint4* pp = (uint4*)(sDXS + r * 128 + ((q ^ sw) << 4));
-                const uint4 pv = *pp, uv = *(const uint4*)(sU + r * 128 + ((q ^ sw) << 4));
-                const uint32_t pa[4] = {pv.x, pv.y, pv.z, pv.w}, ua[4] = {uv.x, uv.y, uv.z, uv.w};
-                uint32_t o[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 x = unpack_bf16(pa[i]), y = unpack_bf16(ua[i]);
-                    o[i] = pack_bf16(x.x + y.x, x.y + y.y);
-                }
-                *pp = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-            fence_proxy_async();
-            mbar_arrive(bar + E_DXS);
             // ---- epilogue 1b: gate derivative -> DZ0 | DZ1 ------------------------------------------
             mbar_wait(bar + G2, ph);
             tc_fence_after();
@@ -338,11 +338,14 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 tmem_ld16(tmem + lane_base + 64 + 16 * half, v);
                 tmem_ld16(tmem + lane_base + 16 * half, w);
                 const uint4 x0 = *(const uint4*)(sDXS + o0), x1 = *(const uint4*)(sDXS + o1);
+                const uint4 y0 = *(const uint4*)(sU + o0), y1 = *(const uint4*)(sU + o1);
                 const uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                const uint32_t yi[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float2 xv = unpack_bf16(xi[i]);
+                    const float2 xp = unpack_bf16(xi[i]), xu = unpack_bf16(yi[i]);
+                    const float2 xv = make_float2(xp.x + xu.x, xp.y + xu.y);
                     po[i] = pack_bf16(__uint_as_float(v[2 * i]) + xv.x, __uint_as_float(v[2 * i + 1]) + xv.y);
                     uo[i] = pack_bf16(__uint_as_float(w[2 * i]), __uint_as_float(w[2 * i + 1]));
                 }
@@ -397,10 +400,11 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         uint32_t v[16];
         tmem_ld16(tmem + lane_base + W2_COL + 16 * j, v);
         tmem_ld_wait();
+        const float sc = r >= CC ? 0.5f : 1.f;     // the skip rows were accumulated once with P and once with U
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            ((float4*)(prow + 192 + 16 * j))[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                                              __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+            ((float4*)(prow + 192 + 16 * j))[q] = make_float4(sc * __uint_as_float(v[4 * q]), sc * __uint_as_float(v[4 * q + 1]),
+                                                              sc * __uint_as_float(v[4 * q + 2]), sc * __uint_as_float(v[4 * q + 3]));
     }
     {
         uint32_t v1[8], v2[8];
@@ -409,7 +413,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tmem_ld_wait();
         if (half == 0) {
             part[128 * PART_LD + r] = __uint_as_float(v1[0]);
-            part[128 * PART_LD + 128 + r] = __uint_as_float(v2[0]);
+            part[128 * PART_LD + 128 + r] = (r >= CC ? 0.5f : 1.f) * __uint_as_float(v2[0]);
         }
     }
     }
