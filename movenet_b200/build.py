@@ -35,7 +35,9 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        # MOVENET_B200_NVCC_EXTRA: extra compile flags for instrumented builds (e.g. -DMVN_PHASE_CLOCKS=1)
+        extra = os.environ.get("MOVENET_B200_NVCC_EXTRA", "").split()
+        cmd = [nvcc] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -20,12 +20,31 @@
 // The weight-gradient accumulators stay in TMEM for the CTA's whole tile loop and are written once
 // per CTA as partial sums; a small second kernel reduces the partials in a fixed order
 // (deterministic, no atomics) into the packed gradient buffer.
+#include <cstdio>
+#include <cstdlib>
 #include "tc_common.cuh"
 #include "layer_tc.h"
 
 using namespace tc;
 
 namespace {
+
+// Instrumented build (MOVENET_B200_NVCC_EXTRA=-DMVN_PHASE_CLOCKS=1): clock64() stamps of tile iterations 5..7 of CTA 0 for
+// the control lane (CLKC), one worker thread (CLKW) and the latest worker (CLKM); printed by launch 20 when MVN_PROF is set.
+#ifndef MVN_PHASE_CLOCKS
+#define MVN_PHASE_CLOCKS 0
+#endif
+#if MVN_PHASE_CLOCKS
+__device__ unsigned long long g_clk[3][3][20];
+#define CLK_(role, i, cond) do { if (blockIdx.x == 0 && it >= 5 && it < 8 && (cond)) g_clk[role][it - 5][i] = clock64(); } while (0)
+#define CLKW(i) CLK_(0, i, tid == 256)
+#define CLKC(i) CLK_(1, i, leader)
+#define CLKM(i) do { if (blockIdx.x == 0 && it >= 5 && it < 8) atomicMax(&g_clk[2][it - 5][i], (unsigned long long)clock64()); } while (0)
+#else
+#define CLKW(i) do {} while (0)
+#define CLKC(i) do {} while (0)
+#define CLKM(i) do {} while (0)
+#endif
 
 constexpr int W1_COL = 192, W2_COL = 384, B1_COL = 448, B2_COL = 464;
 constexpr int PART_LD = 256;                       // partial row: 192 (dWz^T) + 64 (dWrs^T)
@@ -41,6 +60,12 @@ struct BwdArgs {
 __host__ __device__ inline int bwd_tiles_off(int nc, int N2) { return smem_a_off(nc, N2); }
 // tiles after the image: A0..A(nc-1) | DXS | DSK | U | DZ0 | DZ1 | G | [Q, video only] | ONES(1 KB) | barriers
 __host__ __device__ inline int bwd_smem_total(int nc, int N2) { return bwd_tiles_off(nc, N2) + (nc + 6 + (nc == 3)) * TILE_BYTES + 1024 + 128; }
+
+// every lane has fenced its own writes; one lane signals for the warp
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 
 constexpr int N_WORKERS = 512, N_THREADS = N_WORKERS + 32;   // 16 worker warps + the control warp
 
@@ -65,7 +90,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint8_t* sQ = sG + TILE_BYTES;                // running sum of the context gradient (video only)
     uint8_t* sONES = sQ + (nc == 3 ? TILE_BYTES : 0);
     // barriers, one completion per tile each (parity = tile iteration & 1), except IMG (once).
-    // E_* are the worker -> control-warp signals (512 arrivals), the rest are TMA / tcgen05.commit completions.
+    // E_* are the worker -> control-warp signals (one arrival per worker warp), the rest are TMA / tcgen05.commit completions.
     enum { IMG = 0, A_IN, P_IN, U_IN, Q_IN, G1, G2, G3, W1, WALL, E_DSK, E_DZ, E_OUT, N_BARS };
     uint64_t* bar = (uint64_t*)(sONES + 1024);
     uint32_t* tmem_slot = (uint32_t*)(bar + N_BARS);
@@ -76,7 +101,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int NZ = nc * CC;                        // columns of D4 / dWz^T
 
     if (tid == 0) {
-        for (int i = 0; i < N_BARS; ++i) mbar_init(bar + i, i >= E_DSK ? N_WORKERS : 1);
+        for (int i = 0; i < N_BARS; ++i) mbar_init(bar + i, i >= E_DSK ? N_WORKERS / 32 : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t wbytes = (uint32_t)smem_a_off(nc, a.N2);
         mbar_expect_tx(bar + IMG, wbytes);
@@ -150,7 +175,9 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             const bool has_next = nt < a.n_tiles;
             const int nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
             // G1: recompute the gate pre-activations (the tile's TMEM columns are free: E_OUT of the previous tile)
+            CLKC(0);
             mbar_wait(bar + A_IN, ph);
+            CLKC(1);
             tc_fence_after();
             if (leader) {
 #pragma unroll
@@ -161,6 +188,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                             umma(tmem_u, desc_adv(kA, c * TILE_BYTES + k * 32), desc_adv(kBz, c * TILE_BYTES + k * 32), iG1, (c | k) != 0);
                 umma_commit(bar + G1);
             }
+            CLKC(2);
             if (leader && has_next) {              // start pulling the next tile into L2 now
                 tma_prefetch_3d(&map_x, 0, n0 - a.dil, nb);
                 tma_prefetch_3d(&map_x, 0, n0, nb);
@@ -175,9 +203,12 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             }
             // G2: d(gated) = (P + U) . Wr + dskip . Ws as three accumulating products (no pre-sum pass): contraction over
             // the image's ROWS (c_out | s) -> B is MN-major.  Needs only the loads and the DSK tile, so it runs next to G1.
+            CLKC(3);
             mbar_wait(bar + P_IN, ph);
             mbar_wait(bar + U_IN, ph);
+            CLKC(4);
             mbar_wait(bar + E_DSK, ph);
+            CLKC(5);
             tc_fence_after();
             if (leader) {
 #pragma unroll
@@ -191,8 +222,10 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     if (k < (a.S + 15) / 16) umma(tmem_u + 128, desc_adv(kDSK, k * 32), desc_adv(mBrs, (4 + k) * 2048), iG2, 1);
                 umma_commit(bar + G2);
             }
+            CLKC(6);
             // G3: D4[t][kin] = sum_m dz[t][m] Wz[m][kin]  (A = dz tiles K-major, B = the image read MN-major)
             mbar_wait(bar + E_DZ, ph);
+            CLKC(7);
             tc_fence_after();
             if (leader) {
 #pragma unroll
@@ -201,6 +234,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 for (int k = 0; k < 4; ++k)
                     umma(tmem_u, desc_adv(kDZ, c * TILE_BYTES + k * 32), desc_adv(mBz, (c * 64 + k * 16) * 128), iG3, (c | k) != 0);
             umma_commit(bar + G3);
+            CLKC(8);
             // weight / bias gradients: K = time.  Every tile is [time x 64 ch], i.e. an MN-major operand.
             // First the ones that read the x/ctx and DZ tiles (W1): those buffers are needed first.
             const uint32_t acc0 = it != 0;
@@ -210,6 +244,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 umma(tmem_u + B1_COL, desc_adv(mDZ, k * 2048), ones, iB, acc0 | (k != 0));
             }
             umma_commit(bar + W1);
+            CLKC(9);
             // [P|DSK]^T and [U|DSK]^T: the skip rows (64..) are accumulated twice and halved at the flush (exact)
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -222,12 +257,16 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 umma(tmem_u + B2_COL, desc_adv(mU, k * 2048), ones, iB, 1);
             }
             umma_commit(bar + WALL);
+            CLKC(10);
             }
             if (has_next) {
                 mbar_wait(bar + W1, ph);           // W1 no longer reads the x/ctx tiles
+                CLKC(11);
                 if (leader) load_a_tiles(nb, n0);
             }
+            CLKC(12);
             mbar_wait(bar + E_OUT, ph);            // P', U', Q' are staged; nobody reads DXS or the tile's TMEM columns any more
+            CLKC(13);
             if (leader) {
                 tma_store_3d(&map_pout, sDZ, 0, t0, b);
                 tma_store_3d(&map_uout, sDZ + TILE_BYTES, 0, t0, b);
@@ -235,13 +274,16 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 tma_commit();
             }
             if (has_next) {
+                CLKC(14);
                 mbar_wait(bar + WALL, ph);         // W2 no longer reads the P and U tiles
+                CLKC(15);
                 if (leader) {
                     load_tile(sDXS, &map_p, P_IN, nb, n0);
                     load_tile(sU, &map_u, U_IN, nb, n0 + a.dil_up);
                 }
             }
             __syncwarp();
+            CLKC(16);
         }
         if (leader) tma_wait_all0();
     } else if (tid < N_WORKERS) {
@@ -263,6 +305,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             const uint32_t ph = it & 1;
             const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T;
             const int t = t0 + r;
+            CLKW(0);
             if (it) mbar_wait(bar + WALL, ph ^ 1);      // the previous tile's weight-gradient MMAs are done with DSK and G
             if (half == 0) {   // d(skip) row of this thread -> bf16, logical channels [0, S) of the DSK tile
                 *(uint4*)(sDSK + r * 128 + ((0 ^ sw) << 4)) =
@@ -278,10 +321,12 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 }
             }
             fence_proxy_async();
-            mbar_arrive(bar + E_DSK);
+            warp_arrive(bar + E_DSK);
+            CLKW(1); CLKM(1);
             // ---- epilogue 1a (needs G1 only): th, sg, gated -> G tile ---------------------------------
             float th[16], sg[16];
             mbar_wait(bar + G1, ph);
+            CLKW(2);
             tc_fence_after();
             {
                 uint32_t f[16], g[16];
@@ -302,8 +347,10 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 *(uint4*)(sG + o0) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
                 *(uint4*)(sG + o1) = make_uint4(oy[4], oy[5], oy[6], oy[7]);
             }
+            CLKW(3); CLKM(3);
             // ---- epilogue 1b: gate derivative -> DZ0 | DZ1 ------------------------------------------
             mbar_wait(bar + G2, ph);
+            CLKW(4);
             tc_fence_after();
             {
                 uint32_t dg[16];
@@ -328,9 +375,11 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             }
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bar + E_DZ);
+            warp_arrive(bar + E_DZ);
+            CLKW(5); CLKM(5);
             // ---- epilogue 2: P' = dxs + W1^T dz, U' = W0^T dz (registers until the DZ tiles are free); Q' = Q + V^T dz in place
             mbar_wait(bar + G3, ph);
+            CLKW(6);
             tc_fence_after();
             uint32_t po[8], uo[8];
             {
@@ -353,7 +402,9 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             if (nc == 3) {
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + 128 + 16 * half, v);
+                CLKW(7);
                 mbar_wait(bar + Q_IN, ph);
+                CLKW(8);
                 uint4* p0 = (uint4*)(sQ + o0);
                 uint4* p1 = (uint4*)(sQ + o1);
                 const uint4 x0 = *p0, x1 = *p1;
@@ -368,14 +419,17 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 *p0 = make_uint4(o[0], o[1], o[2], o[3]);
                 *p1 = make_uint4(o[4], o[5], o[6], o[7]);
             }
+            CLKW(9);
             mbar_wait(bar + W1, ph);            // W1 no longer reads the DZ tiles
+            CLKW(10);
             *(uint4*)(sDZ + o0) = make_uint4(po[0], po[1], po[2], po[3]);
             *(uint4*)(sDZ + o1) = make_uint4(po[4], po[5], po[6], po[7]);
             *(uint4*)(sDZ + TILE_BYTES + o0) = make_uint4(uo[0], uo[1], uo[2], uo[3]);
             *(uint4*)(sDZ + TILE_BYTES + o1) = make_uint4(uo[4], uo[5], uo[6], uo[7]);
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bar + E_OUT);
+            warp_arrive(bar + E_OUT);
+            CLKW(11); CLKM(11);
             load_dskip(tile + gridDim.x, ds0, ds1);
         }
         if (it) mbar_wait(bar + WALL, (it - 1) & 1);
@@ -502,5 +556,22 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     if (grid > a.n_tiles) grid = a.n_tiles;
     layer_bwd_tc_kernel<<<grid, N_THREADS, smem, st>>>(mx, mc, mp, mu, mpo, muo, mq, mqo, a);
     (void)lg;
+#if MVN_PHASE_CLOCKS
+    if (getenv("MVN_PROF")) {
+        static int launches = 0;
+        if (++launches == 20) {
+            cudaDeviceSynchronize();
+            unsigned long long h[3][3][20];
+            cudaMemcpyFromSymbol(h, g_clk, sizeof(h));
+            const char* names[3] = {"worker", "control", "last-worker"};
+            for (int w = 0; w < 3; ++w)
+                for (int i = 0; i < 3; ++i) {
+                    fprintf(stderr, "CLK %-11s it%d:", names[w], i + 5);
+                    for (int j = 0; j < 17; ++j) fprintf(stderr, " %lld", h[w][i][j] ? (long long)(h[w][i][j] - h[1][0][0]) : -1LL);
+                    fprintf(stderr, "\n");
+                }
+        }
+    }
+#endif
     return mvn_check_launch("layer_bwd_tc");
 }
