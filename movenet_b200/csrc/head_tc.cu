@@ -409,8 +409,10 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
 template <int A>
 __global__ void head_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ pg, PackedLayout P, int S) {
     constexpr int HPART = HP<A>::floats;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HPART; i += gridDim.x * blockDim.x) {
+    {
+        const int i = blockIdx.x * 32 + threadIdx.x;
         float* dst = nullptr;
+        if (i < HPART) {
         if constexpr (A == 64) {      // D_w[m][n]: m < 64 dz, m >= 64 da1 ; n < 64 lrelu(a1), n >= 64 lrelu(skip)
             if (i < 128 * 128) {
                 const int m = i >> 7, n = i & 127;
@@ -425,11 +427,9 @@ __global__ void head_reduce_kernel(const float* __restrict__ partial, int n_cta,
             else if (i < 128 * 128 + 128 * 64) { const int q = i - 128 * 128, m = q >> 6, n = q & 63; if (n < S) dst = pg + P.w1p + (size_t)n * A + m; }
             else { const int m = i - 128 * 128 - 128 * 64; dst = m < 128 ? pg + P.b2 + m : pg + P.b1 + (m - 128); }
         }
-        if (!dst) continue;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < n_cta; ++c) acc += partial[(size_t)c * HPART + i];
-        *dst = acc;
+        }
+        const float acc = column_sum(partial, n_cta, HPART, i, dst != nullptr);
+        if (dst && threadIdx.y == 0) *dst = acc;
     }
 }
 
@@ -515,7 +515,7 @@ int mvn_tc_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, co
     HEAD_DISPATCH(launch_bwd, a, grid, st);
     int rc = mvn_check_launch("head_bwd_tc");
     if (rc) return rc;
-    if (g.A == 64) head_reduce_kernel<64><<<(HP<64>::floats + 255) / 256, 256, 0, st>>>(partial, grid, pg, P, g.S);
-    else head_reduce_kernel<128><<<(HP<128>::floats + 255) / 256, 256, 0, st>>>(partial, grid, pg, P, g.S);
+    if (g.A == 64) head_reduce_kernel<64><<<(HP<64>::floats + 31) / 32, dim3(32, RED_SPLIT), 0, st>>>(partial, grid, pg, P, g.S);
+    else head_reduce_kernel<128><<<(HP<128>::floats + 31) / 32, dim3(32, RED_SPLIT), 0, st>>>(partial, grid, pg, P, g.S);
     return mvn_check_launch("head_reduce");
 }

@@ -122,14 +122,11 @@ input_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_cons
 
 // dwin[tap][a][c] = sum_cta part[tap*64 + a][c]
 __global__ void input_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ dwin, int A) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= IPART) return;
+    const int i = blockIdx.x * 32 + threadIdx.x;
     const int m = i >> 6, col = i & 63, tap = m >> 6, ch = m & 63;
-    if (ch >= A) return;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < n_cta; ++c) acc += partial[(size_t)c * IPART + i];
-    dwin[((size_t)tap * A + ch) * 64 + col] = acc;
+    const bool valid = i < IPART && ch < A;
+    const float acc = column_sum(partial, n_cta, IPART, i, valid);
+    if (valid && threadIdx.y == 0) dwin[((size_t)tap * A + ch) * 64 + col] = acc;
 }
 
 }  // namespace
@@ -152,6 +149,6 @@ int mvn_tc_input_bwd(const float* audio, const int* codes, const unsigned char* 
     const int grid = a.n_tiles < 3 * 148 ? a.n_tiles : 3 * 148;
     input_bwd_tc_kernel<<<grid, 128, smem, st>>>(mp, mu, a);
     if ((rc = mvn_check_launch("input_bwd_tc"))) return rc;
-    input_reduce_kernel<<<(IPART + 255) / 256, 256, 0, st>>>(partial, grid, dwin, g.A);
+    input_reduce_kernel<<<(IPART + 31) / 32, dim3(32, RED_SPLIT), 0, st>>>(partial, grid, dwin, g.A);
     return mvn_check_launch("input_reduce");
 }

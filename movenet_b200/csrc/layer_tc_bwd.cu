@@ -488,7 +488,8 @@ __global__ void tc_bwd_reduce_kernel(const float* __restrict__ partial_all, int 
     const float* partial = partial_all + (size_t)layer * 148 * PART_FLOATS;
     float* lg = pg + P.layer0 + (size_t)layer * P.layer_stride;
     const int has_resid = layer + 1 < n_layers;
-    // one thread per SOURCE element so the n_cta reads of a warp are coalesced; the destination is scattered
+    // one thread per SOURCE element so the n_cta reads of a warp are coalesced; the destination is scattered.  (176 MB of
+    // partials for nine layers: this one is bandwidth-bound, a plain loop per column is the fastest shape.)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < PART_FLOATS; i += gridDim.x * blockDim.x) {
         float* dst = nullptr;
         if (i < 128 * PART_LD) {

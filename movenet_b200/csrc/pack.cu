@@ -118,9 +118,9 @@ __global__ void pack_misc_kernel(const float* const* __restrict__ ptrs, float* _
     } else if (video && grp == 2) {   // video conv: wv[(hw)*Cin + ci][c] = w[c][ci][0][h][w]
         const float *w = ptrs[MVN_PARAM_VIDEO_CONV_W], *b = ptrs[MVN_PARAM_VIDEO_CONV_B];
         const int K = 4096 * Cin;
-        for (int i = i0; i < K * C; i += stride) {
-            const int c = i % C, kk = i / C, ci = kk % Cin, hw = kk / Cin;
-            packed[P.wv + i] = c < Cl ? w[((size_t)c * Cin + ci) * 4096 + hw] : 0.f;
+        for (int i = i0; i < K * C; i += stride) {        // hw fastest: the reads of the reference tensor are coalesced
+            const int hw = i & 4095, r = i >> 12, ci = r % Cin, c = r / Cin;
+            packed[P.wv + ((size_t)hw * Cin + ci) * C + c] = c < Cl ? w[((size_t)c * Cin + ci) * 4096 + hw] : 0.f;
         }
         for (int i = i0; i < C; i += stride) packed[P.bv + i] = i < Cl ? b[i] : 0.f;
     } else if (video && grp >= 3 && grp < 6) {   // ConvTranspose1d: wt[ci][j*C + co] = w[ci][co][j]
@@ -157,9 +157,9 @@ __global__ void unpack_misc_kernel(float* __restrict__ flat, const long long* __
     } else if (grp == 2) {
         float *w = gp(MVN_PARAM_VIDEO_CONV_W), *b = gp(MVN_PARAM_VIDEO_CONV_B);
         const int K = 4096 * Cin;
-        if (w) for (int i = i0; i < K * C; i += stride) {
-            const int c = i % C, kk = i / C, ci = kk % Cin, hw = kk / Cin;
-            if (c < Cl) w[((size_t)c * Cin + ci) * 4096 + hw] = video ? packed[P.wv + i] : 0.f;
+        if (w) for (int i = i0; i < K * C; i += stride) {    // hw fastest: the writes of the reference-shaped gradient are coalesced
+            const int hw = i & 4095, r = i >> 12, ci = r % Cin, c = r / Cin;
+            if (c < Cl) w[((size_t)c * Cin + ci) * 4096 + hw] = video ? packed[P.wv + ((size_t)hw * Cin + ci) * C + c] : 0.f;
         }
         if (b) for (int i = i0; i < Cl; i += stride) b[i] = video ? packed[P.bv + i] : 0.f;
     } else if (grp >= 3 && grp < 6) {
@@ -184,7 +184,7 @@ extern "C" int mvn_pack_weights(const mvn_shape_t* s, const void* const* param_p
     const float* const* ptrs = (const float* const*)param_ptrs_dev;
     dim3 gl(8, g.N);
     pack_layer_kernel<<<gl, 256, 0, st>>>(ptrs, (float*)packed, P, g.C, g.Cl, g.S, g.Kz, g.video);
-    dim3 gm(32, 6);
+    dim3 gm(128, 6);
     pack_misc_kernel<<<gm, 256, 0, st>>>(ptrs, (float*)packed, P, g.A, g.C, g.Cl, g.S, g.Cin, g.N, g.video);
     int rc = mvn_check_launch("pack_weights");
     if (rc) return rc;
@@ -206,7 +206,7 @@ extern "C" int mvn_unpack_grads(const mvn_shape_t* s, const void* packed_grads, 
     const long long* offs = (const long long*)offsets_dev;
     dim3 gl(8, g.N);
     unpack_layer_kernel<<<gl, 256, 0, st>>>(flat_grads, offs, (const float*)packed_grads, P, g.C, g.Cl, g.S, g.Kz, g.video);
-    dim3 gm(32, 6);
+    dim3 gm(128, 6);
     unpack_misc_kernel<<<gm, 256, 0, st>>>(flat_grads, offs, (const float*)packed_grads, P, g.A, g.C, g.Cl, g.S, g.Cin, g.N, g.video);
     return mvn_check_launch("unpack_grads");
 }

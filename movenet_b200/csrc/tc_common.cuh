@@ -150,6 +150,28 @@ __host__ __device__ constexpr uint32_t umma_idesc_major(int M, int N, int a_mn, 
     return umma_idesc(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
 }
 
+// Deterministic sum over the per-CTA partials of one column: partial[c * len + i], c < n.  Launch with blockDim = (32, RED_SPLIT):
+// threadIdx.x = column inside the block's 32 (coalesced 128-byte rows), the n rows are dealt round-robin to the RED_SPLIT
+// threads of a column (so RED_SPLIT loads are in flight per column instead of one dependent chain) and combined through
+// shared memory in a fixed order.  Every thread of the block must call it; the result is valid where threadIdx.y == 0.
+constexpr int RED_SPLIT = 8;
+__device__ __forceinline__ float column_sum(const float* __restrict__ partial, int n, size_t len, size_t i, bool valid) {
+    __shared__ float red[RED_SPLIT][32];
+    float acc = 0.f;
+    if (valid) {
+#pragma unroll 4
+        for (int c = threadIdx.y; c < n; c += RED_SPLIT) acc += partial[(size_t)c * len + i];
+    }
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    float tot = 0.f;
+    if (threadIdx.y == 0) {
+#pragma unroll
+        for (int y = 0; y < RED_SPLIT; ++y) tot += red[y][threadIdx.x];
+    }
+    return tot;
+}
+
 // shared-memory image of one layer's weights (mvn_tc_pack): Wz chunks | [Wr|Ws] | biases (1 KB)
 __host__ __device__ inline int smem_brs_off(int nchunks) { return nchunks * TILE_BYTES; }
 __host__ __device__ inline int smem_bias_off(int nchunks, int N2) { return smem_brs_off(nchunks) + ((N2 * 128 + 1023) & ~1023); }

@@ -276,12 +276,10 @@ up_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_u2, const __grid_consta
 
 // dwt[c_in][n] = sum_cta part[n][c_in] ; dbt[n] = sum_cta bias[n]
 __global__ void up_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ dwt, float* __restrict__ dbt) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= UPART) return;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < n_cta; ++c) acc += partial[(size_t)c * UPART + i];
-    if (i < UN * 64) dwt[(size_t)(i & 63) * UN + (i >> 6)] = acc; else dbt[i - UN * 64] = acc;
+    const int i = blockIdx.x * 32 + threadIdx.x;
+    const bool valid = i < UPART;
+    const float acc = column_sum(partial, n_cta, UPART, i, valid);
+    if (valid && threadIdx.y == 0) { if (i < UN * 64) dwt[(size_t)(i & 63) * UN + (i >> 6)] = acc; else dbt[i - UN * 64] = acc; }
 }
 
 }  // namespace
@@ -319,6 +317,6 @@ int mvn_tc_upsample_bwd(const float* img, const void* u2_bf16, const void* dctx_
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
     up_bwd_tc_kernel<<<grid, 256, smem, st>>>(mu, md, a);
     if ((rc = mvn_check_launch("upsample_bwd_tc"))) return rc;
-    up_reduce_kernel<<<(UPART + 255) / 256, 256, 0, st>>>(partial, grid, dwt, dbt);
+    up_reduce_kernel<<<(UPART + 31) / 32, dim3(32, RED_SPLIT), 0, st>>>(partial, grid, dwt, dbt);
     return mvn_check_launch("upsample_reduce");
 }
