@@ -120,6 +120,16 @@ int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, const float* 
                          const void* acts, const float* out, const float* dout, void* packed_grads,
                          void* scratch, void* stream);
 
+/* mvn_wavenet_backward with the trainer's loss folded in: instead of d(out) it takes the class targets (B, Tn) int64 and
+ * d(loss) (1 float on the device) and forms d(out) = d(loss)/(B Tn) * (softmax_c(out) - onehot(target)) -- the backward of
+ * F.cross_entropy(forward(...), target) on the PROBABILITIES (movenet/pytorch_lightning_trainer.py:62-65) -- inside the
+ * head kernel, so the (B, A, Tn) gradient tensor is never written or read.  Same gradients as mvn_softmax_ce_bwd followed by
+ * mvn_wavenet_backward.  Only for shapes where mvn_fused_loss_supported() is non-zero (bf16 mode, probabilities). */
+int mvn_fused_loss_supported(const mvn_shape_t* s);
+int mvn_wavenet_backward_loss(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,
+                              const void* acts, const float* out, const int64_t* target, const float* grad_loss,
+                              void* packed_grads, void* scratch, void* stream);
+
 /* The trainer's loss, F.cross_entropy(forward(...), target) (movenet/pytorch_lightning_trainer.py:62-65), i.e. a
  * cross-entropy over the PROBABILITIES (a second softmax), mean over B*T columns, fused:
  *   fwd: loss (1 float) from probs (B,A,T) fp32 and int64 targets (B,T); partials: mvn_softmax_ce_partials floats

@@ -43,6 +43,8 @@ SIGNATURES = {
     "mvn_codes_input": (_I, [_SP, _P, _P, _P]),
     "mvn_wavenet_forward": (_I, [_SP, _P, _P, _P, _P, _P, _P, _P]),
     "mvn_wavenet_backward": (_I, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mvn_fused_loss_supported": (_I, [_SP]),
+    "mvn_wavenet_backward_loss": (_I, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mvn_softmax_ce_partials": (_SZ, [_I, _I]),
     "mvn_softmax_ce_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "mvn_softmax_ce_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),

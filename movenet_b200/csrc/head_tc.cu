@@ -35,7 +35,10 @@ struct HeadArgs {
     const float* skip;   // (B, Tout, S)
     float* out;          // forward: (B, A, Tn)
     const float* probs;  // backward
-    const float* dout;   // backward
+    const float* dout;   // backward: d(out), or null when the loss gradient is formed in the kernel:
+    const long long* target;   //   (B, Tn) class indices and
+    const float* gloss;        //   d(loss) (1 float): d(out) = gloss / (B Tn) * (softmax_c(probs) - onehot(target)),
+                               //   the backward of the trainer's cross_entropy(probabilities, target) (loss.py)
     float* dskip;        // backward: (B, Tout, S)
     float* partial;      // backward
     int B, Tout, Tn, S, logits, tiles_per_clip, n_tiles;
@@ -196,8 +199,8 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
     uint8_t* sONES = sLS + TILE_BYTES;            // 1 KB
     float* sw1 = (float*)(sONES + 1024);          // [S][A]
     float* sb1 = sw1 + S * A;
-    float* sx = sb1 + A;                          // [PARTS][128] exchange: <dp,p> partial sums
-    float* sds = sx + PARTS * 128;                // [PARTS-1][128][S+1] exchange: dskip partial sums
+    float* sx = sb1 + A;                          // [3][PARTS][128] exchange: <dp,p> partial sums (fused loss: Z, <e,p>, p[target])
+    float* sds = sx + 3 * PARTS * 128;            // [PARTS-1][128][S+1] exchange: dskip partial sums
     uint64_t* mma_bar = (uint64_t*)(sds + (PARTS - 1) * 128 * (S + 1) + ((PARTS - 1) * 128 * (S + 1) & 1));
     uint64_t* w_bar = mma_bar + 1;
     uint32_t* tmem_slot = (uint32_t*)(mma_bar + 2);
@@ -246,13 +249,37 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
             const size_t o = ((size_t)b * A + n0) * a.Tn + (live ? j : 0);
             float dot = 0.f;
             float p[32];
+            if (a.dout) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                dz[i] = live ? a.dout[o + (size_t)i * a.Tn] : 0.f;
-                p[i] = (live && !a.logits) ? a.probs[o + (size_t)i * a.Tn] : 0.f;
-                dot = fmaf(dz[i], p[i], dot);
+                for (int i = 0; i < 32; ++i) {
+                    dz[i] = live ? a.dout[o + (size_t)i * a.Tn] : 0.f;
+                    p[i] = (live && !a.logits) ? a.probs[o + (size_t)i * a.Tn] : 0.f;
+                    dot = fmaf(dz[i], p[i], dot);
+                }
+            } else {
+                // fused loss gradient: d(out)_i = gs (e_i / Z - [i == target]), e = exp(probs) (probabilities: no overflow);
+                // the three row sums it needs travel through one exchange
+                const int tg = live ? (int)a.target[(size_t)b * a.Tn + j] - n0 : -1;
+                float z = 0.f, ep = 0.f, pt = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    p[i] = live ? a.probs[o + (size_t)i * a.Tn] : 0.f;
+                    dz[i] = __expf(p[i]);
+                    z += dz[i];
+                    ep = fmaf(dz[i], p[i], ep);
+                    if (i == tg) pt = p[i];
+                }
+                sx[part * 128 + r] = z; sx[(PARTS + part) * 128 + r] = ep; sx[(2 * PARTS + part) * 128 + r] = pt;
+                __syncthreads();
+                z = 0.f; ep = 0.f; pt = 0.f;
+#pragma unroll
+                for (int q = 0; q < PARTS; ++q) { z += sx[q * 128 + r]; ep += sx[(PARTS + q) * 128 + r]; pt += sx[(2 * PARTS + q) * 128 + r]; }
+                const float gs = live ? a.gloss[0] / ((float)a.B * (float)a.Tn) : 0.f, inv = gs / z;
+                dot = ep * inv - gs * pt;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dz[i] = p[i] * (dz[i] * inv - (i == tg ? gs : 0.f) - dot);
             }
-            if (!a.logits) {
+            if (a.dout && !a.logits) {
                 sx[part * 128 + r] = dot;
                 __syncthreads();
                 dot = 0.f;
@@ -443,7 +470,7 @@ __global__ void head_pack_kernel(const float* __restrict__ w2, uint8_t* __restri
 
 template <int A> int fwd_smem(int S) { return A * A * 2 + (A / 64) * TILE_BYTES + (S * A + 2 * A + (A / 32) * 128) * 4 + 64 + 1024; }
 template <int A> int bwd_smem(int S) {
-    return A * A * 2 + (3 * (A / 64) + 1) * TILE_BYTES + 1024 + (S * A + A + (A / 32) * 128 + (A / 32 - 1) * 128 * (S + 1) + 2) * 4 + 64 + 1024;
+    return A * A * 2 + (3 * (A / 64) + 1) * TILE_BYTES + 1024 + (S * A + A + 3 * (A / 32) * 128 + (A / 32 - 1) * 128 * (S + 1) + 2) * 4 + 64 + 1024;
 }
 
 template <int A, int S>
@@ -506,9 +533,11 @@ int mvn_tc_head_fwd(const float* packed, const PackedLayout& P, const Geo& g, co
 }
 
 int mvn_tc_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, const float* probs,
-                    const float* dout, float* dskip, float* pg, float* partial, cudaStream_t st) {
+                    const float* dout, const long long* target, const float* grad_loss, float* dskip, float* pg, float* partial,
+                    cudaStream_t st) {
     HeadArgs a; memset(&a, 0, sizeof(a)); fill_args(a, packed, P, g);
-    a.skip = skip; a.probs = probs; a.dout = dout; a.dskip = dskip; a.partial = partial;
+    a.skip = skip; a.probs = probs; a.dout = dout; a.target = target; a.gloss = grad_loss; a.dskip = dskip; a.partial = partial;
+    MVN_REQUIRE(dout || (target && grad_loss && probs && !g.logits), "head backward: d(out) or (target, d(loss)) on probabilities is required");
     if (a.n_tiles <= 0) return 0;
     const int per_sm = g.A == 64 ? 2 : 1;
     const int grid = a.n_tiles < per_sm * 148 ? a.n_tiles : per_sm * 148;

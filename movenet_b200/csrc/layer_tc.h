@@ -26,7 +26,8 @@ size_t mvn_tc_head_partial_bytes();
 int mvn_tc_head_pack(const float* w2_ref, float* packed, const PackedLayout& P, int A, cudaStream_t st);
 int mvn_tc_head_fwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, float* out, cudaStream_t st);
 int mvn_tc_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, const float* probs,
-                    const float* dout, float* dskip, float* pg, float* partial, cudaStream_t st);
+                    const float* dout, const long long* target, const float* grad_loss, float* dskip, float* pg, float* partial,
+                    cudaStream_t st);
 // causal input conv weight gradient on tensor cores (input_tc.cu), A <= 64, C == 64, gradient given as (P, U)
 int mvn_tc_input_supported(int A, int C);
 int mvn_tc_input_bwd(const float* audio, const int* codes, const unsigned char* dense, const void* p, const void* u,

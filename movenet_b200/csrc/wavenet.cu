@@ -451,14 +451,15 @@ extern "C" int mvn_debug_read(const mvn_shape_t* s, const void* acts, int which,
 
 // ------------------------------------------------------------------------------------------------
 // backward
-static int head_bwd(const Ctx& c, const float* out, const float* dout, float* pg) {
+static int head_bwd(const Ctx& c, const float* out, const float* dout, const long long* target, const float* grad_loss, float* pg) {
     const Geo& g = c.g;
     float* skip = (float*)(c.acts + c.AL.skip); float* a1 = (float*)(c.acts + c.AL.a1);
     float* dzh = (float*)(c.scratch + c.SL.z); float* da1 = (float*)(c.scratch + c.SL.da1); float* dskip = (float*)(c.scratch + c.SL.dskip);
     MVN_CUDA(cudaMemsetAsync(dskip, 0, (size_t)g.B * g.Tout * g.S * 4, c.st));
     if (g.Tn <= 0) return 0;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S))
-        return mvn_tc_head_bwd(c.packed, c.P, g, skip, out, dout, dskip, pg, (float*)(c.scratch + c.SL.tc_partial), c.st);
+        return mvn_tc_head_bwd(c.packed, c.P, g, skip, out, dout, target, grad_loss, dskip, pg, (float*)(c.scratch + c.SL.tc_partial), c.st);
+    MVN_REQUIRE(dout, "the fused loss backward needs the tensor-core head (mvn_fused_loss_supported)");
     const long long rows = (long long)g.B * g.Tn;
     int rc;
     dim3 grid(mvn_cdiv(g.Tn, 32), g.B);
@@ -635,16 +636,41 @@ extern "C" int mvn_layer_bwd(const mvn_shape_t* s, const void* packed, int layer
     return layer_bwd(c, layer, layer + 1 < g.N ? c.scratch + c.SL.dxa : nullptr, c.scratch + c.SL.dxb, pg);
 }
 
+static int backward_impl(const mvn_shape_t* s, const void* packed, const float* audio, const float* video, const void* acts,
+                         const float* out, const float* dout, const long long* target, const float* grad_loss,
+                         void* packed_grads, void* scratch, void* stream, const char* who);
+
 extern "C" int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,
                                     const void* acts, const float* out, const float* dout, void* packed_grads,
                                     void* scratch, void* stream) {
-    Ctx c; int rc = ctx_init(c, s, packed, acts, scratch, stream, "mvn_wavenet_backward"); if (rc) return rc;
-    MVN_REQUIRE(dout && packed && acts && scratch && packed_grads, "mvn_wavenet_backward: null buffer");
-    MVN_REQUIRE(c.g.logits || out, "mvn_wavenet_backward: the probabilities returned by forward are required");
+    MVN_REQUIRE(dout, "mvn_wavenet_backward: null buffer");
+    return backward_impl(s, packed, audio, video, acts, out, dout, nullptr, nullptr, packed_grads, scratch, stream, "mvn_wavenet_backward");
+}
+
+extern "C" int mvn_fused_loss_supported(const mvn_shape_t* s) {
+    Geo g; if (!s || geo_init(g, s)) return 0;
+    return !g.logits && g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S) && g.Tn > 0;
+}
+
+extern "C" int mvn_wavenet_backward_loss(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,
+                                         const void* acts, const float* out, const int64_t* target, const float* grad_loss,
+                                         void* packed_grads, void* scratch, void* stream) {
+    MVN_REQUIRE(target && grad_loss && out, "mvn_wavenet_backward_loss: null buffer");
+    MVN_REQUIRE(mvn_fused_loss_supported(s), "mvn_wavenet_backward_loss: not supported for this shape (mvn_fused_loss_supported)");
+    return backward_impl(s, packed, audio, video, acts, out, nullptr, (const long long*)target, grad_loss, packed_grads, scratch,
+                         stream, "mvn_wavenet_backward_loss");
+}
+
+static int backward_impl(const mvn_shape_t* s, const void* packed, const float* audio, const float* video, const void* acts,
+                         const float* out, const float* dout, const long long* target, const float* grad_loss,
+                         void* packed_grads, void* scratch, void* stream, const char* who) {
+    Ctx c; int rc = ctx_init(c, s, packed, acts, scratch, stream, who); if (rc) return rc;
+    MVN_REQUIRE(packed && acts && scratch && packed_grads, "%s: null buffer", who);
+    MVN_REQUIRE(c.g.logits || out, "%s: the probabilities returned by forward are required", who);
     const Geo& g = c.g;
     float* pg = (float*)packed_grads;
     MVN_CUDA(cudaMemsetAsync(pg, 0, c.P.total * 4, c.st));
-    if ((rc = head_bwd(c, out, dout, pg))) return rc;
+    if ((rc = head_bwd(c, out, dout, target, grad_loss, pg))) return rc;
     if (g.video) MVN_CUDA(cudaMemsetAsync(c.scratch + c.SL.dctx, 0, (size_t)g.B * g.T * g.C * 4, c.st));
     const void* dctx_final = c.scratch + c.SL.dctx; int dctx_dtype = MVN_F32;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {

@@ -45,6 +45,46 @@ class _SoftmaxCrossEntropy(torch.autograd.Function):
         return dprobs, None
 
 
+class _FusedLoss(torch.autograd.Function):
+    """loss = cross_entropy(probabilities, target) as ONE autograd node over the network's parameters: its backward runs
+    the whole network backward with the loss gradient formed inside the head kernel (mvn_wavenet_backward_loss), so the
+    (B, A, T) gradient of the probabilities is never materialised.  The probabilities enter detached, so their own autograd
+    node is not part of this loss's graph (it still serves any other use of the tensor)."""
+
+    @staticmethod
+    def forward(ctx, state, probs, target, *params):
+        B, A, T = probs.shape
+        loss = torch.empty((), dtype=torch.float32, device=probs.device)
+        partials = torch.empty(_lib.load().mvn_softmax_ce_partials(B, T), dtype=torch.float32, device=probs.device)
+        with torch.cuda.device(probs.device):
+            _lib.call("mvn_softmax_ce_fwd", probs.data_ptr(), target.data_ptr(), B, A, T, partials.data_ptr(),
+                      loss.data_ptr(), _stream())
+        ctx.state = state
+        ctx.save_for_backward(target, probs)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        st = ctx.state
+        target, probs = ctx.saved_tensors
+        if st.acts is None:
+            raise RuntimeError("the activations of this forward pass were already consumed by a backward pass")
+        module, bufs, audio, video = st.module, st.bufs, st.audio, st.video
+        g = grad_loss.contiguous().float()
+        pg = bufs.get_packed_grads()
+        with torch.cuda.device(audio.device):
+            _lib.call("mvn_wavenet_backward_loss", C.byref(bufs.shape), bufs.packed.data_ptr(),
+                      0 if audio.dim() == 2 else audio.data_ptr(), 0 if video is None else video.data_ptr(),
+                      st.acts.data_ptr(), probs.data_ptr(), target.data_ptr(), g.data_ptr(), pg.data_ptr(),
+                      bufs.get_scratch().data_ptr(), _stream())
+            st.acts = None
+            flat, views = module._flat_grads(st.has_video, audio.device)
+            offs = module._grad_offsets(st.has_video, audio.device)
+            _lib.call("mvn_unpack_grads", C.byref(bufs.shape), pg.data_ptr(), flat.data_ptr(), offs.data_ptr(), _stream())
+        module._reduce_grads(flat)
+        return (None, None, None, *views)
+
+
 def softmax_cross_entropy(probs: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """mean_{b,t} [ logsumexp_c probs[b,c,t] - probs[b,target[b,t],t] ]  ==  F.cross_entropy(probs, target)"""
     return _SoftmaxCrossEntropy.apply(probs.as_subclass(torch.Tensor).contiguous(), target.contiguous())
@@ -71,5 +111,12 @@ class ProbabilityTensor(torch.Tensor):
     def __torch_function__(cls, func, types, args=(), kwargs=None):
         kwargs = kwargs or {}
         if func is F.cross_entropy and _fast_path_ok(args, kwargs):
-            return softmax_cross_entropy(args[0], args[1])
+            x, t = args
+            st = getattr(x, "_mvn_state", None)
+            if (st is not None and st.fused_loss_ok and st.acts is not None and st.out_ptr == x.data_ptr()
+                    and torch.is_grad_enabled() and x.requires_grad
+                    and os.environ.get("MOVENET_B200_FUSED_LOSS_BWD", "1") != "0"):
+                # the probabilities enter detached: this node differentiates the loss w.r.t. the parameters itself
+                return _FusedLoss.apply(st, x.detach().as_subclass(torch.Tensor), t.contiguous(), *st.module._param_list())
+            return softmax_cross_entropy(x, t)
         return super().__torch_function__(func, types, args, kwargs)

@@ -71,6 +71,14 @@ class _Buffers:
         return self.packed_grads
 
 
+class _ForwardState:
+    """what a backward pass needs from the forward pass; shared by the network's autograd node and, when the trainer's loss
+    is taken straight from the returned probabilities, by the fused loss node (loss.py)"""
+    # (never the output tensor itself: output -> grad_fn -> this object -> output would be a reference cycle that keeps a
+    # whole step's activations alive until the garbage collector runs)
+    __slots__ = ("module", "bufs", "acts", "audio", "video", "out_ptr", "has_video", "fused_loss_ok")
+
+
 class _WaveNetFunction(torch.autograd.Function):
     """forward()/backward() of the whole network as ONE autograd node."""
 
@@ -88,23 +96,30 @@ class _WaveNetFunction(torch.autograd.Function):
         _lib.call("mvn_wavenet_forward", C.byref(shape), bufs.packed.data_ptr(), 0 if is_codes else audio.data_ptr(),
                   0 if video is None else video.data_ptr(), acts.data_ptr(), out.data_ptr(),
                   bufs.get_scratch().data_ptr(), _stream())
-        ctx.module, ctx.bufs, ctx.acts = module, bufs, acts
-        ctx.has_video = video is not None
-        ctx.save_for_backward(audio, video, out)
+        st = _ForwardState()
+        st.module, st.bufs, st.acts, st.audio, st.video, st.out_ptr = module, bufs, acts, audio, video, out.data_ptr()
+        st.has_video = video is not None
+        st.fused_loss_ok = bool(_lib.load().mvn_fused_loss_supported(C.byref(shape)))
+        ctx.state = st
+        ctx.save_for_backward(out)
+        module._fwd_state = st
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        module, bufs = ctx.module, ctx.bufs
-        audio, video, out = ctx.saved_tensors
+        st = ctx.state
+        module, bufs, audio, video = st.module, st.bufs, st.audio, st.video
+        (out,) = ctx.saved_tensors
+        if st.acts is None:
+            raise RuntimeError("the activations of this forward pass were already consumed by a backward pass")
         dout = dout.contiguous().float()
         pg = bufs.get_packed_grads()
         _lib.call("mvn_wavenet_backward", C.byref(bufs.shape), bufs.packed.data_ptr(), 0 if audio.dim() == 2 else audio.data_ptr(),
-                  0 if video is None else video.data_ptr(), ctx.acts.data_ptr(), out.data_ptr(), dout.data_ptr(),
+                  0 if video is None else video.data_ptr(), st.acts.data_ptr(), out.data_ptr(), dout.data_ptr(),
                   pg.data_ptr(), bufs.get_scratch().data_ptr(), _stream())
-        ctx.acts = None
-        flat, views = module._flat_grads(ctx.has_video, audio.device)
-        offs = module._grad_offsets(ctx.has_video, audio.device)
+        st.acts = None
+        flat, views = module._flat_grads(st.has_video, audio.device)
+        offs = module._grad_offsets(st.has_video, audio.device)
         _lib.call("mvn_unpack_grads", C.byref(bufs.shape), pg.data_ptr(), flat.data_ptr(), offs.data_ptr(), _stream())
         module._reduce_grads(flat)
         return (None, None, None, None, None, *views)
@@ -216,7 +231,12 @@ class WaveNet(nn.Module):
             out = _WaveNetFunction.apply(self, audio, video, bool(remove_last), not output_unnormalized,
                                          *self._param_list())
         # probabilities know the fused route for the trainer's F.cross_entropy(output, target) (loss.py)
-        return out.as_subclass(ProbabilityTensor) if output_unnormalized else out
+        st = self.__dict__.pop("_fwd_state", None)
+        if not output_unnormalized:
+            return out
+        out = out.as_subclass(ProbabilityTensor)
+        out._mvn_state = st          # lets F.cross_entropy(out, target) run the loss-fused backward (loss.py)
+        return out
 
     @torch.no_grad()
     def generate(self, audio: AudioTensor, video: Optional[VideoTensor] = None, global_features=None,

@@ -154,3 +154,43 @@ def test_bf16_non_one_hot_audio():
     with torch.no_grad():
         a, b = m32(audio, output_unnormalized=False), m16(audio, output_unnormalized=False)
     assert (a - b).abs().max().item() <= LOGIT_RTOL * a.abs().max().item()
+
+
+@pytest.mark.parametrize("name", ["cfg00", "cfg04_short"])
+def test_loss_fused_backward_matches_the_two_step_route(name, monkeypatch):
+    """F.cross_entropy(model(audio), target).backward() runs ONE backward with the loss gradient formed inside the head
+    kernel (mvn_wavenet_backward_loss); with MOVENET_B200_FUSED_LOSS_BWD=0 the same call materialises d(probabilities)
+    (mvn_softmax_ce_bwd) and feeds it to mvn_wavenet_backward.  Same function, same bf16 arithmetic downstream."""
+    fx = load_golden(name)
+    audio = golden_audio(fx).cuda()
+    grads = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("MOVENET_B200_FUSED_LOSS_BWD", fused)
+        m = build(fx, "bf16")
+        out = m(audio)
+        target = audio[:, :, m.receptive_fields:].argmax(1)
+        loss = F.cross_entropy(out, target)
+        assert type(loss.grad_fn).__name__.startswith("_FusedLoss" if fused == "1" else "_SoftmaxCrossEntropy")
+        (3.0 * loss).backward()          # a non-unit d(loss) must flow through both routes
+        grads.append({k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+    assert grads[0].keys() == grads[1].keys()
+    for k in grads[0]:
+        assert rel_l2(grads[0][k], grads[1][k]) < 2e-2, (k, rel_l2(grads[0][k], grads[1][k]))
+
+
+def test_loss_fused_route_only_for_the_plain_call():
+    """any other use of the returned probabilities (a slice, non-default arguments) takes torch's ordinary path and still
+    differentiates through the network's own node"""
+    fx = load_golden("cfg00")
+    audio = golden_audio(fx).cuda()
+    m = build(fx, "bf16")
+    out = m(audio)
+    target = audio[:, :, m.receptive_fields:].argmax(1)
+    fused = F.cross_entropy(out, target)
+    plain = F.cross_entropy(out.as_subclass(torch.Tensor), target)
+    smoothed = F.cross_entropy(out, target, label_smoothing=0.1)
+    assert type(fused.grad_fn).__name__.startswith("_FusedLoss")
+    assert "Fused" not in type(plain.grad_fn).__name__ and "Fused" not in type(smoothed.grad_fn).__name__
+    assert abs(fused.item() - plain.item()) <= 1e-5 * abs(plain.item())
+    plain.backward()
+    assert m.causal_conv.conv.weight.grad is not None
