@@ -14,12 +14,38 @@
 //           per-CTA partials and reduced in a fixed order:
 //             A == 64 : one chain  [dz | da1]^T . [lrelu(a1) | lrelu(skip)]   (M = 128 = 64 + 64)
 //             A == 128: two chains  dz^T . lrelu(a1)   and   da1^T . lrelu(skip)
+#include <cstdio>
+#include <cstdlib>
 #include "tc_common.cuh"
 #include "layer_tc.h"
 
 using namespace tc;
 
 namespace {
+
+// Instrumented build (MOVENET_B200_NVCC_EXTRA=-DMVN_PHASE_CLOCKS=1): clock64() stamps of tiles 2..4 of CTA 0, thread 0, in the
+// head forward (role 0) and backward (role 1) kernels; printed by the host wrappers when MVN_PROF is set.
+#ifndef MVN_PHASE_CLOCKS
+#define MVN_PHASE_CLOCKS 0
+#endif
+#if MVN_PHASE_CLOCKS
+__device__ unsigned long long g_clkh[2][3][12];
+#define CLK(role, i) do { if (blockIdx.x == 0 && tid == 0 && it >= 2 && it < 5) g_clkh[role][it - 2][i] = clock64(); } while (0)
+static void print_clocks(int role, const char* name) {
+    if (!getenv("MVN_PROF")) return;
+    cudaDeviceSynchronize();
+    unsigned long long h[2][3][12];
+    cudaMemcpyFromSymbol(h, g_clkh, sizeof(h));
+    for (int i = 0; i < 3; ++i) {
+        fprintf(stderr, "CLKH %s tile%d:", name, i + 2);
+        for (int j = 0; j < 12; ++j) fprintf(stderr, " %lld", h[role][i][j] ? (long long)(h[role][i][j] - h[role][0][0]) : -1LL);
+        fprintf(stderr, "\n");
+    }
+}
+#else
+#define CLK(role, i) do {} while (0)
+static void print_clocks(int, const char*) {}
+#endif
 
 template <int A> struct HP {      // per-CTA partial gradients
     // A == 64 : D_w[128][128] (rows dz|da1, cols lrelu(a1)|lrelu(skip)) + 128 bias sums
@@ -105,11 +131,14 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_fwd_tc_kernel(con
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t idesc = umma_idesc_major(TILE_T, A, 0, 0);
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
         const int b = tile / a.tiles_per_clip, j = (tile - b * a.tiles_per_clip) * TILE_T + r;
         const bool live = j < a.Tn;
+        CLK(0, 0);
         float ls[S];
         {
             const float* src = a.skip + ((size_t)b * a.Tout + (live ? j : 0)) * S;
@@ -123,21 +152,28 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_fwd_tc_kernel(con
         head_a1<A, S>(sw1, sb1, ls, n0, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
+        CLK(0, 1);
         store_part_row(sA, r, part, v);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        CLK(0, 2);
+        if (warp_u == 0) {             // warp-uniform issue through one elected lane (tc_common.cuh)
             tc_fence_after();
+            const uint64_t kA = umma_desc(smem_u32(sA)), kW2 = umma_desc(smem_u32(sW2));
+            if (elect_one()) {
 #pragma unroll
-            for (int kc = 0; kc < KC; ++kc)
+                for (int kc = 0; kc < KC; ++kc)
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma(tmem, umma_desc(smem_u32(sA + kc * TILE_BYTES) + k * 32), umma_desc(smem_u32(sW2 + kc * A * 128) + k * 32), idesc,
-                         (kc | k) != 0);
-            umma_commit(mma_bar);
+                    for (int k = 0; k < 4; ++k)
+                        umma(tmem_u, desc_adv(kA, kc * TILE_BYTES + k * 32), desc_adv(kW2, kc * A * 128 + k * 32), idesc, (kc | k) != 0);
+                umma_commit(mma_bar);
+            }
+            __syncwarp();
         }
+        CLK(0, 3);
         mbar_wait(mma_bar, it & 1);
+        CLK(0, 4);
         tc_fence_after();
         uint32_t z0[16], z1[16];
         tmem_ld16(tmem + lane_base + n0, z0);
@@ -149,6 +185,7 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_fwd_tc_kernel(con
             v[i] = __uint_as_float(z0[i]) + sb2[n0 + i]; v[16 + i] = __uint_as_float(z1[i]) + sb2[n0 + 16 + i];
             m = fmaxf(m, fmaxf(v[i], v[16 + i]));
         }
+        CLK(0, 5);
         if (!a.logits) {      // softmax over all A channels: a row's channel groups live in threads r, r + 128, ...
             sx[part * 128 + r] = m;
             __syncthreads();
@@ -167,13 +204,16 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_fwd_tc_kernel(con
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= inv;
         }
+        CLK(0, 6);
         if (live) {
             float* dst = a.out + ((size_t)b * A + n0) * a.Tn + j;
 #pragma unroll
             for (int i = 0; i < 32; ++i) dst[(size_t)i * a.Tn] = v[i];
         }
+        CLK(0, 7);
         tc_fence_before();
         __syncthreads();       // every thread has read its TMEM row and the A tiles are free again
+        CLK(0, 8);
     }
     tc_fence_before();
     __syncthreads();
@@ -226,12 +266,29 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
     const uint32_t iW = umma_idesc_major(TILE_T, 128, 1, 1);
     const uint32_t iW1 = umma_idesc_major(TILE_T, 64, 1, 1);
     const uint32_t iB = umma_idesc_major(TILE_T, 16, 1, 1);
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
         const int b = tile / a.tiles_per_clip, j = (tile - b * a.tiles_per_clip) * TILE_T + r;
         const bool live = j < a.Tn;
+        {   // the next tile's probabilities / d(out) rows: towards L2 now (32 channel rows, one 128-byte line per warp each)
+            const int nt = tile + gridDim.x;
+            if (nt < a.n_tiles && (tid & 31) == 0) {
+                const int nb = nt / a.tiles_per_clip, nj = (nt - nb * a.tiles_per_clip) * TILE_T + r;
+                if (nj < a.Tn) {
+                    const size_t o = ((size_t)nb * A + n0) * a.Tn + nj;
+#pragma unroll 8
+                    for (int i = 0; i < 32; ++i) {
+                        if (!a.logits) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.probs + o + (size_t)i * a.Tn));
+                        if (a.dout) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dout + o + (size_t)i * a.Tn));
+                    }
+                }
+            }
+        }
         // ---- loads first (their latency overlaps the previous tile's weight-gradient MMAs) ----------
+        CLK(1, 0);
         float ls[S];
         unsigned long long skip_pos = 0;
         {
@@ -289,12 +346,15 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
                 for (int i = 0; i < 32; ++i) dz[i] = p[i] * (dz[i] - dot);
             }
         }
+        CLK(1, 1);
         float a1[32];
         head_a1<A, S>(sw1, sb1, ls, n0, a1);
         uint32_t a1_pos = 0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) { a1_pos |= (uint32_t)(a1[i] > 0.f) << i; a1[i] = lrelu(a1[i]); }
+        CLK(1, 2);
         if (it) { mbar_wait(w_bar, (it - 1) & 1); tc_fence_after(); }      // previous tile's MMAs are done with the tiles
+        CLK(1, 3);
         store_part_row(sDZ, r, part, dz);
         store_part_row(sLA, r, part, a1);
         if (part == 0) {
@@ -307,16 +367,21 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0) {
             tc_fence_after();
-            // da_pre[t][k] = sum_n dz[t][n] W2[n][k] : contraction over the image's ROWS, 16 per step
+            const uint64_t kDZ = umma_desc(smem_u32(sDZ)), mW2 = umma_desc_mn(smem_u32(sW2), A * 128);
+            if (elect_one()) {
+                // da_pre[t][k] = sum_n dz[t][n] W2[n][k] : contraction over the image's ROWS, 16 per step
 #pragma unroll
-            for (int s = 0; s < A / 16; ++s)
-                umma(tmem + DA_COL, umma_desc(smem_u32(sDZ + (s >> 2) * TILE_BYTES) + (s & 3) * 32),
-                     umma_desc_mn(smem_u32(sW2) + s * 2048, A * 128), iG, s != 0);
-            umma_commit(mma_bar);
+                for (int s = 0; s < A / 16; ++s)
+                    umma(tmem_u + DA_COL, desc_adv(kDZ, (s >> 2) * TILE_BYTES + (s & 3) * 32), desc_adv(mW2, s * 2048), iG, s != 0);
+                umma_commit(mma_bar);
+            }
+            __syncwarp();
         }
+        CLK(1, 4);
         mbar_wait(mma_bar, it & 1);
+        CLK(1, 5);
         tc_fence_after();
         // ---- da1 = (dz W2) * lrelu'(a1); dskip = (da1 W1) * lrelu'(skip) ------------------------------
         float da[32];
@@ -348,29 +413,34 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
 #pragma unroll
             for (int s = 0; s < S; ++s) sds[((part - 1) * 128 + r) * (S + 1) + s] = ls[s];
         }
+        CLK(1, 6);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        CLK(1, 7);
+        if (warp_u == 0) {
             tc_fence_after();
             const uint32_t acc0 = it != 0;
             const uint64_t ones = umma_desc_mn_plain(smem_u32(sONES), 256, 128);
+            const uint64_t mDZ = umma_desc_mn(smem_u32(sDZ), TILE_BYTES), mLA = umma_desc_mn(smem_u32(sLA), TILE_BYTES),
+                           mDA = umma_desc_mn(smem_u32(sDA), TILE_BYTES), mLS = umma_desc_mn(smem_u32(sLS), TILE_BYTES);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t acc = acc0 | (k != 0);
-                const uint64_t dz_mn = umma_desc_mn(smem_u32(sDZ) + k * 2048, TILE_BYTES);
-                if constexpr (A == 64) {          // [dz|da1]^T . [la|ls]
-                    umma(tmem + W_COL, dz_mn, umma_desc_mn(smem_u32(sLA) + k * 2048, TILE_BYTES), iW, acc);
-                    umma(tmem + B_COL, dz_mn, ones, iB, acc);
-                } else {                          // dz^T . la ; da1^T . ls ; bias sums of both
-                    const uint64_t da_mn = umma_desc_mn(smem_u32(sDA) + k * 2048, TILE_BYTES);
-                    umma(tmem + W_COL, dz_mn, umma_desc_mn(smem_u32(sLA) + k * 2048, TILE_BYTES), iW, acc);
-                    umma(tmem + W1_COL, da_mn, umma_desc_mn(smem_u32(sLS) + k * 2048, TILE_BYTES), iW1, acc);
-                    umma(tmem + B_COL, dz_mn, ones, iB, acc);
-                    umma(tmem + B_COL + 16, da_mn, ones, iB, acc);
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t acc = acc0 | (k != 0);
+                    if constexpr (A == 64) {          // [dz|da1]^T . [la|ls]
+                        umma(tmem_u + W_COL, desc_adv(mDZ, k * 2048), desc_adv(mLA, k * 2048), iW, acc);
+                        umma(tmem_u + B_COL, desc_adv(mDZ, k * 2048), ones, iB, acc);
+                    } else {                          // dz^T . la ; da1^T . ls ; bias sums of both
+                        umma(tmem_u + W_COL, desc_adv(mDZ, k * 2048), desc_adv(mLA, k * 2048), iW, acc);
+                        umma(tmem_u + W1_COL, desc_adv(mDA, k * 2048), desc_adv(mLS, k * 2048), iW1, acc);
+                        umma(tmem_u + B_COL, desc_adv(mDZ, k * 2048), ones, iB, acc);
+                        umma(tmem_u + B_COL + 16, desc_adv(mDA, k * 2048), ones, iB, acc);
+                    }
                 }
+                umma_commit(w_bar);
             }
-            umma_commit(w_bar);
+            __syncwarp();
         }
         if (part == 0 && live) {
             float* dst = a.dskip + ((size_t)b * a.Tout + j) * S;
@@ -387,7 +457,9 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
                 *(float4*)(dst + s) = make_float4(o[0], o[1], o[2], o[3]);
             }
         }
+        CLK(1, 8);
         __syncthreads();           // sds / sx are reused by the next tile
+        CLK(1, 9);
     }
     if (it) { mbar_wait(w_bar, (it - 1) & 1); }
     tc_fence_after();
@@ -529,6 +601,7 @@ int mvn_tc_head_fwd(const float* packed, const PackedLayout& P, const Geo& g, co
     const int per_sm = g.A == 64 ? 4 : 1;
     const int grid = a.n_tiles < per_sm * 148 ? a.n_tiles : per_sm * 148;
     HEAD_DISPATCH(launch_fwd, a, grid, st);
+    print_clocks(0, "fwd");
     return mvn_check_launch("head_fwd_tc");
 }
 
@@ -542,6 +615,7 @@ int mvn_tc_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, co
     const int per_sm = g.A == 64 ? 2 : 1;
     const int grid = a.n_tiles < per_sm * 148 ? a.n_tiles : per_sm * 148;
     HEAD_DISPATCH(launch_bwd, a, grid, st);
+    print_clocks(1, "bwd");
     int rc = mvn_check_launch("head_bwd_tc");
     if (rc) return rc;
     if (g.A == 64) head_reduce_kernel<64><<<(HP<64>::floats + 31) / 32, dim3(32, RED_SPLIT), 0, st>>>(partial, grid, pg, P, g.S);

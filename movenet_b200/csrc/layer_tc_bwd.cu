@@ -55,6 +55,7 @@ struct BwdArgs {
     const float* dskip;   // (B, Tout, S) fp32
     float* partial;       // [grid][PART_FLOATS]
     int B, T, Tout, RF, S, N2, dil, dil_up, nchunks, tiles_per_clip, n_tiles;
+    int zero_in;          // the incoming stream gradient (P, U) and context-gradient sum (Q) are zero (last layer): never loaded
 };
 
 __host__ __device__ inline int bwd_tiles_off(int nc, int N2) { return smem_a_off(nc, N2); }
@@ -115,6 +116,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     // constant tiles: DSK is zero outside the S live channels, ONES is all bf16 1.0
     for (int i = tid; i < TILE_BYTES / 16; i += N_THREADS) ((uint4*)sDSK)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < 1024 / 4; i += N_THREADS) ((uint32_t*)sONES)[i] = 0x3F803F80u;
+    if (a.zero_in)        // U | P are adjacent and stay zero for the whole kernel
+        for (int i = tid; i < 2 * TILE_BYTES / 16; i += N_THREADS) ((uint4*)sU)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -164,8 +167,10 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         if (leader) {
             const int lb = (int)blockIdx.x / a.tiles_per_clip, l0 = ((int)blockIdx.x - lb * a.tiles_per_clip) * TILE_T;
             load_a_tiles(lb, l0);
-            load_tile(sDXS, &map_p, P_IN, lb, l0);
-            load_tile(sU, &map_u, U_IN, lb, l0 + a.dil_up);
+            if (!a.zero_in) {
+                load_tile(sDXS, &map_p, P_IN, lb, l0);
+                load_tile(sU, &map_u, U_IN, lb, l0 + a.dil_up);
+            }
         }
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -192,20 +197,25 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             if (leader && has_next) {              // start pulling the next tile into L2 now
                 tma_prefetch_3d(&map_x, 0, n0 - a.dil, nb);
                 tma_prefetch_3d(&map_x, 0, n0, nb);
-                if (nc == 3) { tma_prefetch_3d(&map_ctx, 0, n0, nb); tma_prefetch_3d(&map_q, 0, n0, nb); }
-                tma_prefetch_3d(&map_p, 0, n0, nb);
-                tma_prefetch_3d(&map_u, 0, n0 + a.dil_up, nb);
+                if (nc == 3) tma_prefetch_3d(&map_ctx, 0, n0, nb);
+                if (!a.zero_in) {
+                    if (nc == 3) tma_prefetch_3d(&map_q, 0, n0, nb);
+                    tma_prefetch_3d(&map_p, 0, n0, nb);
+                    tma_prefetch_3d(&map_u, 0, n0 + a.dil_up, nb);
+                }
             }
             if (leader) {
                 tma_wait_read0();     // the previous tile's P'/U'/Q' stores have left DZ0 / DZ1 / Q  (ordered before G2's
                                       // commit: the workers write DZ again only after they have seen G2)
-                if (nc == 3) load_tile(sQ, &map_q, Q_IN, b, t0);                     // needed by epilogue 2 only
+                if (nc == 3 && !a.zero_in) load_tile(sQ, &map_q, Q_IN, b, t0);       // needed by epilogue 2 only
             }
             // G2: d(gated) = (P + U) . Wr + dskip . Ws as three accumulating products (no pre-sum pass): contraction over
             // the image's ROWS (c_out | s) -> B is MN-major.  Needs only the loads and the DSK tile, so it runs next to G1.
             CLKC(3);
-            mbar_wait(bar + P_IN, ph);
-            mbar_wait(bar + U_IN, ph);
+            if (!a.zero_in) {
+                mbar_wait(bar + P_IN, ph);
+                mbar_wait(bar + U_IN, ph);
+            }
             CLKC(4);
             mbar_wait(bar + E_DSK, ph);
             CLKC(5);
@@ -277,7 +287,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 CLKC(14);
                 mbar_wait(bar + WALL, ph);         // W2 no longer reads the P and U tiles
                 CLKC(15);
-                if (leader) {
+                if (leader && !a.zero_in) {
                     load_tile(sDXS, &map_p, P_IN, nb, n0);
                     load_tile(sU, &map_u, U_IN, nb, n0 + a.dil_up);
                 }
@@ -403,11 +413,12 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + 128 + 16 * half, v);
                 CLKW(7);
-                mbar_wait(bar + Q_IN, ph);
+                if (!a.zero_in) mbar_wait(bar + Q_IN, ph);
                 CLKW(8);
                 uint4* p0 = (uint4*)(sQ + o0);
                 uint4* p1 = (uint4*)(sQ + o1);
-                const uint4 x0 = *p0, x1 = *p1;
+                const uint4 zz = make_uint4(0, 0, 0, 0);
+                const uint4 x0 = a.zero_in ? zz : *p0, x1 = a.zero_in ? zz : *p1;
                 const uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                 tmem_ld_wait();
                 uint32_t o[8];
@@ -534,8 +545,9 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     int rc;
     if ((rc = make_act_map(&mx, x_in, g.B, g.T))) return rc;
     if ((rc = make_act_map(&mc, g.video ? ctx : x_in, g.B, g.T))) return rc;
-    if ((rc = make_act_map(&mp, p_in, g.B, g.T))) return rc;
-    if ((rc = make_act_map(&mu, u_in, g.B, g.T))) return rc;
+    MVN_REQUIRE((p_in == nullptr) == (u_in == nullptr), "tensor-core backward kernel: P and U come together");
+    if ((rc = make_act_map(&mp, p_in ? p_in : x_in, g.B, g.T))) return rc;      // p_in == u_in == null: zero incoming gradient
+    if ((rc = make_act_map(&mu, u_in ? u_in : x_in, g.B, g.T))) return rc;
     if ((rc = make_act_map(&mpo, p_out, g.B, g.T))) return rc;
     if ((rc = make_act_map(&muo, u_out, g.B, g.T))) return rc;
     if ((rc = make_act_map(&mq, g.video ? q_in : x_in, g.B, g.T))) return rc;
@@ -544,6 +556,7 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     a.img = lw + P.oTc; a.dskip = dskip; a.partial = partial;
     a.B = g.B; a.T = g.T; a.Tout = g.Tout; a.RF = g.RF; a.S = g.S; a.N2 = ((g.C + g.S + 15) / 16) * 16;
     a.dil = g.dil[layer]; a.dil_up = layer + 1 < g.N ? g.dil[layer + 1] : 0;
+    a.zero_in = p_in == nullptr;
     a.nchunks = g.video ? 3 : 2;
     a.tiles_per_clip = (g.T + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
     const int smem = bwd_smem_total(a.nchunks, a.N2) + 1024;

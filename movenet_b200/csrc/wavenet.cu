@@ -671,21 +671,23 @@ static int backward_impl(const mvn_shape_t* s, const void* packed, const float* 
     float* pg = (float*)packed_grads;
     MVN_CUDA(cudaMemsetAsync(pg, 0, c.P.total * 4, c.st));
     if ((rc = head_bwd(c, out, dout, target, grad_loss, pg))) return rc;
-    if (g.video) MVN_CUDA(cudaMemsetAsync(c.scratch + c.SL.dctx, 0, (size_t)g.B * g.T * g.C * 4, c.st));
+    const bool tc_layers = g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video);
+    if (g.video && !tc_layers) MVN_CUDA(cudaMemsetAsync(c.scratch + c.SL.dctx, 0, (size_t)g.B * g.T * g.C * 4, c.st));
     const void* dctx_final = c.scratch + c.SL.dctx; int dctx_dtype = MVN_F32;
-    if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
+    if (tc_layers) {
         // tensor-core path: the stream gradient travels as (P, U), see layer_tc_bwd.cu
         void* Pb[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};
         void* Ub[2] = {c.scratch + c.SL.dgated, c.scratch + c.SL.dz};
         const size_t nb = (size_t)g.B * g.T * g.C * g.es;
-        MVN_CUDA(cudaMemsetAsync(Pb[0], 0, nb, c.st));     // the last layer's residual output is discarded: zero gradient
-        MVN_CUDA(cudaMemsetAsync(Ub[0], 0, nb, c.st));
-        // running sum of the context gradient, bf16, ping-pong inside the (zeroed) fp32 dctx slot
+        // the last layer's residual output is discarded: its incoming (P, U, Q) are zero and are never read (null pointers)
+        // running sum of the context gradient, bf16, ping-pong inside the fp32 dctx slot
         void* Qb[2] = {c.scratch + c.SL.dctx, c.scratch + c.SL.dctx + nb};
         int cur = 0;
         for (int l = g.N - 1; l >= 0; --l) {
             float* lg = pg + c.P.layer0 + (size_t)l * c.P.layer_stride;
-            if ((rc = mvn_tc_layer_bwd(c.x(l), g.video ? c.acts + c.AL.ctx : nullptr, Pb[cur], Ub[cur], Pb[cur ^ 1], Ub[cur ^ 1],
+            const bool first = l == g.N - 1;
+            if ((rc = mvn_tc_layer_bwd(c.x(l), g.video ? c.acts + c.AL.ctx : nullptr, first ? nullptr : Pb[cur], first ? nullptr : Ub[cur],
+                                       Pb[cur ^ 1], Ub[cur ^ 1],
                                        (const float*)(c.scratch + c.SL.dskip), Qb[cur], Qb[cur ^ 1], c.lw(l), lg,
                                        (float*)(c.scratch + c.SL.tc_layer_partial + (size_t)l * mvn_tc_bwd_partial_bytes()), c.P, g, l,
                                        c.st))) return rc;
