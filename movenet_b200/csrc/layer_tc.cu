@@ -99,6 +99,8 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_launch();
+    griddep_wait();              // everything above overlapped the previous kernel's tail; its output is read from here on
     mbar_wait(full_bar, 0);
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -314,6 +316,6 @@ int mvn_tc_layer_fwd(const void* x_in, const void* ctx, void* x_out, float* skip
     }
     int grid = 2 * 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    layer_fwd_tc_kernel<<<grid, 256, smem, st>>>(map_x, map_ctx, map_out, a);
+    MVN_CUDA(launch_pdl(layer_fwd_tc_kernel, grid, 256, smem, st, map_x, map_ctx, map_out, a));
     return mvn_check_launch("layer_fwd_tc");
 }

@@ -122,6 +122,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    griddep_launch();
+    griddep_wait();              // everything above overlapped the previous kernel's tail; its output is read from here on
     mbar_wait(bar + IMG, 0);
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -568,7 +570,7 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     }
     int grid = 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    layer_bwd_tc_kernel<<<grid, N_THREADS, smem, st>>>(mx, mc, mp, mu, mpo, muo, mq, mqo, a);
+    MVN_CUDA(launch_pdl(layer_bwd_tc_kernel, grid, N_THREADS, smem, st, mx, mc, mp, mu, mpo, muo, mq, mqo, a));
     (void)lg;
 #if MVN_PHASE_CLOCKS
     if (getenv("MVN_PROF")) {
