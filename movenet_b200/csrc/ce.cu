@@ -10,6 +10,7 @@
 
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ p, const long long* __restrict__ target,
                                                      int A, int T, float* __restrict__ partial) {
+    MVN_PDL_PROLOGUE();
     const int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     float loss = 0.f;
     if (t < T) {
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ p
 }
 
 __global__ void ce_finish_kernel(const float* __restrict__ partial, int n, float inv_count, float* __restrict__ loss) {
+    MVN_PDL_PROLOGUE();
     __shared__ double red[256];
     double acc = 0.0;
     for (int i = threadIdx.x; i < n; i += 256) acc += (double)partial[i];
@@ -66,10 +68,10 @@ extern "C" int mvn_softmax_ce_fwd(const float* probs, const int64_t* target, int
     MVN_REQUIRE(probs && target && partials && loss && B > 0 && A > 0 && T > 0, "mvn_softmax_ce_fwd: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((T + 255) / 256, B);
-    ce_fwd_kernel<<<grid, 256, 0, st>>>(probs, (const long long*)target, A, T, partials);
+    MVN_CUDA(mvn_launch_pdl(ce_fwd_kernel, dim3(grid), dim3(256), (size_t)(0), st, probs, (const long long*)target, A, T, partials));
     int rc = mvn_check_launch("ce_fwd");
     if (rc) return rc;
-    ce_finish_kernel<<<1, 256, 0, st>>>(partials, (int)(grid.x * grid.y), 1.f / ((float)B * (float)T), loss);
+    MVN_CUDA(mvn_launch_pdl(ce_finish_kernel, dim3(1), dim3(256), (size_t)(0), st, partials, (int)(grid.x * grid.y), 1.f / ((float)B * (float)T), loss));
     return mvn_check_launch("ce_finish");
 }
 

@@ -32,6 +32,26 @@ int mvn_check_launch(const char* what);
         }                                                                      \
     } while (0)
 
+// Programmatic dependent launch: a kernel launched with mvn_launch_pdl() may be scheduled while the kernel before it in
+// the stream is still draining its last CTAs (its launch latency and prologue overlap that tail); it must call
+// mvn_griddep_wait() before it touches anything that kernel wrote.  mvn_griddep_launch() (issued by every CTA at its
+// start: the trigger fires once ALL CTAs of the grid are running or done) lets the NEXT kernel's CTAs be scheduled as
+// SM resources free up.  Every kernel launched through mvn_launch_pdl starts with MVN_PDL_PROLOGUE().
+__device__ __forceinline__ void mvn_griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void mvn_griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define MVN_PDL_PROLOGUE() do { mvn_griddep_launch(); mvn_griddep_wait(); } while (0)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t mvn_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float mvn_ld(const void* p, int dtype, long long i) {
     return dtype == MVN_BF16 ? __bfloat162float(((const __nv_bfloat16*)p)[i]) : ((const float*)p)[i];
 }

@@ -119,6 +119,7 @@ __device__ __forceinline__ void mvn_load4w(const float* W, int ldw, int k, int K
 #define RG_BK 16
 
 __global__ void __launch_bounds__(256) row_gemm_kernel(const RowGemmArgs a) {
+    MVN_PDL_PROLOGUE();
     __shared__ __align__(16) float As[RG_BK][RG_BM + 4];
     __shared__ __align__(16) float Ws[RG_BK][RG_BN];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -268,7 +269,7 @@ static inline int mvn_row_gemm(RowGemmArgs a, cudaStream_t st) {
             grid.z = ks;
         }
     }
-    row_gemm_kernel<<<grid, 256, 0, st>>>(a);
+    MVN_CUDA(mvn_launch_pdl(row_gemm_kernel, dim3(grid), dim3(256), (size_t)(0), st, a));
     return mvn_check_launch("row_gemm");
 }
 
@@ -277,6 +278,7 @@ static inline int mvn_row_gemm(RowGemmArgs a, cudaStream_t st) {
 #define TN_BR 16
 
 __global__ void __launch_bounds__(256) tn_gemm_kernel(const TnGemmArgs a) {
+    MVN_PDL_PROLOGUE();
     __shared__ __align__(16) float Ps[TN_BR][TN_BK];
     __shared__ __align__(16) float Qs[TN_BR][TN_BN];
     // which (source, k tile) is this block?
@@ -365,6 +367,6 @@ static inline int mvn_tn_gemm(TnGemmArgs a, cudaStream_t st) {
     rpc = ((rpc + TN_BR - 1) / TN_BR) * TN_BR;
     a.rows_per_cta = rpc;
     dim3 grid(ktiles, ntiles, mvn_cdiv(a.rows, rpc));
-    tn_gemm_kernel<<<grid, 256, 0, st>>>(a);
+    MVN_CUDA(mvn_launch_pdl(tn_gemm_kernel, dim3(grid), dim3(256), (size_t)(0), st, a));
     return mvn_check_launch("tn_gemm");
 }

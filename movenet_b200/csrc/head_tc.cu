@@ -103,6 +103,7 @@ __device__ __forceinline__ void store_part_row(uint8_t* tiles, int r, int part, 
 
 template <int A, int S>
 __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_fwd_tc_kernel(const HeadArgs a) {
+    MVN_PDL_PROLOGUE();
     constexpr int PARTS = A / 32, KC = A / 64, NT = A * 4, W2_BYTES = A * A * 2;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_fwd_tc_kernel(con
 
 template <int A, int S>
 __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(const HeadArgs a) {
+    MVN_PDL_PROLOGUE();
     constexpr int PARTS = A / 32, KC = A / 64, NT = A * 4, W2_BYTES = A * A * 2;
     constexpr int TMEM_COLS = A == 64 ? 256 : 512;
     // TMEM columns: da_pre [0, A) | weight-gradient accumulators | bias sums
@@ -507,6 +509,7 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
 
 template <int A>
 __global__ void head_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ pg, PackedLayout P, int S) {
+    MVN_PDL_PROLOGUE();
     constexpr int HPART = HP<A>::floats;
     {
         const int i = blockIdx.x * 32 + threadIdx.x;
@@ -534,6 +537,7 @@ __global__ void head_reduce_kernel(const float* __restrict__ partial, int n_cta,
 
 // W2 image: chunk kc = k / 64 holds [n][k % 64] = dense_conv.conv2.weight[n][k], bf16, 128B swizzle, A rows per chunk
 __global__ void head_pack_kernel(const float* __restrict__ w2, uint8_t* __restrict__ img, int A) {
+    MVN_PDL_PROLOGUE();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A * A) return;
     const int n = i / A, k = i % A, kc = k >> 6, kk = k & 63;
@@ -549,14 +553,14 @@ template <int A, int S>
 int launch_fwd(const HeadArgs& a, int grid, cudaStream_t st) {
     const int smem = fwd_smem<A>(S);
     MVN_CUDA(cudaFuncSetAttribute(head_fwd_tc_kernel<A, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    head_fwd_tc_kernel<A, S><<<grid, A * 4, smem, st>>>(a);
+    MVN_CUDA(mvn_launch_pdl(head_fwd_tc_kernel<A, S>, dim3(grid), dim3(A * 4), (size_t)(smem), st, a));
     return 0;
 }
 template <int A, int S>
 int launch_bwd(const HeadArgs& a, int grid, cudaStream_t st) {
     const int smem = bwd_smem<A>(S);
     MVN_CUDA(cudaFuncSetAttribute(head_bwd_tc_kernel<A, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    head_bwd_tc_kernel<A, S><<<grid, A * 4, smem, st>>>(a);
+    MVN_CUDA(mvn_launch_pdl(head_bwd_tc_kernel<A, S>, dim3(grid), dim3(A * 4), (size_t)(smem), st, a));
     return 0;
 }
 
@@ -570,7 +574,7 @@ int mvn_tc_head_supported(int A, int S) {
 size_t mvn_tc_head_partial_bytes() { return (size_t)2 * 148 * HP<128>::floats * 4; }
 
 int mvn_tc_head_pack(const float* w2_ref, float* packed, const PackedLayout& P, int A, cudaStream_t st) {
-    head_pack_kernel<<<(A * A + 255) / 256, 256, 0, st>>>(w2_ref, (uint8_t*)(packed + P.tc_head), A);
+    MVN_CUDA(mvn_launch_pdl(head_pack_kernel, dim3((A * A + 255) / 256), dim3(256), (size_t)(0), st, w2_ref, (uint8_t*)(packed + P.tc_head), A));
     return mvn_check_launch("head_pack");
 }
 
@@ -618,7 +622,7 @@ int mvn_tc_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, co
     print_clocks(1, "bwd");
     int rc = mvn_check_launch("head_bwd_tc");
     if (rc) return rc;
-    if (g.A == 64) head_reduce_kernel<64><<<(HP<64>::floats + 31) / 32, dim3(32, RED_SPLIT), 0, st>>>(partial, grid, pg, P, g.S);
-    else head_reduce_kernel<128><<<(HP<128>::floats + 31) / 32, dim3(32, RED_SPLIT), 0, st>>>(partial, grid, pg, P, g.S);
+    if (g.A == 64) MVN_CUDA(mvn_launch_pdl(head_reduce_kernel<64>, dim3((HP<64>::floats + 31) / 32), dim3(32, RED_SPLIT), (size_t)(0), st, partial, grid, pg, P, g.S));
+    else MVN_CUDA(mvn_launch_pdl(head_reduce_kernel<128>, dim3((HP<128>::floats + 31) / 32), dim3(32, RED_SPLIT), (size_t)(0), st, partial, grid, pg, P, g.S));
     return mvn_check_launch("head_reduce");
 }

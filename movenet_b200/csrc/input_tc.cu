@@ -22,6 +22,7 @@ struct InArgs {
 
 __global__ void __launch_bounds__(128, 3)
 input_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_u, const InArgs a) {
+    MVN_PDL_PROLOGUE();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sOH = smem;                        // OH0 | OH1
@@ -122,6 +123,7 @@ input_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_cons
 
 // dwin[tap][a][c] = sum_cta part[tap*64 + a][c]
 __global__ void input_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ dwin, int A) {
+    MVN_PDL_PROLOGUE();
     const int i = blockIdx.x * 32 + threadIdx.x;
     const int m = i >> 6, col = i & 63, tap = m >> 6, ch = m & 63;
     const bool valid = i < IPART && ch < A;
@@ -147,8 +149,8 @@ int mvn_tc_input_bwd(const float* audio, const int* codes, const unsigned char* 
     static bool attr = false;
     if (!attr) { MVN_CUDA(cudaFuncSetAttribute(input_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
     const int grid = a.n_tiles < 3 * 148 ? a.n_tiles : 3 * 148;
-    input_bwd_tc_kernel<<<grid, 128, smem, st>>>(mp, mu, a);
+    MVN_CUDA(mvn_launch_pdl(input_bwd_tc_kernel, dim3(grid), dim3(128), (size_t)(smem), st, mp, mu, a));
     if ((rc = mvn_check_launch("input_bwd_tc"))) return rc;
-    input_reduce_kernel<<<(IPART + 31) / 32, dim3(32, RED_SPLIT), 0, st>>>(partial, grid, dwin, g.A);
+    MVN_CUDA(mvn_launch_pdl(input_reduce_kernel, dim3((IPART + 31) / 32), dim3(32, RED_SPLIT), (size_t)(0), st, partial, grid, dwin, g.A));
     return mvn_check_launch("input_reduce");
 }

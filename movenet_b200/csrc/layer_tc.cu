@@ -32,6 +32,7 @@ __host__ __device__ inline int smem_total(int nchunks, int N2) { return smem_a_o
 // image writer: one block row per layer
 __global__ void tc_pack_kernel(const float* const* __restrict__ ptrs, float* __restrict__ packed, PackedLayout P, int S,
                                int nchunks, int N2, int video, int Cl) {
+    MVN_PDL_PROLOGUE();
     const int l = blockIdx.y;
     const float* const* lp = ptrs + MVN_PARAM_LAYER(l, 0);
     const float *wf = lp[0], *wg = lp[1], *vf = lp[2], *bvf = lp[3], *vg = lp[4], *bvg = lp[5], *wr = lp[6], *br = lp[7],
@@ -99,8 +100,8 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    griddep_launch();
-    griddep_wait();              // everything above overlapped the previous kernel's tail; its output is read from here on
+    mvn_griddep_launch();
+    mvn_griddep_wait();              // everything above overlapped the previous kernel's tail; its output is read from here on
     mbar_wait(full_bar, 0);
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -289,7 +290,7 @@ int mvn_tc_pack(const float* const* param_ptrs_dev, float* packed, const PackedL
     const int nchunks = g.video ? 3 : 2, N2 = ((g.C + g.S + 15) / 16) * 16;
     MVN_REQUIRE(smem_a_off(nchunks, N2) <= MVN_TC_IMG_BYTES, "tensor-core weight image does not fit its slot");
     dim3 grid(16, g.N);
-    tc_pack_kernel<<<grid, 256, 0, st>>>(param_ptrs_dev, packed, P, g.S, nchunks, N2, g.video, g.Cl);
+    MVN_CUDA(mvn_launch_pdl(tc_pack_kernel, dim3(grid), dim3(256), (size_t)(0), st, param_ptrs_dev, packed, P, g.S, nchunks, N2, g.video, g.Cl));
     return mvn_check_launch("tc_pack");
 }
 
@@ -316,6 +317,6 @@ int mvn_tc_layer_fwd(const void* x_in, const void* ctx, void* x_out, float* skip
     }
     int grid = 2 * 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    MVN_CUDA(launch_pdl(layer_fwd_tc_kernel, grid, 256, smem, st, map_x, map_ctx, map_out, a));
+    MVN_CUDA(mvn_launch_pdl(layer_fwd_tc_kernel, dim3(grid), dim3(256), (size_t)smem, st, map_x, map_ctx, map_out, a));
     return mvn_check_launch("layer_fwd_tc");
 }

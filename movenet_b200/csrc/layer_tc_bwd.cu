@@ -122,8 +122,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    griddep_launch();
-    griddep_wait();              // everything above overlapped the previous kernel's tail; its output is read from here on
+    mvn_griddep_launch();
+    mvn_griddep_wait();              // everything above overlapped the previous kernel's tail; its output is read from here on
     mbar_wait(bar + IMG, 0);
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -497,6 +497,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 // blockIdx.y = layer: every layer's partials are reduced by ONE launch after the whole backward sweep
 __global__ void tc_bwd_reduce_kernel(const float* __restrict__ partial_all, int n_cta, float* __restrict__ pg, PackedLayout P,
                                      int S, int Kz, int video, int n_layers) {
+    MVN_PDL_PROLOGUE();
     const int layer = blockIdx.y;
     const float* partial = partial_all + (size_t)layer * 148 * PART_FLOATS;
     float* lg = pg + P.layer0 + (size_t)layer * P.layer_stride;
@@ -535,7 +536,7 @@ int mvn_tc_bwd_reduce_all(const float* partial_all, float* pg, const PackedLayou
     const int n_tiles = ((g.T + TILE_T - 1) / TILE_T) * g.B;
     if (grid_ctas > n_tiles) grid_ctas = n_tiles;
     dim3 grid((PART_FLOATS + 255) / 256, g.N);
-    tc_bwd_reduce_kernel<<<grid, 256, 0, st>>>(partial_all, grid_ctas, pg, P, g.S, g.Kz, g.video, g.N);
+    MVN_CUDA(mvn_launch_pdl(tc_bwd_reduce_kernel, dim3(grid), dim3(256), (size_t)(0), st, partial_all, grid_ctas, pg, P, g.S, g.Kz, g.video, g.N));
     return mvn_check_launch("tc_bwd_reduce");
 }
 
@@ -570,7 +571,7 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     }
     int grid = 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    MVN_CUDA(launch_pdl(layer_bwd_tc_kernel, grid, N_THREADS, smem, st, mx, mc, mp, mu, mpo, muo, mq, mqo, a));
+    MVN_CUDA(mvn_launch_pdl(layer_bwd_tc_kernel, dim3(grid), dim3(N_THREADS), (size_t)smem, st, mx, mc, mp, mu, mpo, muo, mq, mqo, a));
     (void)lg;
 #if MVN_PHASE_CLOCKS
     if (getenv("MVN_PROF")) {

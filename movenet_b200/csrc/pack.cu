@@ -8,6 +8,7 @@
 // C: physical channels of the packed layout, Cl <= C: channels of the reference tensors (the rest is zero padding)
 __global__ void pack_layer_kernel(const float* const* __restrict__ ptrs, float* __restrict__ packed,
                                   PackedLayout P, int C, int Cl, int S, int Kz, int video) {
+    MVN_PDL_PROLOGUE();
     const int l = blockIdx.y;
     const float* const* lp = ptrs + MVN_PARAM_LAYER(l, 0);
     const float *wf = lp[0], *wg = lp[1], *vf = lp[2], *bvf = lp[3], *vg = lp[4], *bvg = lp[5], *wr = lp[6],
@@ -48,6 +49,7 @@ __global__ void pack_layer_kernel(const float* const* __restrict__ ptrs, float* 
 
 __global__ void unpack_layer_kernel(float* __restrict__ flat, const long long* __restrict__ offs,
                                     const float* __restrict__ packed, PackedLayout P, int C, int Cl, int S, int Kz, int video) {
+    MVN_PDL_PROLOGUE();
     const int l = blockIdx.y;
     float* lp[10];
 #pragma unroll
@@ -93,6 +95,7 @@ __global__ void unpack_layer_kernel(float* __restrict__ flat, const long long* _
 // input conv, head, video: blockIdx.y selects the group
 __global__ void pack_misc_kernel(const float* const* __restrict__ ptrs, float* __restrict__ packed, PackedLayout P,
                                  int A, int C, int Cl, int S, int Cin, int N, int video) {
+    MVN_PDL_PROLOGUE();
     const int grp = blockIdx.y;
     const int stride = gridDim.x * blockDim.x, i0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (grp == 0) {            // Win[tap][a][c] = w[c][a][tap]
@@ -139,6 +142,7 @@ __global__ void pack_misc_kernel(const float* const* __restrict__ ptrs, float* _
 __global__ void unpack_misc_kernel(float* __restrict__ flat, const long long* __restrict__ offs,
                                    const float* __restrict__ packed, PackedLayout P,
                                    int A, int C, int Cl, int S, int Cin, int N, int video) {
+    MVN_PDL_PROLOGUE();
     const int grp = blockIdx.y;
     auto gp = [&](int i) -> float* { const long long o = offs[i]; return o < 0 ? nullptr : flat + o; };
     const int stride = gridDim.x * blockDim.x, i0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,9 +187,9 @@ extern "C" int mvn_pack_weights(const mvn_shape_t* s, const void* const* param_p
     cudaStream_t st = (cudaStream_t)stream;
     const float* const* ptrs = (const float* const*)param_ptrs_dev;
     dim3 gl(8, g.N);
-    pack_layer_kernel<<<gl, 256, 0, st>>>(ptrs, (float*)packed, P, g.C, g.Cl, g.S, g.Kz, g.video);
+    MVN_CUDA(mvn_launch_pdl(pack_layer_kernel, dim3(gl), dim3(256), (size_t)(0), st, ptrs, (float*)packed, P, g.C, g.Cl, g.S, g.Kz, g.video));
     dim3 gm(128, 6);
-    pack_misc_kernel<<<gm, 256, 0, st>>>(ptrs, (float*)packed, P, g.A, g.C, g.Cl, g.S, g.Cin, g.N, g.video);
+    MVN_CUDA(mvn_launch_pdl(pack_misc_kernel, dim3(gm), dim3(256), (size_t)(0), st, ptrs, (float*)packed, P, g.A, g.C, g.Cl, g.S, g.Cin, g.N, g.video));
     int rc = mvn_check_launch("pack_weights");
     if (rc) return rc;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video))
@@ -205,8 +209,8 @@ extern "C" int mvn_unpack_grads(const mvn_shape_t* s, const void* packed_grads, 
     MVN_REQUIRE(packed_grads && flat_grads && offsets_dev, "mvn_unpack_grads: null buffer");
     const long long* offs = (const long long*)offsets_dev;
     dim3 gl(8, g.N);
-    unpack_layer_kernel<<<gl, 256, 0, st>>>(flat_grads, offs, (const float*)packed_grads, P, g.C, g.Cl, g.S, g.Kz, g.video);
+    MVN_CUDA(mvn_launch_pdl(unpack_layer_kernel, dim3(gl), dim3(256), (size_t)(0), st, flat_grads, offs, (const float*)packed_grads, P, g.C, g.Cl, g.S, g.Kz, g.video));
     dim3 gm(128, 6);
-    unpack_misc_kernel<<<gm, 256, 0, st>>>(flat_grads, offs, (const float*)packed_grads, P, g.A, g.C, g.Cl, g.S, g.Cin, g.N, g.video);
+    MVN_CUDA(mvn_launch_pdl(unpack_misc_kernel, dim3(gm), dim3(256), (size_t)(0), st, flat_grads, offs, (const float*)packed_grads, P, g.A, g.C, g.Cl, g.S, g.Cin, g.N, g.video));
     return mvn_check_launch("unpack_grads");
 }

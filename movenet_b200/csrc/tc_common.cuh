@@ -79,11 +79,6 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
-// Programmatic dependent launch: a kernel launched with launch_pdl() may start (barrier / TMEM setup, weight-image load)
-// while the kernel before it in the stream is still draining its last tiles; it must call griddep_wait() before it touches
-// anything that kernel wrote.  griddep_launch() lets the NEXT kernel's CTAs be scheduled as soon as SM resources free up.
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // one lane of a fully converged warp (the lowest); the compiler keeps the elected region on the uniform datapath
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
@@ -176,17 +171,6 @@ __device__ __forceinline__ float column_sum(const float* __restrict__ partial, i
         for (int y = 0; y < RED_SPLIT; ++y) tot += red[y][threadIdx.x];
     }
     return tot;
-}
-
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, int smem, cudaStream_t st, Args&&... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 // shared-memory image of one layer's weights (mvn_tc_pack): Wz chunks | [Wr|Ws] | biases (1 KB)

@@ -49,6 +49,7 @@ __device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.w
 
 // image: [n][k] = W[k][n] (packed wt layout [C][10C]) as 5 K-major 128B-swizzled blocks of 128 n-rows, then the bias
 __global__ void up_pack_kernel(const float* __restrict__ wt, const float* __restrict__ bt, uint8_t* __restrict__ img) {
+    MVN_PDL_PROLOGUE();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < UN * 64 + UN; i += gridDim.x * blockDim.x) {
         if (i < UN * 64) {
             const int n = i >> 6, k = i & 63, blk = n >> 7, nr = n & 127;
@@ -62,6 +63,7 @@ struct UpArgs { const void* img; float* du2; float* partial; long long rows; int
 
 __global__ void __launch_bounds__(256, 1)
 up_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_u2, const __grid_constant__ CUtensorMap map_ctx, const UpArgs a) {
+    MVN_PDL_PROLOGUE();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sImg = smem;
@@ -149,6 +151,7 @@ up_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_u2, const __grid_consta
 
 __global__ void __launch_bounds__(256, 1)
 up_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_u2, const __grid_constant__ CUtensorMap map_dctx, const UpArgs a) {
+    MVN_PDL_PROLOGUE();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sImg = smem;
@@ -276,6 +279,7 @@ up_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_u2, const __grid_consta
 
 // dwt[c_in][n] = sum_cta part[n][c_in] ; dbt[n] = sum_cta bias[n]
 __global__ void up_reduce_kernel(const float* __restrict__ partial, int n_cta, float* __restrict__ dwt, float* __restrict__ dbt) {
+    MVN_PDL_PROLOGUE();
     const int i = blockIdx.x * 32 + threadIdx.x;
     const bool valid = i < UPART;
     const float acc = column_sum(partial, n_cta, UPART, i, valid);
@@ -288,7 +292,7 @@ int mvn_tc_upsample_supported(int C) { return C == 64; }
 size_t mvn_tc_upsample_img_floats() { return (IMG_BYTES + 3072) / 4; }
 
 int mvn_tc_upsample_pack(const float* wt, const float* bt, float* img, cudaStream_t st) {
-    up_pack_kernel<<<64, 256, 0, st>>>(wt, bt, (uint8_t*)img);
+    MVN_CUDA(mvn_launch_pdl(up_pack_kernel, dim3(64), dim3(256), (size_t)(0), st, wt, bt, (uint8_t*)img));
     return mvn_check_launch("upsample_pack");
 }
 
@@ -301,7 +305,7 @@ int mvn_tc_upsample_fwd(const float* img, const void* u2_bf16, void* ctx_bf16, l
     static bool attr = false;
     if (!attr) { MVN_CUDA(cudaFuncSetAttribute(up_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
-    up_fwd_tc_kernel<<<grid, 256, smem, st>>>(mu, mc, a);
+    MVN_CUDA(mvn_launch_pdl(up_fwd_tc_kernel, dim3(grid), dim3(256), (size_t)(smem), st, mu, mc, a));
     return mvn_check_launch("upsample_fwd_tc");
 }
 
@@ -315,8 +319,8 @@ int mvn_tc_upsample_bwd(const float* img, const void* u2_bf16, const void* dctx_
     static bool attr = false;
     if (!attr) { MVN_CUDA(cudaFuncSetAttribute(up_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
-    up_bwd_tc_kernel<<<grid, 256, smem, st>>>(mu, md, a);
+    MVN_CUDA(mvn_launch_pdl(up_bwd_tc_kernel, dim3(grid), dim3(256), (size_t)(smem), st, mu, md, a));
     if ((rc = mvn_check_launch("upsample_bwd_tc"))) return rc;
-    up_reduce_kernel<<<(UPART + 31) / 32, dim3(32, RED_SPLIT), 0, st>>>(partial, grid, dwt, dbt);
+    MVN_CUDA(mvn_launch_pdl(up_reduce_kernel, dim3((UPART + 31) / 32), dim3(32, RED_SPLIT), (size_t)(0), st, partial, grid, dwt, dbt));
     return mvn_check_launch("upsample_reduce");
 }

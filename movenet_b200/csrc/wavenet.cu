@@ -13,6 +13,7 @@
 // (movenet/pytorch_lightning_trainer.py:64).
 __global__ void codes_kernel(const float* __restrict__ audio, int A, int T, int* __restrict__ codes,
                              unsigned char* __restrict__ dense) {
+    MVN_PDL_PROLOGUE();
     const int t = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (t >= T) return;
     const float* p = audio + (size_t)b * A * T + t;
@@ -31,6 +32,7 @@ __global__ void codes_kernel(const float* __restrict__ audio, int A, int T, int*
 __global__ void input_fwd_kernel(const float* __restrict__ audio, const int* __restrict__ codes,
                                  const unsigned char* __restrict__ dense, const float* __restrict__ win,
                                  void* __restrict__ h0, int adt, int A, int C, int T, long long rows) {
+    MVN_PDL_PROLOGUE();
     const int cg = (C + 7) / 8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * cg) return;
@@ -77,6 +79,7 @@ __global__ void input_fwd_kernel(const float* __restrict__ audio, const int* __r
 // split K over CTAs (8 rows x all channels x one K slice each) and add the slices with fp32 atomics into the
 // bias-initialised output.
 __global__ void video_conv_init_kernel(float* __restrict__ enc, const float* __restrict__ bias, int rows, int C) {
+    MVN_PDL_PROLOGUE();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows * C) enc[i] = bias[i % C];
 }
@@ -84,6 +87,7 @@ __global__ void video_conv_init_kernel(float* __restrict__ enc, const float* __r
 #define VC_K 256
 __global__ void __launch_bounds__(256) video_conv_kernel(const float* __restrict__ video, const float* __restrict__ wv,
                                                          float* __restrict__ enc, int rows, int K, int C) {
+    MVN_PDL_PROLOGUE();
     __shared__ float xs[VC_ROWS][VC_K];
     const int r0 = blockIdx.x * VC_ROWS, k0 = blockIdx.y * VC_K;
     for (int i = threadIdx.x; i < VC_ROWS * VC_K; i += blockDim.x) {
@@ -282,7 +286,7 @@ extern "C" int mvn_output_size(int layer_size, int stack_size, int frames) {
 extern "C" int mvn_onehot_to_codes(const float* audio, int B, int A, int T, int* codes, unsigned char* dense, void* stream) {
     MVN_REQUIRE(audio && codes && dense && B > 0 && A > 0 && T > 0, "mvn_onehot_to_codes: bad arguments");
     dim3 grid(mvn_cdiv(T, 256), B);
-    codes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(audio, A, T, codes, dense);
+    MVN_CUDA(mvn_launch_pdl(codes_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, audio, A, T, codes, dense));
     return mvn_check_launch("onehot_to_codes");
 }
 
@@ -312,7 +316,7 @@ static int input_fwd(const Ctx& c, const float* audio) {
     if (audio) rc = mvn_onehot_to_codes(audio, g.B, g.A, g.T, codes, dense, c.st);   // null: mvn_codes_input filled them
     if (rc) return rc;
     const long long rows = (long long)g.B * g.T, n = rows * ((g.C + 7) / 8);
-    input_fwd_kernel<<<mvn_cdiv(n, 256), 256, 0, c.st>>>(audio, codes, dense, c.packed + c.P.win, c.x(0), g.adt, g.A, g.C, g.T, rows);
+    MVN_CUDA(mvn_launch_pdl(input_fwd_kernel, dim3(mvn_cdiv(n, 256)), dim3(256), (size_t)(0), c.st, audio, codes, dense, c.packed + c.P.win, c.x(0), g.adt, g.A, g.C, g.T, rows));
     return mvn_check_launch("input_fwd");
 }
 
@@ -323,10 +327,10 @@ static int video_fwd(const Ctx& c, const float* video) {
     int rc;
     {   // Conv3d with a (1,64,64) kernel = one 4096*Cin -> C linear map per frame (movenet/wavenet.py:94-98,152)
         const int rows = g.B * 160, K = 4096 * g.Cin;
-        video_conv_init_kernel<<<mvn_cdiv((long long)rows * C, 256), 256, 0, c.st>>>(enc, c.packed + c.P.bv, rows, C);
+        MVN_CUDA(mvn_launch_pdl(video_conv_init_kernel, dim3(mvn_cdiv((long long)rows * C, 256)), dim3(256), (size_t)(0), c.st, enc, c.packed + c.P.bv, rows, C));
         if ((rc = mvn_check_launch("video_conv_init"))) return rc;
         dim3 grid(mvn_cdiv(rows, VC_ROWS), mvn_cdiv(K, VC_K));
-        video_conv_kernel<<<grid, 256, 0, c.st>>>(video, c.packed + c.P.wv, enc, rows, K, C);
+        MVN_CUDA(mvn_launch_pdl(video_conv_kernel, dim3(grid), dim3(256), (size_t)(0), c.st, video, c.packed + c.P.wv, enc, rows, K, C));
         if ((rc = mvn_check_launch("video_conv"))) return rc;
     }
     // ConvTranspose1d(k=10, stride=10): out[10 i + j] = W[:, :, j]^T in[i] + b -- a [rows x C] x [C x 10C] GEMM whose
