@@ -12,6 +12,7 @@
 // time row) and both gate halves of one (t, c) sit in the same thread.  One 128-row tile is in
 // flight per CTA; two CTAs share an SM (106 KB shared memory, 256 TMEM columns each) so one CTA's
 // epilogue overlaps the other's loads and MMAs.
+#include <cstdlib>
 #include <mutex>
 #include "tc_common.cuh"
 #include "layer_tc.h"
@@ -27,7 +28,14 @@ struct TcArgs {
 };
 
 // shared-memory carve-up (dynamic, 1024-byte aligned): weight image (tc_common.cuh) | A tiles | barriers
-__host__ __device__ inline int smem_total(int nchunks, int N2) { return smem_a_off(nchunks, N2) + nchunks * TILE_BYTES + 64; }
+__host__ __device__ inline int smem_total(int nchunks, int N2) { return smem_a_off(nchunks, N2) + nchunks * TILE_BYTES + 64 + 256; }
+
+// packed half-precision helpers of epilogue 1 (two gate outputs per instruction, one MUFU op per two tanh)
+__device__ __forceinline__ uint32_t f16x2(float lo, float hi) { uint32_t d; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo)); return d; }
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) { uint32_t d; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t hmul2(uint32_t a, uint32_t b) { uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t htanh2(uint32_t a) { uint32_t d; asm("tanh.approx.f16x2 %0, %1;" : "=r"(d) : "r"(a)); return d; }
 
 // image writer: one block row per layer
 __global__ void tc_pack_kernel(const float* const* __restrict__ ptrs, float* __restrict__ packed, PackedLayout P, int S,
@@ -64,6 +72,9 @@ __global__ void tc_pack_kernel(const float* const* __restrict__ ptrs, float* __r
     }
 }
 
+// HALF_GATE: epilogue 1 in packed f16x2 (default).  false: the fp32 gate math (MOVENET_B200_GATE_F32=1), kept as the
+// reference point for the accuracy of the packed path.
+template <bool HALF_GATE>
 __global__ void __launch_bounds__(256, 2)
 layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_ctx,
                     const __grid_constant__ CUtensorMap map_out, const TcArgs a) {
@@ -79,6 +90,7 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint64_t* full_bar = (uint64_t*)(sA0 + a.nchunks * TILE_BYTES);
     uint64_t* mma_bar = full_bar + 1;
     uint32_t* tmem_slot = (uint32_t*)(full_bar + 2);
+    uint32_t* sbh = (uint32_t*)(full_bar + 8);            // gate biases as f16x2 pairs: [0,32) filter, [32,64) gate
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);     // warp-uniform copy: the issue branches stay convergent
@@ -103,9 +115,21 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     mvn_griddep_launch();
     mvn_griddep_wait();              // everything above overlapped the previous kernel's tail; its output is read from here on
     mbar_wait(full_bar, 0);
+    if (HALF_GATE) {
+        if (tid < 64) sbh[tid] = f16x2(sbz[2 * tid], sbz[2 * tid + 1]);
+        // kind::f16 wants both operands of one MMA in the same format: this CTA's copy of [Wr|Ws] becomes f16 too (same layout)
+        for (int i = tid; i < a.N2 * 32; i += 256) {
+            const float2 w = unpack_bf16(((const uint32_t*)sBrs)[i]);
+            ((uint32_t*)sBrs)[i] = f16x2(w.x, w.y);
+        }
+        fence_proxy_async();
+        __syncthreads();
+    }
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t idesc1 = umma_idesc(TILE_T, 128), idesc2 = umma_idesc(TILE_T, a.N2);
+    // the out GEMM runs on f16 operands (formats 0): the gated tile is written in f16 by epilogue 1
+    const uint32_t idesc1 = umma_idesc(TILE_T, 128),
+                   idesc2 = HALF_GATE ? umma_idesc(TILE_T, a.N2) & ~((1u << 7) | (1u << 10)) : umma_idesc(TILE_T, a.N2);
     const uint32_t load_bytes = (uint32_t)(a.nchunks * TILE_BYTES);
     const int r = tid & 127;         // this thread's row of the tile == its TMEM lane (warps w and w+4 share a lane quarter
     const int half = tid >> 7;       // and split the channel range between them)
@@ -166,16 +190,27 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             tmem_ld32(tmem + lane_base + 32 * half, f);
             tmem_ld32(tmem + lane_base + 64 + 32 * half, g);
             tmem_ld_wait();
+            const uint32_t h05 = 0x38003800u;     // (0.5, 0.5)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 uint32_t o[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int i = 8 * q + 2 * e, c = 32 * half + i;
-                    const float f0 = __uint_as_float(f[i]) + sbz[c], f1 = __uint_as_float(f[i + 1]) + sbz[c + 1];
-                    const float g0 = __uint_as_float(g[i]) + sbz[64 + c], g1 = __uint_as_float(g[i + 1]) + sbz[64 + c + 1];
-                    o[e] = pack_bf16(tanh_fast(f0) * fmaf(0.5f, tanh_fast(0.5f * g0), 0.5f),
-                                     tanh_fast(f1) * fmaf(0.5f, tanh_fast(0.5f * g1), 0.5f));
+                    const int i = 8 * q + 2 * e;
+                    if (HALF_GATE) {
+                        // tanh(f) * sigmoid(g) on channel pairs in f16x2: the 11-bit intermediate precision is above the
+                        // output's; the tile the out GEMM reads is f16
+                        const int pc = 16 * half + 4 * q + e;
+                        const uint32_t fh = hadd2(f16x2(__uint_as_float(f[i]), __uint_as_float(f[i + 1])), sbh[pc]);
+                        const uint32_t gh = hadd2(f16x2(__uint_as_float(g[i]), __uint_as_float(g[i + 1])), sbh[32 + pc]);
+                        o[e] = hmul2(htanh2(fh), hfma2(htanh2(hmul2(gh, h05)), h05, h05));
+                    } else {
+                        const int c = 32 * half + i;
+                        const float f0 = __uint_as_float(f[i]) + sbz[c], f1 = __uint_as_float(f[i + 1]) + sbz[c + 1];
+                        const float g0 = __uint_as_float(g[i]) + sbz[64 + c], g1 = __uint_as_float(g[i + 1]) + sbz[64 + c + 1];
+                        o[e] = pack_bf16(tanh_fast(f0) * fmaf(0.5f, tanh_fast(0.5f * g0), 0.5f),
+                                         tanh_fast(f1) * fmaf(0.5f, tanh_fast(0.5f * g1), 0.5f));
+                    }
                 }
                 *(uint4*)(sA0 + r * 128 + (((4 * half + q) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
             }
@@ -310,13 +345,16 @@ int mvn_tc_layer_fwd(const void* x_in, const void* ctx, void* x_out, float* skip
     a.dil = g.dil[layer]; a.nchunks = g.video ? 3 : 2; a.has_out = x_out != nullptr; a.skip_init = layer == 0;
     a.tiles_per_clip = (g.T + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
     const int smem = smem_total(a.nchunks, a.N2) + 1024;
+    static const bool gate_f32 = getenv("MOVENET_B200_GATE_F32") != nullptr;
     static int attr_smem = 0;
     if (smem > attr_smem) {
-        MVN_CUDA(cudaFuncSetAttribute(layer_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MVN_CUDA(cudaFuncSetAttribute(layer_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MVN_CUDA(cudaFuncSetAttribute(layer_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
     int grid = 2 * 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    MVN_CUDA(mvn_launch_pdl(layer_fwd_tc_kernel, dim3(grid), dim3(256), (size_t)smem, st, map_x, map_ctx, map_out, a));
+    if (gate_f32) MVN_CUDA(mvn_launch_pdl(layer_fwd_tc_kernel<false>, dim3(grid), dim3(256), (size_t)smem, st, map_x, map_ctx, map_out, a));
+    else MVN_CUDA(mvn_launch_pdl(layer_fwd_tc_kernel<true>, dim3(grid), dim3(256), (size_t)smem, st, map_x, map_ctx, map_out, a));
     return mvn_check_launch("layer_fwd_tc");
 }
