@@ -11,6 +11,37 @@
 // the column is not an exact one-hot (then the input conv takes the dense path).
 // The same codes are the training targets: target[t] = codes[t + RF]
 // (movenet/pytorch_lightning_trainer.py:64).
+// four columns per thread through 16-byte loads (T % 4 == 0, 16-byte aligned rows)
+__global__ void codes4_kernel(const float* __restrict__ audio, int A, int T, int* __restrict__ codes,
+                              unsigned char* __restrict__ dense) {
+    MVN_PDL_PROLOGUE();
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) * 4, b = blockIdx.y;
+    if (t >= T) return;
+    const float* p = audio + (size_t)b * A * T + t;
+    float best[4]; int arg[4] = {0, 0, 0, 0}, ones[4], other[4];
+    {
+        const float4 v4 = *(const float4*)p;
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { best[j] = v[j]; ones[j] = (v[j] == 1.f); other[j] = (v[j] != 0.f && v[j] != 1.f); }
+    }
+#pragma unroll 4
+    for (int a = 1; a < A; ++a) {
+        const float4 v4 = *(const float4*)(p + (size_t)a * T);
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (v[j] > best[j] || (v[j] != v[j] && best[j] == best[j])) { best[j] = v[j]; arg[j] = a; }   // NaN wins like torch
+            ones[j] += (v[j] == 1.f); other[j] += (v[j] != 0.f && v[j] != 1.f);
+        }
+    }
+    *(int4*)(codes + (size_t)b * T + t) = make_int4(arg[0], arg[1], arg[2], arg[3]);
+    uchar4 d;
+    d.x = (ones[0] == 1 && other[0] == 0) ? 0 : 1; d.y = (ones[1] == 1 && other[1] == 0) ? 0 : 1;
+    d.z = (ones[2] == 1 && other[2] == 0) ? 0 : 1; d.w = (ones[3] == 1 && other[3] == 0) ? 0 : 1;
+    *(uchar4*)(dense + (size_t)b * T + t) = d;
+}
+
 __global__ void codes_kernel(const float* __restrict__ audio, int A, int T, int* __restrict__ codes,
                              unsigned char* __restrict__ dense) {
     MVN_PDL_PROLOGUE();
@@ -72,6 +103,55 @@ __global__ void input_fwd_kernel(const float* __restrict__ audio, const int* __r
         d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]); d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     } else {
         for (int j = 0; j < 8 && c0 + j < C; ++j) mvn_st(h0, adt, row * C + c0 + j, acc[j]);
+    }
+}
+
+// The same for C % 8 == 0 with the two tap tables Win[tap][a][:] (2 A C floats) staged in shared memory: persistent
+// CTAs, 8 channels per thread, C/8 threads per row, so a row is one coalesced 128- or 256-byte store and the gather never
+// leaves the SM.  Columns that are not one-hot take the dense sum from the same shared-memory table.
+__global__ void __launch_bounds__(256) input_fwd_smem_kernel(const float* __restrict__ audio, const int* __restrict__ codes,
+                                                            const unsigned char* __restrict__ dense, const float* __restrict__ win,
+                                                            void* __restrict__ h0, int adt, int A, int C, int T, int rows) {
+    MVN_PDL_PROLOGUE();
+    extern __shared__ float swin[];
+    for (int i = threadIdx.x; i < 2 * A * C / 4; i += blockDim.x) ((float4*)swin)[i] = ((const float4*)win)[i];
+    __syncthreads();
+    const int cg = C / 8, rows_per_iter = blockDim.x / cg;
+    const int sub = threadIdx.x / cg, c0 = (threadIdx.x % cg) * 8;
+    if (sub >= rows_per_iter) return;
+    for (int row = blockIdx.x * rows_per_iter + sub; row < rows; row += gridDim.x * rows_per_iter) {
+        const int b = row / T, t = row - b * T;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int tap = 0; tap < 2; ++tap) {
+            const int ts = t - 1 + tap;
+            if (ts < 0) continue;
+            const int r = row - 1 + tap;
+            const float* wt = swin + tap * A * C;
+            if (!dense[r]) {
+                const float* wr = wt + codes[r] * C + c0;
+                const float4 w0 = ((const float4*)wr)[0], w1 = ((const float4*)wr)[1];
+                acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
+                acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
+            } else {
+                for (int a = 0; a < A; ++a) {
+                    const float x = audio[((size_t)b * A + a) * T + ts];
+                    if (x != 0.f) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] = fmaf(x, wt[a * C + c0 + j], acc[j]);
+                    }
+                }
+            }
+        }
+        if (adt == MVN_BF16) {
+            __nv_bfloat162 o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+            *(uint4*)((__nv_bfloat16*)h0 + (size_t)row * C + c0) = *(const uint4*)o;
+        } else {
+            float4* d = (float4*)((float*)h0 + (size_t)row * C + c0);
+            d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]); d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
     }
 }
 
@@ -285,6 +365,11 @@ extern "C" int mvn_output_size(int layer_size, int stack_size, int frames) {
 
 extern "C" int mvn_onehot_to_codes(const float* audio, int B, int A, int T, int* codes, unsigned char* dense, void* stream) {
     MVN_REQUIRE(audio && codes && dense && B > 0 && A > 0 && T > 0, "mvn_onehot_to_codes: bad arguments");
+    if (T % 4 == 0 && (((uintptr_t)audio | (uintptr_t)codes | (uintptr_t)dense) & 15) == 0) {
+        dim3 grid4(mvn_cdiv(T / 4, 128), B);
+        MVN_CUDA(mvn_launch_pdl(codes4_kernel, grid4, dim3(128), (size_t)(0), (cudaStream_t)stream, audio, A, T, codes, dense));
+        return mvn_check_launch("onehot_to_codes4");
+    }
     dim3 grid(mvn_cdiv(T, 256), B);
     MVN_CUDA(mvn_launch_pdl(codes_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, audio, A, T, codes, dense));
     return mvn_check_launch("onehot_to_codes");
@@ -316,6 +401,15 @@ static int input_fwd(const Ctx& c, const float* audio) {
     if (audio) rc = mvn_onehot_to_codes(audio, g.B, g.A, g.T, codes, dense, c.st);   // null: mvn_codes_input filled them
     if (rc) return rc;
     const long long rows = (long long)g.B * g.T, n = rows * ((g.C + 7) / 8);
+    const size_t table = (size_t)2 * g.A * g.C * 4;
+    if (g.C % 8 == 0 && 256 % (g.C / 8) == 0 && table <= 96 * 1024) {
+        static size_t attr = 0;
+        if (table > attr) { MVN_CUDA(cudaFuncSetAttribute(input_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table)); attr = table; }
+        const int per_sm = table <= 48 * 1024 ? 4 : 2;
+        MVN_CUDA(mvn_launch_pdl(input_fwd_smem_kernel, dim3(148 * per_sm), dim3(256), table, c.st, audio, (const int*)codes,
+                                (const unsigned char*)dense, c.packed + c.P.win, c.x(0), g.adt, g.A, g.C, g.T, (int)rows));
+        return mvn_check_launch("input_fwd_smem");
+    }
     MVN_CUDA(mvn_launch_pdl(input_fwd_kernel, dim3(mvn_cdiv(n, 256)), dim3(256), (size_t)(0), c.st, audio, codes, dense, c.packed + c.P.win, c.x(0), g.adt, g.A, g.C, g.T, rows));
     return mvn_check_launch("input_fwd");
 }
