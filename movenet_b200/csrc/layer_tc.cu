@@ -30,12 +30,6 @@ struct TcArgs {
 // shared-memory carve-up (dynamic, 1024-byte aligned): weight image (tc_common.cuh) | A tiles | barriers
 __host__ __device__ inline int smem_total(int nchunks, int N2) { return smem_a_off(nchunks, N2) + nchunks * TILE_BYTES + 64 + 256; }
 
-// packed half-precision helpers of epilogue 1 (two gate outputs per instruction, one MUFU op per two tanh)
-__device__ __forceinline__ uint32_t f16x2(float lo, float hi) { uint32_t d; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo)); return d; }
-__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) { uint32_t d; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
-__device__ __forceinline__ uint32_t hmul2(uint32_t a, uint32_t b) { uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
-__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
-__device__ __forceinline__ uint32_t htanh2(uint32_t a) { uint32_t d; asm("tanh.approx.f16x2 %0, %1;" : "=r"(d) : "r"(a)); return d; }
 
 // image writer: one block row per layer
 __global__ void tc_pack_kernel(const float* const* __restrict__ ptrs, float* __restrict__ packed, PackedLayout P, int S,

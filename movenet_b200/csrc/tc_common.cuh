@@ -2,6 +2,7 @@
 #pragma once
 #include <utility>
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "layout.h"
 
@@ -123,6 +124,14 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
     return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
 }
 
+
+// packed half-precision helpers of the gate epilogues (two outputs per instruction, one MUFU op per two tanh)
+__device__ __forceinline__ uint32_t f16x2(float lo, float hi) { uint32_t d; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo)); return d; }
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) { uint32_t d; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t hmul2(uint32_t a, uint32_t b) { uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t htanh2(uint32_t a) { uint32_t d; asm("tanh.approx.f16x2 %0, %1;" : "=r"(d) : "r"(a)); return d; }
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
 
 // MN-major, SWIZZLE_128B operand: 64 contiguous bf16 (one 128-byte row) along M/N, blocks of 64 `lbo` bytes
 // apart; along K rows are 128 bytes apart, groups of 8 rows 1024 bytes apart (SBO).  A [time x 64 ch] tile
