@@ -10,7 +10,7 @@ hdr = rows[h]
 ki, vi = hdr.index('Kernel Name'), hdr.index('Metric Value')
 launches = [(r[ki].split('(')[0].replace('<unnamed>::', '').replace('void ', '')[:70], float(r[vi].replace(',', '')))
             for r in rows[h + 1:] if len(r) > vi]
-starts = [i for i, (n, _) in enumerate(launches) if n.startswith('codes_kernel')]
+starts = [i for i, (n, _) in enumerate(launches) if n.startswith('codes')]
 which = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 seg = launches[starts[which]:starts[which + 1]]
 agg = collections.OrderedDict()
