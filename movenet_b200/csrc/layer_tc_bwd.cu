@@ -271,11 +271,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             umma_commit(bar + WALL);
             CLKC(10);
             }
-            if (has_next) {
-                mbar_wait(bar + W1, ph);           // W1 no longer reads the x/ctx tiles
-                CLKC(11);
-                if (leader) load_a_tiles(nb, n0);
-            }
+            // (the x/ctx tiles of the next tile are reloaded by worker thread 0 as soon as it has seen W1: this warp is
+            // still blocked issuing W2 then, and the reload is the head of the next tile's dependency chain)
             CLKC(12);
             mbar_wait(bar + E_OUT, ph);            // P', U', Q' are staged; nobody reads DXS or the tile's TMEM columns any more
             CLKC(13);
@@ -433,7 +430,14 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 *p1 = make_uint4(o[4], o[5], o[6], o[7]);
             }
             CLKW(9);
-            mbar_wait(bar + W1, ph);            // W1 no longer reads the DZ tiles
+            mbar_wait(bar + W1, ph);            // W1 no longer reads the DZ tiles, nor the x/ctx tiles:
+            if (tid == 0 && tile + (int)gridDim.x < a.n_tiles) {   // reload those for the next tile right away
+                const int nt = tile + gridDim.x, nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
+                mbar_expect_tx(bar + A_IN, (uint32_t)(nc * TILE_BYTES));
+                tma_load_3d(sA, &map_x, bar + A_IN, 0, n0 - a.dil, nb);
+                tma_load_3d(sA + TILE_BYTES, &map_x, bar + A_IN, 0, n0, nb);
+                if (nc == 3) tma_load_3d(sA + 2 * TILE_BYTES, &map_ctx, bar + A_IN, 0, n0, nb);
+            }
             CLKW(10);
             *(uint4*)(sDZ + o0) = make_uint4(po[0], po[1], po[2], po[3]);
             *(uint4*)(sDZ + o1) = make_uint4(po[4], po[5], po[6], po[7]);
