@@ -140,6 +140,21 @@ int mvn_softmax_ce_fwd(const float* probs, const int64_t* target, int B, int A, 
 int mvn_softmax_ce_bwd(const float* probs, const int64_t* target, const float* grad_loss, int B, int A, int T,
                        float* dprobs, void* stream);
 
+/* AdamW for every parameter tensor in one launch: torch.optim.AdamW's update as built by
+ * movenet/pytorch_lightning_trainer.py:128-202 (amsgrad = False), optionally preceded by the global gradient-norm clip of
+ * :233-243 (max_grad_norm > 0; coefficient min(1, max/(norm + 1e-6)) like torch.nn.utils.clip_grad_norm_).
+ *   segments_dev: array of { float* param; const float* grad; float* exp_avg; float* exp_avg_sq; long long numel }
+ *                 (mvn_adamw_segment_bytes() each), chunks_dev: array of { int segment; int first_chunk_of_segment },
+ *                 one entry per mvn_adamw_chunk_elems() elements of a segment; both on the device, built once by the host.
+ *   bias_correction1/2 = 1 - beta^step; the scalars are doubles because torch forms 1 - beta, lr / bias_correction1, ... in
+ *   double before they reach its kernels.  sq_partials: n_chunks floats of scratch (only read/written when clipping),
+ *   grad_norm_out: optional 1 float that receives the pre-clip gradient norm. */
+size_t mvn_adamw_segment_bytes(void);
+int mvn_adamw_chunk_elems(void);
+int mvn_adamw_step(const void* segments_dev, const void* chunks_dev, int n_chunks, double lr, double beta1, double beta2,
+                   double eps, double weight_decay, double bias_correction1, double bias_correction2, double max_grad_norm,
+                   float* sq_partials, float* grad_norm_out, void* stream);
+
 /* stage-level entry points (the same kernels the two calls above launch) */
 int mvn_onehot_to_codes(const float* audio, int B, int A, int T, int* codes, unsigned char* dense, void* stream);
 int mvn_input_fwd(const mvn_shape_t* s, const void* packed, const float* audio, void* acts, void* stream);

@@ -11,7 +11,8 @@ from .wavenet import (MAX_AUDIO_FRAMES, MAX_VIDEO_FRAMES, UPSAMPLE_STRIDE, VIDEO
 from .modules import CausalConv1d, DenseConv, DilatedCausalConv1d, GatedResidualConv1d, ResidualConvStack
 from .mulaw import mu_law_decoding, mu_law_encoding, one_hot
 from .loss import softmax_cross_entropy
+from . import optim
 
 __all__ = ["WaveNet", "MAX_AUDIO_FRAMES", "MAX_VIDEO_FRAMES", "VIDEO_KERNEL_SIZE", "UPSAMPLE_STRIDE",
            "upsample_kernel_size_solver", "CausalConv1d", "DilatedCausalConv1d", "GatedResidualConv1d",
-           "ResidualConvStack", "DenseConv", "mu_law_encoding", "mu_law_decoding", "one_hot", "softmax_cross_entropy"]
+           "ResidualConvStack", "DenseConv", "mu_law_encoding", "mu_law_decoding", "one_hot", "softmax_cross_entropy", "optim"]

@@ -22,7 +22,7 @@ class Shape(C.Structure):
         return tuple(getattr(self, n) for n, _ in self._fields_)
 
 
-_P, _I, _SZ, _I64 = C.c_void_p, C.c_int, C.c_size_t, C.c_int64
+_P, _I, _SZ, _I64, _D = C.c_void_p, C.c_int, C.c_size_t, C.c_int64, C.c_double
 _SP = C.POINTER(Shape)
 
 # name -> (restype, argtypes); every int-returning launcher is error-checked
@@ -45,6 +45,9 @@ SIGNATURES = {
     "mvn_wavenet_backward": (_I, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mvn_fused_loss_supported": (_I, [_SP]),
     "mvn_wavenet_backward_loss": (_I, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "mvn_adamw_segment_bytes": (_SZ, []),
+    "mvn_adamw_chunk_elems": (_I, []),
+    "mvn_adamw_step": (_I, [_P, _P, _I, _D, _D, _D, _D, _D, _D, _D, _D, _P, _P, _P]),
     "mvn_softmax_ce_partials": (_SZ, [_I, _I]),
     "mvn_softmax_ce_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "mvn_softmax_ce_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P]),
