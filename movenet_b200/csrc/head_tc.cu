@@ -101,6 +101,44 @@ __device__ __forceinline__ void store_part_row(uint8_t* tiles, int r, int part, 
                        pack_bf16(v[8 * q + 4], v[8 * q + 5]), pack_bf16(v[8 * q + 6], v[8 * q + 7]));
 }
 
+// The first 1x1 conv (K = S <= 64) also runs on the tensor core.  Its input lrelu(skip_sum) is fp32 and is NOT rounded to
+// bf16: the row is split into a bf16 head and a bf16 remainder, hi = bf16(x), lo = bf16(x - hi), stored side by side in one
+// [128 x 64] tile (columns [0, S) and [LO, LO + S), LO = max(16, S)), and multiplied by an image that holds W1 twice, so the
+// product sees x to 2^-17.  (S = 64 has no room for the remainder: plain bf16 there.)
+template <int S> struct SkipTile {
+    static constexpr int LO = S < 16 ? 16 : S;
+    static constexpr bool SPLIT = 2 * LO <= 64;
+    static constexpr int K = SPLIT ? 2 * LO : (S < 16 ? 16 : S);     // contraction length of the a1 GEMM (multiple of 16)
+};
+// row r of the skip tile from this thread's S fp32 values
+template <int S>
+__device__ __forceinline__ void store_skip_row(uint8_t* tile, int r, const float* ls) {
+    const int sw = r & 7;
+#pragma unroll
+    for (int s = 0; s < S; s += 8) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            hi[e] = pack_bf16(ls[s + 2 * e], ls[s + 2 * e + 1]);
+            const float2 h = unpack_bf16(hi[e]);
+            lo[e] = pack_bf16(ls[s + 2 * e] - h.x, ls[s + 2 * e + 1] - h.y);
+        }
+        *(uint4*)(tile + r * 128 + (((s >> 3) ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (SkipTile<S>::SPLIT)
+            *(uint4*)(tile + r * 128 + ((((SkipTile<S>::LO + s) >> 3) ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+// W1 image for a1 = skip_tile . W1^T: [A rows n][64 k] bf16 K-major, 128B swizzle; k in [0,S) and [LO, LO+S) hold w1p[k][n]
+template <int A, int S>
+__device__ __forceinline__ void build_w1_image(uint8_t* img, const float* sw1, int tid, int nt) {
+    for (int i = tid; i < A * 64; i += nt) {
+        const int n = i >> 6, k = i & 63;
+        const int s = k < S ? k : (SkipTile<S>::SPLIT && k >= SkipTile<S>::LO && k < SkipTile<S>::LO + S ? k - SkipTile<S>::LO : -1);
+        const float v = s >= 0 ? sw1[s * A + n] : 0.f;
+        *(__nv_bfloat16*)(img + n * 128 + ((((k >> 3) ^ (n & 7)) << 4) | ((k & 7) << 1))) = __float2bfloat16(v);
+    }
+}
+
 template <int A, int S>
 __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_fwd_tc_kernel(const HeadArgs a) {
     MVN_PDL_PROLOGUE();
@@ -109,20 +147,26 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_fwd_tc_kernel(con
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sW2 = smem;
     uint8_t* sA = smem + W2_BYTES;                // KC tiles: lrelu(a1)
-    float* sw1 = (float*)(sA + KC * TILE_BYTES);  // [S][A]
+    uint8_t* sLS = sA + KC * TILE_BYTES;          // skip tile (hi | lo)
+    uint8_t* sW1 = sLS + TILE_BYTES;              // W1 image [A][64]
+    float* sw1 = (float*)(sW1 + A * 128);         // [S][A] (only to build the image)
     float* sb1 = sw1 + S * A;
     float* sb2 = sb1 + A;
     float* sx = sb2 + A;                          // [PARTS][128] softmax exchange
     uint64_t* mma_bar = (uint64_t*)(sx + PARTS * 128);
-    uint32_t* tmem_slot = (uint32_t*)(mma_bar + 1);
+    uint64_t* a1_bar = mma_bar + 1;
+    uint32_t* tmem_slot = (uint32_t*)(mma_bar + 2);
     const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, part = tid >> 7, n0 = 32 * part;
 
     for (int i = tid; i < W2_BYTES / 16; i += NT) ((uint4*)sW2)[i] = ((const uint4*)a.img)[i];
     for (int i = tid; i < S * A; i += NT) sw1[i] = a.w1p[i];
+    for (int i = tid; i < TILE_BYTES / 16; i += NT) ((uint4*)sLS)[i] = make_uint4(0, 0, 0, 0);
     if (tid < A) { sb1[tid] = a.b1[tid]; sb2[tid] = a.b2[tid]; }
-    if (tid == 0) { mbar_init(mma_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) { mbar_init(mma_bar, 1); mbar_init(a1_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    build_w1_image<A, S>(sW1, sw1, tid, NT);
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(A) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * A) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     fence_proxy_async();
@@ -134,25 +178,51 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_fwd_tc_kernel(con
     const uint32_t idesc = umma_idesc_major(TILE_T, A, 0, 0);
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    constexpr int A1_COL = A;                     // TMEM: z [0, A) | a1 pre-activation [A, 2A)
 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
         const int b = tile / a.tiles_per_clip, j = (tile - b * a.tiles_per_clip) * TILE_T + r;
         const bool live = j < a.Tn;
         CLK(0, 0);
-        float ls[S];
-        {
+        if (part == 0) {             // one thread per row builds the skip tile
+            float ls[S];
             const float* src = a.skip + ((size_t)b * a.Tout + (live ? j : 0)) * S;
 #pragma unroll
             for (int s = 0; s < S; s += 4) {
                 const float4 v = live ? *(const float4*)(src + s) : make_float4(0.f, 0.f, 0.f, 0.f);
                 ls[s] = lrelu(v.x); ls[s + 1] = lrelu(v.y); ls[s + 2] = lrelu(v.z); ls[s + 3] = lrelu(v.w);
             }
+            store_skip_row<S>(sLS, r, ls);
         }
-        float v[32];
-        head_a1<A, S>(sw1, sb1, ls, n0, v);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (warp_u == 0) {             // a1_pre = skip_tile . W1^T
+            tc_fence_after();
+            const uint64_t kLS = umma_desc(smem_u32(sLS)), kW1 = umma_desc(smem_u32(sW1));
+            if (elect_one()) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i]);
+                for (int k = 0; k < SkipTile<S>::K / 16; ++k)
+                    umma(tmem_u + A1_COL, desc_adv(kLS, k * 32), desc_adv(kW1, k * 32), idesc, k != 0);
+                umma_commit(a1_bar);
+            }
+            __syncwarp();
+        }
+        mbar_wait(a1_bar, it & 1);
+        tc_fence_after();
+        float v[32];
+        {
+            uint32_t p0[16], p1[16];
+            tmem_ld16(tmem + lane_base + A1_COL + n0, p0);
+            tmem_ld16(tmem + lane_base + A1_COL + n0 + 16, p1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                v[i] = lrelu(__uint_as_float(p0[i]) + sb1[n0 + i]);
+                v[16 + i] = lrelu(__uint_as_float(p1[i]) + sb1[n0 + 16 + i]);
+            }
+        }
         CLK(0, 1);
         store_part_row(sA, r, part, v);
         fence_proxy_async();
@@ -220,7 +290,7 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_fwd_tc_kernel(con
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(A) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * A) : "memory");
     }
 }
 
@@ -544,7 +614,7 @@ __global__ void head_pack_kernel(const float* __restrict__ w2, uint8_t* __restri
     *(__nv_bfloat16*)(img + (size_t)kc * A * 128 + n * 128 + ((((kk >> 3) ^ (n & 7)) << 4) | ((kk & 7) << 1))) = __float2bfloat16(w2[i]);
 }
 
-template <int A> int fwd_smem(int S) { return A * A * 2 + (A / 64) * TILE_BYTES + (S * A + 2 * A + (A / 32) * 128) * 4 + 64 + 1024; }
+template <int A> int fwd_smem(int S) { return A * A * 2 + (A / 64 + 1) * TILE_BYTES + A * 128 + (S * A + 2 * A + (A / 32) * 128) * 4 + 64 + 1024; }
 template <int A> int bwd_smem(int S) {
     return A * A * 2 + (3 * (A / 64) + 1) * TILE_BYTES + 1024 + (S * A + A + 3 * (A / 32) * 128 + (A / 32 - 1) * 128 * (S + 1) + 2) * 4 + 64 + 1024;
 }
