@@ -73,22 +73,6 @@ struct HeadArgs {
 __device__ __forceinline__ float lrelu(float v) { return v > 0.f ? v : MVN_LRELU_SLOPE * v; }
 
 // a1[n] for n in [n0, n0+32) of one row, from the row's S skip values (already leaky-ReLU'd)
-template <int A, int S>
-__device__ __forceinline__ void head_a1(const float* sw1, const float* sb1, const float* ls, int n0, float* a1) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) a1[i] = sb1[n0 + i];
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        const float x = ls[s];
-        const float4* w = (const float4*)(sw1 + s * A + n0);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 wv = w[q];
-            a1[4 * q] = fmaf(wv.x, x, a1[4 * q]); a1[4 * q + 1] = fmaf(wv.y, x, a1[4 * q + 1]);
-            a1[4 * q + 2] = fmaf(wv.z, x, a1[4 * q + 2]); a1[4 * q + 3] = fmaf(wv.w, x, a1[4 * q + 3]);
-        }
-    }
-}
 
 // 32 fp32 values of row r, channels [32*part, +32) -> bf16 chunks of the 128B-swizzled [128 x 64] tile(s) at `tiles`
 __device__ __forceinline__ void store_part_row(uint8_t* tiles, int r, int part, const float* v) {
@@ -299,8 +283,11 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
     MVN_PDL_PROLOGUE();
     constexpr int PARTS = A / 32, KC = A / 64, NT = A * 4, W2_BYTES = A * A * 2;
     constexpr int TMEM_COLS = A == 64 ? 256 : 512;
-    // TMEM columns: da_pre [0, A) | weight-gradient accumulators | bias sums
+    // TMEM columns: a1_pre, then da_pre [0, A) | weight-gradient accumulators | bias sums | dskip_pre [NS]
     constexpr int DA_COL = 0, W_COL = A, W1_COL = 2 * A /* A == 128 only */, B_COL = A == 64 ? 192 : 320;
+    constexpr int NS = S < 16 ? 16 : S;           // columns of the dskip GEMM
+    constexpr int DSK_COL = A == 64 ? 224 : 480;
+    static_assert(DSK_COL + NS <= TMEM_COLS, "no TMEM room for the dskip accumulator");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sW2 = smem;
@@ -309,13 +296,16 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
     uint8_t* sLA = sDA + KC * TILE_BYTES;         // A == 64: [LA | LS] adjacent form the N = 128 operand
     uint8_t* sLS = sLA + KC * TILE_BYTES;
     uint8_t* sONES = sLS + TILE_BYTES;            // 1 KB
-    float* sw1 = (float*)(sONES + 1024);          // [S][A]
+    uint8_t* sW1 = sONES + 1024;                  // W1 image [A n][64 k] for a1 = skip_tile . W1^T
+    uint8_t* sW1T = sW1 + A * 128;                // W1 as [NS s][A k] (KC chunks) for dskip = da1 . W1
+    float* sw1 = (float*)(sW1T + KC * NS * 128);  // [S][A] (only to build the images)
     float* sb1 = sw1 + S * A;
     float* sx = sb1 + A;                          // [3][PARTS][128] exchange: <dp,p> partial sums (fused loss: Z, <e,p>, p[target])
-    float* sds = sx + 3 * PARTS * 128;            // [PARTS-1][128][S+1] exchange: dskip partial sums
-    uint64_t* mma_bar = (uint64_t*)(sds + (PARTS - 1) * 128 * (S + 1) + ((PARTS - 1) * 128 * (S + 1) & 1));
+    uint64_t* mma_bar = (uint64_t*)(sx + 3 * PARTS * 128);
     uint64_t* w_bar = mma_bar + 1;
-    uint32_t* tmem_slot = (uint32_t*)(mma_bar + 2);
+    uint64_t* a1_bar = mma_bar + 2;
+    uint64_t* dsk_bar = mma_bar + 3;
+    uint32_t* tmem_slot = (uint32_t*)(mma_bar + 4);
     const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, part = tid >> 7, n0 = 32 * part, sw = r & 7;
 
     for (int i = tid; i < W2_BYTES / 16; i += NT) ((uint4*)sW2)[i] = ((const uint4*)a.img)[i];
@@ -323,7 +313,17 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
     if (tid < A) sb1[tid] = a.b1[tid];
     for (int i = tid; i < TILE_BYTES / 16; i += NT) ((uint4*)sLS)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < 256; i += NT) ((uint32_t*)sONES)[i] = 0x3F803F80u;
-    if (tid == 0) { mbar_init(mma_bar, 1); mbar_init(w_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid == 0) {
+        mbar_init(mma_bar, 1); mbar_init(w_bar, 1); mbar_init(a1_bar, 1); mbar_init(dsk_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    build_w1_image<A, S>(sW1, sw1, tid, NT);
+    for (int i = tid; i < KC * NS * 64; i += NT) {      // [kc][s][k]: w1p[s][64 kc + k], rows s >= S are zero
+        const int kc = i / (NS * 64), s_ = (i / 64) % NS, k = i & 63;
+        const float v = s_ < S ? sw1[s_ * A + 64 * kc + k] : 0.f;
+        *(__nv_bfloat16*)(sW1T + kc * NS * 128 + s_ * 128 + ((((k >> 3) ^ (s_ & 7)) << 4) | ((k & 7) << 1))) = __float2bfloat16(v);
+    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -338,6 +338,8 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
     const uint32_t iW = umma_idesc_major(TILE_T, 128, 1, 1);
     const uint32_t iW1 = umma_idesc_major(TILE_T, 64, 1, 1);
     const uint32_t iB = umma_idesc_major(TILE_T, 16, 1, 1);
+    const uint32_t iA1 = umma_idesc_major(TILE_T, A, 0, 0);        // a1_pre = skip_tile . W1^T
+    const uint32_t iDS = umma_idesc_major(TILE_T, NS, 0, 0);       // dskip_pre = da1 . W1
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
 
@@ -361,9 +363,10 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
         }
         // ---- loads first (their latency overlaps the previous tile's weight-gradient MMAs) ----------
         CLK(1, 0);
-        float ls[S];
         unsigned long long skip_pos = 0;
-        {
+        if (it) { mbar_wait(w_bar, (it - 1) & 1); tc_fence_after(); }      // previous tile's MMAs are done with the tiles
+        if (part == 0) {             // one thread per row: the skip tile (hi | lo) for the a1 GEMM and the weight gradient
+            float ls[S];
             const float* src = a.skip + ((size_t)b * a.Tout + (live ? j : 0)) * S;
 #pragma unroll
             for (int s = 0; s < S; s += 4) {
@@ -372,6 +375,21 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { skip_pos |= (unsigned long long)(x[e] > 0.f) << (s + e); ls[s + e] = lrelu(x[e]); }
             }
+            store_skip_row<S>(sLS, r, ls);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (warp_u == 0) {             // a1_pre = skip_tile . W1^T into the (still free) da_pre columns; runs under the loads below
+            tc_fence_after();
+            const uint64_t kLS = umma_desc(smem_u32(sLS)), kW1 = umma_desc(smem_u32(sW1));
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < SkipTile<S>::K / 16; ++k)
+                    umma(tmem_u + DA_COL, desc_adv(kLS, k * 32), desc_adv(kW1, k * 32), iA1, k != 0);
+                umma_commit(a1_bar);
+            }
+            __syncwarp();
         }
         float dz[32];
         {
@@ -420,22 +438,26 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
         }
         CLK(1, 1);
         float a1[32];
-        head_a1<A, S>(sw1, sb1, ls, n0, a1);
         uint32_t a1_pos = 0;
+        mbar_wait(a1_bar, it & 1);
+        tc_fence_after();
+        {
+            uint32_t p0[16], p1[16];
+            tmem_ld16(tmem + lane_base + DA_COL + n0, p0);
+            tmem_ld16(tmem + lane_base + DA_COL + n0 + 16, p1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                a1[i] = __uint_as_float(p0[i]) + sb1[n0 + i];
+                a1[16 + i] = __uint_as_float(p1[i]) + sb1[n0 + 16 + i];
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) { a1_pos |= (uint32_t)(a1[i] > 0.f) << i; a1[i] = lrelu(a1[i]); }
         CLK(1, 2);
-        if (it) { mbar_wait(w_bar, (it - 1) & 1); tc_fence_after(); }      // previous tile's MMAs are done with the tiles
         CLK(1, 3);
         store_part_row(sDZ, r, part, dz);
         store_part_row(sLA, r, part, a1);
-        if (part == 0) {
-#pragma unroll
-            for (int s = 0; s < S; s += 8)
-                *(uint4*)(sLS + r * 128 + (((s >> 3) ^ sw) << 4)) =
-                    make_uint4(pack_bf16(ls[s], ls[s + 1]), pack_bf16(ls[s + 2], ls[s + 3]), pack_bf16(ls[s + 4], ls[s + 5]),
-                               pack_bf16(ls[s + 6], ls[s + 7]));
-        }
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -469,22 +491,6 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
             }
         }
         store_part_row(sDA, r, part, da);
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const float4* w = (const float4*)(sw1 + s * A + n0);
-            float acc = 0.f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 wv = w[q];
-                acc = fmaf(wv.x, da[4 * q], acc); acc = fmaf(wv.y, da[4 * q + 1], acc);
-                acc = fmaf(wv.z, da[4 * q + 2], acc); acc = fmaf(wv.w, da[4 * q + 3], acc);
-            }
-            ls[s] = acc;                         // reuse: partial dskip over this thread's 32 channels
-        }
-        if (part > 0) {
-#pragma unroll
-            for (int s = 0; s < S; ++s) sds[((part - 1) * 128 + r) * (S + 1) + s] = ls[s];
-        }
         CLK(1, 6);
         fence_proxy_async();
         tc_fence_before();
@@ -496,7 +502,15 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
             const uint64_t ones = umma_desc_mn_plain(smem_u32(sONES), 256, 128);
             const uint64_t mDZ = umma_desc_mn(smem_u32(sDZ), TILE_BYTES), mLA = umma_desc_mn(smem_u32(sLA), TILE_BYTES),
                            mDA = umma_desc_mn(smem_u32(sDA), TILE_BYTES), mLS = umma_desc_mn(smem_u32(sLS), TILE_BYTES);
+            const uint64_t kDA = umma_desc(smem_u32(sDA)), kW1T = umma_desc(smem_u32(sW1T));
             if (elect_one()) {
+                // dskip_pre[t][s] = sum_a da1[t][a] W1[a][s]  (first: one thread per row is waiting for it)
+#pragma unroll
+                for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma(tmem_u + DSK_COL, desc_adv(kDA, kc * TILE_BYTES + k * 32), desc_adv(kW1T, kc * NS * 128 + k * 32), iDS, (kc | k) != 0);
+                umma_commit(dsk_bar);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint32_t acc = acc0 | (k != 0);
@@ -514,23 +528,27 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
             }
             __syncwarp();
         }
-        if (part == 0 && live) {
-            float* dst = a.dskip + ((size_t)b * a.Tout + j) * S;
+        mbar_wait(dsk_bar, it & 1);
+        tc_fence_after();
+        if (part == 0) {             // dskip = dskip_pre * lrelu'(skip): one thread per row (warp-uniform: TMEM loads are collective)
+            float* dst = a.dskip + ((size_t)b * a.Tout + (live ? j : 0)) * S;
 #pragma unroll
-            for (int s = 0; s < S; s += 4) {
-                float o[4];
+            for (int s = 0; s < S; s += 8) {
+                uint32_t v[8];
+                tmem_ld8(tmem + lane_base + DSK_COL + s, v);
+                tmem_ld_wait();
+                if (live) {
+                    float o[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float acc = ls[s + e];
-#pragma unroll
-                    for (int q = 0; q < PARTS - 1; ++q) acc += sds[(q * 128 + r) * (S + 1) + s + e];
-                    o[e] = acc * ((skip_pos >> (s + e)) & 1 ? 1.f : MVN_LRELU_SLOPE);
+                    for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[e]) * ((skip_pos >> (s + e)) & 1 ? 1.f : MVN_LRELU_SLOPE);
+                    *(float4*)(dst + s) = make_float4(o[0], o[1], o[2], o[3]);
+                    *(float4*)(dst + s + 4) = make_float4(o[4], o[5], o[6], o[7]);
                 }
-                *(float4*)(dst + s) = make_float4(o[0], o[1], o[2], o[3]);
             }
         }
         CLK(1, 8);
-        __syncthreads();           // sds / sx are reused by the next tile
+        tc_fence_before();
+        __syncthreads();           // sx is reused by the next tile; the dskip accumulator has been read
         CLK(1, 9);
     }
     if (it) { mbar_wait(w_bar, (it - 1) & 1); }
@@ -616,7 +634,7 @@ __global__ void head_pack_kernel(const float* __restrict__ w2, uint8_t* __restri
 
 template <int A> int fwd_smem(int S) { return A * A * 2 + (A / 64 + 1) * TILE_BYTES + A * 128 + (S * A + 2 * A + (A / 32) * 128) * 4 + 64 + 1024; }
 template <int A> int bwd_smem(int S) {
-    return A * A * 2 + (3 * (A / 64) + 1) * TILE_BYTES + 1024 + (S * A + A + 3 * (A / 32) * 128 + (A / 32 - 1) * 128 * (S + 1) + 2) * 4 + 64 + 1024;
+    return A * A * 2 + (3 * (A / 64) + 1) * TILE_BYTES + 1024 + A * 128 + (A / 64) * (S < 16 ? 16 : S) * 128 + (S * A + A + 3 * (A / 32) * 128 + 2) * 4 + 64 + 1024;
 }
 
 template <int A, int S>
@@ -637,7 +655,7 @@ int launch_bwd(const HeadArgs& a, int grid, cudaStream_t st) {
 }  // namespace
 
 int mvn_tc_head_supported(int A, int S) {
-    if (A == 64) return S == 8 || S == 16 || S == 32 || S == 64;
+    if (A == 64) return S == 8 || S == 16 || S == 32;
     if (A == 128) return S == 8 || S == 16 || S == 32;
     return 0;
 }
@@ -659,7 +677,7 @@ static void fill_args(HeadArgs& a, const float* packed, const PackedLayout& P, c
         int rc_ = -1;                                                                                   \
         if (g.A == 64) {                                                                                \
             if (g.S == 8) rc_ = FN<64, 8>(__VA_ARGS__); else if (g.S == 16) rc_ = FN<64, 16>(__VA_ARGS__); \
-            else if (g.S == 32) rc_ = FN<64, 32>(__VA_ARGS__); else if (g.S == 64) rc_ = FN<64, 64>(__VA_ARGS__); \
+            else if (g.S == 32) rc_ = FN<64, 32>(__VA_ARGS__);                                          \
         } else if (g.A == 128) {                                                                        \
             if (g.S == 8) rc_ = FN<128, 8>(__VA_ARGS__); else if (g.S == 16) rc_ = FN<128, 16>(__VA_ARGS__); \
             else if (g.S == 32) rc_ = FN<128, 32>(__VA_ARGS__);                                         \
