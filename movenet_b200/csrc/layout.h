@@ -62,6 +62,7 @@ struct PackedLayout {
     size_t wv, bv;              // video conv: [4096*Cin][C], [C]
     size_t wt[3], bt[3], wtT[3];// transposed convs: [C][10C], [10C] (bias tiled), [10C][C]
     size_t tc_up;               // tensor-core image of the last upsampler level (bf16 [640][64] + bias), video && C == 64
+    size_t tc_up01[2];          // ... and of the first two levels
     size_t total;               // elements
 };
 
@@ -88,8 +89,9 @@ static inline void packed_layout(const Geo& g, PackedLayout& p) {
         p.wv = take((size_t)4096 * g.Cin * C); p.bv = take(C);
         for (int i = 0; i < 3; ++i) { p.wt[i] = take(C * 10 * C); p.bt[i] = take(10 * C); p.wtT[i] = take(10 * C * C); }
         p.tc_up = take(C == 64 ? (5 * 16384 + 3072) / 4 : 0);
+        for (int i = 0; i < 2; ++i) p.tc_up01[i] = take(C == 64 ? (5 * 16384 + 3072) / 4 : 0);
     } else {
-        p.tc_up = 0;
+        p.tc_up = 0; p.tc_up01[0] = p.tc_up01[1] = 0;
         p.wv = p.bv = 0;
         for (int i = 0; i < 3; ++i) p.wt[i] = p.bt[i] = p.wtT[i] = 0;
     }

@@ -197,7 +197,11 @@ extern "C" int mvn_pack_weights(const mvn_shape_t* s, const void* const* param_p
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S))   // conv2.weight is (A, A, 1): already [n][k]
         if ((rc = mvn_tc_head_pack((const float*)packed + P.w2pT, (float*)packed, P, g.A, st))) return rc;
     if (g.adt == MVN_DTYPE_BF16 && g.video && mvn_tc_upsample_supported(g.C))
+    {
         if ((rc = mvn_tc_upsample_pack((const float*)packed + P.wt[2], (const float*)packed + P.bt[2], (float*)packed + P.tc_up, st))) return rc;
+        for (int i = 0; i < 2; ++i)
+            if ((rc = mvn_tc_upsample_pack((const float*)packed + P.wt[i], (const float*)packed + P.bt[i], (float*)packed + P.tc_up01[i], st))) return rc;
+    }
     return 0;
 }
 

@@ -59,7 +59,7 @@ __global__ void up_pack_kernel(const float* __restrict__ wt, const float* __rest
     }
 }
 
-struct UpArgs { const void* img; float* du2; float* partial; long long rows; int n_tiles; };
+struct UpArgs { const void* img; float* du2; float* partial; long long rows; int n_tiles; int du_bf16; };
 
 __global__ void __launch_bounds__(256, 1)
 up_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_u2, const __grid_constant__ CUtensorMap map_ctx, const UpArgs a) {
@@ -233,18 +233,27 @@ up_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_u2, const __grid_consta
         }
         mbar_wait(fin_bar, it & 1);
         tc_fence_after();
-        {   // d(u2) rows -> fp32 (B*16000, 64)
+        {   // d(input) rows -> (rows, 64), fp32 or (when the level below also runs here and reads it as its d(output)) bf16
             float* dst = a.du2 + (size_t)(row0 + r) * 64 + 32 * half;
+            __nv_bfloat16* dsth = (__nv_bfloat16*)a.du2 + (size_t)(row0 + r) * 64 + 32 * half;
 #pragma unroll 1
             for (int j = 0; j < 2; ++j) {
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + DU_COL + 32 * half + 16 * j, v);
                 tmem_ld_wait();
                 if (row0 + r < a.rows) {
+                    if (a.du_bf16) {
+                        uint32_t o[8];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        ((float4*)(dst + 16 * j))[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                                                   __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                        for (int q = 0; q < 8; ++q) o[q] = pack_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+                        ((uint4*)(dsth + 16 * j))[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                        ((uint4*)(dsth + 16 * j))[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            ((float4*)(dst + 16 * j))[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                    }
                 }
             }
         }
@@ -300,7 +309,7 @@ int mvn_tc_upsample_fwd(const float* img, const void* u2_bf16, void* ctx_bf16, l
     CUtensorMap mu, mc; int rc;
     if ((rc = make_wide_map(&mc, ctx_bf16, rows, UN))) return rc;
     if ((rc = make_wide_map(&mu, u2_bf16, rows, 64))) return rc;
-    UpArgs a; a.img = img; a.du2 = nullptr; a.partial = nullptr; a.rows = rows; a.n_tiles = (int)((rows + TILE_T - 1) / TILE_T);
+    UpArgs a; a.img = img; a.du2 = nullptr; a.partial = nullptr; a.rows = rows; a.n_tiles = (int)((rows + TILE_T - 1) / TILE_T); a.du_bf16 = 0;
     const int smem = IMG_BYTES + 3072 + 5 * TILE_BYTES + 64 + 1024;
     static bool attr = false;
     if (!attr) { MVN_CUDA(cudaFuncSetAttribute(up_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
@@ -309,12 +318,13 @@ int mvn_tc_upsample_fwd(const float* img, const void* u2_bf16, void* ctx_bf16, l
     return mvn_check_launch("upsample_fwd_tc");
 }
 
-int mvn_tc_upsample_bwd(const float* img, const void* u2_bf16, const void* dctx_bf16, float* du2, float* dwt, float* dbt,
+int mvn_tc_upsample_bwd(const float* img, const void* u2_bf16, const void* dctx_bf16, void* du2, int du_bf16, float* dwt, float* dbt,
                         float* partial, long long rows, cudaStream_t st) {
     CUtensorMap mu, md; int rc;
     if ((rc = make_wide_map(&mu, u2_bf16, rows, 64))) return rc;
     if ((rc = make_wide_map(&md, dctx_bf16, rows, UN))) return rc;
-    UpArgs a; a.img = img; a.du2 = du2; a.partial = partial; a.rows = rows; a.n_tiles = (int)((rows + TILE_T - 1) / TILE_T);
+    UpArgs a; a.img = img; a.du2 = (float*)du2; a.partial = partial; a.rows = rows; a.n_tiles = (int)((rows + TILE_T - 1) / TILE_T);
+    a.du_bf16 = du_bf16;
     const int smem = IMG_BYTES + 5 * TILE_BYTES + 1024 + 64 + 1024;
     static bool attr = false;
     if (!attr) { MVN_CUDA(cudaFuncSetAttribute(up_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }

@@ -295,6 +295,11 @@ __global__ void softmax_nct_bwd_kernel(const float* __restrict__ probs, const fl
     }
 }
 
+__global__ void to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __float2bfloat16(src[i]);
+}
+
 __global__ void to_f32_kernel(const void* __restrict__ src, int dtype, float* __restrict__ dst, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dst[i] = mvn_ld(src, dtype, i);
@@ -431,13 +436,21 @@ static int video_fwd(const Ctx& c, const float* video) {
     // row-major output IS the time-major upsampled signal (movenet/wavenet.py:102-118,154)
     const void* in[3] = {enc, u1, u2}; void* out[3] = {u1, u2, ctx};
     const int len[3] = {160, 1600, 16000};
-    const bool tc3 = g.adt == MVN_DTYPE_BF16 && mvn_tc_upsample_supported(C);   // last level on tensor cores: u2 kept in bf16
+    const bool tc3 = g.adt == MVN_DTYPE_BF16 && mvn_tc_upsample_supported(C);   // all three levels on tensor cores: u1, u2 kept in bf16
+    if (tc3) {
+        // bf16 copy of the encoder output in the (free) second half of the u1 slot
+        void* enc16 = (char*)u1 + (size_t)g.B * 1600 * C * 2;
+        to_bf16_kernel<<<mvn_cdiv((long long)g.B * 160 * C, 256), 256, 0, c.st>>>(enc, (__nv_bfloat16*)enc16, (long long)g.B * 160 * C);
+        if ((rc = mvn_check_launch("to_bf16"))) return rc;
+        if ((rc = mvn_tc_upsample_fwd(c.packed + c.P.tc_up01[0], enc16, u1, g.B * len[0], c.st))) return rc;
+        if ((rc = mvn_tc_upsample_fwd(c.packed + c.P.tc_up01[1], u1, u2, g.B * len[1], c.st))) return rc;
+        return mvn_tc_upsample_fwd(c.packed + c.P.tc_up, u2, ctx, g.B * len[2], c.st);
+    }
     for (int i = 0; i < 3; ++i) {
         const int rows = g.B * len[i];
-        if (i == 2 && tc3) return mvn_tc_upsample_fwd(c.packed + c.P.tc_up, u2, ctx, rows, c.st);
         RowGemmArgs a = new_args(rows, rows, 10 * C, EPI_STORE, c.packed + c.P.bt[i]);
         a.nsrc = 1; a.src[0] = make_src(in[i], MVN_F32, C, C, rows, 0, 0, c.packed + c.P.wt[i], 10 * C);
-        set_out(a, out[i], (i == 2 || (i == 1 && tc3)) ? g.adt : MVN_F32, 10 * C, rows, 0);
+        set_out(a, out[i], i == 2 ? g.adt : MVN_F32, 10 * C, rows, 0);
         a.allow_ksplit = 1;
         if ((rc = mvn_row_gemm(a, c.st))) return rc;
     }
@@ -689,10 +702,13 @@ static int video_bwd(const Ctx& c, const float* video, const void* dctx, int dct
     const int ddt[3] = {MVN_F32, MVN_F32, dctx_dtype};
     const int len[3] = {160, 1600, 16000};
     int rc;
+    const bool tc = dctx_dtype == MVN_BF16 && g.adt == MVN_DTYPE_BF16 && mvn_tc_upsample_supported(C);
     for (int i = 2; i >= 0; --i) {
         const int rows = g.B * len[i];
-        if (i == 2 && dctx_dtype == MVN_BF16 && g.adt == MVN_DTYPE_BF16 && mvn_tc_upsample_supported(C)) {
-            if ((rc = mvn_tc_upsample_bwd(c.packed + c.P.tc_up, u2, dctx, du2, pg + c.P.wt[2], pg + c.P.bt[2],
+        if (tc) {      // every level on tensor cores: bf16 inputs (enc16, u1, u2) and bf16 gradients between the levels
+            const void* in16 = i == 0 ? (const void*)((const char*)u1 + (size_t)g.B * 1600 * C * 2) : (const void*)in[i];
+            const float* img = c.packed + (i == 2 ? c.P.tc_up : c.P.tc_up01[i]);
+            if ((rc = mvn_tc_upsample_bwd(img, in16, dout[i], din[i], i > 0, pg + c.P.wt[i], pg + c.P.bt[i],
                                           (float*)(c.scratch + c.SL.tc_partial), rows, c.st))) return rc;
             continue;
         }
