@@ -15,12 +15,28 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ p
     float loss = 0.f;
     if (t < T) {
         const float* col = p + (size_t)b * A * T + t;
-        float m = -INFINITY;
-        for (int c = 0; c < A; ++c) m = fmaxf(m, col[(size_t)c * T]);
-        float s = 0.f;
-        for (int c = 0; c < A; ++c) s += expf(col[(size_t)c * T] - m);
+        // one pass (online max / sum): the tensor is read once; eight independent loads in flight per thread
         const long long tg = target[(size_t)b * T + t];
-        loss = (m + logf(s)) - col[(size_t)tg * T];
+        float m = -INFINITY, s = 0.f, pt = 0.f;
+        int c = 0;
+        for (; c + 8 <= A; c += 8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = col[(size_t)(c + i) * T];
+            float m8 = v[0];
+#pragma unroll
+            for (int i = 1; i < 8; ++i) m8 = fmaxf(m8, v[i]);
+            if (m8 > m) { s *= expf(m - m8); m = m8; }        // exp(-inf) = 0 on the first group
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { s += expf(v[i] - m); if (c + i == tg) pt = v[i]; }
+        }
+        for (; c < A; ++c) {
+            const float v = col[(size_t)c * T];
+            if (v > m) { s *= expf(m - v); m = v; }
+            s += expf(v - m);
+            if (c == tg) pt = v;
+        }
+        loss = (m + logf(s)) - pt;
     }
     __shared__ float red[8];
     for (int o = 16; o; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
