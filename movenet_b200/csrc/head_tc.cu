@@ -124,7 +124,7 @@ __device__ __forceinline__ void build_w1_image(uint8_t* img, const float* sw1, i
 }
 
 template <int A, int S>
-__global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_fwd_tc_kernel(const HeadArgs a) {
+__global__ void __launch_bounds__(A * 4, A == 64 ? 4 : 1) head_fwd_tc_kernel(const HeadArgs a) {
     MVN_PDL_PROLOGUE();
     constexpr int PARTS = A / 32, KC = A / 64, NT = A * 4, W2_BYTES = A * A * 2;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
