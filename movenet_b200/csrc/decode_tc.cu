@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
     uint8_t* simg = smem;
     const int A = a.A;
     const int tid = threadIdx.x, grp = tid >> 7, r = tid & 127, warp = tid >> 5;
+    // the first warp of each group issues its MMAs from warp-uniform code through one elected lane (tc_common.cuh)
+    const bool issue_warp = __shfl_sync(0xffffffffu, (tid >> 5) & 3, 0) == 0;
     // per-group tiles after the image: layer A [128 x 2C] | gated [128 x C], and -- aliased onto them, the layers are
     // finished when the head runs -- the head's A tile [128 x max(16, A)]
     const int layer_tiles = 128 * 2 * C * 2 + 128 * C * 2, head_tile = 128 * A * 2;
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot + grp * (512 / GROUPS);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     // TMEM columns of the group's window: D1 [0, 2C) ; D2 [2C, 2C + N2) ; the head reuses [0, A) once the layers are done
     constexpr int D1 = 0, D2 = 2 * C, DH = 0;
@@ -166,12 +169,15 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
             fence_proxy_async();
             tc_fence_before();
             group_sync(grp);
-            if (r == 0) {
+            if (issue_warp) {
                 tc_fence_after();
+                const uint64_t dA = desc_k_plain(smem_u32(sA), 2 * C), dW = desc_k_plain(smem_u32(li + I::wz), 2 * C);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 2 * C / 16; ++k)
-                    umma(tmem + D1, desc_k_plain(smem_u32(sA) + k * 256, 2 * C), desc_k_plain(smem_u32(li + I::wz) + k * 256, 2 * C), i1, k != 0);
-                umma_commit(mma_bar);
+                    for (int k = 0; k < 2 * C / 16; ++k) umma(tmem_u + D1, desc_adv(dA, k * 256), desc_adv(dW, k * 256), i1, k != 0);
+                    umma_commit(mma_bar);
+                }
+                __syncwarp();
             }
             mbar_wait(mma_bar, phase); phase ^= 1;
             tc_fence_after();
@@ -196,12 +202,15 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
             fence_proxy_async();
             tc_fence_before();
             group_sync(grp);
-            if (r == 0) {
+            if (issue_warp) {
                 tc_fence_after();
+                const uint64_t dG = desc_k_plain(smem_u32(sG), C), dW = desc_k_plain(smem_u32(li + I::wrs), C);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < C / 16; ++k)
-                    umma(tmem + D2, desc_k_plain(smem_u32(sG) + k * 256, C), desc_k_plain(smem_u32(li + I::wrs) + k * 256, C), i2, k != 0);
-                umma_commit(mma_bar);
+                    for (int k = 0; k < C / 16; ++k) umma(tmem_u + D2, desc_adv(dG, k * 256), desc_adv(dW, k * 256), i2, k != 0);
+                    umma_commit(mma_bar);
+                }
+                __syncwarp();
             }
             mbar_wait(mma_bar, phase); phase ^= 1;
             tc_fence_after();
@@ -232,10 +241,14 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
         fence_proxy_async();
         tc_fence_before();
         group_sync(grp);
-        if (r == 0) {
+        if (issue_warp) {
             tc_fence_after();
-            umma(tmem + DH, desc_k_plain(smem_u32(sH), 16), desc_k_plain(smem_u32(simg + a.oW1), 16), ih, 0);
-            umma_commit(mma_bar);
+            const uint64_t dH = desc_k_plain(smem_u32(sH), 16), dW = desc_k_plain(smem_u32(simg + a.oW1), 16);
+            if (elect_one()) {
+                umma(tmem_u + DH, dH, dW, ih, 0);
+                umma_commit(mma_bar);
+            }
+            __syncwarp();
         }
         mbar_wait(mma_bar, phase); phase ^= 1;
         tc_fence_after();
@@ -258,11 +271,14 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
         fence_proxy_async();
         tc_fence_before();
         group_sync(grp);          // also: every thread has finished reading a1 from TMEM before it is overwritten
-        if (r == 0) {
+        if (issue_warp) {
             tc_fence_after();
-            for (int k = 0; k < A / 16; ++k)
-                umma(tmem + DH, desc_k_plain(smem_u32(sH) + k * 256, A), desc_k_plain(smem_u32(simg + a.oW2) + k * 256, A), ih, k != 0);
-            umma_commit(mma_bar);
+            const uint64_t dH = desc_k_plain(smem_u32(sH), A), dW = desc_k_plain(smem_u32(simg + a.oW2), A);
+            if (elect_one()) {
+                for (int k = 0; k < A / 16; ++k) umma(tmem_u + DH, desc_adv(dH, k * 256), desc_adv(dW, k * 256), ih, k != 0);
+                umma_commit(mma_bar);
+            }
+            __syncwarp();
         }
         mbar_wait(mma_bar, phase); phase ^= 1;
         tc_fence_after();

@@ -44,6 +44,8 @@ input_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_cons
     const uint32_t tmem = *tmem_slot;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const uint32_t idesc = umma_idesc_major(TILE_T, 64, 1, 1);
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
 
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
@@ -88,16 +90,20 @@ input_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_cons
         mbar_wait(full_bar, it & 1);
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0) {             // warp-uniform issue through one elected lane (tc_common.cuh)
             tc_fence_after();
             const uint32_t acc0 = it != 0;
+            const uint64_t mOH = umma_desc_mn(smem_u32(sOH), TILE_BYTES), mP = umma_desc_mn(smem_u32(sP), TILE_BYTES),
+                           mU = umma_desc_mn(smem_u32(sU), TILE_BYTES);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint64_t oh = umma_desc_mn(smem_u32(sOH) + k * 2048, TILE_BYTES);
-                umma(tmem, oh, umma_desc_mn(smem_u32(sP) + k * 2048, TILE_BYTES), idesc, acc0 | (k != 0));
-                umma(tmem, oh, umma_desc_mn(smem_u32(sU) + k * 2048, TILE_BYTES), idesc, 1);
+                for (int k = 0; k < 8; ++k) {
+                    umma(tmem_u, desc_adv(mOH, k * 2048), desc_adv(mP, k * 2048), idesc, acc0 | (k != 0));
+                    umma(tmem_u, desc_adv(mOH, k * 2048), desc_adv(mU, k * 2048), idesc, 1);
+                }
+                umma_commit(w_bar);
             }
-            umma_commit(w_bar);
+            __syncwarp();
         }
     }
     if (it) mbar_wait(w_bar, (it - 1) & 1);
