@@ -151,15 +151,22 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
 #pragma unroll
         for (int s = 0; s < DS; ++s) skip[s] = 0.f;
 
+        // the queue rows x_l[tau - d] do not depend on this step's arithmetic: the row of layer l + 1 is fetched while layer l
+        // computes (one global-memory latency per layer would otherwise sit on the token's critical path)
+        auto ring_of = [&](int l) { return a.queues + a.qoff[l] * a.B + ((size_t)(tau % a.dil[l]) * a.B + (live ? b : 0)) * C; };
+        uint4 old_next[C / 8];
+#pragma unroll
+        for (int q = 0; q < C / 8; ++q) {
+            old_next[q] = make_uint4(0, 0, 0, 0);
+            if (live && tau - a.dil[0] >= 0) old_next[q] = ((const uint4*)ring_of(0))[q];
+        }
         for (int l = 0; l < a.N; ++l) {
             const uint8_t* li = simg + (size_t)l * I::layer_bytes;
-            const int d = a.dil[l];
-            __nv_bfloat16* ring = a.queues + a.qoff[l] * a.B + ((size_t)(tau % d) * a.B + (live ? b : 0)) * C;
+            __nv_bfloat16* ring = ring_of(l);
             // A row = [x_l[tau - d] | x_l[tau]] ; then push x_l[tau]
 #pragma unroll
             for (int q = 0; q < C / 8; ++q) {
-                uint4 old = make_uint4(0, 0, 0, 0);
-                if (live && tau - d >= 0) old = ((const uint4*)ring)[q];
+                const uint4 old = old_next[q];
                 *(uint4*)(sA + core_off(r, 8 * q, 2 * C)) = old;
                 const uint4 cur = make_uint4(pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
                                              pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
@@ -178,6 +185,12 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
                     umma_commit(mma_bar);
                 }
                 __syncwarp();
+            }
+            if (l + 1 < a.N) {
+                const __nv_bfloat16* nring = ring_of(l + 1);
+                const bool has = live && tau - a.dil[l + 1] >= 0;
+#pragma unroll
+                for (int q = 0; q < C / 8; ++q) old_next[q] = has ? ((const uint4*)nring)[q] : make_uint4(0, 0, 0, 0);
             }
             mbar_wait(mma_bar, phase); phase ^= 1;
             tc_fence_after();
