@@ -114,43 +114,51 @@ __global__ void __launch_bounds__(256) input_fwd_smem_kernel(const float* __rest
                                                             void* __restrict__ h0, int adt, int A, int C, int T, int rows) {
     MVN_PDL_PROLOGUE();
     extern __shared__ float swin[];
+    constexpr int CHUNK = 256;                       // rows per step of a CTA: their codes are fetched together (one global latency)
+    __shared__ int scode[CHUNK + 1];                 // entry i = row (chunk start - 1 + i); negative: not one-hot (dense path)
     for (int i = threadIdx.x; i < 2 * A * C / 4; i += blockDim.x) ((float4*)swin)[i] = ((const float4*)win)[i];
-    __syncthreads();
-    const int cg = C / 8, rows_per_iter = blockDim.x / cg;
+    const int cg = C / 8, rows_per_pass = blockDim.x / cg;
     const int sub = threadIdx.x / cg, c0 = (threadIdx.x % cg) * 8;
-    if (sub >= rows_per_iter) return;
-    for (int row = blockIdx.x * rows_per_iter + sub; row < rows; row += gridDim.x * rows_per_iter) {
-        const int b = row / T, t = row - b * T;
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int chunk0 = blockIdx.x * CHUNK; chunk0 < rows; chunk0 += gridDim.x * CHUNK) {
+        __syncthreads();                              // the table is in place / the previous chunk's codes are no longer read
+        for (int i = threadIdx.x; i < CHUNK + 1; i += blockDim.x) {
+            const int rr = chunk0 - 1 + i;
+            scode[i] = (rr >= 0 && rr < rows) ? (dense[rr] ? -1 : codes[rr]) : 0;
+        }
+        __syncthreads();
+        for (int local = sub; local < CHUNK && chunk0 + local < rows; local += rows_per_pass) {
+            const int row = chunk0 + local, b = row / T, t = row - b * T;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int tap = 0; tap < 2; ++tap) {
-            const int ts = t - 1 + tap;
-            if (ts < 0) continue;
-            const int r = row - 1 + tap;
-            const float* wt = swin + tap * A * C;
-            if (!dense[r]) {
-                const float* wr = wt + codes[r] * C + c0;
-                const float4 w0 = ((const float4*)wr)[0], w1 = ((const float4*)wr)[1];
-                acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
-                acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
-            } else {
-                for (int a = 0; a < A; ++a) {
-                    const float x = audio[((size_t)b * A + a) * T + ts];
-                    if (x != 0.f) {
+            for (int tap = 0; tap < 2; ++tap) {
+                const int ts = t - 1 + tap;
+                if (ts < 0) continue;                 // x[-1] = 0: the first column of a clip has no tap 0
+                const float* wt = swin + tap * A * C;
+                const int code = scode[local + tap];
+                if (code >= 0) {
+                    const float* wr = wt + code * C + c0;
+                    const float4 w0 = ((const float4*)wr)[0], w1 = ((const float4*)wr)[1];
+                    acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
+                    acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
+                } else {
+                    for (int ch = 0; ch < A; ++ch) {
+                        const float x = audio[((size_t)b * A + ch) * T + ts];
+                        if (x != 0.f) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[j] = fmaf(x, wt[a * C + c0 + j], acc[j]);
+                            for (int j = 0; j < 8; ++j) acc[j] = fmaf(x, wt[ch * C + c0 + j], acc[j]);
+                        }
                     }
                 }
             }
-        }
-        if (adt == MVN_BF16) {
-            __nv_bfloat162 o[4];
+            if (adt == MVN_BF16) {
+                __nv_bfloat162 o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
-            *(uint4*)((__nv_bfloat16*)h0 + (size_t)row * C + c0) = *(const uint4*)o;
-        } else {
-            float4* d = (float4*)((float*)h0 + (size_t)row * C + c0);
-            d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]); d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+                for (int j = 0; j < 4; ++j) o[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+                *(uint4*)((__nv_bfloat16*)h0 + (size_t)row * C + c0) = *(const uint4*)o;
+            } else {
+                float4* d = (float4*)((float*)h0 + (size_t)row * C + c0);
+                d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]); d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
         }
     }
 }
