@@ -229,9 +229,12 @@ def layer_roofline(model, audio, video, dtype):
     vid = video is not None
     # algorithmic bytes per audio sample of one layer
     fwd_b = Cc * e + Cc * e + (Cc * e if vid else 0) + 8 * S                 # read x, write x', read ctx, RMW skip_sum
-    # backward: read x, P, U (stream gradient pair), d(skip) (+ ctx and the ctx-gradient stream Q);
-    #           write P', U' (+ Q')
-    bwd_b = 3 * Cc * e + 4 * S + 2 * Cc * e + (3 * Cc * e if vid else 0)
+    # backward: read x, the stream gradient D, d(skip) (+ ctx and the ctx-gradient running sum Q); write D' (+ Q').
+    # Layers with dilation <= 128 (all of this workload's) exchange ONE summed gradient stream; with
+    # MOVENET_B200_BWD_PAIR=1 (or a wider dilation) the gradient travels as the pair (P, U): one more read and one more write.
+    pair = bool(int(os.environ.get("MOVENET_B200_BWD_PAIR", "0"))) or max(model.residual_conv_stack.dilations) > 128
+    streams = 2 if pair else 1
+    bwd_b = Cc * e + streams * Cc * e + 4 * S + streams * Cc * e + (3 * Cc * e if vid else 0)
     pk = peaks()
     n = B * T_CLIP
 

@@ -18,6 +18,7 @@ struct InArgs {
     const float* audio; const int* codes; const unsigned char* dense;
     float* partial;
     int B, T, A, dil0, tiles_per_clip, n_tiles;
+    int has_u;            // the gradient comes as the pair (P, U); otherwise one summed stream
 };
 
 __global__ void __launch_bounds__(128, 3)
@@ -52,9 +53,9 @@ input_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_cons
         const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T, t = t0 + r;
         if (it) { mbar_wait(w_bar, (it - 1) & 1); tc_fence_after(); }     // the previous tile's MMAs are done with the tiles
         if (tid == 0) {
-            mbar_expect_tx(full_bar, 2 * TILE_BYTES);
+            mbar_expect_tx(full_bar, (a.has_u ? 2 : 1) * TILE_BYTES);
             tma_load_3d(sP, &map_p, full_bar, 0, t0, b);
-            tma_load_3d(sU, &map_u, full_bar, 0, t0 + a.dil0, b);
+            if (a.has_u) tma_load_3d(sU, &map_u, full_bar, 0, t0 + a.dil0, b);
         }
         // one-hot rows of this time step: tap 1 looks at x[t], tap 0 at x[t-1]
 #pragma unroll
@@ -99,7 +100,7 @@ input_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_cons
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     umma(tmem_u, desc_adv(mOH, k * 2048), desc_adv(mP, k * 2048), idesc, acc0 | (k != 0));
-                    umma(tmem_u, desc_adv(mOH, k * 2048), desc_adv(mU, k * 2048), idesc, 1);
+                    if (a.has_u) umma(tmem_u, desc_adv(mOH, k * 2048), desc_adv(mU, k * 2048), idesc, 1);
                 }
                 umma_commit(w_bar);
             }
@@ -146,10 +147,10 @@ int mvn_tc_input_bwd(const float* audio, const int* codes, const unsigned char* 
     CUtensorMap mp, mu;
     int rc;
     if ((rc = make_act_map(&mp, p, g.B, g.T))) return rc;
-    if ((rc = make_act_map(&mu, u, g.B, g.T))) return rc;
+    if ((rc = make_act_map(&mu, u ? u : p, g.B, g.T))) return rc;
     InArgs a;
     a.audio = audio; a.codes = codes; a.dense = dense; a.partial = partial;
-    a.B = g.B; a.T = g.T; a.A = g.A; a.dil0 = g.dil[0];
+    a.B = g.B; a.T = g.T; a.A = g.A; a.dil0 = g.dil[0]; a.has_u = u != nullptr;
     a.tiles_per_clip = (g.T + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
     const int smem = 4 * TILE_BYTES + 64 + 1024;
     static bool attr = false;

@@ -14,6 +14,9 @@ int mvn_tc_pack(const float* const* param_ptrs_dev, float* packed, const PackedL
 // Backward of one layer on tensor cores (layer_tc_bwd.cu).  The residual-stream gradient travels as the pair
 // (P, U): d(x_{l+1})[t] = P[t] + U[t + dilation_{l+1}].  lg = this layer's slot of the packed gradients.
 // q_in / q_out: running sum over layers of the context gradient, bf16 (B,T,C) (video only).
+// u_in == null (p_in given): the incoming gradient is ONE summed stream; u_out == null: write the summed stream (dilation <= 128).
+// mvn_tc_bwd_sum_out(g, l): does layer l write the summed stream?  (decided from the top layer down, layer_tc_bwd.cu)
+int mvn_tc_bwd_sum_out(const Geo& g, int layer);
 size_t mvn_tc_bwd_partial_bytes();          // per layer; the layers' partial slots are consecutive
 // reduce every layer's per-CTA partials into the packed gradients (one launch, after the backward sweep)
 int mvn_tc_bwd_reduce_all(const float* partial_all, float* pg, const PackedLayout& P, const Geo& g, cudaStream_t st);

@@ -17,6 +17,13 @@
 //         bias grads = the same A operands times an all-ones B
 //   epilogue 2: P' = dxs + D4[tap1] ; U' = D4[tap0]  -> TMA stores ; d(ctx) += D4[ctx]
 //
+// Summed output (layers with dilation <= 128, i.e. every layer of the 00/01/02/03 experiments): the producing layer adds
+// the two terms itself and writes ONE stream D'[t] = P'[t] + U'[t + d]: row r of the sum needs U' row r + d, which is in the
+// same tile (read back from the staging tile) or in the first d rows of the next tile in time.  A CTA therefore walks a
+// CONTIGUOUS run of tiles backwards in time and keeps those d rows ("carry") in shared memory; the run starts with one
+// warm-up tile (the tile after the run, recomputed, nothing stored or accumulated) unless the run ends at a clip's end.
+// The consumer then reads one tile instead of two, and G2 / W2 / the bias sums lose their second pass.
+//
 // The weight-gradient accumulators stay in TMEM for the CTA's whole tile loop and are written once
 // per CTA as partial sums; a small second kernel reduces the partials in a fixed order
 // (deterministic, no atomics) into the packed gradient buffer.
@@ -56,11 +63,30 @@ struct BwdArgs {
     float* partial;       // [grid][PART_FLOATS]
     int B, T, Tout, RF, S, N2, dil, dil_up, nchunks, tiles_per_clip, n_tiles;
     int zero_in;          // the incoming stream gradient (P, U) and context-gradient sum (Q) are zero (last layer): never loaded
+    int pair_in;          // the incoming gradient is the pair (P, U); otherwise one summed stream (or zero)
+    int sum_out;          // write the summed stream D' (dilation <= 128) instead of the pair (P', U')
 };
+
+// The order in which a CTA visits its tiles.  Pair output: grid-strided.  Summed output: a contiguous run, backwards in
+// time, preceded by a warm-up tile when the run does not end at the end of a clip.
+struct TileSeq { int top, step, count, warm; };
+__device__ __forceinline__ TileSeq tile_seq(const BwdArgs& a, bool sum_out) {
+    TileSeq q;
+    if (!sum_out) {
+        q.top = blockIdx.x; q.step = gridDim.x; q.warm = 0;
+        q.count = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    } else {
+        const int lo = (int)((long long)a.n_tiles * blockIdx.x / gridDim.x), hi = (int)((long long)a.n_tiles * (blockIdx.x + 1) / gridDim.x);
+        q.warm = hi < a.n_tiles && hi % a.tiles_per_clip != 0;
+        q.top = q.warm ? hi : hi - 1; q.step = -1; q.count = q.top - lo + 1;
+    }
+    return q;
+}
 
 __host__ __device__ inline int bwd_tiles_off(int nc, int N2) { return smem_a_off(nc, N2); }
 // tiles after the image: A0..A(nc-1) | DXS | DSK | U | DZ0 | DZ1 | G | [Q, video only] | ONES(1 KB) | barriers
-__host__ __device__ inline int bwd_smem_total(int nc, int N2) { return bwd_tiles_off(nc, N2) + (nc + 6 + (nc == 3)) * TILE_BYTES + 1024 + 128; }
+// (audio only: a CARRY tile takes the Q tile's place; with video the carry lives in the U tile, free when the input is one stream)
+__host__ __device__ inline int bwd_smem_total(int nc, int N2) { return bwd_tiles_off(nc, N2) + (nc + 7) * TILE_BYTES + 1024 + 128; }
 
 // every lane has fenced its own writes; one lane signals for the warp
 __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
@@ -70,6 +96,7 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
 
 constexpr int N_WORKERS = 512, N_THREADS = N_WORKERS + 32;   // 16 worker warps + the control warp
 
+template <bool SUM_OUT>          // == a.sum_out (a template parameter so each variant keeps only its own epilogue 2)
 __global__ void __launch_bounds__(N_THREADS, 1)
 layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_ctx,
                     const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_u,
@@ -89,7 +116,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint8_t* sDZ = sDSK + TILE_BYTES;             // DZ0 (filter half) | DZ1 (gate half)
     uint8_t* sG = sDZ + 2 * TILE_BYTES;
     uint8_t* sQ = sG + TILE_BYTES;                // running sum of the context gradient (video only)
-    uint8_t* sONES = sQ + (nc == 3 ? TILE_BYTES : 0);
+    uint8_t* sCARRY = nc == 3 ? sU : sQ;          // first d rows of U' of the tile processed before this one (summed output)
+    uint8_t* sONES = sQ + TILE_BYTES;
     // barriers, one completion per tile each (parity = tile iteration & 1), except IMG (once).
     // E_* are the worker -> control-warp signals (one arrival per worker warp), the rest are TMA / tcgen05.commit completions.
     enum { IMG = 0, A_IN, P_IN, U_IN, Q_IN, G1, G2, G3, W1, WALL, E_DSK, E_DZ, E_OUT, N_BARS };
@@ -166,20 +194,20 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             mbar_expect_tx(bar + which, (uint32_t)TILE_BYTES);
             tma_load_3d(dst, map, bar + which, 0, l0, lb);
         };
+        const TileSeq sq = tile_seq(a, SUM_OUT);
         if (leader) {
-            const int lb = (int)blockIdx.x / a.tiles_per_clip, l0 = ((int)blockIdx.x - lb * a.tiles_per_clip) * TILE_T;
+            const int lb = sq.top / a.tiles_per_clip, l0 = (sq.top - lb * a.tiles_per_clip) * TILE_T;
             load_a_tiles(lb, l0);
-            if (!a.zero_in) {
-                load_tile(sDXS, &map_p, P_IN, lb, l0);
-                load_tile(sU, &map_u, U_IN, lb, l0 + a.dil_up);
-            }
+            if (!a.zero_in) load_tile(sDXS, &map_p, P_IN, lb, l0);
+            if (a.pair_in) load_tile(sU, &map_u, U_IN, lb, l0 + a.dil_up);
         }
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        for (uint32_t it = 0; it < (uint32_t)sq.count; ++it) {
             const uint32_t ph = it & 1;
+            const int tile = sq.top + (int)it * sq.step;
+            const bool is_warm = sq.warm && it == 0;   // recomputed for its U' rows only: nothing stored, nothing accumulated
             const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T;
-            const int nt = tile + gridDim.x;           // this CTA's next tile
-            const bool has_next = nt < a.n_tiles;
+            const int nt = tile + sq.step;             // this CTA's next tile
+            const bool has_next = it + 1 < (uint32_t)sq.count;
             const int nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
             // G1: recompute the gate pre-activations (the tile's TMEM columns are free: E_OUT of the previous tile)
             CLKC(0);
@@ -203,21 +231,19 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 if (!a.zero_in) {
                     if (nc == 3) tma_prefetch_3d(&map_q, 0, n0, nb);
                     tma_prefetch_3d(&map_p, 0, n0, nb);
-                    tma_prefetch_3d(&map_u, 0, n0 + a.dil_up, nb);
+                    if (a.pair_in) tma_prefetch_3d(&map_u, 0, n0 + a.dil_up, nb);
                 }
             }
             if (leader) {
                 tma_wait_read0();     // the previous tile's P'/U'/Q' stores have left DZ0 / DZ1 / Q  (ordered before G2's
                                       // commit: the workers write DZ again only after they have seen G2)
-                if (nc == 3 && !a.zero_in) load_tile(sQ, &map_q, Q_IN, b, t0);       // needed by epilogue 2 only
+                if (nc == 3 && !a.zero_in && !is_warm) load_tile(sQ, &map_q, Q_IN, b, t0);       // needed by epilogue 2 only
             }
             // G2: d(gated) = (P + U) . Wr + dskip . Ws as three accumulating products (no pre-sum pass): contraction over
             // the image's ROWS (c_out | s) -> B is MN-major.  Needs only the loads and the DSK tile, so it runs next to G1.
             CLKC(3);
-            if (!a.zero_in) {
-                mbar_wait(bar + P_IN, ph);
-                mbar_wait(bar + U_IN, ph);
-            }
+            if (!a.zero_in) mbar_wait(bar + P_IN, ph);
+            if (a.pair_in) mbar_wait(bar + U_IN, ph);
             CLKC(4);
             mbar_wait(bar + E_DSK, ph);
             CLKC(5);
@@ -226,9 +252,11 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma(tmem_u + 128, desc_adv(kDXS, k * 32), desc_adv(mBrs, k * 2048), iG2, k != 0);
+                if (a.pair_in) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma(tmem_u + 128, desc_adv(kU, k * 32), desc_adv(mBrs, k * 2048), iG2, 1);
+                    for (int k = 0; k < 4; ++k)
+                        umma(tmem_u + 128, desc_adv(kU, k * 32), desc_adv(mBrs, k * 2048), iG2, 1);
+                }
 #pragma unroll
                 for (int k = 0; k < 4; ++k)                // the skip channels: rows 64.. of the image, 16 per step
                     if (k < (a.S + 15) / 16) umma(tmem_u + 128, desc_adv(kDSK, k * 32), desc_adv(mBrs, (4 + k) * 2048), iG2, 1);
@@ -249,24 +277,30 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             CLKC(8);
             // weight / bias gradients: K = time.  Every tile is [time x 64 ch], i.e. an MN-major operand.
             // First the ones that read the x/ctx and DZ tiles (W1): those buffers are needed first.
-            const uint32_t acc0 = it != 0;
+            const uint32_t acc0 = it != (uint32_t)sq.warm;      // the first tile that counts starts the accumulators
+            if (!is_warm) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                umma(tmem_u + W1_COL, desc_adv(mDZ, k * 2048), desc_adv(mA, k * 2048), iW1, acc0 | (k != 0));
-                umma(tmem_u + B1_COL, desc_adv(mDZ, k * 2048), ones, iB, acc0 | (k != 0));
+                for (int k = 0; k < 8; ++k) {
+                    umma(tmem_u + W1_COL, desc_adv(mDZ, k * 2048), desc_adv(mA, k * 2048), iW1, acc0 | (k != 0));
+                    umma(tmem_u + B1_COL, desc_adv(mDZ, k * 2048), ones, iB, acc0 | (k != 0));
+                }
             }
             umma_commit(bar + W1);
             CLKC(9);
             // [P|DSK]^T and [U|DSK]^T: the skip rows (64..) are accumulated twice and halved at the flush (exact)
+            if (!is_warm) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                umma(tmem_u + W2_COL, desc_adv(mDXS, k * 2048), desc_adv(mG, k * 2048), iW2, acc0 | (k != 0));
-                umma(tmem_u + B2_COL, desc_adv(mDXS, k * 2048), ones, iB, acc0 | (k != 0));
-            }
+                for (int k = 0; k < 8; ++k) {
+                    umma(tmem_u + W2_COL, desc_adv(mDXS, k * 2048), desc_adv(mG, k * 2048), iW2, acc0 | (k != 0));
+                    umma(tmem_u + B2_COL, desc_adv(mDXS, k * 2048), ones, iB, acc0 | (k != 0));
+                }
+                if (a.pair_in) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                umma(tmem_u + W2_COL, desc_adv(mU, k * 2048), desc_adv(mG, k * 2048), iW2, 1);
-                umma(tmem_u + B2_COL, desc_adv(mU, k * 2048), ones, iB, 1);
+                    for (int k = 0; k < 8; ++k) {
+                        umma(tmem_u + W2_COL, desc_adv(mU, k * 2048), desc_adv(mG, k * 2048), iW2, 1);
+                        umma(tmem_u + B2_COL, desc_adv(mU, k * 2048), ones, iB, 1);
+                    }
+                }
             }
             umma_commit(bar + WALL);
             CLKC(10);
@@ -276,9 +310,9 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             CLKC(12);
             mbar_wait(bar + E_OUT, ph);            // P', U', Q' are staged; nobody reads DXS or the tile's TMEM columns any more
             CLKC(13);
-            if (leader) {
+            if (leader && !is_warm) {
                 tma_store_3d(&map_pout, sDZ, 0, t0, b);
-                tma_store_3d(&map_uout, sDZ + TILE_BYTES, 0, t0, b);
+                if (!SUM_OUT) tma_store_3d(&map_uout, sDZ + TILE_BYTES, 0, t0, b);
                 if (nc == 3) tma_store_3d(&map_qout, sQ, 0, t0, b);
                 tma_commit();
             }
@@ -286,10 +320,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 CLKC(14);
                 mbar_wait(bar + WALL, ph);         // W2 no longer reads the P and U tiles
                 CLKC(15);
-                if (leader && !a.zero_in) {
-                    load_tile(sDXS, &map_p, P_IN, nb, n0);
-                    load_tile(sU, &map_u, U_IN, nb, n0 + a.dil_up);
-                }
+                if (leader && !a.zero_in) load_tile(sDXS, &map_p, P_IN, nb, n0);
+                if (leader && a.pair_in) load_tile(sU, &map_u, U_IN, nb, n0 + a.dil_up);
             }
             __syncwarp();
             CLKC(16);
@@ -306,12 +338,15 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 v0 = src[0]; v1 = src[1];
             }
         };
+        const TileSeq sq = tile_seq(a, SUM_OUT);
         float4 ds0, ds1;
-        load_dskip(blockIdx.x, ds0, ds1);
+        load_dskip(sq.top, ds0, ds1);
         const int o0 = r * 128 + (((2 * half) ^ sw) << 4), o1 = r * 128 + (((2 * half + 1) ^ sw) << 4);   // this thread's 16 channels
-        uint32_t it = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        for (uint32_t it = 0; it < (uint32_t)sq.count; ++it) {
             const uint32_t ph = it & 1;
+            const int tile = sq.top + (int)it * sq.step;
+            const bool is_warm = sq.warm && it == 0;
+            const bool has_next = it + 1 < (uint32_t)sq.count;
             const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T;
             const int t = t0 + r;
             CLKW(0);
@@ -386,33 +421,38 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             tc_fence_before();
             warp_arrive(bar + E_DZ);
             CLKW(5); CLKM(5);
-            // ---- epilogue 2: P' = dxs + W1^T dz, U' = W0^T dz (registers until the DZ tiles are free); Q' = Q + V^T dz in place
+            // ---- epilogue 2: U' = W0^T dz, P' = d(x') + W1^T dz (registers until the DZ tiles are free); Q' = Q + V^T dz in place
             mbar_wait(bar + G3, ph);
             CLKW(6);
             tc_fence_after();
             uint32_t po[8], uo[8];
             {
-                uint32_t v[16], w[16];
-                tmem_ld16(tmem + lane_base + 64 + 16 * half, v);
+                uint32_t w[16];
                 tmem_ld16(tmem + lane_base + 16 * half, w);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) uo[i] = pack_bf16(__uint_as_float(w[2 * i]), __uint_as_float(w[2 * i + 1]));
+            }
+            if (!SUM_OUT) {
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_base + 64 + 16 * half, v);
                 const uint4 x0 = *(const uint4*)(sDXS + o0), x1 = *(const uint4*)(sDXS + o1);
-                const uint4 y0 = *(const uint4*)(sU + o0), y1 = *(const uint4*)(sU + o1);
+                const uint4 zz = make_uint4(0, 0, 0, 0);
+                const uint4 y0 = a.pair_in ? *(const uint4*)(sU + o0) : zz, y1 = a.pair_in ? *(const uint4*)(sU + o1) : zz;
                 const uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                 const uint32_t yi[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float2 xp = unpack_bf16(xi[i]), xu = unpack_bf16(yi[i]);
-                    const float2 xv = make_float2(xp.x + xu.x, xp.y + xu.y);
-                    po[i] = pack_bf16(__uint_as_float(v[2 * i]) + xv.x, __uint_as_float(v[2 * i + 1]) + xv.y);
-                    uo[i] = pack_bf16(__uint_as_float(w[2 * i]), __uint_as_float(w[2 * i + 1]));
+                    po[i] = pack_bf16(__uint_as_float(v[2 * i]) + (xp.x + xu.x), __uint_as_float(v[2 * i + 1]) + (xp.y + xu.y));
                 }
             }
-            if (nc == 3) {
+            if (nc == 3 && !is_warm) {
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + 128 + 16 * half, v);
                 CLKW(7);
-                if (!a.zero_in) mbar_wait(bar + Q_IN, ph);
+                if (!a.zero_in) mbar_wait(bar + Q_IN, (it - (uint32_t)sq.warm) & 1);   // no Q load for the warm-up tile
                 CLKW(8);
                 uint4* p0 = (uint4*)(sQ + o0);
                 uint4* p1 = (uint4*)(sQ + o1);
@@ -430,26 +470,60 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 *p1 = make_uint4(o[4], o[5], o[6], o[7]);
             }
             CLKW(9);
+            // summed output: the U' rows this thread's sum needs from the tile processed before this one (rows r + d - 128 of
+            // the carry; written after that tile's barrier below and ordered before this read by E_OUT -> G1 -> G3)
+            const int rs = r + a.dil;
+            const int cs0 = ((2 * half) ^ (rs & 7)) << 4, cs1 = ((2 * half + 1) ^ (rs & 7)) << 4;
+            uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+            if (SUM_OUT && rs >= TILE_T && it != 0 && tile % a.tiles_per_clip != a.tiles_per_clip - 1) {
+                c0 = *(const uint4*)(sCARRY + (rs - TILE_T) * 128 + cs0);
+                c1 = *(const uint4*)(sCARRY + (rs - TILE_T) * 128 + cs1);
+            }
             mbar_wait(bar + W1, ph);            // W1 no longer reads the DZ tiles, nor the x/ctx tiles:
-            if (tid == 0 && tile + (int)gridDim.x < a.n_tiles) {   // reload those for the next tile right away
-                const int nt = tile + gridDim.x, nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
+            if (tid == 0 && has_next) {         // reload those for the next tile right away
+                const int nt = tile + sq.step, nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
                 mbar_expect_tx(bar + A_IN, (uint32_t)(nc * TILE_BYTES));
                 tma_load_3d(sA, &map_x, bar + A_IN, 0, n0 - a.dil, nb);
                 tma_load_3d(sA + TILE_BYTES, &map_x, bar + A_IN, 0, n0, nb);
                 if (nc == 3) tma_load_3d(sA + 2 * TILE_BYTES, &map_ctx, bar + A_IN, 0, n0, nb);
             }
             CLKW(10);
-            *(uint4*)(sDZ + o0) = make_uint4(po[0], po[1], po[2], po[3]);
-            *(uint4*)(sDZ + o1) = make_uint4(po[4], po[5], po[6], po[7]);
             *(uint4*)(sDZ + TILE_BYTES + o0) = make_uint4(uo[0], uo[1], uo[2], uo[3]);
             *(uint4*)(sDZ + TILE_BYTES + o1) = make_uint4(uo[4], uo[5], uo[6], uo[7]);
+            if (SUM_OUT) {
+                asm volatile("bar.sync 1, %0;" ::"n"(N_WORKERS) : "memory");      // every U' row of this tile is staged
+                if (rs < TILE_T) {
+                    c0 = *(const uint4*)(sDZ + TILE_BYTES + rs * 128 + cs0);
+                    c1 = *(const uint4*)(sDZ + TILE_BYTES + rs * 128 + cs1);
+                }
+                if (r < a.dil) {                 // this tile's first d rows of U' are the next tile's carry
+                    *(uint4*)(sCARRY + o0) = make_uint4(uo[0], uo[1], uo[2], uo[3]);
+                    *(uint4*)(sCARRY + o1) = make_uint4(uo[4], uo[5], uo[6], uo[7]);
+                }
+                uint32_t v[16];
+                tmem_ld16(tmem + lane_base + 64 + 16 * half, v);
+                const uint4 x0 = *(const uint4*)(sDXS + o0), x1 = *(const uint4*)(sDXS + o1);
+                const uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                const uint32_t yi[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                const uint4 zz = make_uint4(0, 0, 0, 0);    // pair input (audio only): the incoming U term of the pass-through
+                const uint4 y0 = a.pair_in ? *(const uint4*)(sU + o0) : zz, y1 = a.pair_in ? *(const uint4*)(sU + o1) : zz;
+                const uint32_t ui[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 xp = unpack_bf16(xi[i]), xq = unpack_bf16(ui[i]), xu = unpack_bf16(yi[i]);
+                    po[i] = pack_bf16(__uint_as_float(v[2 * i]) + ((xp.x + xq.x) + xu.x), __uint_as_float(v[2 * i + 1]) + ((xp.y + xq.y) + xu.y));
+                }
+            }
+            *(uint4*)(sDZ + o0) = make_uint4(po[0], po[1], po[2], po[3]);
+            *(uint4*)(sDZ + o1) = make_uint4(po[4], po[5], po[6], po[7]);
             fence_proxy_async();
             tc_fence_before();
             warp_arrive(bar + E_OUT);
             CLKW(11); CLKM(11);
-            load_dskip(tile + gridDim.x, ds0, ds1);
+            load_dskip(has_next ? tile + sq.step : a.n_tiles, ds0, ds1);
         }
-        if (it) mbar_wait(bar + WALL, (it - 1) & 1);
+        mbar_wait(bar + WALL, (uint32_t)(sq.count - 1) & 1);
     }
     // ---- flush this CTA's partial weight / bias gradients ----------------------------------------
     if (tid < N_WORKERS) {
@@ -471,7 +545,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         uint32_t v[16];
         tmem_ld16(tmem + lane_base + W2_COL + 16 * j, v);
         tmem_ld_wait();
-        const float sc = r >= CC ? 0.5f : 1.f;     // the skip rows were accumulated once with P and once with U
+        const float sc = (r >= CC && a.pair_in) ? 0.5f : 1.f;     // pair input: the skip rows were accumulated once with P and once with U
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             ((float4*)(prow + 192 + 16 * j))[q] = make_float4(sc * __uint_as_float(v[4 * q]), sc * __uint_as_float(v[4 * q + 1]),
@@ -484,7 +558,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tmem_ld_wait();
         if (half == 0) {
             part[128 * PART_LD + r] = __uint_as_float(v1[0]);
-            part[128 * PART_LD + 128 + r] = (r >= CC ? 0.5f : 1.f) * __uint_as_float(v2[0]);
+            part[128 * PART_LD + 128 + r] = ((r >= CC && a.pair_in) ? 0.5f : 1.f) * __uint_as_float(v2[0]);
         }
     }
     }
@@ -552,30 +626,34 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     int rc;
     if ((rc = make_act_map(&mx, x_in, g.B, g.T))) return rc;
     if ((rc = make_act_map(&mc, g.video ? ctx : x_in, g.B, g.T))) return rc;
-    MVN_REQUIRE((p_in == nullptr) == (u_in == nullptr), "tensor-core backward kernel: P and U come together");
+    MVN_REQUIRE(p_in || !u_in, "tensor-core backward kernel: U without P");
+    const int sum_out = u_out == nullptr;
+    MVN_REQUIRE(!sum_out || (g.dil[layer] <= TILE_T && !(g.video && u_in)), "tensor-core backward kernel: summed output needs dilation <= 128 (and, with video, a summed input)");
     if ((rc = make_act_map(&mp, p_in ? p_in : x_in, g.B, g.T))) return rc;      // p_in == u_in == null: zero incoming gradient
     if ((rc = make_act_map(&mu, u_in ? u_in : x_in, g.B, g.T))) return rc;
     if ((rc = make_act_map(&mpo, p_out, g.B, g.T))) return rc;
-    if ((rc = make_act_map(&muo, u_out, g.B, g.T))) return rc;
+    if ((rc = make_act_map(&muo, u_out ? u_out : p_out, g.B, g.T))) return rc;
     if ((rc = make_act_map(&mq, g.video ? q_in : x_in, g.B, g.T))) return rc;
     if ((rc = make_act_map(&mqo, g.video ? q_out : p_out, g.B, g.T))) return rc;
     BwdArgs a;
     a.img = lw + P.oTc; a.dskip = dskip; a.partial = partial;
     a.B = g.B; a.T = g.T; a.Tout = g.Tout; a.RF = g.RF; a.S = g.S; a.N2 = ((g.C + g.S + 15) / 16) * 16;
     a.dil = g.dil[layer]; a.dil_up = layer + 1 < g.N ? g.dil[layer + 1] : 0;
-    a.zero_in = p_in == nullptr;
+    a.zero_in = p_in == nullptr; a.pair_in = u_in != nullptr; a.sum_out = sum_out;
     a.nchunks = g.video ? 3 : 2;
     a.tiles_per_clip = (g.T + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
     const int smem = bwd_smem_total(a.nchunks, a.N2) + 1024;
     MVN_REQUIRE(smem <= 227 * 1024, "tensor-core backward kernel: shared memory budget exceeded (%d)", smem);
     static int attr_smem = 0;
     if (smem > attr_smem) {
-        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
     int grid = 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    MVN_CUDA(mvn_launch_pdl(layer_bwd_tc_kernel, dim3(grid), dim3(N_THREADS), (size_t)smem, st, mx, mc, mp, mu, mpo, muo, mq, mqo, a));
+    if (sum_out) MVN_CUDA(mvn_launch_pdl(layer_bwd_tc_kernel<true>, dim3(grid), dim3(N_THREADS), (size_t)smem, st, mx, mc, mp, mu, mpo, muo, mq, mqo, a));
+    else MVN_CUDA(mvn_launch_pdl(layer_bwd_tc_kernel<false>, dim3(grid), dim3(N_THREADS), (size_t)smem, st, mx, mc, mp, mu, mpo, muo, mq, mqo, a));
     (void)lg;
 #if MVN_PHASE_CLOCKS
     if (getenv("MVN_PROF")) {
@@ -595,4 +673,18 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     }
 #endif
     return mvn_check_launch("layer_bwd_tc");
+}
+
+// Layer l writes the summed stream when its dilation fits a tile and the carry has a home: with video the carry lives in the
+// U input tile, so the layer above must have written a summed stream too.  MOVENET_B200_BWD_PAIR=1 keeps the (P, U) pair everywhere.
+int mvn_tc_bwd_sum_out(const Geo& g, int layer) {
+    const char* force_pair = getenv("MOVENET_B200_BWD_PAIR");      // read per call: the tests switch it
+    if (force_pair && atoi(force_pair)) return 0;
+    int above = 1;                                   // the top layer's input is zero
+    for (int l = g.N - 1; l >= layer; --l) {
+        const int s = g.dil[l] <= TILE_T && (!g.video || above);
+        if (l == layer) return s;
+        above = s;
+    }
+    return 0;
 }

@@ -749,8 +749,9 @@ extern "C" int mvn_layer_bwd(const mvn_shape_t* s, const void* packed, int layer
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
         const size_t nb = (size_t)g.B * g.T * g.C * g.es;
         float* lg = pg + c.P.layer0 + (size_t)layer * c.P.layer_stride;
-        return mvn_tc_layer_bwd(c.x(layer), g.video ? c.acts + c.AL.ctx : nullptr, c.scratch + c.SL.dxa, c.scratch + c.SL.dgated,
-                                c.scratch + c.SL.dxb, c.scratch + c.SL.dz, (const float*)(c.scratch + c.SL.dskip),
+        const bool pair_in = layer + 1 < g.N && !mvn_tc_bwd_sum_out(g, layer + 1), sum_out = mvn_tc_bwd_sum_out(g, layer);
+        return mvn_tc_layer_bwd(c.x(layer), g.video ? c.acts + c.AL.ctx : nullptr, c.scratch + c.SL.dxa, pair_in ? c.scratch + c.SL.dgated : nullptr,
+                                c.scratch + c.SL.dxb, sum_out ? nullptr : c.scratch + c.SL.dz, (const float*)(c.scratch + c.SL.dskip),
                                 c.scratch + c.SL.dctx, c.scratch + c.SL.dctx + nb, c.lw(layer), lg,
                                 (float*)(c.scratch + c.SL.tc_layer_partial + (size_t)layer * mvn_tc_bwd_partial_bytes()), c.P, g, layer,
                                 c.st);
@@ -804,22 +805,24 @@ static int backward_impl(const mvn_shape_t* s, const void* packed, const float* 
         // the last layer's residual output is discarded: its incoming (P, U, Q) are zero and are never read (null pointers)
         // running sum of the context gradient, bf16, ping-pong inside the fp32 dctx slot
         void* Qb[2] = {c.scratch + c.SL.dctx, c.scratch + c.SL.dctx + nb};
-        int cur = 0;
+        // a layer with dilation <= 128 writes ONE summed stream into its P slot (mvn_tc_bwd_sum_out) and no U
+        int cur = 0, pair = 0;
         for (int l = g.N - 1; l >= 0; --l) {
             float* lg = pg + c.P.layer0 + (size_t)l * c.P.layer_stride;
             const bool first = l == g.N - 1;
-            if ((rc = mvn_tc_layer_bwd(c.x(l), g.video ? c.acts + c.AL.ctx : nullptr, first ? nullptr : Pb[cur], first ? nullptr : Ub[cur],
-                                       Pb[cur ^ 1], Ub[cur ^ 1],
+            const int sum_out = mvn_tc_bwd_sum_out(g, l);
+            if ((rc = mvn_tc_layer_bwd(c.x(l), g.video ? c.acts + c.AL.ctx : nullptr, first ? nullptr : Pb[cur], first || !pair ? nullptr : Ub[cur],
+                                       Pb[cur ^ 1], sum_out ? nullptr : Ub[cur ^ 1],
                                        (const float*)(c.scratch + c.SL.dskip), Qb[cur], Qb[cur ^ 1], c.lw(l), lg,
                                        (float*)(c.scratch + c.SL.tc_layer_partial + (size_t)l * mvn_tc_bwd_partial_bytes()), c.P, g, l,
                                        c.st))) return rc;
-            cur ^= 1;
+            cur ^= 1; pair = !sum_out;
         }
         if ((rc = mvn_tc_bwd_reduce_all((const float*)(c.scratch + c.SL.tc_layer_partial), pg, c.P, g, c.st))) return rc;
         if (mvn_tc_input_supported(g.A, g.C)) {
             if ((rc = mvn_tc_input_bwd(audio, (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), Pb[cur],
-                                       Ub[cur], pg + c.P.win, (float*)(c.scratch + c.SL.tc_partial), g, c.st))) return rc;
-        } else if ((rc = input_bwd(c, audio, Pb[cur], Ub[cur], g.dil[0], pg))) return rc;
+                                       pair ? Ub[cur] : nullptr, pg + c.P.win, (float*)(c.scratch + c.SL.tc_partial), g, c.st))) return rc;
+        } else if ((rc = input_bwd(c, audio, Pb[cur], pair ? Ub[cur] : nullptr, pair ? g.dil[0] : 0, pg))) return rc;
         dctx_final = Qb[cur]; dctx_dtype = MVN_BF16;
     } else {
         void* bufs[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};

@@ -235,3 +235,44 @@ def test_bf16_training_step_is_bit_reproducible(video):
                 assert rel_l2(g, runs[0][2][k]) < 2e-2, k
             elif not k.startswith(skip):
                 assert torch.equal(g, runs[0][2][k]), k
+
+
+def _grads_of(m, audio, video, target):
+    for p in m.parameters():
+        p.grad = None
+    out = m(audio, video) if video is not None else m(audio)
+    F.cross_entropy(out, target).backward()
+    return {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}
+
+
+@pytest.mark.parametrize("video", [False, True])
+def test_backward_gradient_stream_modes(video, monkeypatch):
+    """The residual-stream gradient between two layer kernels is ONE summed tensor when the producing layer's dilation
+    is <= 128 (it adds its two terms itself, carrying d rows from tile to tile) and the pair (P, U) otherwise.  Dilations
+    1..256 twice: summed, pair, and both hand-overs (pair in / summed out needs the separate carry tile: audio only; with
+    video the layers under a wide one stay on the pair).  Ragged T, several clips per CTA run, warm-up tiles.  Checked
+    against the exact fp32 mode, and the forced-pair build of the same step must agree with the default one."""
+    torch.manual_seed(3)
+    kw = dict(layer_size=9, stack_size=2, input_channels=64, residual_channels=64, skip_channels=8)
+    m32 = movenet_b200.WaveNet(**kw, compute_dtype="fp32").cuda()
+    m16 = movenet_b200.WaveNet(**kw, compute_dtype="bf16").cuda()
+    m16.load_state_dict(m32.state_dict())
+    T, B = (160000, 1) if video else (40000 + 77, 3)
+    codes = torch.randint(0, 64, (B, T), device="cuda")
+    audio = movenet_b200.one_hot(codes, 64)
+    vid = torch.randint(0, 256, (B, 160, 64, 64, 1), device="cuda").float() if video else None
+    target = codes[:, m32.receptive_fields:]
+    ref = _grads_of(m32, audio, vid, target)
+    got = _grads_of(m16, audio, vid, target)
+    monkeypatch.setenv("MOVENET_B200_BWD_PAIR", "1")
+    pair = _grads_of(m16, audio, vid, target)
+    assert ref.keys() == got.keys() == pair.keys()
+    errs = []
+    for k in ref:
+        errs.append(rel_l2(got[k], ref[k]))
+        assert errs[-1] < GRAD_RTOL, (k, errs[-1])
+        assert rel_l2(pair[k], ref[k]) < GRAD_RTOL, (k, "pair", rel_l2(pair[k], ref[k]))
+    assert sum(errs) / len(errs) < GRAD_MEAN_RTOL
+    a, b, c = (torch.cat([g[k].flatten() for k in ref]) for g in (got, ref, pair))
+    assert F.cosine_similarity(a, b, dim=0).item() >= GRAD_COS
+    assert F.cosine_similarity(a, c, dim=0).item() >= 0.999
