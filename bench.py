@@ -229,23 +229,27 @@ def layer_roofline(model, audio, video, dtype):
     vid = video is not None
     # algorithmic bytes per audio sample of one layer
     fwd_b = Cc * e + Cc * e + (Cc * e if vid else 0) + 8 * S                 # read x, write x', read ctx, RMW skip_sum
-    # backward: read x, the stream gradient D, d(skip) (+ ctx and the ctx-gradient running sum Q); write D' (+ Q').
-    # Layers with dilation <= 128 (all of this workload's) exchange ONE summed gradient stream; with
-    # MOVENET_B200_BWD_PAIR=1 (or a wider dilation) the gradient travels as the pair (P, U): one more read and one more write.
-    pair = bool(int(os.environ.get("MOVENET_B200_BWD_PAIR", "0"))) or max(model.residual_conv_stack.dilations) > 128
-    streams = 2 if pair else 1
-    bwd_b = Cc * e + streams * Cc * e + 4 * S + streams * Cc * e + (3 * Cc * e if vid else 0)
+    # backward, algorithmic bytes of any layer-at-a-time backward: read x, the stream gradient D, d(skip) (+ ctx and the
+    # ctx-gradient running sum Q); write D' (+ Q').  The default kernel moves the stream gradient as the pair (P, U) (one more
+    # read and one more write of C*e bytes: `design_bytes_per_sample`); MOVENET_B200_BWD_SUM=1 selects the one-stream variant
+    # (same algorithmic bytes, measured slower: DESIGN.md section 3).
+    summed = bool(int(os.environ.get("MOVENET_B200_BWD_SUM", "0"))) and max(model.residual_conv_stack.dilations) <= 128
+    bwd_b = 3 * Cc * e + 4 * S + (3 * Cc * e if vid else 0)
+    bwd_design = bwd_b + (0 if summed else 2 * Cc * e)
     pk = peaks()
     n = B * T_CLIP
 
-    def obj(name, ms, per_sample, launches, kernel):
+    def obj(name, ms, per_sample, launches, kernel, design=None):
         ach = per_sample * n / (ms * 1e-3) / 1e9
-        return {"bound": "hbm", "kernel": "%s (%s, %d launch(es) per layer)" % (name, dtype, round(launches)),
+        extra = {} if design is None else {"design_bytes_per_sample": design,
+                                           "design_gbs": design * n / (ms * 1e-3) / 1e9,
+                                           "stream_gradient": "one summed stream" if design == per_sample else "pair (P, U)"}
+        return {**extra, "bound": "hbm", "kernel": "%s (%s, %d launch(es) per layer)" % (name, dtype, round(launches)),
                 "achieved": ach, "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": _ncu_traffic(kernel), "ms_per_launch": ms,
                 "bytes_per_sample": per_sample, "samples_per_launch": n}
 
-    return (obj("residual layer backward", ms_b, bwd_b, n_b, "layer_bwd_tc_kernel"),
+    return (obj("residual layer backward", ms_b, bwd_b, n_b, "layer_bwd_tc_kernel", bwd_design),
             obj("residual layer forward", ms_f, fwd_b, n_f, "layer_fwd_tc_kernel"))
 
 
@@ -284,7 +288,7 @@ def decode_bench(dev):
                              d["skip_channels"], compute_dtype="fp32").to(dev)
     RF = m.receptive_fields
     res = {}
-    from movenet_b200.decode import fast_mode_available, prefill, run_steps
+    from movenet_b200.decode import fast_mode_available, prefill, run_steps, steps_into
     for mode, clips, n_new in (("exact_f32", 1, 2000), ("exact_f32", 1184, 400), ("fast_bf16", 148 * 512, 400)):
         fast = mode == "fast_bf16"
         if fast and not fast_mode_available(m, clips, RF):
@@ -301,22 +305,45 @@ def decode_bench(dev):
         else:
             state = prefill(m, prompt, None, fast=fast)
         run_steps(m, state, RF, 8)                                  # warm-up (re-running positions is harmless here)
+        nclips = state.batch
+        A_ = d["input_channels"]
+        e = 2 if fast else 4
+        queue_b = 2 * m.layer_size * m.stack_size * d["residual_channels"] * e      # pop + push per layer
+        # (a) the decode kernel alone: int32 codes out.  Bytes it moves per generated sample: the queue rows + one code.
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         run_steps(m, state, RF, n_new)
         ev1.record()
         torch.cuda.synchronize()
+        sec_k = ev0.elapsed_time(ev1) * 1e-3
+        # (b) the reference's output format: a zeroed (B, A, n_new) fp32 tensor with one 1.0 per generated sample
+        # (movenet/wavenet.py:211-236) -- zero fill + steps + scatter, all inside the timed region.  SURVEY 8(d)'s
+        # algorithmic bytes (queue rows + the 4A-byte one-hot column) are quoted on THIS region.
+        out = torch.empty(nclips, A_, n_new, dtype=torch.float32, device=dev)
+        out.zero_(); steps_into(m, state, RF, 8, out[:, :, :8])     # warm-up of the allocator / scatter kernels
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        out.zero_()
+        steps_into(m, state, RF, n_new, out)
+        ev1.record()
+        torch.cuda.synchronize()
         sec = ev0.elapsed_time(ev1) * 1e-3
-        nclips = state.batch
+        del out
         per_clip_rtf = (n_new / 16000.0) / sec
-        e = 2 if fast else 4
-        bytes_per_sample = 2 * m.layer_size * m.stack_size * d["residual_channels"] * e + 4 * d["input_channels"]
+        bytes_per_sample = queue_b + 4 * A_
         gbs = nclips * n_new * bytes_per_sample / sec / 1e9
+        gbs_k = nclips * n_new * (queue_b + 4) / sec_k / 1e9
         res[f"{mode}_clips_{nclips}"] = {"new_samples_per_clip": n_new, "rtf_per_clip": per_clip_rtf,
                                          "aggregate_samples_per_s": nclips * n_new / sec, "aggregate_rtf": nclips * per_clip_rtf,
+                                         "output": "one-hot (B, A, n) fp32, zero fill + scatter inside the timed region",
                                          "bytes_per_sample": bytes_per_sample, "hbm_gbs_algorithmic": gbs,
-                                         "hbm_frac": gbs / peaks()["hbm_gbs"]}
+                                         "hbm_frac": gbs / peaks()["hbm_gbs"],
+                                         "kernel_only": {"aggregate_samples_per_s": nclips * n_new / sec_k,
+                                                         "rtf_per_clip": (n_new / 16000.0) / sec_k,
+                                                         "output": "int32 codes", "bytes_per_sample": queue_b + 4,
+                                                         "hbm_gbs": gbs_k, "hbm_frac": gbs_k / peaks()["hbm_gbs"]}}
         del state, prompt
     return {"workload": d["name"], "receptive_fields": RF, "dtype": "f32", **res}
 

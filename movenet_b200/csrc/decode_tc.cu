@@ -11,6 +11,7 @@
 // traffic at all.  Two such groups share one CTA (and one copy of the weights in shared memory) and
 // interleave, so one group's MMA / barrier latency hides behind the other's epilogue.
 //
+// The gated tile and [Wr|Ws] are f16 (gate math in packed f16x2), everything else bf16.
 // Queues are bf16, laid out (layer, slot, clip, channel): a group's pop and push of one layer are two
 // contiguous 128 x C x 2-byte blocks.  Operand tiles use the un-swizzled K-major core-matrix layout
 // (8 rows x 16 bytes contiguous), which is compact for any K and conflict-free for one-row-per-thread
@@ -72,7 +73,7 @@ __global__ void decode_tc_pack_kernel(const float* __restrict__ packed, PackedLa
         for (int i = i0; i < I::N2 * C; i += stride) {               // [Wr|Ws]^T[n][k]
             const int n = i / C, k = i % C;
             const float v = n < C + DS ? lw[P.oWrs + (size_t)k * (C + DS) + n] : 0.f;
-            *(__nv_bfloat16*)(li + I::wrs + core_off(n, k, C)) = __float2bfloat16(v);
+            *(__half*)(li + I::wrs + core_off(n, k, C)) = __float2half_rn(v);      // f16: the gated tile it multiplies is f16
         }
         for (int i = i0; i < I::N2; i += stride) ((float*)(li + I::brs))[i] = i < C + DS ? lw[P.obrs + i] : 0.f;
     }
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
     // TMEM columns of the group's window: D1 [0, 2C) ; D2 [2C, 2C + N2) ; the head reuses [0, A) once the layers are done
     constexpr int D1 = 0, D2 = 2 * C, DH = 0;
     static_assert(2 * C + I::N2 <= 512 / GROUPS, "TMEM window");
-    const uint32_t i1 = umma_idesc_major(128, 2 * C, 0, 0), i2 = umma_idesc_major(128, I::N2, 0, 0), ih = umma_idesc_major(128, A, 0, 0);
+    const uint32_t i1 = umma_idesc_major(128, 2 * C, 0, 0), i2 = umma_idesc_major(128, I::N2, 0, 0) & ~((1u << 7) | (1u << 10)) /* f16 operands */, ih = umma_idesc_major(128, A, 0, 0);
 
     const int b = (blockIdx.x * GROUPS + grp) * 128 + r;
     const bool live = b < a.B;
@@ -201,13 +202,16 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
                 tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < C / 8; ++q) {
+                    // tanh(f) * sigmoid(g) on channel pairs in packed f16x2 (one MUFU op per two tanh, as in layer_tc.cu): the
+                    // 11-bit intermediates are above the bf16 queues' precision; the out GEMM runs on f16 operands
+                    const uint32_t h05 = 0x38003800u;     // (0.5, 0.5)
                     uint32_t o[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int c = 8 * q + 2 * e;
-                        const float y0 = tanh_fast(__uint_as_float(f[c])) * fmaf(0.5f, tanh_fast(0.5f * __uint_as_float(g[c])), 0.5f);
-                        const float y1 = tanh_fast(__uint_as_float(f[c + 1])) * fmaf(0.5f, tanh_fast(0.5f * __uint_as_float(g[c + 1])), 0.5f);
-                        o[e] = pack_bf16(y0, y1);
+                        const uint32_t fh = f16x2(__uint_as_float(f[c]), __uint_as_float(f[c + 1]));
+                        const uint32_t gh = f16x2(__uint_as_float(g[c]), __uint_as_float(g[c + 1]));
+                        o[e] = hmul2(htanh2(fh), hfma2(htanh2(hmul2(gh, h05)), h05, h05));
                     }
                     *(uint4*)(sG + core_off(r, 8 * q, C)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }

@@ -17,7 +17,7 @@
 //         bias grads = the same A operands times an all-ones B
 //   epilogue 2: P' = dxs + D4[tap1] ; U' = D4[tap0]  -> TMA stores ; d(ctx) += D4[ctx]
 //
-// Summed output (layers with dilation <= 128, i.e. every layer of the 00/01/02/03 experiments): the producing layer adds
+// Summed output (opt-in, MOVENET_B200_BWD_SUM=1; layers with dilation <= 128): the producing layer adds
 // the two terms itself and writes ONE stream D'[t] = P'[t] + U'[t + d]: row r of the sum needs U' row r + d, which is in the
 // same tile (read back from the staging tile) or in the first d rows of the next tile in time.  A CTA therefore walks a
 // CONTIGUOUS run of tiles backwards in time and keeps those d rows ("carry") in shared memory; the run starts with one
@@ -96,7 +96,7 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
 
 constexpr int N_WORKERS = 512, N_THREADS = N_WORKERS + 32;   // 16 worker warps + the control warp
 
-template <bool SUM_OUT>          // == a.sum_out (a template parameter so each variant keeps only its own epilogue 2)
+template <bool SUM_OUT, bool PAIR_IN>   // == a.sum_out, a.pair_in (template parameters: each variant keeps only its own epilogue 2 and MMAs)
 __global__ void __launch_bounds__(N_THREADS, 1)
 layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_ctx,
                     const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_u,
@@ -199,7 +199,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             const int lb = sq.top / a.tiles_per_clip, l0 = (sq.top - lb * a.tiles_per_clip) * TILE_T;
             load_a_tiles(lb, l0);
             if (!a.zero_in) load_tile(sDXS, &map_p, P_IN, lb, l0);
-            if (a.pair_in) load_tile(sU, &map_u, U_IN, lb, l0 + a.dil_up);
+            if (PAIR_IN) load_tile(sU, &map_u, U_IN, lb, l0 + a.dil_up);
         }
         for (uint32_t it = 0; it < (uint32_t)sq.count; ++it) {
             const uint32_t ph = it & 1;
@@ -231,7 +231,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 if (!a.zero_in) {
                     if (nc == 3) tma_prefetch_3d(&map_q, 0, n0, nb);
                     tma_prefetch_3d(&map_p, 0, n0, nb);
-                    if (a.pair_in) tma_prefetch_3d(&map_u, 0, n0 + a.dil_up, nb);
+                    if (PAIR_IN) tma_prefetch_3d(&map_u, 0, n0 + a.dil_up, nb);
                 }
             }
             if (leader) {
@@ -243,7 +243,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             // the image's ROWS (c_out | s) -> B is MN-major.  Needs only the loads and the DSK tile, so it runs next to G1.
             CLKC(3);
             if (!a.zero_in) mbar_wait(bar + P_IN, ph);
-            if (a.pair_in) mbar_wait(bar + U_IN, ph);
+            if (PAIR_IN) mbar_wait(bar + U_IN, ph);
             CLKC(4);
             mbar_wait(bar + E_DSK, ph);
             CLKC(5);
@@ -252,7 +252,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma(tmem_u + 128, desc_adv(kDXS, k * 32), desc_adv(mBrs, k * 2048), iG2, k != 0);
-                if (a.pair_in) {
+                if (PAIR_IN) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma(tmem_u + 128, desc_adv(kU, k * 32), desc_adv(mBrs, k * 2048), iG2, 1);
@@ -294,7 +294,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     umma(tmem_u + W2_COL, desc_adv(mDXS, k * 2048), desc_adv(mG, k * 2048), iW2, acc0 | (k != 0));
                     umma(tmem_u + B2_COL, desc_adv(mDXS, k * 2048), ones, iB, acc0 | (k != 0));
                 }
-                if (a.pair_in) {
+                if (PAIR_IN) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         umma(tmem_u + W2_COL, desc_adv(mU, k * 2048), desc_adv(mG, k * 2048), iW2, 1);
@@ -321,7 +321,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 mbar_wait(bar + WALL, ph);         // W2 no longer reads the P and U tiles
                 CLKC(15);
                 if (leader && !a.zero_in) load_tile(sDXS, &map_p, P_IN, nb, n0);
-                if (leader && a.pair_in) load_tile(sU, &map_u, U_IN, nb, n0 + a.dil_up);
+                if (leader && PAIR_IN) load_tile(sU, &map_u, U_IN, nb, n0 + a.dil_up);
             }
             __syncwarp();
             CLKC(16);
@@ -426,19 +426,20 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             CLKW(6);
             tc_fence_after();
             uint32_t po[8], uo[8];
-            {
+            auto load_uo = [&]() {
                 uint32_t w[16];
                 tmem_ld16(tmem + lane_base + 16 * half, w);
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) uo[i] = pack_bf16(__uint_as_float(w[2 * i]), __uint_as_float(w[2 * i + 1]));
-            }
+            };
             if (!SUM_OUT) {
+                load_uo();
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + 64 + 16 * half, v);
                 const uint4 x0 = *(const uint4*)(sDXS + o0), x1 = *(const uint4*)(sDXS + o1);
                 const uint4 zz = make_uint4(0, 0, 0, 0);
-                const uint4 y0 = a.pair_in ? *(const uint4*)(sU + o0) : zz, y1 = a.pair_in ? *(const uint4*)(sU + o1) : zz;
+                const uint4 y0 = PAIR_IN ? *(const uint4*)(sU + o0) : zz, y1 = PAIR_IN ? *(const uint4*)(sU + o1) : zz;
                 const uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                 const uint32_t yi[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
                 tmem_ld_wait();
@@ -470,6 +471,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 *p1 = make_uint4(o[4], o[5], o[6], o[7]);
             }
             CLKW(9);
+            if (SUM_OUT) load_uo();              // (after the Q part: fewer values live at once)
             // summed output: the U' rows this thread's sum needs from the tile processed before this one (rows r + d - 128 of
             // the carry; written after that tile's barrier below and ordered before this read by E_OUT -> G1 -> G3)
             const int rs = r + a.dil;
@@ -497,8 +499,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                     c1 = *(const uint4*)(sDZ + TILE_BYTES + rs * 128 + cs1);
                 }
                 if (r < a.dil) {                 // this tile's first d rows of U' are the next tile's carry
-                    *(uint4*)(sCARRY + o0) = make_uint4(uo[0], uo[1], uo[2], uo[3]);
-                    *(uint4*)(sCARRY + o1) = make_uint4(uo[4], uo[5], uo[6], uo[7]);
+                    *(uint4*)(sCARRY + o0) = *(const uint4*)(sDZ + TILE_BYTES + o0);
+                    *(uint4*)(sCARRY + o1) = *(const uint4*)(sDZ + TILE_BYTES + o1);
                 }
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + 64 + 16 * half, v);
@@ -506,7 +508,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 const uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                 const uint32_t yi[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
                 const uint4 zz = make_uint4(0, 0, 0, 0);    // pair input (audio only): the incoming U term of the pass-through
-                const uint4 y0 = a.pair_in ? *(const uint4*)(sU + o0) : zz, y1 = a.pair_in ? *(const uint4*)(sU + o1) : zz;
+                const uint4 y0 = PAIR_IN ? *(const uint4*)(sU + o0) : zz, y1 = PAIR_IN ? *(const uint4*)(sU + o1) : zz;
                 const uint32_t ui[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
                 tmem_ld_wait();
 #pragma unroll
@@ -545,7 +547,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         uint32_t v[16];
         tmem_ld16(tmem + lane_base + W2_COL + 16 * j, v);
         tmem_ld_wait();
-        const float sc = (r >= CC && a.pair_in) ? 0.5f : 1.f;     // pair input: the skip rows were accumulated once with P and once with U
+        const float sc = (r >= CC && PAIR_IN) ? 0.5f : 1.f;     // pair input: the skip rows were accumulated once with P and once with U
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             ((float4*)(prow + 192 + 16 * j))[q] = make_float4(sc * __uint_as_float(v[4 * q]), sc * __uint_as_float(v[4 * q + 1]),
@@ -558,7 +560,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         tmem_ld_wait();
         if (half == 0) {
             part[128 * PART_LD + r] = __uint_as_float(v1[0]);
-            part[128 * PART_LD + 128 + r] = ((r >= CC && a.pair_in) ? 0.5f : 1.f) * __uint_as_float(v2[0]);
+            part[128 * PART_LD + 128 + r] = ((r >= CC && PAIR_IN) ? 0.5f : 1.f) * __uint_as_float(v2[0]);
         }
     }
     }
@@ -646,14 +648,17 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     MVN_REQUIRE(smem <= 227 * 1024, "tensor-core backward kernel: shared memory budget exceeded (%d)", smem);
     static int attr_smem = 0;
     if (smem > attr_smem) {
-        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
     int grid = 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    if (sum_out) MVN_CUDA(mvn_launch_pdl(layer_bwd_tc_kernel<true>, dim3(grid), dim3(N_THREADS), (size_t)smem, st, mx, mc, mp, mu, mpo, muo, mq, mqo, a));
-    else MVN_CUDA(mvn_launch_pdl(layer_bwd_tc_kernel<false>, dim3(grid), dim3(N_THREADS), (size_t)smem, st, mx, mc, mp, mu, mpo, muo, mq, mqo, a));
+    auto kernel = sum_out ? (a.pair_in ? layer_bwd_tc_kernel<true, true> : layer_bwd_tc_kernel<true, false>)
+                          : (a.pair_in ? layer_bwd_tc_kernel<false, true> : layer_bwd_tc_kernel<false, false>);
+    MVN_CUDA(mvn_launch_pdl(kernel, dim3(grid), dim3(N_THREADS), (size_t)smem, st, mx, mc, mp, mu, mpo, muo, mq, mqo, a));
     (void)lg;
 #if MVN_PHASE_CLOCKS
     if (getenv("MVN_PROF")) {
@@ -675,11 +680,14 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     return mvn_check_launch("layer_bwd_tc");
 }
 
-// Layer l writes the summed stream when its dilation fits a tile and the carry has a home: with video the carry lives in the
-// U input tile, so the layer above must have written a summed stream too.  MOVENET_B200_BWD_PAIR=1 keeps the (P, U) pair everywhere.
+// Opt-in (MOVENET_B200_BWD_SUM=1): layer l writes the summed stream when its dilation fits a tile and the carry has a home: with
+// video the carry lives in the U input tile, so the layer above must have written a summed stream too.  Default: the (P, U) pair
+// everywhere -- measured on one box with both variants compiled from the same templates, the summed stream moves 24 % fewer HBM
+// bytes but is 0..8 % SLOWER (147 vs 136 us per launch): the kernel is bound by its per-tile dependency chain, not by HBM, and the
+// warm-up tile per CTA run (+4 % tiles) and the extra worker barrier cost more than the lighter G2 / W2 save (profiles/r01_ablation.md).
 int mvn_tc_bwd_sum_out(const Geo& g, int layer) {
-    const char* force_pair = getenv("MOVENET_B200_BWD_PAIR");      // read per call: the tests switch it
-    if (force_pair && atoi(force_pair)) return 0;
+    const char* sum = getenv("MOVENET_B200_BWD_SUM");      // read per call: the tests switch it
+    if (!sum || !atoi(sum)) return 0;
     int above = 1;                                   // the top layer's input is zero
     for (int l = g.N - 1; l >= layer; --l) {
         const int s = g.dil[l] <= TILE_T && (!g.video || above);

@@ -96,7 +96,14 @@ def cached_generate(model, audio, video, n_samples, temperature, return_logits=F
         return (out, None) if return_logits else out
     with torch.cuda.device(audio.device):
         st = prefill(model, audio[:, :, :RF].contiguous(), video, fast=fast)
-        res = run_steps(model, st, RF, n_new, temperature, return_logits)
-        codes, logits = res if return_logits else (res, None)
-        out[:, :, RF:].scatter_(1, codes.long().unsqueeze(1), 1.0)
+        logits = steps_into(model, st, RF, n_new, out[:, :, RF:], temperature, return_logits)
     return (out, logits) if return_logits else out
+
+
+def steps_into(model, st, t_start, n_new, out_columns, temperature=0.0, return_logits=False):
+    """generate n_new samples per clip and write them as one-hot columns into ``out_columns`` (B, A, n_new), which must
+    be zero on entry: the reference's output format (movenet/wavenet.py:211-236), one 1.0 per generated sample"""
+    res = run_steps(model, st, t_start, n_new, temperature, return_logits)
+    codes, logits = res if return_logits else (res, None)
+    out_columns.scatter_(1, codes.long().unsqueeze(1), 1.0)
+    return logits

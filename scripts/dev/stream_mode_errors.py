@@ -23,8 +23,9 @@ audio = movenet_b200.one_hot(codes, 64)
 vid = torch.randint(0, 256, (B, 160, 64, 64, 1), device="cuda").float() if video else None
 target = codes[:, m32.receptive_fields:]
 ref = grads_of(m32, audio, vid, target)
+os.environ["MOVENET_B200_BWD_SUM"] = "1"
 got = grads_of(m16, audio, vid, target)
-os.environ["MOVENET_B200_BWD_PAIR"] = "1"
+os.environ["MOVENET_B200_BWD_SUM"] = "0"
 pair = grads_of(m16, audio, vid, target)
 for k in ref:
     print("%-70s sum %.4f pair %.4f sum-vs-pair %.4f |g| %.3e" % (k, rel(got[k], ref[k]), rel(pair[k], ref[k]), rel(got[k], pair[k]), ref[k].norm().item()))

@@ -245,15 +245,16 @@ def _grads_of(m, audio, video, target):
     return {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}
 
 
-@pytest.mark.parametrize("video", [False, True])
-def test_backward_gradient_stream_modes(video, monkeypatch):
-    """The residual-stream gradient between two layer kernels is ONE summed tensor when the producing layer's dilation
-    is <= 128 (it adds its two terms itself, carrying d rows from tile to tile) and the pair (P, U) otherwise.  Dilations
+@pytest.mark.parametrize("video,layer_size", [(False, 9), (True, 3), (True, 9)])
+def test_backward_gradient_stream_modes(video, layer_size, monkeypatch):
+    """The residual-stream gradient between two layer kernels is the pair (P, U) by default; with MOVENET_B200_BWD_SUM=1 it
+    is ONE summed tensor when the producing layer's dilation is <= 128 (it adds its two terms itself, carrying d rows
+    from tile to tile).  Dilations
     1..256 twice: summed, pair, and both hand-overs (pair in / summed out needs the separate carry tile: audio only; with
     video the layers under a wide one stay on the pair).  Ragged T, several clips per CTA run, warm-up tiles.  Checked
-    against the exact fp32 mode, and the forced-pair build of the same step must agree with the default one."""
+    against the exact fp32 mode; both variants of the same step must agree with each other."""
     torch.manual_seed(3)
-    kw = dict(layer_size=9, stack_size=2, input_channels=64, residual_channels=64, skip_channels=8)
+    kw = dict(layer_size=layer_size, stack_size=2, input_channels=64, residual_channels=64, skip_channels=8)
     m32 = movenet_b200.WaveNet(**kw, compute_dtype="fp32").cuda()
     m16 = movenet_b200.WaveNet(**kw, compute_dtype="bf16").cuda()
     m16.load_state_dict(m32.state_dict())
@@ -263,8 +264,9 @@ def test_backward_gradient_stream_modes(video, monkeypatch):
     vid = torch.randint(0, 256, (B, 160, 64, 64, 1), device="cuda").float() if video else None
     target = codes[:, m32.receptive_fields:]
     ref = _grads_of(m32, audio, vid, target)
+    monkeypatch.setenv("MOVENET_B200_BWD_SUM", "1")
     got = _grads_of(m16, audio, vid, target)
-    monkeypatch.setenv("MOVENET_B200_BWD_PAIR", "1")
+    monkeypatch.setenv("MOVENET_B200_BWD_SUM", "0")
     pair = _grads_of(m16, audio, vid, target)
     assert ref.keys() == got.keys() == pair.keys()
     errs = []
