@@ -6,6 +6,11 @@
 //   A = [x_l[t-d] | x_l[t]]  (queue pop from HBM, current activation from registers)  -> bf16 tile
 //   tcgen05.mma  D1[128 x 2C] = A . Wz^T   -> gate in-thread -> bf16 tile
 //   tcgen05.mma  D2[128 x (C+S)] = gated . [Wr|Ws]^T -> residual / skip update in registers
+// One barrier round per layer, not two: the residual update h_{l+1} = h_l + Wr g_l + br sits between the two products, but
+//   Wz_{l+1} [old | h_{l+1}] = Wz_{l+1} [old | h_l] + (Wz1_{l+1} Wr_l) g_l + Wz1_{l+1} br_l
+// so layer l+1's pre-activation is issued TOGETHER with layer l's out product, from the tile that already holds bf16(h_l), the
+// gated tile and a pre-multiplied weight (Wc = Wz1_{l+1} Wr_l, f16, built by the pack kernel; the constant goes in as a gate
+// bias).  h_{l+1} itself is still formed in fp32 registers from D2 for the queue push and the layers above.
 // then the dense head (two more MMAs) and the next token is chosen by the thread that owns the clip:
 // argmax (lowest index on ties) or a draw from softmax(softmax(z)/temperature) need no cross-thread
 // traffic at all.  Two such groups share one CTA (and one copy of the weights in shared memory) and
@@ -54,7 +59,10 @@ struct Img {   // image layout shared by the pack kernel and the decode kernel
     static constexpr int N2 = ((C + DS + 15) / 16) * 16;
     static constexpr int wz = 0, wz_bytes = 2 * C * 2 * C * 2;
     static constexpr int wrs = wz + wz_bytes, wrs_bytes = N2 * C * 2;
-    static constexpr int brs = wrs + wrs_bytes, layer_bytes = brs + N2 * 4;
+    static constexpr int brs = wrs + wrs_bytes;
+    static constexpr int wc = brs + N2 * 4, wc_bytes = 2 * C * C * 2;      // Wc^T[n][k] = (Wz1_l Wr_{l-1})[n][k], f16 (layers >= 1)
+    static constexpr int zb = wc + wc_bytes;                              // Wz1_l br_{l-1} as f16x2 pairs: C/2 filter | C/2 gate
+    static constexpr int layer_bytes = zb + 2 * C * 2;
 };
 
 template <int C>
@@ -76,6 +84,21 @@ __global__ void decode_tc_pack_kernel(const float* __restrict__ packed, PackedLa
             *(__half*)(li + I::wrs + core_off(n, k, C)) = __float2half_rn(v);      // f16: the gated tile it multiplies is f16
         }
         for (int i = i0; i < I::N2; i += stride) ((float*)(li + I::brs))[i] = i < C + DS ? lw[P.obrs + i] : 0.f;
+        if (l > 0) {                                                  // the pre-multiplied hand-over from layer l - 1
+            const float* pw = packed + P.layer0 + (size_t)(l - 1) * P.layer_stride;
+            for (int i = i0; i < 2 * C * C; i += stride) {
+                const int n = i / C, k = i % C;
+                float acc = 0.f;
+                for (int j = 0; j < C; ++j)
+                    acc += lw[P.oWz + (size_t)(C + j) * 2 * C + 2 * (n % C) + n / C] * pw[P.oWrs + (size_t)k * (C + DS) + j];
+                *(__half*)(li + I::wc + core_off(n, k, C)) = __float2half_rn(acc);
+            }
+            for (int i = i0; i < 2 * C; i += stride) {
+                float acc = 0.f;
+                for (int j = 0; j < C; ++j) acc += lw[P.oWz + (size_t)(C + j) * 2 * C + 2 * (i % C) + i / C] * pw[P.obrs + j];
+                ((__half*)(li + I::zb))[i] = __float2half_rn(acc);
+            }
+        }
     }
     for (int i = i0; i < A * 16; i += stride) {                      // W1^T[n][k], k padded 8 -> 16
         const int n = i / 16, k = i % 16;
@@ -128,7 +151,7 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
     // TMEM columns of the group's window: D1 [0, 2C) ; D2 [2C, 2C + N2) ; the head reuses [0, A) once the layers are done
     constexpr int D1 = 0, D2 = 2 * C, DH = 0;
     static_assert(2 * C + I::N2 <= 512 / GROUPS, "TMEM window");
-    const uint32_t i1 = umma_idesc_major(128, 2 * C, 0, 0), i2 = umma_idesc_major(128, I::N2, 0, 0) & ~((1u << 7) | (1u << 10)) /* f16 operands */, ih = umma_idesc_major(128, A, 0, 0);
+    const uint32_t i1 = umma_idesc_major(128, 2 * C, 0, 0), i1h = i1 & ~((1u << 7) | (1u << 10)) /* f16 operands */, i2 = umma_idesc_major(128, I::N2, 0, 0) & ~((1u << 7) | (1u << 10)) /* f16 operands */, ih = umma_idesc_major(128, A, 0, 0);
 
     const int b = (blockIdx.x * GROUPS + grp) * 128 + r;
     const bool live = b < a.B;
@@ -154,52 +177,79 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
 
         // the queue rows x_l[tau - d] do not depend on this step's arithmetic: the row of layer l + 1 is fetched while layer l
         // computes (one global-memory latency per layer would otherwise sit on the token's critical path)
-        auto ring_of = [&](int l) { return a.queues + a.qoff[l] * a.B + ((size_t)(tau % a.dil[l]) * a.B + (live ? b : 0)) * C; };
+        // (dilations are powers of two -- movenet/modules.py:113 builds 2**x -- so the ring slot is a mask, not a division: the
+        // kernel is bound by instruction issue, and two runtime modulos per layer were a tenth of its instructions)
+        auto ring_of = [&](int l) { return a.queues + (a.qoff[l] + (long long)(tau & (a.dil[l] - 1)) * C) * a.B + (size_t)(live ? b : 0) * C; };
         uint4 old_next[C / 8];
 #pragma unroll
         for (int q = 0; q < C / 8; ++q) {
             old_next[q] = make_uint4(0, 0, 0, 0);
             if (live && tau - a.dil[0] >= 0) old_next[q] = ((const uint4*)ring_of(0))[q];
         }
-        for (int l = 0; l < a.N; ++l) {
-            const uint8_t* li = simg + (size_t)l * I::layer_bytes;
+        // prologue: A = [x_0[tau - d] | x_0[tau]], push x_0[tau], pre-activation of layer 0
+        auto stage_old = [&]() {
+#pragma unroll
+            for (int q = 0; q < C / 8; ++q) *(uint4*)(sA + core_off(r, 8 * q, 2 * C)) = old_next[q];
+        };
+        auto stage_push_h = [&](int l) {
             __nv_bfloat16* ring = ring_of(l);
-            // A row = [x_l[tau - d] | x_l[tau]] ; then push x_l[tau]
 #pragma unroll
             for (int q = 0; q < C / 8; ++q) {
-                const uint4 old = old_next[q];
-                *(uint4*)(sA + core_off(r, 8 * q, 2 * C)) = old;
                 const uint4 cur = make_uint4(pack_bf16(h[8 * q], h[8 * q + 1]), pack_bf16(h[8 * q + 2], h[8 * q + 3]),
                                              pack_bf16(h[8 * q + 4], h[8 * q + 5]), pack_bf16(h[8 * q + 6], h[8 * q + 7]));
                 *(uint4*)(sA + core_off(r, C + 8 * q, 2 * C)) = cur;
                 if (live) ((uint4*)ring)[q] = cur;
             }
-            fence_proxy_async();
-            tc_fence_before();
-            group_sync(grp);
-            if (issue_warp) {
-                tc_fence_after();
-                const uint64_t dA = desc_k_plain(smem_u32(sA), 2 * C), dW = desc_k_plain(smem_u32(li + I::wz), 2 * C);
-                if (elect_one()) {
-#pragma unroll
-                    for (int k = 0; k < 2 * C / 16; ++k) umma(tmem_u + D1, desc_adv(dA, k * 256), desc_adv(dW, k * 256), i1, k != 0);
-                    umma_commit(mma_bar);
-                }
-                __syncwarp();
-            }
-            if (l + 1 < a.N) {
-                const __nv_bfloat16* nring = ring_of(l + 1);
-                const bool has = live && tau - a.dil[l + 1] >= 0;
+        };
+        auto prefetch_old = [&](int l) {
+            if (l < a.N) {
+                const __nv_bfloat16* nring = ring_of(l);
+                const bool has = live && tau - a.dil[l] >= 0;
 #pragma unroll
                 for (int q = 0; q < C / 8; ++q) old_next[q] = has ? ((const uint4*)nring)[q] : make_uint4(0, 0, 0, 0);
             }
-            mbar_wait(mma_bar, phase); phase ^= 1;
+        };
+        stage_old();
+        stage_push_h(0);
+        fence_proxy_async();
+        tc_fence_before();
+        group_sync(grp);
+        if (issue_warp) {
             tc_fence_after();
+            const uint64_t dA = desc_k_plain(smem_u32(sA), 2 * C), dW = desc_k_plain(smem_u32(simg + I::wz), 2 * C);
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 2 * C / 16; ++k) umma(tmem_u + D1, desc_adv(dA, k * 256), desc_adv(dW, k * 256), i1, k != 0);
+                umma_commit(mma_bar);
+            }
+            __syncwarp();
+        }
+        prefetch_old(1);
+        mbar_wait(mma_bar, phase); phase ^= 1;
+        tc_fence_after();
+        for (int l = 0; l < a.N; ++l) {
+            // here D1 holds layer l's pre-activation and (l > 0) D2 holds layer l - 1's out product
+            const uint8_t* li = simg + (size_t)l * I::layer_bytes;
+            if (l > 0) {
+                const float* brs = (const float*)(li - I::layer_bytes + I::brs);
+                // (TMEM reads are what this kernel is made of -- 64 B/clk per SM: only the C + 8 live columns of D2 are read)
+                uint32_t v[C + DS];
+#pragma unroll
+                for (int q = 0; q < C / 16; ++q) tmem_ld16(tmem + lane_base + D2 + 16 * q, v + 16 * q);
+                tmem_ld8(tmem + lane_base + D2 + C, v + C);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < C; ++c) h[c] += __uint_as_float(v[c]) + brs[c];
+#pragma unroll
+                for (int s = 0; s < DS; ++s) skip[s] += __uint_as_float(v[C + s]) + brs[C + s];
+                stage_push_h(l);                 // x_l[tau]: queue push, and the second half of the next A tile
+            }
             {
                 uint32_t f[C], g[C];
 #pragma unroll
                 for (int q = 0; q < C / 16; ++q) { tmem_ld16(tmem + lane_base + D1 + 16 * q, f + 16 * q); tmem_ld16(tmem + lane_base + D1 + C + 16 * q, g + 16 * q); }
                 tmem_ld_wait();
+                const uint32_t* zb = (const uint32_t*)(li + I::zb);
 #pragma unroll
                 for (int q = 0; q < C / 8; ++q) {
                     // tanh(f) * sigmoid(g) on channel pairs in packed f16x2 (one MUFU op per two tanh, as in layer_tc.cu): the
@@ -209,39 +259,48 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int c = 8 * q + 2 * e;
-                        const uint32_t fh = f16x2(__uint_as_float(f[c]), __uint_as_float(f[c + 1]));
-                        const uint32_t gh = f16x2(__uint_as_float(g[c]), __uint_as_float(g[c + 1]));
+                        uint32_t fh = f16x2(__uint_as_float(f[c]), __uint_as_float(f[c + 1]));
+                        uint32_t gh = f16x2(__uint_as_float(g[c]), __uint_as_float(g[c + 1]));
+                        if (l > 0) { fh = hadd2(fh, zb[c >> 1]); gh = hadd2(gh, zb[(C + c) >> 1]); }
                         o[e] = hmul2(htanh2(fh), hfma2(htanh2(hmul2(gh, h05)), h05, h05));
                     }
                     *(uint4*)(sG + core_off(r, 8 * q, C)) = make_uint4(o[0], o[1], o[2], o[3]);
                 }
             }
+            if (l + 1 < a.N) stage_old();        // x_{l+1}[tau - d] (fetched one layer ahead)
             fence_proxy_async();
             tc_fence_before();
             group_sync(grp);
             if (issue_warp) {
                 tc_fence_after();
                 const uint64_t dG = desc_k_plain(smem_u32(sG), C), dW = desc_k_plain(smem_u32(li + I::wrs), C);
+                const uint64_t dA = desc_k_plain(smem_u32(sA), 2 * C), dWz = desc_k_plain(smem_u32(li + I::layer_bytes + I::wz), 2 * C),
+                               dWc = desc_k_plain(smem_u32(li + I::layer_bytes + I::wc), C);
+                const bool more = l + 1 < a.N;
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < C / 16; ++k) umma(tmem_u + D2, desc_adv(dG, k * 256), desc_adv(dW, k * 256), i2, k != 0);
+                    if (more) {                  // layer l + 1's pre-activation from [old | h_l] and the gated tile
+#pragma unroll
+                        for (int k = 0; k < 2 * C / 16; ++k) umma(tmem_u + D1, desc_adv(dA, k * 256), desc_adv(dWz, k * 256), i1, k != 0);
+#pragma unroll
+                        for (int k = 0; k < C / 16; ++k) umma(tmem_u + D1, desc_adv(dG, k * 256), desc_adv(dWc, k * 256), i1h, 1);
+                    }
                     umma_commit(mma_bar);
                 }
                 __syncwarp();
             }
+            prefetch_old(l + 2);
             mbar_wait(mma_bar, phase); phase ^= 1;
             tc_fence_after();
-            {
-                const float* brs = (const float*)(li + I::brs);
-                uint32_t v[I::N2];
+        }
+        {   // the last layer's out product: only its skip rows are used (the residual output is discarded)
+            const float* brs = (const float*)(simg + (size_t)(a.N - 1) * I::layer_bytes + I::brs);
+            uint32_t v[DS];
+            tmem_ld8(tmem + lane_base + D2 + C, v);
+            tmem_ld_wait();
 #pragma unroll
-                for (int q = 0; q < I::N2 / 16; ++q) tmem_ld16(tmem + lane_base + D2 + 16 * q, v + 16 * q);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < C; ++c) h[c] += __uint_as_float(v[c]) + brs[c];
-#pragma unroll
-                for (int s = 0; s < DS; ++s) skip[s] += __uint_as_float(v[C + s]) + brs[C + s];
-            }
+            for (int s = 0; s < DS; ++s) skip[s] += __uint_as_float(v[s]) + brs[C + s];
             tc_fence_before();
         }
         // ---- dense head: a1 = W1 lrelu(skip) + b1 ; z = W2 lrelu(a1) + b2 -----------------------------
@@ -422,6 +481,7 @@ int run_steps(const Geo& g, DecTcArgs& a, const float* packed, const PackedLayou
 
 int mvn_tc_decode_supported(const Geo& g) {
     if (g.video || g.S != DS || (g.C != 16 && g.C != 32) || g.A % 16 || g.A < 16 || g.A > 128) return 0;
+    for (int l = 0; l < g.N; ++l) if (g.dil[l] & (g.dil[l] - 1)) return 0;      // ring slots are taken with a mask
     DecTcArgs a;
     const int img = g.C == 16 ? image_offsets<16>(g, a) : image_offsets<32>(g, a);
     const int smem = g.C == 16 ? smem_bytes<16>(g, img) : smem_bytes<32>(g, img);
