@@ -176,9 +176,15 @@ def _ncu_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None"""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
-        return json.load(open(path)).get(kernel)
+        table = json.load(open(path))
     except (OSError, ValueError):
         return None
+    if kernel in table:
+        return table[kernel]
+    for k, v in table.items():          # template instantiations: "name<...>"
+        if k.startswith(kernel + "<"):
+            return v
+    return None
 
 
 def layer_roofline(model, audio, video, dtype):
@@ -249,7 +255,7 @@ def layer_roofline(model, audio, video, dtype):
                 "frac": ach / pk["hbm_gbs"], "traffic": _ncu_traffic(kernel), "ms_per_launch": ms,
                 "bytes_per_sample": per_sample, "samples_per_launch": n}
 
-    return (obj("residual layer backward", ms_b, bwd_b, n_b, "layer_bwd_tc_kernel", bwd_design),
+    return (obj("residual layer backward", ms_b, bwd_b, n_b, "layer_bwd_tc_kernel<1, 0>" if summed else "layer_bwd_tc_kernel<0, 1>", bwd_design),
             obj("residual layer forward", ms_f, fwd_b, n_f, "layer_fwd_tc_kernel"))
 
 
