@@ -102,13 +102,19 @@ __global__ void decode_tc_pack_kernel(const float* __restrict__ packed, PackedLa
     }
     for (int i = i0; i < A * 16; i += stride) {                      // W1^T[n][k], k padded 8 -> 16
         const int n = i / 16, k = i % 16;
-        *(__nv_bfloat16*)(img + oW1 + core_off(n, k, 16)) = __float2bfloat16(k < DS ? packed[P.w1p + (size_t)k * A + n] : 0.f);
+        // k = DS carries the bias: the A tile holds 1.0 there (b1 rounded to bf16 like the weights)
+        *(__nv_bfloat16*)(img + oW1 + core_off(n, k, 16)) = __float2bfloat16(k < DS ? packed[P.w1p + (size_t)k * A + n] : k == DS ? packed[P.b1 + n] : 0.f);
     }
     for (int i = i0; i < A * A; i += stride) {                       // W2^T[n][k]
         const int n = i / A, k = i % A;
         *(__nv_bfloat16*)(img + oW2 + core_off(n, k, A)) = __float2bfloat16(packed[P.w2p + (size_t)k * A + n]);
     }
     for (int i = i0; i < A; i += stride) { ((float*)(img + oB1))[i] = packed[P.b1 + i]; ((float*)(img + oB2))[i] = packed[P.b2 + i]; }
+    for (int i = i0; i < DS; i += stride) {          // sum over the layers of the skip biases
+        float acc = 0.f;
+        for (int l = 0; l < N; ++l) acc += packed[P.layer0 + (size_t)l * P.layer_stride + P.obrs + C + i];
+        ((float*)(img + oWin))[i] = acc;
+    }
 }
 
 template <int C>
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
 #pragma unroll
                 for (int c = 0; c < C; ++c) h[c] += __uint_as_float(v[c]) + brs[c];
 #pragma unroll
-                for (int s = 0; s < DS; ++s) skip[s] += __uint_as_float(v[C + s]) + brs[C + s];
+                for (int s = 0; s < DS; ++s) skip[s] += __uint_as_float(v[C + s]);       // (the skip biases are added once, below)
                 stage_push_h(l);                 // x_l[tau]: queue push, and the second half of the next A tile
             }
             {
@@ -295,12 +301,12 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
             tc_fence_after();
         }
         {   // the last layer's out product: only its skip rows are used (the residual output is discarded)
-            const float* brs = (const float*)(simg + (size_t)(a.N - 1) * I::layer_bytes + I::brs);
+            const float* bs = (const float*)(simg + a.oWin);       // sum over the layers of the skip biases (pack kernel)
             uint32_t v[DS];
             tmem_ld8(tmem + lane_base + D2 + C, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int s = 0; s < DS; ++s) skip[s] += __uint_as_float(v[s]) + brs[C + s];
+            for (int s = 0; s < DS; ++s) skip[s] += __uint_as_float(v[s]) + bs[s];
             tc_fence_before();
         }
         // ---- dense head: a1 = W1 lrelu(skip) + b1 ; z = W2 lrelu(a1) + b2 -----------------------------
@@ -312,7 +318,7 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
                 o[e] = pack_bf16(x0 > 0.f ? x0 : MVN_LRELU_SLOPE * x0, x1 > 0.f ? x1 : MVN_LRELU_SLOPE * x1);
             }
             *(uint4*)(sH + core_off(r, 0, 16)) = make_uint4(o[0], o[1], o[2], o[3]);
-            *(uint4*)(sH + core_off(r, 8, 16)) = make_uint4(0, 0, 0, 0);
+            *(uint4*)(sH + core_off(r, 8, 16)) = make_uint4(0x3F80u, 0, 0, 0);      // 1.0 at k = 8: b1 comes out of the MMA
         }
         fence_proxy_async();
         tc_fence_before();
@@ -329,16 +335,15 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
         mbar_wait(mma_bar, phase); phase ^= 1;
         tc_fence_after();
         {
-            const float* b1 = (const float*)(simg + a.oB1);
             for (int q = 0; q < A / 16; ++q) {
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + DH + 16 * q, v);
                 tmem_ld_wait();
                 uint32_t o[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    float x0 = __uint_as_float(v[2 * e]) + b1[16 * q + 2 * e], x1 = __uint_as_float(v[2 * e + 1]) + b1[16 * q + 2 * e + 1];
-                    o[e] = pack_bf16(x0 > 0.f ? x0 : MVN_LRELU_SLOPE * x0, x1 > 0.f ? x1 : MVN_LRELU_SLOPE * x1);
+                for (int e = 0; e < 8; ++e) {       // leaky ReLU as max(x, slope * x): two instructions per element
+                    const float x0 = __uint_as_float(v[2 * e]), x1 = __uint_as_float(v[2 * e + 1]);
+                    o[e] = pack_bf16(fmaxf(x0, MVN_LRELU_SLOPE * x0), fmaxf(x1, MVN_LRELU_SLOPE * x1));
                 }
                 *(uint4*)(sH + core_off(r, 16 * q, A)) = make_uint4(o[0], o[1], o[2], o[3]);
                 *(uint4*)(sH + core_off(r, 16 * q + 8, A)) = make_uint4(o[4], o[5], o[6], o[7]);
@@ -454,7 +459,7 @@ int image_offsets(const Geo& g, DecTcArgs& a) {
     a.oB1 = o; o += g.A * 4;
     a.oW2 = o; o += g.A * g.A * 2;
     a.oB2 = o; o += g.A * 4;
-    a.oWin = o;
+    a.oWin = o; o += DS * 4;                       // (the slot holds the summed skip biases)
     a.img_bytes = (o + 15) & ~15;
     return a.img_bytes;
 }
