@@ -368,15 +368,28 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
         {
             const float* b2 = (const float*)(simg + a.oB2);
             float best = -INFINITY;
+            // (the kernel is bound by instruction issue: the plain path carries no logit-store code, and the biases come as float4)
+            float* zout = (a.out_logits && live) ? a.out_logits + ((size_t)b * a.n_new + (i - a.t_start)) * A : nullptr;
+            const bool any_out = a.out_logits != nullptr;
             for (int q = 0; q < A / 16; ++q) {
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + DH + 16 * q, v);
+                float bb[16];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float4 t4 = ((const float4*)(b2 + 16 * q))[e];
+                    bb[4 * e] = t4.x; bb[4 * e + 1] = t4.y; bb[4 * e + 2] = t4.z; bb[4 * e + 3] = t4.w;
+                }
                 tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const float z = __uint_as_float(v[e]) + b2[16 * q + e];
+                    const float z = __uint_as_float(v[e]) + bb[e];
                     if (z > best) { best = z; arg = 16 * q + e; }
-                    if (a.out_logits && live) a.out_logits[((size_t)b * a.n_new + (i - a.t_start)) * A + 16 * q + e] = z;
+                    bb[e] = z;
+                }
+                if (any_out && zout) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ((float4*)(zout + 16 * q))[e] = make_float4(bb[4 * e], bb[4 * e + 1], bb[4 * e + 2], bb[4 * e + 3]);
                 }
             }
             if (a.temperature > 0.f) {      // draw from softmax(softmax(z) / temperature) (movenet/wavenet.py:227-231)
