@@ -191,7 +191,8 @@ int mvn_decode_steps(const mvn_shape_t* s, const void* packed, void* state, cons
  * overrides the chosen token (teacher forcing, used by the parity tests to compare logits step by step). */
 int mvn_decode_tc_supported(const mvn_shape_t* s);
 size_t mvn_decode_tc_state_bytes(const mvn_shape_t* s);
-int mvn_decode_tc_prefill(const mvn_shape_t* s, const void* acts, void* state, void* stream);
+/* `packed`: the weights of mvn_pack_weights (the queues hold the activations minus the accumulated residual biases). */
+int mvn_decode_tc_prefill(const mvn_shape_t* s, const void* packed, const void* acts, void* state, void* stream);
 int mvn_decode_tc_steps(const mvn_shape_t* s, const void* packed, void* state, int t_start, int n_new,
                         int* out_codes_t, float* out_logits, const int* forced, float temperature, unsigned seed,
                         void* stream);

@@ -63,7 +63,7 @@ SIGNATURES = {
     "mvn_decode_steps": (_I, [_SP, _P, _P, _P, _I, _I, _P, _P, C.c_float, C.c_uint, _P]),
     "mvn_decode_tc_supported": (_I, [_SP]),
     "mvn_decode_tc_state_bytes": (_SZ, [_SP]),
-    "mvn_decode_tc_prefill": (_I, [_SP, _P, _P, _P]),
+    "mvn_decode_tc_prefill": (_I, [_SP, _P, _P, _P, _P]),
     "mvn_decode_tc_steps": (_I, [_SP, _P, _P, _I, _I, _P, _P, _P, C.c_float, C.c_uint, _P]),
 }
 

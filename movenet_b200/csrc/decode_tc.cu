@@ -9,8 +9,11 @@
 // One barrier round per layer, not two: the residual update h_{l+1} = h_l + Wr g_l + br sits between the two products, but
 //   Wz_{l+1} [old | h_{l+1}] = Wz_{l+1} [old | h_l] + (Wz1_{l+1} Wr_l) g_l + Wz1_{l+1} br_l
 // so layer l+1's pre-activation is issued TOGETHER with layer l's out product, from the tile that already holds bf16(h_l), the
-// gated tile and a pre-multiplied weight (Wc = Wz1_{l+1} Wr_l, f16, built by the pack kernel; the constant goes in as a gate
-// bias).  h_{l+1} itself is still formed in fp32 registers from D2 for the queue push and the layers above.
+// gated tile and a pre-multiplied weight (Wc = Wz1_{l+1} Wr_l, f16, built by the pack kernel).  h_{l+1} itself is still formed
+// in fp32 registers from D2 for the queue push and the layers above.  The residual biases never appear in the step loop:
+// registers, tiles and queues hold h^_l = h_l - beta_l with beta_l = br_0 + .. + br_{l-1} (h^_{l+1} = h^_l + Wr g_l exactly), the
+// pre-activation gets the constant (Wz0_l + Wz1_l) beta_l as a gate bias, and the prefill kernel subtracts beta_l from the
+// training forward's activations.
 // then the dense head (two more MMAs) and the next token is chosen by the thread that owns the clip:
 // argmax (lowest index on ties) or a draw from softmax(softmax(z)/temperature) need no cross-thread
 // traffic at all.  Two such groups share one CTA (and one copy of the weights in shared memory) and
@@ -61,7 +64,7 @@ struct Img {   // image layout shared by the pack kernel and the decode kernel
     static constexpr int wrs = wz + wz_bytes, wrs_bytes = N2 * C * 2;
     static constexpr int brs = wrs + wrs_bytes;
     static constexpr int wc = brs + N2 * 4, wc_bytes = 2 * C * C * 2;      // Wc^T[n][k] = (Wz1_l Wr_{l-1})[n][k], f16 (layers >= 1)
-    static constexpr int zb = wc + wc_bytes;                              // Wz1_l br_{l-1} as f16x2 pairs: C/2 filter | C/2 gate
+    static constexpr int zb = wc + wc_bytes;                              // (Wz0_l + Wz1_l) beta_l as f16x2 pairs: C/2 filter | C/2 gate
     static constexpr int layer_bytes = zb + 2 * C * 2;
 };
 
@@ -93,9 +96,14 @@ __global__ void decode_tc_pack_kernel(const float* __restrict__ packed, PackedLa
                     acc += lw[P.oWz + (size_t)(C + j) * 2 * C + 2 * (n % C) + n / C] * pw[P.oWrs + (size_t)k * (C + DS) + j];
                 *(__half*)(li + I::wc + core_off(n, k, C)) = __float2half_rn(acc);
             }
-            for (int i = i0; i < 2 * C; i += stride) {
+            for (int i = i0; i < 2 * C; i += stride) {             // (Wz0_l + Wz1_l) beta_l, beta_l = sum of the residual biases below
                 float acc = 0.f;
-                for (int j = 0; j < C; ++j) acc += lw[P.oWz + (size_t)(C + j) * 2 * C + 2 * (i % C) + i / C] * pw[P.obrs + j];
+                for (int j = 0; j < C; ++j) {
+                    float beta = 0.f;
+                    for (int m = 0; m < l; ++m) beta += packed[P.layer0 + (size_t)m * P.layer_stride + P.obrs + j];
+                    const int col = 2 * (i % C) + i / C;
+                    acc += (lw[P.oWz + (size_t)j * 2 * C + col] + lw[P.oWz + (size_t)(C + j) * 2 * C + col]) * beta;
+                }
                 ((__half*)(li + I::zb))[i] = __float2half_rn(acc);
             }
         }
@@ -169,14 +177,11 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
         const int tau = i - 1;
         float h[C], skip[DS];
 #pragma unroll
-        for (int c = 0; c < C; ++c) h[c] = 0.f;
-        if (code_prev >= 0) {
-#pragma unroll
-            for (int c = 0; c < C; c += 4) { const float4 w = *(const float4*)(win + (size_t)code_prev * C + c); h[c] += w.x; h[c + 1] += w.y; h[c + 2] += w.z; h[c + 3] += w.w; }
-        }
-        if (code_cur >= 0) {
-#pragma unroll
-            for (int c = 0; c < C; c += 4) { const float4 w = *(const float4*)(win + ((size_t)A + code_cur) * C + c); h[c] += w.x; h[c + 1] += w.y; h[c + 2] += w.z; h[c + 3] += w.w; }
+        for (int c = 0; c < C; c += 4) {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 w0 = code_prev >= 0 ? *(const float4*)(win + (size_t)code_prev * C + c) : z4;
+            const float4 w1 = code_cur >= 0 ? *(const float4*)(win + ((size_t)A + code_cur) * C + c) : z4;
+            h[c] = w0.x + w1.x; h[c + 1] = w0.y + w1.y; h[c + 2] = w0.z + w1.z; h[c + 3] = w0.w + w1.w;
         }
 #pragma unroll
         for (int s = 0; s < DS; ++s) skip[s] = 0.f;
@@ -237,7 +242,6 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
             // here D1 holds layer l's pre-activation and (l > 0) D2 holds layer l - 1's out product
             const uint8_t* li = simg + (size_t)l * I::layer_bytes;
             if (l > 0) {
-                const float* brs = (const float*)(li - I::layer_bytes + I::brs);
                 // (TMEM reads are what this kernel is made of -- 64 B/clk per SM: only the C + 8 live columns of D2 are read)
                 uint32_t v[C + DS];
 #pragma unroll
@@ -245,7 +249,7 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
                 tmem_ld8(tmem + lane_base + D2 + C, v + C);
                 tmem_ld_wait();
 #pragma unroll
-                for (int c = 0; c < C; ++c) h[c] += __uint_as_float(v[c]) + brs[c];
+                for (int c = 0; c < C; ++c) h[c] += __uint_as_float(v[c]);            // h^ (bias-free, see the header)
 #pragma unroll
                 for (int s = 0; s < DS; ++s) skip[s] += __uint_as_float(v[C + s]);       // (the skip biases are added once, below)
                 stage_push_h(l);                 // x_l[tau]: queue push, and the second half of the next A tile
@@ -441,13 +445,16 @@ __global__ void __launch_bounds__(128 * Cfg<C>::GROUPS, 1) decode_tc_kernel(cons
 
 // rings (layer, slot, clip, channel) bf16 from the layer inputs of a forward over the T-column prompt:
 // ring_l[tau % d] = x_l[tau] for tau in [T-1-d, T-1)  (the first decode step re-evaluates time T-1 itself)
-__global__ void decode_tc_prefill_kernel(const void* __restrict__ x, int adt, int B, int T, int C, int d, __nv_bfloat16* __restrict__ ring) {
+__global__ void decode_tc_prefill_kernel(const void* __restrict__ x, int adt, int B, int T, int C, int d, __nv_bfloat16* __restrict__ ring,
+                                         const float* __restrict__ packed, long long brs0, long long layer_stride, int layer) {
     const long long n = (long long)B * d * C;
     const int Tend = T - 1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C); const long long rr = i / C; const int b = (int)(rr % B); const int slot = (int)(rr / B);
         int tau = (Tend / d) * d + slot; if (tau >= Tend) tau -= d;
-        ring[i] = __float2bfloat16(tau >= 0 ? mvn_ld(x, adt, ((size_t)b * T + tau) * C + c) : 0.f);
+        float beta = 0.f;                            // the queues hold h^ = h - beta_l (decode_tc_kernel)
+        for (int m = 0; m < layer; ++m) beta += packed[brs0 + m * layer_stride + c];
+        ring[i] = __float2bfloat16(tau >= 0 ? mvn_ld(x, adt, ((size_t)b * T + tau) * C + c) - beta : 0.f);
     }
 }
 __global__ void decode_tc_last2_kernel(const int* __restrict__ codes, int B, int T, int* __restrict__ last2) {
@@ -518,9 +525,10 @@ extern "C" int mvn_decode_tc_supported(const mvn_shape_t* s) {
     return mvn_tc_decode_supported(g);
 }
 
-extern "C" int mvn_decode_tc_prefill(const mvn_shape_t* s, const void* acts, void* state, void* stream) {
+extern "C" int mvn_decode_tc_prefill(const mvn_shape_t* s, const void* packed, const void* acts, void* state, void* stream) {
     Geo g; MVN_REQUIRE(s && geo_init(g, s) == 0, "mvn_decode_tc_prefill: bad shape");
-    MVN_REQUIRE(acts && state && mvn_tc_decode_supported(g), "mvn_decode_tc_prefill: unsupported shape");
+    MVN_REQUIRE(packed && acts && state && mvn_tc_decode_supported(g), "mvn_decode_tc_prefill: unsupported shape");
+    PackedLayout P; packed_layout(g, P);
     ActsLayout AL; acts_layout(g, AL);
     long long qoff[MVN_MAX_LAYERS];
     const size_t qe = queue_elems(g, qoff);
@@ -531,7 +539,9 @@ extern "C" int mvn_decode_tc_prefill(const mvn_shape_t* s, const void* acts, voi
         const void* x = (const char*)acts + AL.x0 + (size_t)l * AL.x_stride;
         const long long n = (long long)g.B * g.dil[l] * g.C;
         decode_tc_prefill_kernel<<<mvn_cdiv(n, 256) < 1184 ? mvn_cdiv(n, 256) : 1184, 256, 0, st>>>(x, g.adt, g.B, g.T, g.C, g.dil[l],
-                                                                                                 queues + qoff[l] * g.B);
+                                                                                                 queues + qoff[l] * g.B,
+                                                                                                 (const float*)packed, (long long)(P.layer0 + P.obrs),
+                                                                                                 (long long)P.layer_stride, l);
     }
     decode_tc_last2_kernel<<<mvn_cdiv(g.B, 128), 128, 0, st>>>((const int*)((const char*)acts + AL.codes), g.B, g.T, last2);
     return mvn_check_launch("decode_tc_prefill");
@@ -542,6 +552,8 @@ extern "C" int mvn_decode_tc_steps(const mvn_shape_t* s, const void* packed, voi
                                    void* stream) {
     Geo g; MVN_REQUIRE(s && geo_init(g, s) == 0, "mvn_decode_tc_steps: bad shape");
     MVN_REQUIRE(packed && state && out_codes_t && n_new >= 0 && t_start >= 1 && mvn_tc_decode_supported(g), "mvn_decode_tc_steps: bad arguments");
+    // every queue row the steps pop was pushed by a real time step (no zero padding inside the queues: they hold h - beta)
+    for (int l = 0; l < g.N; ++l) MVN_REQUIRE(t_start - 1 >= g.dil[l], "mvn_decode_tc_steps: t_start must be past every dilation (prompt >= receptive field)");
     if (n_new == 0) return 0;
     DecTcArgs a; memset(&a, 0, sizeof(a));
     PackedLayout P; packed_layout(g, P);

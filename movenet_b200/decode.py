@@ -52,7 +52,7 @@ def prefill(model, prompt, video, fast=False):
         if not _lib.load().mvn_decode_tc_supported(C.byref(shape)):
             raise _lib.MovenetB200Error("the tensor-core decoder does not support this model shape")
         state = torch.zeros(_lib.size("mvn_decode_tc_state_bytes", shape), dtype=torch.uint8, device=dev)
-        _lib.call("mvn_decode_tc_prefill", C.byref(shape), acts.data_ptr(), state.data_ptr(), _stream())
+        _lib.call("mvn_decode_tc_prefill", C.byref(shape), bufs.packed.data_ptr(), acts.data_ptr(), state.data_ptr(), _stream())
         return DecodeState(shape, bufs, state, None, B, A, fast=True)
     state = torch.zeros(_lib.size("mvn_decode_state_bytes", shape), dtype=torch.uint8, device=dev)
     _lib.call("mvn_decode_prefill", C.byref(shape), acts.data_ptr(), state.data_ptr(), _stream())
