@@ -107,12 +107,14 @@ def test_bf16_ragged_tile_edges():
         assert (a - b).abs().max().item() <= LOGIT_RTOL * a.abs().max().item(), T
 
 
-def test_tensor_core_decoder_teacher_forced_logits():
-    """Throughput decoder (tcgen05, bf16 queues) on the receptive-field architecture (stack_size 1, C 16, A 128):
+@pytest.mark.parametrize("name", ["cfg04_short", "cfg03"])
+def test_tensor_core_decoder_teacher_forced_logits(name):
+    """Throughput decoder (tcgen05, bf16 queues) on the receptive-field architecture (stack_size 1, C 16, A 128) and on
+    the scale-up one (2 x 2 layers, C 32: the two-group variant of the kernel):
     teacher-forced with the reference's own generated tokens, its logits must match the oracle's true-causal logits
     within the bf16 tolerance at every step; free-running it must emit valid tokens = argmax of its own logits."""
     from movenet_b200.decode import fast_mode_available, prefill, run_steps
-    fx = load_golden("cfg04_short")
+    fx = load_golden(name)
     m = build(fx, "fp32")
     RF = m.receptive_fields
     audio = golden_audio(fx).cuda()
@@ -278,3 +280,25 @@ def test_backward_gradient_stream_modes(video, layer_size, monkeypatch):
     a, b, c = (torch.cat([g[k].flatten() for k in ref]) for g in (got, ref, pair))
     assert F.cosine_similarity(a, b, dim=0).item() >= GRAD_COS
     assert F.cosine_similarity(a, c, dim=0).item() >= 0.999
+
+
+def test_tensor_core_decoder_sampling_is_seeded_and_valid():
+    """temperature > 0 in the throughput decoder: tokens are valid codes, identical clips with the same seed draw
+    per-clip streams (clip index enters the counter), the same torch seed reproduces them."""
+    from movenet_b200.decode import prefill, run_steps
+    fx = load_golden("cfg04_short")
+    m = build(fx, "fp32")
+    RF = m.receptive_fields
+    audio = golden_audio(fx).cuda()[:1, :, :RF].repeat(256, 1, 1).contiguous()
+    st = prefill(m, audio, None, fast=True)
+    greedy = run_steps(m, st, RF, 12, 0.0)
+    assert len({tuple(r.tolist()) for r in greedy.cpu()}) == 1   # argmax decoding: identical prompts, identical clips
+    st = prefill(m, audio, None, fast=True)
+    torch.manual_seed(11)
+    hot = run_steps(m, st, RF, 12, 5.0)
+    assert int(hot.min()) >= 0 and int(hot.max()) < m.input_channels
+    assert len({tuple(r.tolist()) for r in hot.cpu()}) > 1   # identical prompts, different clips: different draws
+    st = prefill(m, audio, None, fast=True)
+    torch.manual_seed(11)
+    again = run_steps(m, st, RF, 12, 5.0)
+    assert torch.equal(hot, again)                        # same torch seed: same streams
