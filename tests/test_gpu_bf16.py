@@ -35,8 +35,12 @@ def rel_l2(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
+@pytest.mark.parametrize("summed", ["0", "1"])
 @pytest.mark.parametrize("name", ["cfg00", "cfg00_gain", "cfg03", "cfg04_short", "testarch_small", "odd"])
-def test_bf16_forward_loss_and_grads_against_golden(name):
+def test_bf16_forward_loss_and_grads_against_golden(name, summed, monkeypatch):
+    """summed = "1": the backward's one-stream variant (MOVENET_B200_BWD_SUM, layer_tc_bwd.cu) on the same fixtures: few tiles
+    per clip, so nearly every CTA run is a warm-up tile plus one tile."""
+    monkeypatch.setenv("MOVENET_B200_BWD_SUM", summed)
     fx = load_golden(name)
     m = build(fx, "bf16")
     audio = golden_audio(fx).cuda()
