@@ -17,12 +17,13 @@
 //         bias grads = the same A operands times an all-ones B
 //   epilogue 2: P' = dxs + D4[tap1] ; U' = D4[tap0]  -> TMA stores ; d(ctx) += D4[ctx]
 //
-// Summed output (opt-in, MOVENET_B200_BWD_SUM=1; layers with dilation <= 128): the producing layer adds
-// the two terms itself and writes ONE stream D'[t] = P'[t] + U'[t + d]: row r of the sum needs U' row r + d, which is in the
-// same tile (read back from the staging tile) or in the first d rows of the next tile in time.  A CTA therefore walks a
-// CONTIGUOUS run of tiles backwards in time and keeps those d rows ("carry") in shared memory; the run starts with one
-// warm-up tile (the tile after the run, recomputed, nothing stored or accumulated) unless the run ends at a clip's end.
-// The consumer then reads one tile instead of two, and G2 / W2 / the bias sums lose their second pass.
+// Summed output (opt-in, MOVENET_B200_BWD_SUM=1; every dilation from the top layer down to this one <= 128, <= 32 with video): the
+// producing layer adds the two terms itself and writes ONE stream D'[t] = P'[t] + U'[t + d]: row r of the sum needs U' row r + d,
+// which is in the same tile (exchanged through the U tile, free because the input is one stream too) or in the first d rows of
+// the next tile in time.  A CTA therefore walks a CONTIGUOUS run of tiles backwards in time and keeps those d rows ("carry") in
+// shared memory; the run starts with one warm-up tile (the tile after the run, recomputed, nothing stored or accumulated) unless
+// the run ends at a clip's end.  The consumer reads one tile instead of two, G2 / W2 / the bias sums lose their second pass, the
+// sum is staged in the U tile so epilogue 2 never waits for the weight-gradient MMAs, and the control warp reloads x/ctx itself.
 //
 // The weight-gradient accumulators stay in TMEM for the CTA's whole tile loop and are written once
 // per CTA as partial sums; a small second kernel reduces the partials in a fixed order
@@ -85,8 +86,11 @@ __device__ __forceinline__ TileSeq tile_seq(const BwdArgs& a, bool sum_out) {
 
 __host__ __device__ inline int bwd_tiles_off(int nc, int N2) { return smem_a_off(nc, N2); }
 // tiles after the image: A0..A(nc-1) | DXS | DSK | U | DZ0 | DZ1 | G | [Q, video only] | ONES(1 KB) | barriers
-// (audio only: a CARRY tile takes the Q tile's place; with video the carry lives in the U tile, free when the input is one stream)
-__host__ __device__ inline int bwd_smem_total(int nc, int N2) { return bwd_tiles_off(nc, N2) + (nc + 7) * TILE_BYTES + 1024 + 128; }
+// (audio only: a CARRY tile takes the Q tile's place; with video the carry (dilation <= 32) sits after the barriers)
+constexpr int CARRY_VIDEO_ROWS = 32;
+__host__ __device__ inline int bwd_smem_total(int nc, int N2) {
+    return bwd_tiles_off(nc, N2) + (nc + 7) * TILE_BYTES + 1024 + 128 + (nc == 3 ? CARRY_VIDEO_ROWS * 128 : 0);
+}
 
 // every lane has fenced its own writes; one lane signals for the warp
 __device__ __forceinline__ void warp_arrive(uint64_t* bar) {
@@ -116,7 +120,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     uint8_t* sDZ = sDSK + TILE_BYTES;             // DZ0 (filter half) | DZ1 (gate half)
     uint8_t* sG = sDZ + 2 * TILE_BYTES;
     uint8_t* sQ = sG + TILE_BYTES;                // running sum of the context gradient (video only)
-    uint8_t* sCARRY = nc == 3 ? sU : sQ;          // first d rows of U' of the tile processed before this one (summed output)
+    // first d rows of U' of the tile processed before this one (summed output): audio: the spare tile; video: 4 KB after the barriers
+    uint8_t* sCARRY = nc == 3 ? sQ + TILE_BYTES + 1024 + 128 : sQ;
     uint8_t* sONES = sQ + TILE_BYTES;
     // barriers, one completion per tile each (parity = tile iteration & 1), except IMG (once).
     // E_* are the worker -> control-warp signals (one arrival per worker warp), the rest are TMA / tcgen05.commit completions.
@@ -308,10 +313,14 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             // (the x/ctx tiles of the next tile are reloaded by worker thread 0 as soon as it has seen W1: this warp is
             // still blocked issuing W2 then, and the reload is the head of the next tile's dependency chain)
             CLKC(12);
+            if (SUM_OUT && has_next) {             // summed output: the workers do not wait for W1, this warp reloads x/ctx
+                mbar_wait(bar + W1, ph);
+                if (leader) load_a_tiles(nb, n0);
+            }
             mbar_wait(bar + E_OUT, ph);            // P', U', Q' are staged; nobody reads DXS or the tile's TMEM columns any more
             CLKC(13);
             if (leader && !is_warm) {
-                tma_store_3d(&map_pout, sDZ, 0, t0, b);
+                tma_store_3d(&map_pout, SUM_OUT ? sU : sDZ, 0, t0, b);
                 if (!SUM_OUT) tma_store_3d(&map_uout, sDZ + TILE_BYTES, 0, t0, b);
                 if (nc == 3) tma_store_3d(&map_qout, sQ, 0, t0, b);
                 tma_commit();
@@ -471,54 +480,59 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 *p1 = make_uint4(o[4], o[5], o[6], o[7]);
             }
             CLKW(9);
-            if (SUM_OUT) load_uo();              // (after the Q part: fewer values live at once)
-            // summed output: the U' rows this thread's sum needs from the tile processed before this one (rows r + d - 128 of
-            // the carry; written after that tile's barrier below and ordered before this read by E_OUT -> G1 -> G3)
-            const int rs = r + a.dil;
-            const int cs0 = ((2 * half) ^ (rs & 7)) << 4, cs1 = ((2 * half + 1) ^ (rs & 7)) << 4;
-            uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
-            if (SUM_OUT && rs >= TILE_T && it != 0 && tile % a.tiles_per_clip != a.tiles_per_clip - 1) {
-                c0 = *(const uint4*)(sCARRY + (rs - TILE_T) * 128 + cs0);
-                c1 = *(const uint4*)(sCARRY + (rs - TILE_T) * 128 + cs1);
-            }
-            mbar_wait(bar + W1, ph);            // W1 no longer reads the DZ tiles, nor the x/ctx tiles:
-            if (tid == 0 && has_next) {         // reload those for the next tile right away
-                const int nt = tile + sq.step, nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
-                mbar_expect_tx(bar + A_IN, (uint32_t)(nc * TILE_BYTES));
-                tma_load_3d(sA, &map_x, bar + A_IN, 0, n0 - a.dil, nb);
-                tma_load_3d(sA + TILE_BYTES, &map_x, bar + A_IN, 0, n0, nb);
-                if (nc == 3) tma_load_3d(sA + 2 * TILE_BYTES, &map_ctx, bar + A_IN, 0, n0, nb);
-            }
-            CLKW(10);
-            *(uint4*)(sDZ + TILE_BYTES + o0) = make_uint4(uo[0], uo[1], uo[2], uo[3]);
-            *(uint4*)(sDZ + TILE_BYTES + o1) = make_uint4(uo[4], uo[5], uo[6], uo[7]);
             if (SUM_OUT) {
-                asm volatile("bar.sync 1, %0;" ::"n"(N_WORKERS) : "memory");      // every U' row of this tile is staged
-                if (rs < TILE_T) {
-                    c0 = *(const uint4*)(sDZ + TILE_BYTES + rs * 128 + cs0);
-                    c1 = *(const uint4*)(sDZ + TILE_BYTES + rs * 128 + cs1);
-                }
-                if (r < a.dil) {                 // this tile's first d rows of U' are the next tile's carry
-                    *(uint4*)(sCARRY + o0) = *(const uint4*)(sDZ + TILE_BYTES + o0);
-                    *(uint4*)(sCARRY + o1) = *(const uint4*)(sDZ + TILE_BYTES + o1);
+                // One summed stream: the U' term of row r is U' row r + d -- of this tile, exchanged through the U tile (nothing
+                // else lives there: the input is one stream), or of the tile processed before this one (the carry: its first d
+                // rows, written after that tile's first barrier and ordered before this read by E_OUT -> G1 -> G3).  The sum is
+                // staged in the U tile too, so this epilogue never waits for the weight-gradient MMAs (they read the DZ tiles).
+                load_uo();
+                *(uint4*)(sU + o0) = make_uint4(uo[0], uo[1], uo[2], uo[3]);
+                *(uint4*)(sU + o1) = make_uint4(uo[4], uo[5], uo[6], uo[7]);
+                const int rs = r + a.dil;
+                const int cs0 = ((2 * half) ^ (rs & 7)) << 4, cs1 = ((2 * half + 1) ^ (rs & 7)) << 4;
+                uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+                if (rs >= TILE_T && it != 0 && tile % a.tiles_per_clip != a.tiles_per_clip - 1) {
+                    c0 = *(const uint4*)(sCARRY + (rs - TILE_T) * 128 + cs0);
+                    c1 = *(const uint4*)(sCARRY + (rs - TILE_T) * 128 + cs1);
                 }
                 uint32_t v[16];
                 tmem_ld16(tmem + lane_base + 64 + 16 * half, v);
+                asm volatile("bar.sync 1, %0;" ::"n"(N_WORKERS) : "memory");      // every U' row of this tile is in the U tile
+                if (rs < TILE_T) {
+                    c0 = *(const uint4*)(sU + rs * 128 + cs0);
+                    c1 = *(const uint4*)(sU + rs * 128 + cs1);
+                }
+                if (r < a.dil) {                 // this tile's first d rows of U' are the next tile's carry
+                    *(uint4*)(sCARRY + o0) = make_uint4(uo[0], uo[1], uo[2], uo[3]);
+                    *(uint4*)(sCARRY + o1) = make_uint4(uo[4], uo[5], uo[6], uo[7]);
+                }
                 const uint4 x0 = *(const uint4*)(sDXS + o0), x1 = *(const uint4*)(sDXS + o1);
                 const uint32_t xi[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                 const uint32_t yi[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                const uint4 zz = make_uint4(0, 0, 0, 0);    // pair input (audio only): the incoming U term of the pass-through
-                const uint4 y0 = PAIR_IN ? *(const uint4*)(sU + o0) : zz, y1 = PAIR_IN ? *(const uint4*)(sU + o1) : zz;
-                const uint32_t ui[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float2 xp = unpack_bf16(xi[i]), xq = unpack_bf16(ui[i]), xu = unpack_bf16(yi[i]);
-                    po[i] = pack_bf16(__uint_as_float(v[2 * i]) + ((xp.x + xq.x) + xu.x), __uint_as_float(v[2 * i + 1]) + ((xp.y + xq.y) + xu.y));
+                    const float2 xp = unpack_bf16(xi[i]), xu = unpack_bf16(yi[i]);
+                    po[i] = pack_bf16(__uint_as_float(v[2 * i]) + (xp.x + xu.x), __uint_as_float(v[2 * i + 1]) + (xp.y + xu.y));
                 }
+                asm volatile("bar.sync 1, %0;" ::"n"(N_WORKERS) : "memory");      // every shifted row has been read
+                *(uint4*)(sU + o0) = make_uint4(po[0], po[1], po[2], po[3]);
+                *(uint4*)(sU + o1) = make_uint4(po[4], po[5], po[6], po[7]);
+            } else {
+                mbar_wait(bar + W1, ph);            // W1 no longer reads the DZ tiles, nor the x/ctx tiles:
+                if (tid == 0 && has_next) {         // reload those for the next tile right away
+                    const int nt = tile + sq.step, nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
+                    mbar_expect_tx(bar + A_IN, (uint32_t)(nc * TILE_BYTES));
+                    tma_load_3d(sA, &map_x, bar + A_IN, 0, n0 - a.dil, nb);
+                    tma_load_3d(sA + TILE_BYTES, &map_x, bar + A_IN, 0, n0, nb);
+                    if (nc == 3) tma_load_3d(sA + 2 * TILE_BYTES, &map_ctx, bar + A_IN, 0, n0, nb);
+                }
+                CLKW(10);
+                *(uint4*)(sDZ + TILE_BYTES + o0) = make_uint4(uo[0], uo[1], uo[2], uo[3]);
+                *(uint4*)(sDZ + TILE_BYTES + o1) = make_uint4(uo[4], uo[5], uo[6], uo[7]);
+                *(uint4*)(sDZ + o0) = make_uint4(po[0], po[1], po[2], po[3]);
+                *(uint4*)(sDZ + o1) = make_uint4(po[4], po[5], po[6], po[7]);
             }
-            *(uint4*)(sDZ + o0) = make_uint4(po[0], po[1], po[2], po[3]);
-            *(uint4*)(sDZ + o1) = make_uint4(po[4], po[5], po[6], po[7]);
             fence_proxy_async();
             tc_fence_before();
             warp_arrive(bar + E_OUT);
@@ -630,7 +644,8 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     if ((rc = make_act_map(&mc, g.video ? ctx : x_in, g.B, g.T))) return rc;
     MVN_REQUIRE(p_in || !u_in, "tensor-core backward kernel: U without P");
     const int sum_out = u_out == nullptr;
-    MVN_REQUIRE(!sum_out || (g.dil[layer] <= TILE_T && !(g.video && u_in)), "tensor-core backward kernel: summed output needs dilation <= 128 (and, with video, a summed input)");
+    MVN_REQUIRE(!sum_out || (g.dil[layer] <= (g.video ? CARRY_VIDEO_ROWS : TILE_T) && !u_in),
+                "tensor-core backward kernel: summed output needs a small dilation and a summed (or zero) input");
     if ((rc = make_act_map(&mp, p_in ? p_in : x_in, g.B, g.T))) return rc;      // p_in == u_in == null: zero incoming gradient
     if ((rc = make_act_map(&mu, u_in ? u_in : x_in, g.B, g.T))) return rc;
     if ((rc = make_act_map(&mpo, p_out, g.B, g.T))) return rc;
@@ -651,12 +666,11 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
         MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_smem = smem;
     }
     int grid = 148;
     if (grid > a.n_tiles) grid = a.n_tiles;
-    auto kernel = sum_out ? (a.pair_in ? layer_bwd_tc_kernel<true, true> : layer_bwd_tc_kernel<true, false>)
+    auto kernel = sum_out ? layer_bwd_tc_kernel<true, false>       // (summed output takes a summed or zero input: checked above)
                           : (a.pair_in ? layer_bwd_tc_kernel<false, true> : layer_bwd_tc_kernel<false, false>);
     MVN_CUDA(mvn_launch_pdl(kernel, dim3(grid), dim3(N_THREADS), (size_t)smem, st, mx, mc, mp, mu, mpo, muo, mq, mqo, a));
     (void)lg;
@@ -680,17 +694,17 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     return mvn_check_launch("layer_bwd_tc");
 }
 
-// Opt-in (MOVENET_B200_BWD_SUM=1): layer l writes the summed stream when its dilation fits a tile and the carry has a home: with
-// video the carry lives in the U input tile, so the layer above must have written a summed stream too.  Default: the (P, U) pair
-// everywhere -- measured on one box with both variants compiled from the same templates, the summed stream moves 24 % fewer HBM
-// bytes but is 0..8 % SLOWER (147 vs 136 us per launch): the kernel is bound by its per-tile dependency chain, not by HBM, and the
-// warm-up tile per CTA run (+4 % tiles) and the extra worker barrier cost more than the lighter G2 / W2 save (profiles/r01_ablation.md).
+// Opt-in (MOVENET_B200_BWD_SUM=1): layer l writes the summed stream when its dilation fits the carry and the layer above wrote a
+// summed stream too (the U tile is the exchange / staging tile, so there is no pair input).  Default: the (P, U) pair everywhere --
+// measured on one box, the summed stream moves 24 % fewer HBM bytes and its tile period is the pair's (5.2 us), but every CTA run
+// pays one warm-up tile (26 -> 27 tile periods): 140 vs 137 us per launch.  The kernel is bound by the per-tile dependency chain
+// (W1 done -> x/ctx reload -> G1), not by HBM or MMA count (profiles/r01_ablation.md).
 int mvn_tc_bwd_sum_out(const Geo& g, int layer) {
     const char* sum = getenv("MOVENET_B200_BWD_SUM");      // read per call: the tests switch it
     if (!sum || !atoi(sum)) return 0;
     int above = 1;                                   // the top layer's input is zero
     for (int l = g.N - 1; l >= layer; --l) {
-        const int s = g.dil[l] <= TILE_T && (!g.video || above);
+        const int s = g.dil[l] <= (g.video ? CARRY_VIDEO_ROWS : TILE_T) && above;   // (the U tile is the staging tile: no pair input)
         if (l == layer) return s;
         above = s;
     }

@@ -251,14 +251,13 @@ def _grads_of(m, audio, video, target):
     return {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}
 
 
-@pytest.mark.parametrize("video,layer_size", [(False, 9), (True, 3), (True, 9)])
+@pytest.mark.parametrize("video,layer_size", [(False, 8), (False, 9), (True, 3), (True, 5), (True, 9)])
 def test_backward_gradient_stream_modes(video, layer_size, monkeypatch):
     """The residual-stream gradient between two layer kernels is the pair (P, U) by default; with MOVENET_B200_BWD_SUM=1 it
-    is ONE summed tensor when the producing layer's dilation is <= 128 (it adds its two terms itself, carrying d rows
-    from tile to tile).  Dilations
-    1..256 twice: summed, pair, and both hand-overs (pair in / summed out needs the separate carry tile: audio only; with
-    video the layers under a wide one stay on the pair).  Ragged T, several clips per CTA run, warm-up tiles.  Checked
-    against the exact fp32 mode; both variants of the same step must agree with each other."""
+    is ONE summed tensor when every dilation from the top layer down to the producing one is small enough for the d-row
+    carry (<= 128 audio-only, <= 32 with video).  layer_size 8 / 3 / 5: summed everywhere, carries of up to 128 / 4 / 16 rows;
+    layer_size 9: a 256 dilation on top, the whole stack stays on the pair.  Ragged T, several clips per CTA run, warm-up
+    tiles.  Checked against the exact fp32 mode; both variants of the same step must agree with each other."""
     torch.manual_seed(3)
     kw = dict(layer_size=layer_size, stack_size=2, input_channels=64, residual_channels=64, skip_channels=8)
     m32 = movenet_b200.WaveNet(**kw, compute_dtype="fp32").cuda()
