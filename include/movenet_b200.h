@@ -186,7 +186,9 @@ int mvn_decode_steps(const mvn_shape_t* s, const void* packed, void* state, cons
 /* Throughput mode of the cached decoder on tensor cores (bf16 operands and queues, fp32 accumulation): 128 clips
  * advance in lock-step as the rows of tcgen05 MMAs, weights resident in shared memory.  Available when
  * mvn_decode_tc_supported(shape) (no video, skip_channels == 8, residual_channels 16 or 32, input_channels <= 128:
- * the receptive-field configuration, experiments/04).  Same prefill contract as mvn_decode_prefill.
+ * power-of-two dilations: the receptive-field configuration, experiments/04).  Prefill as mvn_decode_prefill, plus the packed
+ * weights: the queues hold the activations minus the residual biases accumulated below each layer (the step kernel keeps a
+ * bias-free residual track).  t_start must be past every dilation (a prompt of at least receptive_fields columns).
  * out_codes_t is STEP-major (n_new, B) so a step's tokens are one coalesced store; forced (B, n_new) optionally
  * overrides the chosen token (teacher forcing, used by the parity tests to compare logits step by step). */
 int mvn_decode_tc_supported(const mvn_shape_t* s);
