@@ -287,7 +287,8 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     umma(tmem_u + W1_COL, desc_adv(mDZ, k * 2048), desc_adv(mA, k * 2048), iW1, acc0 | (k != 0));
-                    umma(tmem_u + B1_COL, desc_adv(mDZ, k * 2048), ones, iB, acc0 | (k != 0));
+                    if (nc == 3)     // the gate biases are the context convs': no such parameters without video
+                        umma(tmem_u + B1_COL, desc_adv(mDZ, k * 2048), ones, iB, acc0 | (k != 0));
                 }
             }
             umma_commit(bar + W1);
