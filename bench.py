@@ -295,7 +295,8 @@ def decode_bench(dev):
     RF = m.receptive_fields
     res = {}
     from movenet_b200.decode import fast_mode_available, prefill, run_steps, steps_into
-    for mode, clips, n_new in (("exact_f32", 1, 2000), ("exact_f32", 1184, 400), ("fast_bf16", 148 * 512, 400)):
+    # exact decoder: one warp per clip, 16 clips per CTA -> 148 x 16 clips fill the machine once; tensor-core decoder: 512 per CTA
+    for mode, clips, n_new in (("exact_f32", 1, 2000), ("exact_f32", 148 * 16, 400), ("fast_bf16", 148 * 512, 400)):
         fast = mode == "fast_bf16"
         if fast and not fast_mode_available(m, clips, RF):
             continue
