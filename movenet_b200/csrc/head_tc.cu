@@ -348,16 +348,15 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
         const int b = tile / a.tiles_per_clip, j = (tile - b * a.tiles_per_clip) * TILE_T + r;
         const bool live = j < a.Tn;
         {   // the next tile's probabilities / d(out) rows: towards L2 now (32 channel rows, one 128-byte line per warp each)
+            // (one instruction per warp: lane i asks for channel row n0 + i, each line covers the warp's 32 time steps)
             const int nt = tile + gridDim.x;
-            if (nt < a.n_tiles && (tid & 31) == 0) {
-                const int nb = nt / a.tiles_per_clip, nj = (nt - nb * a.tiles_per_clip) * TILE_T + r;
+            if (nt < a.n_tiles) {
+                const int nb = nt / a.tiles_per_clip, nj = (nt - nb * a.tiles_per_clip) * TILE_T + (r & ~31);
                 if (nj < a.Tn) {
-                    const size_t o = ((size_t)nb * A + n0) * a.Tn + nj;
-#pragma unroll 8
-                    for (int i = 0; i < 32; ++i) {
-                        if (!a.logits) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.probs + o + (size_t)i * a.Tn));
-                        if (a.dout) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dout + o + (size_t)i * a.Tn));
-                    }
+                    const size_t o = ((size_t)nb * A + n0 + (tid & 31)) * a.Tn + nj;
+                    // (Tn is not a multiple of 32: the 32 time steps straddle two 128-byte lines)
+                    if (!a.logits) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a.probs + o)); asm volatile("prefetch.global.L2 [%0];" ::"l"(a.probs + o + 31)); }
+                    if (a.dout) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dout + o)); asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dout + o + 31)); }
                 }
             }
         }
