@@ -135,7 +135,7 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int NZ = nc * CC;                        // columns of D4 / dWz^T
 
     if (tid == 0) {
-        for (int i = 0; i < N_BARS; ++i) mbar_init(bar + i, i >= E_DSK ? N_WORKERS / 32 : 1);
+        for (int i = 0; i < N_BARS; ++i) mbar_init(bar + i, i == E_DSK ? 4 : i > E_DSK ? N_WORKERS / 32 : 1);   // E_DSK: the four warps that write the tile
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t wbytes = (uint32_t)smem_a_off(nc, a.N2);
         mbar_expect_tx(bar + IMG, wbytes);
@@ -374,8 +374,10 @@ layer_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                         make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
                 }
             }
-            fence_proxy_async();
-            warp_arrive(bar + E_DSK);
+            if (half == 0) {       // (warp-uniform: only the four writing warps fence and signal)
+                fence_proxy_async();
+                warp_arrive(bar + E_DSK);
+            }
             CLKW(1); CLKM(1);
             // ---- epilogue 1a (needs G1 only): th, sg, gated -> G tile ---------------------------------
             float th[16], sg[16];
