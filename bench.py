@@ -268,11 +268,14 @@ def model_state_repeat(m, st, reps):
     shape = m._shape(B * reps, st.shape.frames, False, False, True, _lib.F32)
     bufs = m._buffers_for(shape, st.state.device)
     m._pack(bufs, m._param_list())
-    name = "mvn_decode_tc_state_bytes" if st.fast else "mvn_decode_state_bytes"
-    big = torch.zeros(_lib.size(name, shape), dtype=torch.uint8, device=st.state.device)
+    big = torch.zeros(_lib.size("mvn_decode_tc_state_bytes", shape) if st.fast else
+                      _lib.size("mvn_decode_state_bytes", shape, st.mode), dtype=torch.uint8, device=st.state.device)
     es = 2 if st.fast else 4
     Cc = m.residual_channels
-    dil = m.residual_conv_stack.dilations
+    dil = list(m.residual_conv_stack.dilations)
+    edge = (not st.fast) and st.mode == _lib.DECODE_REFERENCE and m.stack_size == 1
+    if edge:                                        # reference-window mode: rings reach back to the window edge (decode.cu)
+        dil = [max(d, sum(dil[l + 1:])) for l, d in enumerate(dil)]
     src_off = dst_off = 0
     for d in dil:                                   # per layer: (slot, clip, channel)
         n_src = d * B * Cc * es
@@ -283,76 +286,147 @@ def model_state_repeat(m, st, reps):
     src_l2 = a256(src_off); dst_l2 = a256(dst_off)
     l2 = st.state[src_l2:src_l2 + B * 8].view(B, 8)
     big[dst_l2:dst_l2 + B * reps * 8].view(reps, B, 8).copy_(l2.unsqueeze(0).expand(reps, B, 8))
-    return DecodeState(shape, bufs, big, None, B * reps, st.channels, fast=st.fast)
+    if edge:                                        # code ring [RF][clip]
+        RF = m.receptive_fields
+        src_c = src_l2 + a256(B * 8); dst_c = dst_l2 + a256(B * reps * 8)
+        ring = st.state[src_c:src_c + RF * B * 4].view(RF, B * 4)
+        big[dst_c:dst_c + RF * B * reps * 4].view(RF, reps, B * 4).copy_(ring.unsqueeze(1).expand(RF, reps, B * 4))
+    return DecodeState(shape, bufs, big, None, B * reps, st.channels, fast=st.fast, mode=st.mode)
 
 
-def decode_bench(dev):
-    """cached generation on the receptive-field config: RTF = generated seconds of 16 kHz audio per wall second"""
+def decode_bench(dev, rank=0, world=1):
+    """cached generation on the receptive-field config: RTF = generated seconds of 16 kHz audio per wall second.
+
+    world > 1: independent clips are sharded over the ranks (movenet_b200.parallel.shard_range) with NO communication in
+    the data path; every rank times its shard with CUDA events between barriers, the slowest rank's time
+    is the job's.  Only the throughput legs run there."""
+    import torch.distributed as dist
     import movenet_b200
+    from movenet_b200 import _lib
+    from movenet_b200.parallel import shard_range
     d = DECODE
     m = movenet_b200.WaveNet(d["layer_size"], d["stack_size"], d["input_channels"], d["residual_channels"],
                              d["skip_channels"], compute_dtype="fp32").to(dev)
+    if world > 1:
+        m.enable_data_parallel()            # same weights on every rank (rank 0's); no gradient traffic in decode
     RF = m.receptive_fields
+    N, Cc, A_ = m.layer_size * m.stack_size, d["residual_channels"], d["input_channels"]
     res = {}
     from movenet_b200.decode import fast_mode_available, prefill, run_steps, steps_into
-    # exact decoder: one warp per clip, 16 clips per CTA -> 148 x 16 clips fill the machine once; tensor-core decoder: 512 per CTA
-    for mode, clips, n_new in (("exact_f32", 1, 2000), ("exact_f32", 148 * 16, 400), ("fast_bf16", 148 * 512, 400)):
-        fast = mode == "fast_bf16"
+
+    def job_seconds(fn):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(); fn(); ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = t.item()
+        return ms * 1e-3
+
+    # exact decoders: one warp per clip, 16 clips per CTA -> 148 x 16 clips fill the machine once; tensor-core decoder: 512 per CTA.
+    # "reference_window": the default exact mode -- stack_size == 1 here, so the reference's window edge is evaluated too
+    # (about twice the arithmetic and deeper rings); "causal": the true causal model; "fast": tensor cores, bf16 queues.
+    legs = [("reference_window_f32", "exact", 1, 2000), ("reference_window_f32", "exact", 148 * 16, 400),
+            ("causal_f32", "causal", 148 * 16, 400), ("fast_bf16", "fast", 148 * 512, 400)]
+    if world > 1:
+        legs = [l for l in legs if l[2] > 1 and l[1] != "exact"]
+    for label, mode, clips_per_gpu, n_new in legs:
+        fast = mode == "fast"
+        lo, hi = shard_range(clips_per_gpu * world, rank, world)       # this rank's clips of the global batch
+        clips = hi - lo
         if fast and not fast_mode_available(m, clips, RF):
             continue
-        state = None
         per = min(clips, 2368)                      # build the prompt batch in slices: the one-hot prompt is large
-        codes = torch.randint(0, d["input_channels"], (per, RF), device=dev)
-        prompt = movenet_b200.one_hot(codes, d["input_channels"])
-        if clips > per:                             # big batch: prefill one slice and replicate its queues (timing only)
-            state = prefill(m, prompt, None, fast=fast)
-            reps = clips // per
-            big = model_state_repeat(m, state, reps)
-            state = big
-        else:
-            state = prefill(m, prompt, None, fast=fast)
-        run_steps(m, state, RF, 8)                                  # warm-up (re-running positions is harmless here)
+        codes = torch.randint(0, A_, (per, RF), device=dev, generator=torch.Generator(device=dev).manual_seed(100 + lo))
+        prompt = movenet_b200.one_hot(codes, A_)
+        state = prefill(m, prompt, None, fast=fast, mode="exact" if fast else mode)
+        slice_tokens = None
+        if clips > per:                             # big batch: prefill one slice and replicate its queues
+            pristine = state.state.clone()
+            slice_tokens = run_steps(m, state, RF, 8).clone()
+            state.state.copy_(pristine)
+            del pristine
+            state = model_state_repeat(m, state, clips // per)
         nclips = state.batch
-        A_ = d["input_channels"]
+        warm = run_steps(m, state, RF, 8)           # warm-up (re-running positions afterwards is harmless for timing)
+        replicas_ok = None
+        if slice_tokens is not None:                # every replica of the slice must emit the slice's own tokens
+            replicas_ok = bool((warm.reshape(clips // per, per, 8) == slice_tokens.unsqueeze(0)).all().item())
         e = 2 if fast else 4
-        queue_b = 2 * m.layer_size * m.stack_size * d["residual_channels"] * e      # pop + push per layer
-        # (a) the decode kernel alone: int32 codes out.  Bytes it moves per generated sample: the queue rows + one code.
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        run_steps(m, state, RF, n_new)
-        ev1.record()
-        torch.cuda.synchronize()
-        sec_k = ev0.elapsed_time(ev1) * 1e-3
+        edge = mode == "exact" and m.stack_size == 1
+        # bytes per generated sample: ring pop + push per layer (+ the edge tap of the reference-window mode)
+        queue_b = ((3 * (N - 1) + 1) if edge else 2 * N) * Cc * e
+        # (a) the decode kernel alone: int32 codes out
+        sec_k = job_seconds(lambda: run_steps(m, state, RF, n_new))
         # (b) the reference's output format: a zeroed (B, A, n_new) fp32 tensor with one 1.0 per generated sample
         # (movenet/wavenet.py:211-236) -- zero fill + steps + scatter, all inside the timed region.  SURVEY 8(d)'s
         # algorithmic bytes (queue rows + the 4A-byte one-hot column) are quoted on THIS region.
         out = torch.empty(nclips, A_, n_new, dtype=torch.float32, device=dev)
         out.zero_(); steps_into(m, state, RF, 8, out[:, :, :8])     # warm-up of the allocator / scatter kernels
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        out.zero_()
-        steps_into(m, state, RF, n_new, out)
-        ev1.record()
-        torch.cuda.synchronize()
-        sec = ev0.elapsed_time(ev1) * 1e-3
+
+        def onehot_region():
+            out.zero_()
+            steps_into(m, state, RF, n_new, out)
+        sec = job_seconds(onehot_region)
         del out
+        total = nclips * world                       # equal shards
         per_clip_rtf = (n_new / 16000.0) / sec
         bytes_per_sample = queue_b + 4 * A_
-        gbs = nclips * n_new * bytes_per_sample / sec / 1e9
+        gbs = nclips * n_new * bytes_per_sample / sec / 1e9           # per GPU
         gbs_k = nclips * n_new * (queue_b + 4) / sec_k / 1e9
-        res[f"{mode}_clips_{nclips}"] = {"new_samples_per_clip": n_new, "rtf_per_clip": per_clip_rtf,
-                                         "aggregate_samples_per_s": nclips * n_new / sec, "aggregate_rtf": nclips * per_clip_rtf,
-                                         "output": "one-hot (B, A, n) fp32, zero fill + scatter inside the timed region",
-                                         "bytes_per_sample": bytes_per_sample, "hbm_gbs_algorithmic": gbs,
-                                         "hbm_frac": gbs / peaks()["hbm_gbs"],
-                                         "kernel_only": {"aggregate_samples_per_s": nclips * n_new / sec_k,
-                                                         "rtf_per_clip": (n_new / 16000.0) / sec_k,
-                                                         "output": "int32 codes", "bytes_per_sample": queue_b + 4,
-                                                         "hbm_gbs": gbs_k, "hbm_frac": gbs_k / peaks()["hbm_gbs"]}}
+        res[f"{label}_clips_{total}"] = {
+            "decoder": {"exact": "fp32 CUDA cores, reference-window mode (token-exact vs the reference's generate)",
+                        "causal": "fp32 CUDA cores, true causal model",
+                        "fast": "tcgen05, bf16 queues, true causal model"}[mode],
+            "clips_total": total, "clips_per_gpu": nclips, "n_gpus": world, "new_samples_per_clip": n_new,
+            "rtf_per_clip": per_clip_rtf, "aggregate_samples_per_s": total * n_new / sec, "aggregate_rtf": total * per_clip_rtf,
+            "output": "one-hot (B, A, n) fp32, zero fill + scatter inside the timed region",
+            "bytes_per_sample": bytes_per_sample, "hbm_gbs_algorithmic_per_gpu": gbs, "hbm_frac": gbs / peaks()["hbm_gbs"],
+            "replicas_emit_the_slice_tokens": replicas_ok,
+            "kernel_only": {"aggregate_samples_per_s": total * n_new / sec_k, "rtf_per_clip": (n_new / 16000.0) / sec_k,
+                            "output": "int32 codes", "bytes_per_sample": queue_b + 4,
+                            "hbm_gbs_per_gpu": gbs_k, "hbm_frac": gbs_k / peaks()["hbm_gbs"]}}
         del state, prompt
-    return {"workload": d["name"], "receptive_fields": RF, "dtype": "f32", **res}
+        torch.cuda.empty_cache()
+    return {"workload": d["name"], "receptive_fields": RF, "dtype": "f32", "sharding": "clips over ranks, no communication",
+            **res}
+
+
+def dp_selfcheck(dev, rank, world):
+    """Data-parallel gradient averaging, checked where the driver records it (tests/test_gpu_dp.py needs >= 2 GPUs and is
+    skipped on the 1-GPU test box): every rank builds the model from a DIFFERENT seed (enable_data_parallel must hand out
+    rank 0's weights), runs its shard of one global batch, and the averaged gradients must (a) be bit-identical on all
+    ranks and (b) equal the gradients a single process computes on the whole batch (equal shards, mean loss)."""
+    import torch.distributed as dist
+    import movenet_b200
+    kw = dict(layer_size=2, stack_size=2, input_channels=32, residual_channels=16, skip_channels=8)
+    torch.manual_seed(1000 + rank)
+    m = movenet_b200.WaveNet(**kw, compute_dtype="fp32").to(dev).enable_data_parallel()
+    w0 = torch.cat([p.detach().flatten() for p in m.parameters()])
+    ref_w = w0.clone()
+    dist.broadcast(ref_w, src=0)
+    broadcast_ok = bool(torch.equal(w0, ref_w))
+    per = 2
+    codes = torch.randint(0, 32, (per * world, 300), generator=torch.Generator().manual_seed(1)).to(dev)
+    mine = codes[per * rank:per * (rank + 1)]
+    F.cross_entropy(m(mine), mine[:, m.receptive_fields:]).backward()
+    g_dp = torch.cat([p.grad.flatten() for p in m.parameters() if p.grad is not None])
+    lo, hi = g_dp.clone(), g_dp.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ranks_equal = bool(torch.equal(lo, hi))
+    single = movenet_b200.WaveNet(**kw, compute_dtype="fp32").to(dev)       # no data parallelism: the whole batch here
+    single.load_state_dict(m.state_dict())
+    F.cross_entropy(single(codes), codes[:, single.receptive_fields:]).backward()
+    g_one = torch.cat([p.grad.flatten() for p in single.parameters() if p.grad is not None])
+    err = ((g_dp - g_one).norm() / g_one.norm().clamp_min(1e-30)).item()
+    ok = broadcast_ok and ranks_equal and err < 1e-4
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return {"ok": bool(flag.item() == 1.0), "weights_broadcast_from_rank0": broadcast_ok, "gradients_equal_on_all_ranks": ranks_equal,
+            "rel_err_vs_single_process": err, "ranks": world}
 
 
 def run_ours(args):
@@ -483,8 +557,7 @@ def run_ours(args):
         post_loss(loss)
         state["i"] += 1
 
-    ms_e2e = max_over_ranks(timed_e2e(e2e_step, args.steps)) / args.steps
-    e2e_value = world * B * T_CLIP / (ms_e2e * 1e-3)
+    ms_onehot = max_over_ranks(timed_e2e(e2e_step, args.steps)) / args.steps
 
     # the same loop fed with the integer mu-law codes instead of their one-hot expansion (the non-breaking input
     # overload of forward()): 1/(4A) of the audio bytes cross PCIe
@@ -524,6 +597,24 @@ def run_ours(args):
     h2d = host_audio.numel() * 4 + (host_video.numel() * 4 if w["video"] else 0)
     clocks = sampler.stop()
 
+    # ---- sustained rate: the same device-resident step for >= 1000 steps (seconds, not milliseconds, under load) ----
+    sustained = None
+    if args.sustained_steps > 0:
+        s2 = ClockSampler(local)
+        s2.start()
+        ms_sus = max_over_ranks(timed(lambda: train_step(model, opt, audio, video), args.sustained_steps, 0, sync))
+        c2 = s2.stop()
+        sustained = {"steps": args.sustained_steps, "ms_per_step": ms_sus / args.sustained_steps,
+                     "value": world * B * T_CLIP / (ms_sus / args.sustained_steps * 1e-3), "unit": UNIT,
+                     "sm_mhz_median": c2["sm_mhz"], "sm_max_mhz": c2["sm_max_mhz"], "reasons": c2["reasons"],
+                     "clock_samples": c2.get("samples")}
+
+    # ---- N > 1: data-parallel self-check (recorded in the JSON line) and the sharded decode leg ----
+    dp_check = dp_selfcheck(dev, rank, world) if world > 1 else None
+    generation = None
+    if world > 1 and not args.no_decode:
+        generation = decode_bench(dev, rank, world)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -545,15 +636,25 @@ def run_ours(args):
                        "l2": "inputs and activations (>1 GB per step) exceed the 126 MB L2; no explicit flush"},
             "clocks": clocks, "gpu_launches": launches // max(1, args.steps) * args.steps,
             "gpu_launches_per_step": launches / max(1, args.steps),
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4,
+            # headline end-to-end number: the repo's own public API fed the way SURVEY 8(f).1 asks -- forward(codes), the
+            # integer mu-law codes (what the dataset produces before its one-hot expansion, movenet/dataset.py:284) instead of
+            # the 4A-times larger one-hot fp32 tensor
+            "e2e": {"value": world * B * T_CLIP / (ms_codes * 1e-3), "unit": UNIT, "ms_per_step": ms_codes,
+                    "h2d_bytes_per_step": B * T_CLIP * 8 + (host_video.numel() * 4 if w["video"] else 0),
+                    "d2h_bytes_per_step": 4, "input": "forward(codes): (B, T) int64 mu-law codes + (B,160,64,64,1) fp32 video",
                     "note": "inputs: pinned host -> device on a copy stream, one step ahead; loss: every step's value is copied "
                             "to pinned host memory asynchronously and read on the host one step later, all inside the timed region"},
-            "e2e_integer_codes": {"value": world * B * T_CLIP / (ms_codes * 1e-3), "unit": UNIT, "ms_per_step": ms_codes,
-                                  "h2d_bytes_per_step": B * T_CLIP * 8 + (host_video.numel() * 4 if w["video"] else 0),
-                                  "d2h_bytes_per_step": 4,
-                                  "note": "forward(codes) overload: int64 mu-law codes instead of the one-hot tensor"},
+            # the reference's own input format (one-hot fp32, 4A bytes per sample): host-DRAM / PCIe bound -- 130.7 MB per step
+            # and GPU, eight of them share one NUMA node's memory system at N = 8
+            "e2e_onehot": {"value": world * B * T_CLIP / (ms_onehot * 1e-3), "unit": UNIT, "ms_per_step": ms_onehot,
+                           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                           "input": "forward(one_hot): (B, A, T) fp32, the reference's format"},
+            "sustained": sustained,
             "roofline": roof, "roofline_layer_forward": roof_fwd}
+    if dp_check is not None:
+        line["dp_selfcheck"] = dp_check
+    if generation is not None:
+        line["generation"] = generation
     if world == 1:
         if not args.no_cpu_baseline:
             n, times = cpu_reference_steps(w, 2, 1, video=w["video"], B=1)
@@ -577,6 +678,8 @@ def main():
     ap.add_argument("--dtype", default=os.environ.get("MOVENET_B200_DTYPE", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--sustained-steps", type=int, default=1000,
+                    help="extra device-resident steps timed separately for the sustained rate (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -168,18 +168,35 @@ int mvn_layer_bwd(const mvn_shape_t* s, const void* packed, int layer, const voi
  * 2 upsampled context (B,T,C) */
 int mvn_debug_read(const mvn_shape_t* s, const void* acts, int which, int layer, float* dst, void* stream);
 
+/* byte offset of an internal activation inside the `acts` buffer: which = 0 layer input x_l (B,T,C) act dtype,
+ * 2 upsampled context (B,T,C) act dtype (has_video shapes only; what mvn_decode_steps takes as `ctx`) */
+size_t mvn_acts_offset(const mvn_shape_t* s, int which, int layer);
+
 /* cached autoregressive decoding: WaveNet.generate (movenet/wavenet.py:193-239)
  * with per-layer dilation queues instead of a window recompute per sample.
- * state: mvn_decode_state_bytes; prefill fills the queues from the activations
- * of a mvn_wavenet_forward over the prompt (shape.frames = prompt length);
+ * mode:
+ *   MVN_DECODE_REFERENCE  the reference's function exactly.  generate() evaluates an RF-long window per sample and
+ *       CausalConv1d zero-pads the window's left edge (movenet/modules.py:15-30); with stack_size == 1 that edge
+ *       reaches the output, so besides the queue update one extra "edge" column per layer is evaluated
+ *       per step from rings that hold each layer's inputs back to the window's left edge (decode.cu).  With
+ *       stack_size >= 2 the edge never reaches the output and this mode is identical to MVN_DECODE_CAUSAL.
+ *   MVN_DECODE_CAUSAL     the true causal model (d-deep rings only).
+ * state: mvn_decode_state_bytes; prefill fills the rings from the layer inputs of a forward pass over the prompt
+ * (`acts` of mvn_wavenet_forward, or of mvn_input_fwd + mvn_layer_fwd per layer; the prompt is the first
+ * prompt_frames <= shape.frames columns, 0 = all of them: with video the pass runs at 160000 frames);
  * steps generates n_new samples starting at absolute position t_start
  * and writes int32 codes (B, n_new) and optionally the logits (B, n_new, A).
+ * ctx: the upsampled context (B, frames, C) in act dtype for has_video shapes (acts + mvn_acts_offset(s, 2, 0)):
+ * column t-1 conditions the prediction of sample t, as in forward() -- the reference itself cannot run generate()
+ * with video, this is the window [i-RF, i) definition of oracle/wavenet_oracle.py.
  * temperature == 0: argmax, ties to the lowest index like torch.argmax;
  * temperature > 0: a draw from softmax(softmax(z)/temperature) (movenet/wavenet.py:227-231)
  * from a counter-based generator keyed by (seed, clip, position). */
-size_t mvn_decode_state_bytes(const mvn_shape_t* s);
-int mvn_decode_prefill(const mvn_shape_t* s, const void* acts, void* state, void* stream);
-int mvn_decode_steps(const mvn_shape_t* s, const void* packed, void* state, const void* ctx, int t_start,
+#define MVN_DECODE_CAUSAL 0
+#define MVN_DECODE_REFERENCE 1
+size_t mvn_decode_state_bytes(const mvn_shape_t* s, int mode);
+int mvn_decode_prefill(const mvn_shape_t* s, const void* acts, void* state, int mode, int prompt_frames, void* stream);
+int mvn_decode_steps(const mvn_shape_t* s, const void* packed, void* state, const void* ctx, int mode, int t_start,
                      int n_new, int* out_codes, float* out_logits, float temperature, unsigned seed,
                      void* stream);
 

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmovenet_b200.so")
 
 F32, BF16 = 0, 1
+DECODE_CAUSAL, DECODE_REFERENCE = 0, 1
 
 
 class Shape(C.Structure):
@@ -58,9 +59,10 @@ SIGNATURES = {
     "mvn_head_fwd": (_I, [_SP, _P, _P, _P, _P, _P]),
     "mvn_layer_bwd": (_I, [_SP, _P, _I, _P, _P, _P, _P]),
     "mvn_debug_read": (_I, [_SP, _P, _I, _I, _P, _P]),
-    "mvn_decode_state_bytes": (_SZ, [_SP]),
-    "mvn_decode_prefill": (_I, [_SP, _P, _P, _P]),
-    "mvn_decode_steps": (_I, [_SP, _P, _P, _P, _I, _I, _P, _P, C.c_float, C.c_uint, _P]),
+    "mvn_acts_offset": (_SZ, [_SP, _I, _I]),
+    "mvn_decode_state_bytes": (_SZ, [_SP, _I]),
+    "mvn_decode_prefill": (_I, [_SP, _P, _P, _I, _I, _P]),
+    "mvn_decode_steps": (_I, [_SP, _P, _P, _P, _I, _I, _I, _P, _P, C.c_float, C.c_uint, _P]),
     "mvn_decode_tc_supported": (_I, [_SP]),
     "mvn_decode_tc_state_bytes": (_SZ, [_SP]),
     "mvn_decode_tc_prefill": (_I, [_SP, _P, _P, _P, _P]),
@@ -68,6 +70,8 @@ SIGNATURES = {
 }
 
 _lib = None
+#: bumped by every writer that updates parameters through raw pointers (movenet_b200.optim.AdamW): WaveNet._pack compares it
+weights_epoch = [0]
 
 
 class MovenetB200Error(RuntimeError):
@@ -100,5 +104,5 @@ def call(name, *args):
         raise MovenetB200Error(f"{name} failed ({rc}): {lib.mvn_last_error().decode()}")
 
 
-def size(name, shape):
-    return int(getattr(load(), name)(C.byref(shape)))
+def size(name, shape, *args):
+    return int(getattr(load(), name)(C.byref(shape), *args))

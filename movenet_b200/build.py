@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libmovenet_b200.so")
-SOURCES = ["api.cu", "pack.cu", "wavenet.cu", "mulaw.cu", "decode.cu", "layer_tc.cu", "layer_tc_bwd.cu", "head_tc.cu", "input_tc.cu", "ce.cu", "decode_tc.cu", "upsample_tc.cu", "layer_tc_fwd2.cu", "optim.cu"]
+SOURCES = ["api.cu", "pack.cu", "wavenet.cu", "mulaw.cu", "decode.cu", "layer_tc.cu", "layer_tc_bwd.cu", "head_tc.cu", "input_tc.cu", "ce.cu", "decode_tc.cu", "upsample_tc.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 
@@ -26,8 +26,36 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def source_hash():
+    """sha256 over every source the library is built from (csrc/*, the public header, the compile flags)"""
+    import hashlib
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "movenet_b200.h")]
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS + SOURCES + [os.environ.get("MOVENET_B200_NVCC_EXTRA", "")]).encode())
+    return h.hexdigest()
+
+
+HASH_FILE = os.path.join(LIB_DIR, "SOURCE_HASH")
+
+
+def built_hash():
+    try:
+        with open(HASH_FILE) as fh:
+            return fh.read().strip()
+    except OSError:
+        return None
+
+
 def build(force=False, verbose=False):
-    if not force and not _stale():
+    """(Re)build when the library is missing, older than a source, or was built from different sources: the hash of the
+    sources a prebuilt .so came from is stored next to it and logged, so a stale shipped binary is detectable."""
+    want = source_hash()
+    if not force and not _stale() and built_hash() == want:
+        print(f"movenet_b200.build: up to date (sources sha256 {want[:16]})", file=sys.stderr)
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIB_DIR, exist_ok=True)
@@ -52,6 +80,9 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"]
     subprocess.run(cmd, check=True)
+    with open(HASH_FILE, "w") as fh:
+        fh.write(want + "\n")
+    print(f"movenet_b200.build: compiled {len(SOURCES)} sources for sm_100a (sources sha256 {want[:16]})", file=sys.stderr)
     return LIB
 
 

@@ -12,10 +12,23 @@ void mvn_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-static unsigned long long g_launches = 0;
+#include <atomic>
+static std::atomic<unsigned long long> g_launches{0};
+
+int mvn_sm_count() {
+    static std::atomic<int> cache[MVN_MAX_DEVICES];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MVN_MAX_DEVICES) return 148;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 
 int mvn_check_launch(const char* what) {
-    ++g_launches;
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         mvn_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -25,5 +38,5 @@ int mvn_check_launch(const char* what) {
 }
 
 extern "C" const char* mvn_last_error(void) { return g_err; }
-extern "C" int mvn_version(void) { return 100; }
-extern "C" unsigned long long mvn_launch_count(void) { return g_launches; }
+extern "C" int mvn_version(void) { return 200; }
+extern "C" unsigned long long mvn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

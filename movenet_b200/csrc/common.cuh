@@ -64,3 +64,20 @@ __device__ __forceinline__ float mvn_lrelu_grad(float pre) { return pre > 0.f ? 
 __device__ __forceinline__ float mvn_sigmoid(float v) { return 1.f / (1.f + expf(-v)); }
 
 static inline int mvn_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a function: remember what was set per device so
+// a process that drives several GPUs opts every one of them in (`slot` is a zero-initialised static of the call site).
+#define MVN_MAX_DEVICES 64
+struct MvnSmemAttr { int set[MVN_MAX_DEVICES]; };
+template <typename F>
+inline cudaError_t mvn_ensure_smem(F func, int bytes, MvnSmemAttr& slot) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < MVN_MAX_DEVICES && slot.set[dev] >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < MVN_MAX_DEVICES) slot.set[dev] = bytes;   // (a racing thread sets the same value)
+    return e;
+}
+// SMs of the current device (persistent grids are sized from it); cached per device
+int mvn_sm_count();

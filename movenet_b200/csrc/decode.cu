@@ -19,7 +19,33 @@ struct DecodeArgs {
     int* out_codes; float* out_logits;
     long long qoff[MVN_MAX_LAYERS];      // element offset of layer l's ring (per clip), before the *B factor
     int dil[MVN_MAX_LAYERS];
+    // reference-window mode (stack_size == 1): see the comment above decode_edge_geometry
+    int edge, RF;
+    int hist[MVN_MAX_LAYERS];            // ring depth of layer l (== dil[l] without the edge chain)
+    int age[MVN_MAX_LAYERS];             // the edge chain reads x_l[tau - age[l]]
+    int* code_ring;                      // [RF][B] : code at absolute position p lives in slot p % RF
 };
+
+// The reference's generate() (movenet/wavenet.py:217-224) evaluates a window of exactly RF samples per step and
+// CausalConv1d zero-pads the window's left edge (movenet/modules.py:15-30), so the leftmost column of the window's h0
+// lacks its W[:,:,0] x[i-RF-1] term.  Every layer drops d columns on the left (movenet/modules.py:36-46), so exactly ONE
+// column per layer -- the leftmost one, at absolute position p_l = tau - sum_{k>l} d_k (tau = i - 1) -- descends from
+// that perturbed column.  With stack_size >= 2 it is cut off before the output; with stack_size == 1 the last layer's
+// only column IS the leftmost one.  The skip outputs of layers 0..N-2 at tau are unaffected (movenet/modules.py:90-91
+// keeps the last column).  Reference-exact decoding therefore = the ordinary queue update, plus the "edge chain"
+//     e_0     = W[:,:,1] x[i-RF]
+//     e_{l+1} = Wr_l gate(Wz0_l e_l + Wz1_l x_l[p_l] (+ V_l ctx[p_l])) + br_l + x_l[p_l]           l = 0 .. N-2
+//     logits  = head( sum_{l<N-1} skip_l[tau] + Ws gate(Wz0 e_{N-1} + Wz1 x_{N-1}[tau] (+ V ctx[tau])) + bs )
+// which needs the TRUE layer inputs x_l at age sum_{k>l} d_k: rings of depth max(d_l, age_l) instead of d_l.
+static void decode_edge_geometry(const Geo& g, int mode, int* edge, int* hist, int* age) {
+    *edge = (mode == MVN_DECODE_REFERENCE && g.St == 1) ? 1 : 0;
+    long long above = 0;
+    for (int l = g.N - 1; l >= 0; --l) {
+        age[l] = (int)above;
+        hist[l] = (*edge && above > g.dil[l]) ? (int)above : g.dil[l];
+        above += g.dil[l];
+    }
+}
 
 // out[cb][n] = bias[n] + sum_k W[k][n] * in[cb][k]   for every (cb, n) pair, spread over the CTA
 template <int CB>
@@ -55,7 +81,9 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs a) {
     float* skip = rs + CB * (C + S);     // [CB][S]
     float* a1 = skip + CB * S;           // [CB][A]
     float* zl = a1 + CB * A;             // [CB][A]
-    float* wsm = zl + CB * A;            // staged weights (optional)
+    float* ev = zl + CB * A;             // [CB][C]    edge chain e_l (reference-window mode)
+    float* xes = ev + (a.edge ? CB * C : 0);            // [N][CB][C] edge taps x_l[tau - age_l]
+    float* wsm = xes + (a.edge ? (size_t)N * CB * C : 0);   // staged weights (optional)
     __shared__ int code_prev[CB], code_cur[CB];
 
     const size_t lsz = (size_t)Kz * 2 * C + 2 * C + (size_t)C * (C + S) + (C + S);   // staged floats per layer
@@ -103,11 +131,18 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs a) {
         // all queue pops of this step: their addresses depend on tau only
         for (int idx = threadIdx.x; idx < N * CB * C; idx += blockDim.x) {
             const int l = idx / (CB * C), r = idx - l * CB * C, cb = r / C, c = r - cb * C;
-            const int d = a.dil[l], b = clip0 + cb;
+            const int d = a.dil[l], H = a.hist[l], b = clip0 + cb;
+            const float* ring = a.queues + a.qoff[l] * a.B;
             float v = 0.f;
-            if (b < a.B && tau - d >= 0) v = a.queues[a.qoff[l] * a.B + ((size_t)(tau % d) * a.B + b) * C + c];
+            if (b < a.B && tau - d >= 0) v = ring[((size_t)((tau - d) % H) * a.B + b) * C + c];
             olds[idx] = v;
+            if (a.edge && l < N - 1) xes[idx] = b < a.B ? ring[((size_t)((tau - a.age[l]) % H) * a.B + b) * C + c] : 0.f;
         }
+        if (a.edge)      // e_0 = W[:,:,1] x[i - RF]: the window's first column without its zero-padded left neighbour
+            for (int idx = threadIdx.x; idx < CB * C; idx += blockDim.x) {
+                const int cb = idx / C, c = idx - cb * C, b = clip0 + cb;
+                ev[idx] = b < a.B ? win[((size_t)A + a.code_ring[(size_t)(i % a.RF) * a.B + b]) * C + c] : 0.f;
+            }
         __syncthreads();
         for (int l = 0; l < N; ++l) {
             const float* lw = a.packed + a.P.layer0 + (size_t)l * a.P.layer_stride;
@@ -115,32 +150,44 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs a) {
             if (a.smem_weights) {
                 Wz = wsm + l * lsz; bz = Wz + Kz * 2 * C; Wrs = bz + 2 * C; brs = Wrs + C * (C + S);
             } else { Wz = lw + a.P.oWz; bz = lw + a.P.obz; Wrs = lw + a.P.oWrs; brs = lw + a.P.obrs; }
-            const int d = a.dil[l];
-            // gather [x_l[tau-d] | x_l[tau] | ctx[tau]] and push x_l[tau] into the ring
-            for (int idx = threadIdx.x; idx < CB * C; idx += blockDim.x) {
-                const int cb = idx / C, c = idx - cb * C, b = clip0 + cb;
-                const float hv = h[idx];
-                zin[cb * Kz + c] = olds[(l * CB + cb) * C + c];
-                zin[cb * Kz + C + c] = hv;
-                if (a.video) zin[cb * Kz + 2 * C + c] = (b < a.B && tau >= 0 && tau < a.Tctx)
-                    ? mvn_ld(a.ctx, a.ctx_dtype, ((size_t)b * a.Tctx + tau) * C + c) : 0.f;
-                if (b < a.B && tau >= 0) a.queues[a.qoff[l] * a.B + ((size_t)(tau % d) * a.B + b) * C + c] = hv;
+            const int H = a.hist[l];
+            const bool top = l == N - 1;
+            if (a.edge && top)     // the last layer's edge tap is its current input
+                for (int idx = threadIdx.x; idx < CB * C; idx += blockDim.x) xes[(size_t)l * CB * C + idx] = h[idx];
+            // pass 0: the ordinary update at time tau (in reference-window mode the last layer's own outputs are not used);
+            // pass 1: the edge column of this layer (reference-window mode only)
+            for (int pass = 0; pass < (a.edge ? 2 : 1); ++pass) {
+                const bool edge_pass = pass == 1;
+                const int tq = edge_pass ? tau - a.age[l] : tau;           // absolute time of the column being evaluated
+                // gather [older tap | x_l[tq] | ctx[tq]]; pass 0 pushes x_l[tau] into the ring
+                for (int idx = threadIdx.x; idx < CB * C; idx += blockDim.x) {
+                    const int cb = idx / C, c = idx - cb * C, b = clip0 + cb;
+                    const float hv = edge_pass ? xes[(size_t)l * CB * C + idx] : h[idx];
+                    zin[cb * Kz + c] = edge_pass ? ev[idx] : olds[(l * CB + cb) * C + c];
+                    zin[cb * Kz + C + c] = hv;
+                    if (a.video) zin[cb * Kz + 2 * C + c] = (b < a.B && tq >= 0 && tq < a.Tctx)
+                        ? mvn_ld(a.ctx, a.ctx_dtype, ((size_t)b * a.Tctx + tq) * C + c) : 0.f;
+                    if (!edge_pass && b < a.B && tau >= 0) a.queues[a.qoff[l] * a.B + ((size_t)(tau % H) * a.B + b) * C + c] = hv;
+                }
+                if (!edge_pass && a.edge && top) continue;                  // (block-uniform)
+                __syncthreads();
+                matvec<CB>(Wz, 2 * C, Kz, 2 * C, zin, Kz, bz, zb, 2 * C, false, false);
+                __syncthreads();
+                for (int idx = threadIdx.x; idx < CB * C; idx += blockDim.x) {
+                    const int cb = idx / C, c = idx - cb * C;
+                    gated[idx] = tanhf(zb[cb * 2 * C + 2 * c]) * mvn_sigmoid(zb[cb * 2 * C + 2 * c + 1]);
+                }
+                __syncthreads();
+                matvec<CB>(Wrs, C + S, C, C + S, gated, C, brs, rs, C + S, false, false);
+                __syncthreads();
+                for (int idx = threadIdx.x; idx < CB * (C + S); idx += blockDim.x) {
+                    const int cb = idx / (C + S), n = idx - cb * (C + S);
+                    if (!edge_pass) { if (n < C) h[cb * C + n] += rs[idx]; else skip[cb * S + n - C] += rs[idx]; }
+                    else if (n < C) ev[cb * C + n] = rs[idx] + xes[((size_t)l * CB + cb) * C + n];
+                    else if (top) skip[cb * S + n - C] += rs[idx];
+                }
+                __syncthreads();
             }
-            __syncthreads();
-            matvec<CB>(Wz, 2 * C, Kz, 2 * C, zin, Kz, bz, zb, 2 * C, false, false);
-            __syncthreads();
-            for (int idx = threadIdx.x; idx < CB * C; idx += blockDim.x) {
-                const int cb = idx / C, c = idx - cb * C;
-                gated[idx] = tanhf(zb[cb * 2 * C + 2 * c]) * mvn_sigmoid(zb[cb * 2 * C + 2 * c + 1]);
-            }
-            __syncthreads();
-            matvec<CB>(Wrs, C + S, C, C + S, gated, C, brs, rs, C + S, false, false);
-            __syncthreads();
-            for (int idx = threadIdx.x; idx < CB * (C + S); idx += blockDim.x) {
-                const int cb = idx / (C + S), n = idx - cb * (C + S);
-                if (n < C) h[cb * C + n] += rs[idx]; else skip[cb * S + n - C] += rs[idx];
-            }
-            __syncthreads();
         }
         // dense head (movenet/modules.py:133-142)
         const float *W1, *b1, *W2, *b2;
@@ -202,6 +249,7 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs a) {
             if (lane == 0) {
                 code_prev[cb] = code_cur[cb]; code_cur[cb] = arg;
                 if (b < a.B) a.out_codes[(size_t)b * a.n_new + (i - a.t_start)] = arg;
+                if (a.edge && b < a.B) a.code_ring[(size_t)(i % a.RF) * a.B + b] = arg;
             }
         }
         __syncthreads();
@@ -231,11 +279,12 @@ __global__ void __launch_bounds__(32 * DW_WARPS, 1) decode_warp_kernel(const Dec
     float* hd = wsm + N * lsz;
     float* win = hd + (size_t)S * A + A + (size_t)A * A + A;
     float* scratch = win + (size_t)2 * A * C;
-    const int per_warp = 2 * C + C + 32 + A;            // in | gated | skip (padded) | a1
+    const int per_warp = 2 * C + C + 32 + A + 2 * C;    // in | gated | skip (padded) | a1 | edge chain [e_l | x_l[p_l]]
     float* in_s = scratch + (size_t)warp * per_warp;
     float* gated_s = in_s + 2 * C;
     float* skip_s = gated_s + C;
     float* a1_s = skip_s + 32;
+    float* ein_s = a1_s + A;
     for (int l = 0; l < N; ++l) {
         const float* lw = a.packed + a.P.layer0 + (size_t)l * a.P.layer_stride;
         float* dst = wsm + l * lsz;
@@ -273,41 +322,54 @@ __global__ void __launch_bounds__(32 * DW_WARPS, 1) decode_warp_kernel(const Dec
             in_s[C + c] = v;
         }
         skip_s[lane] = 0.f;
+        if (a.edge) {     // e_0 = W[:,:,1] x[i - RF] (see decode_edge_geometry)
+            const int ce = a.code_ring[(size_t)(i % a.RF) * a.B + b];
+            for (int c = lane; c < C; c += 32) ein_s[c] = win[((size_t)A + ce) * C + c];
+        }
         for (int l = 0; l < N; ++l) {
             const float* Wz = wsm + l * lsz; const float* bz = Wz + Kz * 2 * C; const float* Wrs = bz + 2 * C; const float* brs = Wrs + C * (C + S);
-            const int d = a.dil[l];
+            const int d = a.dil[l], H = a.hist[l];
+            const bool top = l == N - 1;
             __syncwarp();
-            for (int c = lane; c < C; c += 32) {         // queue pop / push
-                float* slot = a.queues + a.qoff[l] * a.B + ((size_t)(tau % d) * a.B + b) * C + c;
-                in_s[c] = tau - d >= 0 ? *slot : 0.f;
-                *slot = in_s[C + c];
+            for (int c = lane; c < C; c += 32) {         // queue pop / push (reads before the write: the slots may coincide)
+                float* ring = a.queues + a.qoff[l] * a.B;
+                in_s[c] = tau - d >= 0 ? ring[((size_t)((tau - d) % H) * a.B + b) * C + c] : 0.f;
+                if (a.edge) ein_s[C + c] = top ? in_s[C + c] : ring[((size_t)((tau - a.age[l]) % H) * a.B + b) * C + c];
+                ring[((size_t)(tau % H) * a.B + b) * C + c] = in_s[C + c];
             }
-            __syncwarp();
+            // pass 0: the ordinary update at time tau (not needed for the last layer in reference-window mode);
+            // pass 1: this layer's edge column
+            for (int pass = (a.edge && top) ? 1 : 0; pass < (a.edge ? 2 : 1); ++pass) {
+                const float* zin = pass ? ein_s : in_s;
+                __syncwarp();
 #pragma unroll
-            for (int o = 0; o < NZ; ++o) {
-                const int n = 32 * o + lane;
-                float acc0 = bz[n], acc1 = 0.f;
+                for (int o = 0; o < NZ; ++o) {
+                    const int n = 32 * o + lane;
+                    float acc0 = bz[n], acc1 = 0.f;
 #pragma unroll 8
-                for (int k = 0; k < Kz; k += 4) {
-                    const float4 x = *(const float4*)(in_s + k);
-                    acc0 = fmaf(Wz[(k + 0) * 2 * C + n], x.x, acc0); acc1 = fmaf(Wz[(k + 1) * 2 * C + n], x.y, acc1);
-                    acc0 = fmaf(Wz[(k + 2) * 2 * C + n], x.z, acc0); acc1 = fmaf(Wz[(k + 3) * 2 * C + n], x.w, acc1);
+                    for (int k = 0; k < Kz; k += 4) {
+                        const float4 x = *(const float4*)(zin + k);
+                        acc0 = fmaf(Wz[(k + 0) * 2 * C + n], x.x, acc0); acc1 = fmaf(Wz[(k + 1) * 2 * C + n], x.y, acc1);
+                        acc0 = fmaf(Wz[(k + 2) * 2 * C + n], x.z, acc0); acc1 = fmaf(Wz[(k + 3) * 2 * C + n], x.w, acc1);
+                    }
+                    const float z = acc0 + acc1;
+                    const float partner = __shfl_xor_sync(0xffffffffu, z, 1);    // columns interleave (filter c, gate c)
+                    if (!(lane & 1)) gated_s[n >> 1] = tanhf(z) * mvn_sigmoid(partner);
                 }
-                const float z = acc0 + acc1;
-                const float partner = __shfl_xor_sync(0xffffffffu, z, 1);    // columns interleave (filter c, gate c)
-                if (!(lane & 1)) gated_s[n >> 1] = tanhf(z) * mvn_sigmoid(partner);
-            }
-            __syncwarp();
-            for (int n = lane; n < C + S; n += 32) {
-                float acc0 = brs[n], acc1 = 0.f;
+                __syncwarp();
+                for (int n = lane; n < C + S; n += 32) {
+                    float acc0 = brs[n], acc1 = 0.f;
 #pragma unroll 4
-                for (int k = 0; k < C; k += 4) {
-                    const float4 x = *(const float4*)(gated_s + k);
-                    acc0 = fmaf(Wrs[(k + 0) * (C + S) + n], x.x, acc0); acc1 = fmaf(Wrs[(k + 1) * (C + S) + n], x.y, acc1);
-                    acc0 = fmaf(Wrs[(k + 2) * (C + S) + n], x.z, acc0); acc1 = fmaf(Wrs[(k + 3) * (C + S) + n], x.w, acc1);
+                    for (int k = 0; k < C; k += 4) {
+                        const float4 x = *(const float4*)(gated_s + k);
+                        acc0 = fmaf(Wrs[(k + 0) * (C + S) + n], x.x, acc0); acc1 = fmaf(Wrs[(k + 1) * (C + S) + n], x.y, acc1);
+                        acc0 = fmaf(Wrs[(k + 2) * (C + S) + n], x.z, acc0); acc1 = fmaf(Wrs[(k + 3) * (C + S) + n], x.w, acc1);
+                    }
+                    const float v = acc0 + acc1;
+                    if (!pass) { if (n < C) in_s[C + n] += v; else skip_s[n - C] += v; }
+                    else if (n < C) ein_s[n] = v + ein_s[C + n];
+                    else if (top) skip_s[n - C] += v;
                 }
-                const float v = acc0 + acc1;
-                if (n < C) in_s[C + n] += v; else skip_s[n - C] += v;
             }
         }
         __syncwarp();
@@ -370,7 +432,10 @@ __global__ void __launch_bounds__(32 * DW_WARPS, 1) decode_warp_kernel(const Dec
             arg = chosen;
         }
         code_prev = code_cur; code_cur = arg;
-        if (lane == 0) a.out_codes[(size_t)b * a.n_new + (i - a.t_start)] = arg;
+        if (lane == 0) {
+            a.out_codes[(size_t)b * a.n_new + (i - a.t_start)] = arg;
+            if (a.edge) a.code_ring[(size_t)(i % a.RF) * a.B + b] = arg;
+        }
     }
     if (lane == 0) { a.last2[2 * b] = code_prev; a.last2[2 * b + 1] = code_cur; }
 }
@@ -379,7 +444,7 @@ template <int C>
 static int launch_decode_warp(DecodeArgs& a, const Geo& g, cudaStream_t st, bool* used) {
     const size_t lsz = (size_t)2 * C * 2 * C + 2 * C + (size_t)C * (C + g.S) + (C + g.S);
     const size_t w_floats = g.N * lsz + (size_t)g.S * g.A + g.A + (size_t)g.A * g.A + g.A + (size_t)2 * g.A * C;
-    const size_t per_warp = 2 * C + C + 32 + g.A;
+    const size_t per_warp = 2 * C + C + 32 + g.A + 2 * C;
     const size_t smem = (w_floats + DW_WARPS * per_warp) * 4;
     *used = false;
     if (smem > 220 * 1024 || g.S > 32 || g.A > 256 || g.A % 4) return 0;
@@ -392,10 +457,11 @@ static int launch_decode_warp(DecodeArgs& a, const Geo& g, cudaStream_t st, bool
 // Fill the rings from the layer inputs of a forward pass over the T-column prompt.  The first decode
 // step re-evaluates time T-1 (the last prompt sample) itself, so the rings must hold the d inputs
 // BEFORE it: ring_l[tau % d] = x_l[tau] for tau in [T-1-d, T-1).
-__global__ void decode_prefill_kernel(const void* __restrict__ x, int adt, int B, int T, int C, int d,
+// (d = the ring depth; Tp = prompt length, T = row stride of x in time steps)
+__global__ void decode_prefill_kernel(const void* __restrict__ x, int adt, int B, int T, int Tp, int C, int d,
                                       float* __restrict__ ring) {
     const long long n = (long long)B * d * C;
-    const int Tend = T - 1;
+    const int Tend = Tp - 1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % C); const long long r = i / C; const int b = (int)(r % B); const int slot = (int)(r / B);
         int tau = (Tend / d) * d + slot; if (tau >= Tend) tau -= d;     // the time in [Tend-d, Tend) living in this slot
@@ -403,47 +469,71 @@ __global__ void decode_prefill_kernel(const void* __restrict__ x, int adt, int B
     }
 }
 
-__global__ void decode_last2_kernel(const int* __restrict__ codes, int B, int T, int* __restrict__ last2) {
+__global__ void decode_last2_kernel(const int* __restrict__ codes, int B, int T, int Tp, int* __restrict__ last2) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    last2[2 * b] = T >= 2 ? codes[(size_t)b * T + T - 2] : -1;
-    last2[2 * b + 1] = T >= 1 ? codes[(size_t)b * T + T - 1] : -1;
+    last2[2 * b] = Tp >= 2 ? codes[(size_t)b * T + Tp - 2] : -1;
+    last2[2 * b + 1] = Tp >= 1 ? codes[(size_t)b * T + Tp - 1] : -1;
+}
+// code_ring[p % RF][b] = codes[b][p] for the last RF prompt positions
+__global__ void decode_code_ring_kernel(const int* __restrict__ codes, int B, int T, int Tp, int RF, int* __restrict__ code_ring) {
+    const long long n = (long long)B * RF;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i % B), p = Tp - RF + (int)(i / B);
+        code_ring[(size_t)(p % RF) * B + b] = codes[(size_t)b * T + p];
+    }
 }
 
-static size_t queue_floats(const Geo& g, long long* qoff) {
+static size_t queue_floats(const Geo& g, const int* hist, long long* qoff) {
     long long o = 0;
-    for (int l = 0; l < g.N; ++l) { if (qoff) qoff[l] = o; o += (long long)g.dil[l] * g.C; }
+    for (int l = 0; l < g.N; ++l) { if (qoff) qoff[l] = o; o += (long long)hist[l] * g.C; }
     return (size_t)o;
 }
 
-extern "C" size_t mvn_decode_state_bytes(const mvn_shape_t* s) {
+extern "C" size_t mvn_decode_state_bytes(const mvn_shape_t* s, int mode) {
     Geo g; if (geo_init(g, s)) return 0;
-    return al256(queue_floats(g, nullptr) * (size_t)g.B * 4) + al256((size_t)g.B * 2 * 4);
+    int edge, hist[MVN_MAX_LAYERS], age[MVN_MAX_LAYERS];
+    decode_edge_geometry(g, mode, &edge, hist, age);
+    return al256(queue_floats(g, hist, nullptr) * (size_t)g.B * 4) + al256((size_t)g.B * 2 * 4) +
+           (edge ? al256((size_t)g.RF * g.B * 4) : 0);
 }
 
-extern "C" int mvn_decode_prefill(const mvn_shape_t* s, const void* acts, void* state, void* stream) {
+extern "C" int mvn_decode_prefill(const mvn_shape_t* s, const void* acts, void* state, int mode, int prompt_frames,
+                                  void* stream) {
     Geo g; MVN_REQUIRE(s && geo_init(g, s) == 0, "mvn_decode_prefill: bad shape");
     MVN_REQUIRE(acts && state, "mvn_decode_prefill: null buffer");
+    const int Tp = prompt_frames > 0 ? prompt_frames : g.T;
+    MVN_REQUIRE(Tp <= g.T, "mvn_decode_prefill: prompt_frames (%d) exceeds the forward pass's frames (%d)", Tp, g.T);
+    int edge, hist[MVN_MAX_LAYERS], age[MVN_MAX_LAYERS];
+    decode_edge_geometry(g, mode, &edge, hist, age);
+    MVN_REQUIRE(!edge || Tp >= g.RF, "mvn_decode_prefill: the reference-window mode needs a prompt of at least receptive_fields (%d) columns", g.RF);
     ActsLayout AL; acts_layout(g, AL);
     long long qoff[MVN_MAX_LAYERS];
-    const size_t qf = queue_floats(g, qoff);
+    const size_t qf = queue_floats(g, hist, qoff);
     float* queues = (float*)state;
     int* last2 = (int*)((char*)state + al256(qf * (size_t)g.B * 4));
     cudaStream_t st = (cudaStream_t)stream;
     for (int l = 0; l < g.N; ++l) {
         const void* x = (const char*)acts + AL.x0 + (size_t)l * AL.x_stride;
-        const long long n = (long long)g.B * g.dil[l] * g.C;
+        const long long n = (long long)g.B * hist[l] * g.C;
         decode_prefill_kernel<<<mvn_cdiv(n, 256) < 1184 ? mvn_cdiv(n, 256) : 1184, 256, 0, st>>>(
-            x, g.adt, g.B, g.T, g.C, g.dil[l], queues + qoff[l] * g.B);
+            x, g.adt, g.B, g.T, Tp, g.C, hist[l], queues + qoff[l] * g.B);
     }
-    decode_last2_kernel<<<mvn_cdiv(g.B, 128), 128, 0, st>>>((const int*)((const char*)acts + AL.codes), g.B, g.T, last2);
+    const int* codes = (const int*)((const char*)acts + AL.codes);
+    decode_last2_kernel<<<mvn_cdiv(g.B, 128), 128, 0, st>>>(codes, g.B, g.T, Tp, last2);
+    if (edge) {
+        int* code_ring = last2 + al256((size_t)g.B * 2 * 4) / 4;
+        const long long n = (long long)g.B * g.RF;
+        decode_code_ring_kernel<<<mvn_cdiv(n, 256) < 1184 ? mvn_cdiv(n, 256) : 1184, 256, 0, st>>>(codes, g.B, g.T, Tp, g.RF, code_ring);
+    }
     return mvn_check_launch("decode_prefill");
 }
 
 template <int CB>
 static int launch_decode(DecodeArgs& a, const Geo& g, cudaStream_t st) {
     const size_t act_floats = (size_t)CB * g.C + (size_t)g.N * CB * g.C + (size_t)CB * g.Kz + (size_t)CB * 2 * g.C +
-                              (size_t)CB * g.C + (size_t)CB * (g.C + g.S) + (size_t)CB * g.S + 2 * (size_t)CB * g.A;
+                              (size_t)CB * g.C + (size_t)CB * (g.C + g.S) + (size_t)CB * g.S + 2 * (size_t)CB * g.A +
+                              (a.edge ? (size_t)CB * g.C + (size_t)g.N * CB * g.C : 0);
     const size_t lsz = (size_t)g.Kz * 2 * g.C + 2 * g.C + (size_t)g.C * (g.C + g.S) + (g.C + g.S);
     const size_t w_floats = g.N * lsz + (size_t)g.S * g.A + g.A + (size_t)g.A * g.A + g.A;
     const size_t cap = 220 * 1024;
@@ -455,9 +545,9 @@ static int launch_decode(DecodeArgs& a, const Geo& g, cudaStream_t st) {
     return mvn_check_launch("decode_steps");
 }
 
-extern "C" int mvn_decode_steps(const mvn_shape_t* s, const void* packed, void* state, const void* ctx, int t_start,
-                                int n_new, int* out_codes, float* out_logits, float temperature, unsigned seed,
-                                void* stream) {
+extern "C" int mvn_decode_steps(const mvn_shape_t* s, const void* packed, void* state, const void* ctx, int mode,
+                                int t_start, int n_new, int* out_codes, float* out_logits, float temperature,
+                                unsigned seed, void* stream) {
     Geo g; MVN_REQUIRE(s && geo_init(g, s) == 0, "mvn_decode_steps: bad shape");
     MVN_REQUIRE(packed && state && out_codes && n_new >= 0 && t_start >= 1, "mvn_decode_steps: bad arguments");
     MVN_REQUIRE(!g.video || ctx, "mvn_decode_steps: shape says video but ctx is null");
@@ -468,8 +558,12 @@ extern "C" int mvn_decode_steps(const mvn_shape_t* s, const void* packed, void* 
     args.N = g.N; args.A = g.A; args.C = g.C; args.S = g.S; args.Kz = g.Kz; args.video = g.video; args.B = g.B;
     args.Tctx = g.T; args.ctx_dtype = g.adt; args.t_start = t_start; args.n_new = n_new;
     args.temperature = temperature; args.seed = seed;
-    const size_t qf = queue_floats(g, args.qoff);
+    decode_edge_geometry(g, mode, &args.edge, args.hist, args.age);
+    args.RF = g.RF;
+    MVN_REQUIRE(!args.edge || t_start >= g.RF, "mvn_decode_steps: the reference-window mode starts at t_start >= receptive_fields");
+    const size_t qf = queue_floats(g, args.hist, args.qoff);
     args.queues = (float*)state; args.last2 = (int*)((char*)state + al256(qf * (size_t)g.B * 4));
+    args.code_ring = args.last2 + al256((size_t)g.B * 2 * 4) / 4;
     args.ctx = ctx; args.out_codes = out_codes; args.out_logits = out_logits;
     for (int l = 0; l < g.N; ++l) args.dil[l] = g.dil[l];
     cudaStream_t st = (cudaStream_t)stream;
@@ -479,8 +573,9 @@ extern "C" int mvn_decode_steps(const mvn_shape_t* s, const void* packed, void* 
         if (used) return rc;
     }
     // clips per CTA: keep every SM busy first, then amortise weight reads over more clips
-    if (g.B >= 148 * 8 && (size_t)g.N * 8 * g.C * 4 <= 64 * 1024) return launch_decode<8>(args, g, st);
-    if (g.B >= 148 * 4 && (size_t)g.N * 4 * g.C * 4 <= 64 * 1024) return launch_decode<4>(args, g, st);
+    const size_t per_clip = (size_t)g.N * g.C * 4 * (args.edge ? 2 : 1);
+    if (g.B >= 148 * 8 && per_clip * 8 <= 64 * 1024) return launch_decode<8>(args, g, st);
+    if (g.B >= 148 * 4 && per_clip * 4 <= 64 * 1024) return launch_decode<4>(args, g, st);
     if (g.B >= 148 * 2) return launch_decode<2>(args, g, st);
     return launch_decode<1>(args, g, st);
 }

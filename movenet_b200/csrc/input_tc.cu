@@ -153,8 +153,8 @@ int mvn_tc_input_bwd(const float* audio, const int* codes, const unsigned char* 
     a.B = g.B; a.T = g.T; a.A = g.A; a.dil0 = g.dil[0]; a.has_u = u != nullptr;
     a.tiles_per_clip = (g.T + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
     const int smem = 4 * TILE_BYTES + 64 + 1024;
-    static bool attr = false;
-    if (!attr) { MVN_CUDA(cudaFuncSetAttribute(input_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    static MvnSmemAttr attr;
+    MVN_CUDA(mvn_ensure_smem(input_bwd_tc_kernel, smem, attr));
     const int grid = a.n_tiles < 3 * 148 ? a.n_tiles : 3 * 148;
     MVN_CUDA(mvn_launch_pdl(input_bwd_tc_kernel, dim3(grid), dim3(128), (size_t)(smem), st, mp, mu, a));
     if ((rc = mvn_check_launch("input_bwd_tc"))) return rc;

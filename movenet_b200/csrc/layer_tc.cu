@@ -297,7 +297,38 @@ EncodeTiledFn encode_fn() {
 
 }  // namespace
 
+// A tensor map is a pure function of (pointer, B, T): the caller-owned buffers of one geometry are reused step after step,
+// so the ~100 descriptors a training step needs are encoded once and then served from this table (mutex-guarded, the only
+// mutable global state of the library besides the per-thread error string and the launch counter).
+namespace {
+struct MapSlot { const void* ptr; int B, T; bool used; CUtensorMap map; };
+constexpr int MAP_SLOTS = 512;
+MapSlot g_maps[MAP_SLOTS];
+std::mutex g_maps_mu;
+int encode_act_map(CUtensorMap* map, const void* ptr, int B, int T);
+}
+
 int tc::make_act_map(CUtensorMap* map, const void* ptr, int B, int T) {
+    const size_t h = ((size_t)(uintptr_t)ptr >> 8) * 0x9E3779B97F4A7C15ull + (size_t)B * 1315423911u + (size_t)T;
+    const int i0 = (int)((h >> 20) % MAP_SLOTS);
+    {
+        std::lock_guard<std::mutex> lk(g_maps_mu);
+        for (int probe = 0; probe < 4; ++probe) {
+            const MapSlot& s = g_maps[(i0 + probe) % MAP_SLOTS];
+            if (s.used && s.ptr == ptr && s.B == B && s.T == T) { *map = s.map; return 0; }
+        }
+    }
+    const int rc = encode_act_map(map, ptr, B, T);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    int victim = i0;
+    for (int probe = 0; probe < 4; ++probe) if (!g_maps[(i0 + probe) % MAP_SLOTS].used) { victim = (i0 + probe) % MAP_SLOTS; break; }
+    g_maps[victim].ptr = ptr; g_maps[victim].B = B; g_maps[victim].T = T; g_maps[victim].map = *map; g_maps[victim].used = true;
+    return 0;
+}
+
+namespace {
+int encode_act_map(CUtensorMap* map, const void* ptr, int B, int T) {
     EncodeTiledFn fn = encode_fn();
     MVN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[3] = {(cuuint64_t)CC, (cuuint64_t)T, (cuuint64_t)B};
@@ -310,6 +341,7 @@ int tc::make_act_map(CUtensorMap* map, const void* ptr, int B, int T) {
     MVN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
+}  // namespace
 
 int mvn_tc_layer_supported(int C, int S, int video) {
     return C == CC && S >= 8 && S % 8 == 0 && S <= (video ? 32 : 64);   // the backward kernel's shared-memory budget
@@ -340,13 +372,10 @@ int mvn_tc_layer_fwd(const void* x_in, const void* ctx, void* x_out, float* skip
     a.tiles_per_clip = (g.T + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
     const int smem = smem_total(a.nchunks, a.N2) + 1024;
     static const bool gate_f32 = getenv("MOVENET_B200_GATE_F32") != nullptr;
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
-        MVN_CUDA(cudaFuncSetAttribute(layer_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        MVN_CUDA(cudaFuncSetAttribute(layer_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
-    }
-    int grid = 2 * 148;
+    static MvnSmemAttr attr_a, attr_b;
+    MVN_CUDA(mvn_ensure_smem(layer_fwd_tc_kernel<true>, smem, attr_a));
+    MVN_CUDA(mvn_ensure_smem(layer_fwd_tc_kernel<false>, smem, attr_b));
+    int grid = 2 * mvn_sm_count();
     if (grid > a.n_tiles) grid = a.n_tiles;
     if (gate_f32) MVN_CUDA(mvn_launch_pdl(layer_fwd_tc_kernel<false>, dim3(grid), dim3(256), (size_t)smem, st, map_x, map_ctx, map_out, a));
     else MVN_CUDA(mvn_launch_pdl(layer_fwd_tc_kernel<true>, dim3(grid), dim3(256), (size_t)smem, st, map_x, map_ctx, map_out, a));

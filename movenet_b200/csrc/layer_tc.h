@@ -42,6 +42,3 @@ int mvn_tc_upsample_pack(const float* wt, const float* bt, float* img, cudaStrea
 int mvn_tc_upsample_fwd(const float* img, const void* u2_bf16, void* ctx_bf16, long long rows, cudaStream_t st);
 int mvn_tc_upsample_bwd(const float* img, const void* u_bf16, const void* dout_bf16, void* du, int du_bf16, float* dwt, float* dbt,
                         float* partial, long long rows, cudaStream_t st);
-// second-generation forward layer kernel (layer_tc_fwd2.cu): persistent, warp-specialised, 3-stage TMA ring
-int mvn_tc_layer_fwd2(const void* x_in, const void* ctx, void* x_out, float* skip_sum, const float* layer_weights,
-                      const PackedLayout& P, const Geo& g, int layer, cudaStream_t st);

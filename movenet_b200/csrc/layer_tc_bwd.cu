@@ -629,7 +629,7 @@ __global__ void tc_bwd_reduce_kernel(const float* __restrict__ partial_all, int 
 size_t mvn_tc_bwd_partial_bytes() { return (size_t)148 * PART_FLOATS * 4; }   // per layer
 
 int mvn_tc_bwd_reduce_all(const float* partial_all, float* pg, const PackedLayout& P, const Geo& g, cudaStream_t st) {
-    int grid_ctas = 148;
+    int grid_ctas = mvn_sm_count() < 148 ? mvn_sm_count() : 148;
     const int n_tiles = ((g.T + TILE_T - 1) / TILE_T) * g.B;
     if (grid_ctas > n_tiles) grid_ctas = n_tiles;
     dim3 grid((PART_FLOATS + 255) / 256, g.N);
@@ -664,14 +664,11 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     a.tiles_per_clip = (g.T + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
     const int smem = bwd_smem_total(a.nchunks, a.N2) + 1024;
     MVN_REQUIRE(smem <= 227 * 1024, "tensor-core backward kernel: shared memory budget exceeded (%d)", smem);
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
-        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        MVN_CUDA(cudaFuncSetAttribute(layer_bwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
-    }
-    int grid = 148;
+    static MvnSmemAttr attr_a, attr_b, attr_c;
+    MVN_CUDA(mvn_ensure_smem(layer_bwd_tc_kernel<false, false>, smem, attr_a));
+    MVN_CUDA(mvn_ensure_smem(layer_bwd_tc_kernel<false, true>, smem, attr_b));
+    MVN_CUDA(mvn_ensure_smem(layer_bwd_tc_kernel<true, false>, smem, attr_c));
+    int grid = mvn_sm_count() < 148 ? mvn_sm_count() : 148;      // the per-CTA partial buffers are sized for 148 CTAs
     if (grid > a.n_tiles) grid = a.n_tiles;
     auto kernel = sum_out ? layer_bwd_tc_kernel<true, false>       // (summed output takes a summed or zero input: checked above)
                           : (a.pair_in ? layer_bwd_tc_kernel<false, true> : layer_bwd_tc_kernel<false, false>);

@@ -311,8 +311,8 @@ int mvn_tc_upsample_fwd(const float* img, const void* u2_bf16, void* ctx_bf16, l
     if ((rc = make_wide_map(&mu, u2_bf16, rows, 64))) return rc;
     UpArgs a; a.img = img; a.du2 = nullptr; a.partial = nullptr; a.rows = rows; a.n_tiles = (int)((rows + TILE_T - 1) / TILE_T); a.du_bf16 = 0;
     const int smem = IMG_BYTES + 3072 + 5 * TILE_BYTES + 64 + 1024;
-    static bool attr = false;
-    if (!attr) { MVN_CUDA(cudaFuncSetAttribute(up_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    static MvnSmemAttr attr;
+    MVN_CUDA(mvn_ensure_smem(up_fwd_tc_kernel, smem, attr));
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
     MVN_CUDA(mvn_launch_pdl(up_fwd_tc_kernel, dim3(grid), dim3(256), (size_t)(smem), st, mu, mc, a));
     return mvn_check_launch("upsample_fwd_tc");
@@ -326,8 +326,8 @@ int mvn_tc_upsample_bwd(const float* img, const void* u2_bf16, const void* dctx_
     UpArgs a; a.img = img; a.du2 = (float*)du2; a.partial = partial; a.rows = rows; a.n_tiles = (int)((rows + TILE_T - 1) / TILE_T);
     a.du_bf16 = du_bf16;
     const int smem = IMG_BYTES + 5 * TILE_BYTES + 1024 + 64 + 1024;
-    static bool attr = false;
-    if (!attr) { MVN_CUDA(cudaFuncSetAttribute(up_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    static MvnSmemAttr attr;
+    MVN_CUDA(mvn_ensure_smem(up_bwd_tc_kernel, smem, attr));
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
     MVN_CUDA(mvn_launch_pdl(up_bwd_tc_kernel, dim3(grid), dim3(256), (size_t)(smem), st, mu, md, a));
     if ((rc = mvn_check_launch("upsample_bwd_tc"))) return rc;

@@ -367,6 +367,12 @@ extern "C" size_t mvn_acts_bytes(const mvn_shape_t* s) {
 extern "C" size_t mvn_scratch_bytes(const mvn_shape_t* s) {
     Geo g; if (geo_init(g, s)) return 0; ScratchLayout w; scratch_layout(g, w); return w.total;
 }
+extern "C" size_t mvn_acts_offset(const mvn_shape_t* s, int which, int layer) {
+    Geo g; if (!s || geo_init(g, s)) return 0; ActsLayout a; acts_layout(g, a);
+    if (which == 0) return a.x0 + (size_t)(layer >= 0 && layer < g.N ? layer : 0) * a.x_stride;
+    if (which == 2) return a.ctx;
+    return 0;
+}
 extern "C" int mvn_receptive_fields(int layer_size, int stack_size) {
     mvn_shape_t s; memset(&s, 0, sizeof(s)); s.layer_size = layer_size; s.stack_size = stack_size;
     Geo g; if (geo_init(g, &s)) return -1; return g.RF;
@@ -416,8 +422,8 @@ static int input_fwd(const Ctx& c, const float* audio) {
     const long long rows = (long long)g.B * g.T, n = rows * ((g.C + 7) / 8);
     const size_t table = (size_t)2 * g.A * g.C * 4;
     if (g.C % 8 == 0 && 256 % (g.C / 8) == 0 && table <= 96 * 1024) {
-        static size_t attr = 0;
-        if (table > attr) { MVN_CUDA(cudaFuncSetAttribute(input_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)table)); attr = table; }
+        static MvnSmemAttr attr;
+        MVN_CUDA(mvn_ensure_smem(input_fwd_smem_kernel, (int)table, attr));
         const int per_sm = table <= 48 * 1024 ? 4 : 2;
         MVN_CUDA(mvn_launch_pdl(input_fwd_smem_kernel, dim3(148 * per_sm), dim3(256), table, c.st, audio, (const int*)codes,
                                 (const unsigned char*)dense, c.packed + c.P.win, c.x(0), g.adt, g.A, g.C, g.T, (int)rows));
@@ -474,11 +480,6 @@ static int layer_fwd(const Ctx& c, int l) {
     float* skip = (float*)(c.acts + c.AL.skip);
     void* ctx = g.video ? c.acts + c.AL.ctx : nullptr;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
-        // A/B switch: the warp-specialised persistent variant (layer_tc_fwd2.cu) measures the same 60 us per layer as
-        // the two-CTAs-per-SM kernel below on B200 (both are bound by the epilogue's XU/issue work and the MMA
-        // round-trip latency, profiles/), so the simpler kernel stays the default
-        static const bool v2 = getenv("MOVENET_B200_FWD_V2") != nullptr;
-        if (v2 && g.S <= 32) return mvn_tc_layer_fwd2(c.x(l), ctx, last ? nullptr : c.x(l + 1), skip, lw, c.P, g, l, c.st);
         return mvn_tc_layer_fwd(c.x(l), ctx, last ? nullptr : c.x(l + 1), skip, lw, c.P, g, l, c.st);
     }
     void* gated = c.scratch + c.SL.gated;

@@ -3,12 +3,25 @@
 Restates the contract of ``WaveNet.generate`` (movenet/wavenet.py:193-239):
 output is a (B, A, n) one-hot tensor whose first RF columns are the prompt and
 whose remaining columns are generated one sample at a time.
+
+Decoder modes (``WaveNet.decode_mode``):
+
+* ``"exact"``  (default) fp32 CUDA-core decoder computing the REFERENCE's function: for
+  ``stack_size >= 2`` the dilation-queue recursion is identical to the reference's window
+  recompute; for ``stack_size == 1`` the reference's zero-padded window edge reaches its
+  output and the decoder additionally evaluates that edge column per layer
+  (MVN_DECODE_REFERENCE, csrc/decode.cu).  Token-exact against ``generate(temperature=0)``.
+* ``"causal"`` fp32 decoder of the true causal model (no window edge); differs from
+  ``"exact"`` only when ``stack_size == 1``.
+* ``"fast"``   tensor-core throughput decoder (bf16 queues / operands, true causal model).
 """
 import ctypes as C
 
 import torch
 
 from . import _lib
+
+MODES = ("exact", "causal", "fast")
 
 
 def _stream():
@@ -18,9 +31,11 @@ def _stream():
 class DecodeState:
     """queues + bookkeeping of one batch of clips being generated"""
 
-    def __init__(self, shape, bufs, state, ctx, batch, channels, fast=False):
+    def __init__(self, shape, bufs, state, ctx, batch, channels, fast=False, mode=_lib.DECODE_REFERENCE, keep=None):
         self.shape, self.bufs, self.state, self.ctx, self.batch, self.channels = shape, bufs, state, ctx, batch, channels
         self.fast = fast
+        self.mode = mode
+        self.keep = keep        # buffers the context pointer points into
 
 
 def fast_mode_available(model, batch, n_prompt):
@@ -29,18 +44,21 @@ def fast_mode_available(model, batch, n_prompt):
     return bool(_lib.load().mvn_decode_tc_supported(C.byref(shape)))
 
 
-def prefill(model, prompt, video, fast=False):
-    """Run the prompt through the stack once and fill the per-layer dilation queues.
+def _abi_mode(mode):
+    if mode not in MODES:
+        raise ValueError(f"decode mode must be one of {MODES}, found {mode!r}")
+    return _lib.DECODE_CAUSAL if mode == "causal" else _lib.DECODE_REFERENCE
 
-    fast=False: the fp32 (exact) decoder, token-exact against the reference (the default of generate()).
-    fast=True : the tensor-core throughput decoder (bf16 queues and MMA operands).
-    """
+
+def prefill(model, prompt, video, fast=False, mode="exact"):
+    """Run the prompt through the stack once and fill the per-layer rings.
+
+    ``prompt`` is the (B, A, n_prompt) one-hot prompt; ``video`` the optional (B,160,64,64,Cin) conditioning clip.
+    fast=True selects the tensor-core throughput decoder (audio-only)."""
     B, A, n_prompt = prompt.shape
     dev = prompt.device
     if video is not None:
-        # finding F4: the reference cannot run generate() with video at all (its upsampled context is
-        # always 160000 frames long while the window is RF long).  Not wired up here either yet.
-        raise NotImplementedError("video-conditioned generate() is not implemented (it raises in the reference too)")
+        return _prefill_video(model, prompt, video, fast, mode)
     shape = model._shape(B, n_prompt, False, False, True, _lib.F32)
     bufs = model._buffers_for(shape, dev)
     model._pack(bufs, model._param_list())
@@ -54,9 +72,43 @@ def prefill(model, prompt, video, fast=False):
         state = torch.zeros(_lib.size("mvn_decode_tc_state_bytes", shape), dtype=torch.uint8, device=dev)
         _lib.call("mvn_decode_tc_prefill", C.byref(shape), bufs.packed.data_ptr(), acts.data_ptr(), state.data_ptr(), _stream())
         return DecodeState(shape, bufs, state, None, B, A, fast=True)
-    state = torch.zeros(_lib.size("mvn_decode_state_bytes", shape), dtype=torch.uint8, device=dev)
-    _lib.call("mvn_decode_prefill", C.byref(shape), acts.data_ptr(), state.data_ptr(), _stream())
-    return DecodeState(shape, bufs, state, None, B, A)
+    m = _abi_mode(mode)
+    state = torch.zeros(_lib.size("mvn_decode_state_bytes", shape, m), dtype=torch.uint8, device=dev)
+    _lib.call("mvn_decode_prefill", C.byref(shape), acts.data_ptr(), state.data_ptr(), m, 0, _stream())
+    return DecodeState(shape, bufs, state, None, B, A, mode=m)
+
+
+def _prefill_video(model, prompt, video, fast, mode):
+    """Video-conditioned prefill.  The reference cannot run generate() with video at all (its upsampled
+    context is always 160000 frames long while the window is RF long); the definition implemented here is the oracle's
+    (oracle/wavenet_oracle.py generate(context=...)): context column t-1 conditions the prediction of sample t, exactly
+    as in forward().  The upsampler only exists at the full clip length, so the stack runs once over a 160000-frame
+    pass whose first n_prompt columns are the prompt (causality: the padding after it cannot reach them)."""
+    from .wavenet import MAX_AUDIO_FRAMES
+    if fast:
+        raise _lib.MovenetB200Error("the tensor-core decoder has no video conditioning; use decode_mode 'exact'")
+    B, A, n_prompt = prompt.shape
+    dev = prompt.device
+    video = model._check_video(video)
+    assert video.shape[0] == B, "expected video and audio tensors to have equal batch sizes"
+    shape = model._shape(B, MAX_AUDIO_FRAMES, True, False, True, _lib.F32)
+    bufs = model._buffers_for(shape, dev)
+    model._pack(bufs, model._param_list())
+    acts = torch.empty(bufs.acts_bytes, dtype=torch.uint8, device=dev)
+    codes = torch.zeros(B, MAX_AUDIO_FRAMES, dtype=torch.int64, device=dev)
+    codes[:, :n_prompt] = prompt.argmax(1)
+    st = _stream()
+    _lib.call("mvn_codes_input", C.byref(shape), codes.data_ptr(), acts.data_ptr(), st)
+    _lib.call("mvn_video_fwd", C.byref(shape), bufs.packed.data_ptr(), video.data_ptr(), acts.data_ptr(), st)
+    _lib.call("mvn_input_fwd", C.byref(shape), bufs.packed.data_ptr(), 0, acts.data_ptr(), st)
+    scratch = bufs.get_scratch()
+    for l in range(model.layer_size * model.stack_size):
+        _lib.call("mvn_layer_fwd", C.byref(shape), bufs.packed.data_ptr(), l, acts.data_ptr(), scratch.data_ptr(), st)
+    m = _abi_mode(mode)
+    state = torch.zeros(_lib.size("mvn_decode_state_bytes", shape, m), dtype=torch.uint8, device=dev)
+    _lib.call("mvn_decode_prefill", C.byref(shape), acts.data_ptr(), state.data_ptr(), m, n_prompt, st)
+    ctx_ptr = acts.data_ptr() + _lib.size("mvn_acts_offset", shape, 2, 0)
+    return DecodeState(shape, bufs, state, ctx_ptr, B, A, mode=m, keep=acts)
 
 
 def run_steps(model, st, t_start, n_new, temperature=0.0, return_logits=False, forced=None):
@@ -76,18 +128,20 @@ def run_steps(model, st, t_start, n_new, temperature=0.0, return_logits=False, f
         raise ValueError("teacher forcing is only wired into the tensor-core decoder")
     codes = torch.empty(st.batch, n_new, dtype=torch.int32, device=dev)
     _lib.call("mvn_decode_steps", C.byref(st.shape), st.bufs.packed.data_ptr(), st.state.data_ptr(),
-              0 if st.ctx is None else st.ctx.data_ptr(), t_start, n_new, codes.data_ptr(),
+              0 if st.ctx is None else st.ctx, st.mode, t_start, n_new, codes.data_ptr(),
               0 if logits is None else logits.data_ptr(), C.c_float(float(temperature)), seed, _stream())
     return (codes, logits) if return_logits else codes
 
 
-def cached_generate(model, audio, video, n_samples, temperature, return_logits=False, fast=False):
+def cached_generate(model, audio, video, n_samples, temperature, return_logits=False, fast=False, mode="exact"):
     audio = model._check_audio(audio)
     B, A, T_in = audio.shape
     RF = model.receptive_fields
     n = T_in if n_samples is None else int(n_samples)
     if T_in < RF:
         raise ValueError(f"generate() needs at least receptive_fields={RF} prompt columns, found {T_in}")
+    if video is not None and n > 160000:
+        raise ValueError("video-conditioned generate() cannot run past the 160000 context frames")
     out = torch.zeros(B, A, n, dtype=audio.dtype, device=audio.device)
     keep = min(RF, n)
     out[:, :, :keep] = audio[:, :, :keep]
@@ -95,7 +149,7 @@ def cached_generate(model, audio, video, n_samples, temperature, return_logits=F
     if n_new <= 0:
         return (out, None) if return_logits else out
     with torch.cuda.device(audio.device):
-        st = prefill(model, audio[:, :, :RF].contiguous(), video, fast=fast)
+        st = prefill(model, audio[:, :, :RF].contiguous(), video, fast=fast, mode=mode)
         logits = steps_into(model, st, RF, n_new, out[:, :, RF:], temperature, return_logits)
     return (out, logits) if return_logits else out
 

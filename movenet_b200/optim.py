@@ -73,4 +73,5 @@ class AdamW(torch.optim.Optimizer):
                           float(b2), float(group["eps"]), float(group["weight_decay"]), 1.0 - math.pow(b1, t),
                           1.0 - math.pow(b2, t), float(clip), partials.data_ptr(),
                           self.grad_norm.data_ptr() if clip > 0 else 0, torch.cuda.current_stream().cuda_stream)
+            _lib.weights_epoch[0] += 1       # the parameters were rewritten behind autograd's version counters
         return loss

@@ -56,6 +56,7 @@ class _Buffers:
         self.shape = shape
         self.device = device
         self.packed = torch.empty(_lib.size("mvn_packed_bytes", shape), dtype=torch.uint8, device=device)
+        self.packed_stamp = None     # identifies the parameter values the packed image was built from (WaveNet._pack)
         self.packed_grads = None
         self.scratch = None
         self.acts_bytes = _lib.size("mvn_acts_bytes", shape)
@@ -163,13 +164,16 @@ class WaveNet(nn.Module):
         self.residual_conv_stack = ResidualConvStack(layer_size, stack_size, residual_channels, skip_channels)
         self.dense_conv = DenseConv(skip_channels, input_channels)
 
-        #: "exact": fp32 CUDA-core decoder, token-exact against the reference (default);
-        #: "fast" : tensor-core decoder (bf16 queues / operands) where mvn_decode_tc_supported -- throughput mode
+        #: "exact" : fp32 CUDA-core decoder, the reference's function incl. its window edge, token-exact (default);
+        #: "causal": fp32 decoder of the true causal model (differs from "exact" only for stack_size == 1);
+        #: "fast"  : tensor-core decoder (bf16 queues / operands) where mvn_decode_tc_supported -- throughput mode
         self.decode_mode = os.environ.get("MOVENET_B200_DECODE", "exact")
         self._bufs = {}
         self._ptr_tables = {}
         self._dp_group = None
         self._dp_world = 1
+        self._dp_avg = False
+        self._weights_epoch = 0      # bumped by anything that rewrites parameters behind autograd's back (see _pack)
 
     # ------------------------------------------------------------------ reference surface
     @property
@@ -245,15 +249,21 @@ class WaveNet(nn.Module):
         generate up to ``n_samples`` TOTAL columns; returns the (B, A, n) one-hot tensor.
 
         The reference recomputes an RF-long window per sample; this runs the cached decoder
-        (per-layer dilation queues, O(layers) per sample).  With stack_size >= 2 the two are the
-        same function of the prompt.  With stack_size == 1 the reference's zero-padded window edge
-        leaks into its output while the cache evaluates the true causal model, so
-        logits differ by O(1e-5..1e-3) there.  Only ``temperature == 0`` (argmax) is deterministic
-        in the reference; ``temperature > 0`` draws from softmax(probs / temperature).
+        (per-layer rings, O(layers) per sample).  With stack_size >= 2 the two are the same
+        function of the prompt.  With stack_size == 1 the reference's zero-padded window edge
+        reaches its output; the default ``decode_mode = "exact"`` reproduces it with
+        one extra edge column per layer per step (movenet_b200/decode.py), ``"causal"`` evaluates
+        the true causal model instead, ``"fast"`` is the tensor-core throughput decoder.
+        Only ``temperature == 0`` (argmax) is deterministic in the reference; ``temperature > 0``
+        draws from softmax(probs / temperature).
+
+        ``video``: the reference raises for it; here context column t-1 conditions
+        sample t exactly as in ``forward`` (the oracle's window definition).
         """
         from .decode import cached_generate
         self.eval()
-        return cached_generate(self, audio, video, n_samples, temperature, fast=(self.decode_mode == "fast"))
+        return cached_generate(self, audio, video, n_samples, temperature, fast=(self.decode_mode == "fast"),
+                               mode="exact" if self.decode_mode == "fast" else self.decode_mode)
 
     # ------------------------------------------------------------------ data parallel
     def enable_data_parallel(self, process_group=None):
@@ -262,13 +272,26 @@ class WaveNet(nn.Module):
         import torch.distributed as dist
         self._dp_group = process_group if process_group is not None else dist.group.WORLD
         self._dp_world = dist.get_world_size(self._dp_group)
+        # the replicas must start identical: like DistributedDataParallel's constructor, take rank 0's parameters
+        # (ranks may have been built with different RNG state, or only some may have loaded a checkpoint)
+        if self._dp_world > 1:
+            src = dist.get_global_rank(self._dp_group, 0)
+            with torch.no_grad():
+                for p in self.parameters():
+                    dist.broadcast(p.data, src=src, group=self._dp_group)
+            self._weights_epoch += 1
+        # NCCL averages inside the reduction (ncclAvg); other backends sum, then scale
+        self._dp_avg = dist.get_backend(self._dp_group) == "nccl"
         return self
 
     def _reduce_grads(self, flat):
         if self._dp_world > 1:
             import torch.distributed as dist
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self._dp_group)
-            flat.mul_(1.0 / self._dp_world)
+            if self._dp_avg:
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self._dp_group)
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self._dp_group)
+                flat.mul_(1.0 / self._dp_world)
 
     # ------------------------------------------------------------------ plumbing
     def _param_list(self):
@@ -327,7 +350,9 @@ class WaveNet(nn.Module):
         return self._buffers_for(shape, audio.device)
 
     def _pack(self, bufs, params):
-        """re-layout the reference parameters for the kernels (weights change every optimizer step)"""
+        """re-layout the reference parameters for the kernels -- only when they changed since this buffer set was last
+        packed: every in-place update through torch bumps a tensor's ``_version``; movenet_b200.optim.AdamW (which writes
+        through raw pointers) and enable_data_parallel bump ``_lib.weights_epoch`` / ``_weights_epoch`` instead"""
         ptrs = tuple(p.data_ptr() for p in params)
         key = ("w", str(bufs.device))
         cached = self._ptr_tables.get(key)
@@ -337,7 +362,12 @@ class WaveNet(nn.Module):
                     raise RuntimeError("movenet_b200.WaveNet parameters must be contiguous fp32 tensors on the input's device")
             table = torch.tensor(ptrs, dtype=torch.int64).to(bufs.device)
             cached = self._ptr_tables[key] = (ptrs, table)
+        stamp = (ptrs, _lib.weights_epoch[0], self._weights_epoch, sum(p._version for p in params),
+                 torch.cuda.current_stream().cuda_stream)
+        if bufs.packed_stamp == stamp:
+            return
         _lib.call("mvn_pack_weights", C.byref(bufs.shape), cached[1].data_ptr(), bufs.packed.data_ptr(), _stream())
+        bufs.packed_stamp = stamp
 
     def _grad_layout(self, has_video):
         """element offset of every parameter's gradient in the flat buffer (-1: no gradient, as in the

@@ -244,3 +244,60 @@ def causal_logits(p, shape: Shape, audio, context=None):
         skips = skips + F.conv1d(gated, p[pre + "conv_skip.weight"], p[pre + "conv_skip.bias"])
         x = F.conv1d(gated, p[pre + "conv_residual.weight"], p[pre + "conv_residual.bias"]) + x
     return dense_head(p, skips)
+
+
+@torch.no_grad()
+def window_edge_logits(p, shape: Shape, audio, context=None):
+    """What generate()'s RF-long window yields at every step i in [RF, n], computed WITHOUT the window recompute.
+
+    Restates the algorithm of the cached decoder's reference-window mode (movenet_b200/csrc/decode.cu,
+    MVN_DECODE_REFERENCE) so that the derivation is pinned on the CPU against the reference's own generate() logits
+    (tests/test_oracle.py).  Only meaningful for stack_size == 1 (finding F5); for stack_size >= 2 it returns
+    causal_logits.  movenet/wavenet.py:217-224 feeds x[i-RF:i]; movenet/modules.py:15-30 zero-pads its left edge, so
+    the window's first h0 column is e_0 = W[:,:,1] x[i-RF]; each layer drops d columns on the left
+    (movenet/modules.py:36-46), hence exactly one column per layer descends from e_0:
+        e_{l+1} = Wr_l gate(Wz0_l e_l + Wz1_l x_l[p_l] (+ ctx[p_l])) + br_l + x_l[p_l],  p_l = i-1 - sum_{k>l} d_k
+    and only the LAST layer's skip output at i-1 is built from it.
+    Returns (B, A, n-RF+1): column j is the logits for sample RF+j.
+    """
+    RF, dil, N = shape.receptive_fields, shape.dilations, shape.n_layers
+    n = audio.shape[2]
+    if shape.stack_size != 1:
+        return causal_logits(p, shape, audio, context)[:, :, RF - 1:]
+    # true causal layer inputs x_l[t] and skip outputs for every t
+    xs, skips = [], []
+    x = causal_conv(p, audio)
+    for i, d in enumerate(dil):
+        xs.append(x)
+        xp = F.pad(x, (d, 0))
+        pre = layer_prefix(i)
+        f = F.conv1d(xp, p[pre + "conv_filter.conv.weight"], None, dilation=d)
+        g = F.conv1d(xp, p[pre + "conv_gate.conv.weight"], None, dilation=d)
+        if context is not None:
+            f = f + F.conv1d(context[:, :, :n], p[pre + "context_conv_filter.weight"], p[pre + "context_conv_filter.bias"])
+            g = g + F.conv1d(context[:, :, :n], p[pre + "context_conv_gate.weight"], p[pre + "context_conv_gate.bias"])
+        gated = torch.tanh(f) * torch.sigmoid(g)
+        skips.append(F.conv1d(gated, p[pre + "conv_skip.weight"], p[pre + "conv_skip.bias"]))
+        x = F.conv1d(gated, p[pre + "conv_residual.weight"], p[pre + "conv_residual.bias"]) + x
+    age = [sum(dil[l + 1:]) for l in range(N)]
+    steps = torch.arange(RF, n + 1)                       # i: the sample being predicted
+    tau = steps - 1
+    W1 = p["causal_conv.conv.weight"][:, :, 1]            # (C, A)
+    e = torch.einsum("ca,bat->bct", W1, audio[:, :, steps - RF])
+    skip_sum = sum(s[:, :, tau] for s in skips[:-1]) if N > 1 else 0
+    for l, d in enumerate(dil):
+        pre = layer_prefix(l)
+        xl = xs[l][:, :, tau - age[l]]
+        wf, wg = p[pre + "conv_filter.conv.weight"], p[pre + "conv_gate.conv.weight"]
+        f = torch.einsum("oc,bct->bot", wf[:, :, 0], e) + torch.einsum("oc,bct->bot", wf[:, :, 1], xl)
+        g = torch.einsum("oc,bct->bot", wg[:, :, 0], e) + torch.einsum("oc,bct->bot", wg[:, :, 1], xl)
+        if context is not None:
+            cx = context[:, :, tau - age[l]]
+            f = f + F.conv1d(cx, p[pre + "context_conv_filter.weight"], p[pre + "context_conv_filter.bias"])
+            g = g + F.conv1d(cx, p[pre + "context_conv_gate.weight"], p[pre + "context_conv_gate.bias"])
+        gated = torch.tanh(f) * torch.sigmoid(g)
+        if l < N - 1:
+            e = F.conv1d(gated, p[pre + "conv_residual.weight"], p[pre + "conv_residual.bias"]) + xl
+        else:
+            skip_sum = skip_sum + F.conv1d(gated, p[pre + "conv_skip.weight"], p[pre + "conv_skip.bias"])
+    return dense_head(p, skip_sum)

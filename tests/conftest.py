@@ -9,7 +9,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-AUDIO_CASES = ["cfg00", "cfg00_gain", "cfg03", "cfg04_short", "testarch_small", "odd"]
+# cfg04_full: the decode benchmark's architecture at full depth (14 x 1 layers, RF 16384)
+AUDIO_CASES = ["cfg00", "cfg00_gain", "cfg03", "cfg04_short", "cfg04_full", "testarch_small", "odd"]
 
 
 def pytest_configure(config):

@@ -182,7 +182,17 @@ def make_wavenet_case(ref_wavenet, name, shape_kw, B, extra_T, seed, out_dir, ga
         fx["logits"] = logits
         fx["probs"] = probs.detach()
 
-    if gen_new:
+    if gen_new and video:
+        # finding F4: the reference's generate() cannot run with video (its upsampled context is always 160000 frames
+        # long, the window RF).  OUR definition (oracle.generate): the window [i-RF, i) of the upsampled context
+        # conditions step i -- the same alignment forward() uses for column i-1.  Pinned by the oracle only.
+        with torch.no_grad():
+            n = RF + gen_new
+            o_gen, o_glog = orc.generate(p, shape, audio[:, :, :RF], ctx[:, :, :n], n, 0.0, return_logits=True)
+            fx["gen_codes"] = o_gen.argmax(1).to(torch.int16)
+            fx["gen_logits"] = o_glog
+            fx["meta"]["generate"] = "oracle only (reference raises, F4): context window [i-RF, i)"
+    elif gen_new:
         with torch.no_grad():
             n = RF + gen_new
             gen = model.generate(audio[:, :, :RF], n_samples=n, temperature=0.0)
@@ -191,7 +201,7 @@ def make_wavenet_case(ref_wavenet, name, shape_kw, B, extra_T, seed, out_dir, ga
             fx["gen_codes"] = gen.argmax(1).to(torch.int16)
             fx["gen_logits"] = o_glog
             # finding F5: windowed logits vs the true causal model on the same tokens
-            cl = orc.causal_logits(p, shape, gen)[:, :, RF - 1:n - 1]
+            cl = orc.causal_logits(p, shape, gen)[:, :, RF - 1:n - 1].clone()
             fx["gen_causal_logits"] = cl
             fx["meta"]["window_vs_causal_maxabs"] = float((cl - o_glog).abs().max())
     path = os.path.join(out_dir, f"wavenet_{name}.pt")
@@ -202,7 +212,30 @@ def make_wavenet_case(ref_wavenet, name, shape_kw, B, extra_T, seed, out_dir, ga
 
 def main():
     torch.set_num_threads(8)
+    only = None
+    for a in sys.argv[1:]:
+        if a.startswith("--only="):
+            only = set(a[len("--only="):].split(","))
     ref_wavenet, ref_modules = import_reference()
+    if only is not None:
+        # round-2 additions, generated without touching the round-1 files
+        if "cfg04_full" in only:
+            # the decode benchmark's architecture at FULL depth (experiments/04_kinetics_receptive_field.mk:58-71):
+            # 14 x 1 layers, RF 16384 -- ring slots up to d = 8192 and the stack_size == 1 window edge (finding F5)
+            make_wavenet_case(ref_wavenet, "cfg04_full", dict(layer_size=14, stack_size=1, input_channels=128,
+                              residual_channels=16, skip_channels=8), B=2, extra_T=300, seed=8, out_dir=HERE, gen_new=32,
+                              gain=1.5)
+        patch_video_crop(ref_modules)
+        if "cfg01_true" in only:
+            # the benchmarked training shape itself (experiments/01_audio_video_debug.mk:10-17), one full-length clip
+            make_wavenet_case(ref_wavenet, "cfg01_true", dict(layer_size=3, stack_size=3, input_channels=64,
+                              residual_channels=64, skip_channels=8), B=1, extra_T=0, seed=9, out_dir=HERE,
+                              video=True, sample_cols=1024, gen_new=32)
+        if "video_gen" in only:
+            make_wavenet_case(ref_wavenet, "video_gen", dict(layer_size=3, stack_size=1, input_channels=32,
+                              residual_channels=16, skip_channels=8), B=2, extra_T=0, seed=10, out_dir=HERE,
+                              video=True, sample_cols=256, gen_new=40)
+        return
     make_mulaw(HERE)
     # audio-only cases run on the UNMODIFIED reference
     make_wavenet_case(ref_wavenet, "cfg00", dict(layer_size=3, stack_size=3, input_channels=64,

@@ -18,8 +18,16 @@ def _worker(rank, world, port, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import movenet_b200
-    m = movenet_b200.WaveNet(2, 2, 16, 8, 8).enable_data_parallel()
+    torch.manual_seed(100 + rank)            # replicas built from different RNG states ...
+    m = movenet_b200.WaveNet(2, 2, 16, 8, 8)
+    before = torch.cat([p.detach().flatten() for p in m.parameters()])
+    m.enable_data_parallel()                 # ... must leave enable_data_parallel with rank 0's parameters (DDP's constructor)
     assert m._dp_world == world
+    mine = torch.cat([p.detach().flatten() for p in m.parameters()])
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    same = all(torch.equal(g, gathered[0]) for g in gathered)
+    kept = torch.equal(mine, before)         # true on rank 0 only
     offs, total = m._grad_layout(has_video=False)
     flat = torch.full((total,), float(rank + 1))
     m._reduce_grads(flat)
@@ -27,7 +35,7 @@ def _worker(rank, world, port, out):
     # sharding helper: disjoint, covering
     from movenet_b200.parallel import shard_range
     lo, hi = shard_range(10, rank, world)
-    out[rank] = (ok, lo, hi)
+    out[rank] = (ok and same and (kept == (rank == 0)), lo, hi)
     dist.destroy_process_group()
 
 

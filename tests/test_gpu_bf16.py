@@ -6,7 +6,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import golden_audio, load_golden
+from conftest import golden_audio, golden_video, load_golden
 import movenet_b200
 
 pytestmark = pytest.mark.gpu
@@ -36,7 +36,7 @@ def rel_l2(a, b):
 
 
 @pytest.mark.parametrize("summed", ["0", "1"])
-@pytest.mark.parametrize("name", ["cfg00", "cfg00_gain", "cfg03", "cfg04_short", "testarch_small", "odd"])
+@pytest.mark.parametrize("name", ["cfg00", "cfg00_gain", "cfg03", "cfg04_short", "cfg04_full", "testarch_small", "odd"])
 def test_bf16_forward_loss_and_grads_against_golden(name, summed, monkeypatch):
     """summed = "1": the backward's one-stream variant (MOVENET_B200_BWD_SUM, layer_tc_bwd.cu) on the same fixtures: few tiles
     per clip, so nearly every CTA run is a warm-up tile plus one tile."""
@@ -60,6 +60,40 @@ def test_bf16_forward_loss_and_grads_against_golden(name, summed, monkeypatch):
         errs.append(rel_l2(got[k].grad.cpu(), g))
         assert errs[-1] < GRAD_RTOL, (k, errs[-1])
     assert sum(errs) / len(errs) < GRAD_MEAN_RTOL, sum(errs) / len(errs)
+    for k in fx["none_grads"]:
+        assert got[k].grad is None, k
+    a = torch.cat([got[k].grad.cpu().flatten() for k in fx["grads"]])
+    b = torch.cat([g.flatten() for g in fx["grads"].values()])
+    assert F.cosine_similarity(a, b, dim=0).item() >= GRAD_COS
+
+
+def test_bf16_benchmarked_shape_against_the_reference():
+    """The shape bench.py times (BASELINE configs[1]: A64 C64 S8 3x3, video, T = 160000) in the mode it times (bf16 tensor
+    cores: the nchunks == 3 path of the tcgen05 layer kernels, the tensor-core upsampler, head and input kernels), compared
+    DIRECTLY with the fixture the patched reference produced at this shape -- not via the fp32 mode."""
+    fx = load_golden("cfg01_true")
+    m = build(fx, "bf16")
+    audio = golden_audio(fx).cuda()
+    video = golden_video(fx, 1).cuda()
+    cols = fx["cols"].cuda()
+    with torch.no_grad():
+        logits = m(audio, video, output_unnormalized=False)
+    ref = fx["logits_cols"]
+    assert (logits[:, :, cols].cpu() - ref).abs().max().item() <= LOGIT_RTOL * ref.abs().max().item()
+    output = m(audio, video)
+    target = audio[:, :, m.receptive_fields:].argmax(1)
+    loss = F.cross_entropy(output, target)
+    assert type(loss.grad_fn).__name__.startswith("_FusedLoss")        # the route the bench takes
+    loss.backward()
+    assert (output.detach()[:, :, cols].cpu() - fx["probs_cols"]).abs().max().item() <= LOGIT_RTOL * fx["probs_cols"].abs().max().item()
+    assert abs(loss.item() - fx["loss"].item()) <= LOSS_RTOL * abs(fx["loss"].item())
+    got = dict(m.named_parameters())
+    errs = {}
+    for k, g in fx["grads"].items():
+        assert got[k].grad is not None, k
+        errs[k] = rel_l2(got[k].grad.cpu(), g)
+        assert errs[k] < GRAD_RTOL, (k, errs[k])
+    assert sum(errs.values()) / len(errs) < GRAD_MEAN_RTOL, sum(errs.values()) / len(errs)
     for k in fx["none_grads"]:
         assert got[k].grad is None, k
     a = torch.cat([got[k].grad.cpu().flatten() for k in fx["grads"]])
@@ -111,7 +145,7 @@ def test_bf16_ragged_tile_edges():
         assert (a - b).abs().max().item() <= LOGIT_RTOL * a.abs().max().item(), T
 
 
-@pytest.mark.parametrize("name", ["cfg04_short", "cfg03"])
+@pytest.mark.parametrize("name", ["cfg04_short", "cfg03", "cfg04_full"])
 def test_tensor_core_decoder_teacher_forced_logits(name):
     """Throughput decoder (tcgen05, bf16 queues) on the receptive-field architecture (stack_size 1, C 16, A 128) and on
     the scale-up one (2 x 2 layers, C 32: the two-group variant of the kernel):

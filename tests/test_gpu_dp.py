@@ -22,7 +22,7 @@ def _worker(rank, world, port, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    torch.manual_seed(0)
+    torch.manual_seed(0 if rank == 0 else 77 + rank)      # only rank 0 holds the weights the single process will use
     m = movenet_b200.WaveNet(2, 2, 32, 16, 8, compute_dtype="fp32").cuda().enable_data_parallel()
     g = torch.Generator().manual_seed(1)
     codes = torch.randint(0, 32, (4, 300), generator=g)
@@ -30,6 +30,9 @@ def _worker(rank, world, port, out_dir):
     out = m(mine)
     F.cross_entropy(out, mine[:, m.receptive_fields:]).backward()
     torch.save({k: v.grad.cpu() for k, v in m.named_parameters() if v.grad is not None}, os.path.join(out_dir, f"g{rank}.pt"))
+    opt = movenet_b200.optim.AdamW(m.parameters(), lr=1e-3)
+    opt.step()                                              # replicas must still agree after an optimizer step
+    torch.save({k: v.detach().cpu() for k, v in m.named_parameters()}, os.path.join(out_dir, f"w{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -40,6 +43,8 @@ def test_nccl_gradient_average_matches_single_process(tmp_path):
     import movenet_b200
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     g0 = torch.load(tmp_path / "g0.pt"); g1 = torch.load(tmp_path / "g1.pt")
+    w0 = torch.load(tmp_path / "w0.pt"); w1 = torch.load(tmp_path / "w1.pt")
+    assert all(torch.equal(w0[k], w1[k]) for k in w0)
     torch.manual_seed(0)
     m = movenet_b200.WaveNet(2, 2, 32, 16, 8, compute_dtype="fp32").cuda()
     codes = torch.randint(0, 32, (4, 300), generator=torch.Generator().manual_seed(1)).cuda()

@@ -45,7 +45,14 @@ def test_buffer_sizes_are_reported_without_a_gpu():
     assert _lib.size("mvn_packed_bytes", s) > 4 * 64 * 4096
     assert _lib.size("mvn_acts_bytes", s) > 9 * 3 * 160000 * 64 * 4
     assert _lib.size("mvn_scratch_bytes", s) > 0
-    assert _lib.size("mvn_decode_state_bytes", s) > 0
+    assert _lib.size("mvn_decode_state_bytes", s, _lib.DECODE_CAUSAL) > 0
+    # stack_size == 1: the reference-window mode keeps every layer's inputs back to the window edge
+    s1 = _lib.Shape(14, 1, 128, 16, 8, 1, 2, 16384, 0, _lib.F32, 0, 1)
+    causal = _lib.size("mvn_decode_state_bytes", s1, _lib.DECODE_CAUSAL)
+    window = _lib.size("mvn_decode_state_bytes", s1, _lib.DECODE_REFERENCE)
+    assert causal >= 2 * 16383 * 16 * 4 and window > 10 * causal
+    s3 = _lib.Shape(3, 3, 64, 64, 8, 1, 2, 24, 0, _lib.F32, 0, 1)
+    assert _lib.size("mvn_decode_state_bytes", s3, _lib.DECODE_CAUSAL) == _lib.size("mvn_decode_state_bytes", s3, _lib.DECODE_REFERENCE)
 
 
 def test_constructor_signature_is_the_reference_one():
@@ -134,3 +141,15 @@ def test_grad_layout_marks_the_parameters_the_reference_leaves_without_grad():
     offs_v, _ = m._grad_layout(has_video=True)
     assert sorted(n for n, o in zip(names, offs_v) if o < 0) == sorted(n for n in fx["none_grads"] if "conv_residual" in n)
     assert total >= sum(p.numel() for n, p in m.named_parameters() if n not in none)
+
+
+def test_movenet_import_shim_resolves_to_this_package():
+    """`from movenet.wavenet import WaveNet` (movenet/pytorch_lightning_trainer.py:16) must give the B200 module"""
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); from movenet.wavenet import WaveNet, MAX_AUDIO_FRAMES, MAX_VIDEO_FRAMES, "
+            "VIDEO_KERNEL_SIZE; from movenet.modules import GatedResidualConv1d, ResidualConvStack, DenseConv, CausalConv1d, "
+            "DilatedCausalConv1d; from movenet.types import AudioTensor, VideoTensor; import movenet_b200; "
+            "assert WaveNet is movenet_b200.WaveNet and MAX_AUDIO_FRAMES == 160000 and MAX_VIDEO_FRAMES == 160 "
+            "and VIDEO_KERNEL_SIZE == (1, 64, 64); print('ok')") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/")
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr

@@ -78,3 +78,34 @@ def test_mulaw_oracle_matches_torchaudio_vectors():
         assert torch.equal(mulaw_oracle.mu_law_decode(torch.arange(A), A), fx[A]["decode_lut"])
     # the reference test's fixture (tests/test_model.py:20-27)
     assert fx[256]["codes64"][:8].tolist() == [128, 203, 218, 227, 233, 238, 242, 245]
+
+
+@pytest.mark.parametrize("name", ["cfg04_short", "cfg04_full", "video_gen"])
+def test_window_edge_chain_reproduces_the_reference_generate(name):
+    """stack_size == 1 (finding F5): the cached decoder's reference-window algorithm, restated on the CPU
+    (oracle.window_edge_logits), gives the logits of the reference's own generate() -- far below the gap between the
+    window and the true causal model -- so the CUDA decoder has a pinned definition to be compared with."""
+    fx = load_golden(name)
+    shape, p = full_params(fx)
+    codes = fx["gen_codes"].long()
+    gen = torch.zeros(codes.shape[0], shape.input_channels, codes.shape[1]).scatter_(1, codes.unsqueeze(1), 1.0)
+    ctx = orc.upsample_video(p, golden_video(fx, codes.shape[0])) if "video_seed" in fx else None
+    z = orc.window_edge_logits(p, shape, gen, ctx)[:, :, :-1]
+    err = (z - fx["gen_logits"]).abs().max().item()
+    assert err < 2e-6, err
+    gap = fx["meta"].get("window_vs_causal_maxabs")
+    if gap is not None and gap > 1e-5:
+        assert err < 1e-2 * gap
+
+
+def test_benchmarked_shape_fixture_matches_patched_reference():
+    """cfg01_true: BASELINE configs[1] at its real size (one 160000-sample clip with video)"""
+    fx = load_golden("cfg01_true")
+    shape, p = full_params(fx)
+    audio = golden_audio(fx)
+    video = golden_video(fx, 1)
+    loss, probs, grads = orc.loss_and_grads(p, shape, audio, video)
+    assert torch.equal(probs[:, :, fx["cols"]], fx["probs_cols"])
+    assert torch.equal(loss, fx["loss"])
+    for k, g in fx["grads"].items():
+        assert torch.equal(grads[k], g), k
