@@ -70,6 +70,11 @@ int mvn_version(void);
 /* number of kernel launches this library has issued in this process (bench bookkeeping) */
 unsigned long long mvn_launch_count(void);
 
+/* which kernel family serves a shape: 0 CUDA-core (fp32 exact mode, or bf16 shapes without a tensor-core kernel),
+ * 1 fused tcgen05 layer kernels with shared-memory-resident weights (residual_channels <= 64, bf16),
+ * 2 wide-channel weight-streaming tcgen05 GEMMs with fused epilogues (residual/skip channels multiples of 128, bf16) */
+int mvn_kernel_path(const mvn_shape_t* s);
+
 /* geometry helpers: WaveNet.receptive_fields (movenet/wavenet.py:125-134) and
  * compute_output_size (movenet/wavenet.py:136-147; returns <1 when the
  * reference raises ValueError). */

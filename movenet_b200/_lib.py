@@ -31,6 +31,7 @@ SIGNATURES = {
     "mvn_last_error": (C.c_char_p, []),
     "mvn_version": (_I, []),
     "mvn_launch_count": (C.c_ulonglong, []),
+    "mvn_kernel_path": (_I, [_SP]),
     "mvn_receptive_fields": (_I, [_I, _I]),
     "mvn_output_size": (_I, [_I, _I, _I]),
     "mvn_packed_bytes": (_SZ, [_SP]),

@@ -44,6 +44,14 @@ static inline int geo_init(Geo& g, const mvn_shape_t* s) {
     return 0;
 }
 
+// Wide-channel tensor-core path (wide.cu, wide_gemm.cuh): weight-streaming tcgen05 GEMMs for residual_channels >= 128
+// (the widened scale-up shape, BASELINE configs[3]); audio-only, every channel count a multiple of 128, A <= 256 (one
+// accumulator chunk holds a whole softmax row)
+static inline int wide_ok(const Geo& g) {
+    return g.adt == MVN_DTYPE_BF16 && !g.video && g.C >= 128 && g.C % 128 == 0 && g.C <= 1024 && g.S >= 128 && g.S % 128 == 0 &&
+           g.S <= 1024 && g.A >= 128 && g.A % 128 == 0 && g.A <= 256;
+}
+
 // ---- packed weights (fp32 elements) -------------------------------------------------------------
 struct PackedLayout {
     size_t win;                 // [2][A][C]      Win[tap][a][c] = causal_conv.conv.weight[c][a][tap]
@@ -63,6 +71,12 @@ struct PackedLayout {
     size_t wt[3], bt[3], wtT[3];// transposed convs: [C][10C], [10C] (bias tiled), [10C][C]
     size_t tc_up;               // tensor-core image of the last upsampler level (bf16 [640][64] + bias), video && C == 64
     size_t tc_up01[2];          // ... and of the first two levels
+    // wide path: bf16 K-major matrices [rows][K] streamed by TMA (offsets in fp32 elements; per layer relative to the layer base)
+    size_t wWz;                 // [2C][2C]   rows in chunks of 256 = (filter | gate) of 128 channels ; K = tap0 C | tap1 C
+    size_t wWrs;                // [C+S][C]   rows: residual C | skip S
+    size_t wWrsT;               // [C][C+S]   d(gated) = [d(x') | d(skip)] . this^T
+    size_t wWzT;                // [C][4C]    d(x) = [dz(t) | dz(t+d)] . this^T ; dz columns interleaved (df c, dg c)
+    size_t wH1, wH2, wH2T, wH1T;// head: [A][S], [A][A], [A][A] (transposed), [S][A]
     size_t total;               // elements
 };
 
@@ -79,12 +93,19 @@ static inline void packed_layout(const Geo& g, PackedLayout& p) {
     p.oWzT = take(2 * C * Kz) - l0;
     p.oWrsT = take((C + S) * C) - l0;
     p.oTc = take(g.C == 64 ? MVN_TC_IMG_BYTES / 4 : 0) - l0;
+    const bool wide = wide_ok(g);
+    p.wWz = take(wide ? 2 * C * 2 * C / 2 : 0) - l0;
+    p.wWrs = take(wide ? (C + S) * C / 2 : 0) - l0;
+    p.wWrsT = take(wide ? C * (C + S) / 2 : 0) - l0;
+    p.wWzT = take(wide ? C * 4 * C / 2 : 0) - l0;
     p.layer0 = l0;
     p.layer_stride = o - l0;
     o = l0 + p.layer_stride * g.N;
     p.w1p = take(S * A); p.b1 = take(A); p.w2p = take(A * A); p.b2 = take(A);
     p.w1pT = take(A * S); p.w2pT = take(A * A);
     p.tc_head = take((A == 64 || A == 128) ? A * A / 2 : 0);
+    p.wH1 = take(wide ? A * S / 2 : 0); p.wH2 = take(wide ? A * A / 2 : 0);
+    p.wH2T = take(wide ? A * A / 2 : 0); p.wH1T = take(wide ? S * A / 2 : 0);
     if (g.video) {
         p.wv = take((size_t)4096 * g.Cin * C); p.bv = take(C);
         for (int i = 0; i < 3; ++i) { p.wt[i] = take(C * 10 * C); p.bt[i] = take(10 * C); p.wtT[i] = take(10 * C * C); }
@@ -143,6 +164,11 @@ struct ScratchLayout {
     size_t du2, du1, denc;
     size_t tc_partial; // per-CTA partial weight gradients of the head / input / upsampler tensor-core kernels
     size_t tc_layer_partial; // ... and of the layer backward kernel, one slot per layer (reduced together at the end)
+    // wide path (wide.cu)
+    size_t w_l0;      // (B,Tout,S) bf16 : lrelu(skip_sum), the head's first A operand
+    size_t w_ds16;    // (B,T,S) bf16    : d(skip) on the T row space (zero outside the last Tn rows of a clip)
+    size_t w_oh16;    // (B,T,A) bf16    : the audio (one-hot) as a GEMM operand of the input conv's weight gradient
+    size_t w_colsum;  // fp32 partial column sums (bias gradients)
     size_t total;
 };
 
@@ -168,5 +194,10 @@ static inline void scratch_layout(const Geo& g, ScratchLayout& w) {
     // slot 0: head / input / upsampler partials (used one after the other); slots 1..N: one per layer
     w.tc_partial = take(g.adt == MVN_DTYPE_BF16 && (g.C == 64 || g.A == 64 || g.A == 128) ? (size_t)2 * 148 * (128 * 256 + 256) * 4 : 0);
     w.tc_layer_partial = take(g.adt == MVN_DTYPE_BF16 && g.C == 64 ? (size_t)g.N * 148 * (128 * 256 + 256) * 4 : 0);
+    const bool wide = wide_ok(g);
+    w.w_l0 = take(wide ? BTo * g.S * 2 : 0);
+    w.w_ds16 = take(wide ? BT * g.S * 2 : 0);
+    w.w_oh16 = take(wide ? BT * g.A * 2 : 0);
+    w.w_colsum = take(wide ? (size_t)1024 * 1024 * 4 : 0);
     w.total = o;
 }

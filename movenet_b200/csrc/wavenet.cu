@@ -373,6 +373,13 @@ extern "C" size_t mvn_acts_offset(const mvn_shape_t* s, int which, int layer) {
     if (which == 2) return a.ctx;
     return 0;
 }
+// which kernel family serves this shape: 0 CUDA-core fp32 / generic, 1 tcgen05 fused layer kernels (C = 64 physical),
+// 2 wide-channel weight-streaming tcgen05 GEMMs (C >= 128)
+extern "C" int mvn_kernel_path(const mvn_shape_t* s) {
+    Geo g; if (!s || geo_init(g, s)) return -1;
+    if (mvn_wide_supported(g)) return 2;
+    return g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video) ? 1 : 0;
+}
 extern "C" int mvn_receptive_fields(int layer_size, int stack_size) {
     mvn_shape_t s; memset(&s, 0, sizeof(s)); s.layer_size = layer_size; s.stack_size = stack_size;
     Geo g; if (geo_init(g, &s)) return -1; return g.RF;
@@ -479,6 +486,8 @@ static int layer_fwd(const Ctx& c, int l) {
     const bool last = (l == g.N - 1);
     float* skip = (float*)(c.acts + c.AL.skip);
     void* ctx = g.video ? c.acts + c.AL.ctx : nullptr;
+    if (mvn_wide_supported(g))
+        return mvn_wide_layer_fwd(c.x(l), last ? nullptr : c.x(l + 1), c.scratch + c.SL.gated, skip, c.packed, c.P, g, l, c.st);
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
         return mvn_tc_layer_fwd(c.x(l), ctx, last ? nullptr : c.x(l + 1), skip, lw, c.P, g, l, c.st);
     }
@@ -507,6 +516,8 @@ static int head_fwd(const Ctx& c, float* out) {
     if (g.Tn <= 0) return 0;
     const long long rows = (long long)g.B * g.Tn;
     float* skip = (float*)(c.acts + c.AL.skip); float* a1 = (float*)(c.acts + c.AL.a1); float* z = (float*)(c.scratch + c.SL.z);
+    if (mvn_wide_supported(g))
+        return mvn_wide_head_fwd(c.packed, c.P, g, skip, a1, out, c.scratch + c.SL.w_l0, c.scratch + c.SL.z, c.st);
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S))
         return mvn_tc_head_fwd(c.packed, c.P, g, skip, out, c.st);
     int rc;
@@ -747,6 +758,12 @@ extern "C" int mvn_layer_bwd(const mvn_shape_t* s, const void* packed, int layer
     const Geo& g = c.g;
     MVN_REQUIRE(layer >= 0 && layer < g.N && packed_grads, "mvn_layer_bwd: bad arguments");
     float* pg = (float*)packed_grads;
+    if (mvn_wide_supported(g)) {
+        float* cs = (float*)(c.scratch + c.SL.w_colsum);
+        return mvn_wide_layer_bwd(c.x(layer), layer + 1 < g.N ? c.scratch + c.SL.dxa : nullptr, c.scratch + c.SL.dxb, c.scratch + c.SL.w_ds16,
+                                  c.scratch + c.SL.dgated, c.scratch + c.SL.gated, c.scratch + c.SL.dz, cs + 512 * 1024, c.packed, pg, cs,
+                                  c.P, g, layer, c.st);
+    }
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
         const size_t nb = (size_t)g.B * g.T * g.C * g.es;
         float* lg = pg + c.P.layer0 + (size_t)layer * c.P.layer_stride;
@@ -773,7 +790,7 @@ extern "C" int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, co
 
 extern "C" int mvn_fused_loss_supported(const mvn_shape_t* s) {
     Geo g; if (!s || geo_init(g, s)) return 0;
-    return !g.logits && g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S) && g.Tn > 0;
+    return !g.logits && g.adt == MVN_DTYPE_BF16 && (mvn_tc_head_supported(g.A, g.S) || mvn_wide_supported(g)) && g.Tn > 0;
 }
 
 extern "C" int mvn_wavenet_backward_loss(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,
@@ -794,6 +811,25 @@ static int backward_impl(const mvn_shape_t* s, const void* packed, const float* 
     const Geo& g = c.g;
     float* pg = (float*)packed_grads;
     MVN_CUDA(cudaMemsetAsync(pg, 0, c.P.total * 4, c.st));
+    if (mvn_wide_supported(g)) {
+        // wide-channel path (wide.cu): every GEMM on the weight-streaming tcgen05 engine, weight gradients through cuBLAS
+        const size_t half = (size_t)g.B * g.Tout * g.A * 2;
+        void* dzh = c.scratch + c.SL.z; void* l1 = c.scratch + c.SL.z + half;
+        void* ds16 = c.scratch + c.SL.w_ds16;
+        float* cs = (float*)(c.scratch + c.SL.w_colsum); float* dbs = cs + 512 * 1024;
+        if ((rc = mvn_wide_head_bwd(c.packed, c.P, g, (const float*)(c.acts + c.AL.skip), (const float*)(c.acts + c.AL.a1), out, dout, target,
+                                    grad_loss, dzh, c.scratch + c.SL.da1, c.scratch + c.SL.w_l0, l1, ds16, cs, pg, c.st))) return rc;
+        if ((rc = mvn_wide_skip_bias_grad(ds16, g, cs, dbs, c.st))) return rc;
+        void* bufs[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};
+        const void* dx_next = nullptr; int cur = 0;
+        for (int l = g.N - 1; l >= 0; --l) {
+            if ((rc = mvn_wide_layer_bwd(c.x(l), dx_next, bufs[cur], ds16, c.scratch + c.SL.dgated, c.scratch + c.SL.gated, c.scratch + c.SL.dz,
+                                         dbs, c.packed, pg, cs, c.P, g, l, c.st))) return rc;
+            dx_next = bufs[cur]; cur ^= 1;
+        }
+        return mvn_wide_input_bwd(audio, (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), dx_next,
+                                  c.scratch + c.SL.w_oh16, pg, c.P, g, c.st);
+    }
     if ((rc = head_bwd(c, out, dout, target, grad_loss, pg))) return rc;
     const bool tc_layers = g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video);
     if (g.video && !tc_layers) MVN_CUDA(cudaMemsetAsync(c.scratch + c.SL.dctx, 0, (size_t)g.B * g.T * g.C * 4, c.st));
