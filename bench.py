@@ -41,6 +41,12 @@ T_CLIP = 160000
 # batch: parser default 3 -- SURVEY section 8)
 WORKLOAD = dict(name="01_audio_video_debug", layer_size=3, stack_size=3, input_channels=64,
                 residual_channels=64, skip_channels=8, batch_per_gpu=3, video=True)
+# BASELINE.json configs[3] "scale-up model (03) with wider residual/skip channels, bf16": the architecture of the reference's own
+# test (tests/test_model.py:42-48: 10 x 3 layers, A = 256) widened to C = S = 256 -- SURVEY section 8 "03w", the one shape of
+# the path that is tensor-bound.  Audio-only (as SURVEY's flop count), one clip per GPU.  `python bench.py --workload 03w`
+WORKLOAD_03W = dict(name="03w_scale_up_wide", layer_size=10, stack_size=3, input_channels=256,
+                    residual_channels=256, skip_channels=256, batch_per_gpu=1, video=False)
+WORKLOADS = {"01": WORKLOAD, "03w": WORKLOAD_03W}
 # BASELINE.json configs[4]: experiments/04_kinetics_receptive_field.mk:58-71
 DECODE = dict(name="04_kinetics_receptive_field", layer_size=14, stack_size=1, input_channels=128,
               residual_channels=16, skip_channels=8)
@@ -107,12 +113,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_steps(w, steps, warmup, video=True, B=1):
+def cpu_reference_steps(w, steps, warmup, video=True, B=1, T=None):
     """the reference's CPU implementation of the step (oracle port), all host threads"""
+    T_CLIP = T or globals()["T_CLIP"]
     from oracle import wavenet_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
     shape = orc.Shape(w["layer_size"], w["stack_size"], w["input_channels"], w["residual_channels"], w["skip_channels"])
-    p = {k: v.requires_grad_(True) for k, v in orc.init_params(shape, 0, video=True).items()}
+    p = {k: v.requires_grad_(True) for k, v in orc.init_params(shape, 0, video=video).items()}
     from movenet_b200.mulaw import _encode_formula
     codes = _encode_formula(synth_codes(B, T_CLIP, shape.input_channels, 1234, "cpu"), shape.input_channels)
     audio = torch.zeros(B, shape.input_channels, T_CLIP).scatter_(1, codes.unsqueeze(1), 1.0)
@@ -134,7 +141,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = WORKLOAD
+    w = WORKLOADS[args.workload]
     n, times = cpu_reference_steps(w, max(1, args.steps), max(0, args.warmup), video=w["video"], B=1)
     ms = 1e3 * sum(times) / len(times)
     value = n / (ms / 1e3)
@@ -233,6 +240,23 @@ def layer_roofline(model, audio, video, dtype):
     e = 2 if dtype == "bf16" else 4
     Cc, S = model.residual_channels, model.skip_channels
     vid = video is not None
+    if lib.mvn_kernel_path(C.byref(shape)) == 2:
+        # wide-channel path: the layer is tensor-bound.  Algorithmic flops per audio sample and layer, 2 per MAC,
+        # the dense formulation exactly as the reference computes it: forward 10 C^2 + 2 C S; backward = data + weight gradient
+        # = twice that (the recomputed gate GEMM of the backward is NOT counted: it is this implementation's choice)
+        pk = peaks()
+        n = B * T_CLIP
+        f_fwd = 10 * Cc * Cc + 2 * Cc * S
+
+        def tobj(name, ms, flops, launches, kernels):
+            ach = flops * n / (ms * 1e-3) / 1e12
+            return {"bound": "tensor", "kernel": "%s (%s, %d launches per layer: %s)" % (name, dtype, round(launches), kernels),
+                    "achieved": ach, "peak": pk["bf16_tflops"], "peak_source": pk["source"] + " (cuBLAS bf16, sustained)",
+                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": _ncu_traffic("wide_gemm_kernel"),
+                    "ms_per_launch": ms, "flops_per_sample": flops, "samples_per_launch": n}
+        return (tobj("residual layer backward", ms_b, 2 * f_fwd, n_b,
+                     "3 wide_gemm_kernel (d(gated); gate recompute + derivative; d(x)) + cuBLAS weight gradients + column sums"),
+                tobj("residual layer forward", ms_f, f_fwd, n_f, "2 wide_gemm_kernel (gate; residual + skip)"))
     # algorithmic bytes per audio sample of one layer
     fwd_b = Cc * e + Cc * e + (Cc * e if vid else 0) + 8 * S                 # read x, write x', read ctx, RMW skip_sum
     # backward, algorithmic bytes of any layer-at-a-time backward: read x, the stream gradient D, d(skip) (+ ctx and the
@@ -438,7 +462,7 @@ def run_ours(args):
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    w = WORKLOAD
+    w = WORKLOADS[args.workload]
     B = w["batch_per_gpu"]
     torch.manual_seed(0)
     model = movenet_b200.WaveNet(w["layer_size"], w["stack_size"], w["input_channels"], w["residual_channels"],
@@ -456,7 +480,8 @@ def run_ours(args):
     wave = synth_codes(B, T_CLIP, w["input_channels"], 1234 + rank, dev)
     host_audio = torch.zeros(B, w["input_channels"], T_CLIP).scatter_(
         1, movenet_b200.mulaw._encode_formula(wave, w["input_channels"]).unsqueeze(1), 1.0).pin_memory()
-    host_video = torch.randint(0, 256, (B, 160, 64, 64, 1), generator=torch.Generator().manual_seed(4321 + rank)).float().pin_memory()
+    host_video = torch.randint(0, 256, (B, 160, 64, 64, 1), generator=torch.Generator().manual_seed(4321 + rank)).float().pin_memory() \
+        if w["video"] else torch.zeros(0)
     audio = host_audio.to(dev, non_blocking=True)
     video = host_video.to(dev, non_blocking=True) if w["video"] else None
 
@@ -612,7 +637,7 @@ def run_ours(args):
     # ---- N > 1: data-parallel self-check (recorded in the JSON line) and the sharded decode leg ----
     dp_check = dp_selfcheck(dev, rank, world) if world > 1 else None
     generation = None
-    if world > 1 and not args.no_decode:
+    if world > 1 and not args.no_decode and args.workload == "01":
         generation = decode_bench(dev, rank, world)
 
     if rank != 0:
@@ -651,16 +676,29 @@ def run_ours(args):
                            "input": "forward(one_hot): (B, A, T) fp32, the reference's format"},
             "sustained": sustained,
             "roofline": roof, "roofline_layer_forward": roof_fwd}
+    if args.workload == "03w":
+        A_, Cc, S_, N_ = w["input_channels"], w["residual_channels"], w["skip_channels"], w["layer_size"] * w["stack_size"]
+        F_ = 4 * A_ * Cc + N_ * (10 * Cc * Cc + 2 * Cc * S_) + 2 * S_ * A_ + 2 * A_ * A_         # SURVEY 8(d), audio-only
+        tf = 3 * F_ * value / world / 1e12
+        line["step_tensor_roofline"] = {"flops_per_sample": 3 * F_, "achieved_tflops_per_gpu": tf, "peak": peaks()["bf16_tflops"],
+                                        "frac": tf / peaks()["bf16_tflops"],
+                                        "note": "whole training step on SURVEY 8(d)'s algorithmic 3F flops per sample (fwd + dgrad + wgrad)"}
     if dp_check is not None:
         line["dp_selfcheck"] = dp_check
     if generation is not None:
         line["generation"] = generation
+    if args.workload != "01":
+        args.no_decode = True
     if world == 1:
         if not args.no_cpu_baseline:
-            n, times = cpu_reference_steps(w, 2, 1, video=w["video"], B=1)
+            if args.workload == "01":
+                n, times = cpu_reference_steps(w, 2, 1, video=w["video"], B=1)
+                sample = "1 clip (160000 samples) per step, 1 warm-up + 2 timed steps, torch CPU fp32"
+            else:       # 72 MFLOP per sample: a tenth of a clip keeps the CPU leg within seconds
+                n, times = cpu_reference_steps(w, 1, 1, video=w["video"], B=1, T=16000)
+                sample = "16000 samples (a tenth of a clip) per step, 1 warm-up + 1 timed step, torch CPU fp32"
             cpu = n / (sum(times) / len(times))
-            line["cpu_baseline"] = {"value": cpu, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "1 clip (160000 samples) per step, 1 warm-up + 2 timed steps, torch CPU fp32"}
+            line["cpu_baseline"] = {"value": cpu, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample}
         if not args.no_decode:
             line["generation"] = decode_bench(dev)
     print(json.dumps(line), flush=True)
@@ -678,6 +716,8 @@ def main():
     ap.add_argument("--dtype", default=os.environ.get("MOVENET_B200_DTYPE", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--workload", default="01", choices=sorted(WORKLOADS),
+                    help="01: BASELINE configs[1] (the headline); 03w: the widened scale-up shape (tensor-bound)")
     ap.add_argument("--sustained-steps", type=int, default=1000,
                     help="extra device-resident steps timed separately for the sustained rate (0: skip)")
     args = ap.parse_args()

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "../../include/movenet_b200.h"
 
 static thread_local char g_err[512] = "";
@@ -30,6 +31,9 @@ int mvn_sm_count() {
 int mvn_check_launch(const char* what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     cudaError_t e = cudaGetLastError();
+    // MOVENET_B200_SYNC=1 (debugging): wait for every kernel so that an asynchronous fault is attributed to the launch that caused it
+    static const bool sync_debug = getenv("MOVENET_B200_SYNC") != nullptr;
+    if (e == cudaSuccess && sync_debug) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         mvn_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
         return (int)e;

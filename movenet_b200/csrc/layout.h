@@ -126,7 +126,7 @@ struct ActsLayout {
     size_t x0;        // layer inputs x_0..x_{N-1}, each (B,T,C) act dtype ; x_0 = causal conv output
     size_t x_stride;
     size_t ctx;       // (B,T,C) act dtype (video only)
-    size_t skip;      // (B,Tout,S) fp32
+    size_t skip;      // (B,Tout,S) fp32 ; wide path: (B,T,S), row t = time t (TMA stores cannot start at a negative row)
     size_t a1;        // (B,Tn,A) fp32 : dense_conv.conv1 output (pre-activation)
     size_t enc, u1, u2; // video: (B,160,C) (B,1600,C) (B,16000,C) fp32
     size_t total;
@@ -141,7 +141,7 @@ static inline void acts_layout(const Geo& g, ActsLayout& a) {
     a.x_stride = al256(BT * g.C * g.es);
     a.x0 = take(a.x_stride * g.N);
     a.ctx = g.video ? take(BT * g.C * g.es) : 0;
-    a.skip = take((size_t)g.B * (g.Tout > 0 ? g.Tout : 0) * g.S * 4);
+    a.skip = take((size_t)g.B * (wide_ok(g) ? g.T : (g.Tout > 0 ? g.Tout : 0)) * g.S * 4);
     a.a1 = take((size_t)g.B * (g.Tout > 0 ? g.Tout : 0) * g.A * 4);
     if (g.video) {
         a.enc = take((size_t)g.B * 160 * g.C * 4);

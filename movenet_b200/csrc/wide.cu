@@ -25,7 +25,7 @@ using namespace wide;
 namespace {
 
 // ------------------------------------------------------------------------------------------------ tensor maps (cached)
-struct WMapSlot { const void* ptr; unsigned long long d0, d1, d2; unsigned box1; bool used; CUtensorMap map; };
+struct WMapSlot { const void* ptr; unsigned long long d0, d1, d2; unsigned box0, box1; bool used; CUtensorMap map; };
 constexpr int WMAP_SLOTS = 1024;
 WMapSlot g_wmaps[WMAP_SLOTS];
 std::mutex g_wmaps_mu;
@@ -42,26 +42,29 @@ EncodeTiledFn w_encode_fn() {
     return fn;
 }
 
-// bf16 tensor [d2][d1][d0] (d0 contiguous), box {64, box1, 1}, 128-byte swizzle; d2 == 0: a 2-D matrix [d1][d0]
-int w_map(CUtensorMap* map, const void* ptr, unsigned long long d0, unsigned long long d1, unsigned long long d2, unsigned box1) {
-    const size_t h = ((size_t)(uintptr_t)ptr >> 8) * 0x9E3779B97F4A7C15ull ^ (d0 * 31 + d1 * 131 + d2 * 1313 + box1);
+// tensor [d2][d1][d0] (d0 contiguous), box {box0, box1, 1} with box0 elements = 128 bytes (64 bf16 or 32 fp32), 128-byte
+// swizzle; d2 == 0: a 2-D matrix [d1][d0]
+int w_map(CUtensorMap* map, const void* ptr, unsigned long long d0, unsigned long long d1, unsigned long long d2, unsigned box1,
+          unsigned box0 = 64) {
+    const unsigned es = box0 == 64 ? 2 : 4;
+    const size_t h = ((size_t)(uintptr_t)ptr >> 8) * 0x9E3779B97F4A7C15ull ^ (d0 * 31 + d1 * 131 + d2 * 1313 + box1 * 7 + box0);
     const int i0 = (int)((h >> 17) % WMAP_SLOTS);
     {
         std::lock_guard<std::mutex> lk(g_wmaps_mu);
         for (int p = 0; p < 8; ++p) {
             const WMapSlot& s = g_wmaps[(i0 + p) % WMAP_SLOTS];
-            if (s.used && s.ptr == ptr && s.d0 == d0 && s.d1 == d1 && s.d2 == d2 && s.box1 == box1) { *map = s.map; return 0; }
+            if (s.used && s.ptr == ptr && s.d0 == d0 && s.d1 == d1 && s.d2 == d2 && s.box1 == box1 && s.box0 == box0) { *map = s.map; return 0; }
         }
     }
     EncodeTiledFn fn = w_encode_fn();
     MVN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
-    MVN_REQUIRE((((uintptr_t)ptr) & 15) == 0 && (d0 * 2) % 16 == 0, "wide path: operands must be 16-byte aligned");
+    MVN_REQUIRE((((uintptr_t)ptr) & 15) == 0 && (d0 * es) % 16 == 0, "wide path: operands must be 16-byte aligned");
     const int rank = d2 ? 3 : 2;
     cuuint64_t dims[3] = {d0, d1, d2 ? d2 : 1};
-    cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
-    cuuint32_t box[3] = {64, box1, 1};
+    cuuint64_t strides[2] = {d0 * es, d0 * d1 * es};
+    cuuint32_t box[3] = {box0, box1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, estr,
+    CUresult r = fn(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MVN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -69,7 +72,7 @@ int w_map(CUtensorMap* map, const void* ptr, unsigned long long d0, unsigned lon
     int victim = i0;
     for (int p = 0; p < 8; ++p) if (!g_wmaps[(i0 + p) % WMAP_SLOTS].used) { victim = (i0 + p) % WMAP_SLOTS; break; }
     WMapSlot& s = g_wmaps[victim];
-    s.ptr = ptr; s.d0 = d0; s.d1 = d1; s.d2 = d2; s.box1 = box1; s.map = *map; s.used = true;
+    s.ptr = ptr; s.d0 = d0; s.d1 = d1; s.d2 = d2; s.box1 = box1; s.box0 = box0; s.map = *map; s.used = true;
     return 0;
 }
 
@@ -81,9 +84,11 @@ int pair_mode() {
 }
 
 struct Operand { const void* ptr; int cols; };       // time-major bf16 (B, rows, cols)
+struct Output { const void* ptr; int cols, rows, fp32; };   // TMA-stored result: time-major (B, rows, cols) bf16 or fp32
 
 template <int PAIR, int EPI>
-int launch_t(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB, const Args& a, cudaStream_t st) {
+int launch_t(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB, const CUtensorMap& mO0, const CUtensorMap& mO1,
+             const Args& a, cudaStream_t st) {
     using C = Cfg<PAIR>;
     static MvnSmemAttr attr;
     MVN_CUDA(mvn_ensure_smem(wide_gemm_kernel<PAIR, EPI>, C::SMEM, attr));
@@ -97,12 +102,15 @@ int launch_t(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& 
     at[1].id = cudaLaunchAttributeClusterDimension;
     at[1].val.clusterDim.x = PAIR; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = PAIR == 2 ? 2 : 1;
-    MVN_CUDA(cudaLaunchKernelEx(&cfg, wide_gemm_kernel<PAIR, EPI>, mA0, mA1, mB, a));
-    return mvn_check_launch("wide_gemm");
+    MVN_CUDA(cudaLaunchKernelEx(&cfg, wide_gemm_kernel<PAIR, EPI>, mA0, mA1, mB, mO0, mO1, a));
+    static const char* names[EPI_COUNT] = {"wide_gemm<gate>", "wide_gemm<resid_skip>", "wide_gemm<store>", "wide_gemm<gate_bwd>",
+                                           "wide_gemm<add_store>", "wide_gemm<head1>", "wide_gemm<head2>", "wide_gemm<lrelu_bwd>"};
+    return mvn_check_launch(names[EPI]);
 }
 
 template <int EPI>
-int launch(const Operand& A0, const Operand& A1, const void* W, int w_rows, int w_k, Args& a, int B, int rows, cudaStream_t st) {
+int launch(const Operand& A0, const Operand& A1, const void* W, int w_rows, int w_k, Args& a, int B, int rows, cudaStream_t st,
+           Output O0 = Output{nullptr, 0, 0, 0}, Output O1 = Output{nullptr, 0, 0, 0}) {
     const int pair = pair_mode();
     a.B = B; a.rows = rows;
     a.tiles_per_clip = (rows + BM * pair - 1) / (BM * pair);
@@ -116,7 +124,10 @@ int launch(const Operand& A0, const Operand& A1, const void* W, int w_rows, int 
     const Operand& A1r = A1.ptr ? A1 : A0;
     if ((rc = w_map(&mA1, A1r.ptr, A1r.cols, rows, B, BM))) return rc;
     if ((rc = w_map(&mB, W, w_k, w_rows, 0, NCH / pair))) return rc;
-    return pair == 2 ? launch_t<2, EPI>(mA0, mA1, mB, a, st) : launch_t<1, EPI>(mA0, mA1, mB, a, st);
+    CUtensorMap mO0 = mA0, mO1 = mA0;                 // (unused by the epilogues that store directly)
+    if (O0.ptr && (rc = w_map(&mO0, O0.ptr, O0.cols, O0.rows, B, 32, O0.fp32 ? 32 : 64))) return rc;
+    if (O1.ptr && (rc = w_map(&mO1, O1.ptr, O1.cols, O1.rows, B, 32, O1.fp32 ? 32 : 64))) return rc;
+    return pair == 2 ? launch_t<2, EPI>(mA0, mA1, mB, mO0, mO1, a, st) : launch_t<1, EPI>(mA0, mA1, mB, mO0, mO1, a, st);
 }
 
 Args new_args() { Args a; memset(&a, 0, sizeof(a)); return a; }
@@ -172,16 +183,17 @@ __global__ void wide_pack_kernel(const float* const* __restrict__ ptrs, float* _
     }
 }
 
-// dst (B, rows_dst, cols) bf16 = lrelu(src (B, rows_src, cols) fp32) ; rows >= rows_src are zero
-__global__ void lrelu16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int rows_src, int rows_dst, int cols) {
+// dst (B, rows_dst, cols) bf16: row t = lrelu(src row t + shift) for t < rows_valid, zero beyond; src is (B, src_rows, cols) fp32
+__global__ void lrelu16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int rows_valid, int rows_dst, int cols,
+                               int src_rows, int shift) {
     MVN_PDL_PROLOGUE();
     const long long n8 = (long long)B * rows_dst * cols / 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         const long long e = i * 8, r = e / cols; const int c = (int)(e - r * cols);
         const int b = (int)(r / rows_dst), t = (int)(r - (long long)b * rows_dst);
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (t < rows_src) {
-            const float4* s = (const float4*)(src + ((size_t)b * rows_src + t) * cols + c);
+        if (t < rows_valid) {
+            const float4* s = (const float4*)(src + ((size_t)b * src_rows + t + shift) * cols + c);
             const float4 a = s[0], q = s[1];
             v[0] = mvn_lrelu(a.x); v[1] = mvn_lrelu(a.y); v[2] = mvn_lrelu(a.z); v[3] = mvn_lrelu(a.w);
             v[4] = mvn_lrelu(q.x); v[5] = mvn_lrelu(q.y); v[6] = mvn_lrelu(q.z); v[7] = mvn_lrelu(q.w);
@@ -258,36 +270,52 @@ __global__ void __launch_bounds__(256) head_dz16_kernel(const float* __restrict_
 #define CS_BLOCKS 296
 __global__ void __launch_bounds__(512) colsum1_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int cols, float* __restrict__ partial) {
     MVN_PDL_PROLOGUE();
-    const int c2 = cols / 2, tx = threadIdx.x % c2, ty = threadIdx.x / c2, ny = blockDim.x / c2;
+    // 16-byte loads: cols / 8 threads cover a row, blockDim / (cols / 8) rows are in flight per step, two steps unrolled
+    const int c8 = cols / 8, tx = threadIdx.x % c8, ty = threadIdx.x / c8, ny = blockDim.x / c8;
     const long long per = (rows + gridDim.x - 1) / gridDim.x, r0 = blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
-    float a0 = 0.f, a1 = 0.f;
-    if (ty < ny)
-        for (long long r = r0 + ty; r < r1; r += ny) {
-            const float2 v = unpack_bf16(*(const uint32_t*)(x + r * cols + 2 * tx));
-            a0 += v.x; a1 += v.y;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ty < ny) {
+        long long r = r0 + ty;
+        for (; r + ny < r1; r += 2 * ny) {
+            float v0[8], v1[8];
+            ld_bf16x8(x + r * cols + 8 * tx, v0);
+            ld_bf16x8(x + (r + ny) * cols + 8 * tx, v1);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += v0[e] + v1[e];
         }
-    __shared__ float red[2][512];
-    red[0][threadIdx.x] = a0; red[1][threadIdx.x] = a1;
+        if (r < r1) {
+            float v0[8];
+            ld_bf16x8(x + r * cols + 8 * tx, v0);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += v0[e];
+        }
+    }
+    __shared__ float red[8][512];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[e][threadIdx.x] = acc[e];
     __syncthreads();
     if (ty == 0) {
-        for (int y = 1; y < ny; ++y) { a0 += red[0][y * c2 + tx]; a1 += red[1][y * c2 + tx]; }
-        partial[(size_t)blockIdx.x * cols + 2 * tx] = a0; partial[(size_t)blockIdx.x * cols + 2 * tx + 1] = a1;
+        for (int y = 1; y < ny; ++y)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += red[e][y * c8 + tx];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) partial[(size_t)blockIdx.x * cols + 8 * tx + e] = acc[e];
     }
 }
+// blockDim = (32, RED_SPLIT): 32 columns per block, the partial rows of a column dealt to RED_SPLIT threads and combined in a
+// fixed order (tc::column_sum)
 __global__ void colsum2_kernel(const float* __restrict__ partial, int nblk, int cols, float* __restrict__ out) {
     MVN_PDL_PROLOGUE();
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= cols) return;
-    float acc = 0.f;
-    for (int i = 0; i < nblk; ++i) acc += partial[(size_t)i * cols + c];
-    out[c] = acc;
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const float tot = column_sum(partial, nblk, (size_t)cols, (size_t)c, c < cols);
+    if (threadIdx.y == 0 && c < cols) out[c] = tot;
 }
 
 int colsum(const void* x, long long rows, int cols, float* partial, float* out, cudaStream_t st) {
-    MVN_REQUIRE(cols % 2 == 0 && cols <= 1024, "wide path: column sum width");
+    MVN_REQUIRE(cols % 8 == 0 && cols <= 1024, "wide path: column sum width");
     MVN_CUDA(mvn_launch_pdl(colsum1_kernel, dim3(CS_BLOCKS), dim3(512), (size_t)0, st, (const __nv_bfloat16*)x, rows, cols, partial));
     int rc = mvn_check_launch("colsum1"); if (rc) return rc;
-    MVN_CUDA(mvn_launch_pdl(colsum2_kernel, dim3(mvn_cdiv(cols, 128)), dim3(128), (size_t)0, st, (const float*)partial, (int)CS_BLOCKS, cols, out));
+    MVN_CUDA(mvn_launch_pdl(colsum2_kernel, dim3(mvn_cdiv(cols, 32)), dim3(32, RED_SPLIT), (size_t)0, st, (const float*)partial, (int)CS_BLOCKS, cols, out));
     return mvn_check_launch("colsum2");
 }
 
@@ -361,7 +389,7 @@ int mvn_wide_layer_fwd(const void* x_in, void* x_out, void* gated, float* skip, 
         Args a = new_args();
         seg(a, 0, C, -d); seg(a, 0, C, 0);
         a.N = 2 * C; a.out = gated; a.ld_out = C;
-        if ((rc = launch<EPI_GATE>(Operand{x_in, C}, Operand{nullptr, 0}, lw + P.wWz, 2 * C, 2 * C, a, g.B, g.T, st))) return rc;
+        if ((rc = launch<EPI_GATE>(Operand{x_in, C}, Operand{nullptr, 0}, lw + P.wWz, 2 * C, 2 * C, a, g.B, g.T, st, Output{gated, C, g.T, 0}))) return rc;
     }
     Args a = new_args();
     seg(a, 0, C, 0);
@@ -369,14 +397,16 @@ int mvn_wide_layer_fwd(const void* x_in, void* x_out, void* gated, float* skip, 
     a.bias = lw + P.obrs + (last ? C : 0);
     a.n_resid = last ? 0 : C; a.aux = x_in; a.ld_aux = C; a.out = x_out; a.ld_out = C;
     a.skip = skip; a.S = S; a.Tout = g.Tout; a.RF = g.RF; a.skip_init = l == 0;
-    return launch<EPI_RESID_SKIP>(Operand{gated, C}, Operand{nullptr, 0}, lw + P.wWrs, C + S, C, a, g.B, g.T, st);
+    return launch<EPI_RESID_SKIP>(Operand{gated, C}, Operand{nullptr, 0}, lw + P.wWrs, C + S, C, a, g.B, g.T, st,
+                                  Output{last ? (const void*)gated : (const void*)x_out, C, g.T, 0}, Output{skip, S, g.T, 1});
 }
 
 // DenseConv + drop-last + softmax (movenet/modules.py:133-142, wavenet.py:183-191)
 int mvn_wide_head_fwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, float* a1, float* out, void* l0, void* l1,
                       cudaStream_t st) {
     int rc;
-    MVN_CUDA(mvn_launch_pdl(lrelu16_kernel, dim3(2 * mvn_sm_count()), dim3(256), (size_t)0, st, skip, (__nv_bfloat16*)l0, g.B, g.Tout, g.Tout, g.S));
+    // (skip_sum lives on the T row space in the wide path: row j of the head is row j + RF - 1 of it)
+    MVN_CUDA(mvn_launch_pdl(lrelu16_kernel, dim3(2 * mvn_sm_count()), dim3(256), (size_t)0, st, skip, (__nv_bfloat16*)l0, g.B, g.Tout, g.Tout, g.S, g.T, g.RF - 1));
     if ((rc = mvn_check_launch("lrelu16"))) return rc;
     {
         Args a = new_args();
@@ -407,9 +437,9 @@ int mvn_wide_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, 
                                                   1.f / ((float)g.B * (float)g.Tn));
         if ((rc = mvn_check_launch("head_dz16"))) return rc;
     }
-    MVN_CUDA(mvn_launch_pdl(lrelu16_kernel, dim3(2 * mvn_sm_count()), dim3(256), (size_t)0, st, a1, (__nv_bfloat16*)l1, g.B, g.Tn, g.Tout, g.A));
+    MVN_CUDA(mvn_launch_pdl(lrelu16_kernel, dim3(2 * mvn_sm_count()), dim3(256), (size_t)0, st, a1, (__nv_bfloat16*)l1, g.B, g.Tn, g.Tout, g.A, g.Tn, 0));
     if ((rc = mvn_check_launch("lrelu16"))) return rc;
-    MVN_CUDA(mvn_launch_pdl(lrelu16_kernel, dim3(2 * mvn_sm_count()), dim3(256), (size_t)0, st, skip, (__nv_bfloat16*)l0, g.B, g.Tout, g.Tout, g.S));
+    MVN_CUDA(mvn_launch_pdl(lrelu16_kernel, dim3(2 * mvn_sm_count()), dim3(256), (size_t)0, st, skip, (__nv_bfloat16*)l0, g.B, g.Tout, g.Tout, g.S, g.T, g.RF - 1));
     if ((rc = mvn_check_launch("lrelu16"))) return rc;
     // conv2: dW2p[k][n] = sum_t lrelu(a1)[t][k] dz[t][n] ; db2 = sum_t dz
     if ((rc = gemm_tn(l1, g.A, dzh, g.A, pg + P.w2p, g.A, g.A, g.A, rows, false, st))) return rc;
@@ -427,7 +457,7 @@ int mvn_wide_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, 
     // d(skip_sum) = (d(a1) . W1) * lrelu'(skip_sum), written at row t = j + RF - 1 of the (B, T, S) gradient every layer reads
     Args a = new_args();
     seg(a, 0, g.A, 0);
-    a.N = g.S; a.aux = skip; a.ld_aux = g.S; a.aux_rows = g.Tout; a.out = ds16; a.ld_out = g.S; a.out_rows = g.T; a.out_shift = g.RF - 1; a.Tn = g.Tn;
+    a.N = g.S; a.aux = skip; a.ld_aux = g.S; a.aux_rows = g.T; a.aux_shift = g.RF - 1; a.out = ds16; a.ld_out = g.S; a.out_rows = g.T; a.out_shift = g.RF - 1; a.Tn = g.Tn;
     return launch<EPI_LRELU_BWD>(Operand{da1, g.A}, Operand{nullptr, 0}, packed + P.wH1T, g.S, g.A, a, g.B, g.Tout, st);
 }
 
@@ -450,19 +480,21 @@ int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, cons
         if (dx_next) seg(a, 0, C, 0);
         seg(a, 1, S, 0);
         a.N = C; a.b_kb0 = dx_next ? 0 : C / BK; a.out = dgated; a.ld_out = C;
-        if ((rc = launch<EPI_STORE>(Operand{dx_next ? dx_next : ds16, dx_next ? C : S}, Operand{ds16, S}, lw + P.wWrsT, C, C + S, a, g.B, g.T, st))) return rc;
+        if ((rc = launch<EPI_STORE>(Operand{dx_next ? dx_next : ds16, dx_next ? C : S}, Operand{ds16, S}, lw + P.wWrsT, C, C + S, a, g.B, g.T, st,
+                                    Output{dgated, C, g.T, 0}))) return rc;
     }
     {   // recompute the pre-activations; gated (for the 1x1 convs' weight gradients) and dz = d(gated) * gate'
         Args a = new_args();
         seg(a, 0, C, -d); seg(a, 0, C, 0);
         a.N = 2 * C; a.aux = dgated; a.ld_aux = C; a.out = gated; a.ld_out = C; a.out2 = dz; a.ld_out2 = 2 * C;
-        if ((rc = launch<EPI_GATE_BWD>(Operand{x_in, C}, Operand{nullptr, 0}, lw + P.wWz, 2 * C, 2 * C, a, g.B, g.T, st))) return rc;
+        if ((rc = launch<EPI_GATE_BWD>(Operand{x_in, C}, Operand{nullptr, 0}, lw + P.wWz, 2 * C, 2 * C, a, g.B, g.T, st,
+                                       Output{gated, C, g.T, 0}, Output{dz, 2 * C, g.T, 0}))) return rc;
     }
     {   // d(x_l)[t] = d(x_{l+1})[t] + W1^T dz[t] + W0^T dz[t + d]
         Args a = new_args();
         seg(a, 0, 2 * C, 0); seg(a, 0, 2 * C, d);
         a.N = C; a.aux = dx_next; a.ld_aux = C; a.out = dx_cur; a.ld_out = C;
-        if ((rc = launch<EPI_ADD_STORE>(Operand{dz, 2 * C}, Operand{nullptr, 0}, lw + P.wWzT, C, 4 * C, a, g.B, g.T, st))) return rc;
+        if ((rc = launch<EPI_ADD_STORE>(Operand{dz, 2 * C}, Operand{nullptr, 0}, lw + P.wWzT, C, 4 * C, a, g.B, g.T, st, Output{dx_cur, C, g.T, 0}))) return rc;
     }
     // weight gradients (plain GEMMs, K = time): packed layout oWz[k = tap C + c_in][2 c_out + gate], oWrs[k = c][n]
     const __nv_bfloat16* x = (const __nv_bfloat16*)x_in; const __nv_bfloat16* dzp = (const __nv_bfloat16*)dz;

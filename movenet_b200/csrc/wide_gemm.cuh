@@ -30,13 +30,15 @@ constexpr int NCH = 256;                      // accumulator columns per N chunk
 constexpr int A_STAGE_BYTES = BM * BK * 2;    // 16 KB
 constexpr int N_EPI_WARPS = 8;
 constexpr int N_THREADS = 32 * (2 + N_EPI_WARPS);
+constexpr int OUT_BUF_BYTES = 32 * 128;                           // one staged store: 32 rows x 128 bytes
+constexpr int OUT_STAGE_BYTES = N_EPI_WARPS * 2 * OUT_BUF_BYTES;  // two per epilogue warp: 64 KB
 
 template <int PAIR> struct Cfg {
     static constexpr int B_ROWS = NCH / PAIR;                     // weight rows one CTA stages per k-block
     static constexpr int B_STAGE_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = PAIR == 1 ? 4 : 6;              // 192 KB of operand ring either way
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 2048;      // + barriers, + slack for the 1024-byte alignment
+    static constexpr int STAGES = PAIR == 1 ? 3 : 5;              // 144 / 160 KB of operand ring
+    static constexpr int SMEM = STAGES * STAGE_BYTES + OUT_STAGE_BYTES + 2048;   // + output staging, barriers, alignment slack
 };
 
 enum Epi {
@@ -66,7 +68,7 @@ struct Args {
     float* skip;                              // (B, Tout, S) fp32 running skip sum
     int n_resid, S, Tout, RF, skip_init;      // EPI_RESID_SKIP
     int Tn, logits;                           // EPI_HEAD2: columns the caller receives; raw logits instead of softmax
-    int out_rows, out_shift, aux_rows;        // EPI_LRELU_BWD: rows per clip of `out` / `aux` and the row shift into `out`
+    int out_rows, out_shift, aux_rows, aux_shift;   // EPI_LRELU_BWD: rows per clip of `out` / `aux` and the row shifts into them
 };
 
 // ---- cluster / pair helpers ----------------------------------------------------------------------------------------
@@ -139,16 +141,160 @@ __device__ __forceinline__ void ld_bf16x8(const void* p, float* v) {
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
 
+// ---- epilogue prefetch: the per-row auxiliary operand of an epilogue (x for the residual add, d(gated) for the gate
+// derivative, d(x') for the data gradient) is loaded into registers BEFORE the thread waits for the accumulator, so its DRAM /
+// L2 latency hides under the chunk's MMAs instead of being paid once per 32-column block by the only eight epilogue warps of
+// the SM (measured at C = 256: residual + skip GEMM 187 -> see profiles/, gate-derivative GEMM 195 us before)
+template <int EPI>
+__device__ __forceinline__ void prefetch(const Args& a, uint4* pre, int nc, int n0, int b, int t, bool ok, int half) {
+    const size_t row = (size_t)b * a.rows + t;
+    if (EPI == EPI_GATE_BWD) {
+        const __nv_bfloat16* dg = (const __nv_bfloat16*)a.aux + row * a.ld_aux + (n0 >> 1) + 64 * half;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pre[i] = ok ? *(const uint4*)(dg + 8 * i) : make_uint4(0, 0, 0, 0);
+    } else if (EPI == EPI_RESID_SKIP || EPI == EPI_ADD_STORE) {
+        const int cnt = nc / 64;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int n = n0 + 32 * (half * cnt + u);
+            const bool need = ok && u < cnt && a.aux != nullptr && (EPI == EPI_ADD_STORE || n < a.n_resid);
+            const __nv_bfloat16* x = (const __nv_bfloat16*)a.aux + row * a.ld_aux + n;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pre[4 * u + q] = need ? *(const uint4*)(x + 8 * q) : make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+__device__ __forceinline__ void unpack8(const uint4 u, float* v) {
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+
+// ---- output staging: scattered 16-byte global stores (one row per lane, rows 512+ bytes apart) cap an epilogue at ~1.9 TB/s
+// (measured: the residual + skip GEMM spent 130 of its 180 us on them), so the layer epilogues write their results into a
+// per-warp shared-memory tile in the 128-byte-swizzled layout and hand it to TMA: full-line, asynchronous stores (or fp32
+// add-reductions for the skip sum) that cost the warp one instruction.  Two 4 KB tiles per warp alternate.
+struct Stager {
+    uint32_t base; int cur, lane;
+    __device__ __forceinline__ void begin() {          // the tile about to be written was handed to TMA two stores ago
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+    }
+    __device__ __forceinline__ void put(int k, uint4 v) {     // 16-byte chunk k (0..7) of this lane's 128-byte row
+        const uint32_t addr = base + cur * OUT_BUF_BYTES + lane * 128 + ((k ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    __device__ __forceinline__ void flush(const CUtensorMap* map, int c0, int c1, int c2, bool add) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t src = base + cur * OUT_BUF_BYTES;
+            if (add) asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
+                                  ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+            else asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                              ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        cur ^= 1;
+    }
+};
+__device__ __forceinline__ uint4 pack8(const float* v) {
+    return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+
+// layer epilogues (TMA-stored): r0 = first row of this warp's 32 rows inside the clip; mO0 / mO1: tensor maps of the outputs
+template <int EPI>
+__device__ __forceinline__ void epilogue_tma(const Args& a, const uint4* pre, Stager& sg, const CUtensorMap* mO0, const CUtensorMap* mO1,
+                                             uint32_t tm, int nc, int n0, int b, int r0, int half) {
+    if (EPI == EPI_GATE || EPI == EPI_GATE_BWD) {
+        // chunk = [f of 128 channels | g of the same 128 channels]; this thread: channels 64 * half .. + 63 of them
+        const int ch0 = (n0 >> 1) + 64 * half;
+        uint4 og[8];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            uint32_t f[32], g[32];
+            tmem_ld32(tm + 64 * half + 32 * u, f);
+            tmem_ld32(tm + 128 + 64 * half + 32 * u, g);
+            tmem_ld_wait();
+            if (EPI == EPI_GATE_BWD) sg.begin();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float d[8], o[8], z0[8], z1[8];
+                if (EPI == EPI_GATE_BWD) unpack8(pre[4 * u + q], d);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float fv = __uint_as_float(f[8 * q + e]), gv = __uint_as_float(g[8 * q + e]);
+                    if (a.bias) { fv += a.bias[n0 + 64 * half + 32 * u + 8 * q + e]; gv += a.bias[n0 + 128 + 64 * half + 32 * u + 8 * q + e]; }
+                    const float th = tanh_fast(fv), sgm = sigmoid_fast(gv);
+                    o[e] = th * sgm;
+                    if (EPI == EPI_GATE_BWD) {
+                        const float df = d[e] * sgm * (1.f - th * th), dgv = d[e] * th * sgm * (1.f - sgm);
+                        if (e < 4) { z0[2 * e] = df; z0[2 * e + 1] = dgv; } else { z1[2 * (e - 4)] = df; z1[2 * (e - 4) + 1] = dgv; }
+                    }
+                }
+                og[4 * u + q] = pack8(o);
+                if (EPI == EPI_GATE_BWD) { sg.put(2 * q, pack8(z0)); sg.put(2 * q + 1, pack8(z1)); }
+            }
+            if (EPI == EPI_GATE_BWD) sg.flush(mO1, 2 * ch0 + 64 * u, r0, b, false);      // dz columns interleave (df c, dg c)
+        }
+        sg.begin();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sg.put(k, og[k]);
+        sg.flush(mO0, ch0, r0, b, false);
+        return;
+    }
+    // column-block epilogues: this thread handles columns [half * nc/2, (half + 1) * nc/2) of the chunk, 32 per TMEM load,
+    // 64 bf16 (or 32 fp32) columns per staged store
+    const int cnt = nc / 64;
+#pragma unroll
+    for (int uu = 0; uu < 4; ++uu) {
+        if (uu >= cnt) break;                  // (warp-uniform)
+        const int u = half * cnt + uu;
+        const int n = n0 + 32 * u;
+        const bool is_skip = EPI == EPI_RESID_SKIP && n >= a.n_resid;      // (never straddles a pair: n_resid % 128 == 0)
+        uint32_t v[32];
+        tmem_ld32(tm + 32 * u, v);
+        tmem_ld_wait();
+        if (is_skip) {       // skip_sum (fp32): layer 0 stores, later layers add (TMA reduction, executed by L2: in layer order)
+            sg.begin();
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                sg.put(q, make_uint4(__float_as_uint(__uint_as_float(v[4 * q]) + a.bias[n + 4 * q]), __float_as_uint(__uint_as_float(v[4 * q + 1]) + a.bias[n + 4 * q + 1]),
+                                     __float_as_uint(__uint_as_float(v[4 * q + 2]) + a.bias[n + 4 * q + 2]), __float_as_uint(__uint_as_float(v[4 * q + 3]) + a.bias[n + 4 * q + 3])));
+            sg.flush(mO1, n - a.n_resid, r0, b, !a.skip_init);      // (the wide path keeps skip_sum on the T row space, see wide.cu)
+            continue;
+        }
+        if ((uu & 1) == 0) sg.begin();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * q + e]);
+            if (EPI == EPI_RESID_SKIP) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] += a.bias[n + 8 * q + e];
+            }
+            if (EPI == EPI_RESID_SKIP || (EPI == EPI_ADD_STORE && a.aux)) {
+                float xv[8];
+                unpack8(pre[4 * uu + q], xv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] += xv[e];
+            }
+            sg.put(4 * (uu & 1) + q, pack8(o));
+        }
+        if (uu & 1) sg.flush(mO0, n - 32, r0, b, false);
+    }
+}
+
 // ---- epilogues: one thread owns one time row of the tile; `half` selects which half of the chunk's columns it handles --
 // tm: TMEM address of this thread's lane at the first column of the accumulator chunk; nc: columns of this chunk (128 / 256);
 // n0: first output column of the chunk; b, t: clip and row (row space of the A operand); ok: the row exists.
 template <int EPI>
-__device__ __forceinline__ void epilogue(const Args& a, uint32_t tm, int nc, int n0, int b, int t, bool ok, int half) {
+__device__ __forceinline__ void epilogue(const Args& a, const uint4* pre, uint32_t tm, int nc, int n0, int b, int t, bool ok, int half) {
     const size_t row = (size_t)b * a.rows + t;
     if (EPI == EPI_GATE || EPI == EPI_GATE_BWD) {
         // chunk = [f of 128 channels | g of the same 128 channels]; this thread: channels 64 * half .. + 63 of them
         const int ch0 = (n0 >> 1) + 64 * half;
-#pragma unroll 1
+#pragma unroll
         for (int u = 0; u < 2; ++u) {
             uint32_t f[32], g[32];
             tmem_ld32(tm + 64 * half + 32 * u, f);
@@ -170,13 +316,12 @@ __device__ __forceinline__ void epilogue(const Args& a, uint32_t tm, int nc, int
                     st_bf16x8(dst + 8 * q, o);
                 }
             } else {
-                const __nv_bfloat16* dg = (const __nv_bfloat16*)a.aux + row * a.ld_aux + c;
                 __nv_bfloat16* gated = (__nv_bfloat16*)a.out + row * a.ld_out + c;
                 __nv_bfloat16* dz = (__nv_bfloat16*)a.out2 + row * a.ld_out2 + 2 * c;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float d[8], o[8], z0[8], z1[8];
-                    ld_bf16x8(dg + 8 * q, d);
+                    unpack8(pre[4 * u + q], d);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         float fv = __uint_as_float(f[8 * q + e]), gv = __uint_as_float(g[8 * q + e]);
@@ -232,8 +377,11 @@ __device__ __forceinline__ void epilogue(const Args& a, uint32_t tm, int nc, int
     }
     // column-block epilogues: this thread handles columns [half * nc/2, (half + 1) * nc/2) of the chunk in blocks of 32
     const int js = t - (a.RF - 1);
-#pragma unroll 1
-    for (int u = half * (nc / 64); u < (half + 1) * (nc / 64); ++u) {
+    const int cnt = nc / 64;
+#pragma unroll
+    for (int uu = 0; uu < 4; ++uu) {
+        if (uu >= cnt) break;                  // (warp-uniform)
+        const int u = half * cnt + uu;
         uint32_t v[32];
         tmem_ld32(tm + 32 * u, v);
         tmem_ld_wait();
@@ -241,30 +389,32 @@ __device__ __forceinline__ void epilogue(const Args& a, uint32_t tm, int nc, int
         if (!ok) continue;
         if (EPI == EPI_RESID_SKIP) {
             if (n < a.n_resid) {       // residual: x' = r + br + x(t)     (the block never straddles: n_resid % 128 == 0)
-                const __nv_bfloat16* x = (const __nv_bfloat16*)a.aux + row * a.ld_aux + n;
                 __nv_bfloat16* dst = (__nv_bfloat16*)a.out + row * a.ld_out + n;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float xv[8], o[8];
-                    ld_bf16x8(x + 8 * q, xv);
+                    unpack8(pre[4 * uu + q], xv);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * q + e]) + a.bias[n + 8 * q + e] + xv[e];
                     st_bf16x8(dst + 8 * q, o);
                 }
             } else if (js >= 0 && js < a.Tout) {     // skip: only the last Tout rows of a clip reach the head (modules.py:90-91)
                 const int s0 = n - a.n_resid;
+                // layer 0 stores, every later layer adds with a vector reduction that L2 executes (red.global.add.v4.f32):
+                // no read reaches the SM -- a load-add-store of the same 128-byte line by one thread serialises on the store's
+                // round trip (measured: 2.5 ms instead of 0.1 ms per layer) -- and since each element receives exactly one add per
+                // launch and launches are ordered, the sum is formed in layer order: deterministic
                 float4* dst = (float4*)(a.skip + ((size_t)b * a.Tout + js) * a.S + s0);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    float4 o = make_float4(__uint_as_float(v[4 * q]) + a.bias[n + 4 * q], __uint_as_float(v[4 * q + 1]) + a.bias[n + 4 * q + 1],
-                                           __uint_as_float(v[4 * q + 2]) + a.bias[n + 4 * q + 2], __uint_as_float(v[4 * q + 3]) + a.bias[n + 4 * q + 3]);
-                    if (!a.skip_init) { const float4 p = dst[q]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-                    dst[q] = o;
+                    const float4 o = make_float4(__uint_as_float(v[4 * q]) + a.bias[n + 4 * q], __uint_as_float(v[4 * q + 1]) + a.bias[n + 4 * q + 1],
+                                                 __uint_as_float(v[4 * q + 2]) + a.bias[n + 4 * q + 2], __uint_as_float(v[4 * q + 3]) + a.bias[n + 4 * q + 3]);
+                    if (a.skip_init) dst[q] = o;
+                    else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
                 }
             }
         } else if (EPI == EPI_STORE || EPI == EPI_ADD_STORE) {
             __nv_bfloat16* dst = (__nv_bfloat16*)a.out + row * a.ld_out + n;
-            const __nv_bfloat16* aux = (const __nv_bfloat16*)a.aux + row * a.ld_aux + n;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float o[8];
@@ -272,7 +422,7 @@ __device__ __forceinline__ void epilogue(const Args& a, uint32_t tm, int nc, int
                 for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * q + e]);
                 if (EPI == EPI_ADD_STORE && a.aux) {
                     float xv[8];
-                    ld_bf16x8(aux + 8 * q, xv);
+                    unpack8(pre[4 * uu + q], xv);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] += xv[e];
                 }
@@ -293,7 +443,7 @@ __device__ __forceinline__ void epilogue(const Args& a, uint32_t tm, int nc, int
             }
         } else if (EPI == EPI_LRELU_BWD) {
             if (t >= a.Tn) continue;          // the dropped last column keeps a zero gradient
-            const float* pre = (const float*)a.aux + ((size_t)b * a.aux_rows + t) * a.ld_aux + n;
+            const float* pre = (const float*)a.aux + ((size_t)b * a.aux_rows + t + a.aux_shift) * a.ld_aux + n;
             __nv_bfloat16* dst = (__nv_bfloat16*)a.out + ((size_t)b * a.out_rows + t + a.out_shift) * a.ld_out + n;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -311,11 +461,13 @@ __device__ __forceinline__ void epilogue(const Args& a, uint32_t tm, int nc, int
 template <int PAIR, int EPI>
 __global__ void __launch_bounds__(N_THREADS, 1)
 wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                 const __grid_constant__ CUtensorMap mapB, const Args a) {
+                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO0,
+                 const __grid_constant__ CUtensorMap mapO1, const Args a) {
     using C = Cfg<PAIR>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = (uint64_t*)(smem + C::STAGES * C::STAGE_BYTES);
+    uint8_t* out_stage = smem + C::STAGES * C::STAGE_BYTES;
+    uint64_t* bars = (uint64_t*)(out_stage + OUT_STAGE_BYTES);
     uint64_t* full = bars;                     // [STAGES] operands landed (the pair's barriers live in the leader CTA)
     uint64_t* empty = bars + C::STAGES;        // [STAGES] operands consumed (one per CTA, signalled by the multicast commit)
     uint64_t* tfull = empty + C::STAGES;       // [2] accumulator chunk complete (one per CTA)
@@ -407,6 +559,8 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     } else {
         // ===== epilogue warps: lane quarter = warp % 4 (the TMEM lanes a warp may read), two warps per quarter split the columns
         const int q = warp & 3, half = (warp - 2) >> 2;
+        constexpr bool TMA_OUT = EPI == EPI_GATE || EPI == EPI_GATE_BWD || EPI == EPI_RESID_SKIP || EPI == EPI_STORE || EPI == EPI_ADD_STORE;
+        Stager sg; sg.base = smem_u32(out_stage + (warp - 2) * 2 * OUT_BUF_BYTES); sg.cur = 0; sg.lane = lane;
         uint32_t acc = 0;
         uint32_t te[2];
         for (int s = 0; s < 2; ++s) { te[s] = smem_u32(tempty + s); if (PAIR == 2) te[s] = mapa_rank(te[s], 0); }
@@ -417,14 +571,18 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             for (int j = 0; j < nchunks; ++j, ++acc) {
                 const int nc = a.N - NCH * j < NCH ? a.N - NCH * j : NCH;
                 const uint32_t buf = acc & 1;
+                uint4 pre[16];
+                prefetch<EPI>(a, pre, nc, NCH * j, b, t, ok, half);
                 mbar_wait_addr(smem_u32(tfull + buf), (acc >> 1) & 1);
                 tc_fence_after();
-                epilogue<EPI>(a, tmem + ((uint32_t)(32 * q) << 16) + buf * NCH, nc, NCH * j, b, t, ok, half);
+                if constexpr (TMA_OUT) epilogue_tma<EPI>(a, pre, sg, &mapO0, &mapO1, tmem + ((uint32_t)(32 * q) << 16) + buf * NCH, nc, NCH * j, b, t0 + 32 * q, half);
+                else epilogue<EPI>(a, pre, tmem + ((uint32_t)(32 * q) << 16) + buf * NCH, nc, NCH * j, b, t, ok, half);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { if (PAIR == 1) mbar_arrive(tempty + buf); else mbar_arrive_remote(te[buf]); }
             }
         }
+        if (TMA_OUT && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the staged tiles are read before the CTA exits
     }
     tc_fence_before();
     if (PAIR == 1) __syncthreads(); else cluster_sync_all();
