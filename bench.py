@@ -256,7 +256,8 @@ def layer_roofline(model, audio, video, dtype):
                     "ms_per_launch": ms, "flops_per_sample": flops, "samples_per_launch": n}
         return (tobj("residual layer backward", ms_b, 2 * f_fwd, n_b,
                      "3 wide_gemm_kernel (d(gated); gate recompute + derivative; d(x)) + cuBLAS weight gradients + column sums"),
-                tobj("residual layer forward", ms_f, f_fwd, n_f, "2 wide_gemm_kernel (gate; residual + skip)"))
+                # (the skip 1x1 convs of all layers run as ONE GEMM after the stack: their 2 C S flops are not in this stage)
+                tobj("residual layer forward", ms_f, 10 * Cc * Cc, n_f, "2 wide_gemm_kernel (gate; residual)"))
     # algorithmic bytes per audio sample of one layer
     fwd_b = Cc * e + Cc * e + (Cc * e if vid else 0) + 8 * S                 # read x, write x', read ctx, RMW skip_sum
     # backward, algorithmic bytes of any layer-at-a-time backward: read x, the stream gradient D, d(skip) (+ ctx and the

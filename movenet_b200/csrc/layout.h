@@ -73,10 +73,12 @@ struct PackedLayout {
     size_t tc_up01[2];          // ... and of the first two levels
     // wide path: bf16 K-major matrices [rows][K] streamed by TMA (offsets in fp32 elements; per layer relative to the layer base)
     size_t wWz;                 // [2C][2C]   rows in chunks of 256 = (filter | gate) of 128 channels ; K = tap0 C | tap1 C
-    size_t wWrs;                // [C+S][C]   rows: residual C | skip S
+    size_t wWrs;                // [C][2C]    [Wr | I]: x' = [gated | x] . this^T + br -- the residual add rides through the tensor core (exact)
     size_t wWrsT;               // [C][C+S]   d(gated) = [d(x') | d(skip)] . this^T
     size_t wWzT;                // [C][4C]    d(x) = [dz(t) | dz(t+d)] . this^T ; dz columns interleaved (df c, dg c)
     size_t wH1, wH2, wH2T, wH1T;// head: [A][S], [A][A], [A][A] (transposed), [S][A]
+    size_t wWsAll;              // [S][N C]   every layer's skip 1x1 conv side by side: skip_sum = [gated_0 | gated_1 | ...] . this^T
+    size_t wbsum;               // [S] fp32   sum over layers of the skip biases
     size_t total;               // elements
 };
 
@@ -95,7 +97,7 @@ static inline void packed_layout(const Geo& g, PackedLayout& p) {
     p.oTc = take(g.C == 64 ? MVN_TC_IMG_BYTES / 4 : 0) - l0;
     const bool wide = wide_ok(g);
     p.wWz = take(wide ? 2 * C * 2 * C / 2 : 0) - l0;
-    p.wWrs = take(wide ? (C + S) * C / 2 : 0) - l0;
+    p.wWrs = take(wide ? C * 2 * C / 2 : 0) - l0;
     p.wWrsT = take(wide ? C * (C + S) / 2 : 0) - l0;
     p.wWzT = take(wide ? C * 4 * C / 2 : 0) - l0;
     p.layer0 = l0;
@@ -106,6 +108,7 @@ static inline void packed_layout(const Geo& g, PackedLayout& p) {
     p.tc_head = take((A == 64 || A == 128) ? A * A / 2 : 0);
     p.wH1 = take(wide ? A * S / 2 : 0); p.wH2 = take(wide ? A * A / 2 : 0);
     p.wH2T = take(wide ? A * A / 2 : 0); p.wH1T = take(wide ? S * A / 2 : 0);
+    p.wWsAll = take(wide ? S * (size_t)g.N * C / 2 : 0); p.wbsum = take(wide ? S : 0);
     if (g.video) {
         p.wv = take((size_t)4096 * g.Cin * C); p.bv = take(C);
         for (int i = 0; i < 3; ++i) { p.wt[i] = take(C * 10 * C); p.bt[i] = take(10 * C); p.wtT[i] = take(10 * C * C); }
@@ -129,6 +132,7 @@ struct ActsLayout {
     size_t skip;      // (B,Tout,S) fp32 ; wide path: (B,T,S), row t = time t (TMA stores cannot start at a negative row)
     size_t a1;        // (B,Tn,A) fp32 : dense_conv.conv1 output (pre-activation)
     size_t enc, u1, u2; // video: (B,160,C) (B,1600,C) (B,16000,C) fp32
+    size_t w_gated;   // wide path: (B,T,N C) bf16, the gated activations of every layer side by side (layer l: columns l C ..)
     size_t total;
 };
 
@@ -148,6 +152,7 @@ static inline void acts_layout(const Geo& g, ActsLayout& a) {
         a.u1 = take((size_t)g.B * 1600 * g.C * 4);
         a.u2 = take((size_t)g.B * 16000 * g.C * 4);
     } else a.enc = a.u1 = a.u2 = 0;
+    a.w_gated = take(wide_ok(g) ? BT * g.N * g.C * 2 : 0);
     a.total = o;
 }
 
@@ -169,6 +174,7 @@ struct ScratchLayout {
     size_t w_ds16;    // (B,T,S) bf16    : d(skip) on the T row space (zero outside the last Tn rows of a clip)
     size_t w_oh16;    // (B,T,A) bf16    : the audio (one-hot) as a GEMM operand of the input conv's weight gradient
     size_t w_colsum;  // fp32 partial column sums (bias gradients)
+    size_t w_wgpart;  // fp32 partial weight-gradient blocks, one [256][512] per CTA pair (wide_wgrad.cuh)
     size_t total;
 };
 
@@ -199,5 +205,6 @@ static inline void scratch_layout(const Geo& g, ScratchLayout& w) {
     w.w_ds16 = take(wide ? BT * g.S * 2 : 0);
     w.w_oh16 = take(wide ? BT * g.A * 2 : 0);
     w.w_colsum = take(wide ? (size_t)1024 * 1024 * 4 : 0);
+    w.w_wgpart = take(wide ? (size_t)80 * 256 * 512 * 4 : 0);
     w.total = o;
 }

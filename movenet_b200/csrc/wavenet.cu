@@ -487,7 +487,7 @@ static int layer_fwd(const Ctx& c, int l) {
     float* skip = (float*)(c.acts + c.AL.skip);
     void* ctx = g.video ? c.acts + c.AL.ctx : nullptr;
     if (mvn_wide_supported(g))
-        return mvn_wide_layer_fwd(c.x(l), last ? nullptr : c.x(l + 1), c.scratch + c.SL.gated, skip, c.packed, c.P, g, l, c.st);
+        return mvn_wide_layer_fwd(c.x(l), last ? nullptr : c.x(l + 1), c.acts + c.AL.w_gated, c.packed, c.P, g, l, c.st);
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
         return mvn_tc_layer_fwd(c.x(l), ctx, last ? nullptr : c.x(l + 1), skip, lw, c.P, g, l, c.st);
     }
@@ -516,6 +516,10 @@ static int head_fwd(const Ctx& c, float* out) {
     if (g.Tn <= 0) return 0;
     const long long rows = (long long)g.B * g.Tn;
     float* skip = (float*)(c.acts + c.AL.skip); float* a1 = (float*)(c.acts + c.AL.a1); float* z = (float*)(c.scratch + c.SL.z);
+    if (mvn_wide_supported(g)) {      // the skip 1x1 convs of all layers: one GEMM over the layer-concatenated gated activations
+        int rc2 = mvn_wide_skip_fwd(c.acts + c.AL.w_gated, skip, c.packed, c.P, g, c.st);
+        if (rc2) return rc2;
+    }
     if (mvn_wide_supported(g))
         return mvn_wide_head_fwd(c.packed, c.P, g, skip, a1, out, c.scratch + c.SL.w_l0, c.scratch + c.SL.z, c.st);
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S))
@@ -761,8 +765,8 @@ extern "C" int mvn_layer_bwd(const mvn_shape_t* s, const void* packed, int layer
     if (mvn_wide_supported(g)) {
         float* cs = (float*)(c.scratch + c.SL.w_colsum);
         return mvn_wide_layer_bwd(c.x(layer), layer + 1 < g.N ? c.scratch + c.SL.dxa : nullptr, c.scratch + c.SL.dxb, c.scratch + c.SL.w_ds16,
-                                  c.scratch + c.SL.dgated, c.scratch + c.SL.gated, c.scratch + c.SL.dz, cs + 512 * 1024, c.packed, pg, cs,
-                                  c.P, g, layer, c.st);
+                                  c.scratch + c.SL.dgated, c.acts + c.AL.w_gated, c.scratch + c.SL.dz, cs + 512 * 1024, c.packed, pg, cs,
+                                  (float*)(c.scratch + c.SL.w_wgpart), c.P, g, layer, c.st);
     }
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
         const size_t nb = (size_t)g.B * g.T * g.C * g.es;
@@ -823,8 +827,8 @@ static int backward_impl(const mvn_shape_t* s, const void* packed, const float* 
         void* bufs[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};
         const void* dx_next = nullptr; int cur = 0;
         for (int l = g.N - 1; l >= 0; --l) {
-            if ((rc = mvn_wide_layer_bwd(c.x(l), dx_next, bufs[cur], ds16, c.scratch + c.SL.dgated, c.scratch + c.SL.gated, c.scratch + c.SL.dz,
-                                         dbs, c.packed, pg, cs, c.P, g, l, c.st))) return rc;
+            if ((rc = mvn_wide_layer_bwd(c.x(l), dx_next, bufs[cur], ds16, c.scratch + c.SL.dgated, c.acts + c.AL.w_gated, c.scratch + c.SL.dz,
+                                         dbs, c.packed, pg, cs, (float*)(c.scratch + c.SL.w_wgpart), c.P, g, l, c.st))) return rc;
             dx_next = bufs[cur]; cur ^= 1;
         }
         return mvn_wide_input_bwd(audio, (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), dx_next,

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <mutex>
 #include "wide_gemm.cuh"
+#include "wide_wgrad.cuh"
 #include "layer_tc.h"
 
 using namespace wide;
@@ -154,10 +155,13 @@ __global__ void wide_pack_kernel(const float* const* __restrict__ ptrs, float* _
             const int tap = k / C, cin = k - tap * C;
             Wz[i] = __float2bfloat16((gate ? wg : wf)[((size_t)ch * C + cin) * 2 + tap]);
         }
-        for (int i = i0; i < (C + S) * C; i += stride) {      // Wrs[n][k] ; WrsT[k][n]
+        for (int i = i0; i < C * 2 * C; i += stride) {        // [Wr | I][n][k]: k < C the residual 1x1 conv, k >= C the identity
+            const int n = i / (2 * C), k = i - n * 2 * C;
+            Wrs[i] = __float2bfloat16(k < C ? wr[(size_t)n * C + k] : (k - C == n ? 1.f : 0.f));
+        }
+        for (int i = i0; i < (C + S) * C; i += stride) {      // WrsT[k][n] = [Wr | Ws][n][k]
             const int n = i / C, k = i - n * C;
             const float v = n < C ? wr[(size_t)n * C + k] : ws[(size_t)(n - C) * C + k];
-            Wrs[i] = __float2bfloat16(v);
             WrsT[(size_t)k * (C + S) + n] = __float2bfloat16(v);
         }
         for (int i = i0; i < C * 4 * C; i += stride) {        // WzT[c][k]: k = seg * 2C + 2 o + gate ; seg 0 <-> tap 1 (dz(t)), seg 1 <-> tap 0 (dz(t+d))
@@ -179,6 +183,17 @@ __global__ void wide_pack_kernel(const float* const* __restrict__ ptrs, float* _
             const int n = i / A, k = i - n * A;
             H2[i] = __float2bfloat16(w2[i]);
             H2T[(size_t)k * A + n] = __float2bfloat16(w2[i]);
+        }
+        __nv_bfloat16* WsAll = (__nv_bfloat16*)(packed + P.wWsAll);
+        const int KA = N * C;
+        for (int i = i0; i < S * KA; i += stride) {           // WsAll[s][l C + c] = conv_skip_l.weight[s][c]
+            const int sidx = i / KA, k = i - sidx * KA, l2 = k / C, c = k - l2 * C;
+            WsAll[i] = __float2bfloat16(ptrs[MVN_PARAM_LAYER(l2, 8)][(size_t)sidx * C + c]);
+        }
+        for (int i = i0; i < S; i += stride) {                // fixed order: deterministic
+            float acc = 0.f;
+            for (int l2 = 0; l2 < N; ++l2) acc += ptrs[MVN_PARAM_LAYER(l2, 9)][i];
+            packed[P.wbsum + i] = acc;
         }
     }
 }
@@ -367,6 +382,39 @@ int gemm_tn(const void* A, int lda, const void* Bm, int ldb, float* Cm, int ldc,
     return 0;
 }
 
+// ---- tcgen05 weight gradients (wide_wgrad.cuh) -------------------------------------------------------------------------
+// MOVENET_B200_WIDE_WGRAD=cublas sends them to cuBLAS instead (also the route for channel counts that are not multiples of 256)
+bool wgrad_tc_ok(const Geo& g) {
+    const char* e = getenv("MOVENET_B200_WIDE_WGRAD");
+    return !(e && e[0] == 'c') && g.C % 256 == 0 && g.S % 256 == 0 && mvn_sm_count() >= 2;
+}
+
+struct WgTensors { const void* ptr[5]; int cols[5]; };     // time-major bf16 (B, T, cols)
+
+int wgrad_launch(WgArgs& a, const WgTensors& t, const Geo& g, float* partial, cudaStream_t st) {
+    const int pairs = mvn_sm_count() / 2;
+    MVN_REQUIRE(a.n_jobs >= 1 && a.n_jobs <= WG_MAX_JOBS && a.n_jobs <= pairs && pairs <= 80, "wide path: weight-gradient job count");
+    a.B = g.B; a.T = g.T; a.kb_per_clip = (g.T + 63) / 64; a.n_splits = pairs / a.n_jobs; a.partial = partial;
+    CUtensorMap m[5];
+    int rc;
+    for (int i = 0; i < 5; ++i)
+        if ((rc = w_map(&m[i], t.ptr[i] ? t.ptr[i] : t.ptr[0], t.ptr[i] ? t.cols[i] : t.cols[0], g.T, g.B, 64))) return rc;
+    static MvnSmemAttr attr;
+    MVN_CUDA(mvn_ensure_smem(wide_wgrad_kernel, WG_SMEM, attr));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * a.n_jobs * a.n_splits); cfg.blockDim = dim3(N_THREADS); cfg.dynamicSmemBytes = WG_SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = 2; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    MVN_CUDA(cudaLaunchKernelEx(&cfg, wide_wgrad_kernel, m[0], m[1], m[2], m[3], m[4], a));
+    if ((rc = mvn_check_launch("wide_wgrad"))) return rc;
+    MVN_CUDA(mvn_launch_pdl(wide_wgrad_reduce_kernel, dim3(64, a.n_jobs), dim3(256), (size_t)0, st, a));
+    return mvn_check_launch("wide_wgrad_reduce");
+}
+
 }  // namespace
 
 // ================================================================================================ public (library-internal) API
@@ -378,27 +426,42 @@ int mvn_wide_pack(const float* const* param_ptrs_dev, float* packed, const Packe
     return mvn_check_launch("wide_pack");
 }
 
-// GatedResidualConv1d.forward (movenet/modules.py:67-93): F1 + F2
-int mvn_wide_layer_fwd(const void* x_in, void* x_out, void* gated, float* skip, const float* packed, const PackedLayout& P, const Geo& g,
+// GatedResidualConv1d.forward (movenet/modules.py:67-93): F1 (gate) + F2 (residual 1x1 conv + x).  The gated activations of
+// every layer are kept side by side in one (B, T, N C) tensor: the skip 1x1 convs of ALL layers then run as ONE GEMM with
+// K = N C whose fp32 result is written once (mvn_wide_skip_fwd) instead of a 2 KB-per-row read-modify-write of skip_sum per
+// layer (which made the per-layer residual + skip GEMM HBM-bound), and the backward reads them for the 1x1 convs' weight
+// gradients instead of re-writing them.  The last layer's residual output is discarded (modules.py:125-130): no F2.
+int mvn_wide_layer_fwd(const void* x_in, void* x_out, void* gated_all, const float* packed, const PackedLayout& P, const Geo& g,
                        int l, cudaStream_t st) {
-    const int C = g.C, S = g.S, d = g.dil[l];
+    const int C = g.C, d = g.dil[l], NC = g.N * C;
     const float* lw = packed + P.layer0 + (size_t)l * P.layer_stride;
-    const bool last = x_out == nullptr;
     int rc;
     {
         Args a = new_args();
         seg(a, 0, C, -d); seg(a, 0, C, 0);
-        a.N = 2 * C; a.out = gated; a.ld_out = C;
-        if ((rc = launch<EPI_GATE>(Operand{x_in, C}, Operand{nullptr, 0}, lw + P.wWz, 2 * C, 2 * C, a, g.B, g.T, st, Output{gated, C, g.T, 0}))) return rc;
+        a.N = 2 * C; a.out = gated_all; a.out_c0 = l * C;
+        if ((rc = launch<EPI_GATE>(Operand{x_in, C}, Operand{nullptr, 0}, lw + P.wWz, 2 * C, 2 * C, a, g.B, g.T, st, Output{gated_all, NC, g.T, 0}))) return rc;
     }
+    if (!x_out) return 0;
+    // x' = Wr gated + br + x as ONE product [gated | x] . [Wr | I]^T: the residual add costs C^2 more MACs on the tensor pipe
+    // (bf16 x times 1.0, accumulated in fp32: exact) instead of a per-row global load in the epilogue, which with only
+    // K = C of MMA work per tile to hide it made this GEMM 74 us instead of 50 (measured)
     Args a = new_args();
-    seg(a, 0, C, 0);
-    a.N = last ? S : C + S; a.b_row0 = last ? C : 0;
-    a.bias = lw + P.obrs + (last ? C : 0);
-    a.n_resid = last ? 0 : C; a.aux = x_in; a.ld_aux = C; a.out = x_out; a.ld_out = C;
-    a.skip = skip; a.S = S; a.Tout = g.Tout; a.RF = g.RF; a.skip_init = l == 0;
-    return launch<EPI_RESID_SKIP>(Operand{gated, C}, Operand{nullptr, 0}, lw + P.wWrs, C + S, C, a, g.B, g.T, st,
-                                  Output{last ? (const void*)gated : (const void*)x_out, C, g.T, 0}, Output{skip, S, g.T, 1});
+    seg(a, 0, C, 0, l * C); seg(a, 1, C, 0);
+    a.N = C; a.bias = lw + P.obrs; a.n_resid = C; a.aux = nullptr; a.out = x_out; a.ld_out = C;
+    return launch<EPI_RESID_SKIP>(Operand{gated_all, NC}, Operand{x_in, C}, lw + P.wWrs, C, 2 * C, a, g.B, g.T, st,
+                                  Output{x_out, C, g.T, 0}, Output{x_out, C, g.T, 0});
+}
+
+// skip_sum = sum_l (Ws_l gated_l + bs_l) (movenet/modules.py:90-91, wavenet.py:181) as one GEMM over the layer-concatenated
+// gated activations; fp32, on the T row space (row t = time t; the head reads rows >= RF - 1)
+int mvn_wide_skip_fwd(const void* gated_all, float* skip, const float* packed, const PackedLayout& P, const Geo& g, cudaStream_t st) {
+    const int NC = g.N * g.C;
+    Args a = new_args();
+    seg(a, 0, NC, 0);
+    a.N = g.S; a.bias = packed + P.wbsum; a.n_resid = 0; a.skip_init = 1; a.S = g.S; a.RF = g.RF; a.Tout = g.Tout;
+    return launch<EPI_RESID_SKIP>(Operand{gated_all, NC}, Operand{nullptr, 0}, packed + P.wWsAll, g.S, NC, a, g.B, g.T, st,
+                                  Output{gated_all, NC, g.T, 0}, Output{skip, g.S, g.T, 1});
 }
 
 // DenseConv + drop-last + softmax (movenet/modules.py:133-142, wavenet.py:183-191)
@@ -467,10 +530,11 @@ int mvn_wide_skip_bias_grad(const void* ds16, const Geo& g, float* colsum_ws, fl
 }
 
 // backward of one layer: dx_next = d(x_{l+1}) (null for the last layer, whose residual output is discarded), dx_cur = d(x_l)
-int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, const void* ds16, void* dgated, void* gated, void* dz,
-                       const float* dbs, const float* packed, float* pg, float* colsum_ws, const PackedLayout& P, const Geo& g, int l,
-                       cudaStream_t st) {
-    const int C = g.C, S = g.S, d = g.dil[l];
+int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, const void* ds16, void* dgated, const void* gated_all, void* dz,
+                       const float* dbs, const float* packed, float* pg, float* colsum_ws, float* wgpart, const PackedLayout& P, const Geo& g,
+                       int l, cudaStream_t st) {
+    const int C = g.C, S = g.S, d = g.dil[l], NC = g.N * C;
+    const __nv_bfloat16* gated = (const __nv_bfloat16*)gated_all + (size_t)l * C;       // layer l's columns, row stride N C
     const float* lw = packed + P.layer0 + (size_t)l * P.layer_stride;
     float* lg = pg + P.layer0 + (size_t)l * P.layer_stride;
     const long long rows = (long long)g.B * g.T;
@@ -483,12 +547,12 @@ int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, cons
         if ((rc = launch<EPI_STORE>(Operand{dx_next ? dx_next : ds16, dx_next ? C : S}, Operand{ds16, S}, lw + P.wWrsT, C, C + S, a, g.B, g.T, st,
                                     Output{dgated, C, g.T, 0}))) return rc;
     }
-    {   // recompute the pre-activations; gated (for the 1x1 convs' weight gradients) and dz = d(gated) * gate'
+    {   // recompute the pre-activations: dz = d(gated) * gate' (the gated activations themselves were kept by the forward)
         Args a = new_args();
         seg(a, 0, C, -d); seg(a, 0, C, 0);
-        a.N = 2 * C; a.aux = dgated; a.ld_aux = C; a.out = gated; a.ld_out = C; a.out2 = dz; a.ld_out2 = 2 * C;
+        a.N = 2 * C; a.aux = dgated; a.ld_aux = C; a.out = nullptr; a.out2 = dz; a.ld_out2 = 2 * C;
         if ((rc = launch<EPI_GATE_BWD>(Operand{x_in, C}, Operand{nullptr, 0}, lw + P.wWz, 2 * C, 2 * C, a, g.B, g.T, st,
-                                       Output{gated, C, g.T, 0}, Output{dz, 2 * C, g.T, 0}))) return rc;
+                                       Output{dz, 2 * C, g.T, 0}, Output{dz, 2 * C, g.T, 0}))) return rc;
     }
     {   // d(x_l)[t] = d(x_{l+1})[t] + W1^T dz[t] + W0^T dz[t + d]
         Args a = new_args();
@@ -496,17 +560,45 @@ int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, cons
         a.N = C; a.aux = dx_next; a.ld_aux = C; a.out = dx_cur; a.ld_out = C;
         if ((rc = launch<EPI_ADD_STORE>(Operand{dz, 2 * C}, Operand{nullptr, 0}, lw + P.wWzT, C, 4 * C, a, g.B, g.T, st, Output{dx_cur, C, g.T, 0}))) return rc;
     }
-    // weight gradients (plain GEMMs, K = time): packed layout oWz[k = tap C + c_in][2 c_out + gate], oWrs[k = c][n]
+    // weight gradients (K = time): packed layout oWz[k = tap C + c_in][2 c_out + gate], oWrs[k = c][n]
+    if (wgrad_tc_ok(g)) {
+        WgArgs w; memset(&w, 0, sizeof(w));
+        WgTensors t = {{x_in, gated_all, dz, dx_next, ds16}, {C, NC, 2 * C, C, S}};
+        for (int tap = 0; tap < 2; ++tap)               // dWz[tap C + c_in][n] = sum_t x[t - (1 - tap) d][c_in] dz[t][n]
+            for (int mt = 0; mt < C / 256; ++mt)
+                for (int n0 = 0; n0 < 2 * C; n0 += 512) {
+                    WgJob& j = w.job[w.n_jobs++];
+                    j.a_map = 0; j.a_c0 = 256 * mt; j.a_shift = tap == 0 ? -d : 0;
+                    j.n = 2 * C - n0 < 512 ? 2 * C - n0 : 512;
+                    j.b_map[0] = j.b_map[1] = 2; j.b_c0[0] = n0; j.b_c0[1] = 0; j.b_n0 = j.n;
+                    j.dst = lg + P.oWz + (size_t)(tap * C + 256 * mt) * 2 * C + n0; j.ld = 2 * C;
+                }
+        const int nx = dx_next ? C : 0, ntot = nx + S;  // d[Wr | Ws][c][n] = sum_t gated[t][c] [d(x') | d(skip)][t][n]
+        for (int mt = 0; mt < C / 256; ++mt)
+            for (int n0 = 0; n0 < ntot; n0 += 512) {
+                WgJob& j = w.job[w.n_jobs++];
+                j.a_map = 1; j.a_c0 = l * C + 256 * mt; j.a_shift = 0;
+                j.n = ntot - n0 < 512 ? ntot - n0 : 512;
+                j.b_map[0] = 3; j.b_map[1] = 4;
+                j.b_n0 = nx - n0 < 0 ? 0 : (nx - n0 > j.n ? j.n : nx - n0);
+                j.b_c0[0] = n0; j.b_c0[1] = n0 > nx ? n0 - nx : 0;
+                j.dst = lg + P.oWrs + (size_t)(256 * mt) * (C + S) + (C - nx) + n0; j.ld = C + S;
+            }
+        if ((rc = wgrad_launch(w, t, g, wgpart, st))) return rc;
+        if (dx_next && (rc = colsum(dx_next, rows, C, colsum_ws, lg + P.obrs, st))) return rc;
+        MVN_CUDA(cudaMemcpyAsync(lg + P.obrs + C, dbs, (size_t)S * 4, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
     const __nv_bfloat16* x = (const __nv_bfloat16*)x_in; const __nv_bfloat16* dzp = (const __nv_bfloat16*)dz;
     for (int b = 0; b < g.B; ++b)       // tap 0 pairs x[t - d] with dz[t]: per clip
         if ((rc = gemm_tn(x + (size_t)b * g.T * C, C, dzp + ((size_t)b * g.T + d) * 2 * C, 2 * C, lg + P.oWz, 2 * C, C, 2 * C, g.T - d, b > 0, st))) return rc;
     if (g.T - d <= 0) MVN_CUDA(cudaMemsetAsync(lg + P.oWz, 0, (size_t)C * 2 * C * 4, st));
     if ((rc = gemm_tn(x, C, dzp, 2 * C, lg + P.oWz + (size_t)C * 2 * C, 2 * C, C, 2 * C, rows, false, st))) return rc;
     if (dx_next) {
-        if ((rc = gemm_tn(gated, C, dx_next, C, lg + P.oWrs, C + S, C, C, rows, false, st))) return rc;
+        if ((rc = gemm_tn(gated, NC, dx_next, C, lg + P.oWrs, C + S, C, C, rows, false, st))) return rc;
         if ((rc = colsum(dx_next, rows, C, colsum_ws, lg + P.obrs, st))) return rc;
     }
-    if ((rc = gemm_tn(gated, C, ds16, S, lg + P.oWrs + C, C + S, C, S, rows, false, st))) return rc;
+    if ((rc = gemm_tn(gated, NC, ds16, S, lg + P.oWrs + C, C + S, C, S, rows, false, st))) return rc;
     MVN_CUDA(cudaMemcpyAsync(lg + P.obrs + C, dbs, (size_t)S * 4, cudaMemcpyDeviceToDevice, st));
     return 0;
 }

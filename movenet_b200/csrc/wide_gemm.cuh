@@ -64,6 +64,7 @@ struct Args {
     const float* bias;                        // [N] fp32 or null
     const void* aux; int ld_aux;              // per-row auxiliary input (bf16 or fp32), row space = the A operand's
     void* out; int ld_out;                    // primary output
+    int out_c0;                               // first column of the primary output inside its (wider) tensor
     void* out2; int ld_out2;                  // secondary output
     float* skip;                              // (B, Tout, S) fp32 running skip sum
     int n_resid, S, Tout, RF, skip_init;      // EPI_RESID_SKIP
@@ -236,10 +237,12 @@ __device__ __forceinline__ void epilogue_tma(const Args& a, const uint4* pre, St
             }
             if (EPI == EPI_GATE_BWD) sg.flush(mO1, 2 * ch0 + 64 * u, r0, b, false);      // dz columns interleave (df c, dg c)
         }
-        sg.begin();
+        if (EPI == EPI_GATE || a.out != nullptr) {
+            sg.begin();
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sg.put(k, og[k]);
-        sg.flush(mO0, ch0, r0, b, false);
+            for (int k = 0; k < 8; ++k) sg.put(k, og[k]);
+            sg.flush(mO0, a.out_c0 + ch0, r0, b, false);
+        }
         return;
     }
     // column-block epilogues: this thread handles columns [half * nc/2, (half + 1) * nc/2) of the chunk, 32 per TMEM load,
