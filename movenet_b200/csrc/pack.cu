@@ -7,7 +7,7 @@
 // one block row per layer: blockIdx.y = layer.  ptrs = device table in state_dict order.
 // C: physical channels of the packed layout, Cl <= C: channels of the reference tensors (the rest is zero padding)
 __global__ void pack_layer_kernel(const float* const* __restrict__ ptrs, float* __restrict__ packed,
-                                  PackedLayout P, int C, int Cl, int S, int Kz, int video) {
+                                  PackedLayout P, int C, int Cl, int S, int Kz, int video, int biases_only) {
     MVN_PDL_PROLOGUE();
     const int l = blockIdx.y;
     const float* const* lp = ptrs + MVN_PARAM_LAYER(l, 0);
@@ -16,8 +16,10 @@ __global__ void pack_layer_kernel(const float* const* __restrict__ ptrs, float* 
     float* base = packed + P.layer0 + (size_t)l * P.layer_stride;
     const int nWz = Kz * 2 * C, nbz = 2 * C, nWrs = C * (C + S), nbrs = C + S;
     const int total = nWz + nbz + nWrs + nbrs;
+    // (the wide tensor-core path reads its own bf16 matrices, wide.cu: only the bias vectors of this layout are used there)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int j = i;
+        if (biases_only && (j < nWz || (j >= nWz + nbz && j < nWz + nbz + nWrs))) continue;
         if (j < nWz) {
             const int k = j / (2 * C), n = j % (2 * C), c = n >> 1, gate = n & 1;
             float v = 0.f;
@@ -187,7 +189,7 @@ extern "C" int mvn_pack_weights(const mvn_shape_t* s, const void* const* param_p
     cudaStream_t st = (cudaStream_t)stream;
     const float* const* ptrs = (const float* const*)param_ptrs_dev;
     dim3 gl(8, g.N);
-    MVN_CUDA(mvn_launch_pdl(pack_layer_kernel, dim3(gl), dim3(256), (size_t)(0), st, ptrs, (float*)packed, P, g.C, g.Cl, g.S, g.Kz, g.video));
+    MVN_CUDA(mvn_launch_pdl(pack_layer_kernel, dim3(gl), dim3(256), (size_t)(0), st, ptrs, (float*)packed, P, g.C, g.Cl, g.S, g.Kz, g.video, (int)mvn_wide_supported(g)));
     dim3 gm(128, 6);
     MVN_CUDA(mvn_launch_pdl(pack_misc_kernel, dim3(gm), dim3(256), (size_t)(0), st, ptrs, (float*)packed, P, g.A, g.C, g.Cl, g.S, g.Cin, g.N, g.video));
     int rc = mvn_check_launch("pack_weights");

@@ -411,7 +411,7 @@ int wgrad_launch(WgArgs& a, const WgTensors& t, const Geo& g, float* partial, cu
     cfg.attrs = at; cfg.numAttrs = 2;
     MVN_CUDA(cudaLaunchKernelEx(&cfg, wide_wgrad_kernel, m[0], m[1], m[2], m[3], m[4], a));
     if ((rc = mvn_check_launch("wide_wgrad"))) return rc;
-    MVN_CUDA(mvn_launch_pdl(wide_wgrad_reduce_kernel, dim3(64, a.n_jobs), dim3(256), (size_t)0, st, a));
+    MVN_CUDA(mvn_launch_pdl(wide_wgrad_reduce_kernel, dim3(128, a.n_jobs), dim3(256), (size_t)0, st, a));
     return mvn_check_launch("wide_wgrad_reduce");
 }
 
@@ -554,11 +554,23 @@ int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, cons
         if ((rc = launch<EPI_GATE_BWD>(Operand{x_in, C}, Operand{nullptr, 0}, lw + P.wWz, 2 * C, 2 * C, a, g.B, g.T, st,
                                        Output{dz, 2 * C, g.T, 0}, Output{dz, 2 * C, g.T, 0}))) return rc;
     }
+    // the residual-bias gradient of layer l - 1 is the column sum of this layer's d(x): taken inside the d(x) GEMM's epilogue
+    // from the staged output tiles when a tile holds every column (C <= 256), else by a separate pass over d(x_{l+1})
+    const bool fused_colsum = C <= NCH;
     {   // d(x_l)[t] = d(x_{l+1})[t] + W1^T dz[t] + W0^T dz[t + d]
         Args a = new_args();
         seg(a, 0, 2 * C, 0); seg(a, 0, 2 * C, d);
         a.N = C; a.aux = dx_next; a.ld_aux = C; a.out = dx_cur; a.ld_out = C;
+        a.csum = (fused_colsum && l > 0) ? colsum_ws : nullptr;
         if ((rc = launch<EPI_ADD_STORE>(Operand{dz, 2 * C}, Operand{nullptr, 0}, lw + P.wWzT, C, 4 * C, a, g.B, g.T, st, Output{dx_cur, C, g.T, 0}))) return rc;
+        if (a.csum) {
+            const int pair = pair_mode();
+            int clusters = mvn_sm_count() / pair; if (clusters > a.n_tiles) clusters = a.n_tiles;
+            float* lg_prev = pg + P.layer0 + (size_t)(l - 1) * P.layer_stride;
+            MVN_CUDA(mvn_launch_pdl(colsum2_kernel, dim3(mvn_cdiv(C, 32)), dim3(32, RED_SPLIT), (size_t)0, st, (const float*)colsum_ws,
+                                    clusters * pair * 4, C, lg_prev + P.obrs));
+            if ((rc = mvn_check_launch("colsum2"))) return rc;
+        }
     }
     // weight gradients (K = time): packed layout oWz[k = tap C + c_in][2 c_out + gate], oWrs[k = c][n]
     if (wgrad_tc_ok(g)) {
@@ -585,7 +597,7 @@ int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, cons
                 j.dst = lg + P.oWrs + (size_t)(256 * mt) * (C + S) + (C - nx) + n0; j.ld = C + S;
             }
         if ((rc = wgrad_launch(w, t, g, wgpart, st))) return rc;
-        if (dx_next && (rc = colsum(dx_next, rows, C, colsum_ws, lg + P.obrs, st))) return rc;
+        if (dx_next && !fused_colsum && (rc = colsum(dx_next, rows, C, colsum_ws, lg + P.obrs, st))) return rc;
         MVN_CUDA(cudaMemcpyAsync(lg + P.obrs + C, dbs, (size_t)S * 4, cudaMemcpyDeviceToDevice, st));
         return 0;
     }
@@ -596,7 +608,7 @@ int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, cons
     if ((rc = gemm_tn(x, C, dzp, 2 * C, lg + P.oWz + (size_t)C * 2 * C, 2 * C, C, 2 * C, rows, false, st))) return rc;
     if (dx_next) {
         if ((rc = gemm_tn(gated, NC, dx_next, C, lg + P.oWrs, C + S, C, C, rows, false, st))) return rc;
-        if ((rc = colsum(dx_next, rows, C, colsum_ws, lg + P.obrs, st))) return rc;
+        if (!fused_colsum && (rc = colsum(dx_next, rows, C, colsum_ws, lg + P.obrs, st))) return rc;
     }
     if ((rc = gemm_tn(gated, NC, ds16, S, lg + P.oWrs + C, C + S, C, S, rows, false, st))) return rc;
     MVN_CUDA(cudaMemcpyAsync(lg + P.obrs + C, dbs, (size_t)S * 4, cudaMemcpyDeviceToDevice, st));

@@ -65,6 +65,7 @@ struct Args {
     const void* aux; int ld_aux;              // per-row auxiliary input (bf16 or fp32), row space = the A operand's
     void* out; int ld_out;                    // primary output
     int out_c0;                               // first column of the primary output inside its (wider) tensor
+    float* csum;                              // EPI_ADD_STORE, N <= 256: per-(CTA, lane quarter) column sums of the stored tile rows
     void* out2; int ld_out2;                  // secondary output
     float* skip;                              // (B, Tout, S) fp32 running skip sum
     int n_resid, S, Tout, RF, skip_init;      // EPI_RESID_SKIP
@@ -132,7 +133,10 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
     } while (!done);
 }
 
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+// (volatile: under register pressure the compiler otherwise RE-EXECUTES a non-volatile tanh asm at every use of its result
+// instead of keeping it in a register -- ncu showed 4 MUFU.TANH per channel instead of 2 in the gate-derivative epilogue)
+__device__ __forceinline__ float tanh_v(float x) { float y; asm volatile("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_v(0.5f * x), 0.5f); }
 __device__ __forceinline__ void st_bf16x8(void* p, const float* v) {
     *(uint4*)p = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
@@ -176,13 +180,26 @@ __device__ __forceinline__ void unpack8(const uint4 u, float* v) {
 // add-reductions for the skip sum) that cost the warp one instruction.  Two 4 KB tiles per warp alternate.
 struct Stager {
     uint32_t base; int cur, lane;
+    uint32_t row, sw;        // this lane's row inside tile 0, and its swizzle term (lane & 7) << 4
+    __device__ __forceinline__ void init(uint32_t b, int l) { base = b; cur = 0; lane = l; row = b + l * 128; sw = (uint32_t)(l & 7) << 4; }
     __device__ __forceinline__ void begin() {          // the tile about to be written was handed to TMA two stores ago
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
     }
     __device__ __forceinline__ void put(int k, uint4 v) {     // 16-byte chunk k (0..7) of this lane's 128-byte row
-        const uint32_t addr = base + cur * OUT_BUF_BYTES + lane * 128 + ((k ^ (lane & 7)) << 4);
+        const uint32_t addr = row + cur * OUT_BUF_BYTES + (((uint32_t)k << 4) ^ sw);
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    // column sums over the 32 rows of the tile that was flushed last (bf16, 64 columns): lane L owns columns 2L, 2L + 1
+    __device__ __forceinline__ void colsum_last(float& s0, float& s1) {
+        const uint32_t t0 = base + (cur ^ 1) * OUT_BUF_BYTES + (lane & 3) * 4;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            uint32_t w;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(t0 + r * 128 + (((lane >> 2) ^ (r & 7)) << 4)) : "memory");
+            const float2 v = unpack_bf16(w);
+            s0 += v.x; s1 += v.y;
+        }
     }
     __device__ __forceinline__ void flush(const CUtensorMap* map, int c0, int c1, int c2, bool add) {
         fence_proxy_async();
@@ -205,7 +222,7 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 // layer epilogues (TMA-stored): r0 = first row of this warp's 32 rows inside the clip; mO0 / mO1: tensor maps of the outputs
 template <int EPI>
 __device__ __forceinline__ void epilogue_tma(const Args& a, const uint4* pre, Stager& sg, const CUtensorMap* mO0, const CUtensorMap* mO1,
-                                             uint32_t tm, int nc, int n0, int b, int r0, int half) {
+                                             uint32_t tm, int nc, int n0, int b, int r0, int half, float* cs) {
     if (EPI == EPI_GATE || EPI == EPI_GATE_BWD) {
         // chunk = [f of 128 channels | g of the same 128 channels]; this thread: channels 64 * half .. + 63 of them
         const int ch0 = (n0 >> 1) + 64 * half;
@@ -217,27 +234,33 @@ __device__ __forceinline__ void epilogue_tma(const Args& a, const uint4* pre, St
             tmem_ld32(tm + 128 + 64 * half + 32 * u, g);
             tmem_ld_wait();
             if (EPI == EPI_GATE_BWD) sg.begin();
+            if (a.bias) {      // (context-conv biases; null on the audio-only wide path -- one uniform branch, not 64 predicated loads)
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    f[e] = __float_as_uint(__uint_as_float(f[e]) + a.bias[n0 + 64 * half + 32 * u + e]);
+                    g[e] = __float_as_uint(__uint_as_float(g[e]) + a.bias[n0 + 128 + 64 * half + 32 * u + e]);
+                }
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float d[8], o[8], z0[8], z1[8];
                 if (EPI == EPI_GATE_BWD) unpack8(pre[4 * u + q], d);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    float fv = __uint_as_float(f[8 * q + e]), gv = __uint_as_float(g[8 * q + e]);
-                    if (a.bias) { fv += a.bias[n0 + 64 * half + 32 * u + 8 * q + e]; gv += a.bias[n0 + 128 + 64 * half + 32 * u + 8 * q + e]; }
-                    const float th = tanh_fast(fv), sgm = sigmoid_fast(gv);
+                    const float th = tanh_v(__uint_as_float(f[8 * q + e])), sgm = sigmoid_fast(__uint_as_float(g[8 * q + e]));
                     o[e] = th * sgm;
                     if (EPI == EPI_GATE_BWD) {
-                        const float df = d[e] * sgm * (1.f - th * th), dgv = d[e] * th * sgm * (1.f - sgm);
+                        // d tanh(f) sigma(g) / df = sigma (1 - tanh^2) ; / dg = tanh sigma (1 - sigma)
+                        const float df = (d[e] * sgm) * fmaf(-th, th, 1.f), dgv = (d[e] * o[e]) * (1.f - sgm);
                         if (e < 4) { z0[2 * e] = df; z0[2 * e + 1] = dgv; } else { z1[2 * (e - 4)] = df; z1[2 * (e - 4) + 1] = dgv; }
                     }
                 }
-                og[4 * u + q] = pack8(o);
+                if (EPI == EPI_GATE) og[4 * u + q] = pack8(o);       // (the backward reads the gated activations the forward kept)
                 if (EPI == EPI_GATE_BWD) { sg.put(2 * q, pack8(z0)); sg.put(2 * q + 1, pack8(z1)); }
             }
             if (EPI == EPI_GATE_BWD) sg.flush(mO1, 2 * ch0 + 64 * u, r0, b, false);      // dz columns interleave (df c, dg c)
         }
-        if (EPI == EPI_GATE || a.out != nullptr) {
+        if (EPI == EPI_GATE) {
             sg.begin();
 #pragma unroll
             for (int k = 0; k < 8; ++k) sg.put(k, og[k]);
@@ -284,7 +307,11 @@ __device__ __forceinline__ void epilogue_tma(const Args& a, const uint4* pre, St
             }
             sg.put(4 * (uu & 1) + q, pack8(o));
         }
-        if (uu & 1) sg.flush(mO0, n - 32, r0, b, false);
+        if (uu & 1) {
+            sg.flush(mO0, n - 32, r0, b, false);
+            // bias gradient of the layer below = column sums of this d(x): taken from the staged tile (rows past the clip are zero)
+            if (EPI == EPI_ADD_STORE && a.csum) sg.colsum_last(cs[uu & 2], cs[(uu & 2) + 1]);
+        }
     }
 }
 
@@ -563,8 +590,9 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
         // ===== epilogue warps: lane quarter = warp % 4 (the TMEM lanes a warp may read), two warps per quarter split the columns
         const int q = warp & 3, half = (warp - 2) >> 2;
         constexpr bool TMA_OUT = EPI == EPI_GATE || EPI == EPI_GATE_BWD || EPI == EPI_RESID_SKIP || EPI == EPI_STORE || EPI == EPI_ADD_STORE;
-        Stager sg; sg.base = smem_u32(out_stage + (warp - 2) * 2 * OUT_BUF_BYTES); sg.cur = 0; sg.lane = lane;
+        Stager sg; sg.init(smem_u32(out_stage + (warp - 2) * 2 * OUT_BUF_BYTES), lane);
         uint32_t acc = 0;
+        float cs[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t te[2];
         for (int s = 0; s < 2; ++s) { te[s] = smem_u32(tempty + s); if (PAIR == 2) te[s] = mapa_rank(te[s], 0); }
         for (int tile = cluster; tile < a.n_tiles; tile += n_clusters) {
@@ -578,7 +606,7 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 prefetch<EPI>(a, pre, nc, NCH * j, b, t, ok, half);
                 mbar_wait_addr(smem_u32(tfull + buf), (acc >> 1) & 1);
                 tc_fence_after();
-                if constexpr (TMA_OUT) epilogue_tma<EPI>(a, pre, sg, &mapO0, &mapO1, tmem + ((uint32_t)(32 * q) << 16) + buf * NCH, nc, NCH * j, b, t0 + 32 * q, half);
+                if constexpr (TMA_OUT) epilogue_tma<EPI>(a, pre, sg, &mapO0, &mapO1, tmem + ((uint32_t)(32 * q) << 16) + buf * NCH, nc, NCH * j, b, t0 + 32 * q, half, cs);
                 else epilogue<EPI>(a, pre, tmem + ((uint32_t)(32 * q) << 16) + buf * NCH, nc, NCH * j, b, t, ok, half);
                 tc_fence_before();
                 __syncwarp();
@@ -586,6 +614,11 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
             }
         }
         if (TMA_OUT && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the staged tiles are read before the CTA exits
+        if (EPI == EPI_ADD_STORE && a.csum) {      // one partial row per (CTA, lane quarter); N <= 256: a single chunk per tile
+            float* dst = a.csum + ((size_t)blockIdx.x * 4 + q) * a.N + (a.N / 2) * half + 2 * lane;
+            dst[0] = cs[0]; dst[1] = cs[1];
+            if (a.N > 128) { dst[64] = cs[2]; dst[65] = cs[3]; }
+        }
     }
     tc_fence_before();
     if (PAIR == 1) __syncthreads(); else cluster_sync_all();

@@ -141,20 +141,29 @@ wide_wgrad_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
     }
 }
 
-// dst[m][n] = sum over the job's time slices, in slice order; one thread per output element (coalesced over n)
-__global__ void wide_wgrad_reduce_kernel(const WgArgs a) {
+// dst[m][n] = sum over the job's time slices, in slice order; one thread per four consecutive n (16-byte loads, eight slices in
+// flight), 128 blocks per job: the 38 MB of partials of a layer stream at HBM speed
+__global__ void __launch_bounds__(256) wide_wgrad_reduce_kernel(const WgArgs a) {
     MVN_PDL_PROLOGUE();
     const int j = blockIdx.y;
     const WgJob job = a.job[j];
     const int total_kb = a.B * a.kb_per_clip, per = (total_kb + a.n_splits - 1) / a.n_splits;
     const int used = (total_kb + per - 1) / per;            // slices that had work
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 256 * job.n; i += gridDim.x * blockDim.x) {
-        const int m = i / job.n, n = i - m * job.n;
-        const float* p = a.partial + ((size_t)j * a.n_splits * 256 + m) * 512 + n;
-        float acc = 0.f;
-#pragma unroll 4
-        for (int s = 0; s < used; ++s) acc += p[(size_t)s * 256 * 512];
-        job.dst[(size_t)m * job.ld + n] = acc;
+    const int n4 = job.n / 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 256 * n4; i += gridDim.x * blockDim.x) {
+        const int m = i / n4, n = (i - m * n4) * 4;
+        const float4* p = (const float4*)(a.partial + ((size_t)j * a.n_splits * 256 + m) * 512 + n);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int s = 0;
+        for (; s + 8 <= used; s += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = p[(size_t)(s + e) * (256 * 512 / 4)];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { acc.x += v[e].x; acc.y += v[e].y; acc.z += v[e].z; acc.w += v[e].w; }
+        }
+        for (; s < used; ++s) { const float4 v = p[(size_t)s * (256 * 512 / 4)]; acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+        *(float4*)(job.dst + (size_t)m * job.ld + n) = acc;
     }
 }
 
