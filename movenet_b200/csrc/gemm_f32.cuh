@@ -42,8 +42,10 @@ struct RowGemmArgs {
     void* out2; int out2_dtype, ldo2, out2_T, out2_shift;
     const void* aux; int aux_dtype, lda, aux_T, aux_shift;
     int split;
-    int allow_ksplit; // caller opt-in (the result then depends on the order of fp32 atomics: not bit-reproducible)
-    int ksplit;      // > 1: the K chunks are dealt round-robin to gridDim.z CTAs which atomically add into a ZEROED fp32 output (EPI_STORE only)
+    int allow_ksplit; // caller opt-in: few rows, long contraction (needs `ws`)
+    int ksplit;      // > 1: the K chunks are dealt round-robin to gridDim.z CTAs, each writes its partial [rows][N] into `ws`;
+                     // a second kernel adds the partials in a fixed order (deterministic: no fp32 atomics) (EPI_STORE only)
+    float* ws; size_t ws_floats;
 };
 
 struct TnSrc {
@@ -58,6 +60,9 @@ struct TnGemmArgs {
     TnSrc src[MVN_MAX_SRC];
     const void* q; int q_dtype, ldq, q_T, q_shift;
     float* dbias;
+    // row slices (gridDim.z) write partial products into ws[z][ktot + 1][N] (the last row: the bias sums); a second kernel adds
+    // them to the outputs in slice order -- deterministic, no fp32 atomics
+    float* ws; size_t ws_floats; int ktot;
 };
 
 __device__ __forceinline__ long long mvn_map_row(long long b, int t, int T, int shift) {
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(256) row_gemm_kernel(const RowGemmArgs a) {
         switch (a.epi) {
         case EPI_STORE:
             if (orow >= 0) {
-                if (a.ksplit > 1) { for (int j = 0; j < 4; ++j) if (nb + j < a.N) atomicAdd((float*)a.out + orow * a.ldo + nb + j, v[j]); }
+                if (a.ksplit > 1) { for (int j = 0; j < 4; ++j) if (nb + j < a.N) a.ws[((size_t)blockIdx.z * a.rows + orow) * a.N + nb + j] = v[j]; }
                 else for (int j = 0; j < 4; ++j) if (nb + j < a.N) mvn_st(a.out, a.out_dtype, orow * a.ldo + nb + j, v[j]);
             }
             break;
@@ -251,6 +256,17 @@ __global__ void __launch_bounds__(256) row_gemm_kernel(const RowGemmArgs a) {
     }
 }
 
+// out[r][n] = sum_z ws[z][r][n], z ascending
+__global__ void ksplit_reduce_kernel(const float* __restrict__ ws, int ks, long long rows, int N, float* __restrict__ out, int ldo) {
+    MVN_PDL_PROLOGUE();
+    const long long n_el = rows * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (long long)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int z = 0; z < ks; ++z) acc += ws[(size_t)z * n_el + i];
+        out[(i / N) * ldo + i % N] = acc;
+    }
+}
+
 static inline int mvn_row_gemm(RowGemmArgs a, cudaStream_t st) {
     if (a.rows <= 0 || a.N <= 0) return 0;
     dim3 grid(mvn_cdiv(a.rows, RG_BM), mvn_cdiv(a.N, RG_BN));
@@ -258,19 +274,19 @@ static inline int mvn_row_gemm(RowGemmArgs a, cudaStream_t st) {
     int ktot = 0;
     for (int s = 0; s < a.nsrc; ++s) ktot += a.src[s].K;
     a.ksplit = 1;
-    if (a.allow_ksplit && a.epi == EPI_STORE && a.out_dtype == MVN_F32 && a.out_shift == 0 && a.out_T == a.Trow && grid.x * grid.y < 148 && ktot >= 256) {
+    if (a.allow_ksplit && a.ws && a.epi == EPI_STORE && a.out_dtype == MVN_F32 && a.out_shift == 0 && a.out_T == a.Trow && grid.x * grid.y < 148 && ktot >= 256) {
         int ks = (2 * 148) / (grid.x * grid.y);
         if (ks > ktot / (2 * RG_BK)) ks = ktot / (2 * RG_BK);
-        if (ks > 1) {
-            a.ksplit = ks;
-            if (cudaMemset2DAsync(a.out, (size_t)a.ldo * 4, 0, (size_t)a.N * 4, (size_t)a.rows, st) != cudaSuccess) {
-                mvn_set_error("row_gemm: clearing the split-K output failed"); return -1;
-            }
-            grid.z = ks;
-        }
+        while (ks > 1 && (size_t)ks * a.rows * a.N > a.ws_floats) --ks;
+        if (ks > 1) { a.ksplit = ks; grid.z = ks; }
     }
     MVN_CUDA(mvn_launch_pdl(row_gemm_kernel, dim3(grid), dim3(256), (size_t)(0), st, a));
-    return mvn_check_launch("row_gemm");
+    int rc = mvn_check_launch("row_gemm");
+    if (rc || a.ksplit <= 1) return rc;
+    const long long n_el = a.rows * a.N;
+    MVN_CUDA(mvn_launch_pdl(ksplit_reduce_kernel, dim3(mvn_cdiv(n_el, 256) < 592 ? mvn_cdiv(n_el, 256) : 592), dim3(256), (size_t)(0), st,
+                            (const float*)a.ws, a.ksplit, a.rows, a.N, (float*)a.out, a.ldo));
+    return mvn_check_launch("ksplit_reduce");
 }
 
 #define TN_BK 64
@@ -335,6 +351,9 @@ __global__ void __launch_bounds__(256) tn_gemm_kernel(const TnGemmArgs a) {
             }
         }
     }
+    int koff = 0;
+    for (int i = 0; i < s; ++i) koff += a.src[i].K;
+    float* part = a.ws + (size_t)blockIdx.z * (a.ktot + 1) * a.N;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int k = k0 + ty * 4 + i;
@@ -342,15 +361,34 @@ __global__ void __launch_bounds__(256) tn_gemm_kernel(const TnGemmArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
-            if (n < a.N && acc[i][j] != 0.f) atomicAdd(S.out + (long long)k * S.ldo + n, acc[i][j]);
+            if (n < a.N) part[(size_t)(koff + k) * a.N + n] = acc[i][j];
         }
     }
     if (do_bias) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
-            if (n < a.N) atomicAdd(a.dbias + n, qsum[j]);
+            if (n < a.N) part[(size_t)a.ktot * a.N + n] = qsum[j];
         }
+    }
+}
+
+// out_s[k][n] += sum_z ws[z][koff_s + k][n] ; dbias[n] += sum_z ws[z][ktot][n]   (z ascending: a fixed order)
+__global__ void tn_reduce_kernel(const TnGemmArgs a, int nz) {
+    MVN_PDL_PROLOGUE();
+    const long long n_el = (long long)(a.ktot + 1) * a.N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (long long)gridDim.x * blockDim.x) {
+        const int kk = (int)(i / a.N), n = (int)(i - (long long)kk * a.N);
+        float* dst;
+        if (kk == a.ktot) { if (!a.dbias) continue; dst = a.dbias + n; }
+        else {
+            int s = 0, k = kk;
+            while (k >= a.src[s].K) { k -= a.src[s].K; ++s; }
+            dst = a.src[s].out + (long long)k * a.src[s].ldo + n;
+        }
+        float acc = 0.f;
+        for (int z = 0; z < nz; ++z) acc += a.ws[(size_t)z * n_el + i];
+        *dst += acc;
     }
 }
 
@@ -365,8 +403,18 @@ static inline int mvn_tn_gemm(TnGemmArgs a, cudaStream_t st) {
     long long rpc = (a.rows + want - 1) / want;
     if (rpc < 64) rpc = 64;
     rpc = ((rpc + TN_BR - 1) / TN_BR) * TN_BR;
+    a.ktot = 0;
+    for (int s = 0; s < a.nsrc; ++s) a.ktot += a.src[s].K;
+    if (!a.ws) { mvn_set_error("tn_gemm: no workspace for the partial products"); return -1; }
+    const size_t per_slice = (size_t)(a.ktot + 1) * a.N;
+    while (mvn_cdiv(a.rows, rpc) > 1 && (size_t)mvn_cdiv(a.rows, rpc) * per_slice > a.ws_floats) rpc *= 2;   // fewer, longer row slices
+    if ((size_t)mvn_cdiv(a.rows, rpc) * per_slice > a.ws_floats) { mvn_set_error("tn_gemm: workspace too small"); return -1; }
     a.rows_per_cta = rpc;
     dim3 grid(ktiles, ntiles, mvn_cdiv(a.rows, rpc));
     MVN_CUDA(mvn_launch_pdl(tn_gemm_kernel, dim3(grid), dim3(256), (size_t)(0), st, a));
-    return mvn_check_launch("tn_gemm");
+    int rc = mvn_check_launch("tn_gemm");
+    if (rc) return rc;
+    MVN_CUDA(mvn_launch_pdl(tn_reduce_kernel, dim3(mvn_cdiv((long long)per_slice, 256) < 592 ? mvn_cdiv((long long)per_slice, 256) : 592), dim3(256),
+                            (size_t)(0), st, a, (int)grid.z));
+    return mvn_check_launch("tn_reduce");
 }

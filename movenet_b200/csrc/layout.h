@@ -5,6 +5,7 @@
 #include "../../include/movenet_b200.h"
 
 #define MVN_MAX_LAYERS 256
+#define MVN_DET_WS_FLOATS (8u << 20)     // 32 MB
 // tensor-core weight image of one layer: 3 Wz chunks + [Wr|Ws] (<=128 rows) of 16 KB each, + 1 KB of biases
 #define MVN_TC_IMG_BYTES (4 * 16384 + 1024)
 
@@ -169,6 +170,7 @@ struct ScratchLayout {
     size_t du2, du1, denc;
     size_t tc_partial; // per-CTA partial weight gradients of the head / input / upsampler tensor-core kernels
     size_t tc_layer_partial; // ... and of the layer backward kernel, one slot per layer (reduced together at the end)
+    size_t det_ws;    // fp32 partial products of the exact-mode split reductions (added in a fixed order: no atomics)
     // wide path (wide.cu)
     size_t w_l0;      // (B,Tout,S) bf16 : lrelu(skip_sum), the head's first A operand
     size_t w_ds16;    // (B,T,S) bf16    : d(skip) on the T row space (zero outside the last Tn rows of a clip)
@@ -200,6 +202,7 @@ static inline void scratch_layout(const Geo& g, ScratchLayout& w) {
     // slot 0: head / input / upsampler partials (used one after the other); slots 1..N: one per layer
     w.tc_partial = take(g.adt == MVN_DTYPE_BF16 && (g.C == 64 || g.A == 64 || g.A == 128) ? (size_t)2 * 148 * (128 * 256 + 256) * 4 : 0);
     w.tc_layer_partial = take(g.adt == MVN_DTYPE_BF16 && g.C == 64 ? (size_t)g.N * 148 * (128 * 256 + 256) * 4 : 0);
+    w.det_ws = take((size_t)MVN_DET_WS_FLOATS * 4);
     const bool wide = wide_ok(g);
     w.w_l0 = take(wide ? BTo * g.S * 2 : 0);
     w.w_ds16 = take(wide ? BT * g.S * 2 : 0);

@@ -164,17 +164,12 @@ __global__ void __launch_bounds__(256) input_fwd_smem_kernel(const float* __rest
 }
 
 // Conv3d with a (1,64,64) kernel over 160-frame clips: [B*160 rows] x [4096*Cin] . [4096*Cin x C].  Few rows, long K:
-// split K over CTAs (8 rows x all channels x one K slice each) and add the slices with fp32 atomics into the
-// bias-initialised output.
-__global__ void video_conv_init_kernel(float* __restrict__ enc, const float* __restrict__ bias, int rows, int C) {
-    MVN_PDL_PROLOGUE();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < rows * C) enc[i] = bias[i % C];
-}
+// split K over CTAs (32 rows x all channels x one K slice each); every slice writes its partial product, a second kernel adds
+// the slices in a fixed order on top of the bias (deterministic: no fp32 atomics).
 #define VC_ROWS 32
 #define VC_K 256
 __global__ void __launch_bounds__(256) video_conv_kernel(const float* __restrict__ video, const float* __restrict__ wv,
-                                                         float* __restrict__ enc, int rows, int K, int C) {
+                                                         float* __restrict__ part, int rows, int K, int C) {
     MVN_PDL_PROLOGUE();
     __shared__ float xs[VC_ROWS][VC_K];
     const int r0 = blockIdx.x * VC_ROWS, k0 = blockIdx.y * VC_K;
@@ -197,55 +192,53 @@ __global__ void __launch_bounds__(256) video_conv_kernel(const float* __restrict
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            if (r0 + 8 * grp + i < rows) atomicAdd(enc + (size_t)(r0 + 8 * grp + i) * C + c, acc[i]);
+            if (r0 + 8 * grp + i < rows) part[((size_t)blockIdx.y * rows + r0 + 8 * grp + i) * C + c] = acc[i];
     }
 }
+__global__ void video_conv_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ enc,
+                                         int rows, int C, int nk) {
+    MVN_PDL_PROLOGUE();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * C) return;
+    float acc = bias[i % C];
+    for (int k = 0; k < nk; ++k) acc += part[(size_t)k * rows * C + i];
+    enc[i] = acc;
+}
 
-// dWin[tap][a][c] += sum_t dh0[t][c] * x[a][t-1+tap]
-// d(h0)[t] = dh0[t] (+ dh0b[t + shift_b] when the gradient arrives as the (P, U) pair of the tensor-core path)
-__global__ void input_bwd_kernel(const float* __restrict__ audio, const int* __restrict__ codes,
-                                 const unsigned char* __restrict__ dense, const void* __restrict__ dh0,
-                                 const void* __restrict__ dh0b, int shift_b, int adt,
-                                 float* __restrict__ dwin, int A, int C, int T, long long rows, int rows_per_cta,
-                                 int use_smem) {
-    extern __shared__ float sacc[];
-    const int n = 2 * A * C;
-    if (use_smem) { for (int i = threadIdx.x; i < n; i += blockDim.x) sacc[i] = 0.f; __syncthreads(); }
-    float* acc = use_smem ? sacc : dwin;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    const long long rbeg = (long long)blockIdx.x * rows_per_cta;
-    long long rend = rbeg + rows_per_cta; if (rend > rows) rend = rows;
-    for (long long row = rbeg + warp; row < rend; row += nw) {
-        const long long b = row / T; const int t = (int)(row % T);
-        for (int tap = 0; tap < 2; ++tap) {
-            const int ts = t - 1 + tap;
-            if (ts < 0) continue;
-            const long long r = b * T + ts;
-            if (!dense[r]) {
-                float* dst = acc + ((size_t)tap * A + codes[r]) * C;
-                for (int c = lane; c < C; c += 32) {
-                    float g = mvn_ld(dh0, adt, row * C + c);
-                    if (dh0b && t + shift_b < T) g += mvn_ld(dh0b, adt, (row + shift_b) * C + c);
-                    if (g != 0.f) atomicAdd(dst + c, g);
-                }
-            } else {
-                for (int a = 0; a < A; ++a) {
-                    const float x = audio[((size_t)b * A + a) * T + ts];
-                    if (x == 0.f) continue;
-                    float* dst = acc + ((size_t)tap * A + a) * C;
-                    for (int c = lane; c < C; c += 32) {
-                        float g = mvn_ld(dh0, adt, row * C + c);
-                        if (dh0b && t + shift_b < T) g += mvn_ld(dh0b, adt, (row + shift_b) * C + c);
-                        atomicAdd(dst + c, x * g);
-                    }
-                }
-            }
+// causal-conv weight gradient, deterministic: block (tap * A + a, z) walks its slice of the rows IN ORDER and adds the d(h0)
+// rows whose input sample is class a (one-hot columns) or x[a][t] times them (dense columns); thread = channel.  The z slices
+// are added in order by input_bwd_reduce_kernel.  d(h0)[t] = dh0[t] (+ dh0b[t + shift_b] for a (P, U) gradient pair).
+__global__ void input_bwd_det_kernel(const float* __restrict__ audio, const int* __restrict__ codes,
+                                     const unsigned char* __restrict__ dense, const void* __restrict__ dh0,
+                                     const void* __restrict__ dh0b, int shift_b, int adt, float* __restrict__ part,
+                                     int A, int C, int T, long long rows, int rows_per_z) {
+    MVN_PDL_PROLOGUE();
+    const int tap = blockIdx.x / A, a = blockIdx.x - tap * A, c = threadIdx.x;
+    const long long rbeg = (long long)blockIdx.y * rows_per_z;
+    long long rend = rbeg + rows_per_z; if (rend > rows) rend = rows;
+    float acc = 0.f;
+    for (long long row = rbeg; row < rend; ++row) {
+        const long long b = row / T; const int t = (int)(row - b * T), ts = t - 1 + tap;
+        if (ts < 0) continue;
+        const long long r = b * T + ts;
+        float x;
+        if (!dense[r]) { if (codes[r] != a) continue; x = 1.f; }
+        else { x = audio[((size_t)b * A + a) * T + ts]; if (x == 0.f) continue; }
+        if (c < C) {
+            float g = mvn_ld(dh0, adt, row * C + c);
+            if (dh0b && t + shift_b < T) g += mvn_ld(dh0b, adt, (row + shift_b) * C + c);
+            acc = fmaf(x, g, acc);
         }
     }
-    if (use_smem) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) if (sacc[i] != 0.f) atomicAdd(dwin + i, sacc[i]);
-    }
+    if (c < C) part[((size_t)blockIdx.y * 2 * A + blockIdx.x) * C + c] = acc;
+}
+__global__ void input_bwd_reduce_kernel(const float* __restrict__ part, float* __restrict__ dwin, int n, int nz) {
+    MVN_PDL_PROLOGUE();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int z = 0; z < nz; ++z) acc += part[(size_t)z * n + i];
+    dwin[i] += acc;
 }
 
 // z (B,Tn,A) time-major fp32 -> out (B,A,Tn) channels-first: softmax over A (movenet/wavenet.py:191)
@@ -342,7 +335,11 @@ struct Ctx {
     const float* packed; char* acts; char* scratch; cudaStream_t st;
     const float* lw(int l) const { return packed + P.layer0 + (size_t)l * P.layer_stride; }
     void* x(int l) const { return acts + AL.x0 + (size_t)l * AL.x_stride; }
+    float* det_ws() const { return scratch ? (float*)(scratch + SL.det_ws) : nullptr; }
 };
+// every split reduction of the exact-mode GEMMs goes through the workspace (partials added in a fixed order: deterministic)
+static int tn_gemm(const Ctx& c, TnGemmArgs& t) { t.ws = c.det_ws(); t.ws_floats = MVN_DET_WS_FLOATS; return mvn_tn_gemm(t, c.st); }
+static int row_gemm(const Ctx& c, RowGemmArgs& a) { a.ws = c.det_ws(); a.ws_floats = MVN_DET_WS_FLOATS; return mvn_row_gemm(a, c.st); }
 
 static int ctx_init(Ctx& c, const mvn_shape_t* s, const void* packed, const void* acts, const void* scratch, void* stream,
                     const char* who) {
@@ -447,11 +444,15 @@ static int video_fwd(const Ctx& c, const float* video) {
     int rc;
     {   // Conv3d with a (1,64,64) kernel = one 4096*Cin -> C linear map per frame (movenet/wavenet.py:94-98,152)
         const int rows = g.B * 160, K = 4096 * g.Cin;
-        MVN_CUDA(mvn_launch_pdl(video_conv_init_kernel, dim3(mvn_cdiv((long long)rows * C, 256)), dim3(256), (size_t)(0), c.st, enc, c.packed + c.P.bv, rows, C));
-        if ((rc = mvn_check_launch("video_conv_init"))) return rc;
         dim3 grid(mvn_cdiv(rows, VC_ROWS), mvn_cdiv(K, VC_K));
-        MVN_CUDA(mvn_launch_pdl(video_conv_kernel, dim3(grid), dim3(256), (size_t)(0), c.st, video, c.packed + c.P.wv, enc, rows, K, C));
+        // the K-slice partials live in the (not yet written) second upsampler level's slot of the activation buffer
+        float* part = u2;
+        MVN_REQUIRE((size_t)grid.y * rows * C <= (size_t)g.B * 16000 * C, "video encoder: context_in_channels too large for the split-K workspace");
+        MVN_CUDA(mvn_launch_pdl(video_conv_kernel, dim3(grid), dim3(256), (size_t)(0), c.st, video, c.packed + c.P.wv, part, rows, K, C));
         if ((rc = mvn_check_launch("video_conv"))) return rc;
+        MVN_CUDA(mvn_launch_pdl(video_conv_reduce_kernel, dim3(mvn_cdiv((long long)rows * C, 256)), dim3(256), (size_t)(0), c.st,
+                                (const float*)part, c.packed + c.P.bv, enc, rows, C, (int)grid.y));
+        if ((rc = mvn_check_launch("video_conv_reduce"))) return rc;
     }
     // ConvTranspose1d(k=10, stride=10): out[10 i + j] = W[:, :, j]^T in[i] + b -- a [rows x C] x [C x 10C] GEMM whose
     // row-major output IS the time-major upsampled signal (movenet/wavenet.py:102-118,154)
@@ -473,7 +474,7 @@ static int video_fwd(const Ctx& c, const float* video) {
         a.nsrc = 1; a.src[0] = make_src(in[i], MVN_F32, C, C, rows, 0, 0, c.packed + c.P.wt[i], 10 * C);
         set_out(a, out[i], i == 2 ? g.adt : MVN_F32, 10 * C, rows, 0);
         a.allow_ksplit = 1;
-        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+        if ((rc = row_gemm(c, a))) return rc;
     }
     return 0;
 }
@@ -499,7 +500,7 @@ static int layer_fwd(const Ctx& c, int l) {
     a.src[1] = make_src(c.x(l), g.adt, C, C, g.T, 0, 0, lw + c.P.oWz + (size_t)C * 2 * C, 2 * C);
     if (g.video) { a.nsrc = 3; a.src[2] = make_src(ctx, g.adt, C, C, g.T, 0, 0, lw + c.P.oWz + (size_t)2 * C * 2 * C, 2 * C); }
     set_out(a, gated, g.adt, C, g.T, 0);
-    if ((rc = mvn_row_gemm(a, c.st))) return rc;
+    if ((rc = row_gemm(c, a))) return rc;
 
     // residual + skip 1x1 convs; the last layer's residual is discarded (movenet/modules.py:125-130)
     RowGemmArgs r = new_args(rows, g.T, last ? S : C + S, EPI_RESID_SKIP, lw + c.P.obrs + (last ? C : 0));
@@ -507,7 +508,7 @@ static int layer_fwd(const Ctx& c, int l) {
     r.split = last ? 0 : C;
     if (!last) { set_out(r, c.x(l + 1), g.adt, C, g.T, 0); set_aux(r, c.x(l), g.adt, C, g.T, 0); }
     set_out2(r, skip, MVN_F32, S, g.Tout, -(g.RF - 1));
-    return mvn_row_gemm(r, c.st);
+    return row_gemm(c, r);
 }
 
 // DenseConv (movenet/modules.py:133-142) + drop-last + softmax (movenet/wavenet.py:183-191)
@@ -528,11 +529,11 @@ static int head_fwd(const Ctx& c, float* out) {
     RowGemmArgs a = new_args(rows, g.Tn, g.A, EPI_STORE, c.packed + c.P.b1);
     a.nsrc = 1; a.src[0] = make_src(skip, MVN_F32, g.S, g.S, g.Tout, 0, 1, c.packed + c.P.w1p, g.A);
     set_out(a, a1, MVN_F32, g.A, g.Tn, 0);
-    if ((rc = mvn_row_gemm(a, c.st))) return rc;
+    if ((rc = row_gemm(c, a))) return rc;
     RowGemmArgs b = new_args(rows, g.Tn, g.A, EPI_STORE, c.packed + c.P.b2);
     b.nsrc = 1; b.src[0] = make_src(a1, MVN_F32, g.A, g.A, g.Tn, 0, 1, c.packed + c.P.w2p, g.A);
     set_out(b, z, MVN_F32, g.A, g.Tn, 0);
-    if ((rc = mvn_row_gemm(b, c.st))) return rc;
+    if ((rc = row_gemm(c, b))) return rc;
     dim3 grid(mvn_cdiv(g.Tn, 32), g.B);
     const size_t smem = (size_t)32 * (g.A + 1) * 4;
     MVN_REQUIRE(smem <= 200 * 1024, "head: input_channels too large (%d)", g.A);
@@ -608,26 +609,26 @@ static int head_bwd(const Ctx& c, const float* out, const float* dout, const lon
         t.rows = rows; t.Trow = g.Tn; t.N = g.A; t.nsrc = 1;
         t.src[0] = make_tn(a1, MVN_F32, g.A, g.A, g.Tn, 0, 1, pg + c.P.w2p, g.A);
         t.q = dzh; t.q_dtype = MVN_F32; t.ldq = g.A; t.q_T = g.Tn; t.q_shift = 0; t.dbias = pg + c.P.b2;
-        if ((rc = mvn_tn_gemm(t, c.st))) return rc;
+        if ((rc = tn_gemm(c, t))) return rc;
     }
     {   // da1 = (dz W2) * lrelu'(a1)
         RowGemmArgs a = new_args(rows, g.Tn, g.A, EPI_MUL_LRELU_GRAD, nullptr);
         a.nsrc = 1; a.src[0] = make_src(dzh, MVN_F32, g.A, g.A, g.Tn, 0, 0, c.packed + c.P.w2pT, g.A);
         set_out(a, da1, MVN_F32, g.A, g.Tn, 0); set_aux(a, a1, MVN_F32, g.A, g.Tn, 0);
-        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+        if ((rc = row_gemm(c, a))) return rc;
     }
     {   // conv1 grads: dW1p[s][a] = sum lrelu(skip)[s] da1[a]
         TnGemmArgs t; memset(&t, 0, sizeof(t));
         t.rows = rows; t.Trow = g.Tn; t.N = g.A; t.nsrc = 1;
         t.src[0] = make_tn(skip, MVN_F32, g.S, g.S, g.Tout, 0, 1, pg + c.P.w1p, g.A);
         t.q = da1; t.q_dtype = MVN_F32; t.ldq = g.A; t.q_T = g.Tn; t.q_shift = 0; t.dbias = pg + c.P.b1;
-        if ((rc = mvn_tn_gemm(t, c.st))) return rc;
+        if ((rc = tn_gemm(c, t))) return rc;
     }
     {   // dskip = (da1 W1) * lrelu'(skip_sum); the dropped last column keeps a zero gradient
         RowGemmArgs a = new_args(rows, g.Tn, g.S, EPI_MUL_LRELU_GRAD, nullptr);
         a.nsrc = 1; a.src[0] = make_src(da1, MVN_F32, g.A, g.A, g.Tn, 0, 0, c.packed + c.P.w1pT, g.S);
         set_out(a, dskip, MVN_F32, g.S, g.Tout, 0); set_aux(a, skip, MVN_F32, g.S, g.Tout, 0);
-        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+        if ((rc = row_gemm(c, a))) return rc;
     }
     return 0;
 }
@@ -649,7 +650,7 @@ static int layer_bwd(const Ctx& c, int l, const void* dx_next, void* dx_cur, flo
         a.src[n++] = make_src(dskip, MVN_F32, S, S, g.Tout, sshift, 0, lw + c.P.oWrsT + (size_t)C * C, C);
         a.nsrc = n;
         set_out(a, dgated, g.adt, C, g.T, 0);
-        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+        if ((rc = row_gemm(c, a))) return rc;
     }
     {   // recompute the pre-activations, then d(pre) = d(gated) * d(tanh*sigmoid)
         RowGemmArgs a = new_args(rows, g.T, 2 * C, EPI_GATE_BWD, lw + c.P.obz);
@@ -658,7 +659,7 @@ static int layer_bwd(const Ctx& c, int l, const void* dx_next, void* dx_cur, flo
         a.src[1] = make_src(c.x(l), g.adt, C, C, g.T, 0, 0, lw + c.P.oWz + (size_t)C * 2 * C, 2 * C);
         if (g.video) { a.nsrc = 3; a.src[2] = make_src(ctx, g.adt, C, C, g.T, 0, 0, lw + c.P.oWz + (size_t)2 * C * 2 * C, 2 * C); }
         set_out(a, dz, g.adt, 2 * C, g.T, 0); set_out2(a, gated, g.adt, C, g.T, 0); set_aux(a, dgated, g.adt, C, g.T, 0);
-        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+        if ((rc = row_gemm(c, a))) return rc;
     }
     {   // weight grads of the dilated convs (+ context convs and their biases)
         TnGemmArgs t; memset(&t, 0, sizeof(t));
@@ -668,21 +669,21 @@ static int layer_bwd(const Ctx& c, int l, const void* dx_next, void* dx_cur, flo
         if (g.video) { t.nsrc = 3; t.src[2] = make_tn(ctx, g.adt, C, C, g.T, 0, 0, lg + c.P.oWz + (size_t)2 * C * 2 * C, 2 * C); }
         t.q = dz; t.q_dtype = g.adt; t.ldq = 2 * C; t.q_T = g.T; t.q_shift = 0;
         t.dbias = g.video ? lg + c.P.obz : nullptr;
-        if ((rc = mvn_tn_gemm(t, c.st))) return rc;
+        if ((rc = tn_gemm(c, t))) return rc;
     }
     if (dx_next) {   // residual 1x1 conv grads
         TnGemmArgs t; memset(&t, 0, sizeof(t));
         t.rows = rows; t.Trow = g.T; t.N = C; t.nsrc = 1;
         t.src[0] = make_tn(gated, g.adt, C, C, g.T, 0, 0, lg + c.P.oWrs, C + S);
         t.q = dx_next; t.q_dtype = g.adt; t.ldq = C; t.q_T = g.T; t.q_shift = 0; t.dbias = lg + c.P.obrs;
-        if ((rc = mvn_tn_gemm(t, c.st))) return rc;
+        if ((rc = tn_gemm(c, t))) return rc;
     }
     {   // skip 1x1 conv grads
         TnGemmArgs t; memset(&t, 0, sizeof(t));
         t.rows = rows; t.Trow = g.T; t.N = S; t.nsrc = 1;
         t.src[0] = make_tn(gated, g.adt, C, C, g.T, 0, 0, lg + c.P.oWrs + C, C + S);
         t.q = dskip; t.q_dtype = MVN_F32; t.ldq = S; t.q_T = g.Tout; t.q_shift = sshift; t.dbias = lg + c.P.obrs + C;
-        if ((rc = mvn_tn_gemm(t, c.st))) return rc;
+        if ((rc = tn_gemm(c, t))) return rc;
     }
     {   // d(x_l)[t] = d(x_{l+1})[t] + W1^T dz[t] + W0^T dz[t+d]
         RowGemmArgs a = new_args(rows, g.T, C, EPI_ADD_AUX, nullptr);
@@ -691,13 +692,13 @@ static int layer_bwd(const Ctx& c, int l, const void* dx_next, void* dx_cur, flo
         a.src[1] = make_src(dz, g.adt, 2 * C, 2 * C, g.T, d, 0, lw + c.P.oWzT, Kz);
         set_out(a, dx_cur, g.adt, C, g.T, 0);
         if (dx_next) set_aux(a, dx_next, g.adt, C, g.T, 0);
-        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+        if ((rc = row_gemm(c, a))) return rc;
     }
     if (g.video) {   // d(ctx) += V^T dz
         RowGemmArgs a = new_args(rows, g.T, C, EPI_ACCUM, nullptr);
         a.nsrc = 1; a.src[0] = make_src(dz, g.adt, 2 * C, 2 * C, g.T, 0, 0, lw + c.P.oWzT + 2 * C, Kz);
         set_out(a, c.scratch + c.SL.dctx, MVN_F32, C, g.T, 0);
-        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+        if ((rc = row_gemm(c, a))) return rc;
     }
     return 0;
 }
@@ -705,15 +706,21 @@ static int layer_bwd(const Ctx& c, int l, const void* dx_next, void* dx_cur, flo
 static int input_bwd(const Ctx& c, const float* audio, const void* dh0, const void* dh0b, int shift_b, float* pg) {
     const Geo& g = c.g;
     const long long rows = (long long)g.B * g.T;
-    const size_t smem = (size_t)2 * g.A * g.C * 4;
-    const int use_smem = smem <= 160 * 1024;
-    const int ctas = 148 * 2;
-    const int rpc = (int)((rows + ctas - 1) / ctas);
-    MVN_CUDA(cudaFuncSetAttribute(input_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    input_bwd_kernel<<<mvn_cdiv(rows, rpc), 256, use_smem ? smem : 0, c.st>>>(
-        audio, (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), dh0, dh0b, shift_b, g.adt,
-        pg + c.P.win, g.A, g.C, g.T, rows, rpc, use_smem);
-    return mvn_check_launch("input_bwd");
+    const int n = 2 * g.A * g.C;
+    MVN_REQUIRE(g.C <= 1024, "input conv gradient: residual_channels too large (%d)", g.C);
+    int nz = 4 * mvn_sm_count() / (2 * g.A); if (nz < 1) nz = 1;
+    while (nz > 1 && (size_t)nz * n > MVN_DET_WS_FLOATS) --nz;
+    if (nz > rows) nz = (int)rows;
+    const int rpz = (int)((rows + nz - 1) / nz);
+    const int threads = ((g.C + 31) / 32) * 32;
+    MVN_CUDA(mvn_launch_pdl(input_bwd_det_kernel, dim3(2 * g.A, nz), dim3(threads), (size_t)(0), c.st, audio,
+                            (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), dh0, dh0b, shift_b, g.adt,
+                            c.det_ws(), g.A, g.C, g.T, rows, rpz));
+    int rc = mvn_check_launch("input_bwd");
+    if (rc) return rc;
+    MVN_CUDA(mvn_launch_pdl(input_bwd_reduce_kernel, dim3(mvn_cdiv(n, 256)), dim3(256), (size_t)(0), c.st, (const float*)c.det_ws(),
+                            pg + c.P.win, n, nz));
+    return mvn_check_launch("input_bwd_reduce");
 }
 
 static int video_bwd(const Ctx& c, const float* video, const void* dctx, int dctx_dtype, float* pg) {
@@ -740,19 +747,19 @@ static int video_bwd(const Ctx& c, const float* video, const void* dctx, int dct
         t.rows = rows; t.Trow = rows; t.N = 10 * C; t.nsrc = 1;
         t.src[0] = make_tn(in[i], MVN_F32, C, C, rows, 0, 0, pg + c.P.wt[i], 10 * C);
         t.q = dout[i]; t.q_dtype = ddt[i]; t.ldq = 10 * C; t.q_T = rows; t.q_shift = 0; t.dbias = pg + c.P.bt[i];
-        if ((rc = mvn_tn_gemm(t, c.st))) return rc;
+        if ((rc = tn_gemm(c, t))) return rc;
         RowGemmArgs a = new_args(rows, rows, C, EPI_STORE, nullptr);
         a.nsrc = 1; a.src[0] = make_src(dout[i], ddt[i], 10 * C, 10 * C, rows, 0, 0, c.packed + c.P.wtT[i], C);
         set_out(a, din[i], MVN_F32, C, rows, 0);
         a.allow_ksplit = 1;
-        if ((rc = mvn_row_gemm(a, c.st))) return rc;
+        if ((rc = row_gemm(c, a))) return rc;
     }
     const int rows = g.B * 160, K = 4096 * g.Cin;
     TnGemmArgs t; memset(&t, 0, sizeof(t));
     t.rows = rows; t.Trow = rows; t.N = C; t.nsrc = 1;
     t.src[0] = make_tn(video, MVN_F32, K, K, rows, 0, 0, pg + c.P.wv, C);
     t.q = denc; t.q_dtype = MVN_F32; t.ldq = C; t.q_T = rows; t.q_shift = 0; t.dbias = pg + c.P.bv;
-    return mvn_tn_gemm(t, c.st);
+    return tn_gemm(c, t);
 }
 
 // one layer of the backward pass on whatever gradient state the scratch buffer holds (profiling / roofline timing)

@@ -321,54 +321,7 @@ __device__ __forceinline__ void epilogue_tma(const Args& a, const uint4* pre, St
 template <int EPI>
 __device__ __forceinline__ void epilogue(const Args& a, const uint4* pre, uint32_t tm, int nc, int n0, int b, int t, bool ok, int half) {
     const size_t row = (size_t)b * a.rows + t;
-    if (EPI == EPI_GATE || EPI == EPI_GATE_BWD) {
-        // chunk = [f of 128 channels | g of the same 128 channels]; this thread: channels 64 * half .. + 63 of them
-        const int ch0 = (n0 >> 1) + 64 * half;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            uint32_t f[32], g[32];
-            tmem_ld32(tm + 64 * half + 32 * u, f);
-            tmem_ld32(tm + 128 + 64 * half + 32 * u, g);
-            tmem_ld_wait();
-            const int c = ch0 + 32 * u;
-            if (!ok) continue;
-            if (EPI == EPI_GATE) {
-                __nv_bfloat16* dst = (__nv_bfloat16*)a.out + row * a.ld_out + c;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float o[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float fv = __uint_as_float(f[8 * q + e]), gv = __uint_as_float(g[8 * q + e]);
-                        if (a.bias) { fv += a.bias[n0 + 64 * half + 32 * u + 8 * q + e]; gv += a.bias[n0 + 128 + 64 * half + 32 * u + 8 * q + e]; }
-                        o[e] = tanh_fast(fv) * sigmoid_fast(gv);
-                    }
-                    st_bf16x8(dst + 8 * q, o);
-                }
-            } else {
-                __nv_bfloat16* gated = (__nv_bfloat16*)a.out + row * a.ld_out + c;
-                __nv_bfloat16* dz = (__nv_bfloat16*)a.out2 + row * a.ld_out2 + 2 * c;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float d[8], o[8], z0[8], z1[8];
-                    unpack8(pre[4 * u + q], d);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        float fv = __uint_as_float(f[8 * q + e]), gv = __uint_as_float(g[8 * q + e]);
-                        if (a.bias) { fv += a.bias[n0 + 64 * half + 32 * u + 8 * q + e]; gv += a.bias[n0 + 128 + 64 * half + 32 * u + 8 * q + e]; }
-                        const float th = tanh_fast(fv), sg = sigmoid_fast(gv);
-                        o[e] = th * sg;
-                        const float df = d[e] * sg * (1.f - th * th), dgv = d[e] * th * sg * (1.f - sg);
-                        if (e < 4) { z0[2 * e] = df; z0[2 * e + 1] = dgv; } else { z1[2 * (e - 4)] = df; z1[2 * (e - 4) + 1] = dgv; }
-                    }
-                    st_bf16x8(gated + 8 * q, o);
-                    st_bf16x8(dz + 16 * q, z0);
-                    st_bf16x8(dz + 16 * q + 8, z1);
-                }
-            }
-        }
-        return;
-    }
+    (void)pre;
     if (EPI == EPI_HEAD2) {
         // softmax over all nc (= A <= 256) columns of the row: both warps of a lane quarter compute the statistics, each writes
         // its half of the channels; lanes are consecutive time steps, so the channels-first (B, A, Tn) store is coalesced
@@ -406,7 +359,6 @@ __device__ __forceinline__ void epilogue(const Args& a, const uint4* pre, uint32
         return;
     }
     // column-block epilogues: this thread handles columns [half * nc/2, (half + 1) * nc/2) of the chunk in blocks of 32
-    const int js = t - (a.RF - 1);
     const int cnt = nc / 64;
 #pragma unroll
     for (int uu = 0; uu < 4; ++uu) {
@@ -417,48 +369,7 @@ __device__ __forceinline__ void epilogue(const Args& a, const uint4* pre, uint32
         tmem_ld_wait();
         const int n = n0 + 32 * u;
         if (!ok) continue;
-        if (EPI == EPI_RESID_SKIP) {
-            if (n < a.n_resid) {       // residual: x' = r + br + x(t)     (the block never straddles: n_resid % 128 == 0)
-                __nv_bfloat16* dst = (__nv_bfloat16*)a.out + row * a.ld_out + n;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float xv[8], o[8];
-                    unpack8(pre[4 * uu + q], xv);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * q + e]) + a.bias[n + 8 * q + e] + xv[e];
-                    st_bf16x8(dst + 8 * q, o);
-                }
-            } else if (js >= 0 && js < a.Tout) {     // skip: only the last Tout rows of a clip reach the head (modules.py:90-91)
-                const int s0 = n - a.n_resid;
-                // layer 0 stores, every later layer adds with a vector reduction that L2 executes (red.global.add.v4.f32):
-                // no read reaches the SM -- a load-add-store of the same 128-byte line by one thread serialises on the store's
-                // round trip (measured: 2.5 ms instead of 0.1 ms per layer) -- and since each element receives exactly one add per
-                // launch and launches are ordered, the sum is formed in layer order: deterministic
-                float4* dst = (float4*)(a.skip + ((size_t)b * a.Tout + js) * a.S + s0);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 o = make_float4(__uint_as_float(v[4 * q]) + a.bias[n + 4 * q], __uint_as_float(v[4 * q + 1]) + a.bias[n + 4 * q + 1],
-                                                 __uint_as_float(v[4 * q + 2]) + a.bias[n + 4 * q + 2], __uint_as_float(v[4 * q + 3]) + a.bias[n + 4 * q + 3]);
-                    if (a.skip_init) dst[q] = o;
-                    else asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
-                }
-            }
-        } else if (EPI == EPI_STORE || EPI == EPI_ADD_STORE) {
-            __nv_bfloat16* dst = (__nv_bfloat16*)a.out + row * a.ld_out + n;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float o[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * q + e]);
-                if (EPI == EPI_ADD_STORE && a.aux) {
-                    float xv[8];
-                    unpack8(pre[4 * uu + q], xv);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] += xv[e];
-                }
-                st_bf16x8(dst + 8 * q, o);
-            }
-        } else if (EPI == EPI_HEAD1) {
+        if (EPI == EPI_HEAD1) {
             if (t >= a.Tn) continue;
             float* a1 = (float*)a.out + ((size_t)b * a.Tn + t) * a.ld_out + n;
             __nv_bfloat16* l1 = (__nv_bfloat16*)a.out2 + row * a.ld_out2 + n;

@@ -13,16 +13,26 @@ pytestmark = pytest.mark.gpu
 
 LOGIT_RTOL = 2e-2
 LOSS_RTOL = 1e-3
-# bf16 activations AND bf16 activation-gradients: every weight gradient is a sum over ~1e2..1e5 time
-# steps of products of rounded terms with heavy cancellation, so the per-tensor error is a few
-# percent, up to ~19 % for the deepest tensors of the gain-2.5 fixture and 24-25 % for ONE bias gradient of
-# the 14-layer C=16 fixture (cfg04_short, |g| ~ 1e-5; 0.242 with the fp32 gate epilogue, 0.251 with the
-# packed f16x2 one -- scripts/dev/grad_error_table.py prints the table).  Stated tolerance: 30 % relative L2
-# per tensor, 15 % on average over the tensors of a model (measured: 1-4 % on the plain fixtures, 10 % on the gain-2.5
-# one, 13 % on cfg04_short), cosine similarity >= 0.99 over the whole gradient.
-GRAD_RTOL = 0.30
+# bf16 activations AND bf16 activation-gradients: every weight gradient is a sum over ~1e2..1e5 time steps of products of
+# rounded terms with heavy cancellation.  The tolerance is CALIBRATED, not flat: tests/golden/make_autocast_floor.py runs the
+# oracle (bit-identical to the reference) under torch.autocast(bfloat16) -- the reference's own mixed-precision recipe,
+# movenet/trainer.py:124 -- on the same fixtures and records its per-tensor relative L2 error against the fp32 golden gradients
+# (tests/golden/autocast_floor.json: 1-4 % on the plain fixtures, up to 21 % / 24 % for single bias gradients of the gain-2.5 and
+# the 14-layer C = 16 fixtures).  The CUDA path must stay within max(10 %, 2 x that floor) per tensor and max(5 %, 2 x the
+# floor's mean) on average, with a cosine similarity >= 0.99 over the whole gradient.
+import json
+import os
+
+GRAD_RTOL = 0.30          # (only for shapes without a recorded floor: random models built inside a test)
 GRAD_MEAN_RTOL = 0.15
 GRAD_COS = 0.99
+_FLOOR = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "autocast_floor.json")))
+
+
+def grad_tolerances(name):
+    """(per-tensor tolerance dict, mean tolerance) for a golden fixture"""
+    fl = _FLOOR[name]
+    return {k: max(0.10, 2.0 * v) for k, v in fl["per_tensor"].items()}, max(0.05, 2.0 * fl["mean"])
 
 
 def build(fx, dtype):
@@ -54,12 +64,13 @@ def test_bf16_forward_loss_and_grads_against_golden(name, summed, monkeypatch):
     loss.backward()
     assert abs(loss.item() - fx["loss"].item()) <= LOSS_RTOL * abs(fx["loss"].item())
     got = dict(m.named_parameters())
+    tol, mean_tol = grad_tolerances(name)
     errs = []
     for k, g in fx["grads"].items():
         assert got[k].grad is not None, k
         errs.append(rel_l2(got[k].grad.cpu(), g))
-        assert errs[-1] < GRAD_RTOL, (k, errs[-1])
-    assert sum(errs) / len(errs) < GRAD_MEAN_RTOL, sum(errs) / len(errs)
+        assert errs[-1] < tol[k], (k, errs[-1], tol[k])
+    assert sum(errs) / len(errs) < mean_tol, (sum(errs) / len(errs), mean_tol)
     for k in fx["none_grads"]:
         assert got[k].grad is None, k
     a = torch.cat([got[k].grad.cpu().flatten() for k in fx["grads"]])
@@ -88,12 +99,13 @@ def test_bf16_benchmarked_shape_against_the_reference():
     assert (output.detach()[:, :, cols].cpu() - fx["probs_cols"]).abs().max().item() <= LOGIT_RTOL * fx["probs_cols"].abs().max().item()
     assert abs(loss.item() - fx["loss"].item()) <= LOSS_RTOL * abs(fx["loss"].item())
     got = dict(m.named_parameters())
+    tol, mean_tol = grad_tolerances("cfg01_true")
     errs = {}
     for k, g in fx["grads"].items():
         assert got[k].grad is not None, k
         errs[k] = rel_l2(got[k].grad.cpu(), g)
-        assert errs[k] < GRAD_RTOL, (k, errs[k])
-    assert sum(errs.values()) / len(errs) < GRAD_MEAN_RTOL, sum(errs.values()) / len(errs)
+        assert errs[k] < tol[k], (k, errs[k], tol[k])
+    assert sum(errs.values()) / len(errs) < mean_tol, (sum(errs.values()) / len(errs), mean_tol)
     for k in fx["none_grads"]:
         assert got[k].grad is None, k
     a = torch.cat([got[k].grad.cpu().flatten() for k in fx["grads"]])
@@ -245,11 +257,10 @@ def test_loss_fused_route_only_for_the_plain_call():
 
 @pytest.mark.parametrize("video", [False, True])
 def test_bf16_training_step_is_bit_reproducible(video):
-    """every reduction of the audio path has a fixed order (per-CTA partials + ordered sums, no atomics), and every hand-off
-    between warps, kernels (programmatic dependent launch) and proxies is fenced: the same step on the same inputs must give the
-    same BITS, run after run, at the full clip length.  With video the encoder GEMM (and its weight gradient) adds its split-K
-    slices with fp32 atomics: the encoder output moves by an ulp between runs, its bf16 copy occasionally by a bf16 ulp, and
-    everything downstream by bf16 rounding noise (measured 3e-3 on the smallest gradient tensor): 2e-2 per tensor there."""
+    """every reduction has a fixed order (per-CTA partials + ordered sums, no atomics -- since round 2 also the video encoder's
+    split-K GEMM and its weight gradient), and every hand-off between warps, kernels (programmatic dependent launch) and
+    proxies is fenced: the same step on the same inputs must give the same BITS, run after run, at the full clip length,
+    with and without video."""
     torch.manual_seed(3)
     m = movenet_b200.WaveNet(3, 3, 64, 64, 8, compute_dtype="bf16").cuda()
     B, T = 2, 160000
@@ -265,16 +276,11 @@ def test_bf16_training_step_is_bit_reproducible(video):
         loss.backward()
         runs.append((out.detach().clone(), loss.detach().clone(),
                      {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
-    skip = ("video_conv.",)
     for out, loss, grads in runs[1:]:
-        assert torch.equal(out, runs[0][0]) or video      # with video the context itself carries the encoder's atomics
-        if not video:
-            assert torch.equal(loss, runs[0][1])
+        assert torch.equal(out, runs[0][0])
+        assert torch.equal(loss, runs[0][1])
         for k, g in grads.items():
-            if video:
-                assert rel_l2(g, runs[0][2][k]) < 2e-2, k
-            elif not k.startswith(skip):
-                assert torch.equal(g, runs[0][2][k]), k
+            assert torch.equal(g, runs[0][2][k]), k
 
 
 def _grads_of(m, audio, video, target):

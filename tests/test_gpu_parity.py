@@ -385,3 +385,27 @@ def test_integer_code_input_equals_one_hot_input(dtype):
         assert rel_l2(dict(m.named_parameters())[k].grad, g) < 1e-5, k
     with pytest.raises(ValueError):
         m(codes[:, :m.receptive_fields - 1])
+
+
+@pytest.mark.parametrize("name", ["cfg03", "video"])
+def test_fp32_exact_mode_is_bit_reproducible(name):
+    """the exact (fp32) mode reduces every split sum -- weight gradients over time slices, the video encoder's split-K GEMM,
+    the input conv's per-class sums -- through per-slice partials added in a fixed order (no fp32 atomics): the mode
+    the golden tests pin gives the same BITS run after run"""
+    fx = load_golden(name)
+    m = build(fx)
+    audio = golden_audio(fx).cuda()
+    video = golden_video(fx, audio.shape[0]).cuda() if "video_seed" in fx else None
+    target = audio[:, :, m.receptive_fields:].argmax(1)
+    runs = []
+    for _ in range(3):
+        m.zero_grad(set_to_none=True)
+        out = m(audio, video)
+        loss = F.cross_entropy(out, target)
+        loss.backward()
+        runs.append((out.detach().clone(), loss.detach().clone(),
+                     {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}))
+    for out, loss, grads in runs[1:]:
+        assert torch.equal(out, runs[0][0]) and torch.equal(loss, runs[0][1])
+        for k, g in grads.items():
+            assert torch.equal(g, runs[0][2][k]), k
