@@ -102,9 +102,11 @@ int mvn_one_hot(const int64_t* codes, float* audio, int B, int A, int T, void* s
 int mvn_pack_weights(const mvn_shape_t* s, const void* const* param_ptrs_dev, void* packed, void* stream);
 /* packed gradients -> reference-layout gradient tensors, all living in ONE flat fp32 buffer (so the
  * data-parallel all-reduce is a single message): offsets_dev[i] is the element offset of parameter i
- * (state_dict order) inside flat_grads, or -1 for a parameter that gets no gradient. */
+ * (state_dict order) inside flat_grads, or -1 for a parameter that gets no gradient.  Every gradient is multiplied by
+ * `scale` on the way (1 / world_size under data parallelism: the all-reduce that follows is then a plain sum and the average
+ * needs no pass of its own, movenet/trainer.py:230-234). */
 int mvn_unpack_grads(const mvn_shape_t* s, const void* packed_grads, float* flat_grads,
-                     const int64_t* offsets_dev, void* stream);
+                     const int64_t* offsets_dev, float scale, void* stream);
 
 /* WaveNet.forward (movenet/wavenet.py:158-191): causal conv (modules.py:15-30),
  * video encoder + upsampler (wavenet.py:149-156), the gated residual stack

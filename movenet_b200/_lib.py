@@ -41,7 +41,7 @@ SIGNATURES = {
     "mvn_mulaw_decode": (_I, [_P, _P, _I, _P, _I64, _P]),
     "mvn_one_hot": (_I, [_P, _P, _I, _I, _I, _P]),
     "mvn_pack_weights": (_I, [_SP, _P, _P, _P]),
-    "mvn_unpack_grads": (_I, [_SP, _P, _P, _P, _P]),
+    "mvn_unpack_grads": (_I, [_SP, _P, _P, _P, C.c_float, _P]),
     "mvn_codes_input": (_I, [_SP, _P, _P, _P]),
     "mvn_wavenet_forward": (_I, [_SP, _P, _P, _P, _P, _P, _P, _P]),
     "mvn_wavenet_backward": (_I, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

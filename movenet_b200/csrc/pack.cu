@@ -50,7 +50,7 @@ __global__ void pack_layer_kernel(const float* const* __restrict__ ptrs, float* 
 }
 
 __global__ void unpack_layer_kernel(float* __restrict__ flat, const long long* __restrict__ offs,
-                                    const float* __restrict__ packed, PackedLayout P, int C, int Cl, int S, int Kz, int video) {
+                                    const float* __restrict__ packed, PackedLayout P, int C, int Cl, int S, int Kz, int video, float scale) {
     MVN_PDL_PROLOGUE();
     const int l = blockIdx.y;
     float* lp[10];
@@ -65,7 +65,7 @@ __global__ void unpack_layer_kernel(float* __restrict__ flat, const long long* _
         if (j < 2 * nW) {
             const int gate = j >= nW; if (gate) j -= nW;
             const int tap = j & 1, k = (j >> 1) % Cl, c = (j >> 1) / Cl;
-            if (lp[gate]) lp[gate][j] = base[P.oWz + (size_t)(tap * C + k) * 2 * C + 2 * c + gate];
+            if (lp[gate]) lp[gate][j] = scale * base[P.oWz + (size_t)(tap * C + k) * 2 * C + 2 * c + gate];
             continue;
         }
         j -= 2 * nW;
@@ -73,24 +73,24 @@ __global__ void unpack_layer_kernel(float* __restrict__ flat, const long long* _
             const int gate = j >= nV; if (gate) j -= nV;
             const int k = j % Cl, c = j / Cl;
             float* dst = lp[gate ? 4 : 2];
-            if (dst) dst[j] = video ? base[P.oWz + (size_t)(2 * C + k) * 2 * C + 2 * c + gate] : 0.f;
+            if (dst) dst[j] = video ? scale * base[P.oWz + (size_t)(2 * C + k) * 2 * C + 2 * c + gate] : 0.f;
             continue;
         }
         j -= 2 * nV;
         if (j < 2 * Cl) {
             const int gate = j >= Cl; if (gate) j -= Cl;
             float* dst = lp[gate ? 5 : 3];
-            if (dst) dst[j] = video ? base[P.obz + 2 * j + gate] : 0.f;
+            if (dst) dst[j] = video ? scale * base[P.obz + 2 * j + gate] : 0.f;
             continue;
         }
         j -= 2 * Cl;
-        if (j < nV) { const int k = j % Cl, n = j / Cl; if (lp[6]) lp[6][j] = base[P.oWrs + (size_t)k * (C + S) + n]; continue; }
+        if (j < nV) { const int k = j % Cl, n = j / Cl; if (lp[6]) lp[6][j] = scale * base[P.oWrs + (size_t)k * (C + S) + n]; continue; }
         j -= nV;
-        if (j < Cl) { if (lp[7]) lp[7][j] = base[P.obrs + j]; continue; }
+        if (j < Cl) { if (lp[7]) lp[7][j] = scale * base[P.obrs + j]; continue; }
         j -= Cl;
-        if (j < S * Cl) { const int k = j % Cl, s = j / Cl; if (lp[8]) lp[8][j] = base[P.oWrs + (size_t)k * (C + S) + C + s]; continue; }
+        if (j < S * Cl) { const int k = j % Cl, s = j / Cl; if (lp[8]) lp[8][j] = scale * base[P.oWrs + (size_t)k * (C + S) + C + s]; continue; }
         j -= S * Cl;
-        if (lp[9]) lp[9][j] = base[P.obrs + C + j];
+        if (lp[9]) lp[9][j] = scale * base[P.obrs + C + j];
     }
 }
 
@@ -143,7 +143,7 @@ __global__ void pack_misc_kernel(const float* const* __restrict__ ptrs, float* _
 
 __global__ void unpack_misc_kernel(float* __restrict__ flat, const long long* __restrict__ offs,
                                    const float* __restrict__ packed, PackedLayout P,
-                                   int A, int C, int Cl, int S, int Cin, int N, int video) {
+                                   int A, int C, int Cl, int S, int Cin, int N, int video, float scale) {
     MVN_PDL_PROLOGUE();
     const int grp = blockIdx.y;
     auto gp = [&](int i) -> float* { const long long o = offs[i]; return o < 0 ? nullptr : flat + o; };
@@ -152,32 +152,32 @@ __global__ void unpack_misc_kernel(float* __restrict__ flat, const long long* __
         float* w = gp(MVN_PARAM_CAUSAL_W);
         if (w) for (int i = i0; i < 2 * A * C; i += stride) {
             const int c = i % C, a = (i / C) % A, tap = i / (A * C);
-            if (c < Cl) w[((size_t)c * A + a) * 2 + tap] = packed[P.win + i];
+            if (c < Cl) w[((size_t)c * A + a) * 2 + tap] = scale * packed[P.win + i];
         }
     } else if (grp == 1) {
         float *w1 = gp(MVN_PARAM_DENSE(N, 0)), *b1 = gp(MVN_PARAM_DENSE(N, 1)),
               *w2 = gp(MVN_PARAM_DENSE(N, 2)), *b2 = gp(MVN_PARAM_DENSE(N, 3));
-        if (w1) for (int i = i0; i < S * A; i += stride) { const int a = i % A, s = i / A; w1[(size_t)a * S + s] = packed[P.w1p + i]; }
-        if (w2) for (int i = i0; i < A * A; i += stride) { const int n = i % A, k = i / A; w2[(size_t)n * A + k] = packed[P.w2p + i]; }
-        for (int i = i0; i < A; i += stride) { if (b1) b1[i] = packed[P.b1 + i]; if (b2) b2[i] = packed[P.b2 + i]; }
+        if (w1) for (int i = i0; i < S * A; i += stride) { const int a = i % A, s = i / A; w1[(size_t)a * S + s] = scale * packed[P.w1p + i]; }
+        if (w2) for (int i = i0; i < A * A; i += stride) { const int n = i % A, k = i / A; w2[(size_t)n * A + k] = scale * packed[P.w2p + i]; }
+        for (int i = i0; i < A; i += stride) { if (b1) b1[i] = scale * packed[P.b1 + i]; if (b2) b2[i] = scale * packed[P.b2 + i]; }
     } else if (grp == 2) {
         float *w = gp(MVN_PARAM_VIDEO_CONV_W), *b = gp(MVN_PARAM_VIDEO_CONV_B);
         const int K = 4096 * Cin;
         if (w) for (int i = i0; i < K * C; i += stride) {    // hw fastest: the writes of the reference-shaped gradient are coalesced
             const int hw = i & 4095, r = i >> 12, ci = r % Cin, c = r / Cin;
-            if (c < Cl) w[((size_t)c * Cin + ci) * 4096 + hw] = video ? packed[P.wv + ((size_t)hw * Cin + ci) * C + c] : 0.f;
+            if (c < Cl) w[((size_t)c * Cin + ci) * 4096 + hw] = video ? scale * packed[P.wv + ((size_t)hw * Cin + ci) * C + c] : 0.f;
         }
-        if (b) for (int i = i0; i < Cl; i += stride) b[i] = video ? packed[P.bv + i] : 0.f;
+        if (b) for (int i = i0; i < Cl; i += stride) b[i] = video ? scale * packed[P.bv + i] : 0.f;
     } else if (grp >= 3 && grp < 6) {
         const int lv = grp - 3;
         float *w = gp(MVN_PARAM_VT_W(lv)), *b = gp(MVN_PARAM_VT_B(lv));
         if (w) for (int i = i0; i < C * 10 * C; i += stride) {
             const int n = i % (10 * C), ci = i / (10 * C), j = n / C, co = n % C;
-            if (ci < Cl && co < Cl) w[((size_t)ci * Cl + co) * 10 + j] = video ? packed[P.wt[lv] + i] : 0.f;
+            if (ci < Cl && co < Cl) w[((size_t)ci * Cl + co) * 10 + j] = video ? scale * packed[P.wt[lv] + i] : 0.f;
         }
         if (b) for (int i = i0; i < Cl; i += stride) {
             float acc = 0.f;
-            if (video) for (int j = 0; j < 10; ++j) acc += packed[P.bt[lv] + j * C + i];
+            if (video) for (int j = 0; j < 10; ++j) acc += scale * packed[P.bt[lv] + j * C + i];
             b[i] = acc;
         }
     }
@@ -209,15 +209,15 @@ extern "C" int mvn_pack_weights(const mvn_shape_t* s, const void* const* param_p
 }
 
 extern "C" int mvn_unpack_grads(const mvn_shape_t* s, const void* packed_grads, float* flat_grads,
-                                const int64_t* offsets_dev, void* stream) {
+                                const int64_t* offsets_dev, float scale, void* stream) {
     Geo g; MVN_REQUIRE(geo_init(g, s) == 0, "mvn_unpack_grads: bad shape");
     PackedLayout P; packed_layout(g, P);
     cudaStream_t st = (cudaStream_t)stream;
     MVN_REQUIRE(packed_grads && flat_grads && offsets_dev, "mvn_unpack_grads: null buffer");
     const long long* offs = (const long long*)offsets_dev;
     dim3 gl(8, g.N);
-    MVN_CUDA(mvn_launch_pdl(unpack_layer_kernel, dim3(gl), dim3(256), (size_t)(0), st, flat_grads, offs, (const float*)packed_grads, P, g.C, g.Cl, g.S, g.Kz, g.video));
+    MVN_CUDA(mvn_launch_pdl(unpack_layer_kernel, dim3(gl), dim3(256), (size_t)(0), st, flat_grads, offs, (const float*)packed_grads, P, g.C, g.Cl, g.S, g.Kz, g.video, scale));
     dim3 gm(128, 6);
-    MVN_CUDA(mvn_launch_pdl(unpack_misc_kernel, dim3(gm), dim3(256), (size_t)(0), st, flat_grads, offs, (const float*)packed_grads, P, g.A, g.C, g.Cl, g.S, g.Cin, g.N, g.video));
+    MVN_CUDA(mvn_launch_pdl(unpack_misc_kernel, dim3(gm), dim3(256), (size_t)(0), st, flat_grads, offs, (const float*)packed_grads, P, g.A, g.C, g.Cl, g.S, g.Cin, g.N, g.video, scale));
     return mvn_check_launch("unpack_grads");
 }

@@ -80,7 +80,8 @@ class _FusedLoss(torch.autograd.Function):
             st.acts = None
             flat, views = module._flat_grads(st.has_video, audio.device)
             offs = module._grad_offsets(st.has_video, audio.device)
-            _lib.call("mvn_unpack_grads", C.byref(bufs.shape), pg.data_ptr(), flat.data_ptr(), offs.data_ptr(), _stream())
+            _lib.call("mvn_unpack_grads", C.byref(bufs.shape), pg.data_ptr(), flat.data_ptr(), offs.data_ptr(),
+                      C.c_float(1.0 / module._dp_world), _stream())
         module._reduce_grads(flat)
         return (None, None, None, *views)
 

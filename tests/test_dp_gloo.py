@@ -29,7 +29,7 @@ def _worker(rank, world, port, out):
     same = all(torch.equal(g, gathered[0]) for g in gathered)
     kept = torch.equal(mine, before)         # true on rank 0 only
     offs, total = m._grad_layout(has_video=False)
-    flat = torch.full((total,), float(rank + 1))
+    flat = torch.full((total,), float(rank + 1)) / world     # (mvn_unpack_grads hands the gradients over scaled by 1 / world)
     m._reduce_grads(flat)
     ok = bool(torch.allclose(flat, torch.full((total,), (1 + world) / 2)))
     # sharding helper: disjoint, covering
