@@ -53,6 +53,13 @@ static inline int wide_ok(const Geo& g) {
            g.S <= 1024 && g.A >= 128 && g.A % 128 == 0 && g.A <= 256;
 }
 
+// The wide engine's head kernels alone (DenseConv + softmax and their backward) also serve shapes whose residual stack runs
+// on the fused C <= 64 kernels but whose head the smem-resident head kernels do not cover: the reference's own test
+// architecture (A = 256, C = 64, S = 64; tests/test_model.py:42-48)
+static inline int wide_head_ok(const Geo& g) {
+    return g.adt == MVN_DTYPE_BF16 && g.A >= 128 && g.A % 128 == 0 && g.A <= 256 && g.S >= 64 && g.S % 64 == 0 && g.S <= 1024;
+}
+
 // ---- packed weights (fp32 elements) -------------------------------------------------------------
 struct PackedLayout {
     size_t win;                 // [2][A][C]      Win[tap][a][c] = causal_conv.conv.weight[c][a][tap]
@@ -107,8 +114,9 @@ static inline void packed_layout(const Geo& g, PackedLayout& p) {
     p.w1p = take(S * A); p.b1 = take(A); p.w2p = take(A * A); p.b2 = take(A);
     p.w1pT = take(A * S); p.w2pT = take(A * A);
     p.tc_head = take((A == 64 || A == 128) ? A * A / 2 : 0);
-    p.wH1 = take(wide ? A * S / 2 : 0); p.wH2 = take(wide ? A * A / 2 : 0);
-    p.wH2T = take(wide ? A * A / 2 : 0); p.wH1T = take(wide ? S * A / 2 : 0);
+    const bool whead = wide || wide_head_ok(g);
+    p.wH1 = take(whead ? A * S / 2 : 0); p.wH2 = take(whead ? A * A / 2 : 0);
+    p.wH2T = take(whead ? A * A / 2 : 0); p.wH1T = take(whead ? S * A / 2 : 0);
     p.wWsAll = take(wide ? S * (size_t)g.N * C / 2 : 0); p.wbsum = take(wide ? S : 0);
     if (g.video) {
         p.wv = take((size_t)4096 * g.Cin * C); p.bv = take(C);
@@ -204,10 +212,10 @@ static inline void scratch_layout(const Geo& g, ScratchLayout& w) {
     w.tc_layer_partial = take(g.adt == MVN_DTYPE_BF16 && g.C == 64 ? (size_t)g.N * 148 * (128 * 256 + 256) * 4 : 0);
     w.det_ws = take((size_t)MVN_DET_WS_FLOATS * 4);
     const bool wide = wide_ok(g);
-    w.w_l0 = take(wide ? BTo * g.S * 2 : 0);
+    w.w_l0 = take(wide || wide_head_ok(g) ? BTo * g.S * 2 : 0);
     w.w_ds16 = take(wide ? BT * g.S * 2 : 0);
     w.w_oh16 = take(wide ? BT * g.A * 2 : 0);
-    w.w_colsum = take(wide ? (size_t)1024 * 1024 * 4 : 0);
+    w.w_colsum = take(wide || wide_head_ok(g) ? (size_t)1024 * 1024 * 4 : 0);
     w.w_wgpart = take(wide ? (size_t)80 * 256 * 512 * 4 : 0);
     w.total = o;
 }

@@ -196,7 +196,7 @@ extern "C" int mvn_pack_weights(const mvn_shape_t* s, const void* const* param_p
     if (rc) return rc;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video))
         if ((rc = mvn_tc_pack(ptrs, (float*)packed, P, g, st))) return rc;
-    if (mvn_wide_supported(g) && (rc = mvn_wide_pack(ptrs, (float*)packed, P, g, st))) return rc;
+    if (mvn_wide_head_supported(g) && (rc = mvn_wide_pack(ptrs, (float*)packed, P, g, st))) return rc;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S))   // conv2.weight is (A, A, 1): already [n][k]
         if ((rc = mvn_tc_head_pack((const float*)packed + P.w2pT, (float*)packed, P, g.A, st))) return rc;
     if (g.adt == MVN_DTYPE_BF16 && g.video && mvn_tc_upsample_supported(g.C))

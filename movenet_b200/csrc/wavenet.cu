@@ -205,39 +205,147 @@ __global__ void video_conv_reduce_kernel(const float* __restrict__ part, const f
     enc[i] = acc;
 }
 
-// causal-conv weight gradient, deterministic: block (tap * A + a, z) walks its slice of the rows IN ORDER and adds the d(h0)
-// rows whose input sample is class a (one-hot columns) or x[a][t] times them (dense columns); thread = channel.  The z slices
-// are added in order by input_bwd_reduce_kernel.  d(h0)[t] = dh0[t] (+ dh0b[t + shift_b] for a (P, U) gradient pair).
-__global__ void input_bwd_det_kernel(const float* __restrict__ audio, const int* __restrict__ codes,
+// causal-conv weight gradient, deterministic: block (tap * A + a, z) owns class a of tap `tap` over slice z of the rows.  It
+// scans its rows 256 at a time (coalesced loads of the codes), compacts the rows whose input sample is class a (one-hot
+// columns) or has x[a][t] != 0 (dense columns) IN ROW ORDER with a ballot / prefix pass, then adds their d(h0) rows, thread =
+// channel.  The z slices are added in order by input_bwd_reduce_kernel.  d(h0)[t] = dh0[t] (+ dh0b[t + shift_b] for a (P, U)
+// gradient pair).
+__global__ void __launch_bounds__(256) input_bwd_det_kernel(const float* __restrict__ audio, const int* __restrict__ codes,
                                      const unsigned char* __restrict__ dense, const void* __restrict__ dh0,
                                      const void* __restrict__ dh0b, int shift_b, int adt, float* __restrict__ part,
                                      int A, int C, int T, long long rows, int rows_per_z) {
     MVN_PDL_PROLOGUE();
-    const int tap = blockIdx.x / A, a = blockIdx.x - tap * A, c = threadIdx.x;
+    __shared__ int s_row[256];
+    __shared__ float s_x[256];
+    __shared__ int s_wcnt[8], s_total;
+    const int tap = blockIdx.x / A, a = blockIdx.x - tap * A, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long rbeg = (long long)blockIdx.y * rows_per_z;
     long long rend = rbeg + rows_per_z; if (rend > rows) rend = rows;
-    float acc = 0.f;
-    for (long long row = rbeg; row < rend; ++row) {
-        const long long b = row / T; const int t = (int)(row - b * T), ts = t - 1 + tap;
-        if (ts < 0) continue;
-        const long long r = b * T + ts;
-        float x;
-        if (!dense[r]) { if (codes[r] != a) continue; x = 1.f; }
-        else { x = audio[((size_t)b * A + a) * T + ts]; if (x == 0.f) continue; }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};          // channels tid, tid + 256, ... (C <= 1024)
+    for (long long chunk = rbeg; chunk < rend; chunk += 256) {
+        const long long row = chunk + tid;
+        float x = 0.f;
+        if (row < rend) {
+            const long long b = row / T; const int t = (int)(row - b * T), ts = t - 1 + tap;
+            if (ts >= 0) {
+                const long long r = b * T + ts;
+                if (!dense[r]) x = codes[r] == a ? 1.f : 0.f;
+                else x = audio[((size_t)b * A + a) * T + ts];
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, x != 0.f);
+        if (lane == 0) s_wcnt[warp] = __popc(m);
+        __syncthreads();
+        int base = 0;
+        for (int w = 0; w < warp; ++w) base += s_wcnt[w];
+        if (x != 0.f) { const int pos = base + __popc(m & ((1u << lane) - 1)); s_row[pos] = (int)(row - chunk); s_x[pos] = x; }
+        if (tid == 0) { int tot = 0; for (int w = 0; w < 8; ++w) tot += s_wcnt[w]; s_total = tot; }
+        __syncthreads();
+        const int n = s_total;
+        for (int i = 0; i < n; ++i) {
+            const long long r2 = chunk + s_row[i];
+            const int t2 = (int)(r2 % T);
+            const float xv = s_x[i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = tid + 256 * j;
+                if (c < C) {
+                    float g = mvn_ld(dh0, adt, r2 * C + c);
+                    if (dh0b && t2 + shift_b < T) g += mvn_ld(dh0b, adt, (r2 + shift_b) * C + c);
+                    acc[j] = fmaf(xv, g, acc[j]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = tid + 256 * j;
+        if (c < C) part[((size_t)blockIdx.y * 2 * A + blockIdx.x) * C + c] = acc[j];
+    }
+}
+// The same gradient when the whole [2][A][C] table fits in shared memory (every shape but the widest): block z owns a slice
+// of the rows and walks it IN ORDER, thread = channel, adding each d(h0) row into the table entry of the row's class (both
+// taps) -- no scan per class, no atomics, a fixed order.  part[z] = the block's table.
+__global__ void input_bwd_table_kernel(const float* __restrict__ audio, const int* __restrict__ codes,
+                                       const unsigned char* __restrict__ dense, const void* __restrict__ dh0,
+                                       const void* __restrict__ dh0b, int shift_b, int adt, float* __restrict__ part,
+                                       int A, int C, int T, long long rows, int rows_per_z) {
+    MVN_PDL_PROLOGUE();
+    extern __shared__ float tab[];                 // [2][A][C]
+    const int n = 2 * A * C, c = threadIdx.x;
+    for (int i = c; i < n; i += blockDim.x) tab[i] = 0.f;
+    __syncthreads();
+    // (32-bit row arithmetic: B * T < 2^31 is checked by the callers; 64-bit divisions per row were most of this kernel's time)
+    const int rbeg = blockIdx.x * rows_per_z;
+    int rend = rbeg + rows_per_z; if (rend > (int)rows) rend = (int)rows;
+    // (each thread touches only column c of the table: no hazards between threads, program order within a thread).  32 rows per
+    // round: their gradients are fetched together (32 loads in flight per thread), their classes staged in shared memory, then
+    // applied one after the other
+    __shared__ int s_code[33];                     // class of row chunk - 1 + i (tap 0 reads i, tap 1 reads i + 1); -1: dense, -2: none
+    int tc = rbeg < rend ? rbeg % T : 0;           // time index of the chunk's first row
+    for (int chunk = rbeg; chunk < rend; chunk += 32, tc = (tc + 32) % T) {
+        __syncthreads();
+        for (int i = c; i < 33; i += blockDim.x) {
+            const int rr = chunk - 1 + i;            // the input sample one before / at each row of the chunk
+            int code = -2;
+            if (rr >= 0 && rr < rend) code = dense[rr] ? -1 : codes[rr];
+            s_code[i] = code;
+        }
+        float gbuf[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int row = chunk + i;
+            float g = 0.f;
+            if (c < C && row < rend) {
+                g = mvn_ld(dh0, adt, (long long)row * C + c);
+                int t = tc + i; if (t >= T) t -= T;
+                if (dh0b && t + shift_b < T) g += mvn_ld(dh0b, adt, (long long)(row + shift_b) * C + c);
+            }
+            gbuf[i] = g;
+        }
+        __syncthreads();
         if (c < C) {
-            float g = mvn_ld(dh0, adt, row * C + c);
-            if (dh0b && t + shift_b < T) g += mvn_ld(dh0b, adt, (row + shift_b) * C + c);
-            acc = fmaf(x, g, acc);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int row = chunk + i;
+                if (row >= rend) break;
+                int t = tc + i; if (t >= T) t -= T;
+                const float g = gbuf[i];
+#pragma unroll
+                for (int tap = 0; tap < 2; ++tap) {
+                    const int ts = t - 1 + tap;
+                    if (ts < 0) continue;                  // x[-1] = 0: the first column of a clip has no tap 0
+                    const int code = s_code[i + tap];
+                    if (code >= 0) tab[(tap * A + code) * C + c] += g;
+                    else if (code == -1) {
+                        const int b = row / T;
+                        for (int a = 0; a < A; ++a) {
+                            const float x = audio[((size_t)b * A + a) * T + ts];
+                            if (x != 0.f) tab[(tap * A + a) * C + c] = fmaf(x, g, tab[(tap * A + a) * C + c]);
+                        }
+                    }
+                }
+            }
         }
     }
-    if (c < C) part[((size_t)blockIdx.y * 2 * A + blockIdx.x) * C + c] = acc;
+    __syncthreads();
+    for (int i = c; i < n; i += blockDim.x) part[(size_t)blockIdx.x * n + i] = tab[i];
 }
 __global__ void input_bwd_reduce_kernel(const float* __restrict__ part, float* __restrict__ dwin, int n, int nz) {
     MVN_PDL_PROLOGUE();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float acc = 0.f;
-    for (int z = 0; z < nz; ++z) acc += part[(size_t)z * n + i];
+    int z = 0;
+    for (; z + 8 <= nz; z += 8) {               // eight loads in flight, added in slice order
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = part[(size_t)(z + e) * n + i];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc += v[e];
+    }
+    for (; z < nz; ++z) acc += part[(size_t)z * n + i];
     dwin[i] += acc;
 }
 
@@ -522,9 +630,11 @@ static int head_fwd(const Ctx& c, float* out) {
         if (rc2) return rc2;
     }
     if (mvn_wide_supported(g))
-        return mvn_wide_head_fwd(c.packed, c.P, g, skip, a1, out, c.scratch + c.SL.w_l0, c.scratch + c.SL.z, c.st);
+        return mvn_wide_head_fwd(c.packed, c.P, g, skip, 1, a1, out, c.scratch + c.SL.w_l0, c.scratch + c.SL.z, c.st);
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S))
         return mvn_tc_head_fwd(c.packed, c.P, g, skip, out, c.st);
+    if (mvn_wide_head_supported(g))       // e.g. the reference's test architecture: A = 256, C = 64, S = 64
+        return mvn_wide_head_fwd(c.packed, c.P, g, skip, 0, a1, out, c.scratch + c.SL.w_l0, c.scratch + c.SL.z, c.st);
     int rc;
     RowGemmArgs a = new_args(rows, g.Tn, g.A, EPI_STORE, c.packed + c.P.b1);
     a.nsrc = 1; a.src[0] = make_src(skip, MVN_F32, g.S, g.S, g.Tout, 0, 1, c.packed + c.P.w1p, g.A);
@@ -595,6 +705,11 @@ static int head_bwd(const Ctx& c, const float* out, const float* dout, const lon
     if (g.Tn <= 0) return 0;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S))
         return mvn_tc_head_bwd(c.packed, c.P, g, skip, out, dout, target, grad_loss, dskip, pg, (float*)(c.scratch + c.SL.tc_partial), c.st);
+    if (mvn_wide_head_supported(g)) {
+        const size_t half = (size_t)g.B * g.Tout * g.A * 2;
+        return mvn_wide_head_bwd(c.packed, c.P, g, skip, 0, a1, out, dout, target, grad_loss, c.scratch + c.SL.z, c.scratch + c.SL.da1,
+                                 c.scratch + c.SL.w_l0, c.scratch + c.SL.z + half, nullptr, dskip, (float*)(c.scratch + c.SL.w_colsum), pg, c.st);
+    }
     MVN_REQUIRE(dout, "the fused loss backward needs the tensor-core head (mvn_fused_loss_supported)");
     const long long rows = (long long)g.B * g.Tn;
     int rc;
@@ -708,14 +823,28 @@ static int input_bwd(const Ctx& c, const float* audio, const void* dh0, const vo
     const long long rows = (long long)g.B * g.T;
     const int n = 2 * g.A * g.C;
     MVN_REQUIRE(g.C <= 1024, "input conv gradient: residual_channels too large (%d)", g.C);
-    int nz = 4 * mvn_sm_count() / (2 * g.A); if (nz < 1) nz = 1;
-    while (nz > 1 && (size_t)nz * n > MVN_DET_WS_FLOATS) --nz;
-    if (nz > rows) nz = (int)rows;
-    const int rpz = (int)((rows + nz - 1) / nz);
-    const int threads = ((g.C + 31) / 32) * 32;
-    MVN_CUDA(mvn_launch_pdl(input_bwd_det_kernel, dim3(2 * g.A, nz), dim3(threads), (size_t)(0), c.st, audio,
-                            (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), dh0, dh0b, shift_b, g.adt,
-                            c.det_ws(), g.A, g.C, g.T, rows, rpz));
+    int nz;
+    const size_t table = (size_t)n * 4;
+    if (table <= 100 * 1024 && g.C <= 1024) {
+        // the table fits in shared memory (twice per SM): one block per row slice, rows applied in order
+        nz = 4 * mvn_sm_count();
+        while (nz > 1 && (size_t)nz * n > MVN_DET_WS_FLOATS) nz /= 2;
+        if (nz > rows) nz = (int)rows;
+        const int rpz = (int)((rows + nz - 1) / nz);
+        static MvnSmemAttr attr;
+        MVN_CUDA(mvn_ensure_smem(input_bwd_table_kernel, (int)table, attr));
+        MVN_CUDA(mvn_launch_pdl(input_bwd_table_kernel, dim3(nz), dim3(((g.C + 31) / 32) * 32), table, c.st, audio,
+                                (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), dh0, dh0b, shift_b, g.adt,
+                                c.det_ws(), g.A, g.C, g.T, rows, rpz));
+    } else {
+        nz = 64;                                   // row slices: 2 A x 64 blocks scan 1/64 of the rows each
+        while (nz > 1 && (size_t)nz * n > MVN_DET_WS_FLOATS) nz /= 2;
+        if (nz > rows) nz = (int)rows;
+        const int rpz = (int)((rows + nz - 1) / nz);
+        MVN_CUDA(mvn_launch_pdl(input_bwd_det_kernel, dim3(2 * g.A, nz), dim3(256), (size_t)(0), c.st, audio,
+                                (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), dh0, dh0b, shift_b, g.adt,
+                                c.det_ws(), g.A, g.C, g.T, rows, rpz));
+    }
     int rc = mvn_check_launch("input_bwd");
     if (rc) return rc;
     MVN_CUDA(mvn_launch_pdl(input_bwd_reduce_kernel, dim3(mvn_cdiv(n, 256)), dim3(256), (size_t)(0), c.st, (const float*)c.det_ws(),
@@ -801,7 +930,7 @@ extern "C" int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, co
 
 extern "C" int mvn_fused_loss_supported(const mvn_shape_t* s) {
     Geo g; if (!s || geo_init(g, s)) return 0;
-    return !g.logits && g.adt == MVN_DTYPE_BF16 && (mvn_tc_head_supported(g.A, g.S) || mvn_wide_supported(g)) && g.Tn > 0;
+    return !g.logits && g.adt == MVN_DTYPE_BF16 && (mvn_tc_head_supported(g.A, g.S) || mvn_wide_head_supported(g)) && g.Tn > 0;
 }
 
 extern "C" int mvn_wavenet_backward_loss(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,
@@ -828,8 +957,8 @@ static int backward_impl(const mvn_shape_t* s, const void* packed, const float* 
         void* dzh = c.scratch + c.SL.z; void* l1 = c.scratch + c.SL.z + half;
         void* ds16 = c.scratch + c.SL.w_ds16;
         float* cs = (float*)(c.scratch + c.SL.w_colsum); float* dbs = cs + 512 * 1024;
-        if ((rc = mvn_wide_head_bwd(c.packed, c.P, g, (const float*)(c.acts + c.AL.skip), (const float*)(c.acts + c.AL.a1), out, dout, target,
-                                    grad_loss, dzh, c.scratch + c.SL.da1, c.scratch + c.SL.w_l0, l1, ds16, cs, pg, c.st))) return rc;
+        if ((rc = mvn_wide_head_bwd(c.packed, c.P, g, (const float*)(c.acts + c.AL.skip), 1, (const float*)(c.acts + c.AL.a1), out, dout, target,
+                                    grad_loss, dzh, c.scratch + c.SL.da1, c.scratch + c.SL.w_l0, l1, ds16, nullptr, cs, pg, c.st))) return rc;
         if ((rc = mvn_wide_skip_bias_grad(ds16, g, cs, dbs, c.st))) return rc;
         void* bufs[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};
         const void* dx_next = nullptr; int cur = 0;

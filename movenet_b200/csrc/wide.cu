@@ -118,7 +118,7 @@ int launch(const Operand& A0, const Operand& A1, const void* W, int w_rows, int 
     a.n_tiles = a.tiles_per_clip * B;
     a.nkb = 0;
     for (int i = 0; i < a.nseg; ++i) a.nkb += a.seg[i].nkb;
-    MVN_REQUIRE(a.N % 128 == 0 && a.N > 0 && a.nkb > 0, "wide path: bad GEMM shape");
+    MVN_REQUIRE(a.N % 64 == 0 && a.N > 0 && a.nkb > 0, "wide path: bad GEMM shape");
     CUtensorMap mA0, mA1, mB;
     int rc;
     if ((rc = w_map(&mA0, A0.ptr, A0.cols, rows, B, BM))) return rc;
@@ -137,11 +137,12 @@ void seg(Args& a, int map, int cols, int shift, int c0 = 0) { a.seg[a.nseg++] = 
 // ------------------------------------------------------------------------------------------------ small kernels
 // bf16 K-major weight matrices from the reference tensors (ptrs in state_dict order); blockIdx.y = layer, or N for the head
 __global__ void wide_pack_kernel(const float* const* __restrict__ ptrs, float* __restrict__ packed, PackedLayout P, int C, int S,
-                                 int A, int N) {
+                                 int A, int N, int layers) {
     MVN_PDL_PROLOGUE();
     const int l = blockIdx.y;
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
     if (l < N) {
+        if (!layers) return;          // head-only use (the residual stack runs on the fused C <= 64 kernels)
         const float* const* lp = ptrs + MVN_PARAM_LAYER(l, 0);
         const float *wf = lp[0], *wg = lp[1], *wr = lp[6], *ws = lp[8];
         float* base = packed + P.layer0 + (size_t)l * P.layer_stride;
@@ -185,12 +186,12 @@ __global__ void wide_pack_kernel(const float* const* __restrict__ ptrs, float* _
             H2T[(size_t)k * A + n] = __float2bfloat16(w2[i]);
         }
         __nv_bfloat16* WsAll = (__nv_bfloat16*)(packed + P.wWsAll);
-        const int KA = N * C;
+        const int KA = layers ? N * C : 0;
         for (int i = i0; i < S * KA; i += stride) {           // WsAll[s][l C + c] = conv_skip_l.weight[s][c]
             const int sidx = i / KA, k = i - sidx * KA, l2 = k / C, c = k - l2 * C;
             WsAll[i] = __float2bfloat16(ptrs[MVN_PARAM_LAYER(l2, 8)][(size_t)sidx * C + c]);
         }
-        for (int i = i0; i < S; i += stride) {                // fixed order: deterministic
+        for (int i = i0; layers && i < S; i += stride) {      // fixed order: deterministic
             float acc = 0.f;
             for (int l2 = 0; l2 < N; ++l2) acc += ptrs[MVN_PARAM_LAYER(l2, 9)][i];
             packed[P.wbsum + i] = acc;
@@ -420,9 +421,11 @@ int wgrad_launch(WgArgs& a, const WgTensors& t, const Geo& g, float* partial, cu
 // ================================================================================================ public (library-internal) API
 int mvn_wide_supported(const Geo& g) { return wide_ok(g); }
 
+int mvn_wide_head_supported(const Geo& g) { return wide_ok(g) || wide_head_ok(g); }
+
 int mvn_wide_pack(const float* const* param_ptrs_dev, float* packed, const PackedLayout& P, const Geo& g, cudaStream_t st) {
     dim3 grid(64, g.N + 1);
-    MVN_CUDA(mvn_launch_pdl(wide_pack_kernel, dim3(grid), dim3(256), (size_t)0, st, param_ptrs_dev, packed, P, g.C, g.S, g.A, g.N));
+    MVN_CUDA(mvn_launch_pdl(wide_pack_kernel, dim3(grid), dim3(256), (size_t)0, st, param_ptrs_dev, packed, P, g.C, g.S, g.A, g.N, (int)wide_ok(g)));
     return mvn_check_launch("wide_pack");
 }
 
@@ -465,11 +468,13 @@ int mvn_wide_skip_fwd(const void* gated_all, float* skip, const float* packed, c
 }
 
 // DenseConv + drop-last + softmax (movenet/modules.py:133-142, wavenet.py:183-191)
-int mvn_wide_head_fwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, float* a1, float* out, void* l0, void* l1,
-                      cudaStream_t st) {
+// skip_on_T: skip_sum lives on the T row space (the wide layer path: row j of the head is row j + RF - 1 of it); otherwise it
+// is the (B, Tout, S) tensor of the fused C <= 64 layer kernels
+int mvn_wide_head_fwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, int skip_on_T, float* a1, float* out,
+                      void* l0, void* l1, cudaStream_t st) {
     int rc;
-    // (skip_sum lives on the T row space in the wide path: row j of the head is row j + RF - 1 of it)
-    MVN_CUDA(mvn_launch_pdl(lrelu16_kernel, dim3(2 * mvn_sm_count()), dim3(256), (size_t)0, st, skip, (__nv_bfloat16*)l0, g.B, g.Tout, g.Tout, g.S, g.T, g.RF - 1));
+    const int srows = skip_on_T ? g.T : g.Tout, sshift = skip_on_T ? g.RF - 1 : 0;
+    MVN_CUDA(mvn_launch_pdl(lrelu16_kernel, dim3(2 * mvn_sm_count()), dim3(256), (size_t)0, st, skip, (__nv_bfloat16*)l0, g.B, g.Tout, g.Tout, g.S, srows, sshift));
     if ((rc = mvn_check_launch("lrelu16"))) return rc;
     {
         Args a = new_args();
@@ -484,12 +489,16 @@ int mvn_wide_head_fwd(const float* packed, const PackedLayout& P, const Geo& g, 
 }
 
 // head backward: d(skip) (bf16, T row space) and the head's weight / bias gradients
-int mvn_wide_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, const float* a1, const float* probs,
-                      const float* dout, const long long* target, const float* grad_loss, void* dzh, void* da1, void* l0, void* l1,
-                      void* ds16, float* colsum_ws, float* pg, cudaStream_t st) {
+// ds16 != null: d(skip) as bf16 on the T row space (what the wide layer kernels read); else dskip32: fp32 (B, Tout, S) (what the
+// fused C <= 64 layer kernels read)
+int mvn_wide_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, int skip_on_T, const float* a1,
+                      const float* probs, const float* dout, const long long* target, const float* grad_loss, void* dzh, void* da1,
+                      void* l0, void* l1, void* ds16, float* dskip32, float* colsum_ws, float* pg, cudaStream_t st) {
     int rc;
     const long long rows = (long long)g.B * g.Tout;
-    MVN_CUDA(cudaMemsetAsync(ds16, 0, (size_t)g.B * g.T * g.S * 2, st));
+    const int srows = skip_on_T ? g.T : g.Tout, sshift = skip_on_T ? g.RF - 1 : 0;
+    if (ds16) MVN_CUDA(cudaMemsetAsync(ds16, 0, (size_t)g.B * g.T * g.S * 2, st));
+    else MVN_CUDA(cudaMemsetAsync(dskip32, 0, (size_t)g.B * g.Tout * g.S * 4, st));
     if (g.Tn <= 0) return 0;
     {
         dim3 grid(mvn_cdiv(g.Tout, 32), g.B);
@@ -502,7 +511,7 @@ int mvn_wide_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, 
     }
     MVN_CUDA(mvn_launch_pdl(lrelu16_kernel, dim3(2 * mvn_sm_count()), dim3(256), (size_t)0, st, a1, (__nv_bfloat16*)l1, g.B, g.Tn, g.Tout, g.A, g.Tn, 0));
     if ((rc = mvn_check_launch("lrelu16"))) return rc;
-    MVN_CUDA(mvn_launch_pdl(lrelu16_kernel, dim3(2 * mvn_sm_count()), dim3(256), (size_t)0, st, skip, (__nv_bfloat16*)l0, g.B, g.Tout, g.Tout, g.S, g.T, g.RF - 1));
+    MVN_CUDA(mvn_launch_pdl(lrelu16_kernel, dim3(2 * mvn_sm_count()), dim3(256), (size_t)0, st, skip, (__nv_bfloat16*)l0, g.B, g.Tout, g.Tout, g.S, srows, sshift));
     if ((rc = mvn_check_launch("lrelu16"))) return rc;
     // conv2: dW2p[k][n] = sum_t lrelu(a1)[t][k] dz[t][n] ; db2 = sum_t dz
     if ((rc = gemm_tn(l1, g.A, dzh, g.A, pg + P.w2p, g.A, g.A, g.A, rows, false, st))) return rc;
@@ -520,7 +529,9 @@ int mvn_wide_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, 
     // d(skip_sum) = (d(a1) . W1) * lrelu'(skip_sum), written at row t = j + RF - 1 of the (B, T, S) gradient every layer reads
     Args a = new_args();
     seg(a, 0, g.A, 0);
-    a.N = g.S; a.aux = skip; a.ld_aux = g.S; a.aux_rows = g.T; a.aux_shift = g.RF - 1; a.out = ds16; a.ld_out = g.S; a.out_rows = g.T; a.out_shift = g.RF - 1; a.Tn = g.Tn;
+    a.N = g.S; a.aux = skip; a.ld_aux = g.S; a.aux_rows = srows; a.aux_shift = sshift; a.ld_out = g.S; a.Tn = g.Tn;
+    if (ds16) { a.out = ds16; a.out_rows = g.T; a.out_shift = g.RF - 1; }
+    else { a.out = dskip32; a.out_rows = g.Tout; a.out_shift = 0; a.out_fp32 = 1; }
     return launch<EPI_LRELU_BWD>(Operand{da1, g.A}, Operand{nullptr, 0}, packed + P.wH1T, g.S, g.A, a, g.B, g.Tout, st);
 }
 

@@ -71,6 +71,7 @@ struct Args {
     int n_resid, S, Tout, RF, skip_init;      // EPI_RESID_SKIP
     int Tn, logits;                           // EPI_HEAD2: columns the caller receives; raw logits instead of softmax
     int out_rows, out_shift, aux_rows, aux_shift;   // EPI_LRELU_BWD: rows per clip of `out` / `aux` and the row shifts into them
+    int out_fp32;                                   // EPI_LRELU_BWD: store fp32 instead of bf16
 };
 
 // ---- cluster / pair helpers ----------------------------------------------------------------------------------------
@@ -385,7 +386,7 @@ __device__ __forceinline__ void epilogue(const Args& a, const uint4* pre, uint32
         } else if (EPI == EPI_LRELU_BWD) {
             if (t >= a.Tn) continue;          // the dropped last column keeps a zero gradient
             const float* pre = (const float*)a.aux + ((size_t)b * a.aux_rows + t + a.aux_shift) * a.ld_aux + n;
-            __nv_bfloat16* dst = (__nv_bfloat16*)a.out + ((size_t)b * a.out_rows + t + a.out_shift) * a.ld_out + n;
+            const size_t orow = ((size_t)b * a.out_rows + t + a.out_shift) * a.ld_out + n;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 p0 = ((const float4*)(pre + 8 * q))[0], p1 = ((const float4*)(pre + 8 * q))[1];
@@ -393,7 +394,10 @@ __device__ __forceinline__ void epilogue(const Args& a, const uint4* pre, uint32
                 float o[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * q + e]) * mvn_lrelu_grad(pv[e]);
-                st_bf16x8(dst + 8 * q, o);
+                if (a.out_fp32) {
+                    float4* d4 = (float4*)((float*)a.out + orow + 8 * q);
+                    d4[0] = make_float4(o[0], o[1], o[2], o[3]); d4[1] = make_float4(o[4], o[5], o[6], o[7]);
+                } else st_bf16x8((__nv_bfloat16*)a.out + orow + 8 * q, o);
             }
         }
     }

@@ -111,3 +111,38 @@ def test_wide_path_full_clip_properties():
         assert torch.equal(p[:, :, :100000 - m.receptive_fields], p2[:, :, :100000 - m.receptive_fields])
         assert not torch.equal(p[:, :, 100000:], p2[:, :, 100000:])
         assert torch.equal(m(codes[1:2])[0], p[1])
+
+
+@pytest.mark.parametrize("kw", [
+    dict(layer_size=4, stack_size=2, input_channels=256, residual_channels=64, skip_channels=64),    # the reference's test architecture (tests/test_model.py:42-48), shortened
+    dict(layer_size=3, stack_size=1, input_channels=128, residual_channels=32, skip_channels=64),    # narrow stack (zero-padded to 64), A = 128
+])
+def test_reference_test_architecture_head_runs_on_the_wide_engine(kw):
+    """A = 256 / S = 64 (the architecture of the reference's own test): the residual stack runs on the fused C <= 64 tcgen05
+    kernels, the DenseConv head + softmax and their backward on the wide engine's head kernels (not on CUDA-core GEMMs)"""
+    shape, p, m, codes, audio = make(kw, 21, 2, 900)
+    s = m._shape(2, audio.shape[2], False, True, False)
+    assert _lib.load().mvn_kernel_path(C.byref(s)) == 1
+    assert _lib.load().mvn_fused_loss_supported(C.byref(s)) == 1
+    RF = shape.receptive_fields
+    with torch.no_grad():
+        logits = m(audio.cuda(), output_unnormalized=False)
+    ref_logits = orc.forward(p, shape, audio, output_unnormalized=False)
+    assert (logits.cpu() - ref_logits).abs().max().item() <= LOGIT_RTOL * ref_logits.abs().max().item()
+    n0 = _lib.load().mvn_launch_count()
+    out = m(audio.cuda())
+    target = audio.cuda()[:, :, RF:].argmax(1)
+    loss = F.cross_entropy(out, target)
+    assert type(loss.grad_fn).__name__.startswith("_FusedLoss")
+    loss.backward()
+    o_loss, o_out, o_grads = orc.loss_and_grads(p, shape, audio)
+    assert (out.detach().cpu() - o_out).abs().max().item() <= LOGIT_RTOL * o_out.abs().max().item()
+    assert abs(loss.item() - o_loss.item()) <= LOSS_RTOL * abs(o_loss.item())
+    got = dict(m.named_parameters())
+    errs = {k: rel_l2(got[k].grad.cpu(), g) for k, g in o_grads.items()
+            if g is not None and not k.startswith("video_") and ".context_conv_" not in k}
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < 0.15, (worst, errs[worst])
+    a = torch.cat([got[k].grad.cpu().flatten() for k in errs])
+    b = torch.cat([o_grads[k].flatten() for k in errs])
+    assert F.cosine_similarity(a, b, dim=0).item() >= GRAD_COS
