@@ -46,7 +46,10 @@ WORKLOAD = dict(name="01_audio_video_debug", layer_size=3, stack_size=3, input_c
 # the path that is tensor-bound.  Audio-only (as SURVEY's flop count), one clip per GPU.  `python bench.py --workload 03w`
 WORKLOAD_03W = dict(name="03w_scale_up_wide", layer_size=10, stack_size=3, input_channels=256,
                     residual_channels=256, skip_channels=256, batch_per_gpu=1, video=False)
-WORKLOADS = {"01": WORKLOAD, "03w": WORKLOAD_03W}
+# the architecture of the reference's own test (tests/test_model.py:14-17,42-48): 10 x 3 layers, A = 256, C = S = 64, batch 4
+WORKLOAD_TESTARCH = dict(name="reference_test_architecture", layer_size=10, stack_size=3, input_channels=256,
+                         residual_channels=64, skip_channels=64, batch_per_gpu=4, video=False)
+WORKLOADS = {"01": WORKLOAD, "03w": WORKLOAD_03W, "testarch": WORKLOAD_TESTARCH}
 # BASELINE.json configs[4]: experiments/04_kinetics_receptive_field.mk:58-71
 DECODE = dict(name="04_kinetics_receptive_field", layer_size=14, stack_size=1, input_channels=128,
               residual_channels=16, skip_channels=8)

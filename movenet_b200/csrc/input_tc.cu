@@ -1,4 +1,4 @@
-// Weight gradient of the causal input conv (movenet/modules.py:15-30) on tensor cores, C = 64, A <= 64 (AH = 1) or <= 128 (AH = 2):
+// Weight gradient of the causal input conv (movenet/modules.py:15-30) on tensor cores, C = 64, A <= 64 (AH = 1), <= 128 (AH = 2), <= 256 (AH = 4):
 //   dW[c][a][tap] = sum_t d(h0)[t][c] * x[a][t-1+tap]
 // With one-hot audio x is a one-hot matrix, so this is  OneHot^T . d(h0)  with K = time: the one-hot tiles
 // [time x 64 codes] are built in shared memory from the integer codes (exact in bf16) and used as the
@@ -23,7 +23,7 @@ struct InArgs {
 };
 
 template <int AH>
-__global__ void __launch_bounds__(128, AH == 1 ? 3 : 2)
+__global__ void __launch_bounds__(128, AH == 1 ? 3 : (AH == 2 ? 2 : 1))
 input_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_u, const InArgs a) {
     MVN_PDL_PROLOGUE();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -156,7 +156,7 @@ __global__ void input_reduce_kernel(const float* __restrict__ partial, int n_cta
 
 }  // namespace
 
-int mvn_tc_input_supported(int A, int C) { return C == 64 && A <= 128; }
+int mvn_tc_input_supported(int A, int C) { return C == 64 && A <= 256; }
 
 int mvn_tc_input_bwd(const float* audio, const int* codes, const unsigned char* dense, const void* p, const void* u,
                      float* dwin, float* partial, const Geo& g, cudaStream_t st) {
@@ -168,20 +168,25 @@ int mvn_tc_input_bwd(const float* audio, const int* codes, const unsigned char* 
     a.audio = audio; a.codes = codes; a.dense = dense; a.partial = partial;
     a.B = g.B; a.T = g.T; a.A = g.A; a.dil0 = g.dil[0]; a.has_u = u != nullptr;
     a.tiles_per_clip = (g.T + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
-    const int AH = g.A <= 64 ? 1 : 2;
+    const int AH = g.A <= 64 ? 1 : (g.A <= 128 ? 2 : 4);
     const int smem = (2 * AH + 2) * TILE_BYTES + 64 + 1024;
-    static MvnSmemAttr attr1, attr2;
+    static MvnSmemAttr attr1, attr2, attr4;
     int grid;
     if (AH == 1) {
         MVN_CUDA(mvn_ensure_smem(input_bwd_tc_kernel<1>, smem, attr1));
         grid = a.n_tiles < 3 * mvn_sm_count() ? a.n_tiles : 3 * mvn_sm_count();
         if (grid > 444) grid = 444;          // (the partial slot holds 2 x 148 x 33024 floats: 444 x 8192 fit)
         MVN_CUDA(mvn_launch_pdl(input_bwd_tc_kernel<1>, dim3(grid), dim3(128), (size_t)(smem), st, mp, mu, a));
-    } else {
+    } else if (AH == 2) {
         MVN_CUDA(mvn_ensure_smem(input_bwd_tc_kernel<2>, smem, attr2));
         grid = a.n_tiles < 2 * mvn_sm_count() ? a.n_tiles : 2 * mvn_sm_count();
         if (grid > 296) grid = 296;
         MVN_CUDA(mvn_launch_pdl(input_bwd_tc_kernel<2>, dim3(grid), dim3(128), (size_t)(smem), st, mp, mu, a));
+    } else {          // A = 256 (the reference's test architecture): four M = 128 operands, 160 KB of one-hot tiles, one CTA per SM
+        MVN_CUDA(mvn_ensure_smem(input_bwd_tc_kernel<4>, smem, attr4));
+        grid = a.n_tiles < mvn_sm_count() ? a.n_tiles : mvn_sm_count();
+        if (grid > 296) grid = 296;
+        MVN_CUDA(mvn_launch_pdl(input_bwd_tc_kernel<4>, dim3(grid), dim3(128), (size_t)(smem), st, mp, mu, a));
     }
     if ((rc = mvn_check_launch("input_bwd_tc"))) return rc;
     MVN_CUDA(mvn_launch_pdl(input_reduce_kernel, dim3((AH * IPART_MAX / 2 + 31) / 32), dim3(32, RED_SPLIT), (size_t)(0), st, partial, grid, dwin, g.A, AH));

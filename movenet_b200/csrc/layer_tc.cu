@@ -256,11 +256,18 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
                 float4 v1 = make_float4(__uint_as_float(sv[4]) + sbrs[CC + s0 + 4], __uint_as_float(sv[5]) + sbrs[CC + s0 + 5],
                                         __uint_as_float(sv[6]) + sbrs[CC + s0 + 6], __uint_as_float(sv[7]) + sbrs[CC + s0 + 7]);
                 float4* d4 = (float4*)(skip_dst + s0);
+                if (!a.skip_init && s0 != 0) {
+                    // channels past the prefetched eight (skip_channels > 8): a vector reduction executed by L2 instead of a
+                    // load-add-store of the same line by one thread, which serialises on the store's round trip (measured on
+                    // the wide path: 25x; here 233 -> see profiles/ us per layer at S = 64).  One add per element and launch,
+                    // launches in layer order: deterministic.
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d4), "f"(v0.x), "f"(v0.y), "f"(v0.z), "f"(v0.w) : "memory");
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d4 + 1), "f"(v1.x), "f"(v1.y), "f"(v1.z), "f"(v1.w) : "memory");
+                    continue;
+                }
                 if (!a.skip_init) {
-                    float4 p0, p1;
-                    if (s0 == 0) { p0 = old0; p1 = old1; } else { p0 = d4[0]; p1 = d4[1]; }
-                    v0.x += p0.x; v0.y += p0.y; v0.z += p0.z; v0.w += p0.w;
-                    v1.x += p1.x; v1.y += p1.y; v1.z += p1.z; v1.w += p1.w;
+                    v0.x += old0.x; v0.y += old0.y; v0.z += old0.z; v0.w += old0.w;
+                    v1.x += old1.x; v1.y += old1.y; v1.z += old1.z; v1.w += old1.w;
                 }
                 d4[0] = v0; d4[1] = v1;
             }

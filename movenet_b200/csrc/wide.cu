@@ -245,39 +245,53 @@ __global__ void onehot16_kernel(const float* __restrict__ audio, const int* __re
 __global__ void __launch_bounds__(256) head_dz16_kernel(const float* __restrict__ probs, const float* __restrict__ dout,
                                                         const long long* __restrict__ target, const float* __restrict__ gloss,
                                                         __nv_bfloat16* __restrict__ dz, int A, int Tn, int Tout, int logits, float inv_count) {
-    extern __shared__ float tile[];        // p[32][A+1], dp[32][A+1]
+    extern __shared__ float tile[];        // p[32][A+1] (, dp[32][A+1] when d(out) is given)
     const int b = blockIdx.y, j0 = blockIdx.x * 32, ld = A + 1;
     float* tp = tile; float* td = tile + 32 * ld;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int j = j0 + lane;
-    if (j < Tn)
+    if (j < Tn) {
+#pragma unroll 4
         for (int a = warp; a < A; a += nw) {
             const size_t o = ((size_t)b * A + a) * Tn + j;
             if (dout) td[lane * ld + a] = dout[o];
             if (!logits) tp[lane * ld + a] = probs[o];
         }
+    }
     __syncthreads();
+    const int per = A / 32;                // channels per lane: lane, lane + 32, ... (A % 32 == 0, A <= 256; conflict-free tile reads)
     for (int r = warp; r < 32; r += nw) {
         const int jj = j0 + r;
         if (jj >= Tout) continue;
         __nv_bfloat16* dr = dz + ((size_t)b * Tout + jj) * A;
-        if (jj >= Tn) { for (int a = lane; a < A; a += 32) dr[a] = __float2bfloat16(0.f); continue; }
-        if (logits) { for (int a = lane; a < A; a += 32) dr[a] = __float2bfloat16(td[r * ld + a]); continue; }
-        if (!dout) {
+        if (jj >= Tn) { for (int e = 0; e < per; ++e) dr[lane + 32 * e] = __float2bfloat16(0.f); continue; }
+        if (logits) { for (int e = 0; e < per; ++e) dr[lane + 32 * e] = __float2bfloat16(td[r * ld + lane + 32 * e]); continue; }
+        float p[8], dp[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) p[e] = e < per ? tp[r * ld + lane + 32 * e] : 0.f;
+        if (dout) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dp[e] = e < per ? td[r * ld + lane + 32 * e] : 0.f;
+        } else {
             float m = -INFINITY;
-            for (int a = lane; a < A; a += 32) m = fmaxf(m, tp[r * ld + a]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if (e < per) m = fmaxf(m, p[e]);
             for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             float z = 0.f;
-            for (int a = lane; a < A; a += 32) { const float e = expf(tp[r * ld + a] - m); td[r * ld + a] = e; z += e; }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { dp[e] = e < per ? expf(p[e] - m) : 0.f; z += dp[e]; }
             for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
             const float gs = gloss[0] * inv_count, inv = gs / z;
             const int tg = (int)target[(size_t)b * Tn + jj];
-            for (int a = lane; a < A; a += 32) td[r * ld + a] = td[r * ld + a] * inv - (a == tg ? gs : 0.f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dp[e] = dp[e] * inv - (lane + 32 * e == tg ? gs : 0.f);
         }
         float dot = 0.f;
-        for (int a = lane; a < A; a += 32) dot = fmaf(td[r * ld + a], tp[r * ld + a], dot);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dot = fmaf(dp[e], p[e], dot);
         for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        for (int a = lane; a < A; a += 32) dr[a] = __float2bfloat16(tp[r * ld + a] * (td[r * ld + a] - dot));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (e < per) dr[lane + 32 * e] = __float2bfloat16(p[e] * (dp[e] - dot));
     }
 }
 
@@ -502,9 +516,9 @@ int mvn_wide_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, 
     if (g.Tn <= 0) return 0;
     {
         dim3 grid(mvn_cdiv(g.Tout, 32), g.B);
-        const size_t smem = (size_t)2 * 32 * (g.A + 1) * 4;
+        const size_t smem = (size_t)(dout ? 2 : 1) * 32 * (g.A + 1) * 4;      // (the d(out) tile only when d(out) is given)
         static MvnSmemAttr attr;
-        MVN_CUDA(mvn_ensure_smem(head_dz16_kernel, (int)smem, attr));
+        MVN_CUDA(mvn_ensure_smem(head_dz16_kernel, (int)((size_t)2 * 32 * (g.A + 1) * 4), attr));
         head_dz16_kernel<<<grid, 256, smem, st>>>(probs, dout, target, grad_loss, (__nv_bfloat16*)dzh, g.A, g.Tn, g.Tout, g.logits,
                                                   1.f / ((float)g.B * (float)g.Tn));
         if ((rc = mvn_check_launch("head_dz16"))) return rc;
