@@ -90,6 +90,12 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);     // warp-uniform copy: the issue branches stay convergent
 
     // ---- one-time setup: barriers, TMEM, and the weight image (one bulk copy) --------------------
+    // INVARIANT (programmatic dependent launch): the image copy below is issued BEFORE griddepcontrol.wait, so it is ordered
+    // only after kernels that completed before the PREVIOUS kernel started.  The image is written by tc_pack_kernel
+    // (mvn_pack_weights); between that kernel and the first layer kernel of a pass there is always at least one full
+    // stream-ordered operation that is not a PDL launch (the cudaMemsetAsync of the skip buffer in mvn_wavenet_forward /
+    // mvn_layer_fwd, the memsets at the top of the backward), which drains the pack kernels.  Keep such an operation there
+    // (or move this copy below the wait) when reordering launches.
     if (tid == 0) {
         mbar_init(full_bar, 1);
         mbar_init(mma_bar, 1);

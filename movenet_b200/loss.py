@@ -7,6 +7,13 @@ behaves like any tensor but recognises exactly that call (default arguments, cla
 routes it to one fused CUDA kernel pair instead of torch's log_softmax + nll_loss chain.  Any other use,
 and any other argument combination, takes torch's ordinary path, so the trainer code is unchanged and
 the numbers are the same function of the inputs.  ``MOVENET_B200_FUSED_CE=0`` switches the routing off.
+
+Limits of the fused route (it is taken for the default arguments only): targets must be valid class indices in
+[0, channels) -- torch's default ``ignore_index=-100`` is accepted as an argument but such targets are NOT ignored (the
+trainers never produce them: ``target = audio[:, :, RF:].argmax(1)``); an out-of-range target contributes
+``logsumexp`` without a picked probability instead of raising.  The output of one ``forward`` may feed several loss
+terms (the fused node plus any other differentiable use): every autograd node of the pass runs once, a second pass
+through the same node raises like torch without ``retain_graph``.
 """
 import ctypes as C
 import os
@@ -67,8 +74,10 @@ class _FusedLoss(torch.autograd.Function):
     def backward(ctx, grad_loss):
         st = ctx.state
         target, probs = ctx.saved_tensors
-        if st.acts is None:
-            raise RuntimeError("the activations of this forward pass were already consumed by a backward pass")
+        key = ("loss", id(ctx))
+        if key in st.done:
+            raise RuntimeError("Trying to backward through the fused loss node a second time (the reference would need retain_graph=True)")
+        st.done.add(key)
         module, bufs, audio, video = st.module, st.bufs, st.audio, st.video
         g = grad_loss.contiguous().float()
         pg = bufs.get_packed_grads()
@@ -77,7 +86,6 @@ class _FusedLoss(torch.autograd.Function):
                       0 if audio.dim() == 2 else audio.data_ptr(), 0 if video is None else video.data_ptr(),
                       st.acts.data_ptr(), probs.data_ptr(), target.data_ptr(), g.data_ptr(), pg.data_ptr(),
                       bufs.get_scratch().data_ptr(), _stream())
-            st.acts = None
             flat, views = module._flat_grads(st.has_video, audio.device)
             offs = module._grad_offsets(st.has_video, audio.device)
             _lib.call("mvn_unpack_grads", C.byref(bufs.shape), pg.data_ptr(), flat.data_ptr(), offs.data_ptr(),

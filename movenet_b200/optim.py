@@ -4,7 +4,11 @@
 ``torch.optim.AdamW`` (the optimizer ``movenet/pytorch_lightning_trainer.py:128-202`` builds by default) and, optionally, the
 global gradient-norm clip of ``:233-243`` (``max_grad_norm``) folded into the same pass.  The model has 10 N + 13 small
 tensors; torch's fused multi-tensor AdamW needs three launches for them, this one needs one (two when clipping), and nothing
-is read back to the host.  Parameters without a gradient are skipped, like in torch.  CUDA fp32 parameters only.
+is read back to the host.  Parameters without a gradient are skipped, like in torch, and -- like in torch -- every
+parameter keeps its OWN step counter (``state[p]["step"]``), so a parameter that only intermittently receives a gradient
+(the video / context tensors when batches mix video and no-video) gets its own bias correction: parameters are grouped by
+step count, one launch per distinct count (one in the usual case).  The clip norm is global over all groups' gradients.
+A ``torch.optim.AdamW`` state_dict loads (its per-parameter ``step`` is taken over).  CUDA fp32 parameters only.
 """
 import ctypes as C
 import math
@@ -23,9 +27,9 @@ class AdamW(torch.optim.Optimizer):
         self._tables = {}          # group index -> (key, segments_dev, chunks_dev, n_chunks, partials)
         self.grad_norm = None      # device scalar holding the last pre-clip gradient norm (when clipping)
 
-    def _table(self, gi, active):
+    def _table(self, key_id, active):
         key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in active)
-        cached = self._tables.get(gi)
+        cached = self._tables.get(key_id)
         if cached is not None and cached[0] == key:
             return cached
         dev = active[0].device
@@ -40,8 +44,8 @@ class AdamW(torch.optim.Optimizer):
         seg_dev = torch.from_numpy(seg).to(dev)
         chunks_dev = torch.tensor(chunks, dtype=torch.int32, device=dev)
         partials = torch.empty(len(chunks), dtype=torch.float32, device=dev)
-        self._tables[gi] = (key, seg_dev, chunks_dev, len(chunks), partials)
-        return self._tables[gi]
+        self._tables[key_id] = (key, seg_dev, chunks_dev, len(chunks), partials)
+        return self._tables[key_id]
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -58,20 +62,27 @@ class AdamW(torch.optim.Optimizer):
                         and p.grad.dtype == torch.float32 and not p.grad.is_sparse):
                     raise RuntimeError("movenet_b200.optim.AdamW: contiguous CUDA fp32 parameters and gradients only")
                 st = self.state[p]
-                if not st:
+                if "exp_avg" not in st:
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            group["step"] = group.get("step", 0) + 1
-            t = group["step"]
+                # per-parameter step (torch keeps a tensor; a loaded torch state_dict is taken over)
+                st["step"] = int(st.get("step", 0)) + 1
             b1, b2 = group["betas"]
-            _, seg_dev, chunks_dev, n_chunks, partials = self._table(gi, active)
             clip = group.get("max_grad_norm") or 0.0
+            by_step = {}
+            for p in active:
+                by_step.setdefault(self.state[p]["step"], []).append(p)
+            if clip > 0 and len(by_step) > 1:
+                raise RuntimeError("movenet_b200.optim.AdamW: max_grad_norm needs all parameters of a group to have the same "
+                                   "step count (the clip norm is computed inside the one launch)")
             if clip > 0 and self.grad_norm is None:
                 self.grad_norm = torch.zeros(1, dtype=torch.float32, device=active[0].device)
-            with torch.cuda.device(active[0].device):
-                _lib.call("mvn_adamw_step", seg_dev.data_ptr(), chunks_dev.data_ptr(), n_chunks, float(group["lr"]), float(b1),
-                          float(b2), float(group["eps"]), float(group["weight_decay"]), 1.0 - math.pow(b1, t),
-                          1.0 - math.pow(b2, t), float(clip), partials.data_ptr(),
-                          self.grad_norm.data_ptr() if clip > 0 else 0, torch.cuda.current_stream().cuda_stream)
+            for si, (t, plist) in enumerate(sorted(by_step.items())):
+                _, seg_dev, chunks_dev, n_chunks, partials = self._table((gi, si), plist)
+                with torch.cuda.device(plist[0].device):
+                    _lib.call("mvn_adamw_step", seg_dev.data_ptr(), chunks_dev.data_ptr(), n_chunks, float(group["lr"]), float(b1),
+                              float(b2), float(group["eps"]), float(group["weight_decay"]), 1.0 - math.pow(b1, t),
+                              1.0 - math.pow(b2, t), float(clip), partials.data_ptr(),
+                              self.grad_norm.data_ptr() if clip > 0 else 0, torch.cuda.current_stream().cuda_stream)
             _lib.weights_epoch[0] += 1       # the parameters were rewritten behind autograd's version counters
         return loss

@@ -77,7 +77,7 @@ class _ForwardState:
     is taken straight from the returned probabilities, by the fused loss node (loss.py)"""
     # (never the output tensor itself: output -> grad_fn -> this object -> output would be a reference cycle that keeps a
     # whole step's activations alive until the garbage collector runs)
-    __slots__ = ("module", "bufs", "acts", "audio", "video", "out_ptr", "has_video", "fused_loss_ok")
+    __slots__ = ("module", "bufs", "acts", "audio", "video", "out_ptr", "has_video", "fused_loss_ok", "done")
 
 
 class _WaveNetFunction(torch.autograd.Function):
@@ -100,6 +100,7 @@ class _WaveNetFunction(torch.autograd.Function):
         st = _ForwardState()
         st.module, st.bufs, st.acts, st.audio, st.video, st.out_ptr = module, bufs, acts, audio, video, out.data_ptr()
         st.has_video = video is not None
+        st.done = set()          # autograd nodes of this forward pass that have run their backward (each may run once)
         st.fused_loss_ok = bool(_lib.load().mvn_fused_loss_supported(C.byref(shape)))
         ctx.state = st
         ctx.save_for_backward(out)
@@ -111,14 +112,17 @@ class _WaveNetFunction(torch.autograd.Function):
         st = ctx.state
         module, bufs, audio, video = st.module, st.bufs, st.audio, st.video
         (out,) = ctx.saved_tensors
-        if st.acts is None:
-            raise RuntimeError("the activations of this forward pass were already consumed by a backward pass")
+        # The activations stay alive as long as the graph does (like autograd's saved tensors): the same output may feed
+        # several loss terms -- e.g. the fused cross-entropy node (loss.py) plus another differentiable use -- and each node
+        # runs its backward once per pass; a SECOND pass through the same node raises like torch does without retain_graph.
+        if "net" in st.done:
+            raise RuntimeError("Trying to backward through the WaveNet graph a second time (the reference would need retain_graph=True)")
+        st.done.add("net")
         dout = dout.contiguous().float()
         pg = bufs.get_packed_grads()
         _lib.call("mvn_wavenet_backward", C.byref(bufs.shape), bufs.packed.data_ptr(), 0 if audio.dim() == 2 else audio.data_ptr(),
                   0 if video is None else video.data_ptr(), st.acts.data_ptr(), out.data_ptr(), dout.data_ptr(),
                   pg.data_ptr(), bufs.get_scratch().data_ptr(), _stream())
-        st.acts = None
         flat, views = module._flat_grads(st.has_video, audio.device)
         offs = module._grad_offsets(st.has_video, audio.device)
         _lib.call("mvn_unpack_grads", C.byref(bufs.shape), pg.data_ptr(), flat.data_ptr(), offs.data_ptr(),

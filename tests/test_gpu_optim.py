@@ -68,3 +68,33 @@ def test_adamw_is_an_optimizer():
     cpu.grad = torch.ones(3)
     with pytest.raises(RuntimeError):
         movenet_b200.optim.AdamW([cpu], lr=1e-3).step()
+
+
+def test_adamw_per_parameter_step_counts_match_torch():
+    """a parameter that only intermittently receives a gradient (the video / context tensors when batches mix video and
+    no-video) keeps its own step counter and bias correction, like torch.optim.AdamW; a torch state_dict loads"""
+    torch.manual_seed(0)
+    pa = [torch.nn.Parameter(torch.randn(257, device="cuda")), torch.nn.Parameter(torch.randn(33, 5, device="cuda"))]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    ours = movenet_b200.optim.AdamW(pa, lr=1e-2, weight_decay=0.01)
+    ref = torch.optim.AdamW(pb, lr=1e-2, weight_decay=0.01)
+    for step in range(5):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            if i == 1 and step % 2 == 1:          # the second parameter skips every other step
+                a.grad = None; b.grad = None
+                continue
+            g = torch.randn_like(a)
+            a.grad = g.clone(); b.grad = g.clone()
+        ours.step(); ref.step()
+        for a, b in zip(pa, pb):
+            assert torch.allclose(a, b, rtol=1e-6, atol=2e-8), (step, (a - b).abs().max().item())
+    assert ours.state[pa[0]]["step"] == 5 and ours.state[pa[1]]["step"] == 3
+    # warm start from torch's optimizer state: moments AND step counters are taken over
+    fresh = movenet_b200.optim.AdamW(pa, lr=1e-2, weight_decay=0.01)
+    fresh.load_state_dict(copy.deepcopy(ref.state_dict()))     # (load_state_dict may alias the tensors it is given)
+    for a, b in zip(pa, pb):
+        g = torch.randn_like(a)
+        a.grad = g.clone(); b.grad = g.clone()
+    fresh.step(); ref.step()
+    for a, b in zip(pa, pb):
+        assert torch.allclose(a, b, rtol=1e-6, atol=2e-8)

@@ -409,3 +409,25 @@ def test_fp32_exact_mode_is_bit_reproducible(name):
         assert torch.equal(out, runs[0][0]) and torch.equal(loss, runs[0][1])
         for k, g in grads.items():
             assert torch.equal(g, runs[0][2][k]), k
+
+
+def test_two_loss_terms_on_one_forward_output():
+    """the output of one forward() may feed several loss terms: the fused cross-entropy node plus another
+    differentiable use of the same tensor -- gradients add up exactly like in the reference's graph"""
+    fx = load_golden("cfg03")
+    audio = golden_audio(fx).cuda()
+    grads = []
+    for fused in (True, False):
+        m = build(fx, "bf16")
+        target = audio[:, :, m.receptive_fields:].argmax(1)
+        out = m(audio)
+        probs = out if fused else out.as_subclass(torch.Tensor)
+        loss = F.cross_entropy(probs, target) + 0.5 * (out.as_subclass(torch.Tensor) ** 2).mean()
+        if fused:
+            assert "_FusedLoss" in type(loss.grad_fn.next_functions[0][0]).__name__
+        loss.backward()
+        grads.append({k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+        with pytest.raises(RuntimeError):
+            loss.backward()            # a second pass through the same graph raises, like torch without retain_graph
+    for k in grads[0]:
+        assert rel_l2(grads[0][k], grads[1][k]) < 2e-2, k
