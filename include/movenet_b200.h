@@ -51,6 +51,8 @@ typedef struct mvn_shape {
     int act_dtype;          /* MVN_DTYPE_F32 (exact mode) | MVN_DTYPE_BF16 (tensor-core mode) */
     int remove_last;        /* forward(remove_last=...) */
     int output_logits;      /* 1: raw logits (output_unnormalized=False, sic), 0: softmax probabilities */
+    int no_grad;            /* 1: inference-only forward -- what only a backward pass needs is neither computed nor stored
+                               (the wide path's gate-derivative factors); mvn_wavenet_backward* then refuses the activations */
 } mvn_shape_t;
 
 /* index of each reference parameter in the pointer tables (state_dict order) */

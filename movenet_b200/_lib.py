@@ -17,7 +17,7 @@ class Shape(C.Structure):
     """mirror of mvn_shape_t"""
     _fields_ = [(n, C.c_int) for n in (
         "layer_size", "stack_size", "input_channels", "residual_channels", "skip_channels",
-        "context_in_channels", "batch", "frames", "has_video", "act_dtype", "remove_last", "output_logits")]
+        "context_in_channels", "batch", "frames", "has_video", "act_dtype", "remove_last", "output_logits", "no_grad")]
 
     def key(self):
         return tuple(getattr(self, n) for n, _ in self._fields_)

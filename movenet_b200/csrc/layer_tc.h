@@ -46,8 +46,8 @@ int mvn_tc_upsample_bwd(const float* img, const void* u_bf16, const void* dout_b
 // ---- wide-channel path (wide.cu): weight-streaming tcgen05 GEMMs with fused epilogues, residual_channels >= 128 -------------
 int mvn_wide_supported(const Geo& g);
 int mvn_wide_pack(const float* const* param_ptrs_dev, float* packed, const PackedLayout& P, const Geo& g, cudaStream_t st);
-int mvn_wide_layer_fwd(const void* x_in, void* x_out, void* gated_all, const float* packed, const PackedLayout& P, const Geo& g,
-                       int l, cudaStream_t st);
+int mvn_wide_layer_fwd(const void* x_in, void* x_out, void* gated_all, void* gab_all, const float* packed, const PackedLayout& P,
+                       const Geo& g, int l, cudaStream_t st);
 int mvn_wide_skip_fwd(const void* gated_all, float* skip, const float* packed, const PackedLayout& P, const Geo& g, cudaStream_t st);
 int mvn_wide_head_supported(const Geo& g);     // the wide engine's head kernels (also for C <= 64 models with A = 128 / 256, S % 64 == 0)
 int mvn_wide_head_fwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, int skip_on_T, float* a1, float* out,
@@ -56,7 +56,7 @@ int mvn_wide_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, 
                       const float* probs, const float* dout, const long long* target, const float* grad_loss, void* dzh, void* da1,
                       void* l0, void* l1, void* ds16, float* dskip32, float* colsum_ws, float* pg, cudaStream_t st);
 int mvn_wide_skip_bias_grad(const void* ds16, const Geo& g, float* colsum_ws, float* out_S, cudaStream_t st);
-int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, const void* ds16, void* dgated, const void* gated_all, void* dz,
+int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, const void* ds16, const void* gab_all, const void* gated_all, void* dz,
                        const float* dbs, const float* packed, float* pg, float* colsum_ws, float* wgpart, const PackedLayout& P, const Geo& g,
                        int l, cudaStream_t st);
 int mvn_wide_input_bwd(const float* audio, const int* codes, const unsigned char* dense, const void* dh0, void* oh16, float* pg,

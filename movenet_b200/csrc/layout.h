@@ -10,7 +10,7 @@
 #define MVN_TC_IMG_BYTES (4 * 16384 + 1024)
 
 struct Geo {
-    int L, St, A, C, S, Cin, B, T, video, adt, remove_last, logits;
+    int L, St, A, C, S, Cin, B, T, video, adt, remove_last, logits, no_grad;
     int Cl;       // the model's residual_channels; C is the PHYSICAL channel count of every internal buffer: in the
                   // tensor-core (bf16) mode narrower models are zero-padded to 64 channels (the pad stays exactly zero
                   // through every layer: tanh(0)*sigmoid(0) = 0), so one set of C = 64 kernels serves them all
@@ -31,6 +31,7 @@ static inline int geo_init(Geo& g, const mvn_shape_t* s) {
            s->skip_channels <= (s->has_video ? 32 : 64)) ? 64 : g.Cl;
     g.S = s->skip_channels; g.Cin = s->context_in_channels; g.B = s->batch; g.T = s->frames;
     g.video = s->has_video; g.adt = s->act_dtype; g.remove_last = s->remove_last; g.logits = s->output_logits;
+    g.no_grad = s->no_grad;
     g.N = g.L * g.St;
     if (g.L < 1 || g.St < 1 || g.N > MVN_MAX_LAYERS || g.L > 24) return -1;
     long long rf = g.St;
@@ -142,6 +143,8 @@ struct ActsLayout {
     size_t a1;        // (B,Tn,A) fp32 : dense_conv.conv1 output (pre-activation)
     size_t enc, u1, u2; // video: (B,160,C) (B,1600,C) (B,16000,C) fp32
     size_t w_gated;   // wide path: (B,T,N C) bf16, the gated activations of every layer side by side (layer l: columns l C ..)
+    size_t w_gab;     // wide path, training: (B,T,N 2C) bf16, the gate's derivative factors (a_c, b_c) interleaved, per layer:
+                      //   a = sigma(g) (1 - tanh(f)^2), b = tanh(f) sigma(g) (1 - sigma(g))  ->  dz = d(gated) * (a, b)
     size_t total;
 };
 
@@ -162,6 +165,7 @@ static inline void acts_layout(const Geo& g, ActsLayout& a) {
         a.u2 = take((size_t)g.B * 16000 * g.C * 4);
     } else a.enc = a.u1 = a.u2 = 0;
     a.w_gated = take(wide_ok(g) ? BT * g.N * g.C * 2 : 0);
+    a.w_gab = take(wide_ok(g) && !g.no_grad ? BT * g.N * 2 * g.C * 2 : 0);
     a.total = o;
 }
 

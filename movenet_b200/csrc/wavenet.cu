@@ -476,6 +476,8 @@ extern "C" size_t mvn_acts_offset(const mvn_shape_t* s, int which, int layer) {
     Geo g; if (!s || geo_init(g, s)) return 0; ActsLayout a; acts_layout(g, a);
     if (which == 0) return a.x0 + (size_t)(layer >= 0 && layer < g.N ? layer : 0) * a.x_stride;
     if (which == 2) return a.ctx;
+    if (which == 3) return a.w_gab;
+    if (which == 4) return a.w_gated;
     return 0;
 }
 // which kernel family serves this shape: 0 CUDA-core fp32 / generic, 1 tcgen05 fused layer kernels (C = 64 physical),
@@ -596,7 +598,8 @@ static int layer_fwd(const Ctx& c, int l) {
     float* skip = (float*)(c.acts + c.AL.skip);
     void* ctx = g.video ? c.acts + c.AL.ctx : nullptr;
     if (mvn_wide_supported(g))
-        return mvn_wide_layer_fwd(c.x(l), last ? nullptr : c.x(l + 1), c.acts + c.AL.w_gated, c.packed, c.P, g, l, c.st);
+        return mvn_wide_layer_fwd(c.x(l), last ? nullptr : c.x(l + 1), c.acts + c.AL.w_gated, g.no_grad ? nullptr : c.acts + c.AL.w_gab,
+                                  c.packed, c.P, g, l, c.st);
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
         return mvn_tc_layer_fwd(c.x(l), ctx, last ? nullptr : c.x(l + 1), skip, lw, c.P, g, l, c.st);
     }
@@ -901,7 +904,7 @@ extern "C" int mvn_layer_bwd(const mvn_shape_t* s, const void* packed, int layer
     if (mvn_wide_supported(g)) {
         float* cs = (float*)(c.scratch + c.SL.w_colsum);
         return mvn_wide_layer_bwd(c.x(layer), layer + 1 < g.N ? c.scratch + c.SL.dxa : nullptr, c.scratch + c.SL.dxb, c.scratch + c.SL.w_ds16,
-                                  c.scratch + c.SL.dgated, c.acts + c.AL.w_gated, c.scratch + c.SL.dz, cs + 512 * 1024, c.packed, pg, cs,
+                                  c.acts + c.AL.w_gab, c.acts + c.AL.w_gated, c.scratch + c.SL.dz, cs + 512 * 1024, c.packed, pg, cs,
                                   (float*)(c.scratch + c.SL.w_wgpart), c.P, g, layer, c.st);
     }
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video)) {
@@ -930,7 +933,7 @@ extern "C" int mvn_wavenet_backward(const mvn_shape_t* s, const void* packed, co
 
 extern "C" int mvn_fused_loss_supported(const mvn_shape_t* s) {
     Geo g; if (!s || geo_init(g, s)) return 0;
-    return !g.logits && g.adt == MVN_DTYPE_BF16 && (mvn_tc_head_supported(g.A, g.S) || mvn_wide_head_supported(g)) && g.Tn > 0;
+    return !g.logits && !g.no_grad && g.adt == MVN_DTYPE_BF16 && (mvn_tc_head_supported(g.A, g.S) || mvn_wide_head_supported(g)) && g.Tn > 0;
 }
 
 extern "C" int mvn_wavenet_backward_loss(const mvn_shape_t* s, const void* packed, const float* audio, const float* video,
@@ -947,6 +950,7 @@ static int backward_impl(const mvn_shape_t* s, const void* packed, const float* 
                          void* packed_grads, void* scratch, void* stream, const char* who) {
     Ctx c; int rc = ctx_init(c, s, packed, acts, scratch, stream, who); if (rc) return rc;
     MVN_REQUIRE(packed && acts && scratch && packed_grads, "%s: null buffer", who);
+    MVN_REQUIRE(!c.g.no_grad, "%s: the forward pass ran with shape.no_grad = 1 (inference only): its activations cannot be differentiated", who);
     MVN_REQUIRE(c.g.logits || out, "%s: the probabilities returned by forward are required", who);
     const Geo& g = c.g;
     float* pg = (float*)packed_grads;
@@ -963,7 +967,7 @@ static int backward_impl(const mvn_shape_t* s, const void* packed, const float* 
         void* bufs[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};
         const void* dx_next = nullptr; int cur = 0;
         for (int l = g.N - 1; l >= 0; --l) {
-            if ((rc = mvn_wide_layer_bwd(c.x(l), dx_next, bufs[cur], ds16, c.scratch + c.SL.dgated, c.acts + c.AL.w_gated, c.scratch + c.SL.dz,
+            if ((rc = mvn_wide_layer_bwd(c.x(l), dx_next, bufs[cur], ds16, c.acts + c.AL.w_gab, c.acts + c.AL.w_gated, c.scratch + c.SL.dz,
                                          dbs, c.packed, pg, cs, (float*)(c.scratch + c.SL.w_wgpart), c.P, g, l, c.st))) return rc;
             dx_next = bufs[cur]; cur ^= 1;
         }

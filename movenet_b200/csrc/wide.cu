@@ -105,7 +105,7 @@ int launch_t(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& 
     cfg.attrs = at; cfg.numAttrs = PAIR == 2 ? 2 : 1;
     MVN_CUDA(cudaLaunchKernelEx(&cfg, wide_gemm_kernel<PAIR, EPI>, mA0, mA1, mB, mO0, mO1, a));
     static const char* names[EPI_COUNT] = {"wide_gemm<gate>", "wide_gemm<resid_skip>", "wide_gemm<store>", "wide_gemm<gate_bwd>",
-                                           "wide_gemm<add_store>", "wide_gemm<head1>", "wide_gemm<head2>", "wide_gemm<lrelu_bwd>"};
+                                           "wide_gemm<add_store>", "wide_gemm<head1>", "wide_gemm<head2>", "wide_gemm<lrelu_bwd>", "wide_gemm<dz>"};
     return mvn_check_launch(names[EPI]);
 }
 
@@ -448,16 +448,17 @@ int mvn_wide_pack(const float* const* param_ptrs_dev, float* packed, const Packe
 // K = N C whose fp32 result is written once (mvn_wide_skip_fwd) instead of a 2 KB-per-row read-modify-write of skip_sum per
 // layer (which made the per-layer residual + skip GEMM HBM-bound), and the backward reads them for the 1x1 convs' weight
 // gradients instead of re-writing them.  The last layer's residual output is discarded (modules.py:125-130): no F2.
-int mvn_wide_layer_fwd(const void* x_in, void* x_out, void* gated_all, const float* packed, const PackedLayout& P, const Geo& g,
-                       int l, cudaStream_t st) {
+int mvn_wide_layer_fwd(const void* x_in, void* x_out, void* gated_all, void* gab_all, const float* packed, const PackedLayout& P,
+                       const Geo& g, int l, cudaStream_t st) {
     const int C = g.C, d = g.dil[l], NC = g.N * C;
     const float* lw = packed + P.layer0 + (size_t)l * P.layer_stride;
     int rc;
-    {
+    {   // gab_all != null (training): the gate's derivative factors are kept next to the gated activations
         Args a = new_args();
         seg(a, 0, C, -d); seg(a, 0, C, 0);
-        a.N = 2 * C; a.out = gated_all; a.out_c0 = l * C;
-        if ((rc = launch<EPI_GATE>(Operand{x_in, C}, Operand{nullptr, 0}, lw + P.wWz, 2 * C, 2 * C, a, g.B, g.T, st, Output{gated_all, NC, g.T, 0}))) return rc;
+        a.N = 2 * C; a.out = gated_all; a.out_c0 = l * C; a.out2 = gab_all; a.out2_c0 = l * 2 * C;
+        if ((rc = launch<EPI_GATE>(Operand{x_in, C}, Operand{nullptr, 0}, lw + P.wWz, 2 * C, 2 * C, a, g.B, g.T, st, Output{gated_all, NC, g.T, 0},
+                                   Output{gab_all ? gab_all : gated_all, gab_all ? 2 * NC : NC, g.T, 0}))) return rc;
     }
     if (!x_out) return 0;
     // x' = Wr gated + br + x as ONE product [gated | x] . [Wr | I]^T: the residual add costs C^2 more MACs on the tensor pipe
@@ -555,7 +556,7 @@ int mvn_wide_skip_bias_grad(const void* ds16, const Geo& g, float* colsum_ws, fl
 }
 
 // backward of one layer: dx_next = d(x_{l+1}) (null for the last layer, whose residual output is discarded), dx_cur = d(x_l)
-int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, const void* ds16, void* dgated, const void* gated_all, void* dz,
+int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, const void* ds16, const void* gab_all, const void* gated_all, void* dz,
                        const float* dbs, const float* packed, float* pg, float* colsum_ws, float* wgpart, const PackedLayout& P, const Geo& g,
                        int l, cudaStream_t st) {
     const int C = g.C, S = g.S, d = g.dil[l], NC = g.N * C;
@@ -564,20 +565,14 @@ int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, cons
     float* lg = pg + P.layer0 + (size_t)l * P.layer_stride;
     const long long rows = (long long)g.B * g.T;
     int rc;
-    {   // d(gated) = Wr^T d(x') + Ws^T d(skip)
+    {   // dz = (Wr^T d(x') + Ws^T d(skip)) * (a, b): the d(gated) GEMM with the gate derivative in its epilogue -- the factors
+        // (a, b) were kept by the forward's gate GEMM, so the backward runs no recompute GEMM and no tanh / sigmoid at all
         Args a = new_args();
         if (dx_next) seg(a, 0, C, 0);
         seg(a, 1, S, 0);
-        a.N = C; a.b_kb0 = dx_next ? 0 : C / BK; a.out = dgated; a.ld_out = C;
-        if ((rc = launch<EPI_STORE>(Operand{dx_next ? dx_next : ds16, dx_next ? C : S}, Operand{ds16, S}, lw + P.wWrsT, C, C + S, a, g.B, g.T, st,
-                                    Output{dgated, C, g.T, 0}))) return rc;
-    }
-    {   // recompute the pre-activations: dz = d(gated) * gate' (the gated activations themselves were kept by the forward)
-        Args a = new_args();
-        seg(a, 0, C, -d); seg(a, 0, C, 0);
-        a.N = 2 * C; a.aux = dgated; a.ld_aux = C; a.out = nullptr; a.out2 = dz; a.ld_out2 = 2 * C;
-        if ((rc = launch<EPI_GATE_BWD>(Operand{x_in, C}, Operand{nullptr, 0}, lw + P.wWz, 2 * C, 2 * C, a, g.B, g.T, st,
-                                       Output{dz, 2 * C, g.T, 0}, Output{dz, 2 * C, g.T, 0}))) return rc;
+        a.N = C; a.b_kb0 = dx_next ? 0 : C / BK; a.out = dz; a.ld_out = 2 * C; a.out2_c0 = l * 2 * C;
+        if ((rc = launch<EPI_DZ>(Operand{dx_next ? dx_next : ds16, dx_next ? C : S}, Operand{ds16, S}, lw + P.wWrsT, C, C + S, a, g.B, g.T, st,
+                                 Output{dz, 2 * C, g.T, 0}, Output{gab_all, 2 * NC, g.T, 0}))) return rc;
     }
     // the residual-bias gradient of layer l - 1 is the column sum of this layer's d(x): taken inside the d(x) GEMM's epilogue
     // from the staged output tiles when a tile holds every column (C <= 256), else by a separate pass over d(x_{l+1})

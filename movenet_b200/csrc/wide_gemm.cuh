@@ -50,6 +50,7 @@ enum Epi {
     EPI_HEAD1,           // a1 = acc + b1 (fp32) ; lrelu(a1) (bf16)                    (movenet/modules.py:139-141)
     EPI_HEAD2,           // z = acc + b2 -> softmax over channels -> (B, A, Tn) fp32   (movenet/wavenet.py:187-191)
     EPI_LRELU_BWD,       // out = acc * lrelu'(aux)  (aux fp32), bf16 store, optional row shift into the T row space
+    EPI_DZ,              // dz = d(gated) * (a, b): the gate-derivative factors the forward kept, loaded by TMA into the staging tiles
     EPI_COUNT
 };
 
@@ -65,6 +66,7 @@ struct Args {
     const void* aux; int ld_aux;              // per-row auxiliary input (bf16 or fp32), row space = the A operand's
     void* out; int ld_out;                    // primary output
     int out_c0;                               // first column of the primary output inside its (wider) tensor
+    int out2_c0;                              // ... and of the secondary one (EPI_GATE: the derivative factors; EPI_DZ: where they are read)
     float* csum;                              // EPI_ADD_STORE, N <= 256: per-(CTA, lane quarter) column sums of the stored tile rows
     void* out2; int ld_out2;                  // secondary output
     float* skip;                              // (B, Tout, S) fp32 running skip sum
@@ -182,7 +184,43 @@ __device__ __forceinline__ void unpack8(const uint4 u, float* v) {
 struct Stager {
     uint32_t base; int cur, lane;
     uint32_t row, sw;        // this lane's row inside tile 0, and its swizzle term (lane & 7) << 4
-    __device__ __forceinline__ void init(uint32_t b, int l) { base = b; cur = 0; lane = l; row = b + l * 128; sw = (uint32_t)(l & 7) << 4; }
+    uint32_t lbar[2], lph[2];   // per-tile load barriers (EPI_DZ: tiles are also filled by TMA) and their phases
+    __device__ __forceinline__ void init(uint32_t b, int l, uint32_t bar0) {
+        base = b; cur = 0; lane = l; row = b + l * 128; sw = (uint32_t)(l & 7) << 4;
+        lbar[0] = bar0; lbar[1] = bar0 + 8; lph[0] = lph[1] = 0;
+    }
+    // TMA load of a [32 rows x 128 bytes] box into tile `buf` (the tile must not be in use by a store: wait_group.read first)
+    __device__ __forceinline__ void load(int buf, const CUtensorMap* map, int c0, int c1, int c2) {
+        if (lane == 0) {
+            mbar_expect_tx_addr(lbar[buf], OUT_BUF_BYTES);
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                         ::"r"(base + buf * OUT_BUF_BYTES), "l"(map), "r"(lbar[buf]), "r"(c0), "r"(c1), "r"(c2) : "memory");
+        }
+    }
+    __device__ __forceinline__ void wait_load(int buf) { mbar_wait_addr(lbar[buf], lph[buf]); lph[buf] ^= 1; }
+    __device__ __forceinline__ uint4 get(int buf, int k) {
+        uint4 v;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "r"(row + buf * OUT_BUF_BYTES + (((uint32_t)k << 4) ^ sw)) : "memory");
+        return v;
+    }
+    __device__ __forceinline__ void put_at(int buf, int k, uint4 v) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + buf * OUT_BUF_BYTES + (((uint32_t)k << 4) ^ sw)),
+                     "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    __device__ __forceinline__ void store_buf(int buf, const CUtensorMap* map, int c0, int c1, int c2) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                         ::"l"(map), "r"(base + buf * OUT_BUF_BYTES), "r"(c0), "r"(c1), "r"(c2) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    __device__ __forceinline__ void drain_reads() {      // every tile handed to a TMA store has been read
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+    }
     __device__ __forceinline__ void begin() {          // the tile about to be written was handed to TMA two stores ago
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
@@ -220,6 +258,14 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
     return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
 }
 
+// EPI_DZ: request the factor tiles of this thread-half's first two 32-channel blocks before waiting for the accumulator
+__device__ __forceinline__ void dz_prefetch(const Args& a, Stager& sg, const CUtensorMap* mO1, int nc, int n0, int b, int r0, int half) {
+    const int cnt = nc / 64, ch = n0 + 32 * half * cnt;
+    sg.drain_reads();                               // the previous chunk's stores have read both tiles
+    sg.load(0, mO1, a.out2_c0 + 2 * ch, r0, b);
+    if (cnt > 1) sg.load(1, mO1, a.out2_c0 + 2 * (ch + 32), r0, b);
+}
+
 // layer epilogues (TMA-stored): r0 = first row of this warp's 32 rows inside the clip; mO0 / mO1: tensor maps of the outputs
 template <int EPI>
 __device__ __forceinline__ void epilogue_tma(const Args& a, const uint4* pre, Stager& sg, const CUtensorMap* mO0, const CUtensorMap* mO1,
@@ -234,7 +280,11 @@ __device__ __forceinline__ void epilogue_tma(const Args& a, const uint4* pre, St
             tmem_ld32(tm + 64 * half + 32 * u, f);
             tmem_ld32(tm + 128 + 64 * half + 32 * u, g);
             tmem_ld_wait();
-            if (EPI == EPI_GATE_BWD) sg.begin();
+            // training forward (EPI_GATE with a second output): the gate's derivative factors are kept for the backward,
+            //   a = d gated / df = sigma (1 - tanh^2),  b = d gated / dg = tanh sigma (1 - sigma),   interleaved (a_c, b_c),
+            // so that the backward needs neither the recomputed pre-activations (an 8 C^2 GEMM per layer) nor tanh / sigmoid
+            const bool keep = EPI == EPI_GATE && a.out2 != nullptr;
+            if (EPI == EPI_GATE_BWD || keep) sg.begin();
             if (a.bias) {      // (context-conv biases; null on the audio-only wide path -- one uniform branch, not 64 predicated loads)
 #pragma unroll
                 for (int e = 0; e < 32; ++e) {
@@ -250,22 +300,56 @@ __device__ __forceinline__ void epilogue_tma(const Args& a, const uint4* pre, St
                 for (int e = 0; e < 8; ++e) {
                     const float th = tanh_v(__uint_as_float(f[8 * q + e])), sgm = sigmoid_fast(__uint_as_float(g[8 * q + e]));
                     o[e] = th * sgm;
-                    if (EPI == EPI_GATE_BWD) {
-                        // d tanh(f) sigma(g) / df = sigma (1 - tanh^2) ; / dg = tanh sigma (1 - sigma)
-                        const float df = (d[e] * sgm) * fmaf(-th, th, 1.f), dgv = (d[e] * o[e]) * (1.f - sgm);
-                        if (e < 4) { z0[2 * e] = df; z0[2 * e + 1] = dgv; } else { z1[2 * (e - 4)] = df; z1[2 * (e - 4) + 1] = dgv; }
-                    }
+                    // d tanh(f) sigma(g) / df = sigma (1 - tanh^2) ; / dg = tanh sigma (1 - sigma)
+                    const float dd = EPI == EPI_GATE_BWD ? d[e] : 1.f;
+                    const float df = (dd * sgm) * fmaf(-th, th, 1.f), dgv = (dd * o[e]) * (1.f - sgm);
+                    if (e < 4) { z0[2 * e] = df; z0[2 * e + 1] = dgv; } else { z1[2 * (e - 4)] = df; z1[2 * (e - 4) + 1] = dgv; }
                 }
                 if (EPI == EPI_GATE) og[4 * u + q] = pack8(o);       // (the backward reads the gated activations the forward kept)
-                if (EPI == EPI_GATE_BWD) { sg.put(2 * q, pack8(z0)); sg.put(2 * q + 1, pack8(z1)); }
+                if (EPI == EPI_GATE_BWD || keep) { sg.put(2 * q, pack8(z0)); sg.put(2 * q + 1, pack8(z1)); }
             }
             if (EPI == EPI_GATE_BWD) sg.flush(mO1, 2 * ch0 + 64 * u, r0, b, false);      // dz columns interleave (df c, dg c)
+            if (keep) sg.flush(mO1, a.out2_c0 + 2 * ch0 + 64 * u, r0, b, false);
         }
         if (EPI == EPI_GATE) {
             sg.begin();
 #pragma unroll
             for (int k = 0; k < 8; ++k) sg.put(k, og[k]);
             sg.flush(mO0, a.out_c0 + ch0, r0, b, false);
+        }
+        return;
+    }
+    if (EPI == EPI_DZ) {
+        // dz[t][2c], dz[t][2c+1] = d(gated)[t][c] * (a_c, b_c).  The factor tile of a 32-channel block ([32 rows x 128 bytes]:
+        // 64 interleaved bf16) was requested by dz_prefetch() (blocks 0, 1) or right after the tile's previous store; the
+        // products overwrite it in place and the same tile is handed to the TMA store.
+        const int cnt = nc / 64;
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
+            if (uu >= cnt) break;                  // (warp-uniform)
+            const int u = half * cnt + uu, ch = n0 + 32 * u, buf = uu & 1;
+            uint32_t v[32];
+            tmem_ld32(tm + 32 * u, v);
+            tmem_ld_wait();
+            sg.wait_load(buf);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint4 ab = sg.get(buf, k);
+                const uint32_t w[4] = {ab.x, ab.y, ab.z, ab.w};
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 f2 = unpack_bf16(w[e]);
+                    const float d = __uint_as_float(v[4 * k + e]);
+                    o[e] = pack_bf16(d * f2.x, d * f2.y);
+                }
+                sg.put_at(buf, k, make_uint4(o[0], o[1], o[2], o[3]));
+            }
+            sg.store_buf(buf, mO0, 2 * ch, r0, b);
+            if (uu + 2 < cnt) {                    // this tile's next factor block, as soon as the store has read it
+                sg.drain_reads();
+                sg.load(buf, mO1, a.out2_c0 + 2 * (ch + 64), r0, b);
+            }
         }
         return;
     }
@@ -417,7 +501,8 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     uint64_t* empty = bars + C::STAGES;        // [STAGES] operands consumed (one per CTA, signalled by the multicast commit)
     uint64_t* tfull = empty + C::STAGES;       // [2] accumulator chunk complete (one per CTA)
     uint64_t* tempty = tfull + 2;              // [2] accumulator chunk drained by the epilogue warps of every CTA of the pair (leader)
-    uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+    uint64_t* lbars = tempty + 2;              // [N_EPI_WARPS][2] staging-tile load barriers (EPI_DZ)
+    uint32_t* tmem_slot = (uint32_t*)(lbars + 2 * N_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = PAIR == 1 ? 0u : cluster_ctarank();
@@ -426,6 +511,7 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, N_EPI_WARPS * PAIR); }
+        for (int s = 0; s < 2 * N_EPI_WARPS; ++s) mbar_init(lbars + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -504,8 +590,9 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
     } else {
         // ===== epilogue warps: lane quarter = warp % 4 (the TMEM lanes a warp may read), two warps per quarter split the columns
         const int q = warp & 3, half = (warp - 2) >> 2;
-        constexpr bool TMA_OUT = EPI == EPI_GATE || EPI == EPI_GATE_BWD || EPI == EPI_RESID_SKIP || EPI == EPI_STORE || EPI == EPI_ADD_STORE;
-        Stager sg; sg.init(smem_u32(out_stage + (warp - 2) * 2 * OUT_BUF_BYTES), lane);
+        constexpr bool TMA_OUT = EPI == EPI_GATE || EPI == EPI_GATE_BWD || EPI == EPI_RESID_SKIP || EPI == EPI_STORE || EPI == EPI_ADD_STORE ||
+                                 EPI == EPI_DZ;
+        Stager sg; sg.init(smem_u32(out_stage + (warp - 2) * 2 * OUT_BUF_BYTES), lane, smem_u32(lbars + 2 * (warp - 2)));
         uint32_t acc = 0;
         float cs[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t te[2];
@@ -519,6 +606,7 @@ wide_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constan
                 const uint32_t buf = acc & 1;
                 uint4 pre[16];
                 prefetch<EPI>(a, pre, nc, NCH * j, b, t, ok, half);
+                if constexpr (EPI == EPI_DZ) dz_prefetch(a, sg, &mapO1, nc, NCH * j, b, t0 + 32 * q, half);
                 mbar_wait_addr(smem_u32(tfull + buf), (acc >> 1) & 1);
                 tc_fence_after();
                 if constexpr (TMA_OUT) epilogue_tma<EPI>(a, pre, sg, &mapO0, &mapO1, tmem + ((uint32_t)(32 * q) << 16) + buf * NCH, nc, NCH * j, b, t0 + 32 * q, half, cs);

@@ -84,8 +84,8 @@ class _WaveNetFunction(torch.autograd.Function):
     """forward()/backward() of the whole network as ONE autograd node."""
 
     @staticmethod
-    def forward(ctx, module, audio, video, remove_last, output_logits, *params):
-        bufs = module._engine_buffers(audio, video is not None, remove_last, output_logits)
+    def forward(ctx, module, audio, video, remove_last, output_logits, no_grad, *params):
+        bufs = module._engine_buffers(audio, video is not None, remove_last, output_logits, no_grad)
         shape = bufs.shape
         module._pack(bufs, params)
         Tn = shape.frames - module.receptive_fields + 1 - (1 if remove_last else 0)
@@ -128,7 +128,7 @@ class _WaveNetFunction(torch.autograd.Function):
         _lib.call("mvn_unpack_grads", C.byref(bufs.shape), pg.data_ptr(), flat.data_ptr(), offs.data_ptr(),
                       C.c_float(1.0 / module._dp_world), _stream())
         module._reduce_grads(flat)
-        return (None, None, None, None, None, *views)
+        return (None, None, None, None, None, None, *views)
 
 
 class WaveNet(nn.Module):
@@ -236,8 +236,10 @@ class WaveNet(nn.Module):
                 "input time steps must be larger than the number of receptive fields. "
                 f"Number of input timesteps = {frames}, receptive fields = {self.receptive_fields}")
         with torch.cuda.device(audio.device):
-            out = _WaveNetFunction.apply(self, audio, video, bool(remove_last), not output_unnormalized,
-                                         *self._param_list())
+            params = self._param_list()
+            # inference-only passes skip what only a backward needs (the wide path's gate-derivative factors)
+            no_grad = not (torch.is_grad_enabled() and any(p.requires_grad for p in params))
+            out = _WaveNetFunction.apply(self, audio, video, bool(remove_last), not output_unnormalized, no_grad, *params)
         # probabilities know the fused route for the trainer's F.cross_entropy(output, target) (loss.py)
         st = self.__dict__.pop("_fwd_state", None)
         if not output_unnormalized:
@@ -330,11 +332,11 @@ class WaveNet(nn.Module):
             f"expected video of shape (B, {MAX_VIDEO_FRAMES}, 64, 64, {self.context_in_channels}), found {tuple(video.shape)}")
         return video.detach().float().contiguous()
 
-    def _shape(self, B, T, has_video, remove_last, output_logits, act_dtype=None):
+    def _shape(self, B, T, has_video, remove_last, output_logits, act_dtype=None, no_grad=False):
         return _lib.Shape(self.layer_size, self.stack_size, self.input_channels, self.residual_channels,
                           self.skip_channels, self.context_in_channels, B, T, int(has_video),
                           _DTYPES[self.compute_dtype] if act_dtype is None else act_dtype,
-                          int(remove_last), int(output_logits))
+                          int(remove_last), int(output_logits), int(no_grad))
 
     def _buffers_for(self, shape, device):
         key = (shape.key(), str(device))
@@ -345,8 +347,8 @@ class WaveNet(nn.Module):
             bufs = self._bufs[key] = _Buffers(shape, device)
         return bufs
 
-    def _engine_buffers(self, audio, has_video, remove_last, output_logits):
-        shape = self._shape(audio.shape[0], audio.shape[-1], has_video, remove_last, output_logits)
+    def _engine_buffers(self, audio, has_video, remove_last, output_logits, no_grad=False):
+        shape = self._shape(audio.shape[0], audio.shape[-1], has_video, remove_last, output_logits, no_grad=no_grad)
         return self._buffers_for(shape, audio.device)
 
     def _pack(self, bufs, params):
