@@ -173,9 +173,26 @@ int mvn_head_fwd(const mvn_shape_t* s, const void* packed, void* acts, float* ou
 /* one layer of the backward pass on the gradient state currently in `scratch` (profiling / roofline timing) */
 int mvn_layer_bwd(const mvn_shape_t* s, const void* packed, int layer, const void* acts, void* packed_grads,
                   void* scratch, void* stream);
-/* read back an internal activation as fp32 (tests): which = 0 layer input x_l (B,T,C), 1 skip sum (B,Tout,S),
- * 2 upsampled context (B,T,C) */
-int mvn_debug_read(const mvn_shape_t* s, const void* acts, int which, int layer, float* dst, void* stream);
+/* copy an internal activation out as fp32: which = 0 layer input x_l (B,T,C), 1 skip sum (B,Tout,S), 2 upsampled context (B,T,C)
+ * -- the context read is the product's WaveNet.upsample_video (movenet/wavenet.py:134-156), the others serve tests */
+int mvn_read_activation(const mvn_shape_t* s, const void* acts, int which, int layer, float* dst, void* stream);
+
+/* ---- data-parallel gradient averaging over NVLink peer memory (one node, one process per GPU; csrc/peer.cu) -------------
+ * Replaces DistributedDataParallel's NCCL bucket all-reduce (movenet/trainer.py:230-234) by ONE kernel fused in front of the
+ * gradient unpack.  Every rank allocates one shareable exchange buffer of stage_bytes + recv_bytes (mvn_peer_layout,
+ * mvn_peer_alloc: zero-filled), hands the 64-byte handle to its peers by any means (the Python host uses torch.distributed)
+ * and maps theirs (mvn_peer_open).  mvn_peer_reduce_unpack(epoch), epoch = 1, 2, ... counted per exchange buffer and called by
+ * every rank once per step, sums the packed gradients of all ranks in rank order IN PLACE (bit-identical on every rank) and
+ * leaves `scale` times the sum, unpacked, in `flat_grads`.  peer_base[r] = rank r's exchange buffer as mapped in THIS process
+ * (own rank: the allocation itself).  A rank that never calls makes the others trap after ~5 s. */
+#define MVN_PEER_MAX 8
+int mvn_peer_layout(const mvn_shape_t* s, size_t* stage_bytes, size_t* recv_bytes);
+int mvn_peer_alloc(size_t bytes, void** ptr, void* handle64);
+int mvn_peer_open(const void* handle64, void** ptr);
+int mvn_peer_close(void* ptr);
+int mvn_peer_free(void* ptr);
+int mvn_peer_reduce_unpack(const mvn_shape_t* s, void* const* peer_base, int rank, int world, unsigned epoch, void* packed_grads,
+                           float* flat_grads, const int64_t* offsets_dev, float scale, void* stream);
 
 /* byte offset of an internal activation inside the `acts` buffer: which = 0 layer input x_l (B,T,C) act dtype,
  * 2 upsampled context (B,T,C) act dtype (has_video shapes only; what mvn_decode_steps takes as `ctx`) */

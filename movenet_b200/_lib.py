@@ -42,6 +42,12 @@ SIGNATURES = {
     "mvn_one_hot": (_I, [_P, _P, _I, _I, _I, _P]),
     "mvn_pack_weights": (_I, [_SP, _P, _P, _P]),
     "mvn_unpack_grads": (_I, [_SP, _P, _P, _P, C.c_float, _P]),
+    "mvn_peer_layout": (_I, [_SP, _P, _P]),
+    "mvn_peer_alloc": (_I, [_SZ, _P, _P]),
+    "mvn_peer_open": (_I, [_P, _P]),
+    "mvn_peer_close": (_I, [_P]),
+    "mvn_peer_free": (_I, [_P]),
+    "mvn_peer_reduce_unpack": (_I, [_SP, _P, _I, _I, C.c_uint, _P, _P, _P, C.c_float, _P]),
     "mvn_codes_input": (_I, [_SP, _P, _P, _P]),
     "mvn_wavenet_forward": (_I, [_SP, _P, _P, _P, _P, _P, _P, _P]),
     "mvn_wavenet_backward": (_I, [_SP, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -59,7 +65,7 @@ SIGNATURES = {
     "mvn_layer_fwd": (_I, [_SP, _P, _I, _P, _P, _P]),
     "mvn_head_fwd": (_I, [_SP, _P, _P, _P, _P, _P]),
     "mvn_layer_bwd": (_I, [_SP, _P, _I, _P, _P, _P, _P]),
-    "mvn_debug_read": (_I, [_SP, _P, _I, _I, _P, _P]),
+    "mvn_read_activation": (_I, [_SP, _P, _I, _I, _P, _P]),
     "mvn_acts_offset": (_SZ, [_SP, _I, _I]),
     "mvn_decode_state_bytes": (_SZ, [_SP, _I]),
     "mvn_decode_prefill": (_I, [_SP, _P, _P, _I, _I, _P]),

@@ -687,15 +687,15 @@ extern "C" int mvn_wavenet_forward(const mvn_shape_t* s, const void* packed, con
     return head_fwd(c, out);
 }
 
-extern "C" int mvn_debug_read(const mvn_shape_t* s, const void* acts, int which, int layer, float* dst, void* stream) {
-    Ctx c; int rc = ctx_init(c, s, nullptr, acts, nullptr, stream, "mvn_debug_read"); if (rc) return rc;
+extern "C" int mvn_read_activation(const mvn_shape_t* s, const void* acts, int which, int layer, float* dst, void* stream) {
+    Ctx c; int rc = ctx_init(c, s, nullptr, acts, nullptr, stream, "mvn_read_activation"); if (rc) return rc;
     const Geo& g = c.g; const void* src; int dt; long long n;
-    if (which == 0) { MVN_REQUIRE(layer >= 0 && layer < g.N, "mvn_debug_read: bad layer"); src = c.x(layer); dt = g.adt; n = (long long)g.B * g.T * g.C; }
+    if (which == 0) { MVN_REQUIRE(layer >= 0 && layer < g.N, "mvn_read_activation: bad layer"); src = c.x(layer); dt = g.adt; n = (long long)g.B * g.T * g.C; }
     else if (which == 1) { src = c.acts + c.AL.skip; dt = MVN_F32; n = (long long)g.B * g.Tout * g.S; }
-    else if (which == 2) { MVN_REQUIRE(g.video, "mvn_debug_read: no context"); src = c.acts + c.AL.ctx; dt = g.adt; n = (long long)g.B * g.T * g.C; }
-    else { mvn_set_error("mvn_debug_read: bad selector"); return -1; }
+    else if (which == 2) { MVN_REQUIRE(g.video, "mvn_read_activation: no context"); src = c.acts + c.AL.ctx; dt = g.adt; n = (long long)g.B * g.T * g.C; }
+    else { mvn_set_error("mvn_read_activation: bad selector"); return -1; }
     to_f32_kernel<<<1184, 256, 0, c.st>>>(src, dt, dst, n);
-    return mvn_check_launch("debug_read");
+    return mvn_check_launch("read_activation");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -426,7 +426,8 @@ int wgrad_launch(WgArgs& a, const WgTensors& t, const Geo& g, float* partial, cu
     cfg.attrs = at; cfg.numAttrs = 2;
     MVN_CUDA(cudaLaunchKernelEx(&cfg, wide_wgrad_kernel, m[0], m[1], m[2], m[3], m[4], a));
     if ((rc = mvn_check_launch("wide_wgrad"))) return rc;
-    MVN_CUDA(mvn_launch_pdl(wide_wgrad_reduce_kernel, dim3(128, a.n_jobs), dim3(256), (size_t)0, st, a));
+    MVN_REQUIRE(!a.cs_partial || a.cs_cols <= 256, "wide path: passenger column sum width");
+    MVN_CUDA(mvn_launch_pdl(wide_wgrad_reduce_kernel, dim3(128, a.n_jobs + (a.cs_partial ? 1 : 0)), dim3(256), (size_t)0, st, a));
     return mvn_check_launch("wide_wgrad_reduce");
 }
 
@@ -577,24 +578,28 @@ int mvn_wide_layer_bwd(const void* x_in, const void* dx_next, void* dx_cur, cons
     // the residual-bias gradient of layer l - 1 is the column sum of this layer's d(x): taken inside the d(x) GEMM's epilogue
     // from the staged output tiles when a tile holds every column (C <= 256), else by a separate pass over d(x_{l+1})
     const bool fused_colsum = C <= NCH;
+    int cs_rows = 0; float* cs_out = nullptr;
     {   // d(x_l)[t] = d(x_{l+1})[t] + W1^T dz[t] + W0^T dz[t + d]
         Args a = new_args();
         seg(a, 0, 2 * C, 0); seg(a, 0, 2 * C, d);
         a.N = C; a.aux = dx_next; a.ld_aux = C; a.out = dx_cur; a.ld_out = C;
         a.csum = (fused_colsum && l > 0) ? colsum_ws : nullptr;
         if ((rc = launch<EPI_ADD_STORE>(Operand{dz, 2 * C}, Operand{nullptr, 0}, lw + P.wWzT, C, 4 * C, a, g.B, g.T, st, Output{dx_cur, C, g.T, 0}))) return rc;
-        if (a.csum) {
+        if (a.csum) {      // per-CTA, per-staging-warp partial rows; reduced by the weight-gradient reduce kernel below (or here)
             const int pair = pair_mode();
             int clusters = mvn_sm_count() / pair; if (clusters > a.n_tiles) clusters = a.n_tiles;
-            float* lg_prev = pg + P.layer0 + (size_t)(l - 1) * P.layer_stride;
-            MVN_CUDA(mvn_launch_pdl(colsum2_kernel, dim3(mvn_cdiv(C, 32)), dim3(32, RED_SPLIT), (size_t)0, st, (const float*)colsum_ws,
-                                    clusters * pair * 4, C, lg_prev + P.obrs));
-            if ((rc = mvn_check_launch("colsum2"))) return rc;
+            cs_rows = clusters * pair * 4;
+            cs_out = pg + P.layer0 + (size_t)(l - 1) * P.layer_stride + P.obrs;
+            if (!wgrad_tc_ok(g)) {
+                MVN_CUDA(mvn_launch_pdl(colsum2_kernel, dim3(mvn_cdiv(C, 32)), dim3(32, RED_SPLIT), (size_t)0, st, (const float*)colsum_ws, cs_rows, C, cs_out));
+                if ((rc = mvn_check_launch("colsum2"))) return rc;
+            }
         }
     }
     // weight gradients (K = time): packed layout oWz[k = tap C + c_in][2 c_out + gate], oWrs[k = c][n]
     if (wgrad_tc_ok(g)) {
         WgArgs w; memset(&w, 0, sizeof(w));
+        if (cs_out) { w.cs_partial = colsum_ws; w.cs_out = cs_out; w.cs_rows = cs_rows; w.cs_cols = C; }
         WgTensors t = {{x_in, gated_all, dz, dx_next, ds16}, {C, NC, 2 * C, C, S}};
         for (int tap = 0; tap < 2; ++tap)               // dWz[tap C + c_in][n] = sum_t x[t - (1 - tap) d][c_in] dz[t][n]
             for (int mt = 0; mt < C / 256; ++mt)

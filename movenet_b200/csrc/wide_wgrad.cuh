@@ -26,6 +26,9 @@ struct WgJob {
 struct WgArgs {
     int B, T, kb_per_clip, n_jobs, n_splits;
     float* partial;                // [n_jobs][n_splits][256][512] fp32
+    // optional passenger of the reduce kernel: column sums of cs_rows partial rows [cs_cols] (the residual-bias gradient the
+    // d(x) GEMM's epilogue left per CTA and staging warp), one extra row of blocks instead of one more launch per layer
+    const float* cs_partial; float* cs_out; int cs_rows, cs_cols;
     WgJob job[WG_MAX_JOBS];
 };
 
@@ -146,6 +149,21 @@ wide_wgrad_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
 __global__ void __launch_bounds__(256) wide_wgrad_reduce_kernel(const WgArgs a) {
     MVN_PDL_PROLOGUE();
     const int j = blockIdx.y;
+    if (j == a.n_jobs) {           // column sums: two columns per block, 128 threads per column, rows dealt round-robin, fixed tree
+        __shared__ float red[256];
+        const int c = 2 * blockIdx.x + (threadIdx.x >> 7), k = threadIdx.x & 127;
+        float acc = 0.f;
+        if (c < a.cs_cols)
+            for (int r = k; r < a.cs_rows; r += 128) acc += a.cs_partial[(size_t)r * a.cs_cols + c];
+        red[threadIdx.x] = acc;
+        __syncthreads();
+        for (int w = 64; w >= 1; w >>= 1) {
+            if (k < w) red[threadIdx.x] += red[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (k == 0 && c < a.cs_cols) a.cs_out[c] = red[threadIdx.x];
+        return;
+    }
     const WgJob job = a.job[j];
     const int total_kb = a.B * a.kb_per_clip, per = (total_kb + a.n_splits - 1) / a.n_splits;
     const int used = (total_kb + per - 1) / per;            // slices that had work

@@ -80,17 +80,13 @@ class _FusedLoss(torch.autograd.Function):
         st.done.add(key)
         module, bufs, audio, video = st.module, st.bufs, st.audio, st.video
         g = grad_loss.contiguous().float()
-        pg = bufs.get_packed_grads()
-        with torch.cuda.device(audio.device):
+        def run(pg_ptr):
             _lib.call("mvn_wavenet_backward_loss", C.byref(bufs.shape), bufs.packed.data_ptr(),
                       0 if audio.dim() == 2 else audio.data_ptr(), 0 if video is None else video.data_ptr(),
-                      st.acts.data_ptr(), probs.data_ptr(), target.data_ptr(), g.data_ptr(), pg.data_ptr(),
+                      st.acts.data_ptr(), probs.data_ptr(), target.data_ptr(), g.data_ptr(), pg_ptr,
                       bufs.get_scratch().data_ptr(), _stream())
-            flat, views = module._flat_grads(st.has_video, audio.device)
-            offs = module._grad_offsets(st.has_video, audio.device)
-            _lib.call("mvn_unpack_grads", C.byref(bufs.shape), pg.data_ptr(), flat.data_ptr(), offs.data_ptr(),
-                      C.c_float(1.0 / module._dp_world), _stream())
-        module._reduce_grads(flat)
+        with torch.cuda.device(audio.device):
+            views = module._backward_and_average(bufs, st.has_video, audio.device, run)
         return (None, None, None, *views)
 
 

@@ -119,15 +119,11 @@ class _WaveNetFunction(torch.autograd.Function):
             raise RuntimeError("Trying to backward through the WaveNet graph a second time (the reference would need retain_graph=True)")
         st.done.add("net")
         dout = dout.contiguous().float()
-        pg = bufs.get_packed_grads()
-        _lib.call("mvn_wavenet_backward", C.byref(bufs.shape), bufs.packed.data_ptr(), 0 if audio.dim() == 2 else audio.data_ptr(),
-                  0 if video is None else video.data_ptr(), st.acts.data_ptr(), out.data_ptr(), dout.data_ptr(),
-                  pg.data_ptr(), bufs.get_scratch().data_ptr(), _stream())
-        flat, views = module._flat_grads(st.has_video, audio.device)
-        offs = module._grad_offsets(st.has_video, audio.device)
-        _lib.call("mvn_unpack_grads", C.byref(bufs.shape), pg.data_ptr(), flat.data_ptr(), offs.data_ptr(),
-                      C.c_float(1.0 / module._dp_world), _stream())
-        module._reduce_grads(flat)
+        def run(pg_ptr):
+            _lib.call("mvn_wavenet_backward", C.byref(bufs.shape), bufs.packed.data_ptr(), 0 if audio.dim() == 2 else audio.data_ptr(),
+                      0 if video is None else video.data_ptr(), st.acts.data_ptr(), out.data_ptr(), dout.data_ptr(),
+                      pg_ptr, bufs.get_scratch().data_ptr(), _stream())
+        views = module._backward_and_average(bufs, st.has_video, audio.device, run)
         return (None, None, None, None, None, None, *views)
 
 
@@ -177,6 +173,7 @@ class WaveNet(nn.Module):
         self._ptr_tables = {}
         self._dp_group = None
         self._dp_world = 1
+        self._dp_peer = {}
         self._weights_epoch = 0      # bumped by anything that rewrites parameters behind autograd's back (see _pack)
 
     # ------------------------------------------------------------------ reference surface
@@ -209,7 +206,7 @@ class WaveNet(nn.Module):
             acts = torch.empty(bufs.acts_bytes, dtype=torch.uint8, device=video.device)
             _lib.call("mvn_video_fwd", C.byref(shape), bufs.packed.data_ptr(), video.data_ptr(), acts.data_ptr(), _stream())
             ctx = torch.empty(B, MAX_AUDIO_FRAMES, self.residual_channels, dtype=torch.float32, device=video.device)
-            _lib.call("mvn_debug_read", C.byref(shape), acts.data_ptr(), 2, 0, ctx.data_ptr(), _stream())
+            _lib.call("mvn_read_activation", C.byref(shape), acts.data_ptr(), 2, 0, ctx.data_ptr(), _stream())
         out = ctx.permute(0, 2, 1).contiguous()
         assert out.shape[-1] == MAX_AUDIO_FRAMES
         return out
@@ -273,11 +270,13 @@ class WaveNet(nn.Module):
 
     # ------------------------------------------------------------------ data parallel
     def enable_data_parallel(self, process_group=None):
-        """Average gradients over ``process_group`` with one all-reduce of the flat gradient
-        buffer per backward (the role DistributedDataParallel plays at movenet/trainer.py:230-234)."""
+        """Average gradients over ``process_group`` once per backward (the role DistributedDataParallel plays at
+        movenet/trainer.py:230-234): on one node over NCCL-capable GPUs by the peer-memory kernel of csrc/peer.cu fused in
+        front of the gradient unpack, otherwise by one all-reduce of the flat gradient buffer."""
         import torch.distributed as dist
         self._dp_group = process_group if process_group is not None else dist.group.WORLD
         self._dp_world = dist.get_world_size(self._dp_group)
+        self._dp_peer = {}
         # the replicas must start identical: like DistributedDataParallel's constructor, take rank 0's parameters
         # (ranks may have been built with different RNG state, or only some may have loaded a checkpoint)
         if self._dp_world > 1:
@@ -294,6 +293,41 @@ class WaveNet(nn.Module):
         if self._dp_world > 1:
             import torch.distributed as dist
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self._dp_group)
+
+    def _peer_gradients(self, bufs, has_video, device):
+        """the NVLink peer-memory exchange of this (model, video flag), set up by a collective at its first backward;
+        None when it does not apply (one rank, gloo, several hosts, $MOVENET_B200_DP=nccl): NCCL all-reduce then"""
+        if self._dp_world <= 1:
+            return None
+        key = (has_video, str(device))
+        if key not in self._dp_peer:
+            from . import peer
+            pgr = None
+            if peer.available(self._dp_group, device):
+                pgr = peer.PeerGradients(bufs.shape, device, self._dp_group)
+                if not pgr.ok:
+                    import warnings
+                    warnings.warn(f"movenet_b200: peer-memory gradient exchange unavailable ({pgr.why}); using the NCCL all-reduce")
+                    pgr = None
+            self._dp_peer[key] = pgr
+        return self._dp_peer[key]
+
+    def _backward_and_average(self, bufs, has_video, device, run):
+        """run(pg_ptr) launches the backward kernels into a packed-gradient buffer; returns the per-parameter gradient
+        views (averaged over the data-parallel group) in parameter order"""
+        peer = self._peer_gradients(bufs, has_video, device)
+        pg = bufs.get_packed_grads()
+        run(pg.data_ptr())
+        flat, views = self._flat_grads(has_video, device)
+        offs = self._grad_offsets(has_video, device)
+        if peer is not None:
+            # one kernel: push slices, rank-ordered sum, push the sums (all NVLink traffic is stores); then the unpack
+            peer.reduce_unpack(bufs.shape, pg.data_ptr(), flat, offs, _stream())
+        else:
+            _lib.call("mvn_unpack_grads", C.byref(bufs.shape), pg.data_ptr(), flat.data_ptr(), offs.data_ptr(),
+                      C.c_float(1.0 / self._dp_world), _stream())
+            self._reduce_grads(flat)
+        return views
 
     # ------------------------------------------------------------------ plumbing
     def _param_list(self):

@@ -22,10 +22,10 @@ def run(model, audio, video, dtype):
     xs = []
     for l in range(model.layer_size * model.stack_size):
         x = torch.empty(B, T, model.residual_channels, device=audio.device)
-        _lib.call("mvn_debug_read", C.byref(shape), acts.data_ptr(), 0, l, x.data_ptr(), st)
+        _lib.call("mvn_read_activation", C.byref(shape), acts.data_ptr(), 0, l, x.data_ptr(), st)
         xs.append(x)
     skip = torch.empty(B, T - model.receptive_fields + 1, model.skip_channels, device=audio.device)
-    _lib.call("mvn_debug_read", C.byref(shape), acts.data_ptr(), 1, 0, skip.data_ptr(), st)
+    _lib.call("mvn_read_activation", C.byref(shape), acts.data_ptr(), 1, 0, skip.data_ptr(), st)
     torch.cuda.synchronize()
     return out, xs, skip
 
