@@ -15,9 +15,15 @@
 // followed by the ordinary unpack kernels (packed layout -> the reference's parameter shapes, times 1/world).  Everything that
 // crosses NVLink is a 16-byte STORE carrying 8 bytes of payload and the step number twice ("flag-in-data", the low-latency
 // protocol of collective libraries): the receiver polls the line until both flags show this step, so there is no barrier, no
-// system-scope fence and no dependence between thread blocks.  Measured on the way (N = 2, 2.65 MB, device time of the
-// exchange in front of the 23 us unpack): pulling with loads behind two flag barriers 24 us, pushing with stores behind two
-// barriers 32 us (the system fences wait for every outstanding remote store), NCCL 13 us.
+// system-scope fence and no dependence between thread blocks.
+//
+// Measured (B200 x 2 / x 8 on NVSwitch, 2.65 MB, device time of the exchange alone, scripts/dev/dp_exchange_time.py;
+// profiles/r02_dp_exchange.md): this kernel 19.5 us at N = 2 and 35.4 us at N = 8; NCCL 2.28 all-reduce 13.4 and 26.3 us; whole
+// training step at N = 8: 2.469 ms with this kernel, 2.408 ms with NCCL (N = 1: 2.339 ms).  Earlier versions: pulling with loads
+// behind two flag barriers 24 us at N = 2, pushing with stores behind two barriers 32 us (a system-scope fence waits for every
+// outstanding remote store).  The flag-in-data protocol doubles the bytes on the wire and NCCL reduces inside the switch;
+// NCCL therefore STAYS THE DEFAULT and this exchange is opt-in ($MOVENET_B200_DP=peer), kept for its fixed summation order
+// and as the tested starting point for a multimem (in-switch reduction) version.
 // No buffer needs a guard: a peer can only push step e+1's slices after it has received ALL of this rank's step-e sums (sent
 // after this rank consumed its staging slots), and step e+1's sums only after this rank's step-e+1 slices (sent by a kernel
 // that follows step e's phase 3 in stream order).

@@ -3,7 +3,9 @@
 `PeerGradients` owns this rank's cudaIpc-shared exchange buffer (staging slots and the receive area of the sums) and the mappings
 of every peer's.  Set up once per (model, video flag) by a collective
 handle exchange over the process group; after that a step's exchange is one kernel launch, no NCCL call and no host
-synchronisation.  Any failure during the set-up (ranks on different hosts, peer access unavailable) is agreed on by all ranks
+synchronisation.  Opt-in with $MOVENET_B200_DP=peer: its sums are taken in rank order (bit-identical results whatever
+algorithm NCCL would pick), but NCCL's all-reduce is the faster exchange on the B200 / NVSwitch boxes measured (csrc/peer.cu)
+and stays the default.  Any failure during the set-up (ranks on different hosts, peer access unavailable) is agreed on by all ranks
 and leaves the NCCL all-reduce in charge (`WaveNet._reduce_grads`): both are device paths, neither is a CPU fallback.
 """
 import ctypes as C
@@ -18,9 +20,10 @@ MAX_PEERS = 8
 
 
 def available(group, device) -> bool:
-    """peer exchange needs: a CUDA device, the NCCL backend (one process per GPU), 2..8 ranks"""
+    """opt-in ($MOVENET_B200_DP=peer; NCCL's all-reduce measured faster on NVSwitch B200 boxes, see csrc/peer.cu); needs a CUDA
+    device, the NCCL backend (one process per GPU) and 2..8 ranks"""
     import torch.distributed as dist
-    if os.environ.get("MOVENET_B200_DP", "peer") != "peer" or device.type != "cuda":
+    if os.environ.get("MOVENET_B200_DP", "nccl") != "peer" or device.type != "cuda":
         return False
     world = dist.get_world_size(group)
     return 2 <= world <= MAX_PEERS and dist.get_backend(group) == "nccl"

@@ -271,8 +271,8 @@ class WaveNet(nn.Module):
     # ------------------------------------------------------------------ data parallel
     def enable_data_parallel(self, process_group=None):
         """Average gradients over ``process_group`` once per backward (the role DistributedDataParallel plays at
-        movenet/trainer.py:230-234): on one node over NCCL-capable GPUs by the peer-memory kernel of csrc/peer.cu fused in
-        front of the gradient unpack, otherwise by one all-reduce of the flat gradient buffer."""
+        movenet/trainer.py:230-234): one NCCL all-reduce of the flat gradient buffer, or with $MOVENET_B200_DP=peer (one
+        node) the peer-memory kernel of csrc/peer.cu fused in front of the gradient unpack."""
         import torch.distributed as dist
         self._dp_group = process_group if process_group is not None else dist.group.WORLD
         self._dp_world = dist.get_world_size(self._dp_group)
@@ -296,7 +296,7 @@ class WaveNet(nn.Module):
 
     def _peer_gradients(self, bufs, has_video, device):
         """the NVLink peer-memory exchange of this (model, video flag), set up by a collective at its first backward;
-        None when it does not apply (one rank, gloo, several hosts, $MOVENET_B200_DP=nccl): NCCL all-reduce then"""
+        None when it was not asked for ($MOVENET_B200_DP=peer) or does not apply (one rank, gloo, several hosts): NCCL all-reduce then"""
         if self._dp_world <= 1:
             return None
         key = (has_video, str(device))
