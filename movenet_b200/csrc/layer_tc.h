@@ -43,6 +43,13 @@ int mvn_tc_upsample_fwd(const float* img, const void* u2_bf16, void* ctx_bf16, l
 int mvn_tc_upsample_bwd(const float* img, const void* u_bf16, const void* dout_bf16, void* du, int du_bf16, float* dwt, float* dbt,
                         float* partial, long long rows, cudaStream_t st);
 
+// video encoder (Conv3d = one 4096 Cin -> C linear map per frame) and its weight gradient on tensor cores (video_tc.cu), C == 64
+int mvn_tc_video_supported(int C, int K);
+size_t mvn_tc_video_partial_floats(int rows, int K);
+int mvn_tc_video_fwd(const float* video, const float* wv, const float* bv, float* part, float* enc, void* enc16_or_null, int rows, int K,
+                     cudaStream_t st);
+int mvn_tc_video_bwd(const float* video, const float* denc, float* part, float* dwv, float* dbv, int rows, int K, cudaStream_t st);
+
 // ---- wide-channel path (wide.cu): weight-streaming tcgen05 GEMMs with fused epilogues, residual_channels >= 128 -------------
 int mvn_wide_supported(const Geo& g);
 int mvn_wide_pack(const float* const* param_ptrs_dev, float* packed, const PackedLayout& P, const Geo& g, cudaStream_t st);

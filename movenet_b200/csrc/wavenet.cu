@@ -552,28 +552,34 @@ static int video_fwd(const Ctx& c, const float* video) {
     float* enc = (float*)(c.acts + c.AL.enc); float* u1 = (float*)(c.acts + c.AL.u1); float* u2 = (float*)(c.acts + c.AL.u2);
     void* ctx = c.acts + c.AL.ctx;
     int rc;
+    const bool tc3 = g.adt == MVN_DTYPE_BF16 && mvn_tc_upsample_supported(C);   // all three upsampler levels on tensor cores: u1, u2 kept in bf16
+    void* enc16 = (char*)u1 + (size_t)g.B * 1600 * C * 2;       // bf16 copy of the encoder output in the (free) second half of the u1 slot
     {   // Conv3d with a (1,64,64) kernel = one 4096*Cin -> C linear map per frame (movenet/wavenet.py:94-98,152)
         const int rows = g.B * 160, K = 4096 * g.Cin;
-        dim3 grid(mvn_cdiv(rows, VC_ROWS), mvn_cdiv(K, VC_K));
         // the K-slice partials live in the (not yet written) second upsampler level's slot of the activation buffer
         float* part = u2;
-        MVN_REQUIRE((size_t)grid.y * rows * C <= (size_t)g.B * 16000 * C, "video encoder: context_in_channels too large for the split-K workspace");
-        MVN_CUDA(mvn_launch_pdl(video_conv_kernel, dim3(grid), dim3(256), (size_t)(0), c.st, video, c.packed + c.P.wv, part, rows, K, C));
-        if ((rc = mvn_check_launch("video_conv"))) return rc;
-        MVN_CUDA(mvn_launch_pdl(video_conv_reduce_kernel, dim3(mvn_cdiv((long long)rows * C, 256)), dim3(256), (size_t)(0), c.st,
-                                (const float*)part, c.packed + c.P.bv, enc, rows, C, (int)grid.y));
-        if ((rc = mvn_check_launch("video_conv_reduce"))) return rc;
+        if (tc3 && mvn_tc_video_supported(C, K)) {       // tcgen05 (video_tc.cu); writes the bf16 copy too
+            MVN_REQUIRE(mvn_tc_video_partial_floats(rows, K) <= (size_t)g.B * 16000 * C, "video encoder: context_in_channels too large for the split-K workspace");
+            if ((rc = mvn_tc_video_fwd(video, c.packed + c.P.wv, c.packed + c.P.bv, part, enc, enc16, rows, K, c.st))) return rc;
+        } else {
+            dim3 grid(mvn_cdiv(rows, VC_ROWS), mvn_cdiv(K, VC_K));
+            MVN_REQUIRE((size_t)grid.y * rows * C <= (size_t)g.B * 16000 * C, "video encoder: context_in_channels too large for the split-K workspace");
+            MVN_CUDA(mvn_launch_pdl(video_conv_kernel, dim3(grid), dim3(256), (size_t)(0), c.st, video, c.packed + c.P.wv, part, rows, K, C));
+            if ((rc = mvn_check_launch("video_conv"))) return rc;
+            MVN_CUDA(mvn_launch_pdl(video_conv_reduce_kernel, dim3(mvn_cdiv((long long)rows * C, 256)), dim3(256), (size_t)(0), c.st,
+                                    (const float*)part, c.packed + c.P.bv, enc, rows, C, (int)grid.y));
+            if ((rc = mvn_check_launch("video_conv_reduce"))) return rc;
+            if (tc3) {
+                to_bf16_kernel<<<mvn_cdiv((long long)g.B * 160 * C, 256), 256, 0, c.st>>>(enc, (__nv_bfloat16*)enc16, (long long)g.B * 160 * C);
+                if ((rc = mvn_check_launch("to_bf16"))) return rc;
+            }
+        }
     }
     // ConvTranspose1d(k=10, stride=10): out[10 i + j] = W[:, :, j]^T in[i] + b -- a [rows x C] x [C x 10C] GEMM whose
     // row-major output IS the time-major upsampled signal (movenet/wavenet.py:102-118,154)
     const void* in[3] = {enc, u1, u2}; void* out[3] = {u1, u2, ctx};
     const int len[3] = {160, 1600, 16000};
-    const bool tc3 = g.adt == MVN_DTYPE_BF16 && mvn_tc_upsample_supported(C);   // all three levels on tensor cores: u1, u2 kept in bf16
     if (tc3) {
-        // bf16 copy of the encoder output in the (free) second half of the u1 slot
-        void* enc16 = (char*)u1 + (size_t)g.B * 1600 * C * 2;
-        to_bf16_kernel<<<mvn_cdiv((long long)g.B * 160 * C, 256), 256, 0, c.st>>>(enc, (__nv_bfloat16*)enc16, (long long)g.B * 160 * C);
-        if ((rc = mvn_check_launch("to_bf16"))) return rc;
         if ((rc = mvn_tc_upsample_fwd(c.packed + c.P.tc_up01[0], enc16, u1, g.B * len[0], c.st))) return rc;
         if ((rc = mvn_tc_upsample_fwd(c.packed + c.P.tc_up01[1], u1, u2, g.B * len[1], c.st))) return rc;
         return mvn_tc_upsample_fwd(c.packed + c.P.tc_up, u2, ctx, g.B * len[2], c.st);
@@ -887,6 +893,8 @@ static int video_bwd(const Ctx& c, const float* video, const void* dctx, int dct
         if ((rc = row_gemm(c, a))) return rc;
     }
     const int rows = g.B * 160, K = 4096 * g.Cin;
+    if (tc && mvn_tc_video_supported(C, K) && mvn_tc_video_partial_floats(rows, K) * 4 <= (size_t)2 * 148 * (128 * 256 + 256) * 4)
+        return mvn_tc_video_bwd(video, denc, (float*)(c.scratch + c.SL.tc_partial), pg + c.P.wv, pg + c.P.bv, rows, K, c.st);
     TnGemmArgs t; memset(&t, 0, sizeof(t));
     t.rows = rows; t.Trow = rows; t.N = C; t.nsrc = 1;
     t.src[0] = make_tn(video, MVN_F32, K, K, rows, 0, 0, pg + c.P.wv, C);
