@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libmovenet_b200.so")
-SOURCES = ["api.cu", "pack.cu", "wavenet.cu", "mulaw.cu", "decode.cu", "layer_tc.cu", "layer_tc_bwd.cu", "head_tc.cu", "input_tc.cu", "ce.cu", "decode_tc.cu", "upsample_tc.cu", "optim.cu", "wide.cu", "peer.cu", "video_tc.cu"]
+SOURCES = ["api.cu", "pack.cu", "wavenet.cu", "mulaw.cu", "decode.cu", "layer_tc.cu", "layer_tc_bwd.cu", "layer_tc_bwd_db.cu", "head_tc.cu", "input_tc.cu", "ce.cu", "decode_tc.cu", "upsample_tc.cu", "optim.cu", "wide.cu", "peer.cu", "video_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 

@@ -314,39 +314,42 @@ EncodeTiledFn encode_fn() {
 // so the ~100 descriptors a training step needs are encoded once and then served from this table (mutex-guarded, the only
 // mutable global state of the library besides the per-thread error string and the launch counter).
 namespace {
-struct MapSlot { const void* ptr; int B, T; bool used; CUtensorMap map; };
+struct MapSlot { const void* ptr; int B, T, rows; bool used; CUtensorMap map; };
 constexpr int MAP_SLOTS = 512;
 MapSlot g_maps[MAP_SLOTS];
 std::mutex g_maps_mu;
-int encode_act_map(CUtensorMap* map, const void* ptr, int B, int T);
+int encode_act_map(CUtensorMap* map, const void* ptr, int B, int T, int rows);
 }
 
-int tc::make_act_map(CUtensorMap* map, const void* ptr, int B, int T) {
-    const size_t h = ((size_t)(uintptr_t)ptr >> 8) * 0x9E3779B97F4A7C15ull + (size_t)B * 1315423911u + (size_t)T;
+int tc::make_act_map(CUtensorMap* map, const void* ptr, int B, int T) { return tc::make_act_map_rows(map, ptr, B, T, TILE_T); }
+
+// box = {64 channels, `rows` time steps, 1 clip}
+int tc::make_act_map_rows(CUtensorMap* map, const void* ptr, int B, int T, int rows) {
+    const size_t h = ((size_t)(uintptr_t)ptr >> 8) * 0x9E3779B97F4A7C15ull + (size_t)B * 1315423911u + (size_t)T + (size_t)rows * 7919u;
     const int i0 = (int)((h >> 20) % MAP_SLOTS);
     {
         std::lock_guard<std::mutex> lk(g_maps_mu);
         for (int probe = 0; probe < 4; ++probe) {
             const MapSlot& s = g_maps[(i0 + probe) % MAP_SLOTS];
-            if (s.used && s.ptr == ptr && s.B == B && s.T == T) { *map = s.map; return 0; }
+            if (s.used && s.ptr == ptr && s.B == B && s.T == T && s.rows == rows) { *map = s.map; return 0; }
         }
     }
-    const int rc = encode_act_map(map, ptr, B, T);
+    const int rc = encode_act_map(map, ptr, B, T, rows);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(g_maps_mu);
     int victim = i0;
     for (int probe = 0; probe < 4; ++probe) if (!g_maps[(i0 + probe) % MAP_SLOTS].used) { victim = (i0 + probe) % MAP_SLOTS; break; }
-    g_maps[victim].ptr = ptr; g_maps[victim].B = B; g_maps[victim].T = T; g_maps[victim].map = *map; g_maps[victim].used = true;
+    g_maps[victim].ptr = ptr; g_maps[victim].B = B; g_maps[victim].T = T; g_maps[victim].rows = rows; g_maps[victim].map = *map; g_maps[victim].used = true;
     return 0;
 }
 
 namespace {
-int encode_act_map(CUtensorMap* map, const void* ptr, int B, int T) {
+int encode_act_map(CUtensorMap* map, const void* ptr, int B, int T, int rows) {
     EncodeTiledFn fn = encode_fn();
     MVN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[3] = {(cuuint64_t)CC, (cuuint64_t)T, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)CC * 2, (cuuint64_t)T * CC * 2};
-    cuuint32_t box[3] = {(cuuint32_t)CC, (cuuint32_t)TILE_T, 1};
+    cuuint32_t box[3] = {(cuuint32_t)CC, (cuuint32_t)rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

@@ -23,6 +23,12 @@ int mvn_tc_bwd_reduce_all(const float* partial_all, float* pg, const PackedLayou
 int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const void* u_in, void* p_out, void* u_out,
                      const float* dskip, const void* q_in, void* q_out, const float* lw, float* lg, float* partial, const PackedLayout& P,
                      const Geo& g, int layer, cudaStream_t st);
+// The same backward with a second x / ctx buffer (layer_tc_bwd_db.cu): layers with dilation <= 8, (P, U) pair output.  The
+// context-gradient running sum is updated IN PLACE in q_sum (bf16 TMA add-reduction; the top layer -- p_in == null -- stores).
+int mvn_tc_bwd_db_supported(const Geo& g, int layer);
+int mvn_tc_layer_bwd_db(const void* x_in, const void* ctx, const void* p_in, const void* u_in, void* p_out, void* u_out,
+                        const float* dskip, void* q_sum, const float* lw, float* partial, const PackedLayout& P, const Geo& g, int layer,
+                        cudaStream_t st);
 // DenseConv head + softmax on tensor cores (head_tc.cu), input_channels == 64 or 128
 int mvn_tc_head_supported(int A, int S);
 size_t mvn_tc_head_partial_bytes();

@@ -192,4 +192,5 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 // (B, T, 64) bf16 time-major activation as a 3-D tensor map {channel, time, clip}, box {64, 128, 1}, 128B swizzle
 int make_act_map(CUtensorMap* map, const void* ptr, int B, int T);
+int make_act_map_rows(CUtensorMap* map, const void* ptr, int B, int T, int rows);     // same, box of `rows` time steps (<= 256)
 }  // namespace tc

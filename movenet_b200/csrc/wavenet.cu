@@ -919,10 +919,14 @@ extern "C" int mvn_layer_bwd(const mvn_shape_t* s, const void* packed, int layer
         const size_t nb = (size_t)g.B * g.T * g.C * g.es;
         float* lg = pg + c.P.layer0 + (size_t)layer * c.P.layer_stride;
         const bool pair_in = layer + 1 < g.N && !mvn_tc_bwd_sum_out(g, layer + 1), sum_out = mvn_tc_bwd_sum_out(g, layer);
+        float* part = (float*)(c.scratch + c.SL.tc_layer_partial + (size_t)layer * mvn_tc_bwd_partial_bytes());
+        if (mvn_tc_bwd_db_supported(g, layer))
+            return mvn_tc_layer_bwd_db(c.x(layer), g.video ? c.acts + c.AL.ctx : nullptr, c.scratch + c.SL.dxa, pair_in ? c.scratch + c.SL.dgated : nullptr,
+                                       c.scratch + c.SL.dxb, c.scratch + c.SL.dz, (const float*)(c.scratch + c.SL.dskip), c.scratch + c.SL.dctx,
+                                       c.lw(layer), part, c.P, g, layer, c.st);
         return mvn_tc_layer_bwd(c.x(layer), g.video ? c.acts + c.AL.ctx : nullptr, c.scratch + c.SL.dxa, pair_in ? c.scratch + c.SL.dgated : nullptr,
                                 c.scratch + c.SL.dxb, sum_out ? nullptr : c.scratch + c.SL.dz, (const float*)(c.scratch + c.SL.dskip),
-                                c.scratch + c.SL.dctx, c.scratch + c.SL.dctx + nb, c.lw(layer), lg,
-                                (float*)(c.scratch + c.SL.tc_layer_partial + (size_t)layer * mvn_tc_bwd_partial_bytes()), c.P, g, layer,
+                                c.scratch + c.SL.dctx, c.scratch + c.SL.dctx + nb, c.lw(layer), lg, part, c.P, g, layer,
                                 c.st);
     }
     return layer_bwd(c, layer, layer + 1 < g.N ? c.scratch + c.SL.dxa : nullptr, c.scratch + c.SL.dxb, pg);
@@ -995,16 +999,25 @@ static int backward_impl(const mvn_shape_t* s, const void* packed, const float* 
         // running sum of the context gradient, bf16, ping-pong inside the fp32 dctx slot
         void* Qb[2] = {c.scratch + c.SL.dctx, c.scratch + c.SL.dctx + nb};
         // a layer with dilation <= 128 writes ONE summed stream into its P slot (mvn_tc_bwd_sum_out) and no U
-        int cur = 0, pair = 0;
+        // (the double-buffered kernel of layer_tc_bwd_db.cu -- dilation <= 8 -- adds to the running sum in place, the other one
+        // reads one buffer and writes the other)
+        int cur = 0, pair = 0, qcur = 0;
         for (int l = g.N - 1; l >= 0; --l) {
             float* lg = pg + c.P.layer0 + (size_t)l * c.P.layer_stride;
             const bool first = l == g.N - 1;
             const int sum_out = mvn_tc_bwd_sum_out(g, l);
-            if ((rc = mvn_tc_layer_bwd(c.x(l), g.video ? c.acts + c.AL.ctx : nullptr, first ? nullptr : Pb[cur], first || !pair ? nullptr : Ub[cur],
-                                       Pb[cur ^ 1], sum_out ? nullptr : Ub[cur ^ 1],
-                                       (const float*)(c.scratch + c.SL.dskip), Qb[cur], Qb[cur ^ 1], c.lw(l), lg,
-                                       (float*)(c.scratch + c.SL.tc_layer_partial + (size_t)l * mvn_tc_bwd_partial_bytes()), c.P, g, l,
-                                       c.st))) return rc;
+            float* part = (float*)(c.scratch + c.SL.tc_layer_partial + (size_t)l * mvn_tc_bwd_partial_bytes());
+            const void* ctx = g.video ? c.acts + c.AL.ctx : nullptr;
+            if (mvn_tc_bwd_db_supported(g, l)) {
+                if ((rc = mvn_tc_layer_bwd_db(c.x(l), ctx, first ? nullptr : Pb[cur], first || !pair ? nullptr : Ub[cur], Pb[cur ^ 1], Ub[cur ^ 1],
+                                              (const float*)(c.scratch + c.SL.dskip), Qb[qcur], c.lw(l), part, c.P, g, l, c.st))) return rc;
+            } else {
+                if ((rc = mvn_tc_layer_bwd(c.x(l), ctx, first ? nullptr : Pb[cur], first || !pair ? nullptr : Ub[cur],
+                                           Pb[cur ^ 1], sum_out ? nullptr : Ub[cur ^ 1],
+                                           (const float*)(c.scratch + c.SL.dskip), Qb[qcur], Qb[qcur ^ 1], c.lw(l), lg, part, c.P, g, l,
+                                           c.st))) return rc;
+                qcur ^= 1;
+            }
             cur ^= 1; pair = !sum_out;
         }
         if ((rc = mvn_tc_bwd_reduce_all((const float*)(c.scratch + c.SL.tc_layer_partial), pg, c.P, g, c.st))) return rc;
@@ -1012,7 +1025,7 @@ static int backward_impl(const mvn_shape_t* s, const void* packed, const float* 
             if ((rc = mvn_tc_input_bwd(audio, (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), Pb[cur],
                                        pair ? Ub[cur] : nullptr, pg + c.P.win, (float*)(c.scratch + c.SL.tc_partial), g, c.st))) return rc;
         } else if ((rc = input_bwd(c, audio, Pb[cur], pair ? Ub[cur] : nullptr, pair ? g.dil[0] : 0, pg))) return rc;
-        dctx_final = Qb[cur]; dctx_dtype = MVN_BF16;
+        dctx_final = Qb[qcur]; dctx_dtype = MVN_BF16;
     } else {
         void* bufs[2] = {c.scratch + c.SL.dxa, c.scratch + c.SL.dxb};
         const void* dx_next = nullptr; int cur = 0;

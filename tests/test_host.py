@@ -55,6 +55,21 @@ def test_buffer_sizes_are_reported_without_a_gpu():
     assert _lib.size("mvn_decode_state_bytes", s3, _lib.DECODE_CAUSAL) == _lib.size("mvn_decode_state_bytes", s3, _lib.DECODE_REFERENCE)
 
 
+def test_peer_exchange_buffers_cover_the_gradient_regions():
+    """csrc/peer.cu: staging + receive areas hold two 16-byte lines per float4 of the gradient regions; the flat gradient
+    (reference shapes) can never be larger than the packed regions it is unpacked from"""
+    import ctypes as C
+    m = movenet_b200.WaveNet(3, 3, 64, 64, 8)
+    for video in (0, 1):
+        s = _lib.Shape(3, 3, 64, 64, 8, 1, 3, 160000, video, _lib.BF16, 1, 0)
+        stage, recv = C.c_size_t(), C.c_size_t()
+        _lib.call("mvn_peer_layout", C.byref(s), C.byref(stage), C.byref(recv))
+        _, flat_floats = m._grad_layout(bool(video))
+        assert stage.value == recv.value and stage.value % 256 == 0
+        assert stage.value >= flat_floats * 4 * 2                  # (value, step) pairs: twice the payload
+        assert stage.value <= _lib.size("mvn_packed_bytes", s) * 2 + 4096
+
+
 def test_constructor_signature_is_the_reference_one():
     sig = inspect.signature(movenet_b200.WaveNet.__init__)
     names = [p for p in sig.parameters if p != "self"]
