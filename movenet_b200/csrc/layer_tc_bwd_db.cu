@@ -14,7 +14,9 @@
 //    the d(skip) tile) by 16 columns of ones that live in the d(skip) tile's unused channels, so W1 = [dz^T x(t-d) | dz^T x(t)]
 //    (N = 128) + [dz^T ctx | dz^T 1] (N = 80) and the eight N = 16 MMAs that re-read the whole dz operand are gone.
 //
-// Shared memory: weight image | set 0 | set 1 | U | P | DSK | DZ0 | DZ1 | G | ONES | barriers, set = x box (17 KB) + ctx tile.
+//  * the residual / skip bias sums ride in W2 the same way ([gated | ones], N = 80): no N = 16 MMA is left in the kernel.
+//
+// Shared memory: weight image | set 0 | set 1 | G | U | P | DSK | DZ0 | DZ1 | barriers, set = x box (17 KB) + ctx tile.
 #include <cstdio>
 #include <cstdlib>
 #include "tc_common.cuh"
@@ -53,7 +55,7 @@ constexpr int XBOX_ROWS = TILE_T + 8, XBOX_BYTES = XBOX_ROWS * 128;       // 174
 constexpr int SET_BYTES = XBOX_BYTES + TILE_BYTES;
 constexpr int ONES_COLS = 16;                      // the ones block: logical channels [0, 16) of the DSK tile, d(skip) follows
 // TMEM: the tile's columns [0, 192) as in layer_tc_bwd.cu; accumulators that live across the CTA's tiles:
-constexpr int W1A_COL = 192, W1B_COL = 320, W2_COL = 400, B2_COL = 464;   // 128 | 64 + 16 | 64 | 16
+constexpr int W1A_COL = 192, W1B_COL = 320, W2_COL = 400;   // 128 | 64 + 16 | 64 + 16 (the 16: products with the ones block = bias sums)
 
 struct DbArgs {
     const void* img;
@@ -64,12 +66,13 @@ struct DbArgs {
 };
 
 __host__ __device__ inline int db_sets_off(int nc, int N2) { return smem_a_off(nc, N2); }
-__host__ __device__ inline int db_smem_total(int nc, int N2) { return db_sets_off(nc, N2) + 2 * SET_BYTES + 6 * TILE_BYTES + 1024 + 128; }
+__host__ __device__ inline int db_smem_total(int nc, int N2) { return db_sets_off(nc, N2) + 2 * SET_BYTES + 6 * TILE_BYTES + 128; }
 
 __device__ __forceinline__ void warp_arrive(uint64_t* bar) {     // every lane has fenced its own writes; one lane signals
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
 }
+__device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
     asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
                  ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
@@ -90,16 +93,15 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
     uint8_t* sBrs = smem + smem_brs_off(nc);
     float* sbz = (float*)(smem + smem_bias_off(nc, a.N2));
     uint8_t* sSet = smem + db_sets_off(nc, a.N2);      // set s: x box at sSet + s SET_BYTES, ctx tile XBOX_BYTES further
-    uint8_t* sU = sSet + 2 * SET_BYTES;                // U | P | DSK in this order: [P|DSK] and [U|DSK] are both M = 128 block pairs
+    uint8_t* sG = sSet + 2 * SET_BYTES;                // gated tile; the ones block of DSK is its second B block (3 tiles further)
+    uint8_t* sU = sG + TILE_BYTES;                     // U | P | DSK in this order: [P|DSK] and [U|DSK] are both M = 128 block pairs
     uint8_t* sDXS = sU + TILE_BYTES;                   // the P tile (the stream gradient is P + U, never summed in memory)
     uint8_t* sDSK = sDXS + TILE_BYTES;
     uint8_t* sDZ = sDSK + TILE_BYTES;                  // DZ0 (filter half) | DZ1 (gate half)
-    uint8_t* sG = sDZ + 2 * TILE_BYTES;
-    uint8_t* sONES = sG + TILE_BYTES;
     // barriers, one completion per tile each (parity = tile iteration & 1), except IMG (once) and A_IN0/1 (every other tile).
     // E_* are the worker -> control-warp signals (one arrival per worker warp), the rest are TMA / tcgen05.commit completions.
     enum { IMG = 0, A_IN0, A_IN1, P_IN, U_IN, G1, G2, G3, W1, WALL, E_DSK, E_G, E_DZ, E_OUT, N_BARS };
-    uint64_t* bar = (uint64_t*)(sONES + 1024);
+    uint64_t* bar = (uint64_t*)(sDZ + 2 * TILE_BYTES);
     uint32_t* tmem_slot = (uint32_t*)(bar + N_BARS);
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -119,14 +121,12 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // constant tiles: DSK = ones in logical channels [0, 16), zero elsewhere (the S live channels are rewritten every tile);
-    // ONES is all bf16 1.0 (the B operand of the residual / skip bias sums)
+    // constant tile: DSK = ones in logical channels [0, 16), zero elsewhere (the S live channels are rewritten every tile)
     for (int i = tid; i < TILE_BYTES / 16; i += N_THREADS) {
         const int row = i >> 3, q = (i & 7) ^ (row & 7);        // 16-byte chunk i holds logical channels [8 q, 8 q + 8)
         const uint32_t v = q < ONES_COLS / 8 ? 0x3F803F80u : 0u;
         ((uint4*)sDSK)[i] = make_uint4(v, v, v, v);
     }
-    for (int i = tid; i < 1024 / 4; i += N_THREADS) ((uint32_t*)sONES)[i] = 0x3F803F80u;
     if (a.zero_in)        // U | P are adjacent and stay zero for the whole kernel
         for (int i = tid; i < 2 * TILE_BYTES / 16; i += N_THREADS) ((uint4*)sU)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
@@ -153,21 +153,19 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
         const uint64_t mBrs = umma_desc_mn(smem_u32(sBrs), TILE_BYTES), mBz = umma_desc_mn(smem_u32(sBz), TILE_BYTES),
                        mDZ = umma_desc_mn(smem_u32(sDZ), TILE_BYTES),
                        mDXS = umma_desc_mn(smem_u32(sDXS), TILE_BYTES), mU = umma_desc_mn(smem_u32(sU), 2 * TILE_BYTES),
-                       mG = umma_desc_mn(smem_u32(sG), TILE_BYTES);
+                       mG = umma_desc_mn(smem_u32(sG), (uint32_t)(sDSK - sG));      // [gated | ones]
         // weight-gradient B operands per set: [x(t-d) | x(t)] = two 64-wide blocks d rows apart; [ctx | ones] = the ctx tile and,
         // one block stride further, the first 16 channels of the DSK tile
         const uint64_t mX0 = umma_desc_mn(smem_u32(sSet) + tap0, (uint32_t)a.dil * 128),
                        mX1 = umma_desc_mn(smem_u32(sSet + SET_BYTES) + tap0, (uint32_t)a.dil * 128);
         const uint64_t mC0 = umma_desc_mn(smem_u32(sSet + XBOX_BYTES), (uint32_t)(sDSK - (sSet + XBOX_BYTES))),
                        mC1 = umma_desc_mn(smem_u32(sSet + SET_BYTES + XBOX_BYTES), (uint32_t)(sDSK - (sSet + SET_BYTES + XBOX_BYTES)));
-        const uint64_t ones = umma_desc_mn_plain(smem_u32(sONES), 256, 128);
         const uint32_t iG1 = umma_idesc_major(TILE_T, 128, 0, 0);
         const uint32_t iG2 = umma_idesc_major(TILE_T, 64, 0, 1);
         const uint32_t iG3 = umma_idesc_major(TILE_T, NZ, 0, 1);
         const uint32_t iW1a = umma_idesc_major(TILE_T, 128, 1, 1);
         const uint32_t iW1b = umma_idesc_major(TILE_T, CC + ONES_COLS, 1, 1);
-        const uint32_t iW2 = umma_idesc_major(TILE_T, 64, 1, 1);
-        const uint32_t iB = umma_idesc_major(TILE_T, 16, 1, 1);
+        const uint32_t iW2 = umma_idesc_major(TILE_T, CC + ONES_COLS, 1, 1);
         auto load_set = [&](int s, int lb, int l0) {       // x box / ctx tile of one time tile -> A_IN[s]
             uint8_t* dst = sSet + s * SET_BYTES;
             mbar_expect_tx(bar + A_IN0 + s, (uint32_t)(XBOX_BYTES + (nc == 3 ? TILE_BYTES : 0)));
@@ -219,19 +217,9 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
 #if !MVN_DB_G1_FIRST
             issue_g1(s, it >> 1);
 #endif
-            if (leader) {
-                // the previous tile's P' / U' / Q' stores have left DZ0 / DZ1 / the other set's ctx tile (ordered before G2's commit:
-                // the workers write DZ again only after they have seen G2) -> the other set takes the NEXT tile's x / ctx now, a whole
-                // tile before its recompute GEMM needs them
-                tma_wait_read0();
-                if (has_next) {
-                    load_set((int)(s ^ 1), nb, n0);
-                    if (!a.zero_in) {                  // ... and the next tile's gradient tiles start towards L2
-                        tma_prefetch_3d(&map_p, 0, n0, nb);
-                        if (PAIR_IN) tma_prefetch_3d(&map_u, 0, n0 + a.dil_up, nb);
-                    }
-                }
-            }
+            // the previous tile's P' / U' stores have left DZ0 / DZ1 (ordered before G2's commit: the workers write DZ again only after
+            // they have seen G2); its context-gradient reduction -- the younger bulk group, and a slow one -- may still be reading
+            if (leader) { if (nc == 3) tma_wait_read1(); else tma_wait_read0(); }
             // G2: d(gated) = (P + U) . Wr + dskip . Ws as three accumulating products (no pre-sum pass): contraction over
             // the image's ROWS (c_out | s) -> B is MN-major.  Needs only the loads and the DSK tile, so it runs next to G1.
             CLKC(3);
@@ -255,24 +243,31 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
                     if (k < (a.S + 15) / 16)               // behind the ones block in the DSK tile (one K step further)
                         umma(tmem_u + 128, desc_adv(kDSK, (k + 1) * 32), desc_adv(mBrs, (4 + k) * 2048), iG2, 1);
                 umma_commit(bar + G2);
+                CLKC(6);
+                // every store of the previous tile has left shared memory -> the other set (its ctx tile was the staging tile of the
+                // reduction) takes the NEXT tile's x / ctx now, most of a tile before its recompute GEMM needs them
+                tma_wait_read0();
+                if (has_next) {
+                    load_set((int)(s ^ 1), nb, n0);
+                    if (!a.zero_in) {                  // ... and the next tile's gradient tiles start towards L2
+                        tma_prefetch_3d(&map_p, 0, n0, nb);
+                        if (PAIR_IN) tma_prefetch_3d(&map_u, 0, n0 + a.dil_up, nb);
+                    }
+                }
             }
-            // W2 (K = time): d[Wr | Ws]^T += [P|DSK]^T . gated + [U|DSK]^T . gated, and the bias sums (the same A operands times ones).
+            // W2 (K = time): d[Wr | Ws]^T += [P|DSK]^T . [gated | 1] + [U|DSK]^T . [gated | 1]: column 64 holds the bias sums.
             // The DSK rows (64..) are accumulated twice and halved at the flush (exact).  MVN_DB_W2_EARLY=1 issues it here, between
             // G2 and G3 (it needs only the gated tile and P / U), so that it executes under epilogue 1b; measured slower (it delays
             // G3 and competes with the epilogue for shared-memory bandwidth), so it follows W1 by default.
             const uint32_t acc0 = it != 0;
             auto issue_w2 = [&]() {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < 8; ++k)
                     umma(tmem_u + W2_COL, desc_adv(mDXS, k * 2048), desc_adv(mG, k * 2048), iW2, acc0 | (k != 0));
-                    umma(tmem_u + B2_COL, desc_adv(mDXS, k * 2048), ones, iB, acc0 | (k != 0));
-                }
                 if (PAIR_IN) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
+                    for (int k = 0; k < 8; ++k)
                         umma(tmem_u + W2_COL, desc_adv(mU, k * 2048), desc_adv(mG, k * 2048), iW2, 1);
-                        umma(tmem_u + B2_COL, desc_adv(mU, k * 2048), ones, iB, 1);
-                    }
                 }
                 umma_commit(bar + WALL);
                 CLKC(10);
@@ -283,7 +278,6 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
             if (leader) issue_w2();
 #endif
             // G3: D4[t][kin] = sum_m dz[t][m] Wz[m][kin]  (A = dz tiles K-major, B = the image read MN-major)
-            CLKC(6);
             mbar_wait(bar + E_DZ, ph);
             CLKC(7);
             tc_fence_after();
@@ -533,7 +527,7 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
         {
             uint32_t v1[8], v2[8];
             tmem_ld8(tmem + lane_base + W1B_COL + CC, v1);
-            tmem_ld8(tmem + lane_base + B2_COL, v2);
+            tmem_ld8(tmem + lane_base + W2_COL + CC, v2);
             tmem_ld_wait();
             if (half == 0) {
                 if (nc == 3) part[128 * PART_LD + r] = __uint_as_float(v1[0]);
