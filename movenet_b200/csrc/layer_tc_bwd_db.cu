@@ -34,8 +34,11 @@ namespace {
 #ifndef MVN_DB_W2_EARLY
 #define MVN_DB_W2_EARLY 0
 #endif
-#ifndef MVN_DB_G1_FIRST
-#define MVN_DB_G1_FIRST 1
+#ifndef MVN_DB_TAIL
+#define MVN_DB_TAIL 0
+#endif
+#ifndef MVN_DB_DSKIP_PF
+#define MVN_DB_DSKIP_PF 1
 #endif
 #if MVN_PHASE_CLOCKS
 __device__ unsigned long long g_clk_db[3][3][20];
@@ -202,9 +205,7 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
             if (!a.zero_in) load_tile(sDXS, &map_p, P_IN, lb, l0);
             if (PAIR_IN) load_tile(sU, &map_u, U_IN, lb, l0 + a.dil_up);
         }
-#if MVN_DB_G1_FIRST
         issue_g1(0, 0);
-#endif
         for (uint32_t it = 0; it < (uint32_t)count; ++it) {
             const uint32_t ph = it & 1, s = it & 1;
             const int tile = top + (int)it * step;
@@ -213,10 +214,7 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
             const bool has_next = it + 1 < (uint32_t)count;
             const int nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
             const int set_off = (int)s * SET_BYTES;
-            // (MVN_DB_G1_FIRST: G1 of this tile was issued at the end of the previous iteration, or before the loop)
-#if !MVN_DB_G1_FIRST
-            issue_g1(s, it >> 1);
-#endif
+            // (G1 of this tile was issued at the end of the previous iteration, or before the loop)
             // the previous tile's P' / U' stores have left DZ0 / DZ1 (ordered before G2's commit: the workers write DZ again only after
             // they have seen G2); its context-gradient reduction -- the younger bulk group, and a slow one -- may still be reading
             if (leader) { if (nc == 3) tma_wait_read1(); else tma_wait_read0(); }
@@ -310,6 +308,9 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
             // left the tensor pipe -- the next tile's G1, because the workers are idle until it completes; the P / U reloads (needed by
             // G2, half a tile away) and the context-gradient add-reduction (it occupies the TMA unit far longer than a store) follow.
             CLKC(12);
+#if MVN_DB_TAIL == 1        // G1 first, then the stores
+            if (has_next) issue_g1(s ^ 1, (it + 1) >> 1);
+#endif
             if (leader) {
                 tma_store_3d(&map_pout, sDZ, 0, t0, b);
                 tma_store_3d(&map_uout, sDZ + TILE_BYTES, 0, t0, b);
@@ -318,11 +319,14 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
             if (has_next) {
                 mbar_wait(bar + WALL, ph);         // W2 no longer reads the P and U tiles
                 CLKC(15);
-#if MVN_DB_G1_FIRST
+#if MVN_DB_TAIL == 0
                 issue_g1(s ^ 1, (it + 1) >> 1);
 #endif
                 if (leader && !a.zero_in) load_tile(sDXS, &map_p, P_IN, nb, n0);
                 if (leader && PAIR_IN) load_tile(sU, &map_u, U_IN, nb, n0 + a.dil_up);
+#if MVN_DB_TAIL == 2        // P / U reloads before G1
+                issue_g1(s ^ 1, (it + 1) >> 1);
+#endif
             }
             if (leader && nc == 3) {
 #if defined(MVN_DB_Q_STORE)
@@ -435,6 +439,14 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
             fence_proxy_async();
             tc_fence_before();
             warp_arrive(bar + E_DZ);
+#if MVN_DB_DSKIP_PF
+            // the next tile's d(skip) row towards L2 now: the load itself (end of the iteration) is the head of the next tile's chain.
+            // (Loading into registers here instead was measured slower: 120.5 vs 116.4 us per launch.)
+            if (half == 0 && has_next) {
+                const int tl = tile + step, lb = tl / a.tiles_per_clip, lt = (tl - lb * a.tiles_per_clip) * TILE_T + r, js = lt - (a.RF - 1);
+                if (lt < a.T && js >= 0 && js < a.Tout) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dskip + ((size_t)lb * a.Tout + js) * a.S));
+            }
+#endif
             CLKW(6); CLKM(6);
             // ---- epilogue 2: U' = W0^T dz, P' = d(x') + W1^T dz, Q contribution = V^T dz: registers until W1 releases the tiles
             mbar_wait(bar + G3, ph);
