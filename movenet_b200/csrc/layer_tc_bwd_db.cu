@@ -31,15 +31,6 @@ namespace {
 #ifndef MVN_PHASE_CLOCKS
 #define MVN_PHASE_CLOCKS 0
 #endif
-#ifndef MVN_DB_W2_EARLY
-#define MVN_DB_W2_EARLY 0
-#endif
-#ifndef MVN_DB_TAIL
-#define MVN_DB_TAIL 0
-#endif
-#ifndef MVN_DB_DSKIP_PF
-#define MVN_DB_DSKIP_PF 1
-#endif
 #if MVN_PHASE_CLOCKS
 __device__ unsigned long long g_clk_db[3][3][20];
 #define CLK_(role, i, cond) do { if (blockIdx.x == 0 && it >= 5 && it < 8 && (cond)) g_clk_db[role][it - 5][i] = clock64(); } while (0)
@@ -103,7 +94,7 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
     uint8_t* sDZ = sDSK + TILE_BYTES;                  // DZ0 (filter half) | DZ1 (gate half)
     // barriers, one completion per tile each (parity = tile iteration & 1), except IMG (once) and A_IN0/1 (every other tile).
     // E_* are the worker -> control-warp signals (one arrival per worker warp), the rest are TMA / tcgen05.commit completions.
-    enum { IMG = 0, A_IN0, A_IN1, P_IN, U_IN, G1, G2, G3, W1, WALL, E_DSK, E_G, E_DZ, E_OUT, N_BARS };
+    enum { IMG = 0, A_IN0, A_IN1, P_IN, U_IN, G1, G2, G3, W1, WALL, E_DSK, E_DZ, E_OUT, N_BARS };
     uint64_t* bar = (uint64_t*)(sDZ + 2 * TILE_BYTES);
     uint32_t* tmem_slot = (uint32_t*)(bar + N_BARS);
 
@@ -254,9 +245,8 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
                 }
             }
             // W2 (K = time): d[Wr | Ws]^T += [P|DSK]^T . [gated | 1] + [U|DSK]^T . [gated | 1]: column 64 holds the bias sums.
-            // The DSK rows (64..) are accumulated twice and halved at the flush (exact).  MVN_DB_W2_EARLY=1 issues it here, between
-            // G2 and G3 (it needs only the gated tile and P / U), so that it executes under epilogue 1b; measured slower (it delays
-            // G3 and competes with the epilogue for shared-memory bandwidth), so it follows W1 by default.
+            // The DSK rows (64..) are accumulated twice and halved at the flush (exact).  It follows W1 (issuing it between G2 and G3, under
+            // epilogue 1b, was measured slower: it delays G3 and competes with the epilogue for shared-memory bandwidth).
             const uint32_t acc0 = it != 0;
             auto issue_w2 = [&]() {
 #pragma unroll
@@ -270,11 +260,6 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
                 umma_commit(bar + WALL);
                 CLKC(10);
             };
-#if MVN_DB_W2_EARLY
-            mbar_wait(bar + E_G, ph);
-            tc_fence_after();
-            if (leader) issue_w2();
-#endif
             // G3: D4[t][kin] = sum_m dz[t][m] Wz[m][kin]  (A = dz tiles K-major, B = the image read MN-major)
             mbar_wait(bar + E_DZ, ph);
             CLKC(7);
@@ -299,18 +284,13 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
                 }
                 umma_commit(bar + W1);
                 CLKC(9);
-#if !MVN_DB_W2_EARLY
                 issue_w2();
-#endif
             }
             mbar_wait(bar + E_OUT, ph);            // P', U', Q' are staged; nobody reads the P / U tiles or the tile's TMEM columns any more
             // Order of the tail: the P' / U' stores (the DZ tiles must drain before the next epilogue 1b), then -- as soon as W2 has
             // left the tensor pipe -- the next tile's G1, because the workers are idle until it completes; the P / U reloads (needed by
             // G2, half a tile away) and the context-gradient add-reduction (it occupies the TMA unit far longer than a store) follow.
             CLKC(12);
-#if MVN_DB_TAIL == 1        // G1 first, then the stores
-            if (has_next) issue_g1(s ^ 1, (it + 1) >> 1);
-#endif
             if (leader) {
                 tma_store_3d(&map_pout, sDZ, 0, t0, b);
                 tma_store_3d(&map_uout, sDZ + TILE_BYTES, 0, t0, b);
@@ -319,22 +299,13 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
             if (has_next) {
                 mbar_wait(bar + WALL, ph);         // W2 no longer reads the P and U tiles
                 CLKC(15);
-#if MVN_DB_TAIL == 0
                 issue_g1(s ^ 1, (it + 1) >> 1);
-#endif
                 if (leader && !a.zero_in) load_tile(sDXS, &map_p, P_IN, nb, n0);
                 if (leader && PAIR_IN) load_tile(sU, &map_u, U_IN, nb, n0 + a.dil_up);
-#if MVN_DB_TAIL == 2        // P / U reloads before G1
-                issue_g1(s ^ 1, (it + 1) >> 1);
-#endif
             }
             if (leader && nc == 3) {
-#if defined(MVN_DB_Q_STORE)
-                tma_store_3d(&map_q, sSet + set_off + XBOX_BYTES, 0, t0, b);          // (timing experiment: wrong sums)
-#else
                 if (a.zero_in) tma_store_3d(&map_q, sSet + set_off + XBOX_BYTES, 0, t0, b);
                 else tma_reduce_add_3d(&map_q, sSet + set_off + XBOX_BYTES, 0, t0, b);
-#endif
                 tma_commit();
             }
             CLKC(13);
@@ -406,10 +377,6 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
                 *(uint4*)(sG + o0) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
                 *(uint4*)(sG + o1) = make_uint4(oy[4], oy[5], oy[6], oy[7]);
             }
-#if MVN_DB_W2_EARLY
-            fence_proxy_async();
-            warp_arrive(bar + E_G);          // the gated tile is complete: W2 may run
-#endif
             // ---- epilogue 1b: gate derivative -> DZ0 | DZ1 ------------------------------------------
             CLKW(4); CLKM(4);
             mbar_wait(bar + G2, ph);
@@ -439,14 +406,12 @@ layer_bwd_db_kernel(const __grid_constant__ CUtensorMap map_xbox, const __grid_c
             fence_proxy_async();
             tc_fence_before();
             warp_arrive(bar + E_DZ);
-#if MVN_DB_DSKIP_PF
             // the next tile's d(skip) row towards L2 now: the load itself (end of the iteration) is the head of the next tile's chain.
             // (Loading into registers here instead was measured slower: 120.5 vs 116.4 us per launch.)
             if (half == 0 && has_next) {
                 const int tl = tile + step, lb = tl / a.tiles_per_clip, lt = (tl - lb * a.tiles_per_clip) * TILE_T + r, js = lt - (a.RF - 1);
                 if (lt < a.T && js >= 0 && js < a.Tout) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.dskip + ((size_t)lb * a.Tout + js) * a.S));
             }
-#endif
             CLKW(6); CLKM(6);
             // ---- epilogue 2: U' = W0^T dz, P' = d(x') + W1^T dz, Q contribution = V^T dz: registers until W1 releases the tiles
             mbar_wait(bar + G3, ph);

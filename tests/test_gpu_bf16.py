@@ -45,12 +45,15 @@ def rel_l2(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize("summed", ["0", "1"])
+@pytest.mark.parametrize("summed,double_buffered", [("0", "1"), ("0", "0"), ("1", "1")])
 @pytest.mark.parametrize("name", ["cfg00", "cfg00_gain", "cfg03", "cfg04_short", "cfg04_full", "testarch_small", "odd"])
-def test_bf16_forward_loss_and_grads_against_golden(name, summed, monkeypatch):
-    """summed = "1": the backward's one-stream variant (MOVENET_B200_BWD_SUM, layer_tc_bwd.cu) on the same fixtures: few tiles
-    per clip, so nearly every CTA run is a warm-up tile plus one tile."""
+def test_bf16_forward_loss_and_grads_against_golden(name, summed, double_buffered, monkeypatch):
+    """The three backward layer kernels on the same fixtures.  Default: layers with dilation <= 8 on the double-buffered kernel
+    (layer_tc_bwd_db.cu: two-tap box, in-place add-reduction of the context gradient), the others on layer_tc_bwd.cu;
+    double_buffered = "0": every layer on layer_tc_bwd.cu; summed = "1": its one-stream variant (MOVENET_B200_BWD_SUM): few tiles per
+    clip, so nearly every CTA run is a warm-up tile plus one tile."""
     monkeypatch.setenv("MOVENET_B200_BWD_SUM", summed)
+    monkeypatch.setenv("MOVENET_B200_BWD_DB", double_buffered)
     fx = load_golden(name)
     m = build(fx, "bf16")
     audio = golden_audio(fx).cuda()
@@ -313,6 +316,14 @@ def test_backward_gradient_stream_modes(video, layer_size, monkeypatch):
     got = _grads_of(m16, audio, vid, target)
     monkeypatch.setenv("MOVENET_B200_BWD_SUM", "0")
     pair = _grads_of(m16, audio, vid, target)
+    # ... and the pair on the single-buffer kernel everywhere (default: dilations <= 8 on the double-buffered kernel, whose
+    # context-gradient sum is accumulated by bf16 add-reductions in place -- a different rounding of the same sum)
+    monkeypatch.setenv("MOVENET_B200_BWD_DB", "0")
+    single = _grads_of(m16, audio, vid, target)
+    monkeypatch.delenv("MOVENET_B200_BWD_DB")
+    for k in ref:
+        assert rel_l2(single[k], ref[k]) < GRAD_RTOL, (k, "single buffer", rel_l2(single[k], ref[k]))
+        assert rel_l2(pair[k], single[k]) < 0.02, (k, "double vs single buffer", rel_l2(pair[k], single[k]))
     assert ref.keys() == got.keys() == pair.keys()
     errs = []
     for k in ref:
