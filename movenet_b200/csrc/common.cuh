@@ -81,3 +81,10 @@ inline cudaError_t mvn_ensure_smem(F func, int bytes, MvnSmemAttr& slot) {
 }
 // SMs of the current device (persistent grids are sized from it); cached per device
 int mvn_sm_count();
+// Side streams of the current device (created on first use, non-blocking) for small follow-up kernels -- partial-sum
+// reductions -- that need not sit between two persistent kernels on the caller's stream.  mvn_stream_after(w, s): everything
+// enqueued on `w` from now on waits for everything enqueued on `s` so far.  mvn_side_stream(i) returns nullptr when side
+// streams are switched off ($MOVENET_B200_SIDE_STREAMS=0): the caller then uses its own stream.
+#define MVN_SIDE_STREAMS 3
+cudaStream_t mvn_side_stream(int i);
+int mvn_stream_after(cudaStream_t waiter, cudaStream_t signaller);

@@ -698,7 +698,7 @@ int mvn_tc_head_fwd(const float* packed, const PackedLayout& P, const Geo& g, co
 
 int mvn_tc_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, const float* probs,
                     const float* dout, const long long* target, const float* grad_loss, float* dskip, float* pg, float* partial,
-                    cudaStream_t st) {
+                    cudaStream_t st, int defer_reduce) {
     HeadArgs a; memset(&a, 0, sizeof(a)); fill_args(a, packed, P, g);
     a.skip = skip; a.probs = probs; a.dout = dout; a.target = target; a.gloss = grad_loss; a.dskip = dskip; a.partial = partial;
     MVN_REQUIRE(dout || (target && grad_loss && probs && !g.logits), "head backward: d(out) or (target, d(loss)) on probabilities is required");
@@ -708,7 +708,16 @@ int mvn_tc_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, co
     HEAD_DISPATCH(launch_bwd, a, grid, st);
     print_clocks(1, "bwd");
     int rc = mvn_check_launch("head_bwd_tc");
-    if (rc) return rc;
+    if (rc || defer_reduce) return rc;
+    return mvn_tc_head_reduce(P, g, pg, partial, st);
+}
+
+// fixed-order sum of the per-CTA partials of mvn_tc_head_bwd into the packed gradients (may run on another stream, later)
+int mvn_tc_head_reduce(const PackedLayout& P, const Geo& g, float* pg, const float* partial, cudaStream_t st) {
+    const int n_tiles = ((g.Tn + TILE_T - 1) / TILE_T) * g.B;      // (the grid mvn_tc_head_bwd launched)
+    if (n_tiles <= 0) return 0;
+    const int per_sm = g.A == 64 ? 2 : 1;
+    const int grid = n_tiles < per_sm * 148 ? n_tiles : per_sm * 148;
     if (g.A == 64) MVN_CUDA(mvn_launch_pdl(head_reduce_kernel<64>, dim3((HP<64>::floats + 31) / 32), dim3(32, RED_SPLIT), (size_t)(0), st, partial, grid, pg, P, g.S));
     else MVN_CUDA(mvn_launch_pdl(head_reduce_kernel<128>, dim3((HP<128>::floats + 31) / 32), dim3(32, RED_SPLIT), (size_t)(0), st, partial, grid, pg, P, g.S));
     return mvn_check_launch("head_reduce");

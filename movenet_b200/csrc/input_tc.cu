@@ -158,8 +158,24 @@ __global__ void input_reduce_kernel(const float* __restrict__ partial, int n_cta
 
 int mvn_tc_input_supported(int A, int C) { return C == 64 && A <= 256; }
 
+static int input_grid(const Geo& g, int* AH_out) {
+    const int tiles = ((g.T + TILE_T - 1) / TILE_T) * g.B;
+    const int AH = g.A <= 64 ? 1 : (g.A <= 128 ? 2 : 4), per_sm = AH == 1 ? 3 : (AH == 2 ? 2 : 1);
+    int grid = tiles < per_sm * mvn_sm_count() ? tiles : per_sm * mvn_sm_count();
+    const int cap = AH == 1 ? 444 : 296;          // (the partial slot holds 2 x 148 x 33024 floats)
+    if (grid > cap) grid = cap;
+    *AH_out = AH;
+    return grid;
+}
+
+int mvn_tc_input_reduce(float* dwin, const float* partial, const Geo& g, cudaStream_t st) {
+    int AH; const int grid = input_grid(g, &AH);
+    MVN_CUDA(mvn_launch_pdl(input_reduce_kernel, dim3((AH * IPART_MAX / 2 + 31) / 32), dim3(32, RED_SPLIT), (size_t)(0), st, partial, grid, dwin, g.A, AH));
+    return mvn_check_launch("input_reduce");
+}
+
 int mvn_tc_input_bwd(const float* audio, const int* codes, const unsigned char* dense, const void* p, const void* u,
-                     float* dwin, float* partial, const Geo& g, cudaStream_t st) {
+                     float* dwin, float* partial, const Geo& g, cudaStream_t st, int defer_reduce) {
     CUtensorMap mp, mu;
     int rc;
     if ((rc = make_act_map(&mp, p, g.B, g.T))) return rc;
@@ -168,27 +184,19 @@ int mvn_tc_input_bwd(const float* audio, const int* codes, const unsigned char* 
     a.audio = audio; a.codes = codes; a.dense = dense; a.partial = partial;
     a.B = g.B; a.T = g.T; a.A = g.A; a.dil0 = g.dil[0]; a.has_u = u != nullptr;
     a.tiles_per_clip = (g.T + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
-    const int AH = g.A <= 64 ? 1 : (g.A <= 128 ? 2 : 4);
+    int AH; const int grid = input_grid(g, &AH);
     const int smem = (2 * AH + 2) * TILE_BYTES + 64 + 1024;
     static MvnSmemAttr attr1, attr2, attr4;
-    int grid;
     if (AH == 1) {
         MVN_CUDA(mvn_ensure_smem(input_bwd_tc_kernel<1>, smem, attr1));
-        grid = a.n_tiles < 3 * mvn_sm_count() ? a.n_tiles : 3 * mvn_sm_count();
-        if (grid > 444) grid = 444;          // (the partial slot holds 2 x 148 x 33024 floats: 444 x 8192 fit)
         MVN_CUDA(mvn_launch_pdl(input_bwd_tc_kernel<1>, dim3(grid), dim3(128), (size_t)(smem), st, mp, mu, a));
     } else if (AH == 2) {
         MVN_CUDA(mvn_ensure_smem(input_bwd_tc_kernel<2>, smem, attr2));
-        grid = a.n_tiles < 2 * mvn_sm_count() ? a.n_tiles : 2 * mvn_sm_count();
-        if (grid > 296) grid = 296;
         MVN_CUDA(mvn_launch_pdl(input_bwd_tc_kernel<2>, dim3(grid), dim3(128), (size_t)(smem), st, mp, mu, a));
     } else {          // A = 256 (the reference's test architecture): four M = 128 operands, 160 KB of one-hot tiles, one CTA per SM
         MVN_CUDA(mvn_ensure_smem(input_bwd_tc_kernel<4>, smem, attr4));
-        grid = a.n_tiles < mvn_sm_count() ? a.n_tiles : mvn_sm_count();
-        if (grid > 296) grid = 296;
         MVN_CUDA(mvn_launch_pdl(input_bwd_tc_kernel<4>, dim3(grid), dim3(128), (size_t)(smem), st, mp, mu, a));
     }
-    if ((rc = mvn_check_launch("input_bwd_tc"))) return rc;
-    MVN_CUDA(mvn_launch_pdl(input_reduce_kernel, dim3((AH * IPART_MAX / 2 + 31) / 32), dim3(32, RED_SPLIT), (size_t)(0), st, partial, grid, dwin, g.A, AH));
-    return mvn_check_launch("input_reduce");
+    if ((rc = mvn_check_launch("input_bwd_tc")) || defer_reduce) return rc;
+    return mvn_tc_input_reduce(dwin, partial, g, st);
 }

@@ -36,25 +36,32 @@ int mvn_tc_head_pack(const float* w2_ref, float* packed, const PackedLayout& P, 
 int mvn_tc_head_fwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, float* out, cudaStream_t st);
 int mvn_tc_head_bwd(const float* packed, const PackedLayout& P, const Geo& g, const float* skip, const float* probs,
                     const float* dout, const long long* target, const float* grad_loss, float* dskip, float* pg, float* partial,
-                    cudaStream_t st);
+                    cudaStream_t st, int defer_reduce);
+// (defer_reduce: only the kernel that writes the per-CTA partials is launched; the caller launches mvn_tc_*_reduce later, possibly
+// on a side stream, so that the small fixed-order reduction does not sit between two persistent kernels)
+int mvn_tc_head_reduce(const PackedLayout& P, const Geo& g, float* pg, const float* partial, cudaStream_t st);
 // causal input conv weight gradient on tensor cores (input_tc.cu), A <= 64, C == 64, gradient given as (P, U)
 int mvn_tc_input_supported(int A, int C);
 int mvn_tc_input_bwd(const float* audio, const int* codes, const unsigned char* dense, const void* p, const void* u,
-                     float* dwin, float* partial, const Geo& g, cudaStream_t st);
+                     float* dwin, float* partial, const Geo& g, cudaStream_t st, int defer_reduce);
+int mvn_tc_input_reduce(float* dwin, const float* partial, const Geo& g, cudaStream_t st);
 // last level of the video upsampler on tensor cores (upsample_tc.cu), C == 64
 int mvn_tc_upsample_supported(int C);
 size_t mvn_tc_upsample_img_floats();
 int mvn_tc_upsample_pack(const float* wt, const float* bt, float* img, cudaStream_t st);
 int mvn_tc_upsample_fwd(const float* img, const void* u2_bf16, void* ctx_bf16, long long rows, cudaStream_t st);
 int mvn_tc_upsample_bwd(const float* img, const void* u_bf16, const void* dout_bf16, void* du, int du_bf16, float* dwt, float* dbt,
-                        float* partial, long long rows, cudaStream_t st);
+                        float* partial, long long rows, cudaStream_t st, int defer_reduce);
+int mvn_tc_upsample_reduce(float* dwt, float* dbt, const float* partial, long long rows, cudaStream_t st);
 
 // video encoder (Conv3d = one 4096 Cin -> C linear map per frame) and its weight gradient on tensor cores (video_tc.cu), C == 64
 int mvn_tc_video_supported(int C, int K);
 size_t mvn_tc_video_partial_floats(int rows, int K);
 int mvn_tc_video_fwd(const float* video, const float* wv, const float* bv, float* part, float* enc, void* enc16_or_null, int rows, int K,
                      cudaStream_t st);
-int mvn_tc_video_bwd(const float* video, const float* denc, float* part, float* dwv, float* dbv, int rows, int K, cudaStream_t st);
+int mvn_tc_video_bwd(const float* video, const float* denc, float* part, float* dwv, float* dbv, int rows, int K, cudaStream_t st,
+                     int defer_reduce);
+int mvn_tc_video_reduce(const float* denc, const float* part, float* dwv, float* dbv, int rows, int K, cudaStream_t st);
 
 // ---- wide-channel path (wide.cu): weight-streaming tcgen05 GEMMs with fused epilogues, residual_channels >= 128 -------------
 int mvn_wide_supported(const Geo& g);

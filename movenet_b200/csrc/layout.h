@@ -170,6 +170,8 @@ static inline void acts_layout(const Geo& g, ActsLayout& a) {
 }
 
 // ---- reusable workspace (byte offsets) ----------------------------------------------------------
+#define MVN_TC_PARTIAL_SLOT_BYTES ((size_t)2 * 148 * (128 * 256 + 256) * 4)
+#define MVN_TC_PARTIAL_SLOTS 6
 struct ScratchLayout {
     size_t gated;     // (B,T,C) act dtype
     size_t z;         // (B,Tn,A) fp32 : head logits, time-major ; backward: d(logits)
@@ -180,7 +182,8 @@ struct ScratchLayout {
     size_t dxa, dxb;  // (B,T,C) act dtype, ping-pong
     size_t dctx;      // (B,T,C) fp32
     size_t du2, du1, denc;
-    size_t tc_partial; // per-CTA partial weight gradients of the head / input / upsampler tensor-core kernels
+    size_t tc_partial; // per-CTA partial weight gradients of the head / input / upsampler / video tensor-core kernels: MVN_TC_PARTIAL_SLOTS
+                       // slots of MVN_TC_PARTIAL_SLOT_BYTES (one per producer: their reductions are deferred to side streams)
     size_t tc_layer_partial; // ... and of the layer backward kernel, one slot per layer (reduced together at the end)
     size_t det_ws;    // fp32 partial products of the exact-mode split reductions (added in a fixed order: no atomics)
     // wide path (wide.cu)
@@ -211,8 +214,8 @@ static inline void scratch_layout(const Geo& g, ScratchLayout& w) {
         w.du1 = take((size_t)g.B * 1600 * g.C * 4);
         w.denc = take((size_t)g.B * 160 * g.C * 4);
     } else w.dctx = w.du2 = w.du1 = w.denc = 0;
-    // slot 0: head / input / upsampler partials (used one after the other); slots 1..N: one per layer
-    w.tc_partial = take(g.adt == MVN_DTYPE_BF16 && (g.C == 64 || g.A == 64 || g.A == 128) ? (size_t)2 * 148 * (128 * 256 + 256) * 4 : 0);
+    // head | input | upsampler levels 0..2 | video encoder ; then one slot per layer
+    w.tc_partial = take(g.adt == MVN_DTYPE_BF16 && (g.C == 64 || g.A == 64 || g.A == 128) ? (size_t)MVN_TC_PARTIAL_SLOTS * MVN_TC_PARTIAL_SLOT_BYTES : 0);
     w.tc_layer_partial = take(g.adt == MVN_DTYPE_BF16 && g.C == 64 ? (size_t)g.N * 148 * (128 * 256 + 256) * 4 : 0);
     w.det_ws = take((size_t)MVN_DET_WS_FLOATS * 4);
     const bool wide = wide_ok(g);

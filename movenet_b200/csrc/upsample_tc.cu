@@ -319,7 +319,7 @@ int mvn_tc_upsample_fwd(const float* img, const void* u2_bf16, void* ctx_bf16, l
 }
 
 int mvn_tc_upsample_bwd(const float* img, const void* u2_bf16, const void* dctx_bf16, void* du2, int du_bf16, float* dwt, float* dbt,
-                        float* partial, long long rows, cudaStream_t st) {
+                        float* partial, long long rows, cudaStream_t st, int defer_reduce) {
     CUtensorMap mu, md; int rc;
     if ((rc = make_wide_map(&mu, u2_bf16, rows, 64))) return rc;
     if ((rc = make_wide_map(&md, dctx_bf16, rows, UN))) return rc;
@@ -330,7 +330,12 @@ int mvn_tc_upsample_bwd(const float* img, const void* u2_bf16, const void* dctx_
     MVN_CUDA(mvn_ensure_smem(up_bwd_tc_kernel, smem, attr));
     const int grid = a.n_tiles < 148 ? a.n_tiles : 148;
     MVN_CUDA(mvn_launch_pdl(up_bwd_tc_kernel, dim3(grid), dim3(256), (size_t)(smem), st, mu, md, a));
-    if ((rc = mvn_check_launch("upsample_bwd_tc"))) return rc;
+    if ((rc = mvn_check_launch("upsample_bwd_tc")) || defer_reduce) return rc;
+    return mvn_tc_upsample_reduce(dwt, dbt, partial, rows, st);
+}
+
+int mvn_tc_upsample_reduce(float* dwt, float* dbt, const float* partial, long long rows, cudaStream_t st) {
+    const int n_tiles = (int)((rows + TILE_T - 1) / TILE_T), grid = n_tiles < 148 ? n_tiles : 148;      // (the grid of the backward kernel)
     MVN_CUDA(mvn_launch_pdl(up_reduce_kernel, dim3((UPART + 31) / 32), dim3(32, RED_SPLIT), (size_t)(0), st, partial, grid, dwt, dbt));
     return mvn_check_launch("upsample_reduce");
 }

@@ -182,14 +182,20 @@ int mvn_tc_video_fwd(const float* video, const float* wv, const float* bv, float
     return mvn_check_launch("video_fwd_reduce");
 }
 
-int mvn_tc_video_bwd(const float* video, const float* denc, float* part, float* dwv, float* dbv, int rows, int K, cudaStream_t st) {
+int mvn_tc_video_reduce(const float* denc, const float* part, float* dwv, float* dbv, int rows, int K, cudaStream_t st) {
+    MVN_CUDA(mvn_launch_pdl(video_bwd_reduce_kernel, dim3(2 * mvn_sm_count(), 2), dim3(256), (size_t)0, st, part, denc, dwv,
+                            dbv, rows, K, video_row_splits(rows)));
+    return mvn_check_launch("video_bwd_reduce");
+}
+
+int mvn_tc_video_bwd(const float* video, const float* denc, float* part, float* dwv, float* dbv, int rows, int K, cudaStream_t st,
+                     int defer_reduce) {
     VcArgs a; a.video = video; a.other = denc; a.part = part; a.rows = rows; a.K = K; a.m_tiles = (rows + TILE_T - 1) / TILE_T;
     const int ns = video_row_splits(rows);
     static MvnSmemAttr attr;
     MVN_CUDA(mvn_ensure_smem(video_conv_tc_kernel<true>, V_SMEM, attr));
     MVN_CUDA(mvn_launch_pdl(video_conv_tc_kernel<true>, dim3(K / VK, ns), dim3(V_THREADS), (size_t)V_SMEM, st, a));
-    int rc = mvn_check_launch("video_wgrad_tc"); if (rc) return rc;
-    MVN_CUDA(mvn_launch_pdl(video_bwd_reduce_kernel, dim3(2 * mvn_sm_count(), 2), dim3(256), (size_t)0, st, (const float*)part, denc, dwv,
-                            dbv, rows, K, ns));
-    return mvn_check_launch("video_bwd_reduce");
+    int rc = mvn_check_launch("video_wgrad_tc");
+    if (rc || defer_reduce) return rc;
+    return mvn_tc_video_reduce(denc, part, dwv, dbv, rows, K, st);
 }

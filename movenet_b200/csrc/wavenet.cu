@@ -441,6 +441,10 @@ static TnSrc make_tn(const void* ptr, int dtype, int ld, int K, int T, int shift
 struct Ctx {
     Geo g; PackedLayout P; ActsLayout AL; ScratchLayout SL;
     const float* packed; char* acts; char* scratch; cudaStream_t st;
+    // backward, tensor-core path: the small fixed-order reductions of the per-CTA partials are deferred (launched on side streams
+    // at two points of the pass instead of between the persistent kernels); which ones are pending
+    mutable int defer = 0, pend_head = 0, pend_input = 0, pend_up = 0, pend_video = 0;
+    float* tc_part(int slot) const { return (float*)(scratch + SL.tc_partial + (size_t)slot * MVN_TC_PARTIAL_SLOT_BYTES); }
     const float* lw(int l) const { return packed + P.layer0 + (size_t)l * P.layer_stride; }
     void* x(int l) const { return acts + AL.x0 + (size_t)l * AL.x_stride; }
     float* det_ws() const { return scratch ? (float*)(scratch + SL.det_ws) : nullptr; }
@@ -713,7 +717,10 @@ static int head_bwd(const Ctx& c, const float* out, const float* dout, const lon
     MVN_CUDA(cudaMemsetAsync(dskip, 0, (size_t)g.B * g.Tout * g.S * 4, c.st));
     if (g.Tn <= 0) return 0;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S))
-        return mvn_tc_head_bwd(c.packed, c.P, g, skip, out, dout, target, grad_loss, dskip, pg, (float*)(c.scratch + c.SL.tc_partial), c.st);
+    {
+        c.pend_head = c.defer;
+        return mvn_tc_head_bwd(c.packed, c.P, g, skip, out, dout, target, grad_loss, dskip, pg, c.tc_part(0), c.st, c.defer);
+    }
     if (mvn_wide_head_supported(g)) {
         const size_t half = (size_t)g.B * g.Tout * g.A * 2;
         return mvn_wide_head_bwd(c.packed, c.P, g, skip, 0, a1, out, dout, target, grad_loss, c.scratch + c.SL.z, c.scratch + c.SL.da1,
@@ -878,7 +885,8 @@ static int video_bwd(const Ctx& c, const float* video, const void* dctx, int dct
             const void* in16 = i == 0 ? (const void*)((const char*)u1 + (size_t)g.B * 1600 * C * 2) : (const void*)in[i];
             const float* img = c.packed + (i == 2 ? c.P.tc_up : c.P.tc_up01[i]);
             if ((rc = mvn_tc_upsample_bwd(img, in16, dout[i], din[i], i > 0, pg + c.P.wt[i], pg + c.P.bt[i],
-                                          (float*)(c.scratch + c.SL.tc_partial), rows, c.st))) return rc;
+                                          c.tc_part(2 + i), rows, c.st, c.defer))) return rc;
+            if (c.defer) c.pend_up |= 1 << i;
             continue;
         }
         TnGemmArgs t; memset(&t, 0, sizeof(t));
@@ -893,8 +901,10 @@ static int video_bwd(const Ctx& c, const float* video, const void* dctx, int dct
         if ((rc = row_gemm(c, a))) return rc;
     }
     const int rows = g.B * 160, K = 4096 * g.Cin;
-    if (tc && mvn_tc_video_supported(C, K) && mvn_tc_video_partial_floats(rows, K) * 4 <= (size_t)2 * 148 * (128 * 256 + 256) * 4)
-        return mvn_tc_video_bwd(video, denc, (float*)(c.scratch + c.SL.tc_partial), pg + c.P.wv, pg + c.P.bv, rows, K, c.st);
+    if (tc && mvn_tc_video_supported(C, K) && mvn_tc_video_partial_floats(rows, K) * 4 <= MVN_TC_PARTIAL_SLOT_BYTES) {
+        c.pend_video = c.defer;
+        return mvn_tc_video_bwd(video, denc, c.tc_part(5), pg + c.P.wv, pg + c.P.bv, rows, K, c.st, c.defer);
+    }
     TnGemmArgs t; memset(&t, 0, sizeof(t));
     t.rows = rows; t.Trow = rows; t.N = C; t.nsrc = 1;
     t.src[0] = make_tn(video, MVN_F32, K, K, rows, 0, 0, pg + c.P.wv, C);
@@ -986,8 +996,9 @@ static int backward_impl(const mvn_shape_t* s, const void* packed, const float* 
         return mvn_wide_input_bwd(audio, (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), dx_next,
                                   c.scratch + c.SL.w_oh16, pg, c.P, g, c.st);
     }
-    if ((rc = head_bwd(c, out, dout, target, grad_loss, pg))) return rc;
     const bool tc_layers = g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video);
+    c.defer = tc_layers && mvn_side_stream(0) != nullptr;
+    if ((rc = head_bwd(c, out, dout, target, grad_loss, pg))) return rc;
     if (g.video && !tc_layers) MVN_CUDA(cudaMemsetAsync(c.scratch + c.SL.dctx, 0, (size_t)g.B * g.T * g.C * 4, c.st));
     const void* dctx_final = c.scratch + c.SL.dctx; int dctx_dtype = MVN_F32;
     if (tc_layers) {
@@ -1020,10 +1031,16 @@ static int backward_impl(const mvn_shape_t* s, const void* packed, const float* 
             }
             cur ^= 1; pair = !sum_out;
         }
-        if ((rc = mvn_tc_bwd_reduce_all((const float*)(c.scratch + c.SL.tc_layer_partial), pg, c.P, g, c.st))) return rc;
+        // the layers' partials (176 MB at cfg01: a 29 us reduction) and the head's are reduced on a side stream, under the input /
+        // upsampler / video kernels that follow
+        cudaStream_t red0 = c.defer ? mvn_side_stream(0) : c.st;
+        if ((rc = mvn_stream_after(red0, c.st))) return rc;
+        if (c.pend_head) { if ((rc = mvn_tc_head_reduce(c.P, g, pg, c.tc_part(0), red0))) return rc; c.pend_head = 0; }
+        if ((rc = mvn_tc_bwd_reduce_all((const float*)(c.scratch + c.SL.tc_layer_partial), pg, c.P, g, red0))) return rc;
         if (mvn_tc_input_supported(g.A, g.C)) {
+            c.pend_input = c.defer;
             if ((rc = mvn_tc_input_bwd(audio, (const int*)(c.acts + c.AL.codes), (const unsigned char*)(c.acts + c.AL.dense), Pb[cur],
-                                       pair ? Ub[cur] : nullptr, pg + c.P.win, (float*)(c.scratch + c.SL.tc_partial), g, c.st))) return rc;
+                                       pair ? Ub[cur] : nullptr, pg + c.P.win, c.tc_part(1), g, c.st, c.defer))) return rc;
         } else if ((rc = input_bwd(c, audio, Pb[cur], pair ? Ub[cur] : nullptr, pair ? g.dil[0] : 0, pg))) return rc;
         dctx_final = Qb[qcur]; dctx_dtype = MVN_BF16;
     } else {
@@ -1036,5 +1053,21 @@ static int backward_impl(const mvn_shape_t* s, const void* packed, const float* 
         if ((rc = input_bwd(c, audio, dx_next, nullptr, 0, pg))) return rc;
     }
     if (g.video && (rc = video_bwd(c, video, dctx_final, dctx_dtype, pg))) return rc;
+    if (c.defer) {
+        // every producer has run: the remaining small reductions side by side (three streams), then the caller's stream waits
+        cudaStream_t red0 = mvn_side_stream(0), red1 = mvn_side_stream(1), red2 = mvn_side_stream(2);
+        if (c.pend_head) { if ((rc = mvn_stream_after(red0, c.st)) || (rc = mvn_tc_head_reduce(c.P, g, pg, c.tc_part(0), red0))) return rc; }
+        if (c.pend_input) { if ((rc = mvn_stream_after(red1, c.st)) || (rc = mvn_tc_input_reduce(pg + c.P.win, c.tc_part(1), g, red1))) return rc; }
+        if (c.pend_up) {
+            const int len[3] = {160, 1600, 16000};
+            if ((rc = mvn_stream_after(red2, c.st))) return rc;
+            for (int i = 2; i >= 0; --i)
+                if ((c.pend_up >> i) & 1)
+                    if ((rc = mvn_tc_upsample_reduce(pg + c.P.wt[i], pg + c.P.bt[i], c.tc_part(2 + i), (long long)g.B * len[i], red2))) return rc;
+        }
+        if (c.pend_video)
+            if ((rc = mvn_tc_video_reduce((const float*)(c.scratch + c.SL.denc), c.tc_part(5), pg + c.P.wv, pg + c.P.bv, g.B * 160, 4096 * g.Cin, c.st))) return rc;
+        if ((rc = mvn_stream_after(c.st, red0)) || (rc = mvn_stream_after(c.st, red1)) || (rc = mvn_stream_after(c.st, red2))) return rc;
+    }
     return 0;
 }
