@@ -188,15 +188,21 @@ extern "C" int mvn_pack_weights(const mvn_shape_t* s, const void* const* param_p
     PackedLayout P; packed_layout(g, P);
     cudaStream_t st = (cudaStream_t)stream;
     const float* const* ptrs = (const float* const*)param_ptrs_dev;
+    // Seven small latency-bound kernels: the independent ones run side by side -- the per-layer re-layout and the tensor-core
+    // layer images (both read only the parameters) on two side streams, the chain pack_misc -> head image -> upsampler images
+    // (each reads what the one before wrote) on the caller's stream; the caller's stream then waits for the side streams.
+    cudaStream_t s0 = mvn_side_stream(0), s1 = mvn_side_stream(1);
+    if (!s0 || !s1) s0 = s1 = st;
+    int rc;
+    if ((rc = mvn_stream_after(s0, st)) || (rc = mvn_stream_after(s1, st))) return rc;
     dim3 gl(8, g.N);
-    MVN_CUDA(mvn_launch_pdl(pack_layer_kernel, dim3(gl), dim3(256), (size_t)(0), st, ptrs, (float*)packed, P, g.C, g.Cl, g.S, g.Kz, g.video, (int)mvn_wide_supported(g)));
+    MVN_CUDA(mvn_launch_pdl(pack_layer_kernel, dim3(gl), dim3(256), (size_t)(0), s0, ptrs, (float*)packed, P, g.C, g.Cl, g.S, g.Kz, g.video, (int)mvn_wide_supported(g)));
     dim3 gm(128, 6);
     MVN_CUDA(mvn_launch_pdl(pack_misc_kernel, dim3(gm), dim3(256), (size_t)(0), st, ptrs, (float*)packed, P, g.A, g.C, g.Cl, g.S, g.Cin, g.N, g.video));
-    int rc = mvn_check_launch("pack_weights");
-    if (rc) return rc;
+    if ((rc = mvn_check_launch("pack_weights"))) return rc;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_layer_supported(g.C, g.S, g.video))
-        if ((rc = mvn_tc_pack(ptrs, (float*)packed, P, g, st))) return rc;
-    if (mvn_wide_head_supported(g) && (rc = mvn_wide_pack(ptrs, (float*)packed, P, g, st))) return rc;
+        if ((rc = mvn_tc_pack(ptrs, (float*)packed, P, g, s1))) return rc;
+    if (mvn_wide_head_supported(g) && (rc = mvn_wide_pack(ptrs, (float*)packed, P, g, s1))) return rc;
     if (g.adt == MVN_DTYPE_BF16 && mvn_tc_head_supported(g.A, g.S))   // conv2.weight is (A, A, 1): already [n][k]
         if ((rc = mvn_tc_head_pack((const float*)packed + P.w2pT, (float*)packed, P, g.A, st))) return rc;
     if (g.adt == MVN_DTYPE_BF16 && g.video && mvn_tc_upsample_supported(g.C))
@@ -205,6 +211,7 @@ extern "C" int mvn_pack_weights(const mvn_shape_t* s, const void* const* param_p
         for (int i = 0; i < 2; ++i)
             if ((rc = mvn_tc_upsample_pack((const float*)packed + P.wt[i], (const float*)packed + P.bt[i], (float*)packed + P.tc_up01[i], st))) return rc;
     }
+    if ((rc = mvn_stream_after(st, s0)) || (rc = mvn_stream_after(st, s1))) return rc;
     return 0;
 }
 
