@@ -268,8 +268,12 @@ def layer_roofline(model, audio, video, dtype):
     # read and one more write of C*e bytes: `design_bytes_per_sample`); MOVENET_B200_BWD_SUM=1 selects the one-stream variant
     # (same algorithmic bytes, measured slower: DESIGN.md section 3).
     summed = bool(int(os.environ.get("MOVENET_B200_BWD_SUM", "0"))) and max(model.residual_conv_stack.dilations) <= 128
+    # the double-buffered kernel (layer_tc_bwd_db.cu: every layer of this model when all dilations are <= 8) does not read Q:
+    # its contribution is added in place by a TMA reduction
+    dbuf = (not summed and os.environ.get("MOVENET_B200_BWD_DB", "1") != "0" and max(model.residual_conv_stack.dilations) <= 8
+            and S <= 32)
     bwd_b = 3 * Cc * e + 4 * S + (3 * Cc * e if vid else 0)
-    bwd_design = bwd_b + (0 if summed else 2 * Cc * e)
+    bwd_design = bwd_b + (0 if summed else 2 * Cc * e) - (Cc * e if (dbuf and vid) else 0)
     pk = peaks()
     n = B * T_CLIP
 
@@ -277,13 +281,14 @@ def layer_roofline(model, audio, video, dtype):
         ach = per_sample * n / (ms * 1e-3) / 1e9
         extra = {} if design is None else {"design_bytes_per_sample": design,
                                            "design_gbs": design * n / (ms * 1e-3) / 1e9,
-                                           "stream_gradient": "one summed stream" if design == per_sample else "pair (P, U)"}
+                                           "stream_gradient": "one summed stream" if summed else "pair (P, U)"}
         return {**extra, "bound": "hbm", "kernel": "%s (%s, %d launch(es) per layer)" % (name, dtype, round(launches)),
                 "achieved": ach, "peak": pk["hbm_gbs"], "peak_source": pk["source"], "unit": "GB/s",
                 "frac": ach / pk["hbm_gbs"], "traffic": _ncu_traffic(kernel), "ms_per_launch": ms,
                 "bytes_per_sample": per_sample, "samples_per_launch": n}
 
-    return (obj("residual layer backward", ms_b, bwd_b, n_b, "layer_bwd_tc_kernel<1, 0>" if summed else "layer_bwd_tc_kernel<0, 1>", bwd_design),
+    bwd_kernel = "layer_bwd_tc_kernel<1, 0>" if summed else ("layer_bwd_db_kernel<1>" if dbuf else "layer_bwd_tc_kernel<0, 1>")
+    return (obj("residual layer backward: %s" % bwd_kernel.split("<")[0], ms_b, bwd_b, n_b, bwd_kernel, bwd_design),
             obj("residual layer forward", ms_f, fwd_b, n_f, "layer_fwd_tc_kernel"))
 
 
