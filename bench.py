@@ -251,16 +251,18 @@ def layer_roofline(model, audio, video, dtype):
         n = B * T_CLIP
         f_fwd = 10 * Cc * Cc + 2 * Cc * S
 
-        def tobj(name, ms, flops, launches, kernels):
+        def tobj(name, ms, flops, launches, kernels, traffic_of):
             ach = flops * n / (ms * 1e-3) / 1e12
             return {"bound": "tensor", "kernel": "%s (%s, %d launches per layer: %s)" % (name, dtype, round(launches), kernels),
                     "achieved": ach, "peak": pk["bf16_tflops"], "peak_source": pk["source"] + " (cuBLAS bf16, sustained)",
-                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": _ncu_traffic("wide_gemm_kernel"),
+                    "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": _ncu_traffic(traffic_of), "traffic_kernel": traffic_of,
                     "ms_per_launch": ms, "flops_per_sample": flops, "samples_per_launch": n}
         return (tobj("residual layer backward", ms_b, 2 * f_fwd, n_b,
-                     "2 wide_gemm_kernel (d(gated) x kept gate-derivative factors -> dz; d(x) + bias column sums) + wide_wgrad_kernel (K = time weight gradients) + its reduction"),
+                     "2 wide_gemm_kernel (d(gated) x kept gate-derivative factors -> dz; d(x) + bias column sums) + wide_wgrad_kernel (K = time weight gradients) + its reduction",
+                     "wide_gemm_kernel<2, 4>"),
                 # (the skip 1x1 convs of all layers run as ONE GEMM after the stack: their 2 C S flops are not in this stage)
-                tobj("residual layer forward", ms_f, 10 * Cc * Cc, n_f, "2 wide_gemm_kernel (gate + derivative factors kept for the backward; residual)"))
+                tobj("residual layer forward", ms_f, 10 * Cc * Cc, n_f, "2 wide_gemm_kernel (gate + derivative factors kept for the backward; residual)",
+                     "wide_gemm_kernel<2, 0>"))
     # algorithmic bytes per audio sample of one layer
     fwd_b = Cc * e + Cc * e + (Cc * e if vid else 0) + 8 * S                 # read x, write x', read ctx, RMW skip_sum
     # backward, algorithmic bytes of any layer-at-a-time backward: read x, the stream gradient D, d(skip) (+ ctx and the
