@@ -662,7 +662,8 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
     a.zero_in = p_in == nullptr; a.pair_in = u_in != nullptr; a.sum_out = sum_out;
     a.nchunks = g.video ? 3 : 2;
     a.tiles_per_clip = (g.T + TILE_T - 1) / TILE_T; a.n_tiles = a.tiles_per_clip * g.B;
-    const int smem = bwd_smem_total(a.nchunks, a.N2) + 1024;
+    // (the carry rows behind the barriers exist only for the summed output with video)
+    const int smem = bwd_smem_total(a.nchunks, a.N2) - ((a.nchunks == 3 && !sum_out) ? CARRY_VIDEO_ROWS * 128 : 0) + 1024;
     MVN_REQUIRE(smem <= 227 * 1024, "tensor-core backward kernel: shared memory budget exceeded (%d)", smem);
     static MvnSmemAttr attr_a, attr_b, attr_c;
     MVN_CUDA(mvn_ensure_smem(layer_bwd_tc_kernel<false, false>, smem, attr_a));
@@ -702,6 +703,7 @@ int mvn_tc_layer_bwd(const void* x_in, const void* ctx, const void* p_in, const 
 int mvn_tc_bwd_sum_out(const Geo& g, int layer) {
     const char* sum = getenv("MOVENET_B200_BWD_SUM");      // read per call: the tests switch it
     if (!sum || !atoi(sum)) return 0;
+    if (bwd_smem_total(g.video ? 3 : 2, ((g.C + g.S + 15) / 16) * 16) + 1024 > 227 * 1024) return 0;   // (video with 32 skip channels: no room for the carry)
     int above = 1;                                   // the top layer's input is zero
     for (int l = g.N - 1; l >= layer; --l) {
         const int s = g.dil[l] <= (g.video ? CARRY_VIDEO_ROWS : TILE_T) && above;   // (the U tile is the staging tile: no pair input)

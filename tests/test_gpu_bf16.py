@@ -336,6 +336,34 @@ def test_backward_gradient_stream_modes(video, layer_size, monkeypatch):
     assert F.cosine_similarity(a, c, dim=0).item() >= 0.999
 
 
+@pytest.mark.parametrize("video,skip_channels,B,T", [(True, 16, 1, 160000), (True, 32, 2, 160000), (False, 32, 3, 20000 + 13),
+                                                       (False, 16, 5, 3000)])
+def test_double_buffered_backward_with_wider_skip(video, skip_channels, B, T, monkeypatch):
+    """layer_tc_bwd_db.cu with skip_channels > 8 (the d(skip) tile then holds [ones | 16 or 32 skip channels], G2 takes two K
+    steps from it and the skip rows of the weight-gradient block move), several clips per CTA (clip boundaries inside a CTA's
+    tile sequence: the two-tap box zero-fills rows before a clip's start) and fewer tiles than CTAs: against the exact fp32 mode
+    and against the single-buffer kernel on the same step."""
+    torch.manual_seed(5)
+    kw = dict(layer_size=4, stack_size=2, input_channels=64, residual_channels=64, skip_channels=skip_channels)
+    m32 = movenet_b200.WaveNet(**kw, compute_dtype="fp32").cuda()
+    m16 = movenet_b200.WaveNet(**kw, compute_dtype="bf16").cuda()
+    m16.load_state_dict(m32.state_dict())
+    codes = torch.randint(0, 64, (B, T), device="cuda")
+    audio = movenet_b200.one_hot(codes, 64)
+    vid = torch.randint(0, 256, (B, 160, 64, 64, 1), device="cuda").float() if video else None
+    target = codes[:, m32.receptive_fields:]
+    ref = _grads_of(m32, audio, vid, target)
+    got = _grads_of(m16, audio, vid, target)
+    monkeypatch.setenv("MOVENET_B200_BWD_DB", "0")
+    single = _grads_of(m16, audio, vid, target)
+    assert ref.keys() == got.keys() == single.keys()
+    for k in ref:
+        assert rel_l2(got[k], ref[k]) < GRAD_RTOL, (k, rel_l2(got[k], ref[k]))
+        assert rel_l2(got[k], single[k]) < 0.02, (k, "double vs single buffer", rel_l2(got[k], single[k]))
+    a, b = (torch.cat([g[k].flatten() for k in ref]) for g in (got, ref))
+    assert F.cosine_similarity(a, b, dim=0).item() >= GRAD_COS
+
+
 def test_tensor_core_decoder_sampling_is_seeded_and_valid():
     """temperature > 0 in the throughput decoder: tokens are valid codes, identical clips with the same seed draw
     per-clip streams (clip index enters the counter), the same torch seed reproduces them."""
