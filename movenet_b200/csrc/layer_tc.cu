@@ -145,11 +145,15 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const int b = tile / a.tiles_per_clip, t0 = (tile - b * a.tiles_per_clip) * TILE_T;
         if (warp_u == 0) {
           if (issuer) {
+            // (the tap t - d and ctx tiles of this tile were requested as soon as the previous tile's out GEMM had released them,
+            // see below; only the first tile of the CTA asks for everything here)
+            if (it == 1) {
+                mbar_expect_tx(full_bar, load_bytes);
+                tma_load_3d(sA0, &map_x, full_bar, 0, t0 - a.dil, b);
+                if (a.nchunks == 3) tma_load_3d(sA2, &map_ctx, full_bar, 0, t0, b);
+            }
             tma_wait_read0();        // the previous tile's x' store must be done reading A1
-            mbar_expect_tx(full_bar, load_bytes);
-            tma_load_3d(sA0, &map_x, full_bar, 0, t0 - a.dil, b);
             tma_load_3d(sA1, &map_x, full_bar, 0, t0, b);
-            if (a.nchunks == 3) tma_load_3d(sA2, &map_ctx, full_bar, 0, t0, b);
             const int nt = tile + gridDim.x;       // this CTA's next tile: start pulling it into L2 now
             if (nt < a.n_tiles) {
                 const int nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
@@ -231,6 +235,17 @@ layer_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
         mbar_wait(mma_bar, 1);
         tc_fence_after();
+        // the out GEMM was the last reader of the gated tile (A0), the gate GEMM of the ctx tile (A2): the next tile's copies are
+        // requested now, an epilogue and a store drain before the loop top could do it (A1 follows there, once x' has left it)
+        if (issuer) {
+            const int nt = tile + gridDim.x;
+            if (nt < a.n_tiles) {
+                const int nb = nt / a.tiles_per_clip, n0 = (nt - nb * a.tiles_per_clip) * TILE_T;
+                mbar_expect_tx(full_bar, load_bytes);
+                tma_load_3d(sA0, &map_x, full_bar, 0, n0 - a.dil, nb);
+                if (a.nchunks == 3) tma_load_3d(sA2, &map_ctx, full_bar, 0, n0, nb);
+            }
+        }
         // ---- epilogue 2: residual in place in the tap-1 tile; skip accumulation ------------------
         if (a.has_out) {
             uint32_t rr[32];
