@@ -170,6 +170,13 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 4 : 1) head_fwd_tc_kernel(con
         const bool live = j < a.Tn;
         CLK(0, 0);
         if (part == 0) {             // one thread per row builds the skip tile
+            {   // this CTA's next tile: its skip rows towards L2 now (they are the head of that tile's dependency chain)
+                const int nt = tile + gridDim.x;
+                if (nt < a.n_tiles) {
+                    const int nb = nt / a.tiles_per_clip, nj = (nt - nb * a.tiles_per_clip) * TILE_T + r;
+                    if (nj < a.Tn) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.skip + ((size_t)nb * a.Tout + nj) * S));
+                }
+            }
             float ls[S];
             const float* src = a.skip + ((size_t)b * a.Tout + (live ? j : 0)) * S;
 #pragma unroll
@@ -352,6 +359,8 @@ __global__ void __launch_bounds__(A * 4, A == 64 ? 2 : 1) head_bwd_tc_kernel(con
             const int nt = tile + gridDim.x;
             if (nt < a.n_tiles) {
                 const int nb = nt / a.tiles_per_clip, nj = (nt - nb * a.tiles_per_clip) * TILE_T + (r & ~31);
+                if (part == 0 && nj + (tid & 31) < a.Tn)       // ... and its skip rows (one 32 S-byte row per thread of the first group)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.skip + ((size_t)nb * a.Tout + nj + (tid & 31)) * S));
                 if (nj < a.Tn) {
                     const size_t o = ((size_t)nb * A + n0 + (tid & 31)) * a.Tn + nj;
                     // (Tn is not a multiple of 32: the 32 time steps straddle two 128-byte lines)
