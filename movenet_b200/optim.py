@@ -32,6 +32,10 @@ class AdamW(torch.optim.Optimizer):
         cached = self._tables.get(key_id)
         if cached is not None and cached[0] == key:
             return cached
+        for p in active:          # (checked when a table is built: the same tensors at the same addresses were checked before)
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()
+                    and p.grad.dtype == torch.float32 and not p.grad.is_sparse):
+                raise RuntimeError("movenet_b200.optim.AdamW: contiguous CUDA fp32 parameters and gradients only")
         dev = active[0].device
         chunk = _lib.load().mvn_adamw_chunk_elems()
         assert _lib.load().mvn_adamw_segment_bytes() == 40
@@ -58,9 +62,6 @@ class AdamW(torch.optim.Optimizer):
             if not active:
                 continue
             for p in active:
-                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()
-                        and p.grad.dtype == torch.float32 and not p.grad.is_sparse):
-                    raise RuntimeError("movenet_b200.optim.AdamW: contiguous CUDA fp32 parameters and gradients only")
                 st = self.state[p]
                 if "exp_avg" not in st:
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)

@@ -174,6 +174,7 @@ class WaveNet(nn.Module):
         self._dp_group = None
         self._dp_world = 1
         self._dp_peer = {}
+        self._flat_in_pass = set()
         self._weights_epoch = 0      # bumped by anything that rewrites parameters behind autograd's back (see _pack)
 
     # ------------------------------------------------------------------ reference surface
@@ -421,15 +422,9 @@ class WaveNet(nn.Module):
                 offsets.append(-1)
             else:
                 offsets.append(off)
-                off += (p.numel() + 3) // 4 * 4
-        # split plan: consecutive chunks of the flat buffer = [grad, pad, grad, pad, ...]
-        sizes, shapes = [], []
-        for o, p in zip(offsets, self._param_list()):
-            if o >= 0:
-                n = p.numel()
-                sizes += [n, (n + 3) // 4 * 4 - n]
-                shapes.append(p.shape)
-        cache[has_video] = (offsets, off, sizes, shapes)
+                off += p.numel()           # dense, no padding: the views come from ONE unflatten call (host time, see _flat_grads)
+        with_grad = [p for o, p in zip(offsets, self._param_list()) if o >= 0]
+        cache[has_video] = (offsets, off, with_grad)
         return offsets, off
 
     def _grad_offsets(self, has_video, device):
@@ -440,17 +435,32 @@ class WaveNet(nn.Module):
         return self._ptr_tables[key]
 
     def _flat_grads(self, has_video, device):
-        """a fresh flat fp32 buffer and, per parameter, the view of it that becomes param.grad (None: no gradient)"""
+        """the flat fp32 gradient buffer and, per parameter, a FRESH view of it that becomes param.grad (None: no gradient).
+
+        Host time matters here (103 parameters; eight trainer processes share one host): the views are made by one
+        ``unflatten_dense_tensors`` call, and the buffer itself is REUSED from step to step as long as every parameter's
+        ``.grad`` is None when the backward runs (``zero_grad(set_to_none=True)``, torch's default) -- so the gradient pointers
+        stay the same and ``movenet_b200.optim.AdamW`` keeps its device tables (like DDP's ``gradient_as_bucket_view``: a
+        gradient tensor the caller kept from an earlier step is overwritten).  Otherwise (gradient accumulation over several
+        backward passes) every pass gets a new buffer."""
         offsets, total = self._grad_layout(has_video)
-        _, _, sizes, shapes = self._grad_cache[has_video]
-        flat = torch.empty(total, dtype=torch.float32, device=device)
-        chunks = flat.split_with_sizes(sizes)[0::2]
-        it = iter(zip(chunks, shapes))
-        views = []
-        for o in offsets:
-            if o < 0:
-                views.append(None)
-            else:
-                c, shp = next(it)
-                views.append(c.view(shp))
+        with_grad = self._grad_cache[has_video][2]
+        key = ("flat", has_video, str(device))
+        flat = self._ptr_tables.get(key)
+        # reusable: nothing aliases the kept buffer any more -- no parameter holds a gradient, and it has not already been handed
+        # out in THIS backward pass (several loss terms / forward passes in one backward: their gradients are still on their way
+        # to .grad; the flag is cleared by an engine callback when the pass is over)
+        reusable = key not in self._flat_in_pass and all(p.grad is None for p in with_grad)
+        if flat is None or not reusable:
+            flat = torch.empty(total, dtype=torch.float32, device=device)
+            if reusable:
+                self._ptr_tables[key] = flat
+        if reusable:
+            self._flat_in_pass.add(key)
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(lambda: self._flat_in_pass.discard(key))
+            except RuntimeError:          # not inside a backward pass (a direct call): nothing to wait for
+                self._flat_in_pass.discard(key)
+        it = iter(torch._C._nn.unflatten_dense_tensors(flat, with_grad))
+        views = [None if o < 0 else next(it) for o in offsets]
         return flat, views
