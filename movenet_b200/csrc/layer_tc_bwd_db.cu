@@ -12,9 +12,13 @@
 //    layer, whose incoming sum is zero, stores instead.  One tile of shared memory and one load per tile less;
 //  * the gate-bias sums ride in the weight gradient: the ctx block of its B operand is followed (block stride = the distance to
 //    the d(skip) tile) by 16 columns of ones that live in the d(skip) tile's unused channels, so W1 = [dz^T x(t-d) | dz^T x(t)]
-//    (N = 128) + [dz^T ctx | dz^T 1] (N = 80) and the eight N = 16 MMAs that re-read the whole dz operand are gone.
-//
+//    (N = 128) + [dz^T ctx | dz^T 1] (N = 80) and the eight N = 16 MMAs that re-read the whole dz operand are gone;
 //  * the residual / skip bias sums ride in W2 the same way ([gated | ones], N = 80): no N = 16 MMA is left in the kernel.
+//
+// The buffer alone bought nothing; the order in which the one service warp issues its work did (profiles/r02_bwd_db.md, measured
+// with the phase clocks below): the add-reduction goes LAST (it occupies the TMA unit ~10x longer than a store and must not sit in
+// front of the next tile's P / U loads), the next tile's G1 is issued the moment W2 has left the in-order tensor pipe but AFTER the
+// P' / U' stores, G2 is committed after wait_group.read 1 (the stores, not the reduction).  130.2 -> 114.7 us per launch at cfg01.
 //
 // Shared memory: weight image | set 0 | set 1 | G | U | P | DSK | DZ0 | DZ1 | barriers, set = x box (17 KB) + ctx tile.
 #include <cstdio>
