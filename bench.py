@@ -77,7 +77,7 @@ def synth_codes(B, T, A, seed, device):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region"""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -85,6 +85,11 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.enabled = enabled        # rank 0 only: one NVML client per GPU polling during a 50 ms timed region disturbs the launches
+        self.t0 = None                # samples before mark() (NVML start-up, warm-up) are not "under load" and are dropped
+
+    def mark(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
 
     def start(self):
         if not self.enabled:
@@ -102,11 +107,18 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         out, _ = self.proc.communicate()
+        import datetime
         sm, mx, reasons = [], None, set()
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
+            if self.t0 is not None:
+                try:          # "2026/10/19 03:12:45.123" (local time, like datetime.now()); an unparsable stamp keeps the sample
+                    if datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f") < self.t0:
+                        continue
+                except ValueError:
+                    pass
             try:
                 sm.append(float(f[1])); mx = float(f[2])
             except ValueError:
@@ -527,6 +539,7 @@ def run_ours(args):
         train_step(model, opt, audio, video)
     sync()
     n0 = _lib.load().mvn_launch_count()
+    sampler.mark()            # clocks are reported from here on: the timed device-resident and end-to-end legs
     ms_total = timed(lambda: train_step(model, opt, audio, video), args.steps, 0, sync)
     launches = int(_lib.load().mvn_launch_count() - n0)
     ms_total = max_over_ranks(ms_total)
