@@ -168,3 +168,45 @@ def test_movenet_import_shim_resolves_to_this_package():
             "and VIDEO_KERNEL_SIZE == (1, 64, 64); print('ok')") % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/")
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr
+
+
+def test_flat_gradient_buffer_is_reused_only_when_nothing_aliases_it():
+    """WaveNet._flat_grads (host-time optimisation): the flat gradient buffer keeps its address from step to step while no
+    parameter holds a gradient; a parameter that still holds one (gradient accumulation), or a second hand-out inside the SAME
+    backward pass (several loss terms), gets a fresh buffer."""
+    import torch
+    m = movenet_b200.WaveNet(2, 1, 8, 8, 8)
+    dev = torch.device("cpu")
+    flat1, views1 = m._flat_grads(False, dev)
+    offsets, total = m._grad_layout(False)
+    assert flat1.numel() == total == sum(p.numel() for o, p in zip(offsets, m.parameters()) if o >= 0)
+    for o, p, v in zip(offsets, m.parameters(), views1):
+        assert (v is None) == (o < 0)
+        if v is not None:
+            assert v.shape == p.shape and v.data_ptr() == flat1.data_ptr() + 4 * o
+    flat2, views2 = m._flat_grads(False, dev)
+    assert flat2.data_ptr() == flat1.data_ptr() and all(a is not b for a, b in zip(views1, views2) if a is not None)   # same buffer, fresh views
+    held = next(p for o, p in zip(offsets, m.parameters()) if o >= 0)
+    held.grad = views2[[i for i, o in enumerate(offsets) if o >= 0][0]]
+    flat3, _ = m._flat_grads(False, dev)
+    assert flat3.data_ptr() != flat1.data_ptr()            # a parameter still holds a gradient: accumulate into a new buffer
+    held.grad = None
+    assert m._flat_grads(False, dev)[0].data_ptr() == flat1.data_ptr()
+
+    seen = []
+
+    class TwoHandOuts(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            return x * 2
+
+        @staticmethod
+        def backward(ctx, g):
+            seen.append(m._flat_grads(False, dev)[0].data_ptr())
+            seen.append(m._flat_grads(False, dev)[0].data_ptr())
+            return g * 2
+
+    x = torch.ones(3, requires_grad=True)
+    TwoHandOuts.apply(x).sum().backward()
+    assert seen[0] == flat1.data_ptr() and seen[1] != seen[0]          # the second hand-out of one pass must not alias the first
+    assert m._flat_grads(False, dev)[0].data_ptr() == flat1.data_ptr()  # the pass is over: reusable again
